@@ -1,0 +1,21 @@
+# Builds libgpz_b200.so (sm_100a only) and nothing else.  `python -c "import __graft_entry__ as g; g.build()"` calls this.
+NVCC ?= nvcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xptxas -v
+SRC := $(wildcard gpz_b200/csrc/*.cu)
+HDR := $(wildcard gpz_b200/csrc/*.cuh) include/gpz_b200.h
+OBJ := $(patsubst gpz_b200/csrc/%.cu,build/%.o,$(SRC))
+LIB := gpz_b200/libgpz_b200.so
+
+all: $(LIB)
+
+build/%.o: gpz_b200/csrc/%.cu $(HDR)
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; false)
+
+$(LIB): $(OBJ)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -ldl
+
+clean:
+	rm -rf build $(LIB)
+.PHONY: all clean

@@ -1,0 +1,1381 @@
+// C ABI of libgpz_b200 (include/gpz_b200.h): dataset context, the two-sweep NLML+gradient
+// evaluation (GPz/GPz.m:1-263), the fit exit (GPz.m:84-87), getPHI, predict, inv_logdet, Dxy and the
+// NCCL row-sharding plumbing.
+//
+// One evaluation =
+//   sweep 1   PHI build (+ln-noise row-dot)  ->  row weights  ->  Gram PHI'W PHI and PHI'W y   [allreduce #1]
+//   solve     SIGMA = Gram + diag(alpha): blocked Cholesky, SIGMA^-1, logdet, w, dw/dalpha     (replicated)
+//   sweep 2   T = PHI SIGMA^-1 with fused nu / H epilogue -> row gradients -> dPHI -> back-projection
+//             onto P, Gamma; column sums for dv, dlnAlpha; train/valid statistics               [allreduce #2]
+//   finish    assemble nlogML, grad (scaled by -1/(n k)), the four statistics
+// Everything is enqueued on one stream; the host only copies theta in and (f, g, stats) out.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "internal.cuh"
+
+namespace gpz {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCCL through dlopen (libnccl.so.2 is only needed when gpz_comm_init is used)
+// ------------------------------------------------------------------------------------------------
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load() {
+    if (g_nccl.h) return GPZ_OK;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+        set_error("cannot load libnccl.so.2: %s", dlerror());
+        return GPZ_ERR_NCCL;
+    }
+    g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+    g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+    g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(h, "ncclAllReduce"));
+    g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+        set_error("libnccl.so.2 lacks required symbols");
+        return GPZ_ERR_NCCL;
+    }
+    g_nccl.h = h;
+    return GPZ_OK;
+}
+
+#define GPZ_NCCL(call)                                                                                   \
+    do {                                                                                                 \
+        ncclResult_t r__ = (call);                                                                       \
+        if (r__ != ncclSuccess) {                                                                        \
+            gpz::set_error("%s:%d NCCL error: %s", __FILE__, __LINE__,                                    \
+                           gpz::g_nccl.GetErrorString ? gpz::g_nccl.GetErrorString(r__) : "?");          \
+            return GPZ_ERR_NCCL;                                                                         \
+        }                                                                                                \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// O(n) row kernels and small assembly kernels
+// ------------------------------------------------------------------------------------------------
+constexpr int RB = 256;        // rows per block of the row kernels
+constexpr int KMAX = 4;        // fused multi-output limit of the element-wise kernels
+
+// sweep 1 rows: lnbi = b + PHI v ; beta ; ob = omega*beta ; yw = ob*y ; partial sums
+//   part[blk][0..k-1] = sum omega*lnbi_o,  [k] = sum omega,  [k+1] = row count
+__global__ void __launch_bounds__(RB)
+rows1_kernel(Params P, const double* __restrict__ Y, const double* __restrict__ omega, int64_t n, int64_t r0, int64_t r1,
+             double* __restrict__ lnbi /*in: PHI v (het) ; out: ln beta^-1*/, double* __restrict__ beta,
+             double* __restrict__ ob, double* __restrict__ yw /*[n][32]*/, double* __restrict__ part, int nsc) {
+    __shared__ double sh[RB / 32];
+    const int64_t i = r0 + static_cast<int64_t>(blockIdx.x) * RB + threadIdx.x;
+    const bool live = i < r1;
+    const double om = live ? omega[i] : 0.0;
+    const int64_t blk = r0 / RB + blockIdx.x;
+    for (int o = 0; o < P.k; ++o) {
+        double ln = 0.0;
+        if (live) {
+            ln = P.bk[o] + (P.het ? lnbi[o * n + i] : 0.0);
+            const double be = exp(-ln);
+            lnbi[o * n + i] = ln;
+            beta[o * n + i] = be;
+            ob[o * n + i] = om * be;
+            yw[i * 32 + o] = om * be * Y[o * n + i];
+        }
+        const double s = block_sum<RB>(om * ln, sh);
+        if (threadIdx.x == 0) part[blk * nsc + o] = s;
+    }
+    if (live)
+        for (int o = P.k; o < 32; ++o) yw[i * 32 + o] = 0.0;
+    const double so = block_sum<RB>(om, sh);
+    const double sc = block_sum<RB>(live ? 1.0 : 0.0, sh);
+    if (threadIdx.x == 0) {
+        part[blk * nsc + P.k] = so;
+        part[blk * nsc + P.k + 1] = sc;
+    }
+}
+
+// sweep 2 rows for output o: nu = sum of tile partials ; delta ; cw = -omega beta delta ; dbeta
+//   part[blk][o] = sum ob*delta^2, [k+o] = sum dbeta, [2k] += sum omega delta^2, [2k+1] += sum omega(-.5 beta delta^2 - .5 lnbi)
+__global__ void __launch_bounds__(RB)
+rows2_kernel(Params P, int o, const double* __restrict__ Y, const double* __restrict__ omega, int64_t n, int64_t r0,
+             int64_t r1, const double* __restrict__ pred, const double* __restrict__ nupart, int ntn,
+             const double* __restrict__ lnbi, const double* __restrict__ beta, const double* __restrict__ ob,
+             double* __restrict__ nu, double* __restrict__ cw, double* __restrict__ dbeta, double* __restrict__ part,
+             int nsc) {
+    __shared__ double sh[RB / 32];
+    const int64_t i = r0 + static_cast<int64_t>(blockIdx.x) * RB + threadIdx.x;
+    const bool live = i < r1;
+    const int64_t blk = r0 / RB + blockIdx.x;
+    const int k = P.k;
+    double a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0;
+    if (live) {
+        double nv = 0.0;
+        if (nupart != nullptr)
+            for (int t = 0; t < ntn; ++t) nv += nupart[static_cast<int64_t>(t) * n + i];
+        const double om = omega[i];
+        const double be = beta[o * n + i];
+        const double dl = pred[o * n + i] - Y[o * n + i];
+        const double obd = ob[o * n + i] * dl;
+        const double db = -0.5 * om * (1.0 - be * (dl * dl + nv));          // GPz.m:93
+        nu[o * n + i] = nv;
+        cw[o * n + i] = -obd;
+        dbeta[o * n + i] = db;
+        a1 = obd * dl;
+        a2 = db;
+        a3 = om * dl * dl;
+        a4 = om * (-0.5 * be * dl * dl - 0.5 * lnbi[o * n + i]);
+    }
+    a1 = block_sum<RB>(a1, sh);
+    a2 = block_sum<RB>(a2, sh);
+    a3 = block_sum<RB>(a3, sh);
+    a4 = block_sum<RB>(a4, sh);
+    if (threadIdx.x == 0) {
+        double* p = part + blk * nsc;
+        p[o] = a1;
+        p[k + o] = a2;
+        p[2 * k] = (o == 0 ? 0.0 : p[2 * k]) + a3;
+        p[2 * k + 1] = (o == 0 ? 0.0 : p[2 * k + 1]) + a4;
+    }
+}
+
+// validation rows: lnbi_v = b + PHI_v v, pred_v = PHI_v w  ->  part[blk][0] += sum omega delta^2, [1] += LL sum, [2] = count
+__global__ void __launch_bounds__(RB)
+rowsv_kernel(Params P, int o, const double* __restrict__ Y, const double* __restrict__ omega, int64_t n, int64_t r0,
+             int64_t r1, const double* __restrict__ dotv, const double* __restrict__ pred, double* __restrict__ part) {
+    __shared__ double sh[RB / 32];
+    const int64_t i = r0 + static_cast<int64_t>(blockIdx.x) * RB + threadIdx.x;
+    const bool live = i < r1;
+    const int64_t blk = r0 / RB + blockIdx.x;
+    double a1 = 0.0, a2 = 0.0;
+    if (live) {
+        const double om = omega[i];
+        const double ln = P.bk[o] + (P.het ? dotv[o * n + i] : 0.0);
+        const double be = exp(-ln);
+        const double dl = pred[o * n + i] - Y[o * n + i];
+        a1 = om * dl * dl;
+        a2 = om * (-0.5 * be * dl * dl - 0.5 * ln);
+    }
+    a1 = block_sum<RB>(a1, sh);
+    a2 = block_sum<RB>(a2, sh);
+    const double c = block_sum<RB>(live ? 1.0 : 0.0, sh);
+    if (threadIdx.x == 0) {
+        double* p = part + blk * 3;
+        p[0] = (o == 0 ? 0.0 : p[0]) + a1;
+        p[1] = (o == 0 ? 0.0 : p[1]) + a2;
+        p[2] = c;
+    }
+}
+
+// out[s] = sum_b part[b][s]  (fixed order)
+__global__ void __launch_bounds__(256)
+reduce_parts_kernel(const double* __restrict__ part, int64_t nblk, int nsc, double* __restrict__ out) {
+    __shared__ double sh[8];
+    const int s = blockIdx.x;
+    double v = 0.0;
+    for (int64_t b = threadIdx.x; b < nblk; b += 256) v += part[b * nsc + s];
+    v = block_sum<256>(v, sh);
+    if (threadIdx.x == 0) out[s] = v;
+}
+
+// dPHI_ij = -H_ij + PHI_ij * sum_o (cw_io w_jo + dbeta_io v_jo)     (GPz.m:72,90,106,113), in place over H
+// column partial sums: colp[slab][o][MP] = sum_i PHI_ij * (-cw_io)  (= PHI'(omega beta delta), GPz.m:89)
+//                      colp[slab][k+o][MP] = sum_i PHI_ij * dbeta_io (GPz.m:104)
+__global__ void __launch_bounds__(128)
+dphi_kernel(Params P, const double* __restrict__ Phi, double* __restrict__ H, int64_t ld, int64_t n, int64_t r0,
+            int64_t r1, int64_t rows_per_slab, const double* __restrict__ cw, const double* __restrict__ dbeta,
+            const double* __restrict__ w, double* __restrict__ colp, int accumulate) {
+    const int j = blockIdx.x * 128 + threadIdx.x;
+    const int k = P.k, MP = P.MP;
+    const int64_t sb = r0 + static_cast<int64_t>(blockIdx.y) * rows_per_slab;
+    int64_t se = sb + rows_per_slab;
+    if (se > r1) se = r1;
+    double wj[KMAX], vj[KMAX], sq[KMAX], sv[KMAX];
+#pragma unroll
+    for (int o = 0; o < KMAX; ++o) {
+        wj[o] = (o < k) ? w[o * MP + j] : 0.0;
+        vj[o] = (o < k) ? P.v[o * MP + j] : 0.0;
+        sq[o] = sv[o] = 0.0;
+    }
+    for (int64_t i = sb; i < se; ++i) {
+        const int64_t off = (i - r0) * ld + j;
+        const double ph = Phi[off];
+        double c = 0.0;
+#pragma unroll
+        for (int o = 0; o < KMAX; ++o) {
+            if (o < k) {
+                const double cwi = __ldg(cw + o * n + i), dbi = __ldg(dbeta + o * n + i);
+                c = fma(cwi, wj[o], fma(dbi, vj[o], c));
+                sq[o] = fma(ph, -cwi, sq[o]);
+                sv[o] = fma(ph, dbi, sv[o]);
+            }
+        }
+        H[off] = fma(ph, c, -H[off]);
+    }
+    double* out = colp + static_cast<int64_t>(blockIdx.y) * 2 * k * MP;
+#pragma unroll
+    for (int o = 0; o < KMAX; ++o) {
+        if (o < k) {
+            double a = sq[o], b = sv[o];
+            if (accumulate) {
+                a += out[o * MP + j];
+                b += out[(k + o) * MP + j];
+            }
+            out[o * MP + j] = a;
+            out[(k + o) * MP + j] = b;
+        }
+    }
+}
+
+// colsum[c][j] = sum_slab colp[slab][c][j]
+__global__ void colsum_reduce_kernel(const double* __restrict__ colp, int nslab, int nc, int MP, double* __restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nc * MP) return;
+    double s = 0.0;
+    for (int sl = 0; sl < nslab; ++sl) s += colp[static_cast<int64_t>(sl) * nc * MP + e];
+    out[e] = s;
+}
+
+__global__ void add_diag_kernel(double* __restrict__ S, int MP, int m, const double* __restrict__ alpha) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < MP) S[static_cast<int64_t>(j) * MP + j] += (j < m) ? alpha[j] : 1.0;
+}
+
+// y[j] = scale * sum_l Sinv[j][l] * (x[l*xs] * (xmul ? xmul[l] : 1))      warp per row
+__global__ void __launch_bounds__(256)
+symv_kernel(const double* __restrict__ Sinv, int MP, int m, const double* __restrict__ x, int xs,
+            const double* __restrict__ xmul, double scale, double* __restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (j >= MP) return;
+    double s = 0.0;
+    if (j < m)
+        for (int l = lane; l < m; l += 32) s += Sinv[static_cast<int64_t>(j) * MP + l] * x[static_cast<int64_t>(l) * xs] * (xmul ? xmul[l] : 1.0);
+    s = warp_sum(s);
+    if (lane == 0) y[j] = (j < m) ? scale * s : 0.0;
+}
+
+struct FinishArgs {
+    Params P;
+    const double* theta;
+    const double* w;        // [k][MP]
+    const double* dwda;     // [k][MP]
+    const double* Sinv;     // [k][MP][MP]
+    const double* logdet;   // [k]
+    const double* scal1;    // [k]: sum omega lnbi_o ; [k]: sum omega ; [k+1]: n rows (global)
+    const double* red2;     // dP | dG | q[k][MP] | dvraw[k][MP] | scal2
+    const int* flag;
+    int has_valid;
+    double* out;            // nlogML | grad[p] | stats[4]
+};
+
+// single CTA: assemble nlogML (GPz.m:81-82,103,110,233), the small gradients (GPz.m:89,104-105), pack and
+// scale (GPz.m:227-234) and the statistics (GPz.m:236-259)
+__global__ void __launch_bounds__(256)
+finish_kernel(FinishArgs A) {
+    __shared__ double sh[8];
+    __shared__ double s_total;
+    const Params& P = A.P;
+    const int m = P.m, k = P.k, MP = P.MP, d = P.d;
+    const int tid = threadIdx.x;
+    const int64_t md = static_cast<int64_t>(m) * d;
+    const double* dP = A.red2;
+    const double* dG = dP + md;
+    const double* q = dG + P.g_dim;
+    const double* dvraw = q + static_cast<int64_t>(k) * MP;
+    const double* sc2 = dvraw + static_cast<int64_t>(k) * MP;
+    const double nrow = A.scal1[k + 1];
+    const double nk = nrow * k;
+    double* grad = A.out + 1;
+    const bool bad = (*A.flag != 0);
+
+    double tot = 0.0;
+    for (int o = 0; o < k; ++o) {
+        double s = 0.0;
+        for (int j = tid; j < m; j += 256) {
+            const double al = P.alpha[o * MP + j], wv = A.w[o * MP + j];
+            s += -0.5 * al * wv * wv + 0.5 * A.theta[P.oA + static_cast<int64_t>(o) * m + j];
+            if (P.het) {
+                const double vv = P.v[o * MP + j], ta = P.tau[o * MP + j];
+                s += -0.5 * vv * vv * ta + 0.5 * A.theta[P.oT + static_cast<int64_t>(o) * m + j];
+            }
+        }
+        s = block_sum<256>(s, sh);
+        if (tid == 0) {
+            s += -0.5 * sc2[o] - 0.5 * A.logdet[o] - 0.5 * A.scal1[o];
+            if (P.het) s += -0.5 * m * k * 1.8378770664093454836;     // m*k on every column (GPz.m:103)
+            tot += s;
+        }
+    }
+    if (tid == 0) {
+        tot -= 0.5 * 1.8378770664093454836 * A.scal1[k];               // GPz.m:110
+        s_total = tot;
+    }
+    __syncthreads();
+    const double nan_ = nan("");
+    const double sgn = -1.0 / nk;
+    if (tid == 0) A.out[0] = bad ? nan_ : -s_total / nk;
+    for (int64_t e = tid; e < md + P.g_dim; e += 256) grad[e] = bad ? nan_ : sgn * A.red2[e];
+    for (int e = tid; e < m * k; e += 256) {
+        const int o = e / m, j = e % m;
+        const double al = P.alpha[o * MP + j], wv = A.w[o * MP + j], dw = A.dwda[o * MP + j];
+        const double sii = A.Sinv[(static_cast<int64_t>(o) * MP + j) * MP + j];
+        const double dla = -0.5 * sii * al - q[o * MP + j] * dw - al * wv * dw - 0.5 * al * wv * wv + 0.5;   // GPz.m:73,89
+        grad[P.oA + e] = bad ? nan_ : sgn * dla;
+        if (P.het) {
+            const double vv = P.v[o * MP + j], ta = P.tau[o * MP + j];
+            grad[P.oV + e] = bad ? nan_ : sgn * (dvraw[o * MP + j] - vv * ta);      // GPz.m:104
+            grad[P.oT + e] = bad ? nan_ : sgn * (-0.5 * ta * vv * vv + 0.5);        // GPz.m:105
+        }
+    }
+    if (tid < k) grad[P.oB + tid] = bad ? nan_ : sgn * sc2[k + tid];               // db, GPz.m:94
+    if (tid == 0) {
+        double* st = A.out + 1 + P.p;
+        st[0] = bad ? nan_ : sqrt(sc2[2 * k] / nk);                                 // trainRMSE  GPz.m:236
+        st[1] = bad ? nan_ : sc2[2 * k + 1] / nk - 0.5 * 1.8378770664093454836;     // trainLL    GPz.m:237
+        if (A.has_valid) {
+            const double nv = sc2[2 * k + 4] * k;
+            st[2] = bad ? nan_ : sqrt(sc2[2 * k + 2] / nv);                         // validRMSE  GPz.m:258
+            st[3] = bad ? nan_ : sc2[2 * k + 3] / nv - 0.5 * 1.8378770664093454836; // validLL    GPz.m:259
+        } else {
+            st[2] = nan_;
+            st[3] = nan_;
+        }
+    }
+}
+
+// fit exit: nl[o] = -1/2 sum ob delta^2 - 1/2 sum alpha w^2 + 1/2 sum lnAlpha - 1/2 logdet - 1/2 sum omega lnbi  (GPz.m:81-82)
+__global__ void __launch_bounds__(256)
+fit_nl_kernel(Params P, const double* theta, const double* w, const double* logdet, const double* scal1,
+              const double* sc2, const int* flag, double* out) {
+    __shared__ double sh[8];
+    for (int o = 0; o < P.k; ++o) {
+        double s = 0.0;
+        for (int j = threadIdx.x; j < P.m; j += 256) {
+            const double al = P.alpha[o * P.MP + j], wv = w[o * P.MP + j];
+            s += -0.5 * al * wv * wv + 0.5 * theta[P.oA + static_cast<int64_t>(o) * P.m + j];
+        }
+        s = block_sum<256>(s, sh);
+        if (threadIdx.x == 0) out[o] = (*flag) ? nan("") : s - 0.5 * sc2[o] - 0.5 * logdet[o] - 0.5 * scal1[o];
+    }
+}
+
+__global__ void nan_fill_kernel(double* p, int64_t n, const int* flag) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n && *flag) p[i] = nan("");
+}
+
+__global__ void sum_cols_kernel(const double* __restrict__ nupart, int ntn, int64_t stride, int64_t count, double* __restrict__ nu) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    double s = 0.0;
+    for (int t = 0; t < ntn; ++t) s += nupart[static_cast<int64_t>(t) * stride + i];
+    nu[i] = s;
+}
+
+__global__ void exp_rows_kernel(const double* __restrict__ dotv, const double* __restrict__ bk, int het, int k, int64_t n,
+                                double* __restrict__ elns, double* __restrict__ beta_i) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int o = 0; o < k; ++o) {
+        const double e = bk[o] + (het ? dotv[o * n + i] : 0.0);
+        elns[o * n + i] = e;
+        beta_i[o * n + i] = exp(e);
+    }
+}
+
+}  // namespace gpz
+
+using namespace gpz;
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct gpz_ctx {
+    Params P{};
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t st = nullptr;
+    RowData tr, va;
+    int has_psi = 0;
+    int64_t launches = 0;
+    // NCCL
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+    // options
+    int64_t opt_chunk_rows = 0;     // 0 = auto
+    // workspaces (allocated at first use)
+    bool ws_ready = false;
+    int64_t chunk_rows = 0;
+    bool resident = true;
+    double *d_theta = nullptr, *d_out = nullptr;
+    double *Phi = nullptr, *H = nullptr;
+    double *lnbi = nullptr, *beta = nullptr, *ob = nullptr, *pred = nullptr, *nu = nullptr, *cw = nullptr, *dbeta = nullptr;
+    double *nupart = nullptr, *yw = nullptr, *ones = nullptr;
+    double *dotv_va = nullptr, *pred_va = nullptr;
+    double *gram_partial = nullptr, *atb_partial = nullptr;
+    int gram_ns = 1, atb_ns = 1, nslab = 1;
+    double *red1 = nullptr, *red2 = nullptr;      // allreduce payloads
+    int64_t red1_len = 0, red2_len = 0;
+    double *S = nullptr, *Rvec = nullptr, *scal1 = nullptr;
+    double *Sinv = nullptr, *w = nullptr, *dwda = nullptr, *logdet = nullptr;
+    double *part1 = nullptr, *part2 = nullptr, *partv = nullptr;
+    double *colp = nullptr, *bp_partial = nullptr, *Fbuf = nullptr, *Rm = nullptr, *scratch = nullptr;
+    int QP = 32;
+    SolveWs sws;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double* h_out = nullptr;   // pinned
+    double* h_theta = nullptr; // pinned
+    std::vector<void*> allocs;
+};
+
+namespace {
+
+int parse_mode(const char* s) {
+    static const char* names[6] = {"GL", "VL", "GD", "VD", "GC", "VC"};
+    for (int i = 0; i < 6; ++i)
+        if (s[0] == names[i][0] && s[1] == names[i][1]) return i;
+    return -1;
+}
+
+int64_t g_dim_of(int mode, int m, int d) {
+    switch (mode) {
+        case GL: return 1;
+        case VL: return m;
+        case GD: return d;
+        case VD: return static_cast<int64_t>(m) * d;
+        case GC: return static_cast<int64_t>(d) * d;
+        default: return static_cast<int64_t>(d) * d * m;
+    }
+}
+
+int fill_params(Params& P, const gpz_model* model) {
+    if (!model) {
+        set_error("model is NULL");
+        return GPZ_ERR_USAGE;
+    }
+    const int mode = parse_mode(model->method);
+    if (mode < 0 || model->d < 1 || model->m < 1 || model->k < 1) {
+        set_error("bad model (method '%c%c', d=%d, m=%d, k=%d)", model->method[0], model->method[1], model->d, model->m, model->k);
+        return GPZ_ERR_USAGE;
+    }
+    if (model->k > KMAX) {
+        set_error("k=%d outputs: at most %d supported", model->k, KMAX);
+        return GPZ_ERR_USAGE;
+    }
+    if (model->d > 32 && mode_is_cov(mode)) {
+        set_error("covariance modes support d <= 32 (got %d)", model->d);
+        return GPZ_ERR_USAGE;
+    }
+    P.d = model->d;
+    P.dp = static_cast<int>(round_up(model->d, 2));
+    P.k = model->k;
+    P.m = model->m;
+    P.MP = static_cast<int>(round_up(model->m, TILE));
+    P.mode = mode;
+    P.het = model->heteroscedastic ? 1 : 0;
+    P.g_dim = g_dim_of(mode, P.m, P.d);
+    const int64_t md = static_cast<int64_t>(P.m) * P.d, mk = static_cast<int64_t>(P.m) * P.k;
+    P.oG = md;
+    P.oA = md + P.g_dim;
+    P.oB = P.oA + mk;
+    P.oV = P.oB + P.k;
+    P.oT = P.oV + mk;
+    P.p = P.oB + P.k + (P.het ? 2 * mk : 0);
+    return GPZ_OK;
+}
+
+template <class T>
+int dev_alloc(std::vector<void*>& list, T** p, int64_t count) {
+    *p = nullptr;
+    if (count <= 0) count = 1;
+    GPZ_CUDA(cudaMalloc(reinterpret_cast<void**>(p), sizeof(T) * static_cast<size_t>(count)));
+    list.push_back(*p);
+    return GPZ_OK;
+}
+
+int alloc_params(Params& P, std::vector<void*>& list, int need_sigma) {
+    const int64_t MP = P.MP, d = P.d;
+    int rc;
+    if ((rc = dev_alloc(list, &P.Pt, d * MP))) return rc;
+    if ((rc = dev_alloc(list, &P.Ct, d * MP))) return rc;
+    if (!mode_is_cov(P.mode)) {
+        if ((rc = dev_alloc(list, &P.Gt, d * MP))) return rc;
+        P.Gam = P.Aj = P.Sj = P.lndS = nullptr;
+    } else {
+        P.Gt = nullptr;
+        if ((rc = dev_alloc(list, &P.Gam, d * P.dp * MP))) return rc;
+        if ((rc = dev_alloc(list, &P.Aj, d * d * MP))) return rc;
+        if (need_sigma) {
+            if ((rc = dev_alloc(list, &P.Sj, d * d * MP))) return rc;
+            if ((rc = dev_alloc(list, &P.lndS, MP))) return rc;
+        } else {
+            P.Sj = P.lndS = nullptr;
+        }
+    }
+    if ((rc = dev_alloc(list, &P.alpha, P.k * MP))) return rc;
+    if ((rc = dev_alloc(list, &P.v, P.k * MP))) return rc;
+    if ((rc = dev_alloc(list, &P.tau, P.k * MP))) return rc;
+    if ((rc = dev_alloc(list, &P.bk, 32))) return rc;
+    return GPZ_OK;
+}
+
+int check_device(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("no CUDA device available (%s); libgpz_b200 has no CPU fallback", cudaGetErrorString(e));
+        return GPZ_ERR_NODEVICE;
+    }
+    if (device < 0 || device >= count) {
+        set_error("device %d out of range (%d devices)", device, count);
+        return GPZ_ERR_USAGE;
+    }
+    GPZ_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    GPZ_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; libgpz_b200 is built for sm_100a only", device, prop.major, prop.minor);
+        return GPZ_ERR_NODEVICE;
+    }
+    return GPZ_OK;
+}
+
+// gather selected rows of a column-major n_all x cols host matrix into a [cols][n] host buffer
+void gather_cols(const double* src, int64_t n_all, int cols, const std::vector<int64_t>& idx, std::vector<double>& dst) {
+    const int64_t n = static_cast<int64_t>(idx.size());
+    dst.resize(static_cast<size_t>(n) * cols);
+    for (int c = 0; c < cols; ++c) {
+        const double* s = src + static_cast<int64_t>(c) * n_all;
+        double* o = dst.data() + static_cast<int64_t>(c) * n;
+        for (int64_t i = 0; i < n; ++i) o[i] = s[idx[i]];
+    }
+}
+
+int upload_rows(gpz_ctx* c, RowData& R, const std::vector<int64_t>& idx, int64_t n_all, const double* X, const double* Y,
+                const double* Psi, const double* omega) {
+    const Params& P = c->P;
+    const int64_t n = static_cast<int64_t>(idx.size());
+    R.n = n;
+    int rc;
+    std::vector<double> buf;
+    if ((rc = dev_alloc(c->allocs, &R.X, n * P.d))) return rc;
+    gather_cols(X, n_all, P.d, idx, buf);
+    R.has_nan = 0;
+    for (double v : buf)
+        if (v != v) { R.has_nan = 1; break; }
+    GPZ_CUDA(cudaMemcpy(R.X, buf.data(), sizeof(double) * buf.size(), cudaMemcpyHostToDevice));
+    if ((rc = dev_alloc(c->allocs, &R.Y, n * P.k))) return rc;
+    if (Y) {
+        gather_cols(Y, n_all, P.k, idx, buf);
+        GPZ_CUDA(cudaMemcpy(R.Y, buf.data(), sizeof(double) * buf.size(), cudaMemcpyHostToDevice));
+    } else {
+        GPZ_CUDA(cudaMemset(R.Y, 0, sizeof(double) * (n * P.k > 0 ? n * P.k : 1)));
+    }
+    if ((rc = dev_alloc(c->allocs, &R.omega, n))) return rc;
+    buf.assign(static_cast<size_t>(n), 1.0);
+    if (omega)
+        for (int64_t i = 0; i < n; ++i) buf[i] = omega[idx[i]];
+    GPZ_CUDA(cudaMemcpy(R.omega, buf.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+    R.Psi = nullptr;
+    if (Psi) {
+        if (mode_is_cov(P.mode)) {
+            const int64_t dd = static_cast<int64_t>(P.d) * P.d;
+            buf.resize(static_cast<size_t>(n * dd));
+            for (int64_t i = 0; i < n; ++i) memcpy(buf.data() + i * dd, Psi + idx[i] * dd, sizeof(double) * dd);
+            if ((rc = dev_alloc(c->allocs, &R.Psi, n * dd))) return rc;
+        } else {
+            gather_cols(Psi, n_all, P.d, idx, buf);
+            if ((rc = dev_alloc(c->allocs, &R.Psi, n * P.d))) return rc;
+        }
+        GPZ_CUDA(cudaMemcpy(R.Psi, buf.data(), sizeof(double) * buf.size(), cudaMemcpyHostToDevice));
+    }
+    return GPZ_OK;
+}
+
+int ensure_workspace(gpz_ctx* c) {
+    if (c->ws_ready) return GPZ_OK;
+    Params& P = c->P;
+    const int64_t n = c->tr.n, nv = c->va.n, MP = P.MP, k = P.k;
+    int rc;
+    auto A = [&](double** p, int64_t cnt) { return dev_alloc(c->allocs, p, cnt); };
+    // row chunking: keep PHI and H (2 x rows x MP doubles) within ~55% of the free memory
+    size_t free_b = 0, total_b = 0;
+    GPZ_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    int64_t max_rows = static_cast<int64_t>(0.55 * static_cast<double>(free_b) / (16.0 * MP));
+    max_rows = max_rows / 1024 * 1024;
+    if (max_rows < 1024) max_rows = 1024;
+    int64_t need = n > nv ? n : nv;
+    if (need < 1) need = 1;
+    c->chunk_rows = need < max_rows ? need : max_rows;
+    if (c->opt_chunk_rows > 0) {
+        c->chunk_rows = round_up(c->opt_chunk_rows, 1024);
+        if (c->chunk_rows > round_up(need, 1024)) c->chunk_rows = round_up(need, 1024);
+    }
+    c->resident = c->chunk_rows >= n;
+    if ((rc = A(&c->Phi, c->chunk_rows * MP))) return rc;
+    if ((rc = A(&c->H, c->chunk_rows * MP))) return rc;
+    if ((rc = A(&c->d_theta, P.p))) return rc;
+    if ((rc = A(&c->d_out, P.p + 5))) return rc;
+    const int64_t nn = n > 0 ? n : 1;
+    if ((rc = A(&c->lnbi, k * nn))) return rc;
+    if ((rc = A(&c->beta, k * nn))) return rc;
+    if ((rc = A(&c->ob, k * nn))) return rc;
+    if ((rc = A(&c->pred, k * nn))) return rc;
+    if ((rc = A(&c->nu, k * nn))) return rc;
+    if ((rc = A(&c->cw, k * nn))) return rc;
+    if ((rc = A(&c->dbeta, k * nn))) return rc;
+    if ((rc = A(&c->nupart, (MP / TILE) * nn))) return rc;
+    if ((rc = A(&c->yw, 32 * nn))) return rc;
+    {
+        const int64_t no = need;
+        if ((rc = A(&c->ones, no))) return rc;
+        std::vector<double> one(static_cast<size_t>(no), 1.0);
+        GPZ_CUDA(cudaMemcpy(c->ones, one.data(), sizeof(double) * no, cudaMemcpyHostToDevice));
+    }
+    if ((rc = A(&c->dotv_va, k * (nv > 0 ? nv : 1)))) return rc;
+    if ((rc = A(&c->pred_va, k * (nv > 0 ? nv : 1)))) return rc;
+    // GEMM partial buffers
+    const int T = static_cast<int>(MP / TILE);
+    const int ntri = T * (T + 1) / 2;
+    c->gram_ns = gram_nsplit(static_cast<int>(MP), c->sm_count);
+    if ((rc = A(&c->gram_partial, static_cast<int64_t>(c->gram_ns) * ntri * TILE * TILE))) return rc;
+    const int q = feature_count(P);
+    c->QP = static_cast<int>(round_up(q, 32));
+    const int tn = c->QP / 32;
+    c->atb_ns = c->sm_count / (T * tn) > 0 ? c->sm_count / (T * tn) : 1;
+    {
+        const int ns1 = c->sm_count / T > 0 ? c->sm_count / T : 1;     // the PHI'(ob*y) product has QP = 32
+        const int64_t a = static_cast<int64_t>(c->atb_ns) * T * tn * TILE * 32;
+        const int64_t b = static_cast<int64_t>(ns1) * T * TILE * 32;
+        if ((rc = A(&c->atb_partial, a > b ? a : b))) return rc;
+    }
+    c->nslab = (2 * c->sm_count) / T > 0 ? (2 * c->sm_count) / T : 1;
+    // allreduce payloads
+    c->red1_len = k * MP * MP + MP * 32 + (k + 2);
+    if ((rc = A(&c->red1, c->red1_len))) return rc;
+    c->S = c->red1;
+    c->Rvec = c->S + k * MP * MP;
+    c->scal1 = c->Rvec + MP * 32;
+    c->red2_len = static_cast<int64_t>(P.m) * P.d + P.g_dim + 2 * k * MP + (2 * k + 5);
+    if ((rc = A(&c->red2, c->red2_len))) return rc;
+    if ((rc = A(&c->Sinv, k * MP * MP))) return rc;
+    if ((rc = A(&c->w, k * MP))) return rc;
+    if ((rc = A(&c->dwda, k * MP))) return rc;
+    if ((rc = A(&c->logdet, 32))) return rc;
+    const int64_t nb1 = ceil_div(nn, RB) + 1, nbv = ceil_div(nv > 0 ? nv : 1, RB) + 1;
+    if ((rc = A(&c->part1, nb1 * (k + 2)))) return rc;
+    if ((rc = A(&c->part2, nb1 * (2 * k + 2)))) return rc;
+    if ((rc = A(&c->partv, nbv * 3))) return rc;
+    if ((rc = A(&c->colp, static_cast<int64_t>(c->nslab) * 2 * k * MP))) return rc;
+    const int64_t bpd = backproj_partial_doubles(P, c->nslab, c->has_psi, c->tr.has_nan);
+    if ((rc = A(&c->bp_partial, bpd))) return rc;
+    const bool fast_bp = !c->has_psi && !c->tr.has_nan;
+    if (fast_bp) {
+        if ((rc = A(&c->Fbuf, c->chunk_rows * c->QP))) return rc;
+        if ((rc = A(&c->Rm, MP * c->QP))) return rc;
+    }
+    {
+        const int64_t dd = static_cast<int64_t>(P.d) * P.d;
+        const int64_t sc = 2 * dd * MP + dd * P.m + static_cast<int64_t>(P.m) * P.d + 64;
+        if ((rc = A(&c->scratch, sc))) return rc;
+    }
+    if ((rc = solve_ws_alloc(c->sws, static_cast<int>(MP)))) return rc;
+    for (auto& e : c->ev) GPZ_CUDA(cudaEventCreate(&e));
+    GPZ_CUDA(cudaMallocHost(&c->h_out, sizeof(double) * (P.p + 5)));
+    GPZ_CUDA(cudaMallocHost(&c->h_theta, sizeof(double) * P.p));
+    c->ws_ready = true;
+    return GPZ_OK;
+}
+
+int allreduce(gpz_ctx* c, double* buf, int64_t len) {
+    if (c->world <= 1 || c->comm == nullptr) return GPZ_OK;
+    GPZ_NCCL(g_nccl.AllReduce(buf, buf, static_cast<size_t>(len), ncclDouble, ncclSum, c->comm, c->st));
+    return GPZ_OK;
+}
+
+// sweep 1 + solve.  Leaves Sinv, w, dwda, logdet, scal1 (global) on the device.
+int forward_and_solve(gpz_ctx* c, const double* d_theta) {
+    Params& P = c->P;
+    cudaStream_t st = c->st;
+    const int64_t n = c->tr.n, MP = P.MP;
+    const int k = P.k;
+    int rc;
+    GPZ_CUDA(cudaMemsetAsync(c->sws.flag, 0, sizeof(int), st));
+    GPZ_CUDA(cudaEventRecord(c->ev[0], st));
+    if ((rc = prep_params(d_theta, P, c->has_psi, st, &c->launches))) return rc;
+    const int T = static_cast<int>(MP / TILE);
+    const int ns1 = c->sm_count / T > 0 ? c->sm_count / T : 1;
+    int nchunks = 0;
+    for (int64_t r0 = 0; r0 < n || (n == 0 && r0 == 0); r0 += c->chunk_rows) {
+        const int64_t r1 = (r0 + c->chunk_rows < n) ? r0 + c->chunk_rows : n;
+        const bool last = r1 >= n;
+        double* phi = c->resident ? c->Phi + r0 * MP : c->Phi;
+        if (n > 0) {
+            DotSpec ds{0, {nullptr, nullptr}, {nullptr, nullptr}};
+            if (P.het && k == 1) ds = DotSpec{1, {P.v, nullptr}, {c->lnbi, nullptr}};
+            if ((rc = phi_build(P, c->tr, r0, r1, phi, ds, st, &c->launches))) return rc;
+            if (P.het && k > 1)
+                for (int o = 0; o < k; ++o)
+                    if ((rc = rowdot(phi, MP, P.m, r1 - r0, DotSpec{1, {P.v + o * MP, nullptr}, {c->lnbi + o * n + r0, nullptr}}, st, &c->launches))) return rc;
+            rows1_kernel<<<static_cast<unsigned>(ceil_div(r1 - r0, RB)), RB, 0, st>>>(P, c->tr.Y, c->tr.omega, n, r0, r1, c->lnbi, c->beta,
+                                                                                    c->ob, c->yw, c->part1, k + 2);
+            GPZ_KERNEL_CHECK();
+            ++c->launches;
+        }
+        if (nchunks == 0) GPZ_CUDA(cudaEventRecord(c->ev[1], st));
+        for (int o = 0; o < k; ++o) {
+            // rows of this chunk are [0, r1-r0) of phi; the weights are indexed by absolute row
+            if ((rc = gram_syrk(phi, MP, static_cast<int>(MP), c->ob + o * n + r0, 0, r1 - r0, c->gram_ns,
+                                c->gram_partial, nchunks > 0, last, c->S + static_cast<int64_t>(o) * MP * MP, st, &c->launches))) return rc;
+            if (k > 1 && !last) {
+                set_error("row chunking with k > 1 outputs is not supported (raise the memory budget)");
+                return GPZ_ERR_USAGE;
+            }
+        }
+        if ((rc = atb_general(phi, MP, static_cast<int>(MP), c->yw + r0 * 32, 32, 32, c->ones, 0, r1 - r0, ns1, c->atb_partial,
+                              nchunks > 0, last, c->Rvec, st, &c->launches))) return rc;
+        ++nchunks;
+        if (last) break;
+    }
+    {
+        const int64_t nb = ceil_div(n > 0 ? n : 1, RB);
+        if (n == 0) GPZ_CUDA(cudaMemsetAsync(c->part1, 0, sizeof(double) * (k + 2), st));
+        reduce_parts_kernel<<<k + 2, 256, 0, st>>>(c->part1, n > 0 ? nb : 1, k + 2, c->scal1);
+        GPZ_KERNEL_CHECK();
+        ++c->launches;
+    }
+    if ((rc = allreduce(c, c->red1, c->red1_len))) return rc;
+    GPZ_CUDA(cudaEventRecord(c->ev[2], st));
+    for (int o = 0; o < k; ++o) {
+        double* S = c->S + static_cast<int64_t>(o) * MP * MP;
+        double* Si = c->Sinv + static_cast<int64_t>(o) * MP * MP;
+        add_diag_kernel<<<static_cast<unsigned>(ceil_div(MP, 256)), 256, 0, st>>>(S, static_cast<int>(MP), P.m, P.alpha + o * MP);
+        GPZ_KERNEL_CHECK();
+        ++c->launches;
+        if ((rc = spd_inverse(S, P.m, static_cast<int>(MP), Si, c->logdet + o, c->sws, st, &c->launches))) return rc;
+        const unsigned gb = static_cast<unsigned>(ceil_div(MP, 8));
+        symv_kernel<<<gb, 256, 0, st>>>(Si, static_cast<int>(MP), P.m, c->Rvec + o, 32, nullptr, 1.0, c->w + o * MP);
+        GPZ_KERNEL_CHECK();
+        symv_kernel<<<gb, 256, 0, st>>>(Si, static_cast<int>(MP), P.m, c->w + o * MP, 1, P.alpha + o * MP, -1.0, c->dwda + o * MP);
+        GPZ_KERNEL_CHECK();
+        c->launches += 2;
+    }
+    GPZ_CUDA(cudaEventRecord(c->ev[3], st));
+    return GPZ_OK;
+}
+
+// pred = PHI w for the training rows of one chunk (PHI resident or rebuilt)
+int chunk_phi_and_pred(gpz_ctx* c, int64_t r0, int64_t r1, double** phi_out) {
+    Params& P = c->P;
+    const int64_t n = c->tr.n, MP = P.MP;
+    int rc;
+    double* phi = c->resident ? c->Phi + r0 * MP : c->Phi;
+    if (!c->resident) {
+        DotSpec ds{1, {c->w, nullptr}, {c->pred, nullptr}};
+        if (P.k > 1) ds.n = 0;
+        if ((rc = phi_build(P, c->tr, r0, r1, phi, ds, c->st, &c->launches))) return rc;
+        if (P.k > 1)
+            for (int o = 0; o < P.k; ++o)
+                if ((rc = rowdot(phi, MP, P.m, r1 - r0, DotSpec{1, {c->w + o * MP, nullptr}, {c->pred + o * n + r0, nullptr}}, c->st, &c->launches))) return rc;
+    } else {
+        for (int o = 0; o < P.k; ++o)
+            if ((rc = rowdot(phi, MP, P.m, r1 - r0, DotSpec{1, {c->w + o * MP, nullptr}, {c->pred + o * n + r0, nullptr}}, c->st, &c->launches))) return rc;
+    }
+    *phi_out = phi;
+    return GPZ_OK;
+}
+
+int eval_device(gpz_ctx* c, const double* d_theta, double* d_out) {
+    Params& P = c->P;
+    cudaStream_t st = c->st;
+    int rc;
+    if ((rc = ensure_workspace(c))) return rc;
+    if ((rc = forward_and_solve(c, d_theta))) return rc;
+    const int64_t n = c->tr.n, nv = c->va.n, MP = P.MP;
+    const int k = P.k;
+    const int ntn = static_cast<int>(MP / TILE);
+    const int64_t md = static_cast<int64_t>(P.m) * P.d;
+    double* dP = c->red2;
+    double* dG = dP + md;
+    double* qcol = dG + P.g_dim;
+    double* sc2 = qcol + 2LL * k * MP;
+    const bool fast_bp = !c->has_psi && !c->tr.has_nan;
+    const int T = static_cast<int>(MP / TILE);
+    int nchunks = 0;
+    bool ev4 = false;
+    for (int64_t r0 = 0; r0 < n; r0 += c->chunk_rows) {
+        const int64_t r1 = (r0 + c->chunk_rows < n) ? r0 + c->chunk_rows : n;
+        const bool last = r1 >= n;
+        const int64_t rows = r1 - r0;
+        double* phi = nullptr;
+        if ((rc = chunk_phi_and_pred(c, r0, r1, &phi))) return rc;
+        for (int o = 0; o < k; ++o) {
+            if ((rc = tgemm(phi, MP, c->Sinv + static_cast<int64_t>(o) * MP * MP, static_cast<int>(MP), P.m, rows, c->ob + o * n + r0,
+                            c->H, o > 0, c->nupart + r0, n, st, &c->launches))) return rc;
+            rows2_kernel<<<static_cast<unsigned>(ceil_div(rows, RB)), RB, 0, st>>>(P, o, c->tr.Y, c->tr.omega, n, r0, r1, c->pred,
+                                                                                 c->nupart, ntn, c->lnbi, c->beta, c->ob, c->nu,
+                                                                                 c->cw, c->dbeta, c->part2, 2 * k + 2);
+            GPZ_KERNEL_CHECK();
+            ++c->launches;
+        }
+        if (!ev4) {
+            GPZ_CUDA(cudaEventRecord(c->ev[4], st));
+            ev4 = true;
+        }
+        {
+            const int64_t rps = ceil_div(rows, c->nslab);
+            dim3 grid(static_cast<unsigned>(T), static_cast<unsigned>(c->nslab));
+            dphi_kernel<<<grid, 128, 0, st>>>(P, phi, c->H, MP, n, r0, r1, rps, c->cw, c->dbeta, c->w, c->colp, nchunks > 0);
+            GPZ_KERNEL_CHECK();
+            ++c->launches;
+        }
+        if (fast_bp) {
+            if ((rc = build_features(P, c->tr, r0, r1, c->Fbuf, c->QP, st, &c->launches))) return rc;
+            if ((rc = atb_general(c->H, MP, static_cast<int>(MP), c->Fbuf, c->QP, c->QP, c->ones, 0, rows, c->atb_ns, c->atb_partial,
+                                  nchunks > 0, last, c->Rm, st, &c->launches))) return rc;
+        } else if (!mode_is_cov(P.mode)) {
+            if ((rc = backproj_diag_generic(P, c->tr, r0, r1, c->H, MP, c->bp_partial, c->nslab, nchunks > 0, st, &c->launches))) return rc;
+        } else {
+            if ((rc = backproj_cov_psi(P, c->tr, r0, r1, c->H, MP, c->bp_partial, c->nslab, nchunks > 0, st, &c->launches))) return rc;
+        }
+        ++nchunks;
+    }
+    if (n == 0) {
+        set_error("no training rows on this rank");
+        return GPZ_ERR_USAGE;
+    }
+    if (!ev4) GPZ_CUDA(cudaEventRecord(c->ev[4], st));
+    if (fast_bp) rc = finalize_moments(P, c->Rm, c->QP, dP, dG, c->scratch, st, &c->launches);
+    else if (!mode_is_cov(P.mode)) rc = backproj_diag_generic_finish(P, c->bp_partial, c->nslab, dP, dG, c->scratch, st, &c->launches);
+    else rc = backproj_cov_psi_finish(P, c->bp_partial, c->nslab, dP, dG, c->scratch, st, &c->launches);
+    if (rc) return rc;
+    colsum_reduce_kernel<<<static_cast<unsigned>(ceil_div(2LL * k * MP, 256)), 256, 0, st>>>(c->colp, c->nslab, 2 * k, static_cast<int>(MP), qcol);
+    GPZ_KERNEL_CHECK();
+    reduce_parts_kernel<<<2 * k + 2, 256, 0, st>>>(c->part2, ceil_div(n, RB), 2 * k + 2, sc2);
+    GPZ_KERNEL_CHECK();
+    c->launches += 2;
+    // validation statistics (GPz.m:239-259): second PHI build on the validation rows
+    if (nv > 0) {
+        for (int64_t r0 = 0; r0 < nv; r0 += c->chunk_rows) {
+            const int64_t r1 = (r0 + c->chunk_rows < nv) ? r0 + c->chunk_rows : nv;
+            const bool need_store = (k > 1) || (mode_is_cov(P.mode) && c->has_psi);
+            DotSpec ds{2, {P.v, c->w}, {c->dotv_va, c->pred_va}};
+            if (k > 1) ds.n = 0;
+            if ((rc = phi_build(P, c->va, r0, r1, need_store ? c->Phi : nullptr, ds, st, &c->launches))) return rc;
+            if (k > 1)
+                for (int o = 0; o < k; ++o)
+                    if ((rc = rowdot(c->Phi, MP, P.m, r1 - r0, DotSpec{2, {P.v + o * MP, c->w + o * MP}, {c->dotv_va + o * nv + r0, c->pred_va + o * nv + r0}}, st, &c->launches))) return rc;
+            for (int o = 0; o < k; ++o) {
+                rowsv_kernel<<<static_cast<unsigned>(ceil_div(r1 - r0, RB)), RB, 0, st>>>(P, o, c->va.Y, c->va.omega, nv, r0, r1, c->dotv_va,
+                                                                                        c->pred_va, c->partv);
+                GPZ_KERNEL_CHECK();
+                ++c->launches;
+            }
+        }
+        reduce_parts_kernel<<<3, 256, 0, st>>>(c->partv, ceil_div(nv, RB), 3, sc2 + 2 * k + 2);
+        GPZ_KERNEL_CHECK();
+        ++c->launches;
+    } else {
+        GPZ_CUDA(cudaMemsetAsync(sc2 + 2 * k + 2, 0, sizeof(double) * 3, st));
+    }
+    if ((rc = allreduce(c, c->red2, c->red2_len))) return rc;
+    FinishArgs fa{P, d_theta, c->w, c->dwda, c->Sinv, c->logdet, c->scal1, c->red2, c->sws.flag,
+                  (nv > 0 || c->world > 1) ? 1 : 0, d_out};
+    finish_kernel<<<1, 256, 0, st>>>(fa);
+    GPZ_KERNEL_CHECK();
+    ++c->launches;
+    GPZ_CUDA(cudaEventRecord(c->ev[5], st));
+    return GPZ_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// exported C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* gpz_last_error(void) { return gpz::g_err; }
+int gpz_version(void) { return 100; }
+
+int64_t gpz_theta_len(const gpz_model* model) {
+    Params P{};
+    if (fill_params(P, model)) return -1;
+    return P.p;
+}
+
+int64_t gpz_g_dim(const gpz_model* model) {
+    Params P{};
+    if (fill_params(P, model)) return -1;
+    return P.g_dim;
+}
+
+int gpz_create(gpz_ctx** out, const gpz_model* model, int64_t n_all, const double* X, const double* Y, const double* Psi,
+               const double* omega, const uint8_t* training, const uint8_t* validation, int device) {
+    if (!out || !X || n_all < 0) {
+        set_error("gpz_create: bad arguments");
+        return GPZ_ERR_USAGE;
+    }
+    *out = nullptr;
+    Params P{};
+    int rc;
+    if ((rc = fill_params(P, model))) return rc;
+    if ((rc = check_device(device))) return rc;
+    gpz_ctx* c = new gpz_ctx();
+    c->P = P;
+    c->device = device;
+    c->has_psi = Psi != nullptr;
+    auto fail = [&](int code) {
+        gpz_destroy(c);
+        return code;
+    };
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("cudaStreamCreate failed");
+        return fail(GPZ_ERR_CUDA);
+    }
+    if ((rc = alloc_params(c->P, c->allocs, c->has_psi))) return fail(rc);
+    std::vector<int64_t> itr, iva;
+    for (int64_t i = 0; i < n_all; ++i) {
+        if (!training || training[i]) itr.push_back(i);
+        if (validation && validation[i]) iva.push_back(i);
+    }
+    if ((rc = upload_rows(c, c->tr, itr, n_all, X, Y, Psi, omega))) return fail(rc);
+    if ((rc = upload_rows(c, c->va, iva, n_all, X, Y, Psi, omega))) return fail(rc);
+    if (mode_is_cov(c->P.mode) && (c->tr.has_nan || c->va.has_nan)) {
+        set_error("covariance modes (GC/VC) with missing inputs (NaN) are not supported yet");
+        return fail(GPZ_ERR_USAGE);
+    }
+    *out = c;
+    return GPZ_OK;
+}
+
+void gpz_destroy(gpz_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->st) cudaStreamSynchronize(c->st);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (void* p : c->allocs) cudaFree(p);
+    solve_ws_free(c->sws);
+    for (auto& e : c->ev)
+        if (e) cudaEventDestroy(e);
+    if (c->h_out) cudaFreeHost(c->h_out);
+    if (c->h_theta) cudaFreeHost(c->h_theta);
+    if (c->st) cudaStreamDestroy(c->st);
+    delete c;
+}
+
+int gpz_comm_unique_id(char id[128]) {
+    int rc;
+    if ((rc = nccl_load())) return rc;
+    ncclUniqueId u;
+    GPZ_NCCL(g_nccl.GetUniqueId(&u));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    memcpy(id, &u, 128);
+    return GPZ_OK;
+}
+
+int gpz_comm_init(gpz_ctx* c, int rank, int world, const char id[128]) {
+    if (!c || world < 1 || rank < 0 || rank >= world) {
+        set_error("gpz_comm_init: bad arguments");
+        return GPZ_ERR_USAGE;
+    }
+    c->rank = rank;
+    c->world = world;
+    if (world == 1) return GPZ_OK;
+    int rc;
+    if ((rc = nccl_load())) return rc;
+    GPZ_CUDA(cudaSetDevice(c->device));
+    ncclUniqueId u;
+    memcpy(&u, id, 128);
+    GPZ_NCCL(g_nccl.CommInitRank(&c->comm, world, u, rank));
+    return GPZ_OK;
+}
+
+int gpz_eval_dev(gpz_ctx* c, const double* d_theta, double* d_out) {
+    if (!c || !d_theta || !d_out) {
+        set_error("gpz_eval_dev: NULL argument");
+        return GPZ_ERR_USAGE;
+    }
+    GPZ_CUDA(cudaSetDevice(c->device));
+    return eval_device(c, d_theta, d_out);
+}
+
+int gpz_eval(gpz_ctx* c, const double* theta, double* nlogML, double* grad, double stats[4]) {
+    if (!c || !theta) {
+        set_error("gpz_eval: NULL argument");
+        return GPZ_ERR_USAGE;
+    }
+    GPZ_CUDA(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure_workspace(c))) return rc;
+    const int64_t p = c->P.p;
+    memcpy(c->h_theta, theta, sizeof(double) * p);
+    GPZ_CUDA(cudaMemcpyAsync(c->d_theta, c->h_theta, sizeof(double) * p, cudaMemcpyHostToDevice, c->st));
+    if ((rc = eval_device(c, c->d_theta, c->d_out))) return rc;
+    GPZ_CUDA(cudaMemcpyAsync(c->h_out, c->d_out, sizeof(double) * (p + 5), cudaMemcpyDeviceToHost, c->st));
+    GPZ_CUDA(cudaStreamSynchronize(c->st));
+    if (nlogML) *nlogML = c->h_out[0];
+    if (grad) memcpy(grad, c->h_out + 1, sizeof(double) * p);
+    if (stats) memcpy(stats, c->h_out + 1 + p, sizeof(double) * 4);
+    return GPZ_OK;
+}
+
+int gpz_fit(gpz_ctx* c, const double* theta, double* nlogML_k, double* w, double* iSigma_w) {
+    if (!c || !theta) {
+        set_error("gpz_fit: NULL argument");
+        return GPZ_ERR_USAGE;
+    }
+    GPZ_CUDA(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure_workspace(c))) return rc;
+    Params& P = c->P;
+    const int64_t p = P.p, MP = P.MP, n = c->tr.n;
+    const int k = P.k;
+    cudaStream_t st = c->st;
+    memcpy(c->h_theta, theta, sizeof(double) * p);
+    GPZ_CUDA(cudaMemcpyAsync(c->d_theta, c->h_theta, sizeof(double) * p, cudaMemcpyHostToDevice, st));
+    if ((rc = forward_and_solve(c, c->d_theta))) return rc;
+    const int64_t m2 = static_cast<int64_t>(P.m) * P.m;
+    nan_fill_kernel<<<static_cast<unsigned>(ceil_div(k * MP * MP, 256)), 256, 0, st>>>(c->Sinv, k * MP * MP, c->sws.flag);
+    nan_fill_kernel<<<static_cast<unsigned>(ceil_div(k * MP, 256)), 256, 0, st>>>(c->w, k * MP, c->sws.flag);
+    GPZ_KERNEL_CHECK();
+    if (nlogML_k) {
+        double* sc2 = c->red2 + static_cast<int64_t>(P.m) * P.d + P.g_dim + 2LL * k * MP;
+        for (int64_t r0 = 0; r0 < n; r0 += c->chunk_rows) {
+            const int64_t r1 = (r0 + c->chunk_rows < n) ? r0 + c->chunk_rows : n;
+            double* phi = nullptr;
+            if ((rc = chunk_phi_and_pred(c, r0, r1, &phi))) return rc;
+            for (int o = 0; o < k; ++o) {
+                rows2_kernel<<<static_cast<unsigned>(ceil_div(r1 - r0, RB)), RB, 0, st>>>(P, o, c->tr.Y, c->tr.omega, n, r0, r1, c->pred, nullptr,
+                                                                                        0, c->lnbi, c->beta, c->ob, c->nu, c->cw, c->dbeta,
+                                                                                        c->part2, 2 * k + 2);
+                GPZ_KERNEL_CHECK();
+                ++c->launches;
+            }
+        }
+        reduce_parts_kernel<<<2 * k + 2, 256, 0, st>>>(c->part2, ceil_div(n > 0 ? n : 1, RB), 2 * k + 2, sc2);
+        GPZ_KERNEL_CHECK();
+        if ((rc = allreduce(c, sc2, 2 * k + 2))) return rc;
+        fit_nl_kernel<<<1, 256, 0, st>>>(P, c->d_theta, c->w, c->logdet, c->scal1, sc2, c->sws.flag, c->d_out);
+        GPZ_KERNEL_CHECK();
+        c->launches += 2;
+        GPZ_CUDA(cudaMemcpyAsync(c->h_out, c->d_out, sizeof(double) * k, cudaMemcpyDeviceToHost, st));
+    }
+    if (w)
+        GPZ_CUDA(cudaMemcpy2DAsync(w, sizeof(double) * P.m, c->w, sizeof(double) * MP, sizeof(double) * P.m, k, cudaMemcpyDeviceToHost, st));
+    if (iSigma_w)
+        for (int o = 0; o < k; ++o)
+            GPZ_CUDA(cudaMemcpy2DAsync(iSigma_w + o * m2, sizeof(double) * P.m, c->Sinv + static_cast<int64_t>(o) * MP * MP, sizeof(double) * MP,
+                                       sizeof(double) * P.m, P.m, cudaMemcpyDeviceToHost, st));
+    GPZ_CUDA(cudaStreamSynchronize(st));
+    if (nlogML_k) memcpy(nlogML_k, c->h_out, sizeof(double) * k);
+    return GPZ_OK;
+}
+
+int64_t gpz_rows(const gpz_ctx* c, int which) { return c ? (which ? c->va.n : c->tr.n) : -1; }
+
+int gpz_phi(gpz_ctx* c, const double* theta, int which, double* PHI, double* lnBeta_i) {
+    if (!c || !theta) {
+        set_error("gpz_phi: NULL argument");
+        return GPZ_ERR_USAGE;
+    }
+    GPZ_CUDA(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure_workspace(c))) return rc;
+    Params& P = c->P;
+    RowData& R = which ? c->va : c->tr;
+    const int64_t n = R.n, MP = P.MP;
+    cudaStream_t st = c->st;
+    if (n == 0) return GPZ_OK;
+    GPZ_CUDA(cudaMemcpyAsync(c->d_theta, theta, sizeof(double) * P.p, cudaMemcpyHostToDevice, st));
+    if ((rc = prep_params(c->d_theta, P, c->has_psi, st, &c->launches))) return rc;
+    double *dotv = nullptr, *colmaj = nullptr;
+    GPZ_CUDA(cudaMalloc(&dotv, sizeof(double) * n * P.k));
+    if (PHI) GPZ_CUDA(cudaMalloc(&colmaj, sizeof(double) * c->chunk_rows * P.m));
+    std::vector<double> hbuf;
+    for (int64_t r0 = 0; r0 < n; r0 += c->chunk_rows) {
+        const int64_t r1 = (r0 + c->chunk_rows < n) ? r0 + c->chunk_rows : n;
+        if ((rc = phi_build(P, R, r0, r1, c->Phi, DotSpec{0, {nullptr, nullptr}, {nullptr, nullptr}}, st, &c->launches))) return rc;
+        if (P.het)
+            for (int o = 0; o < P.k; ++o)
+                if ((rc = rowdot(c->Phi, MP, P.m, r1 - r0, DotSpec{1, {P.v + o * MP, nullptr}, {dotv + o * n + r0, nullptr}}, st, &c->launches))) return rc;
+        if (PHI) {
+            if ((rc = transpose_out(c->Phi, MP, r1 - r0, P.m, colmaj, st))) return rc;
+            // column-major (r1-r0) x m chunk -> rows r0..r1 of the n x m host matrix
+            GPZ_CUDA(cudaMemcpy2DAsync(PHI + r0, sizeof(double) * n, colmaj, sizeof(double) * (r1 - r0), sizeof(double) * (r1 - r0), P.m,
+                                       cudaMemcpyDeviceToHost, st));
+            GPZ_CUDA(cudaStreamSynchronize(st));
+        }
+    }
+    if (lnBeta_i) {
+        hbuf.resize(static_cast<size_t>(n * P.k));
+        std::vector<double> hb(32);
+        if (P.het) GPZ_CUDA(cudaMemcpyAsync(hbuf.data(), dotv, sizeof(double) * n * P.k, cudaMemcpyDeviceToHost, st));
+        GPZ_CUDA(cudaStreamSynchronize(st));
+        for (int o = 0; o < P.k; ++o) {
+            const double b = theta[P.oB + o];
+            for (int64_t i = 0; i < n; ++i) lnBeta_i[o * n + i] = b + (P.het ? hbuf[o * n + i] : 0.0);
+        }
+    }
+    GPZ_CUDA(cudaStreamSynchronize(st));
+    cudaFree(dotv);
+    if (colmaj) cudaFree(colmaj);
+    return GPZ_OK;
+}
+
+int gpz_predict(const gpz_model* model, const double* theta, const double* w, const double* iSigma_w, int64_t n,
+                const double* Xz, const double* Psi, double* mu, double* nu, double* beta_i, double* gamma, double* PHI,
+                int device) {
+    if (!theta || !w || !iSigma_w || !Xz || !mu || !nu || !beta_i || !gamma || n < 0) {
+        set_error("gpz_predict: NULL argument");
+        return GPZ_ERR_USAGE;
+    }
+    Params P{};
+    int rc;
+    if ((rc = fill_params(P, model))) return rc;
+    if ((rc = check_device(device))) return rc;
+    if (Psi && mode_is_cov(P.mode)) {
+        set_error("predictNoisy for covariance modes (predictCov.m:70-133) is not supported yet");
+        return GPZ_ERR_USAGE;
+    }
+    if (n == 0) return GPZ_OK;
+    std::vector<void*> allocs;
+    cudaStream_t st = nullptr;
+    int64_t launches = 0;
+    auto cleanup = [&]() {
+        if (st) {
+            cudaStreamSynchronize(st);
+            cudaStreamDestroy(st);
+        }
+        for (void* p : allocs) cudaFree(p);
+    };
+#define PR(call)             \
+    do {                     \
+        int r__ = (call);    \
+        if (r__) {           \
+            cleanup();       \
+            return r__;      \
+        }                    \
+    } while (0)
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("cudaStreamCreate failed");
+        return GPZ_ERR_CUDA;
+    }
+    const int64_t MP = P.MP;
+    const int k = P.k;
+    PR(alloc_params(P, allocs, 0));
+    double *d_theta, *d_w, *d_Sinv, *d_X, *d_Psi = nullptr, *d_Phi, *d_dotv, *d_mu, *d_nupart, *d_nu, *d_elns, *d_beta, *d_gamma, *d_col = nullptr;
+    PR(dev_alloc(allocs, &d_theta, P.p));
+    PR(dev_alloc(allocs, &d_w, k * MP));
+    PR(dev_alloc(allocs, &d_Sinv, k * MP * MP));
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    int64_t chunk = static_cast<int64_t>(0.4 * static_cast<double>(free_b) / (8.0 * (MP + (PHI ? P.m : 0))));
+    chunk = chunk / 1024 * 1024;
+    if (chunk < 1024) chunk = 1024;
+    if (chunk > n) chunk = n;
+    PR(dev_alloc(allocs, &d_X, n * P.d));
+    if (Psi) PR(dev_alloc(allocs, &d_Psi, n * P.d));
+    PR(dev_alloc(allocs, &d_Phi, chunk * MP));
+    if (PHI) PR(dev_alloc(allocs, &d_col, chunk * P.m));
+    PR(dev_alloc(allocs, &d_dotv, k * n));
+    PR(dev_alloc(allocs, &d_mu, k * n));
+    PR(dev_alloc(allocs, &d_nupart, (MP / TILE) * n));
+    PR(dev_alloc(allocs, &d_nu, k * n));
+    PR(dev_alloc(allocs, &d_elns, k * n));
+    PR(dev_alloc(allocs, &d_beta, k * n));
+    PR(dev_alloc(allocs, &d_gamma, k * n));
+    auto cuda_ok = [&](cudaError_t e, const char* what) -> int {
+        if (e == cudaSuccess) return GPZ_OK;
+        set_error("gpz_predict: %s: %s", what, cudaGetErrorString(e));
+        return (int)GPZ_ERR_CUDA;
+    };
+    PR(cuda_ok(cudaMemcpyAsync(d_theta, theta, sizeof(double) * P.p, cudaMemcpyHostToDevice, st), "H2D theta"));
+    PR(cuda_ok(cudaMemsetAsync(d_w, 0, sizeof(double) * k * MP, st), "memset"));
+    PR(cuda_ok(cudaMemsetAsync(d_Sinv, 0, sizeof(double) * k * MP * MP, st), "memset"));
+    PR(cuda_ok(cudaMemcpy2DAsync(d_w, sizeof(double) * MP, w, sizeof(double) * P.m, sizeof(double) * P.m, k, cudaMemcpyHostToDevice, st), "H2D w"));
+    for (int o = 0; o < k; ++o)
+        PR(cuda_ok(cudaMemcpy2DAsync(d_Sinv + static_cast<int64_t>(o) * MP * MP, sizeof(double) * MP, iSigma_w + static_cast<int64_t>(o) * P.m * P.m,
+                                     sizeof(double) * P.m, sizeof(double) * P.m, P.m, cudaMemcpyHostToDevice, st), "H2D iSigma_w"));
+    PR(cuda_ok(cudaMemcpyAsync(d_X, Xz, sizeof(double) * n * P.d, cudaMemcpyHostToDevice, st), "H2D X"));
+    if (Psi) PR(cuda_ok(cudaMemcpyAsync(d_Psi, Psi, sizeof(double) * n * P.d, cudaMemcpyHostToDevice, st), "H2D Psi"));
+    PR(prep_params(d_theta, P, 0, st, &launches));
+    RowData R;
+    R.n = n;
+    R.X = d_X;
+    R.Psi = d_Psi;
+    {
+        bool has_nan = false;
+        for (int64_t i = 0; i < n * P.d && !has_nan; ++i) has_nan = Xz[i] != Xz[i];
+        if (has_nan) {
+            set_error("gpz_predict: rows with missing inputs (predictMissing, predictDiag.m:127-295) are not supported yet");
+            cleanup();
+            return GPZ_ERR_USAGE;
+        }
+    }
+    for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+        const int64_t r1 = (r0 + chunk < n) ? r0 + chunk : n;
+        DotSpec ds{2, {P.v, d_w}, {d_dotv, d_mu}};
+        if (k > 1) ds.n = 0;
+        PR(phi_build(P, R, r0, r1, d_Phi, ds, st, &launches));
+        if (k > 1)
+            for (int o = 0; o < k; ++o)
+                PR(rowdot(d_Phi, MP, P.m, r1 - r0, DotSpec{2, {P.v + o * MP, d_w + o * MP}, {d_dotv + o * n + r0, d_mu + o * n + r0}}, st, &launches));
+        if (!Psi) {
+            for (int o = 0; o < k; ++o) {
+                PR(tgemm(d_Phi, MP, d_Sinv + static_cast<int64_t>(o) * MP * MP, static_cast<int>(MP), P.m, r1 - r0, nullptr, nullptr, 0,
+                         d_nupart + r0, n, st, &launches));
+                sum_cols_kernel<<<static_cast<unsigned>(ceil_div(r1 - r0, 256)), 256, 0, st>>>(d_nupart + r0, static_cast<int>(MP / TILE), n, r1 - r0, d_nu + o * n + r0);
+            }
+        }
+        if (PHI) {
+            PR(transpose_out(d_Phi, MP, r1 - r0, P.m, d_col, st));
+            PR(cuda_ok(cudaMemcpy2DAsync(PHI + r0, sizeof(double) * n, d_col, sizeof(double) * (r1 - r0), sizeof(double) * (r1 - r0), P.m,
+                                         cudaMemcpyDeviceToHost, st), "D2H PHI"));
+            PR(cuda_ok(cudaStreamSynchronize(st), "sync"));
+        }
+    }
+    exp_rows_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, st>>>(d_dotv, P.bk, P.het, k, n, d_elns, d_beta);
+    PR(cuda_ok(cudaMemsetAsync(d_gamma, 0, sizeof(double) * k * n, st), "memset"));
+    if (Psi) PR(predict_noisy_diag(P, R, d_w, d_Sinv, d_elns, d_mu, d_nu, d_beta, d_gamma, st, &launches));
+    PR(cuda_ok(cudaMemcpyAsync(mu, d_mu, sizeof(double) * k * n, cudaMemcpyDeviceToHost, st), "D2H"));
+    PR(cuda_ok(cudaMemcpyAsync(nu, d_nu, sizeof(double) * k * n, cudaMemcpyDeviceToHost, st), "D2H"));
+    PR(cuda_ok(cudaMemcpyAsync(beta_i, d_beta, sizeof(double) * k * n, cudaMemcpyDeviceToHost, st), "D2H"));
+    PR(cuda_ok(cudaMemcpyAsync(gamma, d_gamma, sizeof(double) * k * n, cudaMemcpyDeviceToHost, st), "D2H"));
+    PR(cuda_ok(cudaStreamSynchronize(st), "sync"));
+    PR(cuda_ok(cudaGetLastError(), "kernel"));
+#undef PR
+    cleanup();
+    return GPZ_OK;
+}
+
+int gpz_inv_logdet(int32_t m, const double* X, double* Xi, double* logdet, int device) {
+    if (m < 1 || !X || !Xi) {
+        set_error("gpz_inv_logdet: bad arguments");
+        return GPZ_ERR_USAGE;
+    }
+    int rc;
+    if ((rc = check_device(device))) return rc;
+    const int64_t MP = round_up(m, TILE);
+    double *S = nullptr, *Si = nullptr, *ld = nullptr;
+    SolveWs ws;
+    cudaStream_t st = nullptr;
+    int64_t launches = 0;
+    GPZ_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    GPZ_CUDA(cudaMalloc(&S, sizeof(double) * MP * MP));
+    GPZ_CUDA(cudaMalloc(&Si, sizeof(double) * MP * MP));
+    GPZ_CUDA(cudaMalloc(&ld, sizeof(double)));
+    if ((rc = solve_ws_alloc(ws, static_cast<int>(MP)))) return rc;
+    GPZ_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * MP * MP, st));
+    GPZ_CUDA(cudaMemsetAsync(ws.flag, 0, sizeof(int), st));
+    GPZ_CUDA(cudaMemcpy2DAsync(S, sizeof(double) * MP, X, sizeof(double) * m, sizeof(double) * m, m, cudaMemcpyHostToDevice, st));
+    rc = spd_inverse(S, m, static_cast<int>(MP), Si, ld, ws, st, &launches);
+    int flag = 0;
+    double hl = 0.0;
+    if (!rc) {
+        GPZ_CUDA(cudaMemcpy2DAsync(Xi, sizeof(double) * m, Si, sizeof(double) * MP, sizeof(double) * m, m, cudaMemcpyDeviceToHost, st));
+        GPZ_CUDA(cudaMemcpyAsync(&hl, ld, sizeof(double), cudaMemcpyDeviceToHost, st));
+        GPZ_CUDA(cudaMemcpyAsync(&flag, ws.flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        GPZ_CUDA(cudaStreamSynchronize(st));
+        if (flag) {
+            const double nan_ = nan("");
+            for (int64_t i = 0; i < static_cast<int64_t>(m) * m; ++i) Xi[i] = nan_;
+            hl = nan_;
+        }
+        if (logdet) *logdet = hl;
+    }
+    cudaFree(S);
+    cudaFree(Si);
+    cudaFree(ld);
+    solve_ws_free(ws);
+    cudaStreamDestroy(st);
+    return rc;
+}
+
+int gpz_dxy(int64_t n, int32_t m, int32_t d, const double* X, const double* Y, double* D, int device) {
+    if (n < 0 || m < 0 || d < 1 || !X || !Y || !D) {
+        set_error("gpz_dxy: bad arguments");
+        return GPZ_ERR_USAGE;
+    }
+    int rc;
+    if ((rc = check_device(device))) return rc;
+    if (n == 0 || m == 0) return GPZ_OK;
+    double *dX = nullptr, *dY = nullptr, *dD = nullptr;
+    GPZ_CUDA(cudaMalloc(&dX, sizeof(double) * n * d));
+    GPZ_CUDA(cudaMalloc(&dY, sizeof(double) * m * d));
+    GPZ_CUDA(cudaMalloc(&dD, sizeof(double) * n * m));
+    GPZ_CUDA(cudaMemcpy(dX, X, sizeof(double) * n * d, cudaMemcpyHostToDevice));
+    GPZ_CUDA(cudaMemcpy(dY, Y, sizeof(double) * m * d, cudaMemcpyHostToDevice));
+    rc = dxy_device(dX, n, dY, m, d, dD, nullptr);
+    if (!rc) GPZ_CUDA(cudaMemcpy(D, dD, sizeof(double) * n * m, cudaMemcpyDeviceToHost));
+    cudaFree(dX);
+    cudaFree(dY);
+    cudaFree(dD);
+    return rc;
+}
+
+void* gpz_stream(gpz_ctx* c) { return c ? static_cast<void*>(c->st) : nullptr; }
+
+int gpz_sync(gpz_ctx* c) {
+    if (!c) return GPZ_ERR_USAGE;
+    GPZ_CUDA(cudaSetDevice(c->device));
+    GPZ_CUDA(cudaStreamSynchronize(c->st));
+    return GPZ_OK;
+}
+
+int64_t gpz_launch_count(const gpz_ctx* c) { return c ? c->launches : -1; }
+
+int gpz_last_timing(gpz_ctx* c, double ms[6]) {
+    if (!c || !c->ws_ready) {
+        set_error("gpz_last_timing: no evaluation yet");
+        return GPZ_ERR_USAGE;
+    }
+    GPZ_CUDA(cudaSetDevice(c->device));
+    GPZ_CUDA(cudaStreamSynchronize(c->st));
+    float t;
+    // ev0 start | ev1 after first PHI build | ev2 after Gram+allreduce | ev3 after solve | ev4 after T-GEMM | ev5 end
+    for (int i = 0; i < 5; ++i) {
+        GPZ_CUDA(cudaEventElapsedTime(&t, c->ev[i], c->ev[i + 1]));
+        ms[i] = t;
+    }
+    GPZ_CUDA(cudaEventElapsedTime(&t, c->ev[0], c->ev[5]));
+    ms[5] = t;
+    return GPZ_OK;
+}
+
+int gpz_set_option(gpz_ctx* c, const char* name, double value) {
+    if (!c || !name) return GPZ_ERR_USAGE;
+    if (strcmp(name, "chunk_rows") == 0) {
+        if (c->ws_ready) {
+            set_error("chunk_rows must be set before the first evaluation");
+            return GPZ_ERR_USAGE;
+        }
+        c->opt_chunk_rows = static_cast<int64_t>(value);
+        return GPZ_OK;
+    }
+    set_error("unknown option '%s'", name);
+    return GPZ_ERR_USAGE;
+}
+
+}  // extern "C"

@@ -1,0 +1,100 @@
+// Internal declarations shared by the translation units of libgpz_b200.
+#pragma once
+#include "../../include/gpz_b200.h"
+#include "common.cuh"
+
+namespace gpz {
+
+enum Mode { GL = 0, VL = 1, GD = 2, VD = 3, GC = 4, VC = 5 };
+__host__ __device__ inline bool mode_is_cov(int mode) { return mode >= GC; }
+
+// theta-derived per-basis parameter arrays (device), rebuilt by prep_params at every call.
+// All [..][MP] arrays are zero-padded in the basis index j >= m.
+struct Params {
+    int d, dp, k, m, MP, mode, het;
+    int64_t g_dim, p;
+    // offsets into theta
+    int64_t oG, oA, oB, oV, oT;
+    double* Pt;     // [d][MP]      P(j,a)
+    double* Gt;     // [d][MP]      diag modes: Gamma(j,a)
+    double* Ct;     // [d][MP]      diag modes: Gamma(j,a)*P(j,a);  cov modes: (Gamma_j p_j)_b
+    double* Gam;    // [d][dp][MP]  cov modes: Gamma_j(b,a) at ((b*dp+a)*MP + j), zero for a>=d
+    double* Aj;     // [d][d][MP]   cov modes: (Gamma_j' Gamma_j)(a,b)  at ((a*d+b)*MP+j)
+    double* Sj;     // [d][d][MP]   cov modes: inverse of Aj (only built when Psi is present)
+    double* lndS;   // [MP]         cov modes: ln det Sigma_j = -ln det Aj
+    double* alpha;  // [k][MP]
+    double* v;      // [k][MP]
+    double* tau;    // [k][MP]
+    double* bk;     // [k]
+};
+
+struct RowData {          // one resident row set (training or validation rows of this rank)
+    int64_t n = 0;
+    double* X = nullptr;      // [d][n]  (column-major n x d)
+    double* Y = nullptr;      // [k][n]
+    double* omega = nullptr;  // [n]
+    double* Psi = nullptr;    // diag: [d][n]; cov: [n][d*d] (MATLAB d x d x n)
+    int has_nan = 0;
+};
+
+struct DotSpec {          // up to 2 fused row-dots  out_q[i] = sum_j PHI_ij vec_q[j]
+    int n;
+    const double* vec[2];
+    double* out[2];
+};
+
+// ---- phi.cu
+int prep_params(const double* d_theta, const Params& P, int need_sigma, cudaStream_t st, int64_t* launches);
+int phi_build(const Params& P, const RowData& R, int64_t r0, int64_t r1, double* Phi /*[rows][MP] at row r0 -> index 0*/,
+              const DotSpec& dots, cudaStream_t st, int64_t* launches);
+int rowdot(const double* Phi, int64_t ld, int m, int64_t n, const DotSpec& dots, cudaStream_t st, int64_t* launches);
+int dxy_device(const double* X, int64_t n, const double* Y, int m, int d, double* D, cudaStream_t st);
+int transpose_out(const double* src_rowmajor, int64_t ld, int64_t n, int m, double* dst_colmajor, cudaStream_t st);
+
+// ---- gemm.cu
+int gram_nsplit(int MP, int sm_count);
+int gram_syrk(const double* Phi, int64_t ld, int MP, const double* wgt, int64_t row0, int64_t row1, int nsplit,
+              double* partial, int accumulate, int reduce, double* S, cudaStream_t st, int64_t* launches);
+int atb_general(const double* A, int64_t lda, int MP, const double* B, int64_t ldb, int QP, const double* wgt,
+                int64_t row0, int64_t row1, int nsplit, double* partial, int accumulate, int reduce, double* R,
+                cudaStream_t st, int64_t* launches);
+int tgemm(const double* Phi, int64_t ld, const double* Sinv, int MP, int m, int64_t n, const double* rw, double* H,
+          int accumulate, double* nupart, int64_t nu_ld, cudaStream_t st, int64_t* launches);
+int sgemm(int M, int N, int K, double alpha, const double* A, int64_t sAi, int64_t sAk, const double* B, int64_t sBk,
+          int64_t sBj, double beta, double* C, int64_t ldc, int lower_only, cudaStream_t st, int64_t* launches);
+
+// ---- solve.cu
+struct SolveWs {
+    double* W = nullptr;      // [MP][MP] L^{-1}
+    double* Linv = nullptr;   // [nb][64*64] inverses of the diagonal blocks
+    double* tmp = nullptr;    // [64][MP]
+    int* flag = nullptr;      // device int: !=0 -> non-positive pivot
+};
+int solve_ws_alloc(SolveWs& ws, int MP);
+void solve_ws_free(SolveWs& ws);
+// S (MP x MP row-major, lower triangle read, overwritten by L) -> Sinv (full symmetric), *d_logdet
+int spd_inverse(double* S, int m, int MP, double* Sinv, double* d_logdet, SolveWs& ws, cudaStream_t st,
+                int64_t* launches);
+
+// ---- backproj.cu
+int build_features(const Params& P, const RowData& R, int64_t r0, int64_t r1, double* F, int QP, cudaStream_t st,
+                   int64_t* launches);
+int feature_count(const Params& P);
+int finalize_moments(const Params& P, const double* Rm /*[MP][QP]*/, int QP, double* dP /*m*d*/, double* dG /*g_dim*/,
+                     double* scratch, cudaStream_t st, int64_t* launches);
+int backproj_diag_generic(const Params& P, const RowData& R, int64_t r0, int64_t r1, const double* dPhi, int64_t ld,
+                          double* partial, int nslab, int accumulate, cudaStream_t st, int64_t* launches);
+int backproj_diag_generic_finish(const Params& P, const double* partial, int nslab, double* dP, double* dG,
+                                 double* scratch, cudaStream_t st, int64_t* launches);
+int backproj_cov_psi(const Params& P, const RowData& R, int64_t r0, int64_t r1, const double* dPhi, int64_t ld,
+                     double* partial, int nslab, int accumulate, cudaStream_t st, int64_t* launches);
+int backproj_cov_psi_finish(const Params& P, const double* partial, int nslab, double* dP, double* dG, double* scratch,
+                            cudaStream_t st, int64_t* launches);
+int64_t backproj_partial_doubles(const Params& P, int nslab, int has_psi, int has_nan);
+
+// ---- predict.cu
+int predict_noisy_diag(const Params& P, const RowData& R, const double* w /*[k][MP]*/, const double* Sinv /*[k][MP][MP]*/,
+                       const double* ElnS /*[k][n] = b + PHI v*/, const double* mu /*[k][n]*/, double* nu, double* beta_i,
+                       double* gamma, cudaStream_t st, int64_t* launches);
+
+}  // namespace gpz

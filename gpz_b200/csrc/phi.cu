@@ -1,0 +1,422 @@
+// Design-matrix kernels: PHI = exp(lnPHI) for the six covariance modes (GPz/getPHI.m:60-113), the
+// fused ln-noise row-dots (getPHI.m:116-125), theta unpacking (getPHI.m:24-40) and Dxy (Dxy.m:3-7).
+//
+// Layout: X is [d][n] (MATLAB column-major n x d, coalesced over rows), PHI is row-major [n][MP]
+// (basis index fastest, zero in the padded columns j >= m), per-basis parameters are [..][MP].
+// A warp owns RT rows and sweeps the bases 64 at a time (2 per lane), so PHI is written with
+// 16-byte stores, 512 contiguous bytes per warp and row, and the row-dots PHI_i.v / PHI_i.w
+// are finished inside the warp with shuffles.
+#include "internal.cuh"
+#include "smallmat.cuh"
+
+namespace gpz {
+
+constexpr double kLn2 = 0.69314718055994530942;
+
+// ------------------------------------------------------------------------------------------------
+// theta -> per-basis arrays
+// ------------------------------------------------------------------------------------------------
+__global__ void prep_kernel(const double* __restrict__ th, Params P, int need_sigma) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.MP) return;
+    const int d = P.d, m = P.m, MP = P.MP, k = P.k, dp = P.dp;
+    const bool live = j < m;
+    const double* thG = th + P.oG;
+    for (int a = 0; a < d; ++a) P.Pt[a * MP + j] = live ? th[a * m + j] : 0.0;
+    if (!mode_is_cov(P.mode)) {
+        for (int a = 0; a < d; ++a) {
+            double gv = 0.0;
+            if (live) {
+                switch (P.mode) {
+                    case GL: gv = thG[0]; break;
+                    case VL: gv = thG[j]; break;
+                    case GD: gv = thG[a]; break;
+                    default: gv = thG[a * m + j]; break;     // VD: Gamma(j,a), column-major m x d
+                }
+            }
+            P.Gt[a * MP + j] = gv;
+            P.Ct[a * MP + j] = live ? gv * th[a * m + j] : 0.0;
+        }
+    } else {
+        const double* G = (P.mode == GC) ? thG : thG + static_cast<int64_t>(d) * d * j;   // Gamma_j(b,a) = G[b + a*d]
+        for (int b = 0; b < d; ++b) {
+            double c = 0.0;
+            for (int a = 0; a < dp; ++a) {
+                const double gv = (live && a < d) ? G[b + a * d] : 0.0;
+                P.Gam[(static_cast<int64_t>(b) * dp + a) * MP + j] = gv;
+                if (live && a < d) c += gv * th[a * m + j];
+            }
+            P.Ct[b * MP + j] = c;
+        }
+        for (int a = 0; a < d; ++a)
+            for (int b = 0; b < d; ++b) {
+                double s = 0.0;
+                if (live)
+                    for (int c = 0; c < d; ++c) s += G[c + a * d] * G[c + b * d];
+                P.Aj[(static_cast<int64_t>(a) * d + b) * MP + j] = live ? s : (a == b ? 1.0 : 0.0);
+            }
+        if (need_sigma) {
+            StridedMat S{P.Sj + j, MP, d};
+            StridedMat A{P.Aj + j, MP, d};
+            for (int a = 0; a < d; ++a)
+                for (int b = 0; b < d; ++b) S(a, b) = A(a, b);
+            double hl = 0.0;
+            const bool ok = spd_inv(S, d, &hl);
+            P.lndS[j] = ok ? -2.0 * hl : nan("");
+        }
+    }
+    for (int o = 0; o < k; ++o) {
+        P.alpha[o * MP + j] = live ? exp(th[P.oA + static_cast<int64_t>(o) * m + j]) : 1.0;
+        if (P.het) {
+            P.v[o * MP + j] = live ? th[P.oV + static_cast<int64_t>(o) * m + j] : 0.0;
+            P.tau[o * MP + j] = live ? exp(th[P.oT + static_cast<int64_t>(o) * m + j]) : 0.0;
+        } else {
+            P.v[o * MP + j] = 0.0;
+            P.tau[o * MP + j] = 0.0;
+        }
+    }
+    if (j < k) P.bk[j] = th[P.oB + j];
+}
+
+int prep_params(const double* d_theta, const Params& P, int need_sigma, cudaStream_t st, int64_t* launches) {
+    prep_kernel<<<static_cast<unsigned>(ceil_div(P.MP, 128)), 128, 0, st>>>(d_theta, P, need_sigma);
+    GPZ_KERNEL_CHECK();
+    ++*launches;
+    return GPZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// PHI build
+// ------------------------------------------------------------------------------------------------
+constexpr int PHI_RT = 8;            // rows per warp
+constexpr int PHI_WARPS = 8;
+constexpr int PHI_ROWS = PHI_RT * PHI_WARPS;   // rows per CTA
+
+// KIND 0: diag modes, no Psi, no NaN   lnPHI = -1/2 sum_a (g x - g p)^2            getPHI.m:93-98
+// KIND 1: diag modes, generic (NaN aware, optional Psi)                             getPHI.m:93-105
+// KIND 2: cov modes, no Psi, no NaN    lnPHI = -1/2 |Gamma_j x - Gamma_j p|^2       getPHI.m:73-77
+template <int KIND, bool PSI>
+__global__ void __launch_bounds__(PHI_WARPS * 32)
+phi_kernel(Params P, const double* __restrict__ X, const double* __restrict__ Psi, int64_t n, int64_t r0, int64_t r1,
+           double* __restrict__ Phi, DotSpec dots) {
+    extern __shared__ __align__(16) double sm[];
+    const int d = P.d, dp = P.dp, MP = P.MP, m = P.m;
+    double* xs = sm;                          // [PHI_ROWS][dp]   (row-major so x pairs are 16-byte loads)
+    double* ps = xs + PHI_ROWS * dp;          // [PHI_ROWS][dp]   Psi rows (KIND 1 with PSI)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t rb = r0 + static_cast<int64_t>(blockIdx.x) * PHI_ROWS;
+
+    for (int e = tid; e < PHI_ROWS * dp; e += blockDim.x) {
+        const int a = e / PHI_ROWS, r = e % PHI_ROWS;       // consecutive threads -> consecutive rows (coalesced)
+        const int64_t gi = rb + r;
+        double xv = 0.0, pv = 0.0;
+        if (gi < r1 && a < d) {
+            xv = X[a * n + gi];
+            if (PSI) pv = Psi[a * n + gi];
+        }
+        xs[r * dp + a] = xv;
+        if (PSI) ps[r * dp + a] = pv;
+    }
+    __syncthreads();
+
+    const int rw = warp * PHI_RT;
+    double dot[PHI_RT][2];
+#pragma unroll
+    for (int r = 0; r < PHI_RT; ++r) dot[r][0] = dot[r][1] = 0.0;
+
+    for (int jc = 0; jc < MP; jc += 64) {
+        const int j = jc + 2 * lane;
+        double acc[PHI_RT][2];
+#pragma unroll
+        for (int r = 0; r < PHI_RT; ++r) acc[r][0] = acc[r][1] = 0.0;
+
+        if (KIND == 0) {
+            for (int a = 0; a < d; ++a) {
+                const double2 gv = __ldg(reinterpret_cast<const double2*>(P.Gt + a * MP + j));
+                const double2 cv = __ldg(reinterpret_cast<const double2*>(P.Ct + a * MP + j));
+#pragma unroll
+                for (int r = 0; r < PHI_RT; ++r) {
+                    const double x = xs[(rw + r) * dp + a];
+                    const double y0 = fma(gv.x, x, -cv.x), y1 = fma(gv.y, x, -cv.y);
+                    acc[r][0] = fma(y0, y0, acc[r][0]);
+                    acc[r][1] = fma(y1, y1, acc[r][1]);
+                }
+            }
+        } else if (KIND == 1) {
+            double lg[PHI_RT][2], pr[PHI_RT][2];
+#pragma unroll
+            for (int r = 0; r < PHI_RT; ++r) { lg[r][0] = lg[r][1] = 0.0; pr[r][0] = pr[r][1] = 1.0; }
+            for (int a = 0; a < d; ++a) {
+                const double2 gv = __ldg(reinterpret_cast<const double2*>(P.Gt + a * MP + j));
+                const double2 pv = __ldg(reinterpret_cast<const double2*>(P.Pt + a * MP + j));
+                const double g0 = gv.x * gv.x, g1 = gv.y * gv.y;
+#pragma unroll
+                for (int r = 0; r < PHI_RT; ++r) {
+                    const double x = xs[(rw + r) * dp + a];
+                    if (x != x) {                 // missing dim: no distance term, -1/2 ln2 (getPHI.m:97)
+                        lg[r][0] += kLn2;
+                        lg[r][1] += kLn2;
+                        continue;
+                    }
+                    const double d0 = x - pv.x, d1 = x - pv.y;
+                    if (PSI) {
+                        const double psi = ps[(rw + r) * dp + a];
+                        const double s0 = fma(psi, g0, 1.0), s1 = fma(psi, g1, 1.0);   // 1 + Psi/Sigma
+                        acc[r][0] += d0 * d0 * g0 / s0;
+                        acc[r][1] += d1 * d1 * g1 / s1;
+                        pr[r][0] *= s0;
+                        pr[r][1] *= s1;
+                    } else {
+                        acc[r][0] = fma(d0 * d0, g0, acc[r][0]);
+                        acc[r][1] = fma(d1 * d1, g1, acc[r][1]);
+                    }
+                }
+                if (PSI && ((a & 7) == 7 || a == d - 1)) {       // fold the product before it can overflow
+#pragma unroll
+                    for (int r = 0; r < PHI_RT; ++r) {
+                        lg[r][0] += log(pr[r][0]);
+                        lg[r][1] += log(pr[r][1]);
+                        pr[r][0] = pr[r][1] = 1.0;
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < PHI_RT; ++r) { acc[r][0] += lg[r][0]; acc[r][1] += lg[r][1]; }
+        } else {
+            for (int b = 0; b < d; ++b) {
+                const double2 cv = __ldg(reinterpret_cast<const double2*>(P.Ct + b * MP + j));
+                double s[PHI_RT][2];
+#pragma unroll
+                for (int r = 0; r < PHI_RT; ++r) { s[r][0] = -cv.x; s[r][1] = -cv.y; }
+                for (int a = 0; a < dp; a += 2) {
+                    const double2 ga = __ldg(reinterpret_cast<const double2*>(P.Gam + (static_cast<int64_t>(b) * dp + a) * MP + j));
+                    const double2 gb = __ldg(reinterpret_cast<const double2*>(P.Gam + (static_cast<int64_t>(b) * dp + a + 1) * MP + j));
+#pragma unroll
+                    for (int r = 0; r < PHI_RT; ++r) {
+                        const double2 xx = *reinterpret_cast<const double2*>(xs + (rw + r) * dp + a);
+                        s[r][0] = fma(ga.x, xx.x, s[r][0]);
+                        s[r][1] = fma(ga.y, xx.x, s[r][1]);
+                        s[r][0] = fma(gb.x, xx.y, s[r][0]);
+                        s[r][1] = fma(gb.y, xx.y, s[r][1]);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < PHI_RT; ++r) {
+                    acc[r][0] = fma(s[r][0], s[r][0], acc[r][0]);
+                    acc[r][1] = fma(s[r][1], s[r][1], acc[r][1]);
+                }
+            }
+        }
+
+        double2 v0 = make_double2(0.0, 0.0), v1 = make_double2(0.0, 0.0);
+        if (dots.n > 0) v0 = __ldg(reinterpret_cast<const double2*>(dots.vec[0] + j));
+        if (dots.n > 1) v1 = __ldg(reinterpret_cast<const double2*>(dots.vec[1] + j));
+#pragma unroll
+        for (int r = 0; r < PHI_RT; ++r) {
+            const int64_t gi = rb + rw + r;
+            const double p0 = (j < m) ? exp(-0.5 * acc[r][0]) : 0.0;
+            const double p1 = (j + 1 < m) ? exp(-0.5 * acc[r][1]) : 0.0;
+            if (Phi != nullptr && gi < r1)
+                *reinterpret_cast<double2*>(Phi + (gi - r0) * MP + j) = make_double2(p0, p1);
+            dot[r][0] = fma(p0, v0.x, fma(p1, v0.y, dot[r][0]));
+            dot[r][1] = fma(p0, v1.x, fma(p1, v1.y, dot[r][1]));
+        }
+    }
+    if (dots.n > 0) {
+#pragma unroll
+        for (int r = 0; r < PHI_RT; ++r) {
+            const double s0 = warp_sum(dot[r][0]);
+            const double s1 = warp_sum(dot[r][1]);
+            const int64_t gi = rb + rw + r;
+            if (lane == 0 && gi < r1) {
+                dots.out[0][gi] = s0;
+                if (dots.n > 1) dots.out[1][gi] = s1;
+            }
+        }
+    }
+}
+
+// cov modes + Psi: one thread per (sample, basis) pair                                getPHI.m:80-88
+//   lnPHI = -1/2 D (Psi_i+Sigma_j)^{-1} D' + 1/2 ln|Sigma_j| - 1/2 ln|Psi_i+Sigma_j|
+template <int DMAX>
+__global__ void __launch_bounds__(128)
+phi_cov_psi_kernel(Params P, const double* __restrict__ X, const double* __restrict__ Psi, int64_t n, int64_t r0,
+                   int64_t r1, double* __restrict__ Phi) {
+    const int d = P.d, MP = P.MP, m = P.m;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gi = r0 + blockIdx.y;
+    if (j >= MP || gi >= r1) return;
+    double val = 0.0;
+    if (j < m) {
+        double S[DMAX * DMAX];
+        double z[DMAX];
+        LocalMat Sm{S, d};
+        const double* psi = Psi + gi * d * d;
+        for (int a = 0; a < d; ++a) {
+            for (int b = 0; b <= a; ++b) Sm(a, b) = psi[a + b * d] + P.Sj[(static_cast<int64_t>(a) * d + b) * MP + j];
+            z[a] = X[a * n + gi] - P.Pt[a * MP + j];
+        }
+        double hl = 0.0;
+        if (chol_lower(Sm, d, &hl)) {
+            double q = 0.0;
+            for (int a = 0; a < d; ++a) {          // forward substitution L y = Delta
+                double s = z[a];
+                for (int b = 0; b < a; ++b) s -= Sm(a, b) * z[b];
+                s /= Sm(a, a);
+                z[a] = s;
+                q += s * s;
+            }
+            val = exp(-0.5 * q + 0.5 * P.lndS[j] - hl);
+        } else {
+            val = nan("");
+        }
+    }
+    if (Phi != nullptr) Phi[(gi - r0) * MP + j] = val;
+}
+
+template <int KIND, bool PSI>
+static int launch_phi(const Params& P, const RowData& R, int64_t r0, int64_t r1, double* Phi, const DotSpec& dots,
+                      cudaStream_t st) {
+    const size_t smem = sizeof(double) * PHI_ROWS * P.dp * 2;
+    if (smem > 48 * 1024) {
+        static bool done = false;
+        if (!done) {
+            GPZ_CUDA(cudaFuncSetAttribute(phi_kernel<KIND, PSI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            done = true;
+        }
+    }
+    const int64_t nblk = ceil_div(r1 - r0, PHI_ROWS);
+    phi_kernel<KIND, PSI><<<static_cast<unsigned>(nblk), PHI_WARPS * 32, smem, st>>>(P, R.X, R.Psi, R.n, r0, r1, Phi, dots);
+    GPZ_KERNEL_CHECK();
+    return GPZ_OK;
+}
+
+int phi_build(const Params& P, const RowData& R, int64_t r0, int64_t r1, double* Phi, const DotSpec& dots,
+              cudaStream_t st, int64_t* launches) {
+    if (r1 <= r0) return GPZ_OK;
+    int rc = GPZ_OK;
+    const bool psi = R.Psi != nullptr;
+    if (!mode_is_cov(P.mode)) {
+        if (!psi && !R.has_nan) rc = launch_phi<0, false>(P, R, r0, r1, Phi, dots, st);
+        else if (!psi) rc = launch_phi<1, false>(P, R, r0, r1, Phi, dots, st);
+        else rc = launch_phi<1, true>(P, R, r0, r1, Phi, dots, st);
+        ++*launches;
+        return rc;
+    }
+    if (R.has_nan) {
+        set_error("covariance modes (GC/VC) with missing inputs (NaN) are not supported yet");
+        return GPZ_ERR_USAGE;
+    }
+    if (!psi) {
+        rc = launch_phi<2, false>(P, R, r0, r1, Phi, dots, st);
+        ++*launches;
+        return rc;
+    }
+    if (Phi == nullptr) {
+        set_error("phi_build: cov+Psi needs a PHI buffer");
+        return GPZ_ERR_USAGE;
+    }
+    const int64_t rows = r1 - r0;
+    for (int64_t c0 = 0; c0 < rows; c0 += 65535) {     // gridDim.y limit
+        const int64_t c1 = (c0 + 65535 < rows) ? c0 + 65535 : rows;
+        dim3 grid(static_cast<unsigned>(ceil_div(P.MP, 128)), static_cast<unsigned>(c1 - c0));
+        double* out = Phi + c0 * P.MP;
+        if (P.d <= 8) phi_cov_psi_kernel<8><<<grid, 128, 0, st>>>(P, R.X, R.Psi, R.n, r0 + c0, r0 + c1, out);
+        else if (P.d <= 16) phi_cov_psi_kernel<16><<<grid, 128, 0, st>>>(P, R.X, R.Psi, R.n, r0 + c0, r0 + c1, out);
+        else phi_cov_psi_kernel<32><<<grid, 128, 0, st>>>(P, R.X, R.Psi, R.n, r0 + c0, r0 + c1, out);
+        GPZ_KERNEL_CHECK();
+        ++*launches;
+    }
+    if (dots.n > 0) return rowdot(Phi, P.MP, P.m, rows, DotSpec{dots.n, {dots.vec[0], dots.vec[1]},
+                                  {dots.out[0] + r0, dots.n > 1 ? dots.out[1] + r0 : nullptr}}, st, launches);
+    return GPZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// row dots on a stored PHI: out_q[i] = sum_j PHI[i][j] vec_q[j]   (warp per row)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rowdot_kernel(const double* __restrict__ Phi, int64_t ld, int m, int64_t n, DotSpec dots) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (i >= n) return;
+    double s0 = 0.0, s1 = 0.0;
+    const double* row = Phi + i * ld;
+    for (int j = 2 * lane; j < m; j += 64) {
+        const double2 p = *reinterpret_cast<const double2*>(row + j);      // padded columns are zero
+        const double2 a = __ldg(reinterpret_cast<const double2*>(dots.vec[0] + j));
+        s0 = fma(p.x, a.x, fma(p.y, a.y, s0));
+        if (dots.n > 1) {
+            const double2 b = __ldg(reinterpret_cast<const double2*>(dots.vec[1] + j));
+            s1 = fma(p.x, b.x, fma(p.y, b.y, s1));
+        }
+    }
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    if (lane == 0) {
+        dots.out[0][i] = s0;
+        if (dots.n > 1) dots.out[1][i] = s1;
+    }
+}
+
+int rowdot(const double* Phi, int64_t ld, int m, int64_t n, const DotSpec& dots, cudaStream_t st, int64_t* launches) {
+    if (n <= 0 || dots.n <= 0) return GPZ_OK;
+    rowdot_kernel<<<static_cast<unsigned>(ceil_div(n, 8)), 256, 0, st>>>(Phi, ld, m, n, dots);
+    GPZ_KERNEL_CHECK();
+    ++*launches;
+    return GPZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dxy (Dxy.m:3-7): D = | xx + yy - 2 X Y' |, column-major n x m output
+// ------------------------------------------------------------------------------------------------
+__global__ void dxy_kernel(const double* __restrict__ X, int64_t n, const double* __restrict__ Y, int m, int d,
+                           double* __restrict__ D) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i >= n) return;
+    double xx = 0.0, yy = 0.0, xy = 0.0;
+    for (int a = 0; a < d; ++a) {
+        const double x = X[a * n + i], y = Y[a * m + j];
+        xx = fma(x, x, xx);
+        yy = fma(y, y, yy);
+        xy = fma(x, y, xy);
+    }
+    D[static_cast<int64_t>(j) * n + i] = fabs(yy + (xx - 2.0 * xy));
+}
+
+int dxy_device(const double* X, int64_t n, const double* Y, int m, int d, double* D, cudaStream_t st) {
+    if (n <= 0 || m <= 0) return GPZ_OK;
+    dim3 grid(static_cast<unsigned>(ceil_div(n, 256)), static_cast<unsigned>(m));
+    dxy_kernel<<<grid, 256, 0, st>>>(X, n, Y, m, d, D);
+    GPZ_KERNEL_CHECK();
+    return GPZ_OK;
+}
+
+// row-major [n][ld] -> column-major n x m (MATLAB) through a 32x32 smem tile
+__global__ void transpose_kernel(const double* __restrict__ src, int64_t ld, int64_t n, int m, double* __restrict__ dst) {
+    __shared__ double tile[32][33];
+    const int64_t i0 = static_cast<int64_t>(blockIdx.x) * 32;
+    const int j0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int64_t i = i0 + r;
+        const int j = j0 + threadIdx.x;
+        tile[r][threadIdx.x] = (i < n && j < m) ? src[i * ld + j] : 0.0;
+    }
+    __syncthreads();
+    for (int c = threadIdx.y; c < 32; c += 8) {
+        const int j = j0 + c;
+        const int64_t i = i0 + threadIdx.x;
+        if (i < n && j < m) dst[static_cast<int64_t>(j) * n + i] = tile[threadIdx.x][c];
+    }
+}
+
+int transpose_out(const double* src, int64_t ld, int64_t n, int m, double* dst, cudaStream_t st) {
+    if (n <= 0 || m <= 0) return GPZ_OK;
+    dim3 grid(static_cast<unsigned>(ceil_div(n, 32)), static_cast<unsigned>(ceil_div(m, 32)));
+    transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(src, ld, n, m, dst);
+    GPZ_KERNEL_CHECK();
+    return GPZ_OK;
+}
+
+}  // namespace gpz

@@ -1,0 +1,166 @@
+// m x m SPD solve of the hot path: SIGMA^{-1} and ln det SIGMA (GPz/inv_logdet.m:1-15, called at
+// GPz/GPz.m:67).  The reference pseudo-inverts by SVD; SIGMA = PHI' W PHI + diag(alpha) is SPD by
+// construction (alpha > 0), so this is a blocked right-looking Cholesky (64-wide panels: diagonal
+// block factored and inverted by one CTA in shared memory, panel solve and trailing update as DMMA
+// GEMMs), a blocked triangular inverse and one W'W product.  A non-positive pivot raises a device
+// flag; the caller turns that into NaN outputs (SURVEY.md 8b "error convention", H3).
+#include "internal.cuh"
+
+namespace gpz {
+
+constexpr int NB = 64;
+
+// factor the nb x nb diagonal block at (k0,k0) in place (lower), invert the factor into Linv (row-major
+// 64 x 64, zero upper triangle), accumulate logdet
+__global__ void __launch_bounds__(256)
+potf2_trti_kernel(double* __restrict__ S, int64_t ld, int k0, int nb, double* __restrict__ Linv,
+                  double* __restrict__ logdet, int* __restrict__ flag, int first) {
+    extern __shared__ double sm_potf[];
+    double (*A)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm_potf);
+    double (*W)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm_potf + NB * (NB + 1));
+    __shared__ int bad;
+    const int tid = threadIdx.x;
+    if (tid == 0) bad = 0;
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int r = e / NB, c = e % NB;
+        A[r][c] = (r < nb && c < nb && c <= r) ? S[static_cast<int64_t>(k0 + r) * ld + k0 + c] : (r == c ? 1.0 : 0.0);
+        W[r][c] = 0.0;
+    }
+    __syncthreads();
+    double ld_acc = 0.0;
+    for (int c = 0; c < nb; ++c) {
+        const double piv = A[c][c];
+        if (!(piv > 0.0)) {
+            if (tid == 0) bad = 1;
+            __syncthreads();
+            break;
+        }
+        const double l = sqrt(piv);
+        ld_acc += 2.0 * log(l);
+        __syncthreads();                       // everyone has read the pivot
+        if (tid == 0) A[c][c] = l;
+        for (int r = c + 1 + tid; r < nb; r += 256) A[r][c] /= l;
+        __syncthreads();
+        // trailing update of the lower triangle: A[r][q] -= A[r][c]*A[q][c], r >= q > c
+        const int rem = nb - c - 1;
+        for (int e = tid; e < rem * rem; e += 256) {
+            const int r = c + 1 + e / rem, q = c + 1 + e % rem;
+            if (q <= r) A[r][q] -= A[r][c] * A[q][c];
+        }
+        __syncthreads();
+    }
+    if (bad) {
+        if (tid == 0) *flag = 1;
+        return;
+    }
+    // W = A^{-1} (lower): thread j solves column j by forward substitution
+    if (tid < nb) {
+        const int j = tid;
+        W[j][j] = 1.0 / A[j][j];
+        for (int r = j + 1; r < nb; ++r) {
+            double s = 0.0;
+            for (int q = j; q < r; ++q) s += A[r][q] * W[q][j];
+            W[r][j] = -s / A[r][r];
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int r = e / NB, c = e % NB;
+        Linv[e] = (r < nb && c < nb) ? W[r][c] : 0.0;
+        if (r < nb && c < nb && c <= r) S[static_cast<int64_t>(k0 + r) * ld + k0 + c] = A[r][c];
+    }
+    if (tid == 0) *logdet = (first ? 0.0 : *logdet) + ld_acc;
+}
+
+__global__ void zero_kernel(double* p, int64_t n) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0.0;
+}
+
+// copy the 64x64 inverse diagonal blocks into W
+__global__ void place_diag_kernel(const double* __restrict__ Linv, double* __restrict__ W, int64_t ld, int m) {
+    const int b = blockIdx.x;
+    for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+        const int r = e / NB, c = e % NB;
+        const int gr = b * NB + r, gc = b * NB + c;
+        if (gr < m && gc < m) W[static_cast<int64_t>(gr) * ld + gc] = Linv[static_cast<int64_t>(b) * NB * NB + e];
+    }
+}
+
+int solve_ws_alloc(SolveWs& ws, int MP) {
+    const int nblk = MP / NB;
+    GPZ_CUDA(cudaMalloc(&ws.W, sizeof(double) * MP * MP));
+    GPZ_CUDA(cudaMalloc(&ws.Linv, sizeof(double) * nblk * NB * NB));
+    GPZ_CUDA(cudaMalloc(&ws.tmp, sizeof(double) * NB * MP));
+    GPZ_CUDA(cudaMalloc(&ws.flag, sizeof(int)));
+    return GPZ_OK;
+}
+
+void solve_ws_free(SolveWs& ws) {
+    cudaFree(ws.W);
+    cudaFree(ws.Linv);
+    cudaFree(ws.tmp);
+    cudaFree(ws.flag);
+    ws = SolveWs();
+}
+
+int spd_inverse(double* S, int m, int MP, double* Sinv, double* d_logdet, SolveWs& ws, cudaStream_t st,
+                int64_t* launches) {
+    const int nblk = static_cast<int>(ceil_div(m, NB));
+    const int64_t ld = MP;
+    int rc;
+    constexpr size_t kPotfSmem = sizeof(double) * 2 * NB * (NB + 1);
+    static bool configured = false;
+    if (!configured) {
+        GPZ_CUDA(cudaFuncSetAttribute(potf2_trti_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kPotfSmem)));
+        configured = true;
+    }
+    // ---- blocked Cholesky: S(lower) <- L
+    for (int kb = 0; kb < nblk; ++kb) {
+        const int k0 = kb * NB;
+        const int nb = (m - k0 < NB) ? (m - k0) : NB;
+        double* Lk = ws.Linv + static_cast<int64_t>(kb) * NB * NB;
+        potf2_trti_kernel<<<1, 256, kPotfSmem, st>>>(S, ld, k0, nb, Lk, d_logdet, ws.flag, kb == 0);
+        GPZ_KERNEL_CHECK();
+        ++*launches;
+        const int rem = m - k0 - nb;
+        if (rem > 0) {
+            double* panel = S + static_cast<int64_t>(k0 + nb) * ld + k0;
+            // L_ik = A_ik * Linv_kk'   (B(k,j) = Linv[j][k])
+            rc = sgemm(rem, nb, nb, 1.0, panel, ld, 1, Lk, 1, NB, 0.0, panel, ld, 0, st, launches);
+            if (rc) return rc;
+            // trailing: A_ij -= L_ik L_jk'  (lower tiles only)
+            double* trail = S + static_cast<int64_t>(k0 + nb) * ld + (k0 + nb);
+            rc = sgemm(rem, rem, nb, -1.0, panel, ld, 1, panel, 1, ld, 1.0, trail, ld, 1, st, launches);
+            if (rc) return rc;
+        }
+    }
+    // ---- W = L^{-1} (lower triangular), block row by block row
+    zero_kernel<<<static_cast<unsigned>(ceil_div(static_cast<int64_t>(MP) * MP, 256)), 256, 0, st>>>(
+        ws.W, static_cast<int64_t>(MP) * MP);
+    GPZ_KERNEL_CHECK();
+    ++*launches;
+    place_diag_kernel<<<nblk, 256, 0, st>>>(ws.Linv, ws.W, ld, m);
+    GPZ_KERNEL_CHECK();
+    ++*launches;
+    for (int ib = 1; ib < nblk; ++ib) {
+        const int i0 = ib * NB;
+        const int nb = (m - i0 < NB) ? (m - i0) : NB;
+        // tmp(nb x i0) = L[i0:i0+nb, 0:i0] * W[0:i0, 0:i0]
+        rc = sgemm(nb, i0, i0, 1.0, S + static_cast<int64_t>(i0) * ld, ld, 1, ws.W, ld, 1, 0.0, ws.tmp, ld, 0, st, launches);
+        if (rc) return rc;
+        // W[i0:i0+nb, 0:i0] = -Linv_ii * tmp
+        rc = sgemm(nb, i0, nb, -1.0, ws.Linv + static_cast<int64_t>(ib) * NB * NB, NB, 1, ws.tmp, ld, 1, 0.0,
+                   ws.W + static_cast<int64_t>(i0) * ld, ld, 0, st, launches);
+        if (rc) return rc;
+    }
+    // ---- Sinv = W' W (full symmetric): A(i,k) = W[k][i], B(k,j) = W[k][j]
+    zero_kernel<<<static_cast<unsigned>(ceil_div(static_cast<int64_t>(MP) * MP, 256)), 256, 0, st>>>(
+        Sinv, static_cast<int64_t>(MP) * MP);
+    GPZ_KERNEL_CHECK();
+    ++*launches;
+    rc = sgemm(m, m, m, 1.0, ws.W, 1, ld, ws.W, ld, 1, 0.0, Sinv, ld, 0, st, launches);
+    return rc;
+}
+
+}  // namespace gpz

@@ -1,0 +1,126 @@
+/*
+ * gpz_b200.h -- C ABI of libgpz_b200.so: the B200 (sm_100a) implementation of GPz's
+ * marginal-likelihood objective / gradient / fit / predict hot path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI for this path (it is
+ * pure MATLAB); the plug point is the closure
+ *     f = @(params) GPz(params,model,X,Y,Psi,omega,training,validation)      GPz/train.m:40, GPz/init.m:89
+ * and the only FFI precedent in the tree is the MEX gateway convention of
+ *     minFunc_2012/minFunc/mex/lbfgsProdC.c:7-44   (mexFunction, mxGetPr in, mxCreateDoubleMatrix out).
+ * Each entry point below names the reference function (file:line) it replaces.  The MEX gateway a
+ * maintainer adds on the MATLAB side is matlab/gpz_b200_mex.cpp.
+ *
+ * Conventions
+ *   - all matrices are fp64, COLUMN-MAJOR (MATLAB layout), passed as plain host pointers unless
+ *     the function name ends in _dev; the library never writes to its inputs and keeps no host
+ *     pointer after a call returns (the dataset is copied to the device in gpz_create);
+ *   - X is already z-scored, Y centred and Psi normalised by fixPsi (GPz/train.m:30-38);
+ *   - NaN in X means "missing" (GPz/getPHI.m:43-54);
+ *   - return value: 0 = ok.  Numerical trouble (a non-positive Cholesky pivot of SIGMA) is NOT an
+ *     error: the call returns 0 and the outputs are NaN, which minFunc's isLegal tests handle
+ *     (minFunc_2012/minFunc/WolfeLineSearch.m:53).  Non-zero = usage / CUDA / NCCL error; the text is
+ *     in gpz_last_error().
+ *   - single caller: one host thread per context (MATLAB calls MEX serially).
+ *   - there is NO CPU fallback: every entry point needs a CUDA device of compute capability 10.x.
+ */
+#ifndef GPZ_B200_H
+#define GPZ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gpz_ctx gpz_ctx;
+
+/* model struct fields that parameterise the kernels (GPz/init.m:16-20,86) */
+typedef struct gpz_model {
+    int32_t d;                /* input dimension                                  */
+    int32_t k;                /* number of outputs                                */
+    int32_t m;                /* number of basis functions                        */
+    char    method[4];        /* "GL","VL","GD","VD","GC","VC" (NUL padded)       */
+    int32_t heteroscedastic;  /* 0/1                                              */
+} gpz_model;
+
+/* status codes */
+enum {
+    GPZ_OK = 0,
+    GPZ_ERR_USAGE = 1,        /* bad argument / unsupported combination           */
+    GPZ_ERR_CUDA = 2,
+    GPZ_ERR_NCCL = 3,
+    GPZ_ERR_NODEVICE = 4
+};
+
+const char* gpz_last_error(void);
+int gpz_version(void);
+
+/* length of theta for a model: [P(:); Gamma(:); lnAlpha(:); b(:); v(:); lnTau(:)]  GPz/init.m:87,97 */
+int64_t gpz_theta_len(const gpz_model* model);
+int64_t gpz_g_dim(const gpz_model* model);
+
+/* ---- dataset context: replaces the closure capture at GPz/train.m:40 ---------------------------
+ * X n_all x d, Y n_all x k, omega n_all (NULL = ones, GPz.m:20-22), training/validation logical
+ * n_all (NULL training = all rows, GPz.m:16-18; NULL validation = none, GPz.m:239).
+ * Psi: NULL, or n_all x d (methods ?L/?D) or d x d x n_all (methods ?C), as GPz/fixPsi.m returns it.
+ * The rows selected by the masks are gathered once and stay resident in HBM.
+ * device: CUDA ordinal to use.                                                                   */
+int gpz_create(gpz_ctx** out, const gpz_model* model, int64_t n_all,
+               const double* X, const double* Y, const double* Psi, const double* omega,
+               const uint8_t* training, const uint8_t* validation, int device);
+void gpz_destroy(gpz_ctx* ctx);
+
+/* ---- multi-GPU: one process per GPU, rows sharded, NCCL sum-allreduce inside eval/fit ------------
+ * Every rank calls gpz_create on ITS row shard, then gpz_comm_init with the same 128-byte id that
+ * rank 0 obtained from gpz_comm_unique_id (distribute it with any host-side channel).            */
+int gpz_comm_unique_id(char id[128]);
+int gpz_comm_init(gpz_ctx* ctx, int rank, int world, const char id[128]);
+
+/* ---- [nlogML,grad] = GPz(theta,...) with nargout<=2   (GPz/GPz.m:1-263, full path) ---------------
+ * stats[4] = trainRMSE, trainLL, validRMSE, validLL  (the globals of GPz/GPz.m:3-7,236-259;
+ * valid* are NaN without a validation mask).                                                     */
+int gpz_eval(gpz_ctx* ctx, const double* theta, double* nlogML, double* grad, double stats[4]);
+
+/* same, device-resident: d_theta (p doubles) and d_out (p+5 doubles: nlogML, grad[p], stats[4]) are
+ * device pointers; the work is enqueued on gpz_stream(ctx) and NOT synchronised.                 */
+int gpz_eval_dev(gpz_ctx* ctx, const double* d_theta, double* d_out);
+
+/* ---- [~,~,w,iSigma_w] = GPz(theta,...) with nargout>2  (GPz/GPz.m:84-87 early exit) --------------
+ * nlogML_k: 1 x k UN-normalised values as the reference returns on this exit (may be NULL);
+ * w m x k; iSigma_w m x m x k.                                                                   */
+int gpz_fit(gpz_ctx* ctx, const double* theta, double* nlogML_k, double* w, double* iSigma_w);
+
+/* ---- [PHI,~,lnBeta_i] = getPHI(X,Psi,theta,model,selection) on the context's rows ----------------
+ * (GPz/getPHI.m:1-127).  which: 0 = training rows, 1 = validation rows.  PHI n x m, lnBeta_i n x k;
+ * either may be NULL.                                                                            */
+int gpz_phi(gpz_ctx* ctx, const double* theta, int which, double* PHI, double* lnBeta_i);
+int64_t gpz_rows(const gpz_ctx* ctx, int which);
+
+/* ---- predict core (GPz/predict.m:60-73 dispatch; predictDiag.m:58-125, predictCov.m:53-69) -------
+ * Xz n x d z-scored rows without NaN; Psi NULL (predictFull) or n x d fixPsi-normalised
+ * (predictNoisy, methods ?L/?D).  theta/w/iSigma_w as stored in model.best / model.last.
+ * Outputs n x k each: mu (WITHOUT muY), nu, beta_i, gamma; PHI n x m (may be NULL).
+ * sigma = nu + beta_i + gamma and mu += muY stay on the host (predict.m:72-73).                  */
+int gpz_predict(const gpz_model* model, const double* theta, const double* w, const double* iSigma_w,
+                int64_t n, const double* Xz, const double* Psi,
+                double* mu, double* nu, double* beta_i, double* gamma, double* PHI, int device);
+
+/* ---- [Xi,logdet] = inv_logdet(X)  (GPz/inv_logdet.m:1-15) for SPD X (blocked Cholesky) ----------- */
+int gpz_inv_logdet(int32_t m, const double* X, double* Xi, double* logdet, int device);
+
+/* ---- D = Dxy(X,Y)  (GPz/Dxy.m:1-10): X n x d, Y m x d -> D n x m -------------------------------- */
+int gpz_dxy(int64_t n, int32_t m, int32_t d, const double* X, const double* Y, double* D, int device);
+
+/* ---- plumbing / measurement ------------------------------------------------------------------- */
+void* gpz_stream(gpz_ctx* ctx);                 /* cudaStream_t the context enqueues on            */
+int   gpz_sync(gpz_ctx* ctx);
+int64_t gpz_launch_count(const gpz_ctx* ctx);   /* kernels launched by this context so far         */
+/* device time (ms, CUDA events on the context stream) of the phases of the LAST eval:
+ * [0] phi build  [1] gram  [2] solve  [3] T-GEMM  [4] back-projection + rest  [5] total           */
+int gpz_last_timing(gpz_ctx* ctx, double ms[6]);
+int gpz_set_option(gpz_ctx* ctx, const char* name, double value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPZ_B200_H */
