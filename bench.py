@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- NLML+gradient evaluations per second of the GPz hot path on B200.
+
+Metric (BASELINE.json): "NLML+grad evals/sec at (n,d,m) per covariance mode; 1/2/4/8 GPU vs CPU ref".
+Headline workload (north_star target): synthetic n=1e6, d=10, m=1000, method VC, heteroscedastic, k=1.
+A "step" = one full objective+gradient evaluation GPz(theta) (GPz/GPz.m:1-263) at a fresh theta
+(theta0 + small perturbations, as a line search visits).  With N GPUs the n rows are sharded
+(strong scaling: total n fixed) and every evaluation does two NCCL allreduces.
+
+  value  : evals/s with theta already in HBM and the result left in HBM (gpz_eval_dev), CUDA events
+           on the library's stream, max over ranks.
+  e2e    : evals/s through the host-buffer C-ABI call a MATLAB/MEX caller makes (gpz_eval): theta H2D
+           and (f, grad, stats) D2H inside the timed region, every step.
+  --impl reference : the reference algorithm's CPU path.  The reference is MATLAB (not installable
+           here), so this arm times the NumPy restatement oracle/gpz_oracle.py ("port") with all
+           host threads on a bounded row sample of the same workload and scales linearly in n.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n, d, m, method)
+    "target": (1_000_000, 10, 1000, "VC"),
+    "cfg3": (1_000_000, 10, 500, "VD"),
+    "photoz": (60_000, 5, 100, "VC"),
+    "small": (20_000, 10, 256, "VC"),
+}
+METRIC = "NLML+grad evals/sec at (n,d,m) per covariance mode"
+
+
+def workload_desc(name, n, d, m, method):
+    return f"synthetic n={n} d={d} m={m} {method} heteroscedastic k=1 ({name})"
+
+
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def fp64_peak_tflops(torch, dev, reps=10, N=8192):
+    """Same protocol as MEASURED_PEAKS.json's GEMM figure, in fp64: cuBLAS DGEMM N^3, best of reps."""
+    a = torch.randn(N, N, dtype=torch.float64, device=dev)
+    b = torch.randn(N, N, dtype=torch.float64, device=dev)
+    torch.matmul(a, b)
+    torch.cuda.synchronize(dev)
+    best = float("inf")
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    return 2.0 * N ** 3 / (best * 1e-3) / 1e12
+
+
+def make_problem(name, seed=0):
+    from gpz_b200 import synth
+    n, d, m, method = WORKLOADS[name]
+    X, Y = synth.make_data(n, d, seed=seed)
+    theta0 = synth.make_theta0(X, Y, method, m, het=True, seed=seed + 1)
+    return n, d, m, method, X, Y, theta0
+
+
+def thetas_for(theta0, count, seed=100):
+    rng = np.random.default_rng(seed)
+    return [theta0 + 0.01 * rng.standard_normal(theta0.size) for _ in range(count)]
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_oracle_time(name, n_sample, reps, seed=0):
+    """Seconds per evaluation of the NumPy restatement on an n_sample-row sample of the workload."""
+    from gpz_b200 import synth
+    from oracle import gpz_oracle as O
+    n, d, m, method = WORKLOADS[name]
+    ns = min(n, n_sample)
+    X, Y = synth.make_data(ns, d, seed=seed)
+    theta0 = synth.make_theta0(X, Y, method, m, het=True, seed=seed + 1)
+    model = O.Model(d=d, k=1, m=m, method=method, heteroscedastic=True)
+    X, Y = np.array(X), np.array(Y)
+    ths = thetas_for(theta0, reps)
+    ts = []
+    for th in ths:
+        t0 = time.perf_counter()
+        O.GPz(th, model, X, Y)
+        ts.append(time.perf_counter() - t0)
+    # the m x m SVD pseudo-inverse does not grow with n: time it alone so only the n-proportional part is scaled
+    A = np.random.default_rng(0).standard_normal((m, m + 8))
+    S = A @ A.T + np.eye(m)
+    t0 = time.perf_counter()
+    O.inv_logdet(S)
+    t_svd = time.perf_counter() - t0
+    return ns, ts, t_svd
+
+
+def scale_cpu_time(sec_sample, t_svd, n, ns):
+    """t(n) = a*n + c with c = the n-independent SVD: scale only the n-proportional part."""
+    t_svd = min(t_svd, 0.5 * sec_sample)
+    return (sec_sample - t_svd) * (n / ns) + t_svd
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    name = args.workload
+    n, d, m, method = WORKLOADS[name]
+    ns = args.cpu_sample or max(2000, min(n, int(4.0e10 / (m * m + 40.0 * m * d * d))))   # ~4-6 s per step
+    total = args.warmup + args.steps
+    ns, ts, t_svd = cpu_oracle_time(name, ns, total)
+    timed = ts[args.warmup:] if len(ts) > args.warmup else ts
+    sec_sample = float(np.mean(timed))
+    sec_full = scale_cpu_time(sec_sample, t_svd, n, ns)
+    value = 1.0 / sec_full
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_full * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_desc(name, n, d, m, method),
+                   "note": "reference is MATLAB (no MATLAB/Octave here): NumPy restatement of GPz.m/getPHI.m/inv_logdet.m, "
+                           "same operation sequence, OpenBLAS threads = all host cores"},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port",
+                         "sample": f"{ns} of {n} rows per step, same d/m/mode; t(n)=a*n+c with c = the m x m SVD ({t_svd:.2f} s) "
+                                   f"timed alone, a*n scaled x{n / ns:.1f}; measured {sec_sample:.3f} s/eval on the sample"},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from gpz_b200 import _lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    name = args.workload
+    n, d, m, method, X, Y, theta0 = make_problem(name)
+    lo, hi = (n * rank) // world, (n * (rank + 1)) // world          # contiguous row shard of this rank
+    t0 = time.perf_counter()
+    ctx = L.Context(L.make_model(d, 1, m, method, True), X[lo:hi], Y[lo:hi], device=local)
+    if world > 1:
+        uid = [L.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(rank, world, uid[0])
+    upload_s = time.perf_counter() - t0
+    p = theta0.size
+    W, K = args.warmup, args.steps
+    ths = thetas_for(theta0, W + K)
+    d_th = [torch.from_numpy(t).to(dev) for t in ths]
+    d_out = torch.empty(p + 5, dtype=torch.float64, device=dev)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident arm ------------------------------------------------------------------
+    for i in range(W):
+        ctx.eval_dev(d_th[i].data_ptr(), d_out.data_ptr())
+    ctx.sync()
+    barrier()
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gram_ms, tgemm_ms, phases = [], [], []
+    e0.record(stream)
+    for i in range(K):
+        ctx.eval_dev(d_th[W + i].data_ptr(), d_out.data_ptr())
+    e1.record(stream)
+    ctx.sync()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - l0
+    tm = ctx.last_timing()            # CUDA events recorded inside the last timed evaluation
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / K
+    f_last = float(d_out[0].item())
+
+    # ---- end-to-end arm: host theta in, host (f, g, stats) out, every step -----------------------
+    for i in range(min(W, 2)):
+        ctx.eval(ths[i])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        f_e2e, g_e2e, st = ctx.eval(ths[W + i])
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_step = float(t.item()) / K
+    assert abs(f_e2e - f_last) <= 1e-12 * abs(f_last), (f_e2e, f_last)   # same theta -> same answer on both arms
+
+    # ---- roofline of the dominant kernel (T = PHI * iSigma, fp64 DMMA) ---------------------------
+    peak = fp64_peak_tflops(torch, dev) if rank == 0 else None
+    line = None
+    if rank == 0:
+        n_loc = hi - lo
+        flops_tgemm = 2.0 * n_loc * m * m                  # algorithmic: one of the two n x m x m GEMMs (F_gemm/2)
+        ach = flops_tgemm / (tm["tgemm_kernel"] * 1e-3) / 1e12
+        prof = {}
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "summary.json")))
+        except Exception:
+            pass
+        roof = {"bound": "tensor", "kernel": "tgemm_kernel (T = PHI*iSigma, DMMA.8x8x4 fp64)",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": prof.get("tgemm_dram_bytes_per_launch"),
+                "peak_source": "measured in this run: cuBLAS DGEMM 8192^3 fp64, best of 10, CUDA events "
+                               "(MEASURED_PEAKS.json has no fp64 figure; tcgen05 has no fp64 kind, DMMA is the fp64 tensor path)",
+                "algorithmic_flops_per_launch": flops_tgemm,
+                "kernel_ms": tm["tgemm_kernel"],
+                "gram_kernel": {"ms": tm["gram_kernel"], "achieved": flops_tgemm / (tm["gram_kernel"] * 1e-3) / 1e12,
+                                "note": "Gram PHI'WPHI credited 2nm^2 although only the lower tile triangle is computed"},
+                "eval_frac_of_fp64_peak": (4.0 * n * m * m / world) / (ms_step * 1e-3) / 1e12 / peak,
+                "phase_ms": {k_: round(v, 3) for k_, v in tm.items()}}
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            ns = args.cpu_sample or max(2000, min(n, int(1.2e11 / (m * m + 40.0 * m * d * d))))   # ~10-20 s of CPU work
+            ns, ts, t_svd = cpu_oracle_time(name, ns, 2)
+            sec = scale_cpu_time(min(ts), t_svd, n, ns)
+            cpu = {"value": 1.0 / sec, "unit": "evals/s", "cores": os.cpu_count() or 1, "kind": "port",
+                   "sample": f"{ns} of {n} rows, same d/m/mode, best of 2; t(n)=a*n+c with c = the m x m SVD ({t_svd:.2f} s), "
+                             f"a*n scaled x{n / ns:.1f}; NumPy restatement of the MATLAB reference, {min(ts):.2f} s on the sample"}
+        line = {
+            "metric": METRIC, "value": 1e3 / ms_step, "unit": "evals/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_desc(name, n, d, m, method), "rows_per_gpu": hi - lo,
+                       "parallelism": f"rows sharded over {world} GPU(s), 2 NCCL allreduces per eval" if world > 1 else "1 GPU",
+                       "cache": "inputs larger than L2: PHI/H working set %.1f GB per GPU" % (16.0 * (hi - lo) * ctx.model.m / 1e9),
+                       "dataset_upload_s": round(upload_s, 3), "theta_len": int(p)},
+            "e2e": {"value": 1.0 / e2e_step, "unit": "evals/s", "h2d_bytes_per_step": 8 * int(p), "d2h_bytes_per_step": 8 * (int(p) + 5),
+                    "ms_per_step": e2e_step * 1e3},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "check": {"nlogML_last": f_last, "trainRMSE": float(st["trainRMSE"])},
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="target", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample", type=int, default=0, help="rows of the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

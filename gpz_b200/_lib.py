@@ -201,9 +201,10 @@ class Context:
         return int(self._lib.gpz_launch_count(self._h))
 
     def last_timing(self):
-        ms = np.empty(6)
+        ms = np.empty(8)
         check(self._lib.gpz_last_timing(self._h, ptr(ms)))
-        return dict(phi=ms[0], gram=ms[1], solve=ms[2], tgemm=ms[3], backproj=ms[4], total=ms[5])
+        return dict(phi=ms[0], gram=ms[1], solve=ms[2], tgemm=ms[3], backproj=ms[4], total=ms[5],
+                    gram_kernel=ms[6], tgemm_kernel=ms[7])
 
 
 def comm_unique_id() -> bytes:

@@ -442,6 +442,7 @@ struct gpz_ctx {
     int QP = 32;
     SolveWs sws;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t kev[4] = {nullptr, nullptr, nullptr, nullptr};   // [0,1] around the first Gram launch, [2,3] around the first T-GEMM launch
     double* h_out = nullptr;   // pinned
     double* h_theta = nullptr; // pinned
     std::vector<void*> allocs;
@@ -700,6 +701,7 @@ int ensure_workspace(gpz_ctx* c) {
     }
     if ((rc = solve_ws_alloc(c->sws, static_cast<int>(MP)))) return rc;
     for (auto& e : c->ev) GPZ_CUDA(cudaEventCreate(&e));
+    for (auto& e : c->kev) GPZ_CUDA(cudaEventCreate(&e));
     GPZ_CUDA(cudaMallocHost(&c->h_out, sizeof(double) * (P.p + 5)));
     GPZ_CUDA(cudaMallocHost(&c->h_theta, sizeof(double) * P.p));
     c->ws_ready = true;
@@ -744,8 +746,13 @@ int forward_and_solve(gpz_ctx* c, const double* d_theta) {
         if (nchunks == 0) GPZ_CUDA(cudaEventRecord(c->ev[1], st));
         for (int o = 0; o < k; ++o) {
             // rows of this chunk are [0, r1-r0) of phi; the weights are indexed by absolute row
-            if ((rc = gram_syrk(phi, MP, static_cast<int>(MP), c->ob + o * n + r0, 0, r1 - r0, c->gram_ns,
-                                c->gram_partial, nchunks > 0, last, c->S + static_cast<int64_t>(o) * MP * MP, st, &c->launches))) return rc;
+            const bool timed = (nchunks == 0 && o == 0);
+            if (timed) GPZ_CUDA(cudaEventRecord(c->kev[0], st));
+            if ((rc = gram_syrk_main(phi, MP, static_cast<int>(MP), c->ob + o * n + r0, 0, r1 - r0, c->gram_ns,
+                                     c->gram_partial, nchunks > 0, st, &c->launches))) return rc;
+            if (timed) GPZ_CUDA(cudaEventRecord(c->kev[1], st));
+            if ((rc = gram_syrk_finish(c->gram_partial, c->gram_ns, static_cast<int>(MP), last, c->S + static_cast<int64_t>(o) * MP * MP, st,
+                                       &c->launches))) return rc;
             if (k > 1 && !last) {
                 set_error("row chunking with k > 1 outputs is not supported (raise the memory budget)");
                 return GPZ_ERR_USAGE;
@@ -829,8 +836,11 @@ int eval_device(gpz_ctx* c, const double* d_theta, double* d_out) {
         double* phi = nullptr;
         if ((rc = chunk_phi_and_pred(c, r0, r1, &phi))) return rc;
         for (int o = 0; o < k; ++o) {
+            const bool timed = (nchunks == 0 && o == 0);
+            if (timed) GPZ_CUDA(cudaEventRecord(c->kev[2], st));
             if ((rc = tgemm(phi, MP, c->Sinv + static_cast<int64_t>(o) * MP * MP, static_cast<int>(MP), P.m, rows, c->ob + o * n + r0,
                             c->H, o > 0, c->nupart + r0, n, st, &c->launches))) return rc;
+            if (timed) GPZ_CUDA(cudaEventRecord(c->kev[3], st));
             rows2_kernel<<<static_cast<unsigned>(ceil_div(rows, RB)), RB, 0, st>>>(P, o, c->tr.Y, c->tr.omega, n, r0, r1, c->pred,
                                                                                  c->nupart, ntn, c->lnbi, c->beta, c->ob, c->nu,
                                                                                  c->cw, c->dbeta, c->part2, 2 * k + 2);
@@ -978,6 +988,8 @@ void gpz_destroy(gpz_ctx* c) {
     for (void* p : c->allocs) cudaFree(p);
     solve_ws_free(c->sws);
     for (auto& e : c->ev)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : c->kev)
         if (e) cudaEventDestroy(e);
     if (c->h_out) cudaFreeHost(c->h_out);
     if (c->h_theta) cudaFreeHost(c->h_theta);
@@ -1346,7 +1358,7 @@ int gpz_sync(gpz_ctx* c) {
 
 int64_t gpz_launch_count(const gpz_ctx* c) { return c ? c->launches : -1; }
 
-int gpz_last_timing(gpz_ctx* c, double ms[6]) {
+int gpz_last_timing(gpz_ctx* c, double ms[8]) {
     if (!c || !c->ws_ready) {
         set_error("gpz_last_timing: no evaluation yet");
         return GPZ_ERR_USAGE;
@@ -1361,6 +1373,10 @@ int gpz_last_timing(gpz_ctx* c, double ms[6]) {
     }
     GPZ_CUDA(cudaEventElapsedTime(&t, c->ev[0], c->ev[5]));
     ms[5] = t;
+    GPZ_CUDA(cudaEventElapsedTime(&t, c->kev[0], c->kev[1]));
+    ms[6] = t;
+    GPZ_CUDA(cudaEventElapsedTime(&t, c->kev[2], c->kev[3]));
+    ms[7] = t;
     return GPZ_OK;
 }
 

@@ -206,19 +206,24 @@ static int launch_atb(const double* A, int64_t lda, const double* B, int64_t ldb
 }
 
 // Gram: S(MP x MP, both triangles) = PHI' diag(w) PHI over rows [row0,row1).
-// partial must hold nsplit * ntri * 128*128 doubles.  reduce=0 leaves the partials (chunked accumulation).
-int gram_syrk(const double* Phi, int64_t ld, int MP, const double* wgt, int64_t row0, int64_t row1, int nsplit,
-              double* partial, int accumulate, int reduce, double* S, cudaStream_t st, int64_t* launches) {
+// partial must hold nsplit * ntri * 128*128 doubles; the finish step sums the split partials (fixed order).
+int gram_syrk_main(const double* Phi, int64_t ld, int MP, const double* wgt, int64_t row0, int64_t row1, int nsplit,
+                   double* partial, int accumulate, cudaStream_t st, int64_t* launches) {
     const int T = MP / TILE;
     const int ntri = T * (T + 1) / 2;
     int rc = launch_atb<2, 4, true>(Phi, ld, Phi, ld, wgt, row0, row1, ntri, T, nsplit, partial, accumulate, st);
     if (rc) return rc;
     ++*launches;
-    if (reduce) {
-        atb_reduce_kernel<TILE, true><<<ntri, 256, 0, st>>>(partial, nsplit, ntri, T, S, MP);
-        GPZ_KERNEL_CHECK();
-        ++*launches;
-    }
+    return GPZ_OK;
+}
+
+int gram_syrk_finish(const double* partial, int nsplit, int MP, int reduce, double* S, cudaStream_t st, int64_t* launches) {
+    if (!reduce) return GPZ_OK;
+    const int T = MP / TILE;
+    const int ntri = T * (T + 1) / 2;
+    atb_reduce_kernel<TILE, true><<<ntri, 256, 0, st>>>(partial, nsplit, ntri, T, S, MP);
+    GPZ_KERNEL_CHECK();
+    ++*launches;
     return GPZ_OK;
 }
 

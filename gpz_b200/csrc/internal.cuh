@@ -53,8 +53,9 @@ int transpose_out(const double* src_rowmajor, int64_t ld, int64_t n, int m, doub
 
 // ---- gemm.cu
 int gram_nsplit(int MP, int sm_count);
-int gram_syrk(const double* Phi, int64_t ld, int MP, const double* wgt, int64_t row0, int64_t row1, int nsplit,
-              double* partial, int accumulate, int reduce, double* S, cudaStream_t st, int64_t* launches);
+int gram_syrk_main(const double* Phi, int64_t ld, int MP, const double* wgt, int64_t row0, int64_t row1, int nsplit,
+                   double* partial, int accumulate, cudaStream_t st, int64_t* launches);
+int gram_syrk_finish(const double* partial, int nsplit, int MP, int reduce, double* S, cudaStream_t st, int64_t* launches);
 int atb_general(const double* A, int64_t lda, int MP, const double* B, int64_t ldb, int QP, const double* wgt,
                 int64_t row0, int64_t row1, int nsplit, double* partial, int accumulate, int reduce, double* R,
                 cudaStream_t st, int64_t* launches);

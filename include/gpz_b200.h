@@ -116,8 +116,10 @@ void* gpz_stream(gpz_ctx* ctx);                 /* cudaStream_t the context enqu
 int   gpz_sync(gpz_ctx* ctx);
 int64_t gpz_launch_count(const gpz_ctx* ctx);   /* kernels launched by this context so far         */
 /* device time (ms, CUDA events on the context stream) of the phases of the LAST eval:
- * [0] phi build  [1] gram  [2] solve  [3] T-GEMM  [4] back-projection + rest  [5] total           */
-int gpz_last_timing(gpz_ctx* ctx, double ms[6]);
+ * [0] phi build  [1] row weights + Gram + PHI'Wy (+allreduce #1)  [2] solve  [3] PHI w + T-GEMM + row gradients
+ * [4] dPHI + back-projection + validation + finish (+allreduce #2)  [5] total
+ * [6] the Gram kernel alone (first launch)  [7] the T-GEMM kernel alone (first launch)            */
+int gpz_last_timing(gpz_ctx* ctx, double ms[8]);
 int gpz_set_option(gpz_ctx* ctx, const char* name, double value);
 
 #ifdef __cplusplus
