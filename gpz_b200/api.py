@@ -1,0 +1,318 @@
+"""Host-side mirror of the reference's MATLAB API for the hot path: init / train / predict / GPz /
+getPHI / inv_logdet / Dxy with the reference's names, argument meaning and error behaviour
+(GPz/init.m:1, GPz/train.m:1, GPz/predict.m:1, GPz/GPz.m:1, GPz/getPHI.m:1).
+
+In production the host stays MATLAB and calls the same C ABI through matlab/gpz_b200_mex.cpp
+(INTEGRATION.md); MATLAB is not available in this environment, so this module is the executable
+stand-in.  Everything numerical on the hot path runs in libgpz_b200.so on the GPU -- this file only
+normalises inputs (z-scoring, fixPsi), packs theta and drives a host L-BFGS, exactly the parts the
+reference keeps on the host.  There is no CPU fallback for the objective.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from . import _lib as L
+
+__all__ = ["init", "train", "predict", "GPz", "getPHI", "inv_logdet", "Dxy", "fixPsi", "Objective"]
+
+
+# ------------------------------------------------------------------------------------------------
+# host preprocessing the reference also does on the host
+# ------------------------------------------------------------------------------------------------
+def fixPsi(Psi, n, sdX, method):
+    """Input-noise layout normalisation (GPz/fixPsi.m:1-55): -> n x d for ?L/?D, d x d x n for ?C."""
+    if Psi is None or np.size(Psi) == 0:
+        return None
+    sdX = np.asarray(sdX, dtype=np.float64).reshape(-1)
+    d = sdX.size
+    Psi = np.asarray(Psi, dtype=np.float64)
+    cube = Psi.ndim == 3 and Psi.shape == (d, d, n)
+    if Psi.ndim == 1:
+        Psi = Psi.reshape(n, 1)
+    if method[1] == "C":
+        if cube:
+            return np.asfortranarray(Psi / np.outer(sdX, sdX)[:, :, None])
+        out = np.zeros((d, d, n), order="F")
+        diag = np.repeat(Psi, d, axis=1) if Psi.shape[1] == 1 else Psi
+        out[np.arange(d), np.arange(d), :] = (diag / sdX[None, :] ** 2).T
+        return out
+    if cube:
+        return np.asfortranarray(np.stack([Psi[a, a, :] for a in range(d)], axis=1) / sdX[None, :] ** 2)
+    if Psi.shape[1] == 1:
+        Psi = np.repeat(Psi, d, axis=1)
+    return np.asfortranarray(Psi / sdX[None, :] ** 2)
+
+
+def _pca(X):
+    """NaN-aware PCA used to rotate the random centres (GPz/pca.m:1-48 with th=1)."""
+    n, d = X.shape
+    miss = np.isnan(X)
+    X0 = np.where(miss, 0.0, X)
+    counts = n - miss.sum(axis=0)
+    mu = X0.sum(axis=0) / counts
+    Xc = np.where(miss, 0.0, X0 - mu[None, :])
+    M = miss.astype(np.float64)
+    sig = n * (Xc.T @ Xc) / (n - M.T @ M)
+    S, U = np.linalg.eigh(sig)
+    S = np.abs(S)
+    order = np.argsort(-S)
+    U, S = U[:, order], S[order]
+    Ssd = np.sqrt(S / (n - 1))
+    Ti = np.diag(Ssd) @ U.T
+    return mu, sig / n, Ti
+
+
+def _fill_linear(X, mu, Sigma):
+    """Conditional-mean fill of missing entries (GPz/fillLinear.m:1-30)."""
+    X = X.copy()
+    miss = np.isnan(X)
+    pats = np.unique(miss, axis=0)
+    for u in pats:
+        if not u.any():
+            continue
+        rows = (miss == u[None, :]).all(axis=1)
+        o = ~u
+        Delta = X[np.ix_(rows, o)] - mu[o][None, :]
+        X[np.ix_(rows, u)] = Delta @ np.linalg.solve(Sigma[np.ix_(o, o)], Sigma[np.ix_(o, u)]) + mu[u][None, :]
+    return X
+
+
+def _theta_offsets(model):
+    m, d, k = model["m"], model["d"], model["k"]
+    oG = m * d
+    oA = oG + model["g_dim"]
+    oB = oA + m * k
+    oV = oB + k
+    return oG, oA, oB, oV, oV + m * k
+
+
+def _c_model(model):
+    return L.make_model(model["d"], model["k"], model["m"], model["method"], model["heteroscedastic"])
+
+
+class Objective:
+    """f = @(params) GPz(params,model,X,Y,Psi,omega,training,validation)  (GPz/train.m:40) with the
+    normalised data resident on the GPU.  Calling it returns (nlogML, grad); the four statistics the
+    reference passes through globals (GPz.m:3-7) are left in ``.stats``."""
+
+    def __init__(self, model, Xz, Yc, Psi=None, omega=None, training=None, validation=None, device=0):
+        self.ctx = L.Context(_c_model(model), Xz, Yc, Psi, omega, training, validation, device=device)
+        self.stats = {}
+        self.evals = 0
+
+    def __call__(self, theta):
+        f, g, self.stats = self.ctx.eval(theta)
+        self.evals += 1
+        return f, g
+
+    def fit(self, theta):
+        _, w, iS = self.ctx.fit(theta, want_nlogML=False)
+        return w, iS
+
+    def close(self):
+        self.ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# reference-signature functions
+# ------------------------------------------------------------------------------------------------
+def GPz(theta, model, X, Y, Psi=None, omega=None, training=None, validation=None, nargout=2, device=0):
+    """[nlogML,grad,w,iSigma_w] = GPz(theta,model,X,Y,Psi,omega,training,validation) (GPz/GPz.m:1).
+    nargout<=2 -> (nlogML, grad, stats); nargout>2 -> the fit exit (nlogML 1 x k un-normalised, 0, w, iSigma_w)
+    of GPz.m:84-87.  One-shot convenience: uploads the data each call; use Objective for loops."""
+    ctx = L.Context(_c_model(model), X, Y, Psi, omega, training, validation, device=device)
+    try:
+        if nargout > 2:
+            nl, w, iS = ctx.fit(theta)
+            return nl, 0.0, w, iS
+        return ctx.eval(theta)
+    finally:
+        ctx.close()
+
+
+def getPHI(X, Psi, theta, model, selection=None, device=0):
+    """[PHI,~,lnBeta_i] = getPHI(X,Psi,theta,model,selection) (GPz/getPHI.m:1)."""
+    ctx = L.Context(_c_model(model), X, np.zeros((X.shape[0], model["k"])), Psi, None, selection, None, device=device)
+    try:
+        return ctx.phi(theta, 0)
+    finally:
+        ctx.close()
+
+
+def inv_logdet(X, device=0):
+    """[Xi,logdet] = inv_logdet(X) (GPz/inv_logdet.m:1) for symmetric positive definite X."""
+    return L.inv_logdet(X, device)
+
+
+def Dxy(X, Y, device=0):
+    """D = Dxy(X,Y) (GPz/Dxy.m:1)."""
+    return L.dxy(X, Y, device)
+
+
+def init(X, Y, method, m, heteroscedastic=True, normalize=True, omega=None, training=None, Psi=None, seed=None, device=0):
+    """model = init(X,Y,method,m,...) (GPz/init.m:1-124): z-scoring statistics, PCA-rotated random
+    centres, length-scale heuristic through Dxy, theta packing and the first fit of w / iSigma_w."""
+    X = np.asarray(X, dtype=np.float64)
+    Y = np.asarray(Y, dtype=np.float64).reshape(X.shape[0], -1)
+    n, d = X.shape
+    k = Y.shape[1]
+    if d == 1:
+        method = method[0] + "L"                                   # init.m:12-14
+    training = np.ones(n, dtype=bool) if training is None else np.asarray(training, dtype=bool).reshape(-1)
+    omega = np.ones(n) if omega is None else np.asarray(omega, dtype=np.float64).reshape(-1)
+    model = dict(d=d, k=k, m=int(m), method=method, heteroscedastic=bool(heteroscedastic))
+    if normalize:                                                  # init.m:22-36
+        miss = np.isnan(X)
+        X0 = np.where(miss, 0.0, X)
+        cnt = (~miss).sum(axis=0)
+        muX = X0.sum(axis=0) / cnt
+        sdX = np.sqrt((X0 ** 2).sum(axis=0) / cnt - muX ** 2)
+    else:
+        muX, sdX = np.zeros(d), np.ones(d)
+    muY = Y[training].mean(axis=0)
+    model.update(muX=muX, sdX=sdX, muY=muY)
+    Yc = Y - muY[None, :]
+    Xz = (X - muX[None, :]) / sdX[None, :]
+    Psi = fixPsi(Psi, n, sdX, method)
+    var = Yc[training].var(axis=0, ddof=1)
+    b = np.log(var)                                                # init.m:54
+    lnAlpha = np.repeat(-np.log(var)[None, :], m, axis=0)          # init.m:55
+    mu, sigmas, Vi = _pca(Xz[training])
+    rng = np.random.default_rng(seed)
+    P = (rng.random((m, d)) - 0.5) * np.sqrt(12.0)                 # init.m:58
+    P = P @ Vi + mu[None, :]                                       # init.m:59
+    Xl = _fill_linear(Xz[training], mu, sigmas)                    # init.m:61
+    if Xl.shape[0] * m <= 20_000_000:
+        meanD = L.dxy(Xl, P, device).mean(axis=0)                  # init.m:62 (Dxy on the GPU)
+    else:                                                          # same expansion as Dxy.m:3-7, column means only
+        meanD = float(np.mean(np.sum(Xl * Xl, axis=1))) - 2.0 * (P @ Xl.mean(axis=0)) + np.sum(P * P, axis=1)
+    gamma = np.sqrt(0.5 * m ** (1.0 / d) / meanD)
+    if method == "GL":
+        G = np.array([gamma.mean()])
+    elif method == "VL":
+        G = gamma.copy()
+    elif method == "GD":
+        G = np.full(d, gamma.mean())
+    elif method == "VD":
+        G = np.repeat(gamma[:, None], d, axis=1)
+    elif method == "GC":
+        G = np.eye(d) * gamma.mean()
+    elif method == "VC":
+        G = np.zeros((d, d, m))
+        G[np.arange(d), np.arange(d), :] = gamma[None, :]
+    else:
+        raise ValueError(f"unknown method {method!r}")
+    model["g_dim"] = int(G.size)                                   # init.m:86
+    parts = [P.reshape(-1, order="F"), G.reshape(-1, order="F"), lnAlpha.reshape(-1, order="F"), b]
+    last = {}
+    if heteroscedastic:                                            # init.m:92-101
+        parts += [np.zeros(m * k), np.zeros(m * k)]
+        last["v"] = np.zeros((m, k))
+    theta = np.concatenate(parts)
+    obj = Objective(model, Xz, Yc, Psi, omega, training, None, device=device)
+    try:
+        w, iS = obj.fit(theta)                                     # init.m:104
+    finally:
+        obj.close()
+    last.update(theta=theta, w=w, iSigma_w=iS, priors=np.ones(m) / m, P=P)
+    best = dict(last)
+    best["LL"] = -np.inf
+    model["last"], model["best"] = last, best
+    return model
+
+
+def train(model, X, Y, maxIter=200, maxAttempts=np.inf, omega=None, training=None, validation=None, Psi=None,
+          display=True, device=0):
+    """model = train(model,X,Y,...) (GPz/train.m:1-81).  The optimiser is a host L-BFGS (SciPy's L-BFGS-B in
+    place of minFunc's, SURVEY.md 2.1: out of scope, stays on the host); the callback follows
+    GPz/callBack.m: best theta by validation log-likelihood, stop after maxAttempts non-improving iterations."""
+    from scipy.optimize import minimize
+
+    X = np.asarray(X, dtype=np.float64)
+    Y = np.asarray(Y, dtype=np.float64).reshape(X.shape[0], -1)
+    n, d = X.shape
+    m, k = model["m"], model["k"]
+    Yc = Y - model["muY"][None, :]
+    Xz = (X - model["muX"][None, :]) / model["sdX"][None, :]
+    Psi = fixPsi(Psi, n, model["sdX"], model["method"])
+    obj = Objective(model, Xz, Yc, Psi, omega, training, validation, device=device)
+    state = dict(best_theta=model["best"]["theta"].copy(), best_valid=model["best"]["LL"], attempts=0, it=0, t=time.time())
+    training_only = validation is None
+
+    class _Stop(Exception):
+        pass
+
+    last = {}
+
+    def fun(th):
+        f, g = obj(th)
+        last["f"], last["stats"], last["theta"] = f, dict(obj.stats), th.copy()
+        if not (np.isfinite(f) and np.all(np.isfinite(g))):       # minFunc tolerates illegal values by backtracking
+            return 1e300, np.zeros_like(g)
+        return f, g
+
+    def callback(th):
+        state["it"] += 1
+        if not np.array_equal(th, last.get("theta")):
+            fun(th)
+        f, st = last["f"], last["stats"]
+        if training_only:
+            state["best_valid"], state["best_theta"] = st["trainLL"], th.copy()
+            mark = ""
+        elif st["validLL"] >= state["best_valid"]:
+            state["best_valid"], state["best_theta"], state["attempts"] = st["validLL"], th.copy(), 0
+            mark = "*"
+        else:
+            state["attempts"] += 1
+            mark = ""
+        if display:
+            print(f"\t{state['it']}\t{-f:1.5e}\t{st['trainRMSE']:1.5e}\t{st['trainLL']:1.5e}\t{st['validRMSE']:1.5e}\t"
+                  f"{st['validLL']:1.5e}{mark}\t{time.time() - state['t']:.3f}")
+        state["t"] = time.time()
+        if state["attempts"] >= maxAttempts:
+            raise _Stop()
+
+    theta = model["last"]["theta"].copy()
+    try:
+        res = minimize(fun, theta, jac=True, method="L-BFGS-B", callback=callback,
+                       options=dict(maxiter=int(maxIter), maxcor=100, gtol=1e-5, ftol=2.2e-9))
+        theta = res.x
+    except _Stop:
+        theta = last["theta"]
+    try:
+        oG, oA, oB, oV, oT = _theta_offsets(model)
+        for name, th in (("last", theta), ("best", state["best_theta"])):
+            w, iS = obj.fit(th)                                     # train.m:53,69
+            model[name].update(theta=th.copy(), w=w, iSigma_w=iS, priors=np.ones(m) / m,
+                               P=th[:m * d].reshape((m, d), order="F"))
+            if model["heteroscedastic"]:
+                model[name]["v"] = th[oV:oV + m * k].reshape((m, k), order="F")
+        model["best"]["LL"] = state["best_valid"]
+        model["evals"] = obj.evals
+    finally:
+        obj.close()
+    return model
+
+
+def predict(X, model, whichSet="best", Psi=None, selection=None, device=0):
+    """[mu,sigma,nu,beta_i,gamma,PHI,w,iSigma_w] = predict(X,model,...) (GPz/predict.m:1-75).  Rows with
+    missing values (predictMissing*, predictDiag.m:127-295) are not supported yet and raise."""
+    st = model["best"] if whichSet == "best" else model["last"]
+    X = np.asarray(X, dtype=np.float64)
+    n_all = X.shape[0]
+    sel = np.ones(n_all, dtype=bool) if selection is None else np.asarray(selection, dtype=bool).reshape(-1)
+    X = X[sel]
+    n = X.shape[0]
+    if Psi is not None:
+        Psi = np.asarray(Psi, dtype=np.float64)
+        Psi = Psi[:, :, sel] if Psi.ndim == 3 else Psi.reshape(n_all, -1)[sel]
+    Xz = (X - model["muX"][None, :]) / model["sdX"][None, :]
+    Psi = fixPsi(Psi, n, model["sdX"], model["method"])
+    mu, nu, beta_i, gamma, PHI = L.predict_core(_c_model(model), st["theta"], st["w"], st["iSigma_w"], Xz, Psi,
+                                                want_phi=True, device=device)
+    sigma = nu + beta_i + gamma                                     # predict.m:72
+    mu = mu + model["muY"][None, :]                                 # predict.m:73
+    return mu, sigma, nu, beta_i, gamma, PHI, st["w"], st["iSigma_w"]
