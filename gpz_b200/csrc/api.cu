@@ -215,20 +215,31 @@ dphi_kernel(Params P, const double* __restrict__ Phi, double* __restrict__ H, in
         vj[o] = (o < k) ? P.v[o * MP + j] : 0.0;
         sq[o] = sv[o] = 0.0;
     }
-    for (int64_t i = sb; i < se; ++i) {
-        const int64_t off = (i - r0) * ld + j;
-        const double ph = Phi[off];
-        double c = 0.0;
+    for (int64_t ib = sb; ib < se; ib += 4) {
+        double ph[4], hh[4];
 #pragma unroll
-        for (int o = 0; o < KMAX; ++o) {
-            if (o < k) {
-                const double cwi = __ldg(cw + o * n + i), dbi = __ldg(dbeta + o * n + i);
-                c = fma(cwi, wj[o], fma(dbi, vj[o], c));
-                sq[o] = fma(ph, -cwi, sq[o]);
-                sv[o] = fma(ph, dbi, sv[o]);
-            }
+        for (int u = 0; u < 4; ++u) {              // issue the loads of 4 rows before using any of them
+            const int64_t i = ib + u;
+            const int64_t off = (i - r0) * ld + j;
+            ph[u] = (i < se) ? Phi[off] : 0.0;
+            hh[u] = (i < se) ? H[off] : 0.0;
         }
-        H[off] = fma(ph, c, -H[off]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = ib + u;
+            if (i >= se) break;
+            double c = 0.0;
+#pragma unroll
+            for (int o = 0; o < KMAX; ++o) {
+                if (o < k) {
+                    const double cwi = __ldg(cw + o * n + i), dbi = __ldg(dbeta + o * n + i);
+                    c = fma(cwi, wj[o], fma(dbi, vj[o], c));
+                    sq[o] = fma(ph[u], -cwi, sq[o]);
+                    sv[o] = fma(ph[u], dbi, sv[o]);
+                }
+            }
+            H[(i - r0) * ld + j] = fma(ph[u], c, -hh[u]);
+        }
     }
     double* out = colp + static_cast<int64_t>(blockIdx.y) * 2 * k * MP;
 #pragma unroll
@@ -422,6 +433,12 @@ struct gpz_ctx {
     int rank = 0, world = 1;
     // options
     int64_t opt_chunk_rows = 0;     // 0 = auto
+    int opt_tensor_phi = 1;         // 1: PHI = exp(F W) on the DMMA pipe; 0: direct-difference kernels
+    int opt_fused_bp = 1;           // 1: fused dPHI + back-projection GEMM; 0: materialise dPHI first
+    std::vector<double> h_shift;    // constant subtracted from X at upload
+    double* Wc_alloc = nullptr;
+    double* dot_scratch = nullptr;
+    int dphi_slabs = 1, fused_ns = 1;
     // workspaces (allocated at first use)
     bool ws_ready = false;
     int64_t chunk_rows = 0;
@@ -501,6 +518,11 @@ int fill_params(Params& P, const gpz_model* model) {
     P.oV = P.oB + P.k;
     P.oT = P.oV + mk;
     P.p = P.oB + P.k + (P.het ? 2 * mk : 0);
+    P.q = mode_is_cov(mode) ? 1 + P.d + P.d * (P.d + 1) / 2 : 1 + 2 * P.d;
+    P.KQ = static_cast<int>(round_up(P.q, KSTEP));
+    P.QP = static_cast<int>(round_up(P.q, 32));
+    P.Wc = nullptr;
+    P.xshift = nullptr;
     return GPZ_OK;
 }
 
@@ -536,6 +558,9 @@ int alloc_params(Params& P, std::vector<void*>& list, int need_sigma) {
     if ((rc = dev_alloc(list, &P.v, P.k * MP))) return rc;
     if ((rc = dev_alloc(list, &P.tau, P.k * MP))) return rc;
     if ((rc = dev_alloc(list, &P.bk, 32))) return rc;
+    if ((rc = dev_alloc(list, &P.Wc, static_cast<int64_t>(P.KQ) * MP))) return rc;
+    if ((rc = dev_alloc(list, &P.xshift, d))) return rc;
+    GPZ_CUDA(cudaMemset(P.xshift, 0, sizeof(double) * d));
     return GPZ_OK;
 }
 
@@ -583,6 +608,11 @@ int upload_rows(gpz_ctx* c, RowData& R, const std::vector<int64_t>& idx, int64_t
     R.has_nan = 0;
     for (double v : buf)
         if (v != v) { R.has_nan = 1; break; }
+    for (int a = 0; a < P.d; ++a) {          // only x - p enters the path: store X relative to a fixed shift
+        const double sh = c->h_shift[a];
+        double* col = buf.data() + static_cast<int64_t>(a) * n;
+        for (int64_t i = 0; i < n; ++i) col[i] -= sh;
+    }
     GPZ_CUDA(cudaMemcpy(R.X, buf.data(), sizeof(double) * buf.size(), cudaMemcpyHostToDevice));
     if ((rc = dev_alloc(c->allocs, &R.Y, n * P.k))) return rc;
     if (Y) {
@@ -659,17 +689,22 @@ int ensure_workspace(gpz_ctx* c) {
     const int ntri = T * (T + 1) / 2;
     c->gram_ns = gram_nsplit(static_cast<int>(MP), c->sm_count);
     if ((rc = A(&c->gram_partial, static_cast<int64_t>(c->gram_ns) * ntri * TILE * TILE))) return rc;
-    const int q = feature_count(P);
-    c->QP = static_cast<int>(round_up(q, 32));
+    c->QP = P.QP;
     const int tn = c->QP / 32;
     c->atb_ns = c->sm_count / (T * tn) > 0 ? c->sm_count / (T * tn) : 1;
     {
         const int ns1 = c->sm_count / T > 0 ? c->sm_count / T : 1;     // the PHI'(ob*y) product has QP = 32
-        const int64_t a = static_cast<int64_t>(c->atb_ns) * T * tn * TILE * 32;
+        c->fused_ns = ns1;
+        int64_t a = static_cast<int64_t>(c->atb_ns) * T * tn * TILE * 32;
         const int64_t b = static_cast<int64_t>(ns1) * T * TILE * 32;
-        if ((rc = A(&c->atb_partial, a > b ? a : b))) return rc;
+        const int64_t f = static_cast<int64_t>(c->fused_ns) * T * TILE * c->QP;
+        if (b > a) a = b;
+        if (f > a) a = f;
+        if ((rc = A(&c->atb_partial, a))) return rc;
     }
     c->nslab = (2 * c->sm_count) / T > 0 ? (2 * c->sm_count) / T : 1;
+    c->dphi_slabs = 16 * c->nslab;
+    if ((rc = A(&c->dot_scratch, 2 * (MP / TILE) * c->chunk_rows))) return rc;
     // allreduce payloads
     c->red1_len = k * MP * MP + MP * 32 + (k + 2);
     if ((rc = A(&c->red1, c->red1_len))) return rc;
@@ -686,14 +721,25 @@ int ensure_workspace(gpz_ctx* c) {
     if ((rc = A(&c->part1, nb1 * (k + 2)))) return rc;
     if ((rc = A(&c->part2, nb1 * (2 * k + 2)))) return rc;
     if ((rc = A(&c->partv, nbv * 3))) return rc;
-    if ((rc = A(&c->colp, static_cast<int64_t>(c->nslab) * 2 * k * MP))) return rc;
+    {
+        const int64_t sl = c->dphi_slabs > c->fused_ns ? c->dphi_slabs : c->fused_ns;
+        if ((rc = A(&c->colp, sl * 2 * k * MP))) return rc;
+    }
     const int64_t bpd = backproj_partial_doubles(P, c->nslab, c->has_psi, c->tr.has_nan);
     if ((rc = A(&c->bp_partial, bpd))) return rc;
     const bool fast_bp = !c->has_psi && !c->tr.has_nan;
     if (fast_bp) {
-        if ((rc = A(&c->Fbuf, c->chunk_rows * c->QP))) return rc;
         if ((rc = A(&c->Rm, MP * c->QP))) return rc;
+        // monomial row features are dataset constants: built once, resident
+        if ((rc = A(&c->tr.F, (n > 0 ? n : 1) * c->QP))) return rc;
+        if ((rc = build_features(P, c->tr.X, n, 0, n, c->tr.F, c->st, &c->launches))) return rc;
     }
+    if (!c->has_psi && !c->va.has_nan && nv > 0) {
+        if ((rc = A(&c->va.F, nv * c->QP))) return rc;
+        if ((rc = build_features(P, c->va.X, nv, 0, nv, c->va.F, c->st, &c->launches))) return rc;
+    }
+    c->Wc_alloc = P.Wc;
+    if (!c->opt_tensor_phi) P.Wc = nullptr;
     {
         const int64_t dd = static_cast<int64_t>(P.d) * P.d;
         const int64_t sc = 2 * dd * MP + dd * P.m + static_cast<int64_t>(P.m) * P.d + 64;
@@ -734,7 +780,7 @@ int forward_and_solve(gpz_ctx* c, const double* d_theta) {
         if (n > 0) {
             DotSpec ds{0, {nullptr, nullptr}, {nullptr, nullptr}};
             if (P.het && k == 1) ds = DotSpec{1, {P.v, nullptr}, {c->lnbi, nullptr}};
-            if ((rc = phi_build(P, c->tr, r0, r1, phi, ds, st, &c->launches))) return rc;
+            if ((rc = phi_build(P, c->tr, r0, r1, phi, ds, c->dot_scratch, st, &c->launches))) return rc;
             if (P.het && k > 1)
                 for (int o = 0; o < k; ++o)
                     if ((rc = rowdot(phi, MP, P.m, r1 - r0, DotSpec{1, {P.v + o * MP, nullptr}, {c->lnbi + o * n + r0, nullptr}}, st, &c->launches))) return rc;
@@ -799,7 +845,7 @@ int chunk_phi_and_pred(gpz_ctx* c, int64_t r0, int64_t r1, double** phi_out) {
     if (!c->resident) {
         DotSpec ds{1, {c->w, nullptr}, {c->pred, nullptr}};
         if (P.k > 1) ds.n = 0;
-        if ((rc = phi_build(P, c->tr, r0, r1, phi, ds, c->st, &c->launches))) return rc;
+        if ((rc = phi_build(P, c->tr, r0, r1, phi, ds, c->dot_scratch, c->st, &c->launches))) return rc;
         if (P.k > 1)
             for (int o = 0; o < P.k; ++o)
                 if ((rc = rowdot(phi, MP, P.m, r1 - r0, DotSpec{1, {c->w + o * MP, nullptr}, {c->pred + o * n + r0, nullptr}}, c->st, &c->launches))) return rc;
@@ -827,7 +873,7 @@ int eval_device(gpz_ctx* c, const double* d_theta, double* d_out) {
     double* sc2 = qcol + 2LL * k * MP;
     const bool fast_bp = !c->has_psi && !c->tr.has_nan;
     const int T = static_cast<int>(MP / TILE);
-    int nchunks = 0;
+    int nchunks = 0, colp_slabs = 1;
     bool ev4 = false;
     for (int64_t r0 = 0; r0 < n; r0 += c->chunk_rows) {
         const int64_t r1 = (r0 + c->chunk_rows < n) ? r0 + c->chunk_rows : n;
@@ -851,21 +897,26 @@ int eval_device(gpz_ctx* c, const double* d_theta, double* d_out) {
             GPZ_CUDA(cudaEventRecord(c->ev[4], st));
             ev4 = true;
         }
-        {
-            const int64_t rps = ceil_div(rows, c->nslab);
-            dim3 grid(static_cast<unsigned>(T), static_cast<unsigned>(c->nslab));
+        const bool fused = fast_bp && c->opt_fused_bp && k == 1 && c->QP <= 128;
+        if (fused) {
+            if ((rc = atb_dphi(phi, c->H, MP, static_cast<int>(MP), c->tr.F + r0 * c->QP, c->QP, c->cw + r0, c->dbeta + r0, c->w, P.v,
+                               0, rows, c->fused_ns, c->atb_partial, c->colp, nchunks > 0, last, c->Rm, st, &c->launches))) return rc;
+            colp_slabs = c->fused_ns;
+        } else {
+            const int64_t rps = ceil_div(rows, c->dphi_slabs);
+            dim3 grid(static_cast<unsigned>(T), static_cast<unsigned>(c->dphi_slabs));
             dphi_kernel<<<grid, 128, 0, st>>>(P, phi, c->H, MP, n, r0, r1, rps, c->cw, c->dbeta, c->w, c->colp, nchunks > 0);
             GPZ_KERNEL_CHECK();
             ++c->launches;
-        }
-        if (fast_bp) {
-            if ((rc = build_features(P, c->tr, r0, r1, c->Fbuf, c->QP, st, &c->launches))) return rc;
-            if ((rc = atb_general(c->H, MP, static_cast<int>(MP), c->Fbuf, c->QP, c->QP, c->ones, 0, rows, c->atb_ns, c->atb_partial,
-                                  nchunks > 0, last, c->Rm, st, &c->launches))) return rc;
-        } else if (!mode_is_cov(P.mode)) {
-            if ((rc = backproj_diag_generic(P, c->tr, r0, r1, c->H, MP, c->bp_partial, c->nslab, nchunks > 0, st, &c->launches))) return rc;
-        } else {
-            if ((rc = backproj_cov_psi(P, c->tr, r0, r1, c->H, MP, c->bp_partial, c->nslab, nchunks > 0, st, &c->launches))) return rc;
+            colp_slabs = c->dphi_slabs;
+            if (fast_bp) {
+                if ((rc = atb_general(c->H, MP, static_cast<int>(MP), c->tr.F + r0 * c->QP, c->QP, c->QP, c->ones, 0, rows, c->atb_ns,
+                                      c->atb_partial, nchunks > 0, last, c->Rm, st, &c->launches))) return rc;
+            } else if (!mode_is_cov(P.mode)) {
+                if ((rc = backproj_diag_generic(P, c->tr, r0, r1, c->H, MP, c->bp_partial, c->nslab, nchunks > 0, st, &c->launches))) return rc;
+            } else {
+                if ((rc = backproj_cov_psi(P, c->tr, r0, r1, c->H, MP, c->bp_partial, c->nslab, nchunks > 0, st, &c->launches))) return rc;
+            }
         }
         ++nchunks;
     }
@@ -878,7 +929,7 @@ int eval_device(gpz_ctx* c, const double* d_theta, double* d_out) {
     else if (!mode_is_cov(P.mode)) rc = backproj_diag_generic_finish(P, c->bp_partial, c->nslab, dP, dG, c->scratch, st, &c->launches);
     else rc = backproj_cov_psi_finish(P, c->bp_partial, c->nslab, dP, dG, c->scratch, st, &c->launches);
     if (rc) return rc;
-    colsum_reduce_kernel<<<static_cast<unsigned>(ceil_div(2LL * k * MP, 256)), 256, 0, st>>>(c->colp, c->nslab, 2 * k, static_cast<int>(MP), qcol);
+    colsum_reduce_kernel<<<static_cast<unsigned>(ceil_div(2LL * k * MP, 256)), 256, 0, st>>>(c->colp, colp_slabs, 2 * k, static_cast<int>(MP), qcol);
     GPZ_KERNEL_CHECK();
     reduce_parts_kernel<<<2 * k + 2, 256, 0, st>>>(c->part2, ceil_div(n, RB), 2 * k + 2, sc2);
     GPZ_KERNEL_CHECK();
@@ -890,7 +941,7 @@ int eval_device(gpz_ctx* c, const double* d_theta, double* d_out) {
             const bool need_store = (k > 1) || (mode_is_cov(P.mode) && c->has_psi);
             DotSpec ds{2, {P.v, c->w}, {c->dotv_va, c->pred_va}};
             if (k > 1) ds.n = 0;
-            if ((rc = phi_build(P, c->va, r0, r1, need_store ? c->Phi : nullptr, ds, st, &c->launches))) return rc;
+            if ((rc = phi_build(P, c->va, r0, r1, need_store ? c->Phi : nullptr, ds, c->dot_scratch, st, &c->launches))) return rc;
             if (k > 1)
                 for (int o = 0; o < k; ++o)
                     if ((rc = rowdot(c->Phi, MP, P.m, r1 - r0, DotSpec{2, {P.v + o * MP, c->w + o * MP}, {c->dotv_va + o * nv + r0, c->pred_va + o * nv + r0}}, st, &c->launches))) return rc;
@@ -969,6 +1020,21 @@ int gpz_create(gpz_ctx** out, const gpz_model* model, int64_t n_all, const doubl
     for (int64_t i = 0; i < n_all; ++i) {
         if (!training || training[i]) itr.push_back(i);
         if (validation && validation[i]) iva.push_back(i);
+    }
+    c->h_shift.assign(static_cast<size_t>(P.d), 0.0);
+    for (int a = 0; a < P.d; ++a) {          // column means of the finite training entries
+        double s = 0.0;
+        int64_t cnt = 0;
+        const double* col = X + static_cast<int64_t>(a) * n_all;
+        for (int64_t i : itr) {
+            const double v = col[i];
+            if (v == v) { s += v; ++cnt; }
+        }
+        c->h_shift[a] = cnt > 0 ? s / static_cast<double>(cnt) : 0.0;
+    }
+    if (cudaMemcpy(c->P.xshift, c->h_shift.data(), sizeof(double) * P.d, cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("gpz_create: upload of the shift failed");
+        return fail(GPZ_ERR_CUDA);
     }
     if ((rc = upload_rows(c, c->tr, itr, n_all, X, Y, Psi, omega))) return fail(rc);
     if ((rc = upload_rows(c, c->va, iva, n_all, X, Y, Psi, omega))) return fail(rc);
@@ -1128,7 +1194,7 @@ int gpz_phi(gpz_ctx* c, const double* theta, int which, double* PHI, double* lnB
     std::vector<double> hbuf;
     for (int64_t r0 = 0; r0 < n; r0 += c->chunk_rows) {
         const int64_t r1 = (r0 + c->chunk_rows < n) ? r0 + c->chunk_rows : n;
-        if ((rc = phi_build(P, R, r0, r1, c->Phi, DotSpec{0, {nullptr, nullptr}, {nullptr, nullptr}}, st, &c->launches))) return rc;
+        if ((rc = phi_build(P, R, r0, r1, c->Phi, DotSpec{0, {nullptr, nullptr}, {nullptr, nullptr}}, c->dot_scratch, st, &c->launches))) return rc;
         if (P.het)
             for (int o = 0; o < P.k; ++o)
                 if ((rc = rowdot(c->Phi, MP, P.m, r1 - r0, DotSpec{1, {P.v + o * MP, nullptr}, {dotv + o * n + r0, nullptr}}, st, &c->launches))) return rc;
@@ -1230,13 +1296,32 @@ int gpz_predict(const gpz_model* model, const double* theta, const double* w, co
     for (int o = 0; o < k; ++o)
         PR(cuda_ok(cudaMemcpy2DAsync(d_Sinv + static_cast<int64_t>(o) * MP * MP, sizeof(double) * MP, iSigma_w + static_cast<int64_t>(o) * P.m * P.m,
                                      sizeof(double) * P.m, sizeof(double) * P.m, P.m, cudaMemcpyHostToDevice, st), "H2D iSigma_w"));
-    PR(cuda_ok(cudaMemcpyAsync(d_X, Xz, sizeof(double) * n * P.d, cudaMemcpyHostToDevice, st), "H2D X"));
+    {   // store X relative to its column means (only x - p matters); prep_params shifts P by the same constant
+        std::vector<double> hx(static_cast<size_t>(n) * P.d), sh(static_cast<size_t>(P.d), 0.0);
+        for (int a = 0; a < P.d; ++a) {
+            const double* col = Xz + static_cast<int64_t>(a) * n;
+            double sum = 0.0;
+            int64_t cnt = 0;
+            for (int64_t i = 0; i < n; ++i)
+                if (col[i] == col[i]) { sum += col[i]; ++cnt; }
+            sh[a] = cnt > 0 ? sum / static_cast<double>(cnt) : 0.0;
+            for (int64_t i = 0; i < n; ++i) hx[static_cast<size_t>(a) * n + i] = col[i] - sh[a];
+        }
+        PR(cuda_ok(cudaMemcpy(d_X, hx.data(), sizeof(double) * n * P.d, cudaMemcpyHostToDevice), "H2D X"));
+        PR(cuda_ok(cudaMemcpy(P.xshift, sh.data(), sizeof(double) * P.d, cudaMemcpyHostToDevice), "H2D shift"));
+    }
     if (Psi) PR(cuda_ok(cudaMemcpyAsync(d_Psi, Psi, sizeof(double) * n * P.d, cudaMemcpyHostToDevice, st), "H2D Psi"));
     PR(prep_params(d_theta, P, 0, st, &launches));
     RowData R;
     R.n = n;
     R.X = d_X;
     R.Psi = d_Psi;
+    double* d_scratch = nullptr;
+    PR(dev_alloc(allocs, &d_scratch, 2 * (MP / TILE) * chunk));
+    if (!Psi) {
+        PR(dev_alloc(allocs, &R.F, n * P.QP));
+        PR(build_features(P, d_X, n, 0, n, R.F, st, &launches));
+    }
     {
         bool has_nan = false;
         for (int64_t i = 0; i < n * P.d && !has_nan; ++i) has_nan = Xz[i] != Xz[i];
@@ -1250,7 +1335,7 @@ int gpz_predict(const gpz_model* model, const double* theta, const double* w, co
         const int64_t r1 = (r0 + chunk < n) ? r0 + chunk : n;
         DotSpec ds{2, {P.v, d_w}, {d_dotv, d_mu}};
         if (k > 1) ds.n = 0;
-        PR(phi_build(P, R, r0, r1, d_Phi, ds, st, &launches));
+        PR(phi_build(P, R, r0, r1, d_Phi, ds, d_scratch, st, &launches));
         if (k > 1)
             for (int o = 0; o < k; ++o)
                 PR(rowdot(d_Phi, MP, P.m, r1 - r0, DotSpec{2, {P.v + o * MP, d_w + o * MP}, {d_dotv + o * n + r0, d_mu + o * n + r0}}, st, &launches));
@@ -1388,6 +1473,14 @@ int gpz_set_option(gpz_ctx* c, const char* name, double value) {
             return GPZ_ERR_USAGE;
         }
         c->opt_chunk_rows = static_cast<int64_t>(value);
+        return GPZ_OK;
+    }
+    if (strcmp(name, "tensor_phi") == 0 || strcmp(name, "fused_backproj") == 0) {
+        if (c->ws_ready) {
+            set_error("%s must be set before the first evaluation", name);
+            return GPZ_ERR_USAGE;
+        }
+        if (name[0] == 't') c->opt_tensor_phi = value != 0.0; else c->opt_fused_bp = value != 0.0;
         return GPZ_OK;
     }
     set_error("unknown option '%s'", name);

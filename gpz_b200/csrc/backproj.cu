@@ -47,11 +47,11 @@ features_kernel(const double* __restrict__ X, int64_t n, int64_t r0, int64_t r1,
     }
 }
 
-int build_features(const Params& P, const RowData& R, int64_t r0, int64_t r1, double* F, int QP, cudaStream_t st,
+int build_features(const Params& P, const double* X, int64_t n, int64_t r0, int64_t r1, double* F, cudaStream_t st,
                    int64_t* launches) {
     if (r1 <= r0) return GPZ_OK;
     features_kernel<<<static_cast<unsigned>(ceil_div(r1 - r0, 32)), 256, sizeof(double) * 32 * P.d, st>>>(
-        R.X, R.n, r0, r1, P.d, mode_is_cov(P.mode) ? 1 : 0, QP, F);
+        X, n, r0, r1, P.d, mode_is_cov(P.mode) ? 1 : 0, P.QP, F);
     GPZ_KERNEL_CHECK();
     ++*launches;
     return GPZ_OK;

@@ -160,8 +160,8 @@ atb_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__
 }
 
 // sum the split-K partials in fixed order and scatter the tiles into C (row-major, ldc)
-template <int TN, bool SYRK>
-__global__ void atb_reduce_kernel(const double* __restrict__ partial, int nsplit, int ntiles, int ntiles_n,
+template <bool SYRK>
+__global__ void atb_reduce_kernel(const double* __restrict__ partial, int nsplit, int ntiles, int ntiles_n, int TN,
                                   double* __restrict__ C, int64_t ldc) {
     const int tile = blockIdx.x;
     int jt, ct;
@@ -221,7 +221,7 @@ int gram_syrk_finish(const double* partial, int nsplit, int MP, int reduce, doub
     if (!reduce) return GPZ_OK;
     const int T = MP / TILE;
     const int ntri = T * (T + 1) / 2;
-    atb_reduce_kernel<TILE, true><<<ntri, 256, 0, st>>>(partial, nsplit, ntri, T, S, MP);
+    atb_reduce_kernel<true><<<ntri, 256, 0, st>>>(partial, nsplit, ntri, T, TILE, S, MP);
     GPZ_KERNEL_CHECK();
     ++*launches;
     return GPZ_OK;
@@ -243,7 +243,7 @@ int atb_general(const double* A, int64_t lda, int MP, const double* B, int64_t l
     if (rc) return rc;
     ++*launches;
     if (reduce) {
-        atb_reduce_kernel<32, false><<<tm * tn, 256, 0, st>>>(partial, nsplit, tm * tn, tn, R, QP);
+        atb_reduce_kernel<false><<<tm * tn, 256, 0, st>>>(partial, nsplit, tm * tn, tn, 32, R, QP);
         GPZ_KERNEL_CHECK();
         ++*launches;
     }
@@ -251,17 +251,38 @@ int atb_general(const double* A, int64_t lda, int MP, const double* B, int64_t l
 }
 
 // ------------------------------------------------------------------------------------------------
-// T = PHI * iSigma with fused epilogue
+// row-tile GEMM  C(128 x 128 tile) = A[rows][K] * B[K][cols]  with two fused epilogues
+//   EPI_T   (A = PHI, B = iSigma):  h = PHI_ij * T_ij ; nu partial = sum_j h ; H (+)= rw_i * h      GPz.m:69,72
+//   EPI_PHI (A = row features F, B = per-basis coefficients W):  PHI_ij = exp(F_i . W_j)             getPHI.m:60-113
+//           (the quadratic form -1/2 (x-p)' A_j (x-p) expanded in the monomials of x), PHI stored row-major,
+//           plus up to two fused row-dot partials  sum_j PHI_ij vec_q[j]  (ln-noise head getPHI.m:124, PHI*w)
 // ------------------------------------------------------------------------------------------------
+struct TEpi {
+    const double* Phi;      // [rows][ld] (same matrix as A)
+    const double* rw;       // row weights omega*beta (may be null)
+    double* H;              // may be null
+    int accumulate;
+    double* nupart;         // [ntn][nu_ld]
+    int64_t nu_ld;
+};
+struct PEpi {
+    int m;
+    double* Phi;            // [rows][MP] (may be null)
+    int ndot;
+    const double* vec[2];
+    double* part[2];        // [ntn][part_ld]
+    int64_t part_ld;
+};
+
+template <int EPI>
 __global__ void __launch_bounds__(256, 1)
-tgemm_kernel(const double* __restrict__ Phi, int64_t ld, const double* __restrict__ Sinv, int MP, int nk, int64_t n,
-             const double* __restrict__ rw, double* __restrict__ H, int accumulate, double* __restrict__ nupart,
-             int64_t nu_ld) {
+tgemm_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int MP, int nk, int64_t n,
+             TEpi te, PEpi pe) {
     constexpr int WM = 64, MT = 8, NT = 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* As = reinterpret_cast<double*>(smem_raw);          // [STAGES][TILE][LDK]
     double* Bs = As + STAGES * TILE * LDK;                     // [STAGES][KSTEP][LDT]
-    __shared__ double red[4][TILE];
+    __shared__ double red[2][4][TILE];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -284,13 +305,13 @@ tgemm_kernel(const double* __restrict__ Phi, int64_t ld, const double* __restric
             const int r = c >> 3, cc = c & 7;
             const int64_t gr = i0 + r;
             const bool ok = gr < n;
-            cp_async16(as + r * LDK + cc * 2, Phi + (ok ? gr : 0) * ld + k0 + cc * 2, ok ? 16 : 0);
+            cp_async16(as + r * LDK + cc * 2, A + (ok ? gr : 0) * lda + k0 + cc * 2, ok ? 16 : 0);
         }
 #pragma unroll
         for (int q = 0; q < (KSTEP * TILE / 2) / 256; ++q) {
             const int c = tid + q * 256;
             const int r = c >> 6, cc = c & 63;
-            cp_async16(bs + r * LDT + cc * 2, Sinv + static_cast<int64_t>(k0 + r) * MP + j0 + cc * 2, 16);
+            cp_async16(bs + r * LDT + cc * 2, B + static_cast<int64_t>(k0 + r) * MP + j0 + cc * 2, 16);
         }
     };
 
@@ -332,66 +353,339 @@ tgemm_kernel(const double* __restrict__ Phi, int64_t ld, const double* __restric
     }
     cp_async_wait<0>();
 
-    // epilogue: h = PHI_ij * T_ij ; nu partial over this tile's 128 columns ; H (+)= rw_i * h
-    double rs[MT];
+    double rs0[MT], rs1[MT];
+    if (EPI == 0) {
+        // h = PHI_ij * T_ij ; nu partial over this tile's 128 columns ; H (+)= rw_i * h
 #pragma unroll
-    for (int i = 0; i < MT; ++i) {
-        const int64_t gi = i0 + wm0 + i * 8 + g;
-        const bool ok = gi < n;
-        double s = 0.0;
-        const double wrow = (rw != nullptr && ok) ? rw[gi] : 1.0;
+        for (int i = 0; i < MT; ++i) {
+            const int64_t gi = i0 + wm0 + i * 8 + g;
+            const bool ok = gi < n;
+            double s = 0.0;
+            const double wrow = (te.rw != nullptr && ok) ? te.rw[gi] : 1.0;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const int64_t gj = j0 + wn0 + j * 8 + 2 * t;
+                if (ok) {
+                    const double2 ph = *reinterpret_cast<const double2*>(te.Phi + gi * lda + gj);
+                    const double h0 = ph.x * acc[i][j][0], h1 = ph.y * acc[i][j][1];
+                    s += h0 + h1;
+                    if (te.H != nullptr) {
+                        double2* hp = reinterpret_cast<double2*>(te.H + gi * lda + gj);
+                        double2 v = make_double2(wrow * h0, wrow * h1);
+                        if (te.accumulate) {
+                            const double2 o = *hp;
+                            v.x += o.x;
+                            v.y += o.y;
+                        }
+                        *hp = v;
+                    }
+                }
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            rs0[i] = s;
+            rs1[i] = 0.0;
+        }
+    } else {
+        double2 v0[NT], v1[NT];
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
             const int64_t gj = j0 + wn0 + j * 8 + 2 * t;
-            if (ok) {
-                const double2 ph = *reinterpret_cast<const double2*>(Phi + gi * ld + gj);
-                const double h0 = ph.x * acc[i][j][0], h1 = ph.y * acc[i][j][1];
-                s += h0 + h1;
-                if (H != nullptr) {
-                    double2* hp = reinterpret_cast<double2*>(H + gi * ld + gj);
-                    double2 v = make_double2(wrow * h0, wrow * h1);
-                    if (accumulate) {
-                        const double2 o = *hp;
-                        v.x += o.x;
-                        v.y += o.y;
-                    }
-                    *hp = v;
-                }
-            }
+            v0[j] = pe.ndot > 0 ? *reinterpret_cast<const double2*>(pe.vec[0] + gj) : make_double2(0.0, 0.0);
+            v1[j] = pe.ndot > 1 ? *reinterpret_cast<const double2*>(pe.vec[1] + gj) : make_double2(0.0, 0.0);
         }
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        rs[i] = s;
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            const int64_t gi = i0 + wm0 + i * 8 + g;
+            const bool ok = gi < n;
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const int64_t gj = j0 + wn0 + j * 8 + 2 * t;
+                const double p0 = (gj < pe.m) ? exp(acc[i][j][0]) : 0.0;
+                const double p1 = (gj + 1 < pe.m) ? exp(acc[i][j][1]) : 0.0;
+                if (ok && pe.Phi != nullptr) *reinterpret_cast<double2*>(pe.Phi + gi * MP + gj) = make_double2(p0, p1);
+                s0 = fma(p0, v0[j].x, fma(p1, v0[j].y, s0));
+                s1 = fma(p0, v1[j].x, fma(p1, v1[j].y, s1));
+            }
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+            rs0[i] = s0;
+            rs1[i] = s1;
+        }
     }
     if (t == 0) {
 #pragma unroll
-        for (int i = 0; i < MT; ++i) red[warp & 3][wm0 + i * 8 + g] = rs[i];
+        for (int i = 0; i < MT; ++i) {
+            red[0][warp & 3][wm0 + i * 8 + g] = rs0[i];
+            if (EPI == 1) red[1][warp & 3][wm0 + i * 8 + g] = rs1[i];
+        }
     }
     __syncthreads();
     if (tid < TILE) {
         const int64_t gi = i0 + tid;
-        if (gi < n) nupart[static_cast<int64_t>(ct) * nu_ld + gi] = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
+        if (gi < n) {
+            if (EPI == 0) {
+                te.nupart[static_cast<int64_t>(ct) * te.nu_ld + gi] = red[0][0][tid] + red[0][1][tid] + red[0][2][tid] + red[0][3][tid];
+            } else {
+                if (pe.ndot > 0) pe.part[0][static_cast<int64_t>(ct) * pe.part_ld + gi] = red[0][0][tid] + red[0][1][tid] + red[0][2][tid] + red[0][3][tid];
+                if (pe.ndot > 1) pe.part[1][static_cast<int64_t>(ct) * pe.part_ld + gi] = red[1][0][tid] + red[1][1][tid] + red[1][2][tid] + red[1][3][tid];
+            }
+        }
     }
 }
 
-int tgemm(const double* Phi, int64_t ld, const double* Sinv, int MP, int m, int64_t n, const double* rw, double* H,
-          int accumulate, double* nupart, int64_t nu_ld, cudaStream_t st, int64_t* launches) {
+template <int EPI>
+static int launch_tgemm(const double* A, int64_t lda, const double* B, int MP, int nk, int64_t n, const TEpi& te,
+                        const PEpi& pe, cudaStream_t st) {
     const size_t smem = sizeof(double) * (STAGES * TILE * LDK + STAGES * KSTEP * LDT);
     static bool configured = false;
     if (!configured) {
-        GPZ_CUDA(cudaFuncSetAttribute(tgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        GPZ_CUDA(cudaFuncSetAttribute(tgemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         configured = true;
     }
-    if (n <= 0) return GPZ_OK;
-    const int nk = static_cast<int>(round_up(m, KSTEP) / KSTEP);
     const int64_t nblk = ceil_div(n, TILE) * (MP / TILE);
     if (nblk > 2147483647LL) {
         set_error("tgemm: grid too large");
         return GPZ_ERR_USAGE;
     }
-    tgemm_kernel<<<static_cast<unsigned>(nblk), 256, smem, st>>>(Phi, ld, Sinv, MP, nk, n, rw, H, accumulate, nupart, nu_ld);
+    tgemm_kernel<EPI><<<static_cast<unsigned>(nblk), 256, smem, st>>>(A, lda, B, MP, nk, n, te, pe);
     GPZ_KERNEL_CHECK();
+    return GPZ_OK;
+}
+
+int tgemm(const double* Phi, int64_t ld, const double* Sinv, int MP, int m, int64_t n, const double* rw, double* H,
+          int accumulate, double* nupart, int64_t nu_ld, cudaStream_t st, int64_t* launches) {
+    if (n <= 0) return GPZ_OK;
+    const int nk = static_cast<int>(round_up(m, KSTEP) / KSTEP);
+    TEpi te{Phi, rw, H, accumulate, nupart, nu_ld};
+    PEpi pe{};
+    int rc = launch_tgemm<0>(Phi, ld, Sinv, MP, nk, n, te, pe, st);
+    if (!rc) ++*launches;
+    return rc;
+}
+
+// PHI = exp(F W): F [n][ldf] row features (K = kq columns used, kq % 16 == 0), W [kq][MP] coefficients
+int phi_gemm(const double* F, int64_t ldf, int kq, const double* W, int MP, int m, int64_t n, double* Phi, int ndot,
+             const double* vec0, const double* vec1, double* part0, double* part1, int64_t part_ld, cudaStream_t st,
+             int64_t* launches) {
+    if (n <= 0) return GPZ_OK;
+    TEpi te{};
+    PEpi pe{m, Phi, ndot, {vec0, vec1}, {part0, part1}, part_ld};
+    int rc = launch_tgemm<1>(F, ldf, W, MP, kq / KSTEP, n, te, pe, st);
+    if (!rc) ++*launches;
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused back-projection GEMM:  R[j][c] = sum_i dPHI_ij F_ic  with dPHI formed on the fly,
+//   dPHI_ij = -H_ij + PHI_ij (cw_i w_j + dbeta_i v_j)                         GPz.m:72,90,106,113
+// and the column sums  q_j = sum_i PHI_ij (-cw_i),  dv_j = sum_i PHI_ij dbeta_i   GPz.m:89,104
+// The A operand goes global -> registers -> (transform) -> shared; F tiles use cp.async.
+// CTA tile: 128 bases x TN = 8*NT feature columns (all of QP), split over rows.
+// ------------------------------------------------------------------------------------------------
+constexpr int DSTAGES = 3;
+
+template <int NT>
+__global__ void __launch_bounds__(256, 1)
+atb_dphi_kernel(const double* __restrict__ Phi, const double* __restrict__ H, int64_t ld, const double* __restrict__ F,
+                int64_t ldf, const double* __restrict__ cw, const double* __restrict__ dbeta,
+                const double* __restrict__ w, const double* __restrict__ v, int64_t row0, int64_t row1,
+                int64_t rows_per_split, double* __restrict__ partial, double* __restrict__ colp, int MP, int accumulate) {
+    constexpr int TN = 8 * NT;
+    constexpr int LDB = TN + 4;
+    constexpr int MT = 2;                    // 8 warps x 16 bases
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* As = reinterpret_cast<double*>(smem_raw);           // [DSTAGES][KSTEP][LDT]
+    double* Bs = As + DSTAGES * KSTEP * LDT;                    // [DSTAGES][KSTEP][LDB]
+    __shared__ double csum[4][4][64];                           // [row group][q0,q1,v0,v1][column pair]
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm0 = warp * 16;
+    const int jt = blockIdx.x;
+    const int64_t a_col0 = static_cast<int64_t>(jt) * TILE;
+    const int64_t rbeg = row0 + static_cast<int64_t>(blockIdx.y) * rows_per_split;
+    int64_t rend = rbeg + rows_per_split;
+    if (rend > row1) rend = row1;
+    const int64_t nrows = rend > rbeg ? rend - rbeg : 0;
+    const int nk = static_cast<int>((nrows + KSTEP - 1) / KSTEP);
+
+    // this thread's fixed column pair and row group in the A tile
+    const int cc = tid & 63, rg = tid >> 6;
+    const double2 wj = *reinterpret_cast<const double2*>(w + a_col0 + cc * 2);
+    const double2 vj = *reinterpret_cast<const double2*>(v + a_col0 + cc * 2);
+    double sq0 = 0.0, sq1 = 0.0, sv0 = 0.0, sv1 = 0.0;
+
+    double2 rp[4], rh[4];
+    double rc_[4], rd_[4];
+    auto load_a_regs = [&](int kt) {
+        const int64_t rb = rbeg + static_cast<int64_t>(kt) * KSTEP;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int64_t gr = rb + rg + 4 * q;
+            if (gr < rend) {
+                rp[q] = *reinterpret_cast<const double2*>(Phi + gr * ld + a_col0 + cc * 2);
+                rh[q] = *reinterpret_cast<const double2*>(H + gr * ld + a_col0 + cc * 2);
+                rc_[q] = __ldg(cw + gr);
+                rd_[q] = __ldg(dbeta + gr);
+            } else {
+                rp[q] = rh[q] = make_double2(0.0, 0.0);
+                rc_[q] = rd_[q] = 0.0;
+            }
+        }
+    };
+    auto store_a_smem = [&](int stage) {
+        double* as = As + stage * KSTEP * LDT;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double c0 = fma(rc_[q], wj.x, rd_[q] * vj.x), c1 = fma(rc_[q], wj.y, rd_[q] * vj.y);
+            const double2 dphi = make_double2(fma(rp[q].x, c0, -rh[q].x), fma(rp[q].y, c1, -rh[q].y));
+            *reinterpret_cast<double2*>(as + (rg + 4 * q) * LDT + cc * 2) = dphi;
+            sq0 = fma(rp[q].x, -rc_[q], sq0);
+            sq1 = fma(rp[q].y, -rc_[q], sq1);
+            sv0 = fma(rp[q].x, rd_[q], sv0);
+            sv1 = fma(rp[q].y, rd_[q], sv1);
+        }
+    };
+    auto load_b = [&](int kt, int stage) {
+        const int64_t rb = rbeg + static_cast<int64_t>(kt) * KSTEP;
+        double* bs = Bs + stage * KSTEP * LDB;
+        constexpr int BCH = KSTEP * TN / 2;
+#pragma unroll
+        for (int q = 0; q < (BCH + 255) / 256; ++q) {
+            const int c = tid + q * 256;
+            if (c < BCH) {
+                const int r = c / (TN / 2), c2 = c % (TN / 2);
+                const int64_t gr = rb + r;
+                const bool ok = gr < rend;
+                cp_async16(bs + r * LDB + c2 * 2, F + (ok ? gr : row0) * ldf + c2 * 2, ok ? 16 : 0);
+            }
+        }
+    };
+
+    double acc[MT][NT][2];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < DSTAGES - 1; ++s) {
+        if (s < nk) {
+            load_a_regs(s);
+            store_a_smem(s);
+            load_b(s, s);
+        }
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<DSTAGES - 2>();
+        __syncthreads();
+        const int nx = kt + DSTAGES - 1;
+        const bool more = nx < nk;
+        if (more) {
+            load_a_regs(nx);
+            load_b(nx, nx % DSTAGES);
+        }
+        cp_async_commit();
+        const int stage = kt % DSTAGES;
+        const double* as = As + stage * KSTEP * LDT;
+        const double* bs = Bs + stage * KSTEP * LDB;
+#pragma unroll
+        for (int kk = 0; kk < KSTEP / 4; ++kk) {
+            const int kr = kk * 4 + t;
+            double bf[NT];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) bf[j] = bs[kr * LDB + j * 8 + g];
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
+                const double af = as[kr * LDT + wm0 + i * 8 + g];
+#pragma unroll
+                for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], af, bf[j]);
+            }
+        }
+        if (more) store_a_smem(nx % DSTAGES);
+    }
+    cp_async_wait<0>();
+
+    double* out = partial + (static_cast<int64_t>(blockIdx.y) * gridDim.x + jt) * (TILE * TN);
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+        const int r = wm0 + i * 8 + g;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int c = j * 8 + 2 * t;
+            double2* p = reinterpret_cast<double2*>(out + r * TN + c);
+            double2 val = make_double2(acc[i][j][0], acc[i][j][1]);
+            if (accumulate) {
+                const double2 o = *p;
+                val.x += o.x;
+                val.y += o.y;
+            }
+            *p = val;
+        }
+    }
+    // column sums: fixed-order sum over the 4 row groups
+    csum[rg][0][cc] = sq0;
+    csum[rg][1][cc] = sq1;
+    csum[rg][2][cc] = sv0;
+    csum[rg][3][cc] = sv1;
+    __syncthreads();
+    if (tid < 128) {
+        const int c2 = tid >> 1, e = tid & 1;
+        const double q = csum[0][e][c2] + csum[1][e][c2] + csum[2][e][c2] + csum[3][e][c2];
+        const double dv = csum[0][2 + e][c2] + csum[1][2 + e][c2] + csum[2][2 + e][c2] + csum[3][2 + e][c2];
+        double* cp = colp + static_cast<int64_t>(blockIdx.y) * 2 * MP + a_col0 + tid;
+        cp[0] = (accumulate ? cp[0] : 0.0) + q;
+        cp[MP] = (accumulate ? cp[MP] : 0.0) + dv;
+    }
+}
+
+template <int NT>
+static int launch_atb_dphi(const double* Phi, const double* H, int64_t ld, const double* F, int64_t ldf, const double* cw,
+                           const double* dbeta, const double* w, const double* v, int64_t row0, int64_t row1, int nsplit,
+                           double* partial, double* colp, int MP, int accumulate, cudaStream_t st) {
+    constexpr int TN = 8 * NT;
+    const size_t smem = sizeof(double) * (DSTAGES * KSTEP * LDT + DSTAGES * KSTEP * (TN + 4));
+    static bool configured = false;
+    if (!configured) {
+        GPZ_CUDA(cudaFuncSetAttribute(atb_dphi_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        configured = true;
+    }
+    int64_t rps = ceil_div(row1 - row0, nsplit);
+    rps = round_up(rps > 0 ? rps : 1, KSTEP);
+    dim3 grid(MP / TILE, nsplit);
+    atb_dphi_kernel<NT><<<grid, 256, smem, st>>>(Phi, H, ld, F, ldf, cw, dbeta, w, v, row0, row1, rps, partial, colp, MP, accumulate);
+    GPZ_KERNEL_CHECK();
+    return GPZ_OK;
+}
+
+// QP in {32, 64, 96, 128}.  partial: nsplit * (MP/128) * 128 * QP doubles; colp: nsplit * 2 * MP doubles.
+int atb_dphi(const double* Phi, const double* H, int64_t ld, int MP, const double* F, int QP, const double* cw,
+             const double* dbeta, const double* w, const double* v, int64_t row0, int64_t row1, int nsplit, double* partial,
+             double* colp, int accumulate, int reduce, double* R, cudaStream_t st, int64_t* launches) {
+    int rc;
+    switch (QP) {
+        case 32: rc = launch_atb_dphi<4>(Phi, H, ld, F, QP, cw, dbeta, w, v, row0, row1, nsplit, partial, colp, MP, accumulate, st); break;
+        case 64: rc = launch_atb_dphi<8>(Phi, H, ld, F, QP, cw, dbeta, w, v, row0, row1, nsplit, partial, colp, MP, accumulate, st); break;
+        case 96: rc = launch_atb_dphi<12>(Phi, H, ld, F, QP, cw, dbeta, w, v, row0, row1, nsplit, partial, colp, MP, accumulate, st); break;
+        case 128: rc = launch_atb_dphi<16>(Phi, H, ld, F, QP, cw, dbeta, w, v, row0, row1, nsplit, partial, colp, MP, accumulate, st); break;
+        default:
+            set_error("atb_dphi: unsupported feature width %d", QP);
+            return GPZ_ERR_USAGE;
+    }
+    if (rc) return rc;
     ++*launches;
+    if (reduce) {
+        const int tm = MP / TILE;
+        atb_reduce_kernel<false><<<tm, 256, 0, st>>>(partial, nsplit, tm, 1, QP, R, QP);
+        GPZ_KERNEL_CHECK();
+        ++*launches;
+    }
     return GPZ_OK;
 }
 

@@ -26,6 +26,10 @@ struct Params {
     double* v;      // [k][MP]
     double* tau;    // [k][MP]
     double* bk;     // [k]
+    // fast path (no Psi, no NaN): PHI = exp(F W) on the fp64 tensor pipe
+    int q, KQ, QP;  // feature count, K extent (multiple of 16), row stride of F (multiple of 32)
+    double* Wc;     // [KQ][MP]     coefficients of the monomial features (zero rows/columns in the padding)
+    double* xshift; // [d]          constant subtracted from X at upload (and from P here): only x - p matters
 };
 
 struct RowData {          // one resident row set (training or validation rows of this rank)
@@ -35,6 +39,7 @@ struct RowData {          // one resident row set (training or validation rows o
     double* omega = nullptr;  // [n]
     double* Psi = nullptr;    // diag: [d][n]; cov: [n][d*d] (MATLAB d x d x n)
     int has_nan = 0;
+    double* F = nullptr;      // [n][QP] monomial row features (fast path only)
 };
 
 struct DotSpec {          // up to 2 fused row-dots  out_q[i] = sum_j PHI_ij vec_q[j]
@@ -45,8 +50,9 @@ struct DotSpec {          // up to 2 fused row-dots  out_q[i] = sum_j PHI_ij vec
 
 // ---- phi.cu
 int prep_params(const double* d_theta, const Params& P, int need_sigma, cudaStream_t st, int64_t* launches);
+// dot_scratch: >= 2 * (MP/128) * (r1-r0) doubles (row-dot partials of the tensor-core path)
 int phi_build(const Params& P, const RowData& R, int64_t r0, int64_t r1, double* Phi /*[rows][MP] at row r0 -> index 0*/,
-              const DotSpec& dots, cudaStream_t st, int64_t* launches);
+              const DotSpec& dots, double* dot_scratch, cudaStream_t st, int64_t* launches);
 int rowdot(const double* Phi, int64_t ld, int m, int64_t n, const DotSpec& dots, cudaStream_t st, int64_t* launches);
 int dxy_device(const double* X, int64_t n, const double* Y, int m, int d, double* D, cudaStream_t st);
 int transpose_out(const double* src_rowmajor, int64_t ld, int64_t n, int m, double* dst_colmajor, cudaStream_t st);
@@ -61,6 +67,12 @@ int atb_general(const double* A, int64_t lda, int MP, const double* B, int64_t l
                 cudaStream_t st, int64_t* launches);
 int tgemm(const double* Phi, int64_t ld, const double* Sinv, int MP, int m, int64_t n, const double* rw, double* H,
           int accumulate, double* nupart, int64_t nu_ld, cudaStream_t st, int64_t* launches);
+int phi_gemm(const double* F, int64_t ldf, int kq, const double* W, int MP, int m, int64_t n, double* Phi, int ndot,
+             const double* vec0, const double* vec1, double* part0, double* part1, int64_t part_ld, cudaStream_t st,
+             int64_t* launches);
+int atb_dphi(const double* Phi, const double* H, int64_t ld, int MP, const double* F, int QP, const double* cw,
+             const double* dbeta, const double* w, const double* v, int64_t row0, int64_t row1, int nsplit, double* partial,
+             double* colp, int accumulate, int reduce, double* R, cudaStream_t st, int64_t* launches);
 int sgemm(int M, int N, int K, double alpha, const double* A, int64_t sAi, int64_t sAk, const double* B, int64_t sBk,
           int64_t sBj, double beta, double* C, int64_t ldc, int lower_only, cudaStream_t st, int64_t* launches);
 
@@ -78,7 +90,7 @@ int spd_inverse(double* S, int m, int MP, double* Sinv, double* d_logdet, SolveW
                 int64_t* launches);
 
 // ---- backproj.cu
-int build_features(const Params& P, const RowData& R, int64_t r0, int64_t r1, double* F, int QP, cudaStream_t st,
+int build_features(const Params& P, const double* X, int64_t n, int64_t r0, int64_t r1, double* F, cudaStream_t st,
                    int64_t* launches);
 int feature_count(const Params& P);
 int finalize_moments(const Params& P, const double* Rm /*[MP][QP]*/, int QP, double* dP /*m*d*/, double* dG /*g_dim*/,

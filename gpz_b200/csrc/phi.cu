@@ -22,7 +22,8 @@ __global__ void prep_kernel(const double* __restrict__ th, Params P, int need_si
     const int d = P.d, m = P.m, MP = P.MP, k = P.k, dp = P.dp;
     const bool live = j < m;
     const double* thG = th + P.oG;
-    for (int a = 0; a < d; ++a) P.Pt[a * MP + j] = live ? th[a * m + j] : 0.0;
+    // centres are stored relative to the dataset shift (X was shifted by the same constant at upload)
+    for (int a = 0; a < d; ++a) P.Pt[a * MP + j] = live ? th[a * m + j] - P.xshift[a] : 0.0;
     if (!mode_is_cov(P.mode)) {
         for (int a = 0; a < d; ++a) {
             double gv = 0.0;
@@ -35,7 +36,21 @@ __global__ void prep_kernel(const double* __restrict__ th, Params P, int need_si
                 }
             }
             P.Gt[a * MP + j] = gv;
-            P.Ct[a * MP + j] = live ? gv * th[a * m + j] : 0.0;
+            const double pa = P.Pt[a * MP + j];
+            P.Ct[a * MP + j] = live ? gv * pa : 0.0;
+            if (P.Wc != nullptr) {          // lnPHI = sum_a [ -1/2 g^2 x^2 + g^2 p x - 1/2 g^2 p^2 ]
+                P.Wc[static_cast<int64_t>(1 + a) * MP + j] = live ? gv * gv * pa : 0.0;
+                P.Wc[static_cast<int64_t>(1 + d + a) * MP + j] = live ? -0.5 * gv * gv : 0.0;
+            }
+        }
+        if (P.Wc != nullptr) {
+            double c0 = 0.0;
+            for (int a = 0; a < d; ++a) {
+                const double gp = P.Ct[a * MP + j];
+                c0 = fma(gp, gp, c0);
+            }
+            P.Wc[j] = live ? -0.5 * c0 : 0.0;
+            for (int r = 1 + 2 * d; r < P.KQ; ++r) P.Wc[static_cast<int64_t>(r) * MP + j] = 0.0;
         }
     } else {
         const double* G = (P.mode == GC) ? thG : thG + static_cast<int64_t>(d) * d * j;   // Gamma_j(b,a) = G[b + a*d]
@@ -44,7 +59,7 @@ __global__ void prep_kernel(const double* __restrict__ th, Params P, int need_si
             for (int a = 0; a < dp; ++a) {
                 const double gv = (live && a < d) ? G[b + a * d] : 0.0;
                 P.Gam[(static_cast<int64_t>(b) * dp + a) * MP + j] = gv;
-                if (live && a < d) c += gv * th[a * m + j];
+                if (live && a < d) c += gv * P.Pt[a * MP + j];
             }
             P.Ct[b * MP + j] = c;
         }
@@ -55,6 +70,22 @@ __global__ void prep_kernel(const double* __restrict__ th, Params P, int need_si
                     for (int c = 0; c < d; ++c) s += G[c + a * d] * G[c + b * d];
                 P.Aj[(static_cast<int64_t>(a) * d + b) * MP + j] = live ? s : (a == b ? 1.0 : 0.0);
             }
+        if (P.Wc != nullptr) {              // lnPHI = -1/2 x'Ax + (Ap)'x - 1/2 p'Ap over the upper-triangular monomials
+            double c0 = 0.0;
+            int idx = 1 + d;
+            for (int a = 0; a < d; ++a) {
+                double bv = 0.0;
+                for (int b = 0; b < d; ++b) bv += P.Aj[(static_cast<int64_t>(a) * d + b) * MP + j] * P.Pt[b * MP + j];
+                c0 += bv * P.Pt[a * MP + j];
+                P.Wc[static_cast<int64_t>(1 + a) * MP + j] = live ? bv : 0.0;
+                for (int b = a; b < d; ++b, ++idx) {
+                    const double av = P.Aj[(static_cast<int64_t>(a) * d + b) * MP + j];
+                    P.Wc[static_cast<int64_t>(idx) * MP + j] = live ? (a == b ? -0.5 * av : -av) : 0.0;
+                }
+            }
+            P.Wc[j] = live ? -0.5 * c0 : 0.0;
+            for (int r = idx; r < P.KQ; ++r) P.Wc[static_cast<int64_t>(r) * MP + j] = 0.0;
+        }
         if (need_sigma) {
             StridedMat S{P.Sj + j, MP, d};
             StridedMat A{P.Aj + j, MP, d};
@@ -291,11 +322,34 @@ static int launch_phi(const Params& P, const RowData& R, int64_t r0, int64_t r1,
     return GPZ_OK;
 }
 
+__global__ void sum_parts_kernel(const double* __restrict__ part, int ntn, int64_t stride, int64_t count, double* __restrict__ out) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    double s = 0.0;
+    for (int t = 0; t < ntn; ++t) s += part[static_cast<int64_t>(t) * stride + i];
+    out[i] = s;
+}
+
 int phi_build(const Params& P, const RowData& R, int64_t r0, int64_t r1, double* Phi, const DotSpec& dots,
-              cudaStream_t st, int64_t* launches) {
+              double* dot_scratch, cudaStream_t st, int64_t* launches) {
     if (r1 <= r0) return GPZ_OK;
     int rc = GPZ_OK;
     const bool psi = R.Psi != nullptr;
+    if (R.F != nullptr && P.Wc != nullptr && !psi && !R.has_nan) {
+        // tensor-core path: PHI = exp(F W), row-dot partials per 128-column tile, then an ordered sum
+        const int64_t rows = r1 - r0;
+        const int ntn = P.MP / TILE;
+        double* p0 = dot_scratch;
+        double* p1 = dot_scratch + static_cast<int64_t>(ntn) * rows;
+        rc = phi_gemm(R.F + r0 * P.QP, P.QP, P.KQ, P.Wc, P.MP, P.m, rows, Phi, dots.n, dots.vec[0], dots.vec[1], p0, p1, rows, st, launches);
+        if (rc) return rc;
+        for (int q = 0; q < dots.n; ++q) {
+            sum_parts_kernel<<<static_cast<unsigned>(ceil_div(rows, 256)), 256, 0, st>>>(q == 0 ? p0 : p1, ntn, rows, rows, dots.out[q] + r0);
+            GPZ_KERNEL_CHECK();
+            ++*launches;
+        }
+        return GPZ_OK;
+    }
     if (!mode_is_cov(P.mode)) {
         if (!psi && !R.has_nan) rc = launch_phi<0, false>(P, R, r0, r1, Phi, dots, st);
         else if (!psi) rc = launch_phi<1, false>(P, R, r0, r1, Phi, dots, st);

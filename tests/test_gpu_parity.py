@@ -188,3 +188,35 @@ def test_large_n_properties():
     fm, _, _ = ctx.eval(theta - h * u)
     assert abs((fp - fm) / (2 * h) - g1 @ u) <= 1e-5 * max(1.0, np.linalg.norm(g1))
     ctx.close()
+
+
+@pytest.mark.parametrize("method", ["VD", "VC", "GL", "GC"])
+def test_tensor_core_phi_and_fused_backproj_agree_with_direct_kernels(method):
+    """The fast path (PHI = exp(F W) on the DMMA pipe, fused dPHI back-projection GEMM) against the
+    direct-difference kernels + materialised dPHI, and both against the oracle."""
+    model, theta, X, Y, Psi, omega, tr, va = problem(method, True, False, False, n=3000, d=5, m=140, seed=21)
+    ref = O.GPz(theta, model, X, Y, None, omega, tr, va)
+    gm = L.make_model(model.d, 1, model.m, method, True)
+    out = {}
+    for tp, fb in ((1, 1), (0, 0), (1, 0), (0, 1)):
+        ctx = L.Context(gm, X, Y, None, omega, tr, va)
+        ctx.set_option("tensor_phi", tp)
+        ctx.set_option("fused_backproj", fb)
+        out[(tp, fb)] = ctx.eval(theta)
+        assert_eval_matches(model, ref, *out[(tp, fb)])
+        ctx.close()
+    f0, g0, _ = out[(1, 1)]
+    for key, (f, g, _) in out.items():
+        assert abs(f - f0) <= 1e-12 * abs(f0) and rel(g, g0) <= 1e-10, key
+
+
+def test_unnormalised_inputs_with_large_offset():
+    """normalize=false style data (x ~ 50 +- 1): only x - p enters, the library stores X relative to its
+    column means so the monomial expansion does not cancel."""
+    model, theta, X, Y, Psi, omega, tr, va = problem("VC", True, False, False, n=1500, d=4, m=30, seed=31)
+    X = X + 50.0
+    theta = theta.copy()
+    theta[:model.m * model.d] += 50.0
+    ref, f, g, st, ctx = run_both(model, theta, X, Y, None, omega, tr, va)
+    assert_eval_matches(model, ref, f, g, st, tol=1e-8)
+    ctx.close()
