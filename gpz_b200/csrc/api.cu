@@ -1475,6 +1475,14 @@ int gpz_set_option(gpz_ctx* c, const char* name, double value) {
         c->opt_chunk_rows = static_cast<int64_t>(value);
         return GPZ_OK;
     }
+    if (strcmp(name, "gemm_warps") == 0) {          // process-wide: 8 or 16 warps per CTA in the Gram / T-GEMM kernels
+        if (value != 0.0 && value != 8.0 && value != 16.0) {
+            set_error("gemm_warps must be 0 (defaults), 8 or 16");
+            return GPZ_ERR_USAGE;
+        }
+        g_gemm_warps = static_cast<int>(value);
+        return GPZ_OK;
+    }
     if (strcmp(name, "tensor_phi") == 0 || strcmp(name, "fused_backproj") == 0) {
         if (c->ws_ready) {
             set_error("%s must be set before the first evaluation", name);

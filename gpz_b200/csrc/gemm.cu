@@ -15,16 +15,17 @@
 namespace gpz {
 
 constexpr int STAGES = 4;
+int g_gemm_warps = 0;       // 0 = measured defaults (T-GEMM 16 warps, Gram 8 warps); 8 / 16 force both (gpz_set_option)
 
 // ------------------------------------------------------------------------------------------------
 // C = A' diag(w) B over a row range, 128 x TN output tile per CTA, split over rows
 // ------------------------------------------------------------------------------------------------
 template <int WARPS_M, int WARPS_N, bool SYRK>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, 1)
 atb_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
            const double* __restrict__ wgt, int64_t row0, int64_t row1, int64_t rows_per_split,
            int ntiles_n, double* __restrict__ partial, int accumulate) {
-    static_assert(WARPS_M * WARPS_N == 8, "8 warps");
+    constexpr int NTHR = WARPS_M * WARPS_N * 32;
     constexpr int TN = WARPS_N * 32;
     constexpr int LDB = TN + 4;
     constexpr int WM = TILE / WARPS_M;   // warp tile rows
@@ -68,8 +69,8 @@ atb_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__
         double* as = As + stage * KSTEP * LDT;
         double* bs = Bs + stage * KSTEP * LDB;
 #pragma unroll
-        for (int q = 0; q < (KSTEP * TILE / 2) / 256; ++q) {
-            const int c = tid + q * 256;
+        for (int q = 0; q < (KSTEP * TILE / 2) / NTHR; ++q) {
+            const int c = tid + q * NTHR;
             const int r = c >> 6, cc = c & 63;
             const int64_t gr = rb + r;
             const bool ok = gr < rend;
@@ -79,8 +80,8 @@ atb_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__
         if (!alias) {
             constexpr int BCH = KSTEP * TN / 2;      // 16-byte chunks in the B tile
 #pragma unroll
-            for (int q = 0; q < (BCH + 255) / 256; ++q) {
-                const int c = tid + q * 256;
+            for (int q = 0; q < (BCH + NTHR - 1) / NTHR; ++q) {
+                const int c = tid + q * NTHR;
                 if (c < BCH) {
                     const int r = c / (TN / 2), cc = c % (TN / 2);
                     const int64_t gr = rb + r;
@@ -199,8 +200,8 @@ static int launch_atb(const double* A, int64_t lda, const double* B, int64_t ldb
     int64_t rps = ceil_div(row1 - row0, nsplit);
     rps = round_up(rps > 0 ? rps : 1, KSTEP);
     dim3 grid(ntiles, nsplit);
-    atb_kernel<WARPS_M, WARPS_N, SYRK><<<grid, 256, smem, st>>>(A, lda, B, ldb, wgt, row0, row1, rps, ntiles_n, partial,
-                                                               accumulate);
+    atb_kernel<WARPS_M, WARPS_N, SYRK><<<grid, WARPS_M * WARPS_N * 32, smem, st>>>(A, lda, B, ldb, wgt, row0, row1, rps, ntiles_n,
+                                                                                  partial, accumulate);
     GPZ_KERNEL_CHECK();
     return GPZ_OK;
 }
@@ -211,7 +212,8 @@ int gram_syrk_main(const double* Phi, int64_t ld, int MP, const double* wgt, int
                    double* partial, int accumulate, cudaStream_t st, int64_t* launches) {
     const int T = MP / TILE;
     const int ntri = T * (T + 1) / 2;
-    int rc = launch_atb<2, 4, true>(Phi, ld, Phi, ld, wgt, row0, row1, ntri, T, nsplit, partial, accumulate, st);
+    int rc = g_gemm_warps == 16 ? launch_atb<4, 4, true>(Phi, ld, Phi, ld, wgt, row0, row1, ntri, T, nsplit, partial, accumulate, st)
+                                : launch_atb<2, 4, true>(Phi, ld, Phi, ld, wgt, row0, row1, ntri, T, nsplit, partial, accumulate, st);
     if (rc) return rc;
     ++*launches;
     return GPZ_OK;
@@ -274,11 +276,12 @@ struct PEpi {
     int64_t part_ld;
 };
 
-template <int EPI>
-__global__ void __launch_bounds__(256, 1)
+template <int EPI, int WARPS_M>
+__global__ void __launch_bounds__(WARPS_M * 128, 1)
 tgemm_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int MP, int nk, int64_t n,
              TEpi te, PEpi pe) {
-    constexpr int WM = 64, MT = 8, NT = 4;
+    constexpr int NTHR = WARPS_M * 128;
+    constexpr int WM = TILE / WARPS_M, MT = WM / 8, NT = 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* As = reinterpret_cast<double*>(smem_raw);          // [STAGES][TILE][LDK]
     double* Bs = As + STAGES * TILE * LDK;                     // [STAGES][KSTEP][LDT]
@@ -300,16 +303,16 @@ tgemm_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict
         double* as = As + stage * TILE * LDK;
         double* bs = Bs + stage * KSTEP * LDT;
 #pragma unroll
-        for (int q = 0; q < (TILE * KSTEP / 2) / 256; ++q) {
-            const int c = tid + q * 256;
+        for (int q = 0; q < (TILE * KSTEP / 2) / NTHR; ++q) {
+            const int c = tid + q * NTHR;
             const int r = c >> 3, cc = c & 7;
             const int64_t gr = i0 + r;
             const bool ok = gr < n;
             cp_async16(as + r * LDK + cc * 2, A + (ok ? gr : 0) * lda + k0 + cc * 2, ok ? 16 : 0);
         }
 #pragma unroll
-        for (int q = 0; q < (KSTEP * TILE / 2) / 256; ++q) {
-            const int c = tid + q * 256;
+        for (int q = 0; q < (KSTEP * TILE / 2) / NTHR; ++q) {
+            const int c = tid + q * NTHR;
             const int r = c >> 6, cc = c & 63;
             cp_async16(bs + r * LDT + cc * 2, B + static_cast<int64_t>(k0 + r) * MP + j0 + cc * 2, 16);
         }
@@ -437,13 +440,13 @@ tgemm_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict
     }
 }
 
-template <int EPI>
+template <int EPI, int WARPS_M>
 static int launch_tgemm(const double* A, int64_t lda, const double* B, int MP, int nk, int64_t n, const TEpi& te,
                         const PEpi& pe, cudaStream_t st) {
     const size_t smem = sizeof(double) * (STAGES * TILE * LDK + STAGES * KSTEP * LDT);
     static bool configured = false;
     if (!configured) {
-        GPZ_CUDA(cudaFuncSetAttribute(tgemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        GPZ_CUDA(cudaFuncSetAttribute(tgemm_kernel<EPI, WARPS_M>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         configured = true;
     }
     const int64_t nblk = ceil_div(n, TILE) * (MP / TILE);
@@ -451,7 +454,7 @@ static int launch_tgemm(const double* A, int64_t lda, const double* B, int MP, i
         set_error("tgemm: grid too large");
         return GPZ_ERR_USAGE;
     }
-    tgemm_kernel<EPI><<<static_cast<unsigned>(nblk), 256, smem, st>>>(A, lda, B, MP, nk, n, te, pe);
+    tgemm_kernel<EPI, WARPS_M><<<static_cast<unsigned>(nblk), WARPS_M * 128, smem, st>>>(A, lda, B, MP, nk, n, te, pe);
     GPZ_KERNEL_CHECK();
     return GPZ_OK;
 }
@@ -462,7 +465,7 @@ int tgemm(const double* Phi, int64_t ld, const double* Sinv, int MP, int m, int6
     const int nk = static_cast<int>(round_up(m, KSTEP) / KSTEP);
     TEpi te{Phi, rw, H, accumulate, nupart, nu_ld};
     PEpi pe{};
-    int rc = launch_tgemm<0>(Phi, ld, Sinv, MP, nk, n, te, pe, st);
+    int rc = g_gemm_warps != 8 ? launch_tgemm<0, 4>(Phi, ld, Sinv, MP, nk, n, te, pe, st) : launch_tgemm<0, 2>(Phi, ld, Sinv, MP, nk, n, te, pe, st);
     if (!rc) ++*launches;
     return rc;
 }
@@ -474,7 +477,8 @@ int phi_gemm(const double* F, int64_t ldf, int kq, const double* W, int MP, int 
     if (n <= 0) return GPZ_OK;
     TEpi te{};
     PEpi pe{m, Phi, ndot, {vec0, vec1}, {part0, part1}, part_ld};
-    int rc = launch_tgemm<1>(F, ldf, W, MP, kq / KSTEP, n, te, pe, st);
+    int rc = g_gemm_warps != 8 ? launch_tgemm<1, 4>(F, ldf, W, MP, kq / KSTEP, n, te, pe, st)
+                                : launch_tgemm<1, 2>(F, ldf, W, MP, kq / KSTEP, n, te, pe, st);
     if (!rc) ++*launches;
     return rc;
 }

@@ -58,6 +58,7 @@ int dxy_device(const double* X, int64_t n, const double* Y, int m, int d, double
 int transpose_out(const double* src_rowmajor, int64_t ld, int64_t n, int m, double* dst_colmajor, cudaStream_t st);
 
 // ---- gemm.cu
+extern int g_gemm_warps;
 int gram_nsplit(int MP, int sm_count);
 int gram_syrk_main(const double* Phi, int64_t ld, int MP, const double* wgt, int64_t row0, int64_t row1, int nsplit,
                    double* partial, int accumulate, cudaStream_t st, int64_t* launches);

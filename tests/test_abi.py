@@ -48,3 +48,16 @@ def test_no_cpu_fallback():
         L.inv_logdet(np.eye(3))
     with pytest.raises(L.GpzError):
         L.dxy(np.zeros((3, 2)), np.zeros((2, 2)))
+
+
+def test_mex_gateway_source_compiles_against_stub():
+    """matlab/gpz_b200_mex.cpp cannot be built without MATLAB; at least keep it syntactically valid and in
+    step with include/gpz_b200.h (g++ -fsyntax-only against a stub mex.h)."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I" + os.path.join(ROOT, "include"),
+                        "-I" + os.path.join(ROOT, "tests", "mex_stub"), os.path.join(ROOT, "matlab", "gpz_b200_mex.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

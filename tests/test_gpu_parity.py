@@ -203,11 +203,13 @@ def test_tensor_core_phi_and_fused_backproj_agree_with_direct_kernels(method):
         ctx.set_option("tensor_phi", tp)
         ctx.set_option("fused_backproj", fb)
         out[(tp, fb)] = ctx.eval(theta)
-        assert_eval_matches(model, ref, *out[(tp, fb)])
+        # m=140 bases on 2400 rows: SIGMA is ill-conditioned here, so the oracle's SVD pseudo-inverse and the
+        # Cholesky inverse differ at the 1e-9 level in dlnAlpha; the stated tolerance is 1e-5
+        assert_eval_matches(model, ref, *out[(tp, fb)], tol=1e-7)
         ctx.close()
     f0, g0, _ = out[(1, 1)]
     for key, (f, g, _) in out.items():
-        assert abs(f - f0) <= 1e-12 * abs(f0) and rel(g, g0) <= 1e-10, key
+        assert abs(f - f0) <= 1e-11 * abs(f0) and rel(g, g0) <= 1e-8, key
 
 
 def test_unnormalised_inputs_with_large_offset():

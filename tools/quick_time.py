@@ -14,13 +14,14 @@ def dgemm_peak(N=8192, reps=5):
         best = min(best, e0.elapsed_time(e1))
     return 2 * N**3 / best / 1e9
 
-print("cuBLAS DGEMM 8192^3 TF/s:", dgemm_peak())
+if not os.environ.get("NO_PEAK"): print("cuBLAS DGEMM 8192^3 TF/s:", dgemm_peak())
 cfgs = [("VD", 100000, 10, 500), ("VC", 100000, 10, 1000), ("VC", 1000000, 10, 1000), ("VD", 1000000, 10, 500)]
-if len(sys.argv) > 1: cfgs = cfgs[:int(sys.argv[1])]
+if len(sys.argv) > 1: cfgs = [cfgs[int(i)] for i in sys.argv[1].split(",")]
 for meth, n, d, m in cfgs:
     X, Y = synth.make_data(n, d, seed=0)
     th = synth.make_theta0(X, Y, meth, m, het=True, seed=1)
     t0 = time.time(); ctx = L.Context(L.make_model(d, 1, m, meth, True), X, Y); t1 = time.time()
+    if os.environ.get("GEMM_WARPS"): ctx.set_option("gemm_warps", float(os.environ["GEMM_WARPS"]))
     f, g, st = ctx.eval(th)
     ts = []
     for _ in range(3):
