@@ -284,6 +284,12 @@ symv_kernel(const double* __restrict__ Sinv, int MP, int m, const double* __rest
     if (lane == 0) y[j] = (j < m) ? scale * s : 0.0;
 }
 
+// iSigma[l][m] := w[l] (l < m): the spare column of the T-GEMM's B operand, so that T[:, m] = PHI*w
+__global__ void set_aug_col_kernel(double* __restrict__ Sinv, int MP, int m, const double* __restrict__ w) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < m) Sinv[static_cast<int64_t>(l) * MP + m] = w[l];
+}
+
 struct FinishArgs {
     Params P;
     const double* theta;
@@ -435,10 +441,12 @@ struct gpz_ctx {
     int64_t opt_chunk_rows = 0;     // 0 = auto
     int opt_tensor_phi = 1;         // 1: PHI = exp(F W) on the DMMA pipe; 0: direct-difference kernels
     int opt_fused_bp = 1;           // 1: fused dPHI + back-projection GEMM; 0: materialise dPHI first
+    int opt_aug = 1;                // 1: spare-column trick (see aug)
     std::vector<double> h_shift;    // constant subtracted from X at upload
     double* Wc_alloc = nullptr;
     double* dot_scratch = nullptr;
     int dphi_slabs = 1, fused_ns = 1;
+    bool aug = false;               // PHI[:, m] carries y and iSigma[:, m] carries w: r and PHI*w come out of the two big GEMMs
     // workspaces (allocated at first use)
     bool ws_ready = false;
     int64_t chunk_rows = 0;
@@ -740,6 +748,8 @@ int ensure_workspace(gpz_ctx* c) {
     }
     c->Wc_alloc = P.Wc;
     if (!c->opt_tensor_phi) P.Wc = nullptr;
+    c->aug = fast_bp && P.Wc != nullptr && k == 1 && P.m < MP && c->opt_aug;
+    if (c->aug) c->tr.ycol = c->tr.Y;
     {
         const int64_t dd = static_cast<int64_t>(P.d) * P.d;
         const int64_t sc = 2 * dd * MP + dd * P.m + static_cast<int64_t>(P.m) * P.d + 64;
@@ -804,8 +814,9 @@ int forward_and_solve(gpz_ctx* c, const double* d_theta) {
                 return GPZ_ERR_USAGE;
             }
         }
-        if ((rc = atb_general(phi, MP, static_cast<int>(MP), c->yw + r0 * 32, 32, 32, c->ones, 0, r1 - r0, ns1, c->atb_partial,
-                              nchunks > 0, last, c->Rvec, st, &c->launches))) return rc;
+        if (!c->aug)
+            if ((rc = atb_general(phi, MP, static_cast<int>(MP), c->yw + r0 * 32, 32, 32, c->ones, 0, r1 - r0, ns1, c->atb_partial,
+                                  nchunks > 0, last, c->Rvec, st, &c->launches))) return rc;
         ++nchunks;
         if (last) break;
     }
@@ -826,22 +837,36 @@ int forward_and_solve(gpz_ctx* c, const double* d_theta) {
         ++c->launches;
         if ((rc = spd_inverse(S, P.m, static_cast<int>(MP), Si, c->logdet + o, c->sws, st, &c->launches))) return rc;
         const unsigned gb = static_cast<unsigned>(ceil_div(MP, 8));
-        symv_kernel<<<gb, 256, 0, st>>>(Si, static_cast<int>(MP), P.m, c->Rvec + o, 32, nullptr, 1.0, c->w + o * MP);
+        if (c->aug)     // r = PHI'(omega beta y) is row m of the Gram (the spare column of PHI carries y)
+            symv_kernel<<<gb, 256, 0, st>>>(Si, static_cast<int>(MP), P.m, S + static_cast<int64_t>(P.m) * MP, 1, nullptr, 1.0, c->w + o * MP);
+        else
+            symv_kernel<<<gb, 256, 0, st>>>(Si, static_cast<int>(MP), P.m, c->Rvec + o, 32, nullptr, 1.0, c->w + o * MP);
         GPZ_KERNEL_CHECK();
         symv_kernel<<<gb, 256, 0, st>>>(Si, static_cast<int>(MP), P.m, c->w + o * MP, 1, P.alpha + o * MP, -1.0, c->dwda + o * MP);
         GPZ_KERNEL_CHECK();
         c->launches += 2;
+        if (c->aug) {
+            set_aug_col_kernel<<<static_cast<unsigned>(ceil_div(P.m, 256)), 256, 0, st>>>(Si, static_cast<int>(MP), P.m, c->w + o * MP);
+            GPZ_KERNEL_CHECK();
+            ++c->launches;
+        }
     }
     GPZ_CUDA(cudaEventRecord(c->ev[3], st));
     return GPZ_OK;
 }
 
 // pred = PHI w for the training rows of one chunk (PHI resident or rebuilt)
-int chunk_phi_and_pred(gpz_ctx* c, int64_t r0, int64_t r1, double** phi_out) {
+int chunk_phi_and_pred(gpz_ctx* c, int64_t r0, int64_t r1, double** phi_out, bool need_pred) {
     Params& P = c->P;
     const int64_t n = c->tr.n, MP = P.MP;
     int rc;
     double* phi = c->resident ? c->Phi + r0 * MP : c->Phi;
+    if (!need_pred) {
+        if (!c->resident)
+            if ((rc = phi_build(P, c->tr, r0, r1, phi, DotSpec{0, {nullptr, nullptr}, {nullptr, nullptr}}, c->dot_scratch, c->st, &c->launches))) return rc;
+        *phi_out = phi;
+        return GPZ_OK;
+    }
     if (!c->resident) {
         DotSpec ds{1, {c->w, nullptr}, {c->pred, nullptr}};
         if (P.k > 1) ds.n = 0;
@@ -880,12 +905,12 @@ int eval_device(gpz_ctx* c, const double* d_theta, double* d_out) {
         const bool last = r1 >= n;
         const int64_t rows = r1 - r0;
         double* phi = nullptr;
-        if ((rc = chunk_phi_and_pred(c, r0, r1, &phi))) return rc;
+        if ((rc = chunk_phi_and_pred(c, r0, r1, &phi, !c->aug))) return rc;
         for (int o = 0; o < k; ++o) {
             const bool timed = (nchunks == 0 && o == 0);
             if (timed) GPZ_CUDA(cudaEventRecord(c->kev[2], st));
             if ((rc = tgemm(phi, MP, c->Sinv + static_cast<int64_t>(o) * MP * MP, static_cast<int>(MP), P.m, rows, c->ob + o * n + r0,
-                            c->H, o > 0, c->nupart + r0, n, st, &c->launches))) return rc;
+                            c->H, o > 0, c->nupart + r0, n, c->aug ? c->pred + r0 : nullptr, st, &c->launches))) return rc;
             if (timed) GPZ_CUDA(cudaEventRecord(c->kev[3], st));
             rows2_kernel<<<static_cast<unsigned>(ceil_div(rows, RB)), RB, 0, st>>>(P, o, c->tr.Y, c->tr.omega, n, r0, r1, c->pred,
                                                                                  c->nupart, ntn, c->lnbi, c->beta, c->ob, c->nu,
@@ -1143,7 +1168,7 @@ int gpz_fit(gpz_ctx* c, const double* theta, double* nlogML_k, double* w, double
         for (int64_t r0 = 0; r0 < n; r0 += c->chunk_rows) {
             const int64_t r1 = (r0 + c->chunk_rows < n) ? r0 + c->chunk_rows : n;
             double* phi = nullptr;
-            if ((rc = chunk_phi_and_pred(c, r0, r1, &phi))) return rc;
+            if ((rc = chunk_phi_and_pred(c, r0, r1, &phi, true))) return rc;
             for (int o = 0; o < k; ++o) {
                 rows2_kernel<<<static_cast<unsigned>(ceil_div(r1 - r0, RB)), RB, 0, st>>>(P, o, c->tr.Y, c->tr.omega, n, r0, r1, c->pred, nullptr,
                                                                                         0, c->lnbi, c->beta, c->ob, c->nu, c->cw, c->dbeta,
@@ -1342,7 +1367,7 @@ int gpz_predict(const gpz_model* model, const double* theta, const double* w, co
         if (!Psi) {
             for (int o = 0; o < k; ++o) {
                 PR(tgemm(d_Phi, MP, d_Sinv + static_cast<int64_t>(o) * MP * MP, static_cast<int>(MP), P.m, r1 - r0, nullptr, nullptr, 0,
-                         d_nupart + r0, n, st, &launches));
+                         d_nupart + r0, n, nullptr, st, &launches));
                 sum_cols_kernel<<<static_cast<unsigned>(ceil_div(r1 - r0, 256)), 256, 0, st>>>(d_nupart + r0, static_cast<int>(MP / TILE), n, r1 - r0, d_nu + o * n + r0);
             }
         }
@@ -1489,6 +1514,14 @@ int gpz_set_option(gpz_ctx* c, const char* name, double value) {
             return GPZ_ERR_USAGE;
         }
         if (name[0] == 't') c->opt_tensor_phi = value != 0.0; else c->opt_fused_bp = value != 0.0;
+        return GPZ_OK;
+    }
+    if (strcmp(name, "spare_column") == 0) {
+        if (c->ws_ready) {
+            set_error("%s must be set before the first evaluation", name);
+            return GPZ_ERR_USAGE;
+        }
+        c->opt_aug = value != 0.0;
         return GPZ_OK;
     }
     set_error("unknown option '%s'", name);

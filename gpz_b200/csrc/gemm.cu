@@ -266,6 +266,8 @@ struct TEpi {
     int accumulate;
     double* nupart;         // [ntn][nu_ld]
     int64_t nu_ld;
+    int aug_col;            // >= 0: column that carries y in PHI and w in B; its T value is PHI_i.w (GPz.m:77)
+    double* pred;           // [rows] receives T[:, aug_col]
 };
 struct PEpi {
     int m;
@@ -274,6 +276,7 @@ struct PEpi {
     const double* vec[2];
     double* part[2];        // [ntn][part_ld]
     int64_t part_ld;
+    const double* ycol;     // non-null: PHI[:, m] := y (spare padded column), so the Gram also yields PHI'(w y) (GPz.m:70)
 };
 
 template <int EPI, int WARPS_M>
@@ -370,7 +373,11 @@ tgemm_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict
                 const int64_t gj = j0 + wn0 + j * 8 + 2 * t;
                 if (ok) {
                     const double2 ph = *reinterpret_cast<const double2*>(te.Phi + gi * lda + gj);
-                    const double h0 = ph.x * acc[i][j][0], h1 = ph.y * acc[i][j][1];
+                    double h0 = ph.x * acc[i][j][0], h1 = ph.y * acc[i][j][1];
+                    if (te.aug_col >= 0) {
+                        if (gj == te.aug_col) { te.pred[gi] = acc[i][j][0]; h0 = 0.0; }
+                        if (gj + 1 == te.aug_col) { te.pred[gi] = acc[i][j][1]; h1 = 0.0; }
+                    }
                     s += h0 + h1;
                     if (te.H != nullptr) {
                         double2* hp = reinterpret_cast<double2*>(te.H + gi * lda + gj);
@@ -405,8 +412,12 @@ tgemm_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
                 const int64_t gj = j0 + wn0 + j * 8 + 2 * t;
-                const double p0 = (gj < pe.m) ? exp(acc[i][j][0]) : 0.0;
-                const double p1 = (gj + 1 < pe.m) ? exp(acc[i][j][1]) : 0.0;
+                double p0 = (gj < pe.m) ? exp(acc[i][j][0]) : 0.0;
+                double p1 = (gj + 1 < pe.m) ? exp(acc[i][j][1]) : 0.0;
+                if (pe.ycol != nullptr && ok) {
+                    if (gj == pe.m) p0 = pe.ycol[gi];
+                    if (gj + 1 == pe.m) p1 = pe.ycol[gi];
+                }
                 if (ok && pe.Phi != nullptr) *reinterpret_cast<double2*>(pe.Phi + gi * MP + gj) = make_double2(p0, p1);
                 s0 = fma(p0, v0[j].x, fma(p1, v0[j].y, s0));
                 s1 = fma(p0, v1[j].x, fma(p1, v1[j].y, s1));
@@ -460,10 +471,10 @@ static int launch_tgemm(const double* A, int64_t lda, const double* B, int MP, i
 }
 
 int tgemm(const double* Phi, int64_t ld, const double* Sinv, int MP, int m, int64_t n, const double* rw, double* H,
-          int accumulate, double* nupart, int64_t nu_ld, cudaStream_t st, int64_t* launches) {
+          int accumulate, double* nupart, int64_t nu_ld, double* pred_aug, cudaStream_t st, int64_t* launches) {
     if (n <= 0) return GPZ_OK;
     const int nk = static_cast<int>(round_up(m, KSTEP) / KSTEP);
-    TEpi te{Phi, rw, H, accumulate, nupart, nu_ld};
+    TEpi te{Phi, rw, H, accumulate, nupart, nu_ld, pred_aug != nullptr ? m : -1, pred_aug};
     PEpi pe{};
     int rc = g_gemm_warps != 8 ? launch_tgemm<0, 4>(Phi, ld, Sinv, MP, nk, n, te, pe, st) : launch_tgemm<0, 2>(Phi, ld, Sinv, MP, nk, n, te, pe, st);
     if (!rc) ++*launches;
@@ -472,11 +483,11 @@ int tgemm(const double* Phi, int64_t ld, const double* Sinv, int MP, int m, int6
 
 // PHI = exp(F W): F [n][ldf] row features (K = kq columns used, kq % 16 == 0), W [kq][MP] coefficients
 int phi_gemm(const double* F, int64_t ldf, int kq, const double* W, int MP, int m, int64_t n, double* Phi, int ndot,
-             const double* vec0, const double* vec1, double* part0, double* part1, int64_t part_ld, cudaStream_t st,
-             int64_t* launches) {
+             const double* vec0, const double* vec1, double* part0, double* part1, int64_t part_ld, const double* ycol,
+             cudaStream_t st, int64_t* launches) {
     if (n <= 0) return GPZ_OK;
     TEpi te{};
-    PEpi pe{m, Phi, ndot, {vec0, vec1}, {part0, part1}, part_ld};
+    PEpi pe{m, Phi, ndot, {vec0, vec1}, {part0, part1}, part_ld, ycol};
     int rc = g_gemm_warps != 8 ? launch_tgemm<1, 4>(F, ldf, W, MP, kq / KSTEP, n, te, pe, st)
                                 : launch_tgemm<1, 2>(F, ldf, W, MP, kq / KSTEP, n, te, pe, st);
     if (!rc) ++*launches;

@@ -40,6 +40,7 @@ struct RowData {          // one resident row set (training or validation rows o
     double* Psi = nullptr;    // diag: [d][n]; cov: [n][d*d] (MATLAB d x d x n)
     int has_nan = 0;
     double* F = nullptr;      // [n][QP] monomial row features (fast path only)
+    const double* ycol = nullptr;   // set (to Y) when PHI's spare column m should carry y (see api.cu "aug")
 };
 
 struct DotSpec {          // up to 2 fused row-dots  out_q[i] = sum_j PHI_ij vec_q[j]
@@ -67,10 +68,10 @@ int atb_general(const double* A, int64_t lda, int MP, const double* B, int64_t l
                 int64_t row0, int64_t row1, int nsplit, double* partial, int accumulate, int reduce, double* R,
                 cudaStream_t st, int64_t* launches);
 int tgemm(const double* Phi, int64_t ld, const double* Sinv, int MP, int m, int64_t n, const double* rw, double* H,
-          int accumulate, double* nupart, int64_t nu_ld, cudaStream_t st, int64_t* launches);
+          int accumulate, double* nupart, int64_t nu_ld, double* pred_aug, cudaStream_t st, int64_t* launches);
 int phi_gemm(const double* F, int64_t ldf, int kq, const double* W, int MP, int m, int64_t n, double* Phi, int ndot,
-             const double* vec0, const double* vec1, double* part0, double* part1, int64_t part_ld, cudaStream_t st,
-             int64_t* launches);
+             const double* vec0, const double* vec1, double* part0, double* part1, int64_t part_ld, const double* ycol,
+             cudaStream_t st, int64_t* launches);
 int atb_dphi(const double* Phi, const double* H, int64_t ld, int MP, const double* F, int QP, const double* cw,
              const double* dbeta, const double* w, const double* v, int64_t row0, int64_t row1, int nsplit, double* partial,
              double* colp, int accumulate, int reduce, double* R, cudaStream_t st, int64_t* launches);

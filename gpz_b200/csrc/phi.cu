@@ -341,7 +341,8 @@ int phi_build(const Params& P, const RowData& R, int64_t r0, int64_t r1, double*
         const int ntn = P.MP / TILE;
         double* p0 = dot_scratch;
         double* p1 = dot_scratch + static_cast<int64_t>(ntn) * rows;
-        rc = phi_gemm(R.F + r0 * P.QP, P.QP, P.KQ, P.Wc, P.MP, P.m, rows, Phi, dots.n, dots.vec[0], dots.vec[1], p0, p1, rows, st, launches);
+        rc = phi_gemm(R.F + r0 * P.QP, P.QP, P.KQ, P.Wc, P.MP, P.m, rows, Phi, dots.n, dots.vec[0], dots.vec[1], p0, p1, rows,
+                      R.ycol != nullptr ? R.ycol + r0 : nullptr, st, launches);
         if (rc) return rc;
         for (int q = 0; q < dots.n; ++q) {
             sum_parts_kernel<<<static_cast<unsigned>(ceil_div(rows, 256)), 256, 0, st>>>(q == 0 ? p0 : p1, ntn, rows, rows, dots.out[q] + r0);

@@ -196,18 +196,22 @@ def test_tensor_core_phi_and_fused_backproj_agree_with_direct_kernels(method):
     direct-difference kernels + materialised dPHI, and both against the oracle."""
     model, theta, X, Y, Psi, omega, tr, va = problem(method, True, False, False, n=3000, d=5, m=140, seed=21)
     ref = O.GPz(theta, model, X, Y, None, omega, tr, va)
+    ref_fit = O.GPz(theta, model, X, Y, None, omega, tr, None, fit_only=True)
     gm = L.make_model(model.d, 1, model.m, method, True)
     out = {}
-    for tp, fb in ((1, 1), (0, 0), (1, 0), (0, 1)):
+    for tp, fb, sc in ((1, 1, 1), (0, 0, 1), (1, 0, 1), (0, 1, 1), (1, 1, 0)):
         ctx = L.Context(gm, X, Y, None, omega, tr, va)
         ctx.set_option("tensor_phi", tp)
         ctx.set_option("fused_backproj", fb)
-        out[(tp, fb)] = ctx.eval(theta)
+        ctx.set_option("spare_column", sc)
+        out[(tp, fb, sc)] = ctx.eval(theta)
         # m=140 bases on 2400 rows: SIGMA is ill-conditioned here, so the oracle's SVD pseudo-inverse and the
         # Cholesky inverse differ at the 1e-9 level in dlnAlpha; the stated tolerance is 1e-5
-        assert_eval_matches(model, ref, *out[(tp, fb)], tol=1e-7)
+        assert_eval_matches(model, ref, *out[(tp, fb, sc)], tol=1e-7)
+        nl, w, iS = ctx.fit(theta)
+        assert rel(w, ref_fit.w) <= 1e-6 and rel(nl, ref_fit.nlogML) <= 1e-9
         ctx.close()
-    f0, g0, _ = out[(1, 1)]
+    f0, g0, _ = out[(1, 1, 1)]
     for key, (f, g, _) in out.items():
         assert abs(f - f0) <= 1e-11 * abs(f0) and rel(g, g0) <= 1e-8, key
 
