@@ -15,7 +15,8 @@
 namespace gpz {
 
 constexpr int STAGES = 4;
-int g_gemm_warps = 0;       // 0 = measured defaults (T-GEMM 16 warps, Gram 8 warps); 8 / 16 force both (gpz_set_option)
+int g_gemm_warps = 0;       // 0 = defaults (Gram / T-GEMM 8 warps, PHI build 16 warps: its exp epilogue likes more warps);
+                            // 8 / 16 force all three (gpz_set_option "gemm_warps").  8 vs 16 differ by <4 % either way across boxes.
 
 // ------------------------------------------------------------------------------------------------
 // C = A' diag(w) B over a row range, 128 x TN output tile per CTA, split over rows
@@ -476,7 +477,7 @@ int tgemm(const double* Phi, int64_t ld, const double* Sinv, int MP, int m, int6
     const int nk = static_cast<int>(round_up(m, KSTEP) / KSTEP);
     TEpi te{Phi, rw, H, accumulate, nupart, nu_ld, pred_aug != nullptr ? m : -1, pred_aug};
     PEpi pe{};
-    int rc = g_gemm_warps != 8 ? launch_tgemm<0, 4>(Phi, ld, Sinv, MP, nk, n, te, pe, st) : launch_tgemm<0, 2>(Phi, ld, Sinv, MP, nk, n, te, pe, st);
+    int rc = g_gemm_warps == 16 ? launch_tgemm<0, 4>(Phi, ld, Sinv, MP, nk, n, te, pe, st) : launch_tgemm<0, 2>(Phi, ld, Sinv, MP, nk, n, te, pe, st);
     if (!rc) ++*launches;
     return rc;
 }

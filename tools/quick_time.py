@@ -22,9 +22,11 @@ for meth, n, d, m in cfgs:
     th = synth.make_theta0(X, Y, meth, m, het=True, seed=1)
     t0 = time.time(); ctx = L.Context(L.make_model(d, 1, m, meth, True), X, Y); t1 = time.time()
     if os.environ.get("GEMM_WARPS"): ctx.set_option("gemm_warps", float(os.environ["GEMM_WARPS"]))
+    for opt in ("spare_column", "tensor_phi", "fused_backproj"):
+        if os.environ.get(opt.upper()): ctx.set_option(opt, float(os.environ[opt.upper()]))
     f, g, st = ctx.eval(th)
     ts = []
-    for _ in range(3):
+    for _ in range(6):
         t = time.time(); f, g, st = ctx.eval(th); ts.append(time.time() - t)
     print(meth, n, d, m, "create %.2fs" % (t1 - t0), "eval %.1f ms" % (1e3 * min(ts)), "f=%.6f" % f, {k: round(v, 3) for k, v in ctx.last_timing().items()},
           "GEMM TF/s (4nm^2): %.1f" % (4 * n * m * m / min(ts) / 1e12), flush=True)
