@@ -14,6 +14,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <algorithm>
+#include <map>
+#include <numeric>
 #include <string>
 #include <vector>
 
@@ -531,6 +534,9 @@ int fill_params(Params& P, const gpz_model* model) {
     P.QP = static_cast<int>(round_up(P.q, 32));
     P.Wc = nullptr;
     P.xshift = nullptr;
+    P.npat = 1;
+    P.obs = nullptr;
+    P.Mg = P.Gg = nullptr;
     return GPZ_OK;
 }
 
@@ -566,7 +572,13 @@ int alloc_params(Params& P, std::vector<void*>& list, int need_sigma) {
     if ((rc = dev_alloc(list, &P.v, P.k * MP))) return rc;
     if ((rc = dev_alloc(list, &P.tau, P.k * MP))) return rc;
     if ((rc = dev_alloc(list, &P.bk, 32))) return rc;
-    if ((rc = dev_alloc(list, &P.Wc, static_cast<int64_t>(P.KQ) * MP))) return rc;
+    if ((rc = dev_alloc(list, &P.Wc, static_cast<int64_t>(P.npat) * P.KQ * MP))) return rc;
+    if (mode_is_cov(P.mode)) {
+        if ((rc = dev_alloc(list, &P.Mg, static_cast<int64_t>(P.npat) * d * d * MP))) return rc;
+        if ((rc = dev_alloc(list, &P.Gg, static_cast<int64_t>(P.npat) * d * d * MP))) return rc;
+        if ((rc = dev_alloc(list, &P.obs, static_cast<int64_t>(P.npat) * d))) return rc;
+        GPZ_CUDA(cudaMemset(P.obs, 1, static_cast<size_t>(P.npat) * d));
+    }
     if ((rc = dev_alloc(list, &P.xshift, d))) return rc;
     GPZ_CUDA(cudaMemset(P.xshift, 0, sizeof(double) * d));
     return GPZ_OK;
@@ -605,7 +617,7 @@ void gather_cols(const double* src, int64_t n_all, int cols, const std::vector<i
 }
 
 int upload_rows(gpz_ctx* c, RowData& R, const std::vector<int64_t>& idx, int64_t n_all, const double* X, const double* Y,
-                const double* Psi, const double* omega) {
+                const double* Psi, const double* omega, bool zero_fill_nan) {
     const Params& P = c->P;
     const int64_t n = static_cast<int64_t>(idx.size());
     R.n = n;
@@ -620,6 +632,11 @@ int upload_rows(gpz_ctx* c, RowData& R, const std::vector<int64_t>& idx, int64_t
         const double sh = c->h_shift[a];
         double* col = buf.data() + static_cast<int64_t>(a) * n;
         for (int64_t i = 0; i < n; ++i) col[i] -= sh;
+    }
+    if (zero_fill_nan) {                     // pattern-grouped covariance modes: missing dims drop out of the monomials
+        for (double& v : buf)
+            if (v != v) v = 0.0;
+        R.has_nan = 0;
     }
     GPZ_CUDA(cudaMemcpy(R.X, buf.data(), sizeof(double) * buf.size(), cudaMemcpyHostToDevice));
     if ((rc = dev_alloc(c->allocs, &R.Y, n * P.k))) return rc;
@@ -923,25 +940,46 @@ int eval_device(gpz_ctx* c, const double* d_theta, double* d_out) {
             ev4 = true;
         }
         const bool fused = fast_bp && c->opt_fused_bp && k == 1 && c->QP <= 128;
-        if (fused) {
-            if ((rc = atb_dphi(phi, c->H, MP, static_cast<int>(MP), c->tr.F + r0 * c->QP, c->QP, c->cw + r0, c->dbeta + r0, c->w, P.v,
-                               0, rows, c->fused_ns, c->atb_partial, c->colp, nchunks > 0, last, c->Rm, st, &c->launches))) return rc;
-            colp_slabs = c->fused_ns;
-        } else {
+        const size_t ng = c->tr.g_pat.empty() ? 1 : c->tr.g_pat.size();
+        if (ng > 1 && !c->resident) {
+            set_error("missing-input pattern groups need PHI resident in HBM (raise the memory budget / lower n per GPU)");
+            return GPZ_ERR_USAGE;
+        }
+        if (!fused) {
             const int64_t rps = ceil_div(rows, c->dphi_slabs);
             dim3 grid(static_cast<unsigned>(T), static_cast<unsigned>(c->dphi_slabs));
             dphi_kernel<<<grid, 128, 0, st>>>(P, phi, c->H, MP, n, r0, r1, rps, c->cw, c->dbeta, c->w, c->colp, nchunks > 0);
             GPZ_KERNEL_CHECK();
             ++c->launches;
             colp_slabs = c->dphi_slabs;
-            if (fast_bp) {
-                if ((rc = atb_general(c->H, MP, static_cast<int>(MP), c->tr.F + r0 * c->QP, c->QP, c->QP, c->ones, 0, rows, c->atb_ns,
-                                      c->atb_partial, nchunks > 0, last, c->Rm, st, &c->launches))) return rc;
-            } else if (!mode_is_cov(P.mode)) {
-                if ((rc = backproj_diag_generic(P, c->tr, r0, r1, c->H, MP, c->bp_partial, c->nslab, nchunks > 0, st, &c->launches))) return rc;
-            } else {
-                if ((rc = backproj_cov_psi(P, c->tr, r0, r1, c->H, MP, c->bp_partial, c->nslab, nchunks > 0, st, &c->launches))) return rc;
+        } else {
+            colp_slabs = c->fused_ns;
+        }
+        if (fast_bp) {
+            // one moment GEMM per missing-input pattern group (a single group when the data have no NaN)
+            for (size_t g = 0; g < ng; ++g) {
+                int64_t s0 = r0, s1 = r1;
+                if (ng > 1) {
+                    s0 = c->tr.g_r0[g];
+                    s1 = c->tr.g_r1[g];
+                }
+                const int acc = ng > 1 ? 0 : (nchunks > 0);
+                const int red = ng > 1 ? 1 : (last ? 1 : 0);
+                if (fused) {
+                    if ((rc = atb_dphi(phi + (s0 - r0) * MP, c->H + (s0 - r0) * MP, MP, static_cast<int>(MP), c->tr.F + s0 * c->QP, c->QP,
+                                       c->cw + s0, c->dbeta + s0, c->w, P.v, 0, s1 - s0, c->fused_ns, c->atb_partial, c->colp, acc,
+                                       ng > 1 ? (g > 0) : (nchunks > 0), red, c->Rm, st, &c->launches))) return rc;
+                } else {
+                    if ((rc = atb_general(c->H + (s0 - r0) * MP, MP, static_cast<int>(MP), c->tr.F + s0 * c->QP, c->QP, c->QP, c->ones, 0,
+                                          s1 - s0, c->atb_ns, c->atb_partial, acc, red, c->Rm, st, &c->launches))) return rc;
+                }
+                if (ng > 1)
+                    if ((rc = moments_to_grad(P, c->tr.g_pat[g], c->Rm, c->QP, dP, c->scratch, g > 0, st, &c->launches))) return rc;
             }
+        } else if (!mode_is_cov(P.mode)) {
+            if ((rc = backproj_diag_generic(P, c->tr, r0, r1, c->H, MP, c->bp_partial, c->nslab, nchunks > 0, st, &c->launches))) return rc;
+        } else {
+            if ((rc = backproj_cov_psi(P, c->tr, r0, r1, c->H, MP, c->bp_partial, c->nslab, nchunks > 0, st, &c->launches))) return rc;
         }
         ++nchunks;
     }
@@ -950,7 +988,11 @@ int eval_device(gpz_ctx* c, const double* d_theta, double* d_out) {
         return GPZ_ERR_USAGE;
     }
     if (!ev4) GPZ_CUDA(cudaEventRecord(c->ev[4], st));
-    if (fast_bp) rc = finalize_moments(P, c->Rm, c->QP, dP, dG, c->scratch, st, &c->launches);
+    if (fast_bp) {
+        if (c->tr.g_pat.size() <= 1)
+            rc = moments_to_grad(P, c->tr.g_pat.empty() ? 0 : c->tr.g_pat[0], c->Rm, c->QP, dP, c->scratch, 0, st, &c->launches);
+        if (!rc) rc = mode_reduce(P, c->scratch, dG, st, &c->launches);
+    }
     else if (!mode_is_cov(P.mode)) rc = backproj_diag_generic_finish(P, c->bp_partial, c->nslab, dP, dG, c->scratch, st, &c->launches);
     else rc = backproj_cov_psi_finish(P, c->bp_partial, c->nslab, dP, dG, c->scratch, st, &c->launches);
     if (rc) return rc;
@@ -1040,7 +1082,6 @@ int gpz_create(gpz_ctx** out, const gpz_model* model, int64_t n_all, const doubl
         set_error("cudaStreamCreate failed");
         return fail(GPZ_ERR_CUDA);
     }
-    if ((rc = alloc_params(c->P, c->allocs, c->has_psi))) return fail(rc);
     std::vector<int64_t> itr, iva;
     for (int64_t i = 0; i < n_all; ++i) {
         if (!training || training[i]) itr.push_back(i);
@@ -1057,16 +1098,82 @@ int gpz_create(gpz_ctx** out, const gpz_model* model, int64_t n_all, const doubl
         }
         c->h_shift[a] = cnt > 0 ? s / static_cast<double>(cnt) : 0.0;
     }
+    // covariance modes with missing inputs: group rows by NaN pattern (getPHI.m:43-54), patterns numbered in order
+    // of first appearance over training then validation rows
+    bool grouped = false;
+    std::vector<std::vector<unsigned char>> pats;
+    std::vector<int> pat_tr, pat_va;
+    if (mode_is_cov(P.mode)) {
+        std::map<std::string, int> seen;
+        auto scan = [&](const std::vector<int64_t>& idx, std::vector<int>& out_pat) {
+            out_pat.resize(idx.size());
+            std::string key(static_cast<size_t>(P.d), '1');
+            for (size_t r = 0; r < idx.size(); ++r) {
+                bool any = false;
+                for (int a = 0; a < P.d; ++a) {
+                    const double v = X[static_cast<int64_t>(a) * n_all + idx[r]];
+                    key[a] = (v == v) ? '1' : '0';
+                    any = any || (v != v);
+                }
+                grouped = grouped || any;
+                auto it = seen.find(key);
+                if (it == seen.end()) {
+                    it = seen.emplace(key, static_cast<int>(pats.size())).first;
+                    std::vector<unsigned char> ob(static_cast<size_t>(P.d));
+                    for (int a = 0; a < P.d; ++a) ob[a] = key[a] == '1';
+                    pats.push_back(ob);
+                }
+                out_pat[r] = it->second;
+            }
+        };
+        scan(itr, pat_tr);
+        scan(iva, pat_va);
+        if (grouped && Psi) {
+            set_error("covariance modes with missing inputs AND input noise Psi are not supported yet");
+            return fail(GPZ_ERR_USAGE);
+        }
+        if (grouped && pats.size() > 4096) {
+            set_error("too many distinct missing-input patterns (%zu)", pats.size());
+            return fail(GPZ_ERR_USAGE);
+        }
+    }
+    if (grouped) c->P.npat = static_cast<int>(pats.size());
+    if ((rc = alloc_params(c->P, c->allocs, c->has_psi))) return fail(rc);
     if (cudaMemcpy(c->P.xshift, c->h_shift.data(), sizeof(double) * P.d, cudaMemcpyHostToDevice) != cudaSuccess) {
         set_error("gpz_create: upload of the shift failed");
         return fail(GPZ_ERR_CUDA);
     }
-    if ((rc = upload_rows(c, c->tr, itr, n_all, X, Y, Psi, omega))) return fail(rc);
-    if ((rc = upload_rows(c, c->va, iva, n_all, X, Y, Psi, omega))) return fail(rc);
-    if (mode_is_cov(c->P.mode) && (c->tr.has_nan || c->va.has_nan)) {
-        set_error("covariance modes (GC/VC) with missing inputs (NaN) are not supported yet");
-        return fail(GPZ_ERR_USAGE);
+    auto sort_groups = [&](std::vector<int64_t>& idx, const std::vector<int>& pat, RowData& R) {
+        if (!grouped) return;
+        std::vector<int64_t> order(idx.size());
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return pat[a] < pat[b]; });
+        std::vector<int64_t> sorted(idx.size());
+        for (size_t r = 0; r < order.size(); ++r) sorted[r] = idx[order[r]];
+        R.perm = order;
+        size_t r = 0;
+        while (r < order.size()) {
+            size_t e = r;
+            while (e < order.size() && pat[order[e]] == pat[order[r]]) ++e;
+            R.g_r0.push_back(static_cast<int64_t>(r));
+            R.g_r1.push_back(static_cast<int64_t>(e));
+            R.g_pat.push_back(pat[order[r]]);
+            r = e;
+        }
+        idx.swap(sorted);
+    };
+    sort_groups(itr, pat_tr, c->tr);
+    sort_groups(iva, pat_va, c->va);
+    if (grouped) {
+        std::vector<unsigned char> flat;
+        for (auto& ob : pats) flat.insert(flat.end(), ob.begin(), ob.end());
+        if (cudaMemcpy(c->P.obs, flat.data(), flat.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("gpz_create: upload of the patterns failed");
+            return fail(GPZ_ERR_CUDA);
+        }
     }
+    if ((rc = upload_rows(c, c->tr, itr, n_all, X, Y, Psi, omega, grouped))) return fail(rc);
+    if ((rc = upload_rows(c, c->va, iva, n_all, X, Y, Psi, omega, grouped))) return fail(rc);
     *out = c;
     return GPZ_OK;
 }
@@ -1231,6 +1338,14 @@ int gpz_phi(gpz_ctx* c, const double* theta, int which, double* PHI, double* lnB
             GPZ_CUDA(cudaStreamSynchronize(st));
         }
     }
+    if (PHI && !R.perm.empty()) {            // rows are stored sorted by missing-input pattern: restore selection order
+        std::vector<double> tmp(static_cast<size_t>(n));
+        for (int j = 0; j < P.m; ++j) {
+            double* col = PHI + static_cast<int64_t>(j) * n;
+            for (int64_t i = 0; i < n; ++i) tmp[static_cast<size_t>(R.perm[i])] = col[i];
+            memcpy(col, tmp.data(), sizeof(double) * n);
+        }
+    }
     if (lnBeta_i) {
         hbuf.resize(static_cast<size_t>(n * P.k));
         std::vector<double> hb(32);
@@ -1238,7 +1353,10 @@ int gpz_phi(gpz_ctx* c, const double* theta, int which, double* PHI, double* lnB
         GPZ_CUDA(cudaStreamSynchronize(st));
         for (int o = 0; o < P.k; ++o) {
             const double b = theta[P.oB + o];
-            for (int64_t i = 0; i < n; ++i) lnBeta_i[o * n + i] = b + (P.het ? hbuf[o * n + i] : 0.0);
+            for (int64_t i = 0; i < n; ++i) {
+                const int64_t dst = R.perm.empty() ? i : R.perm[i];
+                lnBeta_i[o * n + dst] = b + (P.het ? hbuf[o * n + i] : 0.0);
+            }
         }
     }
     GPZ_CUDA(cudaStreamSynchronize(st));

@@ -92,7 +92,7 @@ __global__ void copy_kernel(const double* __restrict__ src, double* __restrict__
     if (i < n) dst[i] = src[i];
 }
 
-static int mode_reduce(const Params& P, const double* full, double* dG, cudaStream_t st, int64_t* launches) {
+int mode_reduce(const Params& P, const double* full, double* dG, cudaStream_t st, int64_t* launches) {
     if (P.mode == VD || P.mode == VC) {
         copy_kernel<<<static_cast<unsigned>(ceil_div(P.g_dim, 256)), 256, 0, st>>>(full, dG, P.g_dim);
     } else {
@@ -107,54 +107,93 @@ static int mode_reduce(const Params& P, const double* full, double* dG, cudaStre
 // moments R = dPHI' F  ->  dP, per-basis dGamma
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-moments_kernel(Params P, const double* __restrict__ Rm, int QP, double* __restrict__ dP, double* __restrict__ full) {
+moments_diag_kernel(Params P, const double* __restrict__ Rm, int QP, double* __restrict__ dP, double* __restrict__ full) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int d = P.d, m = P.m, MP = P.MP, dp = P.dp;
+    const int d = P.d, m = P.m, MP = P.MP;
     if (j >= m) return;
     const double* R = Rm + static_cast<int64_t>(j) * QP;
     const double M0 = R[0];
-    if (!mode_is_cov(P.mode)) {
-        for (int a = 0; a < d; ++a) {
-            const double p = P.Pt[a * MP + j], gv = P.Gt[a * MP + j];
-            const double S1 = R[1 + a], S2 = R[1 + d + a];
-            const double sP = S1 - p * M0;                       // sum dPHI * Delta
-            const double sG = S2 - 2.0 * p * S1 + p * p * M0;    // sum dPHI * Delta^2
-            dP[a * m + j] = gv * gv * sP;                        // GPz.m:192
-            full[a * m + j] = -gv * sG;                          // GPz.m:194
-        }
-        return;
+    for (int a = 0; a < d; ++a) {
+        const double p = P.Pt[a * MP + j], gv = P.Gt[a * MP + j];
+        const double S1 = R[1 + a], S2 = R[1 + d + a];
+        const double sP = S1 - p * M0;                       // sum dPHI * Delta
+        const double sG = S2 - 2.0 * p * S1 + p * p * M0;    // sum dPHI * Delta^2
+        dP[a * m + j] = gv * gv * sP;                        // GPz.m:192
+        full[a * m + j] = -gv * sG;                          // GPz.m:194
     }
-    // cov modes: dP_j = M1d * A_j ; dGamma_j = -Gamma_j * M2d        (GPz.m:152-158 with no missing dims)
+}
+
+// cov modes, one missing-input pattern (observed set o, missing set u):                       GPz.m:146-159
+//   iSoo = (Sigma_j(o,o))^-1 = Mg;  dP_j(o) += M1d(o) iSoo;  diSoo = -1/2 M2d(o,o);
+//   GuuGuo = Gg;  dGo = 2 (Gamma(:,o) - Gamma(:,u) GuuGuo) diSoo;  dGamma(:,o) += dGo;  dGamma(:,u) -= dGo GuuGuo'
+template <int DMAX>
+__global__ void __launch_bounds__(128)
+moments_cov_kernel(Params P, int pat, const double* __restrict__ Rm, int QP, double* __restrict__ dP,
+                   double* __restrict__ full, int accumulate) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int d = P.d, m = P.m, MP = P.MP, dp = P.dp;
+    if (j >= m) return;
+    const unsigned char* ob = P.obs + pat * d;
+    const double* Mg = P.Mg + static_cast<int64_t>(pat) * d * d * MP;
+    const double* Gg = P.Gg + static_cast<int64_t>(pat) * d * d * MP;
+    const double* R = Rm + static_cast<int64_t>(j) * QP;
+    const double M0 = R[0];
+    double m1[DMAX], pj[DMAX];
+    for (int a = 0; a < d; ++a) {
+        pj[a] = P.Pt[a * MP + j];
+        m1[a] = ob[a] ? R[1 + a] - pj[a] * M0 : 0.0;
+    }
     for (int a = 0; a < d; ++a) {
         double s = 0.0;
-        for (int b = 0; b < d; ++b) {
-            const double m1 = R[1 + b] - P.Pt[b * MP + j] * M0;
-            s += m1 * P.Aj[(static_cast<int64_t>(b) * d + a) * MP + j];
-        }
-        dP[a * m + j] = s;
+        if (ob[a])
+            for (int b = 0; b < d; ++b)
+                if (ob[b]) s += m1[b] * Mg[(static_cast<int64_t>(b) * d + a) * MP + j];
+        const int64_t o = a * m + j;
+        dP[o] = (accumulate ? dP[o] : 0.0) + s;
     }
-    for (int a = 0; a < d; ++a) {            // column a of M2d, then dGamma(:,a)
-        const double pa = P.Pt[a * MP + j];
-        for (int c = 0; c < d; ++c) {
-            double s = 0.0;
-            for (int b = 0; b < d; ++b) {
+    // Gproj(c,b) = Gamma(c,b) - sum_{e in u} Gamma(c,e) G(e,b)   (b in o)
+    double dGo[DMAX];      // one row c of dGo at a time
+    for (int c = 0; c < d; ++c) {
+        for (int a = 0; a < d; ++a) dGo[a] = 0.0;
+        for (int b = 0; b < d; ++b) {
+            if (!ob[b]) continue;
+            double gp = P.Gam[(static_cast<int64_t>(c) * dp + b) * MP + j];
+            for (int e = 0; e < d; ++e)
+                if (!ob[e]) gp -= P.Gam[(static_cast<int64_t>(c) * dp + e) * MP + j] * Gg[(static_cast<int64_t>(e) * d + b) * MP + j];
+            const double pb = pj[b];
+            for (int a = 0; a < d; ++a) {
+                if (!ob[a]) continue;
                 const int lo = b < a ? b : a, hi = b < a ? a : b;
                 const int idx = 1 + d + lo * d - lo * (lo - 1) / 2 + (hi - lo);
-                const double pb = P.Pt[b * MP + j];
-                const double m2 = R[idx] - pb * R[1 + a] - R[1 + b] * pa + pa * pb * M0;
-                s += P.Gam[(static_cast<int64_t>(c) * dp + b) * MP + j] * m2;
+                const double m2 = R[idx] - pb * R[1 + a] - R[1 + b] * pj[a] + pj[a] * pb * M0;
+                dGo[a] -= gp * m2;                      // 2 * Gproj * (-1/2 M2d)
             }
-            full[c + a * d + static_cast<int64_t>(d) * d * j] = -s;
+        }
+        for (int a = 0; a < d; ++a) {
+            double val;
+            if (ob[a]) {
+                val = dGo[a];
+            } else {                                    // dGamma(c, e in u) -= sum_{a in o} dGo(c,a) G(e,a)
+                val = 0.0;
+                for (int b = 0; b < d; ++b)
+                    if (ob[b]) val -= dGo[b] * Gg[(static_cast<int64_t>(a) * d + b) * MP + j];
+            }
+            const int64_t o = c + a * d + static_cast<int64_t>(d) * d * j;
+            full[o] = (accumulate ? full[o] : 0.0) + val;
         }
     }
 }
 
-int finalize_moments(const Params& P, const double* Rm, int QP, double* dP, double* dG, double* scratch,
-                     cudaStream_t st, int64_t* launches) {
-    moments_kernel<<<static_cast<unsigned>(ceil_div(P.m, 128)), 128, 0, st>>>(P, Rm, QP, dP, scratch);
+int moments_to_grad(const Params& P, int pat, const double* Rm, int QP, double* dP, double* full, int accumulate,
+                    cudaStream_t st, int64_t* launches) {
+    const unsigned nb = static_cast<unsigned>(ceil_div(P.m, 128));
+    if (!mode_is_cov(P.mode)) moments_diag_kernel<<<nb, 128, 0, st>>>(P, Rm, QP, dP, full);
+    else if (P.d <= 8) moments_cov_kernel<8><<<nb, 128, 0, st>>>(P, pat, Rm, QP, dP, full, accumulate);
+    else if (P.d <= 16) moments_cov_kernel<16><<<nb, 128, 0, st>>>(P, pat, Rm, QP, dP, full, accumulate);
+    else moments_cov_kernel<32><<<nb, 128, 0, st>>>(P, pat, Rm, QP, dP, full, accumulate);
     GPZ_KERNEL_CHECK();
     ++*launches;
-    return mode_reduce(P, scratch, dG, st, launches);
+    return GPZ_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

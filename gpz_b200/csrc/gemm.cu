@@ -509,7 +509,8 @@ __global__ void __launch_bounds__(256, 1)
 atb_dphi_kernel(const double* __restrict__ Phi, const double* __restrict__ H, int64_t ld, const double* __restrict__ F,
                 int64_t ldf, const double* __restrict__ cw, const double* __restrict__ dbeta,
                 const double* __restrict__ w, const double* __restrict__ v, int64_t row0, int64_t row1,
-                int64_t rows_per_split, double* __restrict__ partial, double* __restrict__ colp, int MP, int accumulate) {
+                int64_t rows_per_split, double* __restrict__ partial, double* __restrict__ colp, int MP, int accumulate,
+                int col_accumulate) {
     constexpr int TN = 8 * NT;
     constexpr int LDB = TN + 4;
     constexpr int MT = 2;                    // 8 warps x 16 bases
@@ -656,15 +657,15 @@ atb_dphi_kernel(const double* __restrict__ Phi, const double* __restrict__ H, in
         const double q = csum[0][e][c2] + csum[1][e][c2] + csum[2][e][c2] + csum[3][e][c2];
         const double dv = csum[0][2 + e][c2] + csum[1][2 + e][c2] + csum[2][2 + e][c2] + csum[3][2 + e][c2];
         double* cp = colp + static_cast<int64_t>(blockIdx.y) * 2 * MP + a_col0 + tid;
-        cp[0] = (accumulate ? cp[0] : 0.0) + q;
-        cp[MP] = (accumulate ? cp[MP] : 0.0) + dv;
+        cp[0] = (col_accumulate ? cp[0] : 0.0) + q;
+        cp[MP] = (col_accumulate ? cp[MP] : 0.0) + dv;
     }
 }
 
 template <int NT>
 static int launch_atb_dphi(const double* Phi, const double* H, int64_t ld, const double* F, int64_t ldf, const double* cw,
                            const double* dbeta, const double* w, const double* v, int64_t row0, int64_t row1, int nsplit,
-                           double* partial, double* colp, int MP, int accumulate, cudaStream_t st) {
+                           double* partial, double* colp, int MP, int accumulate, int col_accumulate, cudaStream_t st) {
     constexpr int TN = 8 * NT;
     const size_t smem = sizeof(double) * (DSTAGES * KSTEP * LDT + DSTAGES * KSTEP * (TN + 4));
     static bool configured = false;
@@ -675,7 +676,8 @@ static int launch_atb_dphi(const double* Phi, const double* H, int64_t ld, const
     int64_t rps = ceil_div(row1 - row0, nsplit);
     rps = round_up(rps > 0 ? rps : 1, KSTEP);
     dim3 grid(MP / TILE, nsplit);
-    atb_dphi_kernel<NT><<<grid, 256, smem, st>>>(Phi, H, ld, F, ldf, cw, dbeta, w, v, row0, row1, rps, partial, colp, MP, accumulate);
+    atb_dphi_kernel<NT><<<grid, 256, smem, st>>>(Phi, H, ld, F, ldf, cw, dbeta, w, v, row0, row1, rps, partial, colp, MP, accumulate,
+                                                 col_accumulate);
     GPZ_KERNEL_CHECK();
     return GPZ_OK;
 }
@@ -683,13 +685,13 @@ static int launch_atb_dphi(const double* Phi, const double* H, int64_t ld, const
 // QP in {32, 64, 96, 128}.  partial: nsplit * (MP/128) * 128 * QP doubles; colp: nsplit * 2 * MP doubles.
 int atb_dphi(const double* Phi, const double* H, int64_t ld, int MP, const double* F, int QP, const double* cw,
              const double* dbeta, const double* w, const double* v, int64_t row0, int64_t row1, int nsplit, double* partial,
-             double* colp, int accumulate, int reduce, double* R, cudaStream_t st, int64_t* launches) {
+             double* colp, int accumulate, int col_accumulate, int reduce, double* R, cudaStream_t st, int64_t* launches) {
     int rc;
     switch (QP) {
-        case 32: rc = launch_atb_dphi<4>(Phi, H, ld, F, QP, cw, dbeta, w, v, row0, row1, nsplit, partial, colp, MP, accumulate, st); break;
-        case 64: rc = launch_atb_dphi<8>(Phi, H, ld, F, QP, cw, dbeta, w, v, row0, row1, nsplit, partial, colp, MP, accumulate, st); break;
-        case 96: rc = launch_atb_dphi<12>(Phi, H, ld, F, QP, cw, dbeta, w, v, row0, row1, nsplit, partial, colp, MP, accumulate, st); break;
-        case 128: rc = launch_atb_dphi<16>(Phi, H, ld, F, QP, cw, dbeta, w, v, row0, row1, nsplit, partial, colp, MP, accumulate, st); break;
+        case 32: rc = launch_atb_dphi<4>(Phi, H, ld, F, QP, cw, dbeta, w, v, row0, row1, nsplit, partial, colp, MP, accumulate, col_accumulate, st); break;
+        case 64: rc = launch_atb_dphi<8>(Phi, H, ld, F, QP, cw, dbeta, w, v, row0, row1, nsplit, partial, colp, MP, accumulate, col_accumulate, st); break;
+        case 96: rc = launch_atb_dphi<12>(Phi, H, ld, F, QP, cw, dbeta, w, v, row0, row1, nsplit, partial, colp, MP, accumulate, col_accumulate, st); break;
+        case 128: rc = launch_atb_dphi<16>(Phi, H, ld, F, QP, cw, dbeta, w, v, row0, row1, nsplit, partial, colp, MP, accumulate, col_accumulate, st); break;
         default:
             set_error("atb_dphi: unsupported feature width %d", QP);
             return GPZ_ERR_USAGE;

@@ -1,5 +1,7 @@
 // Internal declarations shared by the translation units of libgpz_b200.
 #pragma once
+#include <vector>
+
 #include "../../include/gpz_b200.h"
 #include "common.cuh"
 
@@ -28,8 +30,14 @@ struct Params {
     double* bk;     // [k]
     // fast path (no Psi, no NaN): PHI = exp(F W) on the fp64 tensor pipe
     int q, KQ, QP;  // feature count, K extent (multiple of 16), row stride of F (multiple of 32)
-    double* Wc;     // [KQ][MP]     coefficients of the monomial features (zero rows/columns in the padding)
+    double* Wc;     // [npat][KQ][MP]  coefficients of the monomial features (zero rows/columns in the padding)
     double* xshift; // [d]          constant subtracted from X at upload (and from P here): only x - p matters
+    // missing-input patterns of the covariance modes (getPHI.m:43-54,76; GPz.m:151-159); npat = 1 and all
+    // dims observed when the data have no NaN
+    int npat;
+    unsigned char* obs;   // [npat][d]          1 = dim observed in this pattern
+    double* Mg;     // [npat][d*d][MP]  (Sigma_j(o,o))^-1 embedded in d x d (zero on missing rows/cols)
+    double* Gg;     // [npat][d*d][MP]  iSigma(u,u)^-1 iSigma(u,o) embedded (row e in u, col b in o)
 };
 
 struct RowData {          // one resident row set (training or validation rows of this rank)
@@ -41,6 +49,10 @@ struct RowData {          // one resident row set (training or validation rows o
     int has_nan = 0;
     double* F = nullptr;      // [n][QP] monomial row features (fast path only)
     const double* ycol = nullptr;   // set (to Y) when PHI's spare column m should carry y (see api.cu "aug")
+    // covariance modes with missing inputs: rows are stored sorted by NaN pattern (NaN entries zero-filled),
+    // group g = rows [g_r0[g], g_r1[g]) with pattern g_pat[g]; perm[sorted position] = position in selection order
+    std::vector<int64_t> g_r0, g_r1, perm;
+    std::vector<int> g_pat;
 };
 
 struct DotSpec {          // up to 2 fused row-dots  out_q[i] = sum_j PHI_ij vec_q[j]
@@ -74,7 +86,7 @@ int phi_gemm(const double* F, int64_t ldf, int kq, const double* W, int MP, int 
              cudaStream_t st, int64_t* launches);
 int atb_dphi(const double* Phi, const double* H, int64_t ld, int MP, const double* F, int QP, const double* cw,
              const double* dbeta, const double* w, const double* v, int64_t row0, int64_t row1, int nsplit, double* partial,
-             double* colp, int accumulate, int reduce, double* R, cudaStream_t st, int64_t* launches);
+             double* colp, int accumulate, int col_accumulate, int reduce, double* R, cudaStream_t st, int64_t* launches);
 int sgemm(int M, int N, int K, double alpha, const double* A, int64_t sAi, int64_t sAk, const double* B, int64_t sBk,
           int64_t sBj, double beta, double* C, int64_t ldc, int lower_only, cudaStream_t st, int64_t* launches);
 
@@ -95,8 +107,10 @@ int spd_inverse(double* S, int m, int MP, double* Sinv, double* d_logdet, SolveW
 int build_features(const Params& P, const double* X, int64_t n, int64_t r0, int64_t r1, double* F, cudaStream_t st,
                    int64_t* launches);
 int feature_count(const Params& P);
-int finalize_moments(const Params& P, const double* Rm /*[MP][QP]*/, int QP, double* dP /*m*d*/, double* dG /*g_dim*/,
-                     double* scratch, cudaStream_t st, int64_t* launches);
+// moments of one pattern group -> dP / per-basis dGamma (in `full`), accumulated when accumulate != 0
+int moments_to_grad(const Params& P, int pat, const double* Rm /*[MP][QP]*/, int QP, double* dP /*m*d*/, double* full,
+                    int accumulate, cudaStream_t st, int64_t* launches);
+int mode_reduce(const Params& P, const double* full, double* dG, cudaStream_t st, int64_t* launches);
 int backproj_diag_generic(const Params& P, const RowData& R, int64_t r0, int64_t r1, const double* dPhi, int64_t ld,
                           double* partial, int nslab, int accumulate, cudaStream_t st, int64_t* launches);
 int backproj_diag_generic_finish(const Params& P, const double* partial, int nslab, double* dP, double* dG,

@@ -70,22 +70,6 @@ __global__ void prep_kernel(const double* __restrict__ th, Params P, int need_si
                     for (int c = 0; c < d; ++c) s += G[c + a * d] * G[c + b * d];
                 P.Aj[(static_cast<int64_t>(a) * d + b) * MP + j] = live ? s : (a == b ? 1.0 : 0.0);
             }
-        if (P.Wc != nullptr) {              // lnPHI = -1/2 x'Ax + (Ap)'x - 1/2 p'Ap over the upper-triangular monomials
-            double c0 = 0.0;
-            int idx = 1 + d;
-            for (int a = 0; a < d; ++a) {
-                double bv = 0.0;
-                for (int b = 0; b < d; ++b) bv += P.Aj[(static_cast<int64_t>(a) * d + b) * MP + j] * P.Pt[b * MP + j];
-                c0 += bv * P.Pt[a * MP + j];
-                P.Wc[static_cast<int64_t>(1 + a) * MP + j] = live ? bv : 0.0;
-                for (int b = a; b < d; ++b, ++idx) {
-                    const double av = P.Aj[(static_cast<int64_t>(a) * d + b) * MP + j];
-                    P.Wc[static_cast<int64_t>(idx) * MP + j] = live ? (a == b ? -0.5 * av : -av) : 0.0;
-                }
-            }
-            P.Wc[j] = live ? -0.5 * c0 : 0.0;
-            for (int r = idx; r < P.KQ; ++r) P.Wc[static_cast<int64_t>(r) * MP + j] = 0.0;
-        }
         if (need_sigma) {
             StridedMat S{P.Sj + j, MP, d};
             StridedMat A{P.Aj + j, MP, d};
@@ -109,10 +93,88 @@ __global__ void prep_kernel(const double* __restrict__ th, Params P, int need_si
     if (j < k) P.bk[j] = th[P.oB + j];
 }
 
+// cov modes, per missing-input pattern g (observed set o, missing u) and basis j:
+//   M  = (Sigma_j(o,o))^-1 = A_oo - A_ou A_uu^-1 A_uo      (A = Gamma_j' Gamma_j, getPHI.m:73-76)
+//   G  = A_uu^-1 A_uo                                       (GPz.m:156)
+//   W  = coefficients of  -1/2 (x-p)_o' M (x-p)_o - 1/2 |u| ln 2  in the monomials [1, x_a, x_a x_b (a<=b)]
+template <int DMAX>
+__global__ void __launch_bounds__(128)
+prep_patterns_kernel(Params P) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = blockIdx.y;
+    const int d = P.d, m = P.m, MP = P.MP;
+    if (j >= MP) return;
+    const unsigned char* ob = P.obs + g * d;
+    double* Mg = P.Mg + static_cast<int64_t>(g) * d * d * MP;
+    double* Gg = P.Gg + static_cast<int64_t>(g) * d * d * MP;
+    double* Wg = P.Wc != nullptr ? P.Wc + static_cast<int64_t>(g) * P.KQ * MP : nullptr;
+    if (j >= m) {
+        for (int e = 0; e < d * d; ++e) Mg[static_cast<int64_t>(e) * MP + j] = Gg[static_cast<int64_t>(e) * MP + j] = 0.0;
+        if (Wg != nullptr)
+            for (int r = 0; r < P.KQ; ++r) Wg[static_cast<int64_t>(r) * MP + j] = 0.0;
+        return;
+    }
+    int ui[DMAX];
+    int nu = 0;
+    for (int a = 0; a < d; ++a)
+        if (!ob[a]) ui[nu++] = a;
+    double U[DMAX * DMAX];            // A_uu, then its inverse (nu x nu)
+    LocalMat Um{U, nu};
+    for (int r = 0; r < nu; ++r)
+        for (int c = 0; c < nu; ++c) Um(r, c) = P.Aj[(static_cast<int64_t>(ui[r]) * d + ui[c]) * MP + j];
+    double hl = 0.0;
+    bool ok = true;
+    if (nu > 0) ok = spd_inv(Um, nu, &hl);
+    // G(e,b) for e in u, b in o; zero elsewhere
+    for (int a = 0; a < d; ++a)
+        for (int b = 0; b < d; ++b) Gg[(static_cast<int64_t>(a) * d + b) * MP + j] = 0.0;
+    for (int r = 0; r < nu; ++r)
+        for (int b = 0; b < d; ++b) {
+            if (!ob[b]) continue;
+            double s = 0.0;
+            for (int c = 0; c < nu; ++c) s += Um(r, c) * P.Aj[(static_cast<int64_t>(ui[c]) * d + b) * MP + j];
+            Gg[(static_cast<int64_t>(ui[r]) * d + b) * MP + j] = ok ? s : nan("");
+        }
+    // M(a,b) = A(a,b) - sum_{e in u} A(a,e) G(e,b)   for a,b in o
+    for (int a = 0; a < d; ++a)
+        for (int b = 0; b < d; ++b) {
+            double v = 0.0;
+            if (ob[a] && ob[b]) {
+                v = P.Aj[(static_cast<int64_t>(a) * d + b) * MP + j];
+                for (int r = 0; r < nu; ++r)
+                    v -= P.Aj[(static_cast<int64_t>(a) * d + ui[r]) * MP + j] * Gg[(static_cast<int64_t>(ui[r]) * d + b) * MP + j];
+            }
+            Mg[(static_cast<int64_t>(a) * d + b) * MP + j] = v;
+        }
+    if (Wg == nullptr) return;
+    double c0 = 0.0;
+    int idx = 1 + d;
+    for (int a = 0; a < d; ++a) {
+        double bv = 0.0;
+        for (int b = 0; b < d; ++b) bv += Mg[(static_cast<int64_t>(a) * d + b) * MP + j] * P.Pt[b * MP + j];
+        c0 += bv * P.Pt[a * MP + j];
+        Wg[static_cast<int64_t>(1 + a) * MP + j] = bv;
+        for (int b = a; b < d; ++b, ++idx) {
+            const double av = Mg[(static_cast<int64_t>(a) * d + b) * MP + j];
+            Wg[static_cast<int64_t>(idx) * MP + j] = (a == b) ? -0.5 * av : -av;
+        }
+    }
+    Wg[j] = -0.5 * c0 - 0.5 * nu * kLn2;
+    for (int r = idx; r < P.KQ; ++r) Wg[static_cast<int64_t>(r) * MP + j] = 0.0;
+}
+
 int prep_params(const double* d_theta, const Params& P, int need_sigma, cudaStream_t st, int64_t* launches) {
     prep_kernel<<<static_cast<unsigned>(ceil_div(P.MP, 128)), 128, 0, st>>>(d_theta, P, need_sigma);
     GPZ_KERNEL_CHECK();
     ++*launches;
+    if (mode_is_cov(P.mode) && P.Mg != nullptr) {
+        dim3 grid(static_cast<unsigned>(ceil_div(P.MP, 128)), static_cast<unsigned>(P.npat));
+        if (P.d <= 8) prep_patterns_kernel<8><<<grid, 128, 0, st>>>(P);
+        else if (P.d <= 16) prep_patterns_kernel<16><<<grid, 128, 0, st>>>(P);
+        else prep_patterns_kernel<32><<<grid, 128, 0, st>>>(P);
+        GPZ_KERNEL_CHECK();
+        ++*launches;
+    }
     return GPZ_OK;
 }
 
@@ -337,17 +399,29 @@ int phi_build(const Params& P, const RowData& R, int64_t r0, int64_t r1, double*
     const bool psi = R.Psi != nullptr;
     if (R.F != nullptr && P.Wc != nullptr && !psi && !R.has_nan) {
         // tensor-core path: PHI = exp(F W), row-dot partials per 128-column tile, then an ordered sum
-        const int64_t rows = r1 - r0;
         const int ntn = P.MP / TILE;
-        double* p0 = dot_scratch;
-        double* p1 = dot_scratch + static_cast<int64_t>(ntn) * rows;
-        rc = phi_gemm(R.F + r0 * P.QP, P.QP, P.KQ, P.Wc, P.MP, P.m, rows, Phi, dots.n, dots.vec[0], dots.vec[1], p0, p1, rows,
-                      R.ycol != nullptr ? R.ycol + r0 : nullptr, st, launches);
-        if (rc) return rc;
-        for (int q = 0; q < dots.n; ++q) {
-            sum_parts_kernel<<<static_cast<unsigned>(ceil_div(rows, 256)), 256, 0, st>>>(q == 0 ? p0 : p1, ntn, rows, rows, dots.out[q] + r0);
-            GPZ_KERNEL_CHECK();
-            ++*launches;
+        const size_t ng = R.g_pat.empty() ? 1 : R.g_pat.size();
+        for (size_t g = 0; g < ng; ++g) {        // one launch per missing-input pattern group (one group without NaN)
+            int64_t s0 = r0, s1 = r1;
+            int pat = 0;
+            if (!R.g_pat.empty()) {
+                s0 = R.g_r0[g] > r0 ? R.g_r0[g] : r0;
+                s1 = R.g_r1[g] < r1 ? R.g_r1[g] : r1;
+                pat = R.g_pat[g];
+            }
+            if (s1 <= s0) continue;
+            const int64_t rows = s1 - s0;
+            double* p0 = dot_scratch;
+            double* p1 = dot_scratch + static_cast<int64_t>(ntn) * rows;
+            rc = phi_gemm(R.F + s0 * P.QP, P.QP, P.KQ, P.Wc + static_cast<int64_t>(pat) * P.KQ * P.MP, P.MP, P.m, rows,
+                          Phi != nullptr ? Phi + (s0 - r0) * P.MP : nullptr, dots.n, dots.vec[0], dots.vec[1], p0, p1, rows,
+                          R.ycol != nullptr ? R.ycol + s0 : nullptr, st, launches);
+            if (rc) return rc;
+            for (int q = 0; q < dots.n; ++q) {
+                sum_parts_kernel<<<static_cast<unsigned>(ceil_div(rows, 256)), 256, 0, st>>>(q == 0 ? p0 : p1, ntn, rows, rows, dots.out[q] + s0);
+                GPZ_KERNEL_CHECK();
+                ++*launches;
+            }
         }
         return GPZ_OK;
     }
@@ -358,8 +432,8 @@ int phi_build(const Params& P, const RowData& R, int64_t r0, int64_t r1, double*
         ++*launches;
         return rc;
     }
-    if (R.has_nan) {
-        set_error("covariance modes (GC/VC) with missing inputs (NaN) are not supported yet");
+    if (R.has_nan || R.g_pat.size() > 1 || (R.g_pat.size() == 1 && R.g_pat[0] != 0)) {
+        set_error("covariance modes with missing inputs need the tensor-core PHI path (no Psi, option tensor_phi=1)");
         return GPZ_ERR_USAGE;
     }
     if (!psi) {

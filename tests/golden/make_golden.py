@@ -21,6 +21,7 @@ CASES = {
     "cfg5_GC_psi": (150, 6, 20, "GC", True, True, False, 1),
     "GL_nan": (300, 4, 16, "GL", True, False, True, 1),
     "GD_psi_nan_k2": (300, 3, 12, "GD", False, True, True, 2),
+    "VC_nan": (400, 4, 24, "VC", True, False, True, 1),
 }
 
 
