@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libgpz_b200.so")
 
 EXPORTS = [
     "gpz_last_error", "gpz_version", "gpz_theta_len", "gpz_g_dim", "gpz_create", "gpz_destroy",
-    "gpz_comm_unique_id", "gpz_comm_init", "gpz_eval", "gpz_eval_dev", "gpz_fit", "gpz_phi", "gpz_rows",
+    "gpz_comm_unique_id", "gpz_comm_init", "gpz_eval", "gpz_eval_dev", "gpz_fit", "gpz_phi", "gpz_get_prior", "gpz_rows",
     "gpz_predict", "gpz_inv_logdet", "gpz_dxy", "gpz_stream", "gpz_sync", "gpz_launch_count",
     "gpz_last_timing", "gpz_set_option",
 ]
@@ -66,7 +66,9 @@ def load():
     lib.gpz_fit.restype = C.c_int
     lib.gpz_fit.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
     lib.gpz_phi.restype = C.c_int
-    lib.gpz_phi.argtypes = [C.c_void_p, _dp, C.c_int, _dp, _dp]
+    lib.gpz_phi.argtypes = [C.c_void_p, _dp, C.c_int, _dp, _dp, _dp]
+    lib.gpz_get_prior.restype = C.c_int
+    lib.gpz_get_prior.argtypes = [C.c_void_p, _dp, _dp]
     lib.gpz_rows.restype = C.c_int64
     lib.gpz_rows.argtypes = [C.c_void_p, C.c_int]
     lib.gpz_predict.restype = C.c_int
@@ -183,13 +185,21 @@ class Context:
     def rows(self, which=0):
         return int(self._lib.gpz_rows(self._h, which))
 
-    def phi(self, theta, which=0, want_phi=True):
+    def phi(self, theta, which=0, want_phi=True, want_N=False):
         th = f64(theta).reshape(-1)
         n = self.rows(which)
         PHI = np.empty((n, self.model.m), order="F") if want_phi else None
         lnb = np.empty((n, self.model.k), order="F")
-        check(self._lib.gpz_phi(self._h, ptr(th), which, ptr(PHI), ptr(lnb)))
-        return PHI, lnb
+        N = np.empty((n, self.model.m), order="F") if want_N else None
+        check(self._lib.gpz_phi(self._h, ptr(th), which, ptr(PHI), ptr(lnb), ptr(N)))
+        return (PHI, lnb, N) if want_N else (PHI, lnb)
+
+    def get_prior(self, theta):
+        """prior = getPrior(X,Psi,theta,model,training) (GPz/getPrior.m)."""
+        th = f64(theta).reshape(-1)
+        pr = np.empty(self.model.m)
+        check(self._lib.gpz_get_prior(self._h, ptr(th), ptr(pr)))
+        return pr
 
     def stream(self) -> int:
         return int(self._lib.gpz_stream(self._h) or 0)

@@ -536,7 +536,7 @@ int fill_params(Params& P, const gpz_model* model) {
     P.xshift = nullptr;
     P.npat = 1;
     P.obs = nullptr;
-    P.Mg = P.Gg = nullptr;
+    P.Mg = P.Gg = P.lndM = nullptr;
     return GPZ_OK;
 }
 
@@ -576,6 +576,7 @@ int alloc_params(Params& P, std::vector<void*>& list, int need_sigma) {
     if (mode_is_cov(P.mode)) {
         if ((rc = dev_alloc(list, &P.Mg, static_cast<int64_t>(P.npat) * d * d * MP))) return rc;
         if ((rc = dev_alloc(list, &P.Gg, static_cast<int64_t>(P.npat) * d * d * MP))) return rc;
+        if ((rc = dev_alloc(list, &P.lndM, static_cast<int64_t>(P.npat) * MP))) return rc;
         if ((rc = dev_alloc(list, &P.obs, static_cast<int64_t>(P.npat) * d))) return rc;
         GPZ_CUDA(cudaMemset(P.obs, 1, static_cast<size_t>(P.npat) * d));
     }
@@ -1305,7 +1306,7 @@ int gpz_fit(gpz_ctx* c, const double* theta, double* nlogML_k, double* w, double
 
 int64_t gpz_rows(const gpz_ctx* c, int which) { return c ? (which ? c->va.n : c->tr.n) : -1; }
 
-int gpz_phi(gpz_ctx* c, const double* theta, int which, double* PHI, double* lnBeta_i) {
+int gpz_phi(gpz_ctx* c, const double* theta, int which, double* PHI, double* lnBeta_i, double* N) {
     if (!c || !theta) {
         set_error("gpz_phi: NULL argument");
         return GPZ_ERR_USAGE;
@@ -1322,7 +1323,7 @@ int gpz_phi(gpz_ctx* c, const double* theta, int which, double* PHI, double* lnB
     if ((rc = prep_params(c->d_theta, P, c->has_psi, st, &c->launches))) return rc;
     double *dotv = nullptr, *colmaj = nullptr;
     GPZ_CUDA(cudaMalloc(&dotv, sizeof(double) * n * P.k));
-    if (PHI) GPZ_CUDA(cudaMalloc(&colmaj, sizeof(double) * c->chunk_rows * P.m));
+    if (PHI || N) GPZ_CUDA(cudaMalloc(&colmaj, sizeof(double) * c->chunk_rows * P.m));
     std::vector<double> hbuf;
     for (int64_t r0 = 0; r0 < n; r0 += c->chunk_rows) {
         const int64_t r1 = (r0 + c->chunk_rows < n) ? r0 + c->chunk_rows : n;
@@ -1337,13 +1338,22 @@ int gpz_phi(gpz_ctx* c, const double* theta, int which, double* PHI, double* lnB
                                        cudaMemcpyDeviceToHost, st));
             GPZ_CUDA(cudaStreamSynchronize(st));
         }
+        if (N) {
+            if ((rc = phi_to_density(P, R, r0, r1, c->Phi, c->H, st, &c->launches))) return rc;
+            if ((rc = transpose_out(c->H, MP, r1 - r0, P.m, colmaj, st))) return rc;
+            GPZ_CUDA(cudaMemcpy2DAsync(N + r0, sizeof(double) * n, colmaj, sizeof(double) * (r1 - r0), sizeof(double) * (r1 - r0), P.m,
+                                       cudaMemcpyDeviceToHost, st));
+            GPZ_CUDA(cudaStreamSynchronize(st));
+        }
     }
-    if (PHI && !R.perm.empty()) {            // rows are stored sorted by missing-input pattern: restore selection order
-        std::vector<double> tmp(static_cast<size_t>(n));
-        for (int j = 0; j < P.m; ++j) {
-            double* col = PHI + static_cast<int64_t>(j) * n;
-            for (int64_t i = 0; i < n; ++i) tmp[static_cast<size_t>(R.perm[i])] = col[i];
-            memcpy(col, tmp.data(), sizeof(double) * n);
+    for (double* M : {PHI, N}) {
+        if (M && !R.perm.empty()) {          // rows are stored sorted by missing-input pattern: restore selection order
+            std::vector<double> tmp(static_cast<size_t>(n));
+            for (int j = 0; j < P.m; ++j) {
+                double* col = M + static_cast<int64_t>(j) * n;
+                for (int64_t i = 0; i < n; ++i) tmp[static_cast<size_t>(R.perm[i])] = col[i];
+                memcpy(col, tmp.data(), sizeof(double) * n);
+            }
         }
     }
     if (lnBeta_i) {
@@ -1362,6 +1372,84 @@ int gpz_phi(gpz_ctx* c, const double* theta, int which, double* PHI, double* lnB
     GPZ_CUDA(cudaStreamSynchronize(st));
     cudaFree(dotv);
     if (colmaj) cudaFree(colmaj);
+    return GPZ_OK;
+}
+
+// priors over the bases by EM on the normalised densities (GPz/getPrior.m:1-22), training rows
+__global__ void prior_inv_kernel(const double* __restrict__ s, int64_t n, double* __restrict__ yw) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    yw[i * 32] = 1.0 / s[i];
+    for (int c = 1; c < 32; ++c) yw[i * 32 + c] = 0.0;
+}
+// prior_j <- prior_j * t_j / n ; out[0] = |old-new|^2, out[1] = |old+new|^2      (getPrior.m:12-17)
+__global__ void __launch_bounds__(256)
+prior_update_kernel(double* __restrict__ prior, const double* __restrict__ R32, const double* __restrict__ nrows, int m,
+                    double* __restrict__ out) {
+    __shared__ double sh[8];
+    double a = 0.0, b = 0.0;
+    for (int j = threadIdx.x; j < m; j += 256) {
+        const double o = prior[j];
+        const double nw = o * R32[static_cast<int64_t>(j) * 32] / nrows[0];
+        prior[j] = nw;
+        a += (o - nw) * (o - nw);
+        b += (o + nw) * (o + nw);
+    }
+    a = gpz::block_sum<256>(a, sh);
+    b = gpz::block_sum<256>(b, sh);
+    if (threadIdx.x == 0) {
+        out[0] = a;
+        out[1] = b;
+    }
+}
+
+int gpz_get_prior(gpz_ctx* c, const double* theta, double* prior) {
+    if (!c || !theta || !prior) {
+        set_error("gpz_get_prior: NULL argument");
+        return GPZ_ERR_USAGE;
+    }
+    GPZ_CUDA(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure_workspace(c))) return rc;
+    Params& P = c->P;
+    const int64_t n = c->tr.n, MP = P.MP;
+    cudaStream_t st = c->st;
+    if (!c->resident) {
+        set_error("gpz_get_prior needs PHI resident in HBM (lower n per GPU)");
+        return GPZ_ERR_USAGE;
+    }
+    GPZ_CUDA(cudaMemcpyAsync(c->d_theta, theta, sizeof(double) * P.p, cudaMemcpyHostToDevice, st));
+    if ((rc = prep_params(c->d_theta, P, c->has_psi, st, &c->launches))) return rc;
+    if ((rc = phi_build(P, c->tr, 0, n, c->Phi, DotSpec{0, {nullptr, nullptr}, {nullptr, nullptr}}, c->dot_scratch, st, &c->launches))) return rc;
+    if ((rc = phi_to_density(P, c->tr, 0, n, c->Phi, c->H, st, &c->launches))) return rc;       // N lives in the H buffer
+    double* d_prior = c->dwda;             // [MP] scratch vectors of the eval path are free here
+    double* d_s = c->pred;
+    double* d_R = c->Rvec;                 // [MP][32]
+    double* d_cnt = c->scal1;              // [0] = global row count
+    std::vector<double> h(static_cast<size_t>(MP), 0.0);
+    for (int j = 0; j < P.m; ++j) h[j] = 1.0 / P.m;                                               // getPrior.m:5
+    GPZ_CUDA(cudaMemcpyAsync(d_prior, h.data(), sizeof(double) * MP, cudaMemcpyHostToDevice, st));
+    const double nd = static_cast<double>(n);
+    GPZ_CUDA(cudaMemcpyAsync(d_cnt, &nd, sizeof(double), cudaMemcpyHostToDevice, st));
+    if ((rc = allreduce(c, d_cnt, 1))) return rc;
+    const int T = static_cast<int>(MP / TILE);
+    const int ns1 = c->sm_count / T > 0 ? c->sm_count / T : 1;
+    for (int iter = 0; iter < 100; ++iter) {                                                      // getPrior.m:7
+        if ((rc = rowdot(c->H, MP, P.m, n, DotSpec{1, {d_prior, nullptr}, {d_s, nullptr}}, st, &c->launches))) return rc;
+        prior_inv_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, st>>>(d_s, n, c->yw);
+        GPZ_KERNEL_CHECK();
+        if ((rc = atb_general(c->H, MP, static_cast<int>(MP), c->yw, 32, 32, c->ones, 0, n, ns1, c->atb_partial, 0, 1, d_R, st, &c->launches))) return rc;
+        if ((rc = allreduce(c, d_R, MP * 32))) return rc;
+        prior_update_kernel<<<1, 256, 0, st>>>(d_prior, d_R, d_cnt, P.m, c->d_out);
+        GPZ_KERNEL_CHECK();
+        c->launches += 2;
+        double nr[2];
+        GPZ_CUDA(cudaMemcpyAsync(nr, c->d_out, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
+        GPZ_CUDA(cudaStreamSynchronize(st));
+        if (!(sqrt(nr[0]) / sqrt(nr[1]) >= 1e-10)) break;                                         // getPrior.m:17 (also stops on NaN)
+    }
+    GPZ_CUDA(cudaMemcpyAsync(prior, d_prior, sizeof(double) * P.m, cudaMemcpyDeviceToHost, st));
+    GPZ_CUDA(cudaStreamSynchronize(st));
     return GPZ_OK;
 }
 

@@ -38,6 +38,7 @@ struct Params {
     unsigned char* obs;   // [npat][d]          1 = dim observed in this pattern
     double* Mg;     // [npat][d*d][MP]  (Sigma_j(o,o))^-1 embedded in d x d (zero on missing rows/cols)
     double* Gg;     // [npat][d*d][MP]  iSigma(u,u)^-1 iSigma(u,o) embedded (row e in u, col b in o)
+    double* lndM;   // [npat][MP]       ln det of the marginal precision = -ln det Sigma_j(o,o)
 };
 
 struct RowData {          // one resident row set (training or validation rows of this rank)
@@ -66,6 +67,9 @@ int prep_params(const double* d_theta, const Params& P, int need_sigma, cudaStre
 // dot_scratch: >= 2 * (MP/128) * (r1-r0) doubles (row-dot partials of the tensor-core path)
 int phi_build(const Params& P, const RowData& R, int64_t r0, int64_t r1, double* Phi /*[rows][MP] at row r0 -> index 0*/,
               const DotSpec& dots, double* dot_scratch, cudaStream_t st, int64_t* launches);
+// N = PHI .* exp(lnN - lnPHI): the normalised basis densities, getPHI's 4th output (getPHI.m:77,87,98,105,114)
+int phi_to_density(const Params& P, const RowData& R, int64_t r0, int64_t r1, const double* Phi, double* N, cudaStream_t st,
+                   int64_t* launches);
 int rowdot(const double* Phi, int64_t ld, int m, int64_t n, const DotSpec& dots, cudaStream_t st, int64_t* launches);
 int dxy_device(const double* X, int64_t n, const double* Y, int m, int d, double* D, cudaStream_t st);
 int transpose_out(const double* src_rowmajor, int64_t ld, int64_t n, int m, double* dst_colmajor, cudaStream_t st);

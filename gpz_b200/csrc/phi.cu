@@ -109,6 +109,7 @@ prep_patterns_kernel(Params P) {
     double* Gg = P.Gg + static_cast<int64_t>(g) * d * d * MP;
     double* Wg = P.Wc != nullptr ? P.Wc + static_cast<int64_t>(g) * P.KQ * MP : nullptr;
     if (j >= m) {
+        P.lndM[static_cast<int64_t>(g) * MP + j] = 0.0;
         for (int e = 0; e < d * d; ++e) Mg[static_cast<int64_t>(e) * MP + j] = Gg[static_cast<int64_t>(e) * MP + j] = 0.0;
         if (Wg != nullptr)
             for (int r = 0; r < P.KQ; ++r) Wg[static_cast<int64_t>(r) * MP + j] = 0.0;
@@ -146,6 +147,18 @@ prep_patterns_kernel(Params P) {
             }
             Mg[(static_cast<int64_t>(a) * d + b) * MP + j] = v;
         }
+    {   // ln det M over the observed block (for the normalised densities N)
+        int oi[DMAX];
+        int no = 0;
+        for (int a = 0; a < d; ++a)
+            if (ob[a]) oi[no++] = a;
+        LocalMat Om{U, no};
+        for (int r = 0; r < no; ++r)
+            for (int c = 0; c <= r; ++c) Om(r, c) = Mg[(static_cast<int64_t>(oi[r]) * d + oi[c]) * MP + j];
+        double hm = 0.0;
+        const bool okm = no == 0 || chol_lower(Om, no, &hm);
+        P.lndM[static_cast<int64_t>(g) * MP + j] = okm ? 2.0 * hm : nan("");
+    }
     if (Wg == nullptr) return;
     double c0 = 0.0;
     int idx = 1 + d;
@@ -458,6 +471,62 @@ int phi_build(const Params& P, const RowData& R, int64_t r0, int64_t r1, double*
     }
     if (dots.n > 0) return rowdot(Phi, P.MP, P.m, rows, DotSpec{dots.n, {dots.vec[0], dots.vec[1]},
                                   {dots.out[0] + r0, dots.n > 1 ? dots.out[1] + r0 : nullptr}}, st, launches);
+    return GPZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// N_ij = PHI_ij * exp(c_ij),  c_ij = -1/2 ln|Sigma_j(o,o)| - 1/2 |o| ln 2pi + 1/2 |u| ln 2   (o/u = observed/missing dims of row i)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+density_kernel(Params P, const double* __restrict__ X, int64_t n, int64_t r0, int64_t r1, int pat,
+               const double* __restrict__ Phi, double* __restrict__ N) {
+    const int j = blockIdx.x * 128 + threadIdx.x;
+    const int d = P.d, MP = P.MP;
+    const int64_t rb = r0 + static_cast<int64_t>(blockIdx.y) * 64;
+    const bool cov = mode_is_cov(P.mode);
+    const double hl2pi = 0.91893853320467274178;    // 1/2 ln 2pi
+    double cj = 0.0;
+    int no_pat = d;
+    if (cov) {
+        no_pat = 0;
+        for (int a = 0; a < d; ++a) no_pat += P.obs[pat * d + a];
+        cj = 0.5 * P.lndM[static_cast<int64_t>(pat) * MP + j] - hl2pi * no_pat + 0.5 * kLn2 * (d - no_pat);
+    }
+    for (int r = 0; r < 64; ++r) {
+        const int64_t i = rb + r;
+        if (i >= r1) break;
+        double c = cj;
+        if (!cov) {
+            int nu = 0;
+            for (int a = 0; a < d; ++a) {
+                const double x = X[a * n + i];
+                if (x != x) { ++nu; continue; }
+                c += log(fabs(P.Gt[a * MP + j])) - hl2pi;
+            }
+            c += 0.5 * kLn2 * nu;
+        }
+        const int64_t off = (i - r0) * MP + j;
+        N[off] = (j < P.m) ? Phi[off] * exp(c) : 0.0;
+    }
+}
+
+int phi_to_density(const Params& P, const RowData& R, int64_t r0, int64_t r1, const double* Phi, double* N, cudaStream_t st,
+                   int64_t* launches) {
+    const size_t ng = R.g_pat.empty() ? 1 : R.g_pat.size();
+    for (size_t g = 0; g < ng; ++g) {
+        int64_t s0 = r0, s1 = r1;
+        int pat = 0;
+        if (!R.g_pat.empty()) {
+            s0 = R.g_r0[g] > r0 ? R.g_r0[g] : r0;
+            s1 = R.g_r1[g] < r1 ? R.g_r1[g] : r1;
+            pat = R.g_pat[g];
+        }
+        if (s1 <= s0) continue;
+        dim3 grid(static_cast<unsigned>(P.MP / 128), static_cast<unsigned>(ceil_div(s1 - s0, 64)));
+        density_kernel<<<grid, 128, 0, st>>>(P, R.X, R.n, s0, s1, pat, Phi + (s0 - r0) * P.MP, N + (s0 - r0) * P.MP);
+        GPZ_KERNEL_CHECK();
+        ++*launches;
+    }
     return GPZ_OK;
 }
 

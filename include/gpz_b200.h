@@ -90,10 +90,14 @@ int gpz_eval_dev(gpz_ctx* ctx, const double* d_theta, double* d_out);
  * w m x k; iSigma_w m x m x k.                                                                   */
 int gpz_fit(gpz_ctx* ctx, const double* theta, double* nlogML_k, double* w, double* iSigma_w);
 
-/* ---- [PHI,~,lnBeta_i] = getPHI(X,Psi,theta,model,selection) on the context's rows ----------------
- * (GPz/getPHI.m:1-127).  which: 0 = training rows, 1 = validation rows.  PHI n x m, lnBeta_i n x k;
- * either may be NULL.                                                                            */
-int gpz_phi(gpz_ctx* ctx, const double* theta, int which, double* PHI, double* lnBeta_i);
+/* ---- [PHI,~,lnBeta_i,N] = getPHI(X,Psi,theta,model,selection) on the context's rows --------------
+ * (GPz/getPHI.m:1-127).  which: 0 = training rows, 1 = validation rows.  PHI n x m, lnBeta_i n x k,
+ * N n x m (normalised densities, getPHI.m:114); any of them may be NULL.                         */
+int gpz_phi(gpz_ctx* ctx, const double* theta, int which, double* PHI, double* lnBeta_i, double* N);
+
+/* ---- prior = getPrior(X,Psi,theta,model,training)  (GPz/getPrior.m:1-22, called at train.m:59,74) ---
+ * EM for the mixture weights of the bases on the training rows; prior: m doubles.                */
+int gpz_get_prior(gpz_ctx* ctx, const double* theta, double* prior);
 int64_t gpz_rows(const gpz_ctx* ctx, int which);
 
 /* ---- predict core (GPz/predict.m:60-73 dispatch; predictDiag.m:58-125, predictCov.m:53-69) -------

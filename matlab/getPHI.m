@@ -1,10 +1,12 @@
 function [PHI,Gamma,lnBeta_i,N] = getPHI(X,Psi,theta,model,selection)
 % Drop-in for GPz/getPHI.m:1 (PHI and lnBeta_i on the GPU; Gamma unpacked on the host as getPHI.m:26-40).
-% The 4th output N (normalised densities, used only by getPrior.m) is not provided by the library yet.
-if nargout > 3, error('gpz_b200:unsupported','getPHI: output N (getPrior) is not provided yet'); end
 if isempty(selection), selection = true(size(X,1),1); end
 h = gpz_b200_mex('create',model,X,zeros(size(X,1),model.k),Psi,[],selection,[]);
-[PHI,lnBeta_i] = gpz_b200_mex('phi',h,theta,0,model);
+if nargout > 3
+    [PHI,lnBeta_i,N] = gpz_b200_mex('phi',h,theta,0,model);
+else
+    [PHI,lnBeta_i] = gpz_b200_mex('phi',h,theta,0,model);
+end
 gpz_b200_mex('destroy',h);
 m = model.m; d = model.d;
 switch model.method

@@ -9,7 +9,8 @@
 //     h = gpz_b200_mex('create', model, X, Y, Psi, omega, training, validation)    -> uint64 handle
 //     [f, g, stats] = gpz_b200_mex('eval', h, theta)
 //     [nl, w, iSigma_w] = gpz_b200_mex('fit', h, theta)
-//     [PHI, lnBeta_i] = gpz_b200_mex('phi', h, theta, which)
+//     [PHI, lnBeta_i, N] = gpz_b200_mex('phi', h, theta, which, model)
+//     prior = gpz_b200_mex('get_prior', h, theta, model)
 //     [mu, nu, beta_i, gamma, PHI] = gpz_b200_mex('predict', model, theta, w, iSigma_w, Xz, Psi)
 //     [Xi, logdet] = gpz_b200_mex('inv_logdet', X)
 //     D = gpz_b200_mex('dxy', X, Y)
@@ -132,8 +133,15 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         const int64_t n = gpz_rows(ctx, which);
         plhs[0] = mxCreateDoubleMatrix(n, m.m, mxREAL);
         mxArray* lb = mxCreateDoubleMatrix(n, m.k, mxREAL);
-        if (gpz_phi(ctx, mxGetPr(prhs[2]), which, mxGetPr(plhs[0]), mxGetPr(lb))) fail("gpz_phi");
+        mxArray* N = nlhs > 2 ? mxCreateDoubleMatrix(n, m.m, mxREAL) : nullptr;
+        if (gpz_phi(ctx, mxGetPr(prhs[2]), which, mxGetPr(plhs[0]), mxGetPr(lb), N ? mxGetPr(N) : nullptr)) fail("gpz_phi");
         if (nlhs > 1) plhs[1] = lb; else mxDestroyArray(lb);
+        if (nlhs > 2) plhs[2] = N;
+    } else if (c == "get_prior") {
+        gpz_ctx* ctx = lookup(prhs[1]);
+        gpz_model m = read_model(prhs[3]);
+        plhs[0] = mxCreateDoubleMatrix(1, m.m, mxREAL);
+        if (gpz_get_prior(ctx, mxGetPr(prhs[2]), mxGetPr(plhs[0]))) fail("gpz_get_prior");
     } else if (c == "predict") {
         gpz_model m = read_model(prhs[1]);
         const size_t n = mxGetM(prhs[5]);

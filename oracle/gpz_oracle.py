@@ -238,6 +238,24 @@ def getPHI(X, Psi, theta, model: Model, selection=None, want_N=True):
 
 
 # --------------------------------------------------------------------------------------
+# getPrior.m:1-22
+# --------------------------------------------------------------------------------------
+def getPrior(X, Psi, theta, model: Model, selection=None):
+    """EM for the mixture weights of the bases (getPrior.m:5-20); N does not change between iterations."""
+    m = model.m
+    prior = np.ones((1, m)) / m
+    _, _, _, N = getPHI(X, Psi, theta, model, selection)
+    for _ in range(100):
+        old = prior
+        w = N * prior
+        w = w / np.sum(w, axis=1, keepdims=True)
+        prior = np.mean(w, axis=0, keepdims=True)
+        if np.linalg.norm(old - prior) / np.linalg.norm(old + prior) < 1e-10:
+            break
+    return prior
+
+
+# --------------------------------------------------------------------------------------
 # GPz.m:1-263
 # --------------------------------------------------------------------------------------
 @dataclass

@@ -239,3 +239,19 @@ def test_unnormalised_inputs_with_large_offset():
     ref, f, g, st, ctx = run_both(model, theta, X, Y, None, omega, tr, va)
     assert_eval_matches(model, ref, f, g, st, tol=1e-8)
     ctx.close()
+
+
+@pytest.mark.parametrize("method,psi,nan", [("VD", False, False), ("VD", True, True), ("GL", False, True), ("VC", False, False),
+                                            ("VC", False, True), ("GC", True, False)])
+def test_densities_and_get_prior(method, psi, nan):
+    """getPHI's 4th output N (getPHI.m:114) and getPrior.m's EM for the basis priors."""
+    model, theta, X, Y, Psi, omega, tr, va = problem(method, True, psi, nan, n=400, d=3, m=10, seed=17)
+    gm = L.make_model(model.d, 1, model.m, method, True)
+    ctx = L.Context(gm, X, Y, Psi, omega, tr, va)
+    PHI, lnb, N = ctx.phi(theta, 0, want_N=True)
+    _, _, _, Nr = O.getPHI(X, Psi, theta, model, tr)
+    assert rel(N, Nr) <= 1e-11
+    prior = ctx.get_prior(theta)
+    pr = O.getPrior(X, Psi, theta, model, tr)
+    assert abs(prior.sum() - 1.0) <= 1e-12 and rel(prior, pr.reshape(-1)) <= 1e-8
+    ctx.close()
