@@ -72,7 +72,7 @@ def load():
     lib.gpz_rows.restype = C.c_int64
     lib.gpz_rows.argtypes = [C.c_void_p, C.c_int]
     lib.gpz_predict.restype = C.c_int
-    lib.gpz_predict.argtypes = [C.POINTER(GpzModel), _dp, _dp, _dp, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int]
+    lib.gpz_predict.argtypes = [C.POINTER(GpzModel), _dp, _dp, _dp, C.c_int64, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int]
     lib.gpz_inv_logdet.restype = C.c_int
     lib.gpz_inv_logdet.argtypes = [C.c_int32, _dp, _dp, _dp, C.c_int]
     lib.gpz_dxy.restype = C.c_int
@@ -223,7 +223,7 @@ def comm_unique_id() -> bytes:
     return buf.raw
 
 
-def predict_core(model: GpzModel, theta, w, iSigma_w, Xz, Psi=None, want_phi=False, device=0):
+def predict_core(model: GpzModel, theta, w, iSigma_w, Xz, Psi=None, want_phi=False, device=0, priors=None):
     lib = load()
     Xz = f64(Xz)
     n = Xz.shape[0]
@@ -232,9 +232,10 @@ def predict_core(model: GpzModel, theta, w, iSigma_w, Xz, Psi=None, want_phi=Fal
     w = f64(w).reshape(m, k, order="F")
     iS = f64(iSigma_w).reshape(m, m, k, order="F")
     psi = None if Psi is None else f64(Psi)
+    pri = None if priors is None else f64(priors).reshape(-1)
     mu, nu, be, ga = (np.empty((n, k), order="F") for _ in range(4))
     PHI = np.empty((n, m), order="F") if want_phi else None
-    check(lib.gpz_predict(C.byref(model), ptr(th), ptr(w), ptr(iS), n, ptr(Xz), ptr(psi), ptr(mu), ptr(nu), ptr(be),
+    check(lib.gpz_predict(C.byref(model), ptr(th), ptr(w), ptr(iS), n, ptr(Xz), ptr(psi), ptr(pri), ptr(mu), ptr(nu), ptr(be),
                           ptr(ga), ptr(PHI), int(device)))
     return mu, nu, be, ga, PHI
 

@@ -225,7 +225,7 @@ def init(X, Y, method, m, heteroscedastic=True, normalize=True, omega=None, trai
 
 
 def train(model, X, Y, maxIter=200, maxAttempts=np.inf, omega=None, training=None, validation=None, Psi=None,
-          display=True, device=0):
+          display=True, device=0, priors_wanted=True):
     """model = train(model,X,Y,...) (GPz/train.m:1-81).  The optimiser is a host L-BFGS (SciPy's L-BFGS-B in
     place of minFunc's, SURVEY.md 2.1: out of scope, stays on the host); the callback follows
     GPz/callBack.m: best theta by validation log-likelihood, stop after maxAttempts non-improving iterations."""
@@ -286,7 +286,8 @@ def train(model, X, Y, maxIter=200, maxAttempts=np.inf, omega=None, training=Non
         oG, oA, oB, oV, oT = _theta_offsets(model)
         for name, th in (("last", theta), ("best", state["best_theta"])):
             w, iS = obj.fit(th)                                     # train.m:53,69
-            model[name].update(theta=th.copy(), w=w, iSigma_w=iS, priors=np.ones(m) / m,
+            priors = obj.ctx.get_prior(th) if priors_wanted else np.ones(m) / m          # train.m:59,74 (getPrior.m)
+            model[name].update(theta=th.copy(), w=w, iSigma_w=iS, priors=priors,
                                P=th[:m * d].reshape((m, d), order="F"))
             if model["heteroscedastic"]:
                 model[name]["v"] = th[oV:oV + m * k].reshape((m, k), order="F")
@@ -298,8 +299,8 @@ def train(model, X, Y, maxIter=200, maxAttempts=np.inf, omega=None, training=Non
 
 
 def predict(X, model, whichSet="best", Psi=None, selection=None, device=0):
-    """[mu,sigma,nu,beta_i,gamma,PHI,w,iSigma_w] = predict(X,model,...) (GPz/predict.m:1-75).  Rows with
-    missing values (predictMissing*, predictDiag.m:127-295) are not supported yet and raise."""
+    """[mu,sigma,nu,beta_i,gamma,PHI,w,iSigma_w] = predict(X,model,...) (GPz/predict.m:1-75).  Rows with missing
+    values go through predictMissing / predictNoisyMissing (diagonal modes; covariance modes raise)."""
     st = model["best"] if whichSet == "best" else model["last"]
     X = np.asarray(X, dtype=np.float64)
     n_all = X.shape[0]
@@ -312,7 +313,7 @@ def predict(X, model, whichSet="best", Psi=None, selection=None, device=0):
     Xz = (X - model["muX"][None, :]) / model["sdX"][None, :]
     Psi = fixPsi(Psi, n, model["sdX"], model["method"])
     mu, nu, beta_i, gamma, PHI = L.predict_core(_c_model(model), st["theta"], st["w"], st["iSigma_w"], Xz, Psi,
-                                                want_phi=True, device=device)
+                                                want_phi=True, device=device, priors=st.get("priors"))
     sigma = nu + beta_i + gamma                                     # predict.m:72
     mu = mu + model["muY"][None, :]                                 # predict.m:73
     return mu, sigma, nu, beta_i, gamma, PHI, st["w"], st["iSigma_w"]

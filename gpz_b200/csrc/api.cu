@@ -1453,9 +1453,82 @@ int gpz_get_prior(gpz_ctx* c, const double* theta, double* prior) {
     return GPZ_OK;
 }
 
+// one group of rows sharing a missing-input pattern, diagonal modes (predictDiag.m:127-295); host buffers in/out
+static int predict_missing_group(const gpz_model* model, const double* theta, const double* w, const double* iSigma_w,
+                                 int64_t n, const double* Xg, const double* Psig, const double* priors,
+                                 const std::vector<unsigned char>& ob, double* mu, double* nu, double* beta_i, double* gamma,
+                                 double* PHI, int device) {
+    Params P{};
+    int rc;
+    if ((rc = fill_params(P, model))) return rc;
+    if ((rc = check_device(device))) return rc;
+    std::vector<void*> allocs;
+    cudaStream_t st = nullptr;
+    int64_t launches = 0;
+    auto cleanup = [&](int code) {
+        if (st) {
+            cudaStreamSynchronize(st);
+            cudaStreamDestroy(st);
+        }
+        for (void* p : allocs) cudaFree(p);
+        return code;
+    };
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("cudaStreamCreate failed");
+        return GPZ_ERR_CUDA;
+    }
+    const int64_t MP = P.MP;
+    const int k = P.k, d = P.d;
+    if ((rc = alloc_params(P, allocs, 0))) return cleanup(rc);
+    double *d_theta, *d_w, *d_Sinv, *d_prior, *d_X, *d_Psi = nullptr, *d_out, *d_Phi, *d_col = nullptr;
+    unsigned char* d_ob;
+    if ((rc = dev_alloc(allocs, &d_theta, P.p)) || (rc = dev_alloc(allocs, &d_w, k * MP)) || (rc = dev_alloc(allocs, &d_Sinv, k * MP * MP)) ||
+        (rc = dev_alloc(allocs, &d_prior, MP)) || (rc = dev_alloc(allocs, &d_X, n * d)) || (rc = dev_alloc(allocs, &d_out, 4 * k * n)) ||
+        (rc = dev_alloc(allocs, &d_Phi, n * MP)) || (rc = dev_alloc(allocs, &d_ob, d)))
+        return cleanup(rc);
+    if (Psig && (rc = dev_alloc(allocs, &d_Psi, n * d))) return cleanup(rc);
+    if (PHI && (rc = dev_alloc(allocs, &d_col, n * P.m))) return cleanup(rc);
+    std::vector<double> hx(Xg, Xg + n * d);
+    for (double& v : hx)
+        if (v != v) v = 0.0;                      // missing dims are never read (ob mask); keep the buffer NaN-free
+    bool ok = cudaMemcpy(d_theta, theta, sizeof(double) * P.p, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemset(d_w, 0, sizeof(double) * k * MP) == cudaSuccess && cudaMemset(d_Sinv, 0, sizeof(double) * k * MP * MP) == cudaSuccess;
+    ok = ok && cudaMemset(d_prior, 0, sizeof(double) * MP) == cudaSuccess;
+    ok = ok && cudaMemcpy2D(d_w, sizeof(double) * MP, w, sizeof(double) * P.m, sizeof(double) * P.m, k, cudaMemcpyHostToDevice) == cudaSuccess;
+    for (int o = 0; o < k && ok; ++o)
+        ok = cudaMemcpy2D(d_Sinv + static_cast<int64_t>(o) * MP * MP, sizeof(double) * MP, iSigma_w + static_cast<int64_t>(o) * P.m * P.m,
+                          sizeof(double) * P.m, sizeof(double) * P.m, P.m, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemcpy(d_prior, priors, sizeof(double) * P.m, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemcpy(d_X, hx.data(), sizeof(double) * n * d, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemcpy(d_ob, ob.data(), d, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (Psig) ok = ok && cudaMemcpy(d_Psi, Psig, sizeof(double) * n * d, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) {
+        set_error("predict_missing_group: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return cleanup(GPZ_ERR_CUDA);
+    }
+    if ((rc = prep_params(d_theta, P, 0, st, &launches))) return cleanup(rc);
+    double *d_mu = d_out, *d_nu = d_out + k * n, *d_be = d_out + 2 * k * n, *d_ga = d_out + 3 * k * n;
+    if ((rc = predict_missing_diag(P, d_X, d_Psi, n, d_ob, d_prior, d_w, d_Sinv, d_mu, d_nu, d_be, d_ga, d_Phi, st, &launches)))
+        return cleanup(rc);
+    if (PHI) {
+        if ((rc = transpose_out(d_Phi, MP, n, P.m, d_col, st))) return cleanup(rc);
+        ok = cudaMemcpyAsync(PHI, d_col, sizeof(double) * n * P.m, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    }
+    ok = ok && cudaMemcpyAsync(mu, d_mu, sizeof(double) * k * n, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(nu, d_nu, sizeof(double) * k * n, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(beta_i, d_be, sizeof(double) * k * n, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(gamma, d_ga, sizeof(double) * k * n, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(st) == cudaSuccess;
+    if (!ok) {
+        set_error("predict_missing_group: %s", cudaGetErrorString(cudaGetLastError()));
+        return cleanup(GPZ_ERR_CUDA);
+    }
+    return cleanup(GPZ_OK);
+}
+
 int gpz_predict(const gpz_model* model, const double* theta, const double* w, const double* iSigma_w, int64_t n,
-                const double* Xz, const double* Psi, double* mu, double* nu, double* beta_i, double* gamma, double* PHI,
-                int device) {
+                const double* Xz, const double* Psi, const double* priors, double* mu, double* nu, double* beta_i,
+                double* gamma, double* PHI, int device) {
     if (!theta || !w || !iSigma_w || !Xz || !mu || !nu || !beta_i || !gamma || n < 0) {
         set_error("gpz_predict: NULL argument");
         return GPZ_ERR_USAGE;
@@ -1464,6 +1537,70 @@ int gpz_predict(const gpz_model* model, const double* theta, const double* w, co
     int rc;
     if ((rc = fill_params(P, model))) return rc;
     if ((rc = check_device(device))) return rc;
+    {   // rows with missing inputs: group by NaN pattern and dispatch per group (predict.m:45-69)
+        bool any_nan = false;
+        for (int64_t i = 0; i < n * P.d && !any_nan; ++i) any_nan = Xz[i] != Xz[i];
+        if (any_nan) {
+            if (mode_is_cov(P.mode)) {
+                set_error("gpz_predict: rows with missing inputs are not supported for covariance modes yet (predictCov.m:134-336)");
+                return GPZ_ERR_USAGE;
+            }
+            if (!priors) {
+                set_error("gpz_predict: rows with missing inputs need the basis priors (model.best.priors, getPrior.m)");
+                return GPZ_ERR_USAGE;
+            }
+            std::map<std::string, std::vector<int64_t>> groups;
+            std::vector<std::string> order;
+            std::string key(static_cast<size_t>(P.d), '1');
+            for (int64_t i = 0; i < n; ++i) {
+                for (int a = 0; a < P.d; ++a) key[a] = (Xz[static_cast<int64_t>(a) * n + i] == Xz[static_cast<int64_t>(a) * n + i]) ? '1' : '0';
+                auto it = groups.find(key);
+                if (it == groups.end()) {
+                    order.push_back(key);
+                    it = groups.emplace(key, std::vector<int64_t>()).first;
+                }
+                it->second.push_back(i);
+            }
+            const int k = P.k;
+            for (const std::string& pk : order) {
+                const std::vector<int64_t>& rows = groups[pk];
+                const int64_t ng = static_cast<int64_t>(rows.size());
+                std::vector<double> Xg(static_cast<size_t>(ng) * P.d), Pg, o_mu(static_cast<size_t>(ng) * k), o_nu(o_mu.size()),
+                    o_be(o_mu.size()), o_ga(o_mu.size()), o_phi(PHI ? static_cast<size_t>(ng) * P.m : 0);
+                for (int a = 0; a < P.d; ++a)
+                    for (int64_t r = 0; r < ng; ++r) Xg[static_cast<size_t>(a) * ng + r] = Xz[static_cast<int64_t>(a) * n + rows[r]];
+                if (Psi) {
+                    Pg.resize(static_cast<size_t>(ng) * P.d);
+                    for (int a = 0; a < P.d; ++a)
+                        for (int64_t r = 0; r < ng; ++r) Pg[static_cast<size_t>(a) * ng + r] = Psi[static_cast<int64_t>(a) * n + rows[r]];
+                }
+                bool full = true;
+                std::vector<unsigned char> ob(static_cast<size_t>(P.d));
+                for (int a = 0; a < P.d; ++a) {
+                    ob[a] = pk[a] == '1';
+                    full = full && ob[a];
+                }
+                if (full)
+                    rc = gpz_predict(model, theta, w, iSigma_w, ng, Xg.data(), Psi ? Pg.data() : nullptr, priors, o_mu.data(), o_nu.data(),
+                                     o_be.data(), o_ga.data(), PHI ? o_phi.data() : nullptr, device);
+                else
+                    rc = predict_missing_group(model, theta, w, iSigma_w, ng, Xg.data(), Psi ? Pg.data() : nullptr, priors, ob, o_mu.data(),
+                                               o_nu.data(), o_be.data(), o_ga.data(), PHI ? o_phi.data() : nullptr, device);
+                if (rc) return rc;
+                for (int o = 0; o < k; ++o)
+                    for (int64_t r = 0; r < ng; ++r) {
+                        mu[o * n + rows[r]] = o_mu[o * ng + r];
+                        nu[o * n + rows[r]] = o_nu[o * ng + r];
+                        beta_i[o * n + rows[r]] = o_be[o * ng + r];
+                        gamma[o * n + rows[r]] = o_ga[o * ng + r];
+                    }
+                if (PHI)
+                    for (int j = 0; j < P.m; ++j)
+                        for (int64_t r = 0; r < ng; ++r) PHI[static_cast<int64_t>(j) * n + rows[r]] = o_phi[static_cast<size_t>(j) * ng + r];
+            }
+            return GPZ_OK;
+        }
+    }
     if (Psi && mode_is_cov(P.mode)) {
         set_error("predictNoisy for covariance modes (predictCov.m:70-133) is not supported yet");
         return GPZ_ERR_USAGE;
@@ -1552,15 +1689,6 @@ int gpz_predict(const gpz_model* model, const double* theta, const double* w, co
     if (!Psi) {
         PR(dev_alloc(allocs, &R.F, n * P.QP));
         PR(build_features(P, d_X, n, 0, n, R.F, st, &launches));
-    }
-    {
-        bool has_nan = false;
-        for (int64_t i = 0; i < n * P.d && !has_nan; ++i) has_nan = Xz[i] != Xz[i];
-        if (has_nan) {
-            set_error("gpz_predict: rows with missing inputs (predictMissing, predictDiag.m:127-295) are not supported yet");
-            cleanup();
-            return GPZ_ERR_USAGE;
-        }
     }
     for (int64_t r0 = 0; r0 < n; r0 += chunk) {
         const int64_t r1 = (r0 + chunk < n) ? r0 + chunk : n;

@@ -5,6 +5,8 @@
 // A pair table (C_ij, c_ij, lnZ_ij and the three weights) is built once per call; the row kernel
 // keeps x_i, Psi_i in registers/local memory and streams the table through L1 (every thread of a CTA
 // reads the same pair, so the loads are broadcasts).
+#include <vector>
+
 #include "internal.cuh"
 
 namespace gpz {
@@ -139,6 +141,256 @@ int predict_noisy_diag(const Params& P, const RowData& R, const double* w, const
         return GPZ_ERR_CUDA;
     }
     return GPZ_OK;
+}
+
+}  // namespace gpz
+
+// ================================================================================================
+// predictMissing / predictNoisyMissing for the diagonal modes (GPz/predictDiag.m:127-295): rows of ONE
+// missing-input pattern (observed set o, missing u).  Expected basis under the mixture prior over bases,
+// then the basis-pair sum with the missing dims integrated out analytically.
+//   No_il   = N(x_o; p_l(o), Sigma_l(o) [+Psi_i])              Pio = No .* prior / rowsum      (:145-155)
+//   Nmat_lj = N(p_l(u); p_j(u), Sigma_l(u)+Sigma_j(u))         PHI = No .* (Pio Nmat') e^{lnz} (:161-164)
+//   pair (a>=b): C, c (:177-178), NU_l = N(p_l(u); c(u), Sigma_l(u)+C(u)) (:183-184), Q = Pio NU (GEMM),
+//   Z = e^{lnZ_ab} N(x_o; c(o), C(o)[+Psi_i]) Q_i,ab           gamma, VlnS, nu += f Z {w w, v v, iSigma}  (:186-199)
+// ================================================================================================
+namespace gpz {
+
+__global__ void __launch_bounds__(128)
+pm_no_kernel(Params P, const double* __restrict__ X, const double* __restrict__ Psi, int64_t n, const unsigned char* __restrict__ ob,
+             const double* __restrict__ prior, double* __restrict__ No, double* __restrict__ Pio) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int d = P.d, m = P.m, MP = P.MP;
+    double ey = 0.0;
+    for (int l = 0; l < MP; ++l) {
+        double val = 0.0;
+        if (l < m) {
+            double q = 0.0, lp = 0.0;
+            for (int a = 0; a < d; ++a) {
+                if (!ob[a]) continue;
+                const double g = P.Gt[a * MP + l];
+                const double s = 1.0 / (g * g) + (Psi ? Psi[a * n + i] : 0.0);
+                const double dl = X[a * n + i] - P.Pt[a * MP + l];
+                q += dl * dl / s;
+                lp += log(s);
+            }
+            val = exp(-0.5 * q - 0.5 * lp);
+        }
+        No[i * MP + l] = val;
+        const double ex = val * (l < m ? prior[l] : 0.0);
+        Pio[i * MP + l] = ex;
+        ey += ex;
+    }
+    for (int l = 0; l < MP; ++l) Pio[i * MP + l] /= ey;
+}
+
+__global__ void __launch_bounds__(128)
+pm_nmat_kernel(Params P, const unsigned char* __restrict__ ob, double* __restrict__ Nmat) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    const int d = P.d, m = P.m, MP = P.MP;
+    if (l >= MP) return;
+    double val = 0.0;
+    if (l < m && j < m) {
+        double q = 0.0, lp = 0.0;
+        for (int a = 0; a < d; ++a) {
+            if (ob[a]) continue;
+            const double gl = P.Gt[a * MP + l], gj = P.Gt[a * MP + j];
+            const double s = 1.0 / (gl * gl) + 1.0 / (gj * gj);
+            const double dl = P.Pt[a * MP + l] - P.Pt[a * MP + j];
+            q += dl * dl / s;
+            lp += log(s);
+        }
+        val = exp(-0.5 * q - 0.5 * lp);
+    }
+    Nmat[static_cast<int64_t>(j) * MP + l] = val;
+}
+
+// PHI = No .* T .* e^{lnz}  (T = Pio Nmat')
+__global__ void pm_phi_kernel(Params P, int64_t n, const double* __restrict__ No, const double* __restrict__ T, double* __restrict__ Phi) {
+    const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int MP = P.MP;
+    if (e >= n * MP) return;
+    const int l = static_cast<int>(e % MP);
+    double v = 0.0;
+    if (l < P.m) {
+        double lnz = 0.0;
+        for (int a = 0; a < P.d; ++a) lnz -= log(fabs(P.Gt[a * MP + l]));
+        v = No[e] * T[e] * exp(lnz);
+    }
+    Phi[e] = v;
+}
+
+struct MPairTab {
+    int64_t npairs;
+    double* C;      // [d][npairs]
+    double* c;      // [d][npairs]
+    double* cst;    // [npairs]
+    double* ww;     // [k][npairs]
+    double* vv;
+    double* ss;
+    double* NU;     // [MP][npairs]  (row l, column pair)
+};
+
+__global__ void __launch_bounds__(128)
+pm_pairs_kernel(Params P, const unsigned char* __restrict__ ob, const double* __restrict__ w, const double* __restrict__ Sinv,
+                MPairTab T) {
+    const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (q >= T.npairs) return;
+    int64_t i = static_cast<int64_t>((sqrt(8.0 * static_cast<double>(q) + 1.0) - 1.0) * 0.5);
+    while ((i + 1) * (i + 2) / 2 <= q) ++i;
+    while (i * (i + 1) / 2 > q) --i;
+    const int64_t j = q - i * (i + 1) / 2;
+    const int d = P.d, m = P.m, MP = P.MP;
+    double lz = 0.0;
+    for (int a = 0; a < d; ++a) {
+        const double gi = P.Gt[a * MP + i], gj = P.Gt[a * MP + j];
+        const double isi = gi * gi, isj = gj * gj, si = 1.0 / isi, sj = 1.0 / isj;
+        const double C = 1.0 / (isi + isj);
+        T.C[a * T.npairs + q] = C;
+        T.c[a * T.npairs + q] = (P.Pt[a * MP + i] * isi + P.Pt[a * MP + j] * isj) * C;
+        const double dl = P.Pt[a * MP + i] - P.Pt[a * MP + j];
+        lz += -0.5 * log(isi) - 0.5 * log(isj) - 0.5 * dl * dl / (si + sj) - 0.5 * log(si + sj);
+    }
+    T.cst[q] = lz;
+    const double f = (i == j) ? 1.0 : 2.0;
+    for (int o = 0; o < P.k; ++o) {
+        T.ww[o * T.npairs + q] = f * w[o * MP + i] * w[o * MP + j];
+        T.vv[o * T.npairs + q] = f * P.v[o * MP + i] * P.v[o * MP + j];
+        T.ss[o * T.npairs + q] = f * Sinv[(static_cast<int64_t>(o) * MP + i) * MP + j];
+    }
+    for (int l = 0; l < MP; ++l) {
+        double val = 0.0;
+        if (l < m) {
+            double qd = 0.0, lp = 0.0;
+            for (int a = 0; a < d; ++a) {
+                if (ob[a]) continue;
+                const double g = P.Gt[a * MP + l];
+                const double s = 1.0 / (g * g) + T.C[a * T.npairs + q];
+                const double dl = P.Pt[a * MP + l] - T.c[a * T.npairs + q];
+                qd += dl * dl / s;
+                lp += log(s);
+            }
+            val = exp(-0.5 * qd - 0.5 * lp);
+        }
+        T.NU[static_cast<int64_t>(l) * T.npairs + q] = val;
+    }
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(128)
+pm_rows_kernel(Params P, const double* __restrict__ X, const double* __restrict__ Psi, int64_t n, int64_t r0, int64_t r1,
+               const unsigned char* __restrict__ ob, MPairTab T, const double* __restrict__ Q /*[rows][npairs]*/,
+               const double* __restrict__ elns0 /*[k][n] = PHI v*/, const double* __restrict__ mu, double* __restrict__ nu,
+               double* __restrict__ beta_i, double* __restrict__ gamma) {
+    const int64_t i = r0 + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= r1) return;
+    const int d = P.d, k = P.k;
+    double g[KMAX], vl[KMAX], nv[KMAX];
+#pragma unroll
+    for (int o = 0; o < KMAX; ++o) g[o] = vl[o] = nv[o] = 0.0;
+    const double* Qi = Q + (i - r0) * T.npairs;
+    for (int64_t q = 0; q < T.npairs; ++q) {
+        double quad = 0.0, lp = 0.0;
+        for (int a = 0; a < d; ++a) {
+            if (!ob[a]) continue;
+            const double cp = __ldg(T.C + a * T.npairs + q) + (Psi ? Psi[a * n + i] : 0.0);
+            const double dl = X[a * n + i] - __ldg(T.c + a * T.npairs + q);
+            quad += dl * dl / cp;
+            lp += log(cp);
+        }
+        const double Z = exp(__ldg(T.cst + q) - 0.5 * quad - 0.5 * lp) * Qi[q];
+#pragma unroll
+        for (int o = 0; o < KMAX; ++o) {
+            if (o < k) {
+                g[o] = fma(Z, __ldg(T.ww + o * T.npairs + q), g[o]);
+                vl[o] = fma(Z, __ldg(T.vv + o * T.npairs + q), vl[o]);
+                nv[o] = fma(Z, __ldg(T.ss + o * T.npairs + q), nv[o]);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < KMAX; ++o) {
+        if (o < k) {
+            const double e0 = elns0[o * n + i];
+            const double m_ = mu[o * n + i];
+            const double V = vl[o] - e0 * e0;                              // predictDiag.m:204
+            gamma[o * n + i] = g[o] - m_ * m_;                             // :210
+            beta_i[o * n + i] = exp(e0 + P.bk[o]) * (1.0 + 0.5 * V);       // :206-208
+            nu[o * n + i] = nv[o];
+        }
+    }
+}
+
+// X, Psi: [d][n] device (shifted like P.Pt); ob: [d] device; prior: [MP] device; outputs [k][n] device, Phi [n][MP] device
+int predict_missing_diag(const Params& P, const double* X, const double* Psi, int64_t n, const unsigned char* ob,
+                         const double* prior, const double* w, const double* Sinv, double* mu, double* nu, double* beta_i,
+                         double* gamma, double* Phi, cudaStream_t st, int64_t* launches) {
+    if (P.k > 4) {
+        set_error("predictMissing: k > 4 outputs not supported");
+        return GPZ_ERR_USAGE;
+    }
+    const int64_t MP = P.MP;
+    const int64_t npairs = static_cast<int64_t>(P.m) * (P.m + 1) / 2;
+    int64_t chunk = static_cast<int64_t>(1.0e9 / (8.0 * static_cast<double>(npairs)));
+    if (chunk < 1) chunk = 1;
+    if (chunk > n) chunk = n;
+    double *No = nullptr, *Pio = nullptr, *Nmat = nullptr, *Tm = nullptr, *tab = nullptr, *Q = nullptr, *elns0 = nullptr;
+    std::vector<double*> bufs;
+    auto A = [&](double** p, int64_t cnt) {
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), sizeof(double) * static_cast<size_t>(cnt > 0 ? cnt : 1));
+        if (e != cudaSuccess) {
+            set_error("predict_missing_diag: cudaMalloc: %s", cudaGetErrorString(e));
+            return static_cast<int>(GPZ_ERR_CUDA);
+        }
+        bufs.push_back(*p);
+        return static_cast<int>(GPZ_OK);
+    };
+    auto done = [&](int rc) {
+        cudaStreamSynchronize(st);
+        for (double* b : bufs) cudaFree(b);
+        return rc;
+    };
+    int rc;
+    const int64_t per = 2LL * P.d + 1 + 3LL * P.k + MP;
+    if ((rc = A(&No, n * MP)) || (rc = A(&Pio, n * MP)) || (rc = A(&Nmat, MP * MP)) || (rc = A(&Tm, n * MP)) ||
+        (rc = A(&tab, per * npairs)) || (rc = A(&Q, chunk * npairs)) || (rc = A(&elns0, P.k * n)))
+        return done(rc);
+    MPairTab T;
+    T.npairs = npairs;
+    T.C = tab;
+    T.c = T.C + static_cast<int64_t>(P.d) * npairs;
+    T.cst = T.c + static_cast<int64_t>(P.d) * npairs;
+    T.ww = T.cst + npairs;
+    T.vv = T.ww + static_cast<int64_t>(P.k) * npairs;
+    T.ss = T.vv + static_cast<int64_t>(P.k) * npairs;
+    T.NU = T.ss + static_cast<int64_t>(P.k) * npairs;
+    pm_no_kernel<<<static_cast<unsigned>(ceil_div(n, 128)), 128, 0, st>>>(P, X, Psi, n, ob, prior, No, Pio);
+    pm_nmat_kernel<<<dim3(static_cast<unsigned>(MP / 128), static_cast<unsigned>(MP)), 128, 0, st>>>(P, ob, Nmat);
+    *launches += 2;
+    // T = Pio * Nmat'   (B(k=j, col=l) = Nmat[l][j]; Nmat is stored [j][l] so B(k,col) = Nmat_store[k*MP + col] transposed twice = symmetric)
+    if ((rc = sgemm(static_cast<int>(n), P.m, P.m, 1.0, Pio, MP, 1, Nmat, MP, 1, 0.0, Tm, MP, 0, st, launches))) return done(rc);
+    pm_phi_kernel<<<static_cast<unsigned>(ceil_div(n * MP, 256)), 256, 0, st>>>(P, n, No, Tm, Phi);
+    ++*launches;
+    for (int o = 0; o < P.k; ++o)
+        if ((rc = rowdot(Phi, MP, P.m, n, DotSpec{2, {w + o * MP, P.v + o * MP}, {mu + o * n, elns0 + o * n}}, st, launches))) return done(rc);
+    pm_pairs_kernel<<<static_cast<unsigned>(ceil_div(npairs, 128)), 128, 0, st>>>(P, ob, w, Sinv, T);
+    ++*launches;
+    for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+        const int64_t r1 = (r0 + chunk < n) ? r0 + chunk : n;
+        // Q(rows x npairs) = Pio[rows] (rows x m) * NU (m x npairs)
+        if ((rc = sgemm(static_cast<int>(r1 - r0), static_cast<int>(npairs), P.m, 1.0, Pio + r0 * MP, MP, 1, T.NU, npairs, 1, 0.0, Q,
+                        npairs, 0, st, launches))) return done(rc);
+        pm_rows_kernel<4><<<static_cast<unsigned>(ceil_div(r1 - r0, 128)), 128, 0, st>>>(P, X, Psi, n, r0, r1, ob, T, Q, elns0, mu, nu,
+                                                                                        beta_i, gamma);
+        ++*launches;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("predict_missing_diag: %s", cudaGetErrorString(e));
+        return done(GPZ_ERR_CUDA);
+    }
+    return done(GPZ_OK);
 }
 
 }  // namespace gpz

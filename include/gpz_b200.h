@@ -100,13 +100,15 @@ int gpz_phi(gpz_ctx* ctx, const double* theta, int which, double* PHI, double* l
 int gpz_get_prior(gpz_ctx* ctx, const double* theta, double* prior);
 int64_t gpz_rows(const gpz_ctx* ctx, int which);
 
-/* ---- predict core (GPz/predict.m:60-73 dispatch; predictDiag.m:58-125, predictCov.m:53-69) -------
- * Xz n x d z-scored rows without NaN; Psi NULL (predictFull) or n x d fixPsi-normalised
- * (predictNoisy, methods ?L/?D).  theta/w/iSigma_w as stored in model.best / model.last.
+/* ---- predict core (GPz/predict.m:45-73 grouping + dispatch; predictDiag.m:58-295, predictCov.m:53-69) ---
+ * Xz n x d z-scored rows (NaN = missing); Psi NULL or n x d fixPsi-normalised (methods ?L/?D).
+ * Complete rows: predictFull (all methods) / predictNoisy (?L/?D).  Rows with NaN: predictMissing /
+ * predictNoisyMissing (?L/?D only), which need priors (m doubles, model.best.priors; may be NULL otherwise).
+ * theta/w/iSigma_w as stored in model.best / model.last.
  * Outputs n x k each: mu (WITHOUT muY), nu, beta_i, gamma; PHI n x m (may be NULL).
  * sigma = nu + beta_i + gamma and mu += muY stay on the host (predict.m:72-73).                  */
 int gpz_predict(const gpz_model* model, const double* theta, const double* w, const double* iSigma_w,
-                int64_t n, const double* Xz, const double* Psi,
+                int64_t n, const double* Xz, const double* Psi, const double* priors,
                 double* mu, double* nu, double* beta_i, double* gamma, double* PHI, int device);
 
 /* ---- [Xi,logdet] = inv_logdet(X)  (GPz/inv_logdet.m:1-15) for SPD X (blocked Cholesky) ----------- */

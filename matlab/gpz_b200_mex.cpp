@@ -11,7 +11,7 @@
 //     [nl, w, iSigma_w] = gpz_b200_mex('fit', h, theta)
 //     [PHI, lnBeta_i, N] = gpz_b200_mex('phi', h, theta, which, model)
 //     prior = gpz_b200_mex('get_prior', h, theta, model)
-//     [mu, nu, beta_i, gamma, PHI] = gpz_b200_mex('predict', model, theta, w, iSigma_w, Xz, Psi)
+//     [mu, nu, beta_i, gamma, PHI] = gpz_b200_mex('predict', model, theta, w, iSigma_w, Xz, Psi, priors)
 //     [Xi, logdet] = gpz_b200_mex('inv_logdet', X)
 //     D = gpz_b200_mex('dxy', X, Y)
 //     gpz_b200_mex('destroy', h)
@@ -149,8 +149,8 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         for (int i = 0; i < 4; ++i) out[i] = mxCreateDoubleMatrix(n, m.k, mxREAL);
         out[4] = mxCreateDoubleMatrix(n, m.m, mxREAL);
         if (gpz_predict(&m, mxGetPr(prhs[2]), mxGetPr(prhs[3]), mxGetPr(prhs[4]), static_cast<int64_t>(n), mxGetPr(prhs[5]),
-                        nrhs > 6 ? opt_double(prhs[6]) : nullptr, mxGetPr(out[0]), mxGetPr(out[1]), mxGetPr(out[2]), mxGetPr(out[3]),
-                        mxGetPr(out[4]), 0))
+                        nrhs > 6 ? opt_double(prhs[6]) : nullptr, nrhs > 7 ? opt_double(prhs[7]) : nullptr, mxGetPr(out[0]),
+                        mxGetPr(out[1]), mxGetPr(out[2]), mxGetPr(out[3]), mxGetPr(out[4]), 0))
             fail("gpz_predict");
         for (int i = 0; i < 5; ++i) {
             if (i < nlhs || i == 0) plhs[i] = out[i]; else mxDestroyArray(out[i]);

@@ -1,7 +1,7 @@
 function [mu,sigma,nu,beta_i,gamma,PHI,w,iSigma_w] = predict(X,model,varargin)
 % Drop-in for GPz/predict.m:1-75: host-side selection / z-scoring / fixPsi as in the reference, the
-% per-row work (predictFull, predictNoisy for the diagonal modes) on the GPU.  Rows with missing values
-% (predictMissing*, predictDiag.m:127-295) are not supported yet and raise an error.
+% per-row work on the GPU: predictFull (all methods), predictNoisy / predictMissing / predictNoisyMissing for the
+% diagonal methods (predictDiag.m:58-295).  Missing values with a covariance method raise an error.
 pnames = {'whichSet' 'Psi' 'selection'};
 defaults = {'best' [] true(size(X,1),1)};
 [whichSet,Psi,selection] = internal.stats.parseArgs(pnames,defaults,varargin{:});
@@ -14,7 +14,7 @@ end
 X = bsxfun(@rdivide,bsxfun(@minus,X,model.muX),model.sdX);
 Psi = fixPsi(Psi,n,model.sdX,model.method);
 w = set.w; iSigma_w = set.iSigma_w;
-[mu,nu,beta_i,gamma,PHI] = gpz_b200_mex('predict',model,set.theta,w,iSigma_w,X,Psi);
+[mu,nu,beta_i,gamma,PHI] = gpz_b200_mex('predict',model,set.theta,w,iSigma_w,X,Psi,set.priors);
 sigma = nu+beta_i+gamma;
 mu = bsxfun(@plus,mu,model.muY);
 end

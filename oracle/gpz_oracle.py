@@ -516,10 +516,70 @@ def _predictNoisyCov(X, Psi, Gamma, w, v, b, P, iSigma_w, theta, model):
     return mu, nu, beta_i, gamma, PHI
 
 
+def _predictMissingDiag(X, Psi, Gamma, w, v, b, P, iSigma_w, priors):
+    """predictMissing (Psi is None, predictDiag.m:127-212) and predictNoisyMissing (predictDiag.m:213-295) for one
+    group of rows sharing a NaN pattern.  The two reference functions differ only in Psi being added to the
+    variances of the observed dims (:230-232, :262-264)."""
+    o = ~np.isnan(X[0, :])
+    u = ~o
+    n = X.shape[0]
+    m, k = w.shape
+    iSigma = Gamma ** 2
+    Sigma = Gamma ** -2.0
+    lnz = -0.5 * np.sum(np.log(iSigma), axis=1)                         # :141 (== +0.5*sum(log(Sigma)), :224)
+    Ps = np.zeros((n, int(o.sum()))) if Psi is None else Psi[:, o]
+    No = np.zeros((n, m))
+    Ex = np.zeros((n, m))
+    for i in range(m):                                                  # :145-151 / :228-235
+        Delta = X[:, o] - P[i, o][None, :]
+        SpP = Ps + Sigma[i, o][None, :]
+        No[:, i] = np.exp(-0.5 * np.sum(Delta ** 2 / SpP, axis=1) - 0.5 * np.sum(np.log(SpP), axis=1))
+        Ex[:, i] = No[:, i] * priors.reshape(-1)[i]
+    Pio = Ex / np.sum(Ex, axis=1, keepdims=True)                        # :153-155
+    ii = np.arange(m * m) % m                                           # :157-158
+    jj = np.arange(m * m) // m
+    Nij = np.exp(-0.5 * np.sum((P[ii][:, u] - P[jj][:, u]) ** 2 / (Sigma[ii][:, u] + Sigma[jj][:, u]), axis=1)
+                 - 0.5 * np.sum(np.log(Sigma[ii][:, u] + Sigma[jj][:, u]), axis=1))          # :161
+    Nmat = Nij.reshape((m, m), order="F")                               # Nmat[i, j]
+    PHI = No * (Pio @ Nmat.T)                                           # :163  sum_j No(:,i) Pio(:,j) Nij(i,j)
+    PHI = PHI * np.exp(lnz)[None, :]                                    # :164
+    mu = PHI @ w
+    ElnS = PHI @ v
+    gamma = np.zeros((n, k))
+    nu = np.zeros((n, k))
+    VlnS = np.zeros((n, k))
+    for i in range(m):                                                  # :173
+        Z = None
+        for j in range(i + 1):
+            Cij = 1.0 / (iSigma[i, :] + iSigma[j, :])
+            cij = (P[i, :] * iSigma[i, :] + P[j, :] * iSigma[j, :]) * Cij
+            Delta = X[:, o] - cij[o][None, :]
+            CpP = Ps + Cij[o][None, :]
+            No_p = np.exp(-0.5 * np.sum(Delta ** 2 / CpP, axis=1) - 0.5 * np.sum(np.log(CpP), axis=1))   # :180 / :263
+            Dl = P[:, u] - cij[u][None, :]
+            CpS = Sigma[:, u] + Cij[u][None, :]
+            Nu = np.exp(-0.5 * np.sum(Dl ** 2 / CpS, axis=1) - 0.5 * np.sum(np.log(CpS), axis=1))          # :184
+            EcCij = np.sum(np.outer(No_p, Nu) * Pio, axis=1)            # :186-187
+            Dp = P[i, :] - P[j, :]
+            Z = (np.exp(lnz[i] + lnz[j] - 0.5 * np.sum(Dp ** 2 / (Sigma[i, :] + Sigma[j, :]))
+                        - 0.5 * np.sum(np.log(Sigma[i, :] + Sigma[j, :]))) * EcCij)[:, None]               # :190
+            gamma += 2.0 * Z * (w[i, :] * w[j, :])[None, :]
+            VlnS += 2.0 * Z * (v[i, :] * v[j, :])[None, :]
+            nu += 2.0 * Z * iSigma_w[i, j, :][None, :]
+        gamma -= Z * (w[i, :] * w[i, :])[None, :]                       # :197-199
+        VlnS -= Z * (v[i, :] * v[i, :])[None, :]
+        nu -= Z * iSigma_w[i, i, :][None, :]
+    VlnS = VlnS - ElnS ** 2                                             # :204
+    ElnS = ElnS + b.reshape(1, k)                                       # :206
+    beta_i = np.exp(ElnS) * (1.0 + 0.5 * VlnS)                          # :208
+    gamma = gamma - mu ** 2                                             # :210
+    return mu, nu, beta_i, gamma, PHI
+
+
 def predict(X, model: Model, which="best", Psi=None, selection=None):
-    """predict.m:1-75 for rows with no missing values (Full / Noisy sub-paths).  Rows with NaN
-    take predictMissing / predictNoisyMissing in the reference and are
-    rejected here."""
+    """predict.m:1-75: rows grouped by NaN pattern; Full / Noisy for complete rows (both mode families),
+    Missing / NoisyMissing for the diagonal modes (predictDiag.m:127-295).  Missing rows with a covariance
+    mode (predictCov.m:134-336) are not restated."""
     st = model.best if which == "best" else model.last
     n_all = X.shape[0]
     if selection is None:
@@ -538,18 +598,26 @@ def predict(X, model: Model, which="best", Psi=None, selection=None):
     Xz = (X - model.muX[None, :]) / model.sdX[None, :]                  # :35-36
     theta, w, iSigma_w, P = st["theta"], st["w"], st["iSigma_w"], st["P"]
     Psi = fixPsi(Psi, n, model.sdX, meth)                               # :43
-    if np.isnan(Xz).any():
-        raise NotImplementedError("predictMissing/predictNoisyMissing: SURVEY 8(f) rank 2")
     v = st["v"] if model.heteroscedastic else np.zeros((m, k))
     Gamma = unpack_gamma(theta, model)
     off = m * d + model.g_dim + m * k
     b = theta[off:off + k]
-    if Psi is None:
-        mu, nu, beta_i, gamma, PHI = _predictFull(Xz, theta, w, iSigma_w, model)
-    elif meth[1] == "C":
-        mu, nu, beta_i, gamma, PHI = _predictNoisyCov(Xz, Psi, Gamma, w, v, b, P, iSigma_w, theta, model)
-    else:
-        mu, nu, beta_i, gamma, PHI = _predictNoisyDiag(Xz, Psi, Gamma, w, v, b, P, iSigma_w, theta, model)
+    mu, nu, beta_i, gamma = (np.zeros((n, k)) for _ in range(4))
+    PHI = np.zeros((n, m))
+    for grp in nan_groups(np.isnan(Xz)):                                # predict.m:45-69
+        Xg = Xz[grp]
+        full = not np.isnan(Xg[0]).any()
+        if full and Psi is None:
+            r = _predictFull(Xg, theta, w, iSigma_w, model)
+        elif full and meth[1] == "C":
+            r = _predictNoisyCov(Xg, Psi[:, :, grp], Gamma, w, v, b, P, iSigma_w, theta, model)
+        elif full:
+            r = _predictNoisyDiag(Xg, Psi[grp], Gamma, w, v, b, P, iSigma_w, theta, model)
+        elif meth[1] == "C":
+            raise NotImplementedError("predictMissing for covariance modes (predictCov.m:134-336): SURVEY 8(f)")
+        else:
+            r = _predictMissingDiag(Xg, None if Psi is None else Psi[grp], Gamma, w, v, b, P, iSigma_w, st["priors"])
+        mu[grp], nu[grp], beta_i[grp], gamma[grp], PHI[grp] = r
     sigma = nu + beta_i + gamma                                         # :72
     mu = mu + model.muY.reshape(1, k)                                   # :73
     return mu, sigma, nu, beta_i, gamma, PHI

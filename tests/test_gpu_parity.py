@@ -255,3 +255,29 @@ def test_densities_and_get_prior(method, psi, nan):
     pr = O.getPrior(X, Psi, theta, model, tr)
     assert abs(prior.sum() - 1.0) <= 1e-12 and rel(prior, pr.reshape(-1)) <= 1e-8
     ctx.close()
+
+
+@pytest.mark.parametrize("method,psi", [("VD", False), ("VD", True), ("GL", False), ("VL", True), ("GD", False)])
+def test_predict_with_missing_inputs(method, psi):
+    """predict.m:45-69 grouping; predictMissing / predictNoisyMissing (predictDiag.m:127-295) with priors from getPrior."""
+    n, d, m = 300, 3, 9
+    model, theta, X, Y, _, omega, tr, _ = problem(method, True, False, False, n=n, d=d, m=m, seed=23)
+    r = O.GPz(theta, model, X, Y, None, omega, tr, None, fit_only=True)
+    pri = O.getPrior(X, None, theta, model, tr)
+    model.muX, model.sdX, model.muY = np.zeros(d), np.ones(d), np.zeros(1)
+    o2 = m * d + model.g_dim + m + 1
+    model.best = dict(theta=theta, w=r.w, iSigma_w=r.iSigma_w, P=theta[:m * d].reshape((m, d), order="F"),
+                      v=theta[o2:o2 + m].reshape(m, 1), priors=pri)
+    Xt = X[:60].copy()
+    Xt[5:25, 1] = np.nan
+    Xt[15:40, 2] = np.nan
+    Xt[50:55, 0] = np.nan
+    Psi = synth.make_psi(60, d, method, seed=4) if psi else None
+    mu, sigma, nu, be, ga, PHI = O.predict(Xt, model, Psi=Psi)
+    gm = L.make_model(d, 1, m, method, True)
+    mu2, nu2, be2, ga2, PHI2 = L.predict_core(gm, theta, r.w, r.iSigma_w, Xt, Psi, want_phi=True, priors=pri)
+    assert rel(mu2, mu) <= TOL and rel(PHI2, PHI) <= 1e-10
+    assert rel(nu2, nu) <= 1e-8 and rel(be2, be) <= 1e-8
+    assert np.max(np.abs(ga2 - ga)) <= 1e-9 * max(1.0, np.max(np.abs(mu)) ** 2)
+    with pytest.raises(L.GpzError):
+        L.predict_core(gm, theta, r.w, r.iSigma_w, Xt, Psi)          # missing rows without priors: loud failure
