@@ -445,6 +445,9 @@ struct gpz_ctx {
     int opt_tensor_phi = 1;         // 1: PHI = exp(F W) on the DMMA pipe; 0: direct-difference kernels
     int opt_fused_bp = 1;           // 1: fused dPHI + back-projection GEMM; 0: materialise dPHI first
     int opt_aug = 1;                // 1: spare-column trick (see aug)
+    int opt_ozaki = 0;              // >0: T-GEMM through the int8 tensor cores with this many 7-bit slices (ozaki.cu)
+    void* oz_ws = nullptr;
+    int64_t oz_chunk = 0;
     std::vector<double> h_shift;    // constant subtracted from X at upload
     double* Wc_alloc = nullptr;
     double* dot_scratch = nullptr;
@@ -773,6 +776,16 @@ int ensure_workspace(gpz_ctx* c) {
         const int64_t sc = 2 * dd * MP + dd * P.m + static_cast<int64_t>(P.m) * P.d + 64;
         if ((rc = A(&c->scratch, sc))) return rc;
     }
+    if (c->opt_ozaki > 0) {
+        if (!i8gemm_available()) {
+            set_error("ozaki_slices: this build has no tcgen05 int8 GEMM (CUTLASS headers were not found at build time)");
+            return GPZ_ERR_USAGE;
+        }
+        c->oz_chunk = nn < 262144 ? nn : 262144;
+        double* tmp = nullptr;
+        if ((rc = A(&tmp, oz_workspace_bytes(static_cast<int>(MP), c->opt_ozaki, c->oz_chunk) / 8 + 1))) return rc;
+        c->oz_ws = tmp;
+    }
     if ((rc = solve_ws_alloc(c->sws, static_cast<int>(MP)))) return rc;
     for (auto& e : c->ev) GPZ_CUDA(cudaEventCreate(&e));
     for (auto& e : c->kev) GPZ_CUDA(cudaEventCreate(&e));
@@ -927,12 +940,18 @@ int eval_device(gpz_ctx* c, const double* d_theta, double* d_out) {
         for (int o = 0; o < k; ++o) {
             const bool timed = (nchunks == 0 && o == 0);
             if (timed) GPZ_CUDA(cudaEventRecord(c->kev[2], st));
-            if ((rc = tgemm(phi, MP, c->Sinv + static_cast<int64_t>(o) * MP * MP, static_cast<int>(MP), P.m, rows, c->ob + o * n + r0,
-                            c->H, o > 0, c->nupart + r0, n, c->aug ? c->pred + r0 : nullptr, st, &c->launches))) return rc;
+            if (c->opt_ozaki > 0) {
+                if ((rc = ozaki_tgemm(phi, MP, c->Sinv + static_cast<int64_t>(o) * MP * MP, static_cast<int>(MP), P.m, rows, c->opt_ozaki,
+                                      c->oz_chunk, c->ob + o * n + r0, c->H, o > 0, c->nupart + r0, c->aug ? c->w + o * MP : nullptr,
+                                      c->aug ? c->pred + r0 : nullptr, c->oz_ws, st, &c->launches))) return rc;
+            } else {
+                if ((rc = tgemm(phi, MP, c->Sinv + static_cast<int64_t>(o) * MP * MP, static_cast<int>(MP), P.m, rows, c->ob + o * n + r0,
+                                c->H, o > 0, c->nupart + r0, n, c->aug ? c->pred + r0 : nullptr, st, &c->launches))) return rc;
+            }
             if (timed) GPZ_CUDA(cudaEventRecord(c->kev[3], st));
             rows2_kernel<<<static_cast<unsigned>(ceil_div(rows, RB)), RB, 0, st>>>(P, o, c->tr.Y, c->tr.omega, n, r0, r1, c->pred,
-                                                                                 c->nupart, ntn, c->lnbi, c->beta, c->ob, c->nu,
-                                                                                 c->cw, c->dbeta, c->part2, 2 * k + 2);
+                                                                                 c->nupart, c->opt_ozaki > 0 ? 1 : ntn, c->lnbi, c->beta,
+                                                                                 c->ob, c->nu, c->cw, c->dbeta, c->part2, 2 * k + 2);
             GPZ_KERNEL_CHECK();
             ++c->launches;
         }
@@ -1848,6 +1867,18 @@ int gpz_set_option(gpz_ctx* c, const char* name, double value) {
             return GPZ_ERR_USAGE;
         }
         if (name[0] == 't') c->opt_tensor_phi = value != 0.0; else c->opt_fused_bp = value != 0.0;
+        return GPZ_OK;
+    }
+    if (strcmp(name, "ozaki_slices") == 0) {
+        if (c->ws_ready) {
+            set_error("%s must be set before the first evaluation", name);
+            return GPZ_ERR_USAGE;
+        }
+        if (value != 0.0 && (value < 4.0 || value > 9.0)) {
+            set_error("ozaki_slices must be 0 (off) or 4..9");
+            return GPZ_ERR_USAGE;
+        }
+        c->opt_ozaki = static_cast<int>(value);
         return GPZ_OK;
     }
     if (strcmp(name, "spare_column") == 0) {

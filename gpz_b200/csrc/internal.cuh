@@ -134,4 +134,13 @@ int predict_missing_diag(const Params& P, const double* X, const double* Psi, in
                          const double* prior, const double* w, const double* Sinv, double* mu, double* nu, double* beta_i,
                          double* gamma, double* Phi, cudaStream_t st, int64_t* launches);
 
+// ---- i8gemm_cutlass.cu / ozaki.cu
+bool i8gemm_available();
+int i8gemm_tn(const int8_t* A, int64_t lda, const int8_t* B, int64_t ldb, int32_t* D, int64_t ldd, int M, int N, int K,
+              void* workspace, size_t ws_bytes, cudaStream_t st);
+int64_t oz_workspace_bytes(int MP, int s, int64_t chunk_rows);
+int ozaki_tgemm(const double* Phi, int64_t ld, const double* Sinv, int MP, int m, int64_t n, int s, int64_t chunk_rows,
+                const double* rw, double* H, int accumulate, double* nu, const double* waug, double* pred, void* ws,
+                cudaStream_t st, int64_t* launches);
+
 }  // namespace gpz

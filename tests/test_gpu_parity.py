@@ -281,3 +281,26 @@ def test_predict_with_missing_inputs(method, psi):
     assert np.max(np.abs(ga2 - ga)) <= 1e-9 * max(1.0, np.max(np.abs(mu)) ** 2)
     with pytest.raises(L.GpzError):
         L.predict_core(gm, theta, r.w, r.iSigma_w, Xt, Psi)          # missing rows without priors: loud failure
+
+
+@pytest.mark.parametrize("method,slices,tol", [("VC", 8, 1e-9), ("VD", 8, 1e-9), ("GL", 9, 1e-7), ("VC", 7, 1e-7)])
+def test_int8_tensor_core_tgemm_matches_fp64(method, slices, tol):
+    """T = PHI*iSigma as error-free int8 slice GEMMs on tcgen05 (ozaki.cu) against the fp64 DMMA path and the oracle."""
+    model, theta, X, Y, Psi, omega, tr, va = problem(method, True, False, False, n=3000, d=5, m=140, seed=21)
+    ref = O.GPz(theta, model, X, Y, None, omega, tr, va)
+    gm = L.make_model(model.d, 1, model.m, method, True)
+    res = {}
+    for oz in (0, slices):
+        ctx = L.Context(gm, X, Y, None, omega, tr, va)
+        ctx.set_option("ozaki_slices", oz)
+        res[oz] = ctx.eval(theta)
+        f2, g2, _ = ctx.eval(theta)
+        assert f2 == res[oz][0] and np.array_equal(g2, res[oz][1])
+        ctx.close()
+    assert_eval_matches(model, ref, *res[slices], tol=max(tol, 1e-7))
+    f0, g0, _ = res[0]
+    f1, g1, _ = res[slices]
+    assert abs(f1 - f0) <= 1e-12 * abs(f0)          # the objective value does not depend on T
+    gb0, gb1 = grad_blocks(model, g0), grad_blocks(model, g1)
+    for nm in gb0:
+        assert rel(gb1[nm], gb0[nm]) <= tol, (nm, rel(gb1[nm], gb0[nm]))
