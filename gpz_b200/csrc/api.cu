@@ -445,7 +445,8 @@ struct gpz_ctx {
     int opt_tensor_phi = 1;         // 1: PHI = exp(F W) on the DMMA pipe; 0: direct-difference kernels
     int opt_fused_bp = 1;           // 1: fused dPHI + back-projection GEMM; 0: materialise dPHI first
     int opt_aug = 1;                // 1: spare-column trick (see aug)
-    int opt_ozaki = 0;              // >0: T-GEMM through the int8 tensor cores with this many 7-bit slices (ozaki.cu)
+    int opt_ozaki = -1;             // >0: T-GEMM through the int8 tensor cores with this many 7-bit slices (ozaki.cu);
+                                    // -1: default = 8 when the tcgen05 int8 GEMM was built in, else 0 (fp64 DMMA)
     void* oz_ws = nullptr;
     int64_t oz_chunk = 0;
     std::vector<double> h_shift;    // constant subtracted from X at upload
@@ -776,6 +777,7 @@ int ensure_workspace(gpz_ctx* c) {
         const int64_t sc = 2 * dd * MP + dd * P.m + static_cast<int64_t>(P.m) * P.d + 64;
         if ((rc = A(&c->scratch, sc))) return rc;
     }
+    if (c->opt_ozaki < 0) c->opt_ozaki = i8gemm_available() ? 8 : 0;
     if (c->opt_ozaki > 0) {
         if (!i8gemm_available()) {
             set_error("ozaki_slices: this build has no tcgen05 int8 GEMM (CUTLASS headers were not found at build time)");
