@@ -293,6 +293,22 @@ __global__ void set_aug_col_kernel(double* __restrict__ Sinv, int MP, int m, con
     if (l < m) Sinv[static_cast<int64_t>(l) * MP + m] = w[l];
 }
 
+// out[0] = max_i |v_i|  (single CTA, order-independent)
+__global__ void __launch_bounds__(1024)
+max_abs_kernel(const double* __restrict__ v, int64_t n, double* __restrict__ out) {
+    __shared__ double sh[32];
+    double mx = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) mx = fmax(mx, fabs(v[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < 32; ++q) mx = fmax(mx, sh[q]);
+        out[0] = mx;
+    }
+}
+
 struct FinishArgs {
     Params P;
     const double* theta;
@@ -449,6 +465,11 @@ struct gpz_ctx {
                                     // -1: default = 8 when the tcgen05 int8 GEMM was built in, else 0 (fp64 DMMA)
     void* oz_ws = nullptr;
     int64_t oz_chunk = 0;
+    cudaStream_t aux = nullptr;     // second stream of the int8 T-GEMM pipeline
+    cudaEvent_t oz_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int opt_ozaki_gram = -1;        // Gram through the int8 tensor cores too (-1: follows ozaki_slices > 0, k == 1)
+    void* ozg_ws = nullptr;
+    double* d_scal = nullptr;       // [0] max row weight of this eval, [1] max |y| (constant)
     std::vector<double> h_shift;    // constant subtracted from X at upload
     double* Wc_alloc = nullptr;
     double* dot_scratch = nullptr;
@@ -783,10 +804,23 @@ int ensure_workspace(gpz_ctx* c) {
             set_error("ozaki_slices: this build has no tcgen05 int8 GEMM (CUTLASS headers were not found at build time)");
             return GPZ_ERR_USAGE;
         }
-        c->oz_chunk = nn < 262144 ? nn : 262144;
+        c->oz_chunk = nn < 131072 ? nn : 131072;
+        GPZ_CUDA(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
+        for (auto& e : c->oz_ev) GPZ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         double* tmp = nullptr;
         if ((rc = A(&tmp, oz_workspace_bytes(static_cast<int>(MP), c->opt_ozaki, c->oz_chunk) / 8 + 1))) return rc;
         c->oz_ws = tmp;
+    }
+    if (c->opt_ozaki_gram < 0) c->opt_ozaki_gram = (c->opt_ozaki > 0 && k == 1) ? 1 : 0;
+    if (c->opt_ozaki_gram > 0 && (c->opt_ozaki <= 0 || c->opt_ozaki > 8 || k != 1)) c->opt_ozaki_gram = 0;   // 9 slices: T-GEMM only
+    if ((rc = A(&c->d_scal, 8))) return rc;
+    if (c->opt_ozaki_gram > 0) {
+        double* tmp = nullptr;
+        const int64_t rows = n < c->chunk_rows ? (n > 0 ? n : 1) : c->chunk_rows;
+        if ((rc = A(&tmp, oz_gram_workspace_bytes(static_cast<int>(MP), c->opt_ozaki, rows) / 8 + 1))) return rc;
+        c->ozg_ws = tmp;
+        max_abs_kernel<<<1, 1024, 0, c->st>>>(c->tr.Y, n, c->d_scal + 1);
+        GPZ_KERNEL_CHECK();
     }
     if ((rc = solve_ws_alloc(c->sws, static_cast<int>(MP)))) return rc;
     for (auto& e : c->ev) GPZ_CUDA(cudaEventCreate(&e));
@@ -837,6 +871,17 @@ int forward_and_solve(gpz_ctx* c, const double* d_theta) {
             // rows of this chunk are [0, r1-r0) of phi; the weights are indexed by absolute row
             const bool timed = (nchunks == 0 && o == 0);
             if (timed) GPZ_CUDA(cudaEventRecord(c->kev[0], st));
+            if (c->opt_ozaki_gram > 0) {
+                if (nchunks == 0) {
+                    max_abs_kernel<<<1, 1024, 0, st>>>(c->ob, n, c->d_scal);     // max row weight over ALL rows of this rank
+                    GPZ_KERNEL_CHECK();
+                    ++c->launches;
+                }
+                if ((rc = ozaki_gram(phi, MP, static_cast<int>(MP), P.m, r1 - r0, c->opt_ozaki, c->ob + r0, c->d_scal, c->aug ? 1 : 0,
+                                     nchunks > 0, c->S, c->ozg_ws, st, &c->launches))) return rc;
+                if (timed) GPZ_CUDA(cudaEventRecord(c->kev[1], st));
+                continue;
+            }
             if ((rc = gram_syrk_main(phi, MP, static_cast<int>(MP), c->ob + o * n + r0, 0, r1 - r0, c->gram_ns,
                                      c->gram_partial, nchunks > 0, st, &c->launches))) return rc;
             if (timed) GPZ_CUDA(cudaEventRecord(c->kev[1], st));
@@ -945,7 +990,7 @@ int eval_device(gpz_ctx* c, const double* d_theta, double* d_out) {
             if (c->opt_ozaki > 0) {
                 if ((rc = ozaki_tgemm(phi, MP, c->Sinv + static_cast<int64_t>(o) * MP * MP, static_cast<int>(MP), P.m, rows, c->opt_ozaki,
                                       c->oz_chunk, c->ob + o * n + r0, c->H, o > 0, c->nupart + r0, c->aug ? c->w + o * MP : nullptr,
-                                      c->aug ? c->pred + r0 : nullptr, c->oz_ws, st, &c->launches))) return rc;
+                                      c->aug ? c->pred + r0 : nullptr, c->oz_ws, st, c->aux, c->oz_ev, &c->launches))) return rc;
             } else {
                 if ((rc = tgemm(phi, MP, c->Sinv + static_cast<int64_t>(o) * MP * MP, static_cast<int>(MP), P.m, rows, c->ob + o * n + r0,
                                 c->H, o > 0, c->nupart + r0, n, c->aug ? c->pred + r0 : nullptr, st, &c->launches))) return rc;
@@ -1211,6 +1256,9 @@ void gpz_destroy(gpz_ctx* c) {
         if (e) cudaEventDestroy(e);
     for (auto& e : c->kev)
         if (e) cudaEventDestroy(e);
+    for (auto& e : c->oz_ev)
+        if (e) cudaEventDestroy(e);
+    if (c->aux) cudaStreamDestroy(c->aux);
     if (c->h_out) cudaFreeHost(c->h_out);
     if (c->h_theta) cudaFreeHost(c->h_theta);
     if (c->st) cudaStreamDestroy(c->st);
@@ -1881,6 +1929,14 @@ int gpz_set_option(gpz_ctx* c, const char* name, double value) {
             return GPZ_ERR_USAGE;
         }
         c->opt_ozaki = static_cast<int>(value);
+        return GPZ_OK;
+    }
+    if (strcmp(name, "ozaki_gram") == 0) {
+        if (c->ws_ready) {
+            set_error("%s must be set before the first evaluation", name);
+            return GPZ_ERR_USAGE;
+        }
+        c->opt_ozaki_gram = value != 0.0;
         return GPZ_OK;
     }
     if (strcmp(name, "spare_column") == 0) {

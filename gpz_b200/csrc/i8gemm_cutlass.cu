@@ -44,16 +44,25 @@ bool i8gemm_available() { return true; }
 
 int i8gemm_tn(const int8_t* A, int64_t lda, const int8_t* B, int64_t ldb, int32_t* D, int64_t ldd, int M, int N, int K,
               void* workspace, size_t ws_bytes, cudaStream_t st) {
+    return i8gemm_tn_batched(A, lda, 0, B, ldb, 0, D, ldd, 0, M, N, K, 1, workspace, ws_bytes, st);
+}
+
+int i8gemm_tn_batched(const int8_t* A, int64_t lda, int64_t bsA, const int8_t* B, int64_t ldb, int64_t bsB, int32_t* D,
+                      int64_t ldd, int64_t bsD, int M, int N, int K, int batches, void* workspace, size_t ws_bytes,
+                      cudaStream_t st) {
     using StrideA = typename Gemm::GemmKernel::StrideA;
     using StrideB = typename Gemm::GemmKernel::StrideB;
     using StrideC = typename Gemm::GemmKernel::StrideC;
-    StrideA sa = cutlass::make_cute_packed_stride(StrideA{}, cute::make_shape(M, K, 1));
-    StrideB sb = cutlass::make_cute_packed_stride(StrideB{}, cute::make_shape(N, K, 1));
-    StrideC sc = cutlass::make_cute_packed_stride(StrideC{}, cute::make_shape(M, N, 1));
+    StrideA sa = cutlass::make_cute_packed_stride(StrideA{}, cute::make_shape(M, K, batches));
+    StrideB sb = cutlass::make_cute_packed_stride(StrideB{}, cute::make_shape(N, K, batches));
+    StrideC sc = cutlass::make_cute_packed_stride(StrideC{}, cute::make_shape(M, N, batches));
     get<0>(sa) = lda;
     get<0>(sb) = ldb;
     get<0>(sc) = ldd;
-    typename Gemm::Arguments args{cutlass::gemm::GemmUniversalMode::kGemm, {M, N, K, 1}, {A, sa, B, sb}, {{1, 0}, D, sc, D, sc}};
+    get<2>(sa) = bsA;
+    get<2>(sb) = bsB;
+    get<2>(sc) = bsD;
+    typename Gemm::Arguments args{cutlass::gemm::GemmUniversalMode::kGemm, {M, N, K, batches}, {A, sa, B, sb}, {{1, 0}, D, sc, D, sc}};
     Gemm gemm;
     if (gemm.can_implement(args) != cutlass::Status::kSuccess) {
         set_error("i8gemm: CUTLASS cannot implement M=%d N=%d K=%d", M, N, K);
@@ -74,6 +83,11 @@ int i8gemm_tn(const int8_t* A, int64_t lda, const int8_t* B, int64_t ldb, int32_
 namespace gpz {
 bool i8gemm_available() { return false; }
 int i8gemm_tn(const int8_t*, int64_t, const int8_t*, int64_t, int32_t*, int64_t, int, int, int, void*, size_t, cudaStream_t) {
+    set_error("built without the CUTLASS headers: the tcgen05 int8 GEMM is unavailable");
+    return GPZ_ERR_USAGE;
+}
+int i8gemm_tn_batched(const int8_t*, int64_t, int64_t, const int8_t*, int64_t, int64_t, int32_t*, int64_t, int64_t, int, int, int,
+                      int, void*, size_t, cudaStream_t) {
     set_error("built without the CUTLASS headers: the tcgen05 int8 GEMM is unavailable");
     return GPZ_ERR_USAGE;
 }

@@ -290,17 +290,21 @@ def test_int8_tensor_core_tgemm_matches_fp64(method, slices, tol):
     ref = O.GPz(theta, model, X, Y, None, omega, tr, va)
     gm = L.make_model(model.d, 1, model.m, method, True)
     res = {}
-    for oz in (0, slices):
+    for oz in (0, slices, -slices):
         ctx = L.Context(gm, X, Y, None, omega, tr, va)
-        ctx.set_option("ozaki_slices", oz)
+        ctx.set_option("ozaki_slices", abs(oz))
+        ctx.set_option("ozaki_gram", 1 if oz > 0 else 0)      # -slices: int8 T-GEMM with the fp64 DMMA Gram
         res[oz] = ctx.eval(theta)
         f2, g2, _ = ctx.eval(theta)
         assert f2 == res[oz][0] and np.array_equal(g2, res[oz][1])
         ctx.close()
     assert_eval_matches(model, ref, *res[slices], tol=max(tol, 1e-7))
     f0, g0, _ = res[0]
-    f1, g1, _ = res[slices]
-    assert abs(f1 - f0) <= 1e-12 * abs(f0)          # the objective value does not depend on T
-    gb0, gb1 = grad_blocks(model, g0), grad_blocks(model, g1)
-    for nm in gb0:
-        assert rel(gb1[nm], gb0[nm]) <= tol, (nm, rel(gb1[nm], gb0[nm]))
+    f2, g2, _ = res[-slices]
+    assert abs(f2 - f0) <= 1e-12 * abs(f0)          # the objective value does not depend on T
+    for key in (slices, -slices):
+        f1, g1, _ = res[key]
+        assert abs(f1 - f0) <= 1e-10 * abs(f0)
+        gb0, gb1 = grad_blocks(model, g0), grad_blocks(model, g1)
+        for nm in gb0:
+            assert rel(gb1[nm], gb0[nm]) <= tol, (key, nm, rel(gb1[nm], gb0[nm]))
