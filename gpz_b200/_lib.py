@@ -211,10 +211,11 @@ class Context:
         return int(self._lib.gpz_launch_count(self._h))
 
     def last_timing(self):
-        ms = np.empty(8)
+        ms = np.empty(12)
         check(self._lib.gpz_last_timing(self._h, ptr(ms)))
         return dict(phi=ms[0], gram=ms[1], solve=ms[2], tgemm=ms[3], backproj=ms[4], total=ms[5],
-                    gram_kernel=ms[6], tgemm_kernel=ms[7])
+                    gram_kernel=ms[6], tgemm_kernel=ms[7], i8_gemms_ms=ms[8], i8_gemms_ops=ms[9],
+                    int8_slices=int(ms[10]), int8_gram=int(ms[11]))
 
 
 def comm_unique_id() -> bytes:

@@ -495,7 +495,7 @@ struct gpz_ctx {
     int QP = 32;
     SolveWs sws;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t kev[4] = {nullptr, nullptr, nullptr, nullptr};   // [0,1] around the first Gram launch, [2,3] around the first T-GEMM launch
+    cudaEvent_t kev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // + [4,5] around the int8 level GEMMs of row chunk 0   // [0,1] around the first Gram launch, [2,3] around the first T-GEMM launch
     double* h_out = nullptr;   // pinned
     double* h_theta = nullptr; // pinned
     std::vector<void*> allocs;
@@ -990,7 +990,8 @@ int eval_device(gpz_ctx* c, const double* d_theta, double* d_out) {
             if (c->opt_ozaki > 0) {
                 if ((rc = ozaki_tgemm(phi, MP, c->Sinv + static_cast<int64_t>(o) * MP * MP, static_cast<int>(MP), P.m, rows, c->opt_ozaki,
                                       c->oz_chunk, c->ob + o * n + r0, c->H, o > 0, c->nupart + r0, c->aug ? c->w + o * MP : nullptr,
-                                      c->aug ? c->pred + r0 : nullptr, c->oz_ws, st, c->aux, c->oz_ev, &c->launches))) return rc;
+                                      c->aug ? c->pred + r0 : nullptr, c->oz_ws, st, c->aux, c->oz_ev, timed ? c->kev[4] : nullptr,
+                                      timed ? c->kev[5] : nullptr, &c->launches))) return rc;
             } else {
                 if ((rc = tgemm(phi, MP, c->Sinv + static_cast<int64_t>(o) * MP * MP, static_cast<int>(MP), P.m, rows, c->ob + o * n + r0,
                                 c->H, o > 0, c->nupart + r0, n, c->aug ? c->pred + r0 : nullptr, st, &c->launches))) return rc;
@@ -1871,7 +1872,7 @@ int gpz_sync(gpz_ctx* c) {
 
 int64_t gpz_launch_count(const gpz_ctx* c) { return c ? c->launches : -1; }
 
-int gpz_last_timing(gpz_ctx* c, double ms[8]) {
+int gpz_last_timing(gpz_ctx* c, double ms[12]) {
     if (!c || !c->ws_ready) {
         set_error("gpz_last_timing: no evaluation yet");
         return GPZ_ERR_USAGE;
@@ -1890,6 +1891,17 @@ int gpz_last_timing(gpz_ctx* c, double ms[8]) {
     ms[6] = t;
     GPZ_CUDA(cudaEventElapsedTime(&t, c->kev[2], c->kev[3]));
     ms[7] = t;
+    ms[8] = ms[9] = ms[10] = ms[11] = 0.0;
+    if (c->opt_ozaki > 0) {
+        GPZ_CUDA(cudaEventElapsedTime(&t, c->kev[4], c->kev[5]));
+        ms[8] = t;                                              // the s int8 level GEMMs of row chunk 0
+        const double rows = static_cast<double>(c->tr.n < c->oz_chunk ? c->tr.n : c->oz_chunk);
+        double levels = 0.0;
+        for (int e = 2; e <= c->opt_ozaki + 1; ++e) levels += e - 1;
+        ms[9] = 2.0 * rows * c->P.MP * c->P.MP * levels;        // int8 operations those GEMMs executed
+    }
+    ms[10] = c->opt_ozaki;
+    ms[11] = c->opt_ozaki_gram;
     return GPZ_OK;
 }
 

@@ -148,6 +148,6 @@ int ozaki_gram(const double* Phi, int64_t ld, int MP, int m, int64_t rows, int s
                int aug, int accumulate, double* S, void* ws, cudaStream_t st, int64_t* launches);
 int ozaki_tgemm(const double* Phi, int64_t ld, const double* Sinv, int MP, int m, int64_t n, int s, int64_t chunk_rows,
                 const double* rw, double* H, int accumulate, double* nu, const double* waug, double* pred, void* ws,
-                cudaStream_t st, cudaStream_t aux, cudaEvent_t* ev6, int64_t* launches);
+                cudaStream_t st, cudaStream_t aux, cudaEvent_t* ev6, cudaEvent_t tev0, cudaEvent_t tev1, int64_t* launches);
 
 }  // namespace gpz

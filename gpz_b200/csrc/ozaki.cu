@@ -176,7 +176,7 @@ int64_t oz_workspace_bytes(int MP, int s, int64_t chunk_rows) {
 // the slicing of chunk c+1 and the fp64 combine/epilogue of chunk c-1 (both HBM bound, stream aux).  ev: 6 events.
 int ozaki_tgemm(const double* Phi, int64_t ld, const double* Sinv, int MP, int m, int64_t n, int s, int64_t chunk_rows,
                 const double* rw, double* H, int accumulate, double* nu, const double* waug, double* pred, void* ws,
-                cudaStream_t st, cudaStream_t aux, cudaEvent_t* ev, int64_t* launches) {
+                cudaStream_t st, cudaStream_t aux, cudaEvent_t* ev, cudaEvent_t tev0, cudaEvent_t tev1, int64_t* launches) {
     if (s < 2 || s > OZ_MAXS) {
         set_error("ozaki_tgemm: slices must be in [2, %d]", OZ_MAXS);
         return GPZ_ERR_USAGE;
@@ -240,12 +240,14 @@ int ozaki_tgemm(const double* Phi, int64_t ld, const double* Sinv, int MP, int m
         }
         GPZ_CUDA(cudaStreamWaitEvent(st, evS[b], 0));
         if (c >= 2) GPZ_CUDA(cudaStreamWaitEvent(st, evC[b], 0));               // D[b] was read by the combine of chunk c-2
+        if (c == 0 && tev0) GPZ_CUDA(cudaEventRecord(tev0, st));
         for (int e = 2; e <= s + 1; ++e) {
             const int K = (e - 1) * MP;
             int rc = i8gemm_tn(A8[b], static_cast<int64_t>(s) * MP, L.B[e], K, Dbuf[b][e], MP, static_cast<int>(rows), MP, K, cws, 64 << 20, st);
             if (rc) return rc;
             ++*launches;
         }
+        if (c == 0 && tev1) GPZ_CUDA(cudaEventRecord(tev1, st));
         GPZ_CUDA(cudaEventRecord(evG[b], st));
         GPZ_CUDA(cudaStreamWaitEvent(aux, evG[b], 0));
         oz_combine_kernel<<<static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, aux>>>(Dl[b], s, ea[b], eb, Phi + r0 * ld, ld, MP, m, rows,

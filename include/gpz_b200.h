@@ -124,8 +124,10 @@ int64_t gpz_launch_count(const gpz_ctx* ctx);   /* kernels launched by this cont
 /* device time (ms, CUDA events on the context stream) of the phases of the LAST eval:
  * [0] phi build  [1] row weights + Gram + PHI'Wy (+allreduce #1)  [2] solve  [3] PHI w + T-GEMM + row gradients
  * [4] dPHI + back-projection + validation + finish (+allreduce #2)  [5] total
- * [6] the Gram kernel alone (first launch)  [7] the T-GEMM kernel alone (first launch)            */
-int gpz_last_timing(gpz_ctx* ctx, double ms[8]);
+ * [6] the Gram step alone  [7] the T-GEMM step alone (fp64 DMMA kernel, or slicing + int8 level GEMMs + combine)
+ * [8] the int8 level GEMMs of row chunk 0 (ms)  [9] int8 operations those GEMMs executed
+ * [10] int8 slices in use (0 = fp64 DMMA path)  [11] 1 if the Gram also runs on the int8 tensor cores   */
+int gpz_last_timing(gpz_ctx* ctx, double ms[12]);
 int gpz_set_option(gpz_ctx* ctx, const char* name, double value);
 
 #ifdef __cplusplus
