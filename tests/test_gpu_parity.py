@@ -89,7 +89,9 @@ def test_eval_multi_tile_m(method):
     """m > 128: several Gram tiles, several Cholesky panels with a ragged last one."""
     model, theta, X, Y, Psi, omega, tr, va = problem(method, True, False, False, n=2500, d=4, m=150, seed=7)
     ref, f, g, st, ctx = run_both(model, theta, X, Y, Psi, omega, tr, va)
-    assert_eval_matches(model, ref, f, g, st)
+    # m=150 bases on 2000 rows: cond(SIGMA) ~ 1e7, so the oracle (SVD pseudo-inverse), the fp64 DMMA Gram and the int8-slice
+    # Gram legitimately differ at the cond*eps ~ 1e-9 level; 5e-9 here, 1e-9 on the well-conditioned cases
+    assert_eval_matches(model, ref, f, g, st, tol=5e-9)
     ctx.close()
 
 
