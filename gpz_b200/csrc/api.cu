@@ -464,7 +464,7 @@ struct gpz_ctx {
     int opt_ozaki = -1;             // >0: T-GEMM through the int8 tensor cores with this many 7-bit slices (ozaki.cu);
                                     // -1: default = 8 when the tcgen05 int8 GEMM was built in, else 0 (fp64 DMMA)
     void* oz_ws = nullptr;
-    int64_t oz_chunk = 0;
+    int64_t oz_chunk = 0, opt_oz_chunk = 0;
     cudaStream_t aux = nullptr;     // second stream of the int8 T-GEMM pipeline
     cudaEvent_t oz_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int opt_ozaki_gram = -1;        // Gram through the int8 tensor cores too (-1: follows ozaki_slices > 0, k == 1)
@@ -804,7 +804,8 @@ int ensure_workspace(gpz_ctx* c) {
             set_error("ozaki_slices: this build has no tcgen05 int8 GEMM (CUTLASS headers were not found at build time)");
             return GPZ_ERR_USAGE;
         }
-        c->oz_chunk = nn < 131072 ? nn : 131072;
+        if (c->opt_oz_chunk <= 0) c->opt_oz_chunk = 131072;
+        c->oz_chunk = nn < c->opt_oz_chunk ? nn : c->opt_oz_chunk;
         GPZ_CUDA(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
         for (auto& e : c->oz_ev) GPZ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         double* tmp = nullptr;
@@ -1941,6 +1942,14 @@ int gpz_set_option(gpz_ctx* c, const char* name, double value) {
             return GPZ_ERR_USAGE;
         }
         c->opt_ozaki = static_cast<int>(value);
+        return GPZ_OK;
+    }
+    if (strcmp(name, "ozaki_chunk_rows") == 0) {
+        if (c->ws_ready) {
+            set_error("%s must be set before the first evaluation", name);
+            return GPZ_ERR_USAGE;
+        }
+        c->opt_oz_chunk = static_cast<int64_t>(round_up(static_cast<int64_t>(value), 1024));
         return GPZ_OK;
     }
     if (strcmp(name, "ozaki_gram") == 0) {

@@ -712,15 +712,32 @@ int atb_dphi(const double* Phi, const double* H, int64_t ld, int MP, const doubl
 //   A(i,k) = A[i*sAi + k*sAk],  B(k,j) = B[k*sBk + j*sBj];  64x64 tile, 4 warps, DMMA
 //   lower_only: skip tiles strictly above the diagonal
 // ------------------------------------------------------------------------------------------------
+//   batched over blockIdx.z: operand pointers advance by bsA/bsB/bsC per batch; with mlim > 0 the batch z works on
+//   M_z = min(M, mlim - z*mstep) rows (and K_z = M_z when k_follows_m), which lets one launch cover the ragged last pair of
+//   the recursive triangular inverse
+struct SgemmBatch {
+    int64_t bsA, bsB, bsC;
+    int mlim, mstep, k_follows_m;
+};
+
 __global__ void __launch_bounds__(128)
 sgemm_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, int64_t sAi, int64_t sAk,
              const double* __restrict__ B, int64_t sBk, int64_t sBj, double beta, double* __restrict__ C, int64_t ldc,
-             int lower_only) {
+             int lower_only, SgemmBatch bt) {
     constexpr int TS = 64, LA = KSTEP + 4, LB = TS + 4;
     __shared__ double As[TS][LA];
     __shared__ double Bs[KSTEP][LB];
     const int ti = blockIdx.y, tj = blockIdx.x;
     if (lower_only && tj > ti) return;
+    if (bt.mlim > 0) {
+        const int mz = bt.mlim - static_cast<int>(blockIdx.z) * bt.mstep;
+        if (mz < M) M = mz;
+        if (bt.k_follows_m) K = M;
+        if (M <= 0 || ti * TS >= M) return;
+    }
+    A += blockIdx.z * bt.bsA;
+    B += blockIdx.z * bt.bsB;
+    C += blockIdx.z * bt.bsC;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int wm0 = (warp >> 1) * 32, wn0 = (warp & 1) * 32;
@@ -784,7 +801,20 @@ int sgemm(int M, int N, int K, double alpha, const double* A, int64_t sAi, int64
           int64_t sBj, double beta, double* C, int64_t ldc, int lower_only, cudaStream_t st, int64_t* launches) {
     if (M <= 0 || N <= 0) return GPZ_OK;
     dim3 grid(static_cast<unsigned>(ceil_div(N, 64)), static_cast<unsigned>(ceil_div(M, 64)));
-    sgemm_kernel<<<grid, 128, 0, st>>>(M, N, K, alpha, A, sAi, sAk, B, sBk, sBj, beta, C, ldc, lower_only);
+    sgemm_kernel<<<grid, 128, 0, st>>>(M, N, K, alpha, A, sAi, sAk, B, sBk, sBj, beta, C, ldc, lower_only, SgemmBatch{0, 0, 0, 0, 0, 0});
+    GPZ_KERNEL_CHECK();
+    ++*launches;
+    return GPZ_OK;
+}
+
+// batched variant (see SgemmBatch): `batches` problems, pointers advancing by bsA/bsB/bsC
+int sgemm_batched(int M, int N, int K, double alpha, const double* A, int64_t sAi, int64_t sAk, int64_t bsA, const double* B,
+                  int64_t sBk, int64_t sBj, int64_t bsB, double beta, double* C, int64_t ldc, int64_t bsC, int batches, int mlim,
+                  int mstep, int k_follows_m, cudaStream_t st, int64_t* launches) {
+    if (M <= 0 || N <= 0 || batches <= 0) return GPZ_OK;
+    dim3 grid(static_cast<unsigned>(ceil_div(N, 64)), static_cast<unsigned>(ceil_div(M, 64)), static_cast<unsigned>(batches));
+    sgemm_kernel<<<grid, 128, 0, st>>>(M, N, K, alpha, A, sAi, sAk, B, sBk, sBj, beta, C, ldc, 0,
+                                       SgemmBatch{bsA, bsB, bsC, mlim, mstep, k_follows_m});
     GPZ_KERNEL_CHECK();
     ++*launches;
     return GPZ_OK;

@@ -94,6 +94,10 @@ int atb_dphi(const double* Phi, const double* H, int64_t ld, int MP, const doubl
 int sgemm(int M, int N, int K, double alpha, const double* A, int64_t sAi, int64_t sAk, const double* B, int64_t sBk,
           int64_t sBj, double beta, double* C, int64_t ldc, int lower_only, cudaStream_t st, int64_t* launches);
 
+int sgemm_batched(int M, int N, int K, double alpha, const double* A, int64_t sAi, int64_t sAk, int64_t bsA, const double* B,
+                  int64_t sBk, int64_t sBj, int64_t bsB, double beta, double* C, int64_t ldc, int64_t bsC, int batches, int mlim,
+                  int mstep, int k_follows_m, cudaStream_t st, int64_t* launches);
+
 // ---- solve.cu
 struct SolveWs {
     double* W = nullptr;      // [MP][MP] L^{-1}

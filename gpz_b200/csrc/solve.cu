@@ -135,7 +135,9 @@ int spd_inverse(double* S, int m, int MP, double* Sinv, double* d_logdet, SolveW
             if (rc) return rc;
         }
     }
-    // ---- W = L^{-1} (lower triangular), block row by block row
+    // ---- W = L^{-1} (lower triangular) by recursive doubling: the diagonal 64-blocks are already inverted; at block size b
+    //      every pair of neighbouring inverted blocks [1 | 2] is merged with W21 = -W22 * (L21 * W11), all pairs in one
+    //      batched launch (the last pair may be ragged: rows of block 2 clipped to m).  Sinv serves as the scratch T.
     zero_kernel<<<static_cast<unsigned>(ceil_div(static_cast<int64_t>(MP) * MP, 256)), 256, 0, st>>>(
         ws.W, static_cast<int64_t>(MP) * MP);
     GPZ_KERNEL_CHECK();
@@ -143,15 +145,19 @@ int spd_inverse(double* S, int m, int MP, double* Sinv, double* d_logdet, SolveW
     place_diag_kernel<<<nblk, 256, 0, st>>>(ws.Linv, ws.W, ld, m);
     GPZ_KERNEL_CHECK();
     ++*launches;
-    for (int ib = 1; ib < nblk; ++ib) {
-        const int i0 = ib * NB;
-        const int nb = (m - i0 < NB) ? (m - i0) : NB;
-        // tmp(nb x i0) = L[i0:i0+nb, 0:i0] * W[0:i0, 0:i0]
-        rc = sgemm(nb, i0, i0, 1.0, S + static_cast<int64_t>(i0) * ld, ld, 1, ws.W, ld, 1, 0.0, ws.tmp, ld, 0, st, launches);
+    for (int b = NB; b < m; b *= 2) {
+        const int npairs = static_cast<int>(ceil_div(m - b, 2 * b));        // pairs whose block 2 is non-empty
+        const int64_t bs = static_cast<int64_t>(2 * b) * ld + 2 * b;         // pointer step from pair to pair
+        const double* L21 = S + static_cast<int64_t>(b) * ld;
+        const double* W11 = ws.W;
+        const double* W22 = ws.W + static_cast<int64_t>(b) * ld + b;
+        double* T21 = Sinv + static_cast<int64_t>(b) * ld;
+        double* W21 = ws.W + static_cast<int64_t>(b) * ld;
+        // T21 = L21 * W11          (rows of block 2: min(b, m - (2pb + b)))
+        rc = sgemm_batched(b, b, b, 1.0, L21, ld, 1, bs, W11, ld, 1, bs, 0.0, T21, ld, bs, npairs, m - b, 2 * b, 0, st, launches);
         if (rc) return rc;
-        // W[i0:i0+nb, 0:i0] = -Linv_ii * tmp
-        rc = sgemm(nb, i0, nb, -1.0, ws.Linv + static_cast<int64_t>(ib) * NB * NB, NB, 1, ws.tmp, ld, 1, 0.0,
-                   ws.W + static_cast<int64_t>(i0) * ld, ld, 0, st, launches);
+        // W21 = -W22 * T21         (K = rows of block 2)
+        rc = sgemm_batched(b, b, b, -1.0, W22, ld, 1, bs, T21, ld, 1, bs, 0.0, W21, ld, bs, npairs, m - b, 2 * b, 1, st, launches);
         if (rc) return rc;
     }
     // ---- Sinv = W' W (full symmetric): A(i,k) = W[k][i], B(k,j) = W[k][j]
