@@ -1672,11 +1672,8 @@ int gpz_predict(const gpz_model* model, const double* theta, const double* w, co
             return GPZ_OK;
         }
     }
-    if (Psi && mode_is_cov(P.mode)) {
-        set_error("predictNoisy for covariance modes (predictCov.m:70-133) is not supported yet");
-        return GPZ_ERR_USAGE;
-    }
     if (n == 0) return GPZ_OK;
+    const bool cov_psi = Psi && mode_is_cov(P.mode);
     std::vector<void*> allocs;
     cudaStream_t st = nullptr;
     int64_t launches = 0;
@@ -1701,7 +1698,7 @@ int gpz_predict(const gpz_model* model, const double* theta, const double* w, co
     }
     const int64_t MP = P.MP;
     const int k = P.k;
-    PR(alloc_params(P, allocs, 0));
+    PR(alloc_params(P, allocs, cov_psi ? 1 : 0));
     double *d_theta, *d_w, *d_Sinv, *d_X, *d_Psi = nullptr, *d_Phi, *d_dotv, *d_mu, *d_nupart, *d_nu, *d_elns, *d_beta, *d_gamma, *d_col = nullptr;
     PR(dev_alloc(allocs, &d_theta, P.p));
     PR(dev_alloc(allocs, &d_w, k * MP));
@@ -1713,7 +1710,7 @@ int gpz_predict(const gpz_model* model, const double* theta, const double* w, co
     if (chunk < 1024) chunk = 1024;
     if (chunk > n) chunk = n;
     PR(dev_alloc(allocs, &d_X, n * P.d));
-    if (Psi) PR(dev_alloc(allocs, &d_Psi, n * P.d));
+    if (Psi) PR(dev_alloc(allocs, &d_Psi, n * P.d * (cov_psi ? P.d : 1)));
     PR(dev_alloc(allocs, &d_Phi, chunk * MP));
     if (PHI) PR(dev_alloc(allocs, &d_col, chunk * P.m));
     PR(dev_alloc(allocs, &d_dotv, k * n));
@@ -1749,8 +1746,8 @@ int gpz_predict(const gpz_model* model, const double* theta, const double* w, co
         PR(cuda_ok(cudaMemcpy(d_X, hx.data(), sizeof(double) * n * P.d, cudaMemcpyHostToDevice), "H2D X"));
         PR(cuda_ok(cudaMemcpy(P.xshift, sh.data(), sizeof(double) * P.d, cudaMemcpyHostToDevice), "H2D shift"));
     }
-    if (Psi) PR(cuda_ok(cudaMemcpyAsync(d_Psi, Psi, sizeof(double) * n * P.d, cudaMemcpyHostToDevice, st), "H2D Psi"));
-    PR(prep_params(d_theta, P, 0, st, &launches));
+    if (Psi) PR(cuda_ok(cudaMemcpyAsync(d_Psi, Psi, sizeof(double) * n * P.d * (cov_psi ? P.d : 1), cudaMemcpyHostToDevice, st), "H2D Psi"));
+    PR(prep_params(d_theta, P, cov_psi ? 1 : 0, st, &launches));
     RowData R;
     R.n = n;
     R.X = d_X;
@@ -1785,7 +1782,8 @@ int gpz_predict(const gpz_model* model, const double* theta, const double* w, co
     }
     exp_rows_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, st>>>(d_dotv, P.bk, P.het, k, n, d_elns, d_beta);
     PR(cuda_ok(cudaMemsetAsync(d_gamma, 0, sizeof(double) * k * n, st), "memset"));
-    if (Psi) PR(predict_noisy_diag(P, R, d_w, d_Sinv, d_elns, d_mu, d_nu, d_beta, d_gamma, st, &launches));
+    if (cov_psi) PR(predict_noisy_cov(P, R, d_w, d_Sinv, d_elns, d_mu, d_nu, d_beta, d_gamma, st, &launches));
+    else if (Psi) PR(predict_noisy_diag(P, R, d_w, d_Sinv, d_elns, d_mu, d_nu, d_beta, d_gamma, st, &launches));
     PR(cuda_ok(cudaMemcpyAsync(mu, d_mu, sizeof(double) * k * n, cudaMemcpyDeviceToHost, st), "D2H"));
     PR(cuda_ok(cudaMemcpyAsync(nu, d_nu, sizeof(double) * k * n, cudaMemcpyDeviceToHost, st), "D2H"));
     PR(cuda_ok(cudaMemcpyAsync(beta_i, d_beta, sizeof(double) * k * n, cudaMemcpyDeviceToHost, st), "D2H"));

@@ -134,6 +134,8 @@ int predict_noisy_diag(const Params& P, const RowData& R, const double* w /*[k][
                        const double* ElnS /*[k][n] = b + PHI v*/, const double* mu /*[k][n]*/, double* nu, double* beta_i,
                        double* gamma, cudaStream_t st, int64_t* launches);
 
+int predict_noisy_cov(const Params& P, const RowData& R, const double* w, const double* Sinv, const double* ElnS,
+                      const double* mu, double* nu, double* beta_i, double* gamma, cudaStream_t st, int64_t* launches);
 int predict_missing_diag(const Params& P, const double* X, const double* Psi, int64_t n, const unsigned char* ob,
                          const double* prior, const double* w, const double* Sinv, double* mu, double* nu, double* beta_i,
                          double* gamma, double* Phi, cudaStream_t st, int64_t* launches);

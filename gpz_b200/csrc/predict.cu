@@ -394,3 +394,176 @@ int predict_missing_diag(const Params& P, const double* X, const double* Psi, in
 }
 
 }  // namespace gpz
+
+// ================================================================================================
+// predictNoisy for the covariance modes (GPz/predictCov.m:70-133): per basis pair (a >= b)
+//   iC = iSigma_a + iSigma_b, C = iC^-1, c = (p_a iSigma_a + p_b iSigma_b) C,
+//   lnZ = lnz_a + lnz_b - 1/2 dp (Sigma_a+Sigma_b)^-1 dp' - 1/2 ln|Sigma_a+Sigma_b|            (:101-107)
+// and per (sample, pair) a d x d Cholesky of C + Psi_i for N(x_i; c, C + Psi_i)                   (:109-113)
+// ================================================================================================
+#include "smallmat.cuh"
+
+namespace gpz {
+
+struct CPairTab {
+    int64_t npairs;
+    double* C;      // [d*d][npairs]
+    double* c;      // [d][npairs]
+    double* lnZ;    // [npairs]
+    double* ww;     // [k][npairs]
+    double* vv;
+    double* ss;
+};
+
+template <int DMAX>
+__global__ void __launch_bounds__(64)
+cpair_table_kernel(Params P, const double* __restrict__ w, const double* __restrict__ Sinv, CPairTab T) {
+    const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (q >= T.npairs) return;
+    int64_t i = static_cast<int64_t>((sqrt(8.0 * static_cast<double>(q) + 1.0) - 1.0) * 0.5);
+    while ((i + 1) * (i + 2) / 2 <= q) ++i;
+    while (i * (i + 1) / 2 > q) --i;
+    const int64_t j = q - i * (i + 1) / 2;
+    const int d = P.d, MP = P.MP;
+    double M[DMAX * DMAX], dp[DMAX], t[DMAX];
+    LocalMat Mm{M, d};
+    // C = (iSigma_i + iSigma_j)^-1
+    for (int a = 0; a < d; ++a)
+        for (int b = 0; b < d; ++b)
+            Mm(a, b) = P.Aj[(static_cast<int64_t>(a) * d + b) * MP + i] + P.Aj[(static_cast<int64_t>(a) * d + b) * MP + j];
+    double hl = 0.0;
+    bool ok = spd_inv(Mm, d, &hl);
+    for (int a = 0; a < d; ++a) {
+        double s = 0.0;                       // t = p_i iSigma_i + p_j iSigma_j   (row vector)
+        for (int b = 0; b < d; ++b)
+            s += P.Pt[b * MP + i] * P.Aj[(static_cast<int64_t>(b) * d + a) * MP + i] + P.Pt[b * MP + j] * P.Aj[(static_cast<int64_t>(b) * d + a) * MP + j];
+        t[a] = s;
+    }
+    for (int a = 0; a < d; ++a) {
+        double s = 0.0;
+        for (int b = 0; b < d; ++b) {
+            s += t[b] * Mm(b, a);
+            T.C[(static_cast<int64_t>(a) * d + b) * T.npairs + q] = Mm(a, b);
+        }
+        T.c[a * T.npairs + q] = s;
+    }
+    // lnZ: Cholesky of Sigma_i + Sigma_j
+    for (int a = 0; a < d; ++a) {
+        for (int b = 0; b <= a; ++b)
+            Mm(a, b) = P.Sj[(static_cast<int64_t>(a) * d + b) * MP + i] + P.Sj[(static_cast<int64_t>(a) * d + b) * MP + j];
+        dp[a] = P.Pt[a * MP + i] - P.Pt[a * MP + j];
+    }
+    double hs = 0.0, quad = 0.0;
+    ok = chol_lower(Mm, d, &hs) && ok;
+    for (int a = 0; a < d; ++a) {
+        double s = dp[a];
+        for (int b = 0; b < a; ++b) s -= Mm(a, b) * dp[b];
+        s /= Mm(a, a);
+        dp[a] = s;
+        quad += s * s;
+    }
+    T.lnZ[q] = ok ? 0.5 * P.lndS[i] + 0.5 * P.lndS[j] - 0.5 * quad - hs : nan("");
+    const double f = (i == j) ? 1.0 : 2.0;
+    for (int o = 0; o < P.k; ++o) {
+        T.ww[o * T.npairs + q] = f * w[o * MP + i] * w[o * MP + j];
+        T.vv[o * T.npairs + q] = f * P.v[o * MP + i] * P.v[o * MP + j];
+        T.ss[o * T.npairs + q] = f * Sinv[(static_cast<int64_t>(o) * MP + i) * MP + j];
+    }
+}
+
+template <int DMAX, int KMAX>
+__global__ void __launch_bounds__(64)
+predict_noisy_cov_kernel(Params P, const double* __restrict__ X, const double* __restrict__ Psi, int64_t n, CPairTab T,
+                         const double* __restrict__ ElnS, const double* __restrict__ mu, double* __restrict__ nu,
+                         double* __restrict__ beta_i, double* __restrict__ gamma) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int d = P.d, k = P.k;
+    double x[DMAX], S[DMAX * DMAX], z[DMAX];
+    LocalMat Sm{S, d};
+    for (int a = 0; a < d; ++a) x[a] = X[a * n + i];
+    const double* psi = Psi + i * d * d;
+    double g[KMAX], vl[KMAX], nv[KMAX];
+#pragma unroll
+    for (int o = 0; o < KMAX; ++o) g[o] = vl[o] = nv[o] = 0.0;
+    for (int64_t q = 0; q < T.npairs; ++q) {
+        for (int a = 0; a < d; ++a) {
+            for (int b = 0; b <= a; ++b) Sm(a, b) = psi[a + b * d] + __ldg(T.C + (static_cast<int64_t>(a) * d + b) * T.npairs + q);
+            z[a] = x[a] - __ldg(T.c + a * T.npairs + q);
+        }
+        double hl = 0.0, quad = 0.0;
+        if (!chol_lower(Sm, d, &hl)) {
+            g[0] = nan("");
+            continue;
+        }
+        for (int a = 0; a < d; ++a) {
+            double s = z[a];
+            for (int b = 0; b < a; ++b) s -= Sm(a, b) * z[b];
+            s /= Sm(a, a);
+            z[a] = s;
+            quad += s * s;
+        }
+        const double Z = exp(__ldg(T.lnZ + q) - 0.5 * quad - hl);
+#pragma unroll
+        for (int o = 0; o < KMAX; ++o) {
+            if (o < k) {
+                g[o] = fma(Z, __ldg(T.ww + o * T.npairs + q), g[o]);
+                vl[o] = fma(Z, __ldg(T.vv + o * T.npairs + q), vl[o]);
+                nv[o] = fma(Z, __ldg(T.ss + o * T.npairs + q), nv[o]);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < KMAX; ++o) {
+        if (o < k) {
+            const double e = ElnS[o * n + i];
+            const double m_ = mu[o * n + i];
+            const double dv = e - P.bk[o];
+            const double V = vl[o] - dv * dv;                    // predictCov.m:131
+            gamma[o * n + i] = g[o] - m_ * m_;                   // :132
+            beta_i[o * n + i] = exp(e) * (1.0 + 0.5 * V);        // :133
+            nu[o * n + i] = nv[o];
+        }
+    }
+}
+
+// needs P.Sj / P.lndS (prep_params with need_sigma = 1); X shifted like P.Pt; Psi [n][d*d]
+int predict_noisy_cov(const Params& P, const RowData& R, const double* w, const double* Sinv, const double* ElnS,
+                      const double* mu, double* nu, double* beta_i, double* gamma, cudaStream_t st, int64_t* launches) {
+    if (P.k > 4 || P.d > 32) {
+        set_error("predictNoisy (cov): k <= 4 and d <= 32 supported");
+        return GPZ_ERR_USAGE;
+    }
+    CPairTab T;
+    T.npairs = static_cast<int64_t>(P.m) * (P.m + 1) / 2;
+    double* buf = nullptr;
+    const int64_t per = static_cast<int64_t>(P.d) * P.d + P.d + 1 + 3LL * P.k;
+    GPZ_CUDA(cudaMalloc(&buf, sizeof(double) * per * T.npairs));
+    T.C = buf;
+    T.c = T.C + static_cast<int64_t>(P.d) * P.d * T.npairs;
+    T.lnZ = T.c + static_cast<int64_t>(P.d) * T.npairs;
+    T.ww = T.lnZ + T.npairs;
+    T.vv = T.ww + static_cast<int64_t>(P.k) * T.npairs;
+    T.ss = T.vv + static_cast<int64_t>(P.k) * T.npairs;
+    const unsigned nbp = static_cast<unsigned>(ceil_div(T.npairs, 64)), nbr = static_cast<unsigned>(ceil_div(R.n, 64));
+    if (P.d <= 8) {
+        cpair_table_kernel<8><<<nbp, 64, 0, st>>>(P, w, Sinv, T);
+        predict_noisy_cov_kernel<8, 4><<<nbr, 64, 0, st>>>(P, R.X, R.Psi, R.n, T, ElnS, mu, nu, beta_i, gamma);
+    } else if (P.d <= 16) {
+        cpair_table_kernel<16><<<nbp, 64, 0, st>>>(P, w, Sinv, T);
+        predict_noisy_cov_kernel<16, 4><<<nbr, 64, 0, st>>>(P, R.X, R.Psi, R.n, T, ElnS, mu, nu, beta_i, gamma);
+    } else {
+        cpair_table_kernel<32><<<nbp, 64, 0, st>>>(P, w, Sinv, T);
+        predict_noisy_cov_kernel<32, 4><<<nbr, 64, 0, st>>>(P, R.X, R.Psi, R.n, T, ElnS, mu, nu, beta_i, gamma);
+    }
+    *launches += 2;
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(buf);
+    if (e != cudaSuccess) {
+        set_error("predict_noisy_cov: %s", cudaGetErrorString(e));
+        return GPZ_ERR_CUDA;
+    }
+    return GPZ_OK;
+}
+
+}  // namespace gpz

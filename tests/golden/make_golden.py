@@ -56,8 +56,8 @@ def build(name):
         Xt = X[va][:40]
         mu, sigma, nu, be, ga, _ = O.predict(Xt, model, Psi=None)
         out.update(pred_X=Xt, pred_mu=mu, pred_nu=nu, pred_beta_i=be, pred_gamma=ga)
-        if Psi is not None and method[1] != "C":
-            Pt = Psi[va][:40]
+        if Psi is not None:
+            Pt = Psi[:, :, va][:, :, :40] if method[1] == "C" else Psi[va][:40]
             mu, sigma, nu, be, ga, _ = O.predict(Xt, model, Psi=Pt)
             out.update(predn_Psi=Pt, predn_mu=mu, predn_nu=nu, predn_beta_i=be, predn_gamma=ga)
     return out
