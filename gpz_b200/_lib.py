@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgpz_b200.so")
+LIB_PATH = os.environ.get("GPZ_B200_LIB") or os.path.join(_HERE, "libgpz_b200.so")
 
 EXPORTS = [
     "gpz_last_error", "gpz_version", "gpz_theta_len", "gpz_g_dim", "gpz_create", "gpz_destroy",

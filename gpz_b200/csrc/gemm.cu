@@ -749,21 +749,40 @@ sgemm_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, in
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    for (int k0 = 0; k0 < K; k0 += KSTEP) {
-        // A tile 64 x 16
-        for (int e = tid; e < TS * KSTEP; e += 128) {
+    // software pipeline: the next K tile is fetched into registers while the current one is multiplied
+    const bool a_kfast = (sAk == 1), b_jfast = (sBj == 1);
+    double ra[8], rb[8];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int e = tid + q * 128;
             int r, c;
-            if (sAk == 1) { r = e / KSTEP; c = e % KSTEP; } else { c = e / TS; r = e % TS; }
+            if (a_kfast) { r = e / KSTEP; c = e % KSTEP; } else { c = e / TS; r = e % TS; }
             const int gi = i0 + r, gk = k0 + c;
-            As[r][c] = (gi < M && gk < K) ? A[gi * sAi + gk * sAk] : 0.0;
+            ra[q] = (gi < M && gk < K) ? A[gi * sAi + gk * sAk] : 0.0;
+            int rr, cc;
+            if (b_jfast) { rr = e / TS; cc = e % TS; } else { cc = e / KSTEP; rr = e % KSTEP; }
+            const int gk2 = k0 + rr, gj = j0 + cc;
+            rb[q] = (gk2 < K && gj < N) ? B[gk2 * sBk + gj * sBj] : 0.0;
         }
-        for (int e = tid; e < TS * KSTEP; e += 128) {
+    };
+    auto stash = [&]() {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int e = tid + q * 128;
             int r, c;
-            if (sBj == 1) { r = e / TS; c = e % TS; } else { c = e / KSTEP; r = e % KSTEP; }
-            const int gk = k0 + r, gj = j0 + c;
-            Bs[r][c] = (gk < K && gj < N) ? B[gk * sBk + gj * sBj] : 0.0;
+            if (a_kfast) { r = e / KSTEP; c = e % KSTEP; } else { c = e / TS; r = e % TS; }
+            As[r][c] = ra[q];
+            int rr, cc;
+            if (b_jfast) { rr = e / TS; cc = e % TS; } else { cc = e / KSTEP; rr = e % KSTEP; }
+            Bs[rr][cc] = rb[q];
         }
+    };
+    if (K > 0) fetch(0);
+    for (int k0 = 0; k0 < K; k0 += KSTEP) {
+        stash();
         __syncthreads();
+        if (k0 + KSTEP < K) fetch(k0 + KSTEP);
 #pragma unroll
         for (int kk = 0; kk < KSTEP / 4; ++kk) {
             const int kc = kk * 4 + t;

@@ -10,42 +10,97 @@ namespace gpz {
 
 constexpr int NB = 64;
 
-// factor the nb x nb diagonal block at (k0,k0) in place (lower), invert the factor into Linv (row-major
-// 64 x 64, zero upper triangle), accumulate logdet
-__global__ void __launch_bounds__(256)
+// warp-synchronous Cholesky of the 32 x 32 block at (o,o) of the smem tile A (lower, in place); lane = row.
+// (A register/shuffle variant was measured slower: 2.7 vs 2.2 ms for the whole m=1000 solve.)
+// returns false (uniformly) on a non-positive pivot; *ld2 accumulates 2*sum(log L_cc)
+__device__ __forceinline__ bool chol32(double (*A)[NB + 1], int o, double* ld2) {
+    const int lane = threadIdx.x & 31;
+    for (int c = 0; c < 32; ++c) {
+        const double piv = A[o + c][o + c];
+        if (!(piv > 0.0)) return false;
+        const double l = sqrt(piv);
+        *ld2 += 2.0 * log(l);
+        __syncwarp();
+        if (lane == c) A[o + c][o + c] = l;
+        else if (lane > c) A[o + lane][o + c] /= l;
+        __syncwarp();
+        if (lane > c) {
+            const double arc = A[o + lane][o + c];
+            for (int q = c + 1; q <= lane; ++q) A[o + lane][o + q] -= arc * A[o + q][o + c];
+        }
+        __syncwarp();
+    }
+    return true;
+}
+
+// W(o..o+32, o..o+32) = inverse of the lower-triangular 32 x 32 block of A at (o,o); lane = column (forward substitution
+// by rows, no cross-lane traffic: L[r][q] is a broadcast read)
+__device__ __forceinline__ void trinv32(double (*A)[NB + 1], double (*W)[NB + 1], int o) {
+    const int c = threadIdx.x & 31;
+    double x[32];
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+        double s = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+        for (int q = 0; q < r; ++q) s -= A[o + r][o + q] * x[q];
+        x[r] = (r >= c) ? s / A[o + r][o + r] : 0.0;
+        W[o + r][o + c] = x[r];
+    }
+}
+
+// C(32x32 at (ro,co) of Cm) = alpha * sum_k X[xr+i][xc+k] * Y(k,j) + beta*C, Y(k,j) = Yt ? Ym[yr+j][yc+k] : Ym[yr+k][yc+j];
+// all 128 threads, 8 outputs each
+__device__ __forceinline__ void mm32(double (*Cm)[NB + 1], int ro, int co, double alpha, double (*X)[NB + 1], int xr, int xc,
+                                     double (*Ym)[NB + 1], int yr, int yc, bool Yt, double beta, bool lower_only) {
+    for (int e = threadIdx.x; e < 1024; e += 128) {
+        const int i = e >> 5, j = e & 31;
+        if (lower_only && j > i) continue;
+        double s = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) s += X[xr + i][xc + k] * (Yt ? Ym[yr + j][yc + k] : Ym[yr + k][yc + j]);
+        Cm[ro + i][co + j] = alpha * s + (beta != 0.0 ? beta * Cm[ro + i][co + j] : 0.0);
+    }
+}
+
+// factor the nb x nb diagonal block at (k0,k0) in place (lower), invert the factor into Linv (row-major 64 x 64, zero
+// upper triangle), accumulate logdet.  The 64 x 64 block is handled as 2 x 2 blocks of 32: warp-level Cholesky and
+// triangular inverse on the diagonal blocks, 32^3 products by the whole CTA in between.  Rows/cols >= nb are padded
+// with the identity.
+__global__ void __launch_bounds__(128)
 potf2_trti_kernel(double* __restrict__ S, int64_t ld, int k0, int nb, double* __restrict__ Linv,
                   double* __restrict__ logdet, int* __restrict__ flag, int first) {
     extern __shared__ double sm_potf[];
     double (*A)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm_potf);
     double (*W)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm_potf + NB * (NB + 1));
+    double (*T)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm_potf + 2 * NB * (NB + 1));
     __shared__ int bad;
-    const int tid = threadIdx.x;
-    if (tid == 0) bad = 0;
-    for (int e = tid; e < NB * NB; e += 256) {
+    __shared__ double ldsum;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) { bad = 0; ldsum = 0.0; }
+    for (int e = tid; e < NB * NB; e += 128) {
         const int r = e / NB, c = e % NB;
         A[r][c] = (r < nb && c < nb && c <= r) ? S[static_cast<int64_t>(k0 + r) * ld + k0 + c] : (r == c ? 1.0 : 0.0);
         W[r][c] = 0.0;
     }
     __syncthreads();
-    double ld_acc = 0.0;
-    for (int c = 0; c < nb; ++c) {
-        const double piv = A[c][c];
-        if (!(piv > 0.0)) {
-            if (tid == 0) bad = 1;
-            __syncthreads();
-            break;
-        }
-        const double l = sqrt(piv);
-        ld_acc += 2.0 * log(l);
-        __syncthreads();                       // everyone has read the pivot
-        if (tid == 0) A[c][c] = l;
-        for (int r = c + 1 + tid; r < nb; r += 256) A[r][c] /= l;
+    double ld2 = 0.0;
+    if (warp == 0) {                              // L11, W11
+        const bool ok = chol32(A, 0, &ld2);
+        if (!ok && tid == 0) bad = 1;
+        if (ok) trinv32(A, W, 0);
+    }
+    __syncthreads();
+    if (!bad) {
+        mm32(T, 32, 0, 1.0, A, 32, 0, W, 0, 0, true, 0.0, false);       // T21 = A21 * W11'  (= L21)
         __syncthreads();
-        // trailing update of the lower triangle: A[r][q] -= A[r][c]*A[q][c], r >= q > c
-        const int rem = nb - c - 1;
-        for (int e = tid; e < rem * rem; e += 256) {
-            const int r = c + 1 + e / rem, q = c + 1 + e % rem;
-            if (q <= r) A[r][q] -= A[r][c] * A[q][c];
+        for (int e = tid; e < 1024; e += 128) A[32 + (e >> 5)][e & 31] = T[32 + (e >> 5)][e & 31];
+        __syncthreads();
+        mm32(A, 32, 32, -1.0, A, 32, 0, A, 32, 0, true, 1.0, true);     // A22 -= L21 L21'  (lower)
+        __syncthreads();
+        if (warp == 0) {                          // L22, W22
+            const bool ok = chol32(A, 32, &ld2);
+            if (!ok && tid == 0) bad = 1;
+            if (ok) trinv32(A, W, 32);
         }
         __syncthreads();
     }
@@ -53,23 +108,18 @@ potf2_trti_kernel(double* __restrict__ S, int64_t ld, int k0, int nb, double* __
         if (tid == 0) *flag = 1;
         return;
     }
-    // W = A^{-1} (lower): thread j solves column j by forward substitution
-    if (tid < nb) {
-        const int j = tid;
-        W[j][j] = 1.0 / A[j][j];
-        for (int r = j + 1; r < nb; ++r) {
-            double s = 0.0;
-            for (int q = j; q < r; ++q) s += A[r][q] * W[q][j];
-            W[r][j] = -s / A[r][r];
-        }
-    }
+    mm32(T, 32, 0, 1.0, A, 32, 0, W, 0, 0, false, 0.0, false);          // T21 = L21 * W11
     __syncthreads();
-    for (int e = tid; e < NB * NB; e += 256) {
+    mm32(W, 32, 0, -1.0, W, 32, 32, T, 32, 0, false, 0.0, false);       // W21 = -W22 * T21
+    __syncthreads();
+    if (tid == 0) ldsum = ld2;                    // both chol32 calls ran on warp 0: lane 0 holds the full sum
+    __syncthreads();
+    for (int e = tid; e < NB * NB; e += 128) {
         const int r = e / NB, c = e % NB;
-        Linv[e] = (r < nb && c < nb) ? W[r][c] : 0.0;
+        Linv[e] = (r < nb && c < nb && c <= r) ? W[r][c] : 0.0;
         if (r < nb && c < nb && c <= r) S[static_cast<int64_t>(k0 + r) * ld + k0 + c] = A[r][c];
     }
-    if (tid == 0) *logdet = (first ? 0.0 : *logdet) + ld_acc;
+    if (tid == 0) *logdet = (first ? 0.0 : *logdet) + ldsum;
 }
 
 __global__ void zero_kernel(double* p, int64_t n) {
@@ -109,7 +159,7 @@ int spd_inverse(double* S, int m, int MP, double* Sinv, double* d_logdet, SolveW
     const int nblk = static_cast<int>(ceil_div(m, NB));
     const int64_t ld = MP;
     int rc;
-    constexpr size_t kPotfSmem = sizeof(double) * 2 * NB * (NB + 1);
+    constexpr size_t kPotfSmem = sizeof(double) * 3 * NB * (NB + 1);
     static bool configured = false;
     if (!configured) {
         GPZ_CUDA(cudaFuncSetAttribute(potf2_trti_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kPotfSmem)));
@@ -120,7 +170,7 @@ int spd_inverse(double* S, int m, int MP, double* Sinv, double* d_logdet, SolveW
         const int k0 = kb * NB;
         const int nb = (m - k0 < NB) ? (m - k0) : NB;
         double* Lk = ws.Linv + static_cast<int64_t>(kb) * NB * NB;
-        potf2_trti_kernel<<<1, 256, kPotfSmem, st>>>(S, ld, k0, nb, Lk, d_logdet, ws.flag, kb == 0);
+        potf2_trti_kernel<<<1, 128, kPotfSmem, st>>>(S, ld, k0, nb, Lk, d_logdet, ws.flag, kb == 0);
         GPZ_KERNEL_CHECK();
         ++*launches;
         const int rem = m - k0 - nb;
