@@ -879,7 +879,7 @@ int forward_and_solve(gpz_ctx* c, const double* d_theta) {
                     ++c->launches;
                 }
                 if ((rc = ozaki_gram(phi, MP, static_cast<int>(MP), P.m, r1 - r0, c->opt_ozaki, c->ob + r0, c->d_scal, c->aug ? 1 : 0,
-                                     nchunks > 0, c->S, c->ozg_ws, st, &c->launches))) return rc;
+                                     nchunks > 0, c->S, c->ozg_ws, st, c->aux, c->oz_ev, &c->launches))) return rc;
                 if (timed) GPZ_CUDA(cudaEventRecord(c->kev[1], st));
                 continue;
             }
@@ -1035,7 +1035,7 @@ int eval_device(gpz_ctx* c, const double* d_theta, double* d_out) {
                 const int acc = ng > 1 ? 0 : (nchunks > 0);
                 const int red = ng > 1 ? 1 : (last ? 1 : 0);
                 if (fused) {
-                    if ((rc = atb_dphi(phi + (s0 - r0) * MP, c->H + (s0 - r0) * MP, MP, static_cast<int>(MP), c->tr.F + s0 * c->QP, c->QP,
+                    if ((rc = atb_dphi(phi + (s0 - r0) * MP, c->H + (s0 - r0) * MP, MP, static_cast<int>(MP), c->tr.F + s0 * c->QP, c->QP, P.q,
                                        c->cw + s0, c->dbeta + s0, c->w, P.v, 0, s1 - s0, c->fused_ns, c->atb_partial, c->colp, acc,
                                        ng > 1 ? (g > 0) : (nchunks > 0), red, c->Rm, st, &c->launches))) return rc;
                 } else {

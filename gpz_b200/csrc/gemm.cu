@@ -682,25 +682,33 @@ static int launch_atb_dphi(const double* Phi, const double* H, int64_t ld, const
     return GPZ_OK;
 }
 
-// QP in {32, 64, 96, 128}.  partial: nsplit * (MP/128) * 128 * QP doubles; colp: nsplit * 2 * MP doubles.
-int atb_dphi(const double* Phi, const double* H, int64_t ld, int MP, const double* F, int QP, const double* cw,
+// F rows have stride QP (multiple of 32, <= 128); only the first q feature columns are multiplied, rounded up to the
+// narrowest instantiated tile (24, 32, 48, 64, 72, 96 or 128 columns).
+// partial: nsplit * (MP/128) * 128 * QP doubles; colp: nsplit * 2 * MP doubles.
+int atb_dphi(const double* Phi, const double* H, int64_t ld, int MP, const double* F, int QP, int q, const double* cw,
              const double* dbeta, const double* w, const double* v, int64_t row0, int64_t row1, int nsplit, double* partial,
              double* colp, int accumulate, int col_accumulate, int reduce, double* R, cudaStream_t st, int64_t* launches) {
-    int rc;
-    switch (QP) {
-        case 32: rc = launch_atb_dphi<4>(Phi, H, ld, F, QP, cw, dbeta, w, v, row0, row1, nsplit, partial, colp, MP, accumulate, col_accumulate, st); break;
-        case 64: rc = launch_atb_dphi<8>(Phi, H, ld, F, QP, cw, dbeta, w, v, row0, row1, nsplit, partial, colp, MP, accumulate, col_accumulate, st); break;
-        case 96: rc = launch_atb_dphi<12>(Phi, H, ld, F, QP, cw, dbeta, w, v, row0, row1, nsplit, partial, colp, MP, accumulate, col_accumulate, st); break;
-        case 128: rc = launch_atb_dphi<16>(Phi, H, ld, F, QP, cw, dbeta, w, v, row0, row1, nsplit, partial, colp, MP, accumulate, col_accumulate, st); break;
-        default:
-            set_error("atb_dphi: unsupported feature width %d", QP);
-            return GPZ_ERR_USAGE;
+    int rc, TN;
+#define GPZ_DPHI(NT_)                                                                                                      \
+    TN = 8 * NT_;                                                                                                         \
+    rc = launch_atb_dphi<NT_>(Phi, H, ld, F, QP, cw, dbeta, w, v, row0, row1, nsplit, partial, colp, MP, accumulate, col_accumulate, st)
+    if (QP > 128 || q > QP) {
+        set_error("atb_dphi: unsupported feature width %d (q=%d)", QP, q);
+        return GPZ_ERR_USAGE;
     }
+    if (q <= 24) { GPZ_DPHI(3); }
+    else if (q <= 32) { GPZ_DPHI(4); }
+    else if (q <= 48 && QP >= 48) { GPZ_DPHI(6); }
+    else if (q <= 64) { GPZ_DPHI(8); }
+    else if (q <= 72 && QP >= 72) { GPZ_DPHI(9); }
+    else if (q <= 96) { GPZ_DPHI(12); }
+    else { GPZ_DPHI(16); }
+#undef GPZ_DPHI
     if (rc) return rc;
     ++*launches;
     if (reduce) {
         const int tm = MP / TILE;
-        atb_reduce_kernel<false><<<tm, 256, 0, st>>>(partial, nsplit, tm, 1, QP, R, QP);
+        atb_reduce_kernel<false><<<tm, 256, 0, st>>>(partial, nsplit, tm, 1, TN, R, QP);
         GPZ_KERNEL_CHECK();
         ++*launches;
     }

@@ -88,7 +88,7 @@ int tgemm(const double* Phi, int64_t ld, const double* Sinv, int MP, int m, int6
 int phi_gemm(const double* F, int64_t ldf, int kq, const double* W, int MP, int m, int64_t n, double* Phi, int ndot,
              const double* vec0, const double* vec1, double* part0, double* part1, int64_t part_ld, const double* ycol,
              cudaStream_t st, int64_t* launches);
-int atb_dphi(const double* Phi, const double* H, int64_t ld, int MP, const double* F, int QP, const double* cw,
+int atb_dphi(const double* Phi, const double* H, int64_t ld, int MP, const double* F, int QP, int q, const double* cw,
              const double* dbeta, const double* w, const double* v, int64_t row0, int64_t row1, int nsplit, double* partial,
              double* colp, int accumulate, int col_accumulate, int reduce, double* R, cudaStream_t st, int64_t* launches);
 int sgemm(int M, int N, int K, double alpha, const double* A, int64_t sAi, int64_t sAk, const double* B, int64_t sBk,
@@ -151,7 +151,8 @@ int64_t oz_workspace_bytes(int MP, int s, int64_t chunk_rows);
 int64_t oz_gram_workspace_bytes(int MP, int s, int64_t rows);
 // S (+)= PHI' diag(wgt) PHI over `rows` rows through the int8 tensor cores; scal[0] >= max wgt, scal[1] >= max |PHI[:, aug]|
 int ozaki_gram(const double* Phi, int64_t ld, int MP, int m, int64_t rows, int s, const double* wgt, const double* d_scal,
-               int aug, int accumulate, double* S, void* ws, cudaStream_t st, int64_t* launches);
+               int aug, int accumulate, double* S, void* ws, cudaStream_t st, cudaStream_t aux, cudaEvent_t* ev4,
+               int64_t* launches);
 int ozaki_tgemm(const double* Phi, int64_t ld, const double* Sinv, int MP, int m, int64_t n, int s, int64_t chunk_rows,
                 const double* rw, double* H, int accumulate, double* nu, const double* waug, double* pred, void* ws,
                 cudaStream_t st, cudaStream_t aux, cudaEvent_t* ev6, cudaEvent_t tev0, cudaEvent_t tev1, int64_t* launches);

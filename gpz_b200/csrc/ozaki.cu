@@ -381,7 +381,7 @@ int64_t oz_gram_workspace_bytes(int MP, int s, int64_t rows) {
 }
 
 int ozaki_gram(const double* Phi, int64_t ld, int MP, int m, int64_t rows, int s, const double* wgt, const double* d_scal,
-               int aug, int accumulate, double* S, void* ws, cudaStream_t st, int64_t* launches) {
+               int aug, int accumulate, double* S, void* ws, cudaStream_t st, cudaStream_t aux, cudaEvent_t* ev, int64_t* launches) {
     if (s < 2 || s > OZ_MAXS || static_cast<int64_t>(s) * OZG_CH * 127 * 127 >= 2147483647LL) {
         set_error("ozaki_gram: unsupported slice count %d", s);
         return GPZ_ERR_USAGE;
@@ -403,25 +403,55 @@ int ozaki_gram(const double* Phi, int64_t ld, int MP, int m, int64_t rows, int s
         Dl.D[e] = Dbuf[e];
     }
     void* cws = take(64 << 20);
-    // slices (the tail of the last chunk is zero-filled by the kernel: rows beyond `rows` read as 0)
-    dim3 gs(static_cast<unsigned>(static_cast<int64_t>(nch) * OZG_CH / 128), static_cast<unsigned>(MP / 32));
-    ozg_slice_kernel<<<gs, 256, 0, st>>>(Phi, ld, MP, m, rows, s, wgt, d_scal, aug, F, R);
-    GPZ_KERNEL_CHECK();
-    ++*launches;
     const int64_t rowstride = static_cast<int64_t>(s) * OZG_CH;          // bytes between consecutive j
     const int64_t bstride = static_cast<int64_t>(MP) * rowstride;        // bytes between chunks
-    for (int e = 2; e <= s + 1; ++e) {
-        const int K = (e - 1) * OZG_CH;
-        for (int J = 0; J * 256 < MP; ++J) {
-            const int n0 = J * 256;
-            const int N = (MP - n0 < 256) ? (MP - n0) : 256;
-            const int M = MP - n0;
-            int rc = i8gemm_tn_batched(F + static_cast<int64_t>(n0) * rowstride, rowstride, bstride,
-                                       R + static_cast<int64_t>(n0) * rowstride + static_cast<int64_t>(s - e + 1) * OZG_CH, rowstride, bstride,
-                                       Dbuf[e] + static_cast<int64_t>(n0) * MP + n0, MP, static_cast<int64_t>(MP) * MP, M, N, K, nch, cws,
-                                       64 << 20, st);
-            if (rc) return rc;
-            ++*launches;
+    // The chunks are processed in up to 4 groups: the HBM-bound slicing of groups 1.. (stream aux) runs under the int8
+    // GEMMs of the earlier groups (stream st).  Every chunk has its own slice and D storage, so a group only needs its
+    // "slices ready" event.  ev: >= 4 events.
+    const int ngroups = nch >= 8 ? 4 : 1;
+    const int cpg = static_cast<int>(ceil_div(nch, ngroups));
+    auto slice_group = [&](int gidx, cudaStream_t ss) {
+        const int c0 = gidx * cpg;
+        const int c1 = (c0 + cpg < nch) ? c0 + cpg : nch;
+        if (c1 <= c0) return;
+        const int64_t r0 = static_cast<int64_t>(c0) * OZG_CH;
+        int64_t rcount = (static_cast<int64_t>(c1) * OZG_CH < rows ? static_cast<int64_t>(c1) * OZG_CH : rows) - r0;
+        if (rcount < 0) rcount = 0;
+        dim3 gs(static_cast<unsigned>(static_cast<int64_t>(c1 - c0) * OZG_CH / 128), static_cast<unsigned>(MP / 32));
+        ozg_slice_kernel<<<gs, 256, 0, ss>>>(Phi + r0 * ld, ld, MP, m, rcount, s, wgt + r0, d_scal, aug,
+                                             F + static_cast<int64_t>(c0) * bstride, R + static_cast<int64_t>(c0) * bstride);
+        ++*launches;
+    };
+    if (ngroups > 1) {
+        GPZ_CUDA(cudaEventRecord(ev[0], st));                            // PHI / weights / scales are ready
+        GPZ_CUDA(cudaStreamWaitEvent(aux, ev[0], 0));
+        for (int gidx = 1; gidx < ngroups; ++gidx) {
+            slice_group(gidx, aux);
+            GPZ_CUDA(cudaEventRecord(ev[gidx], aux));
+        }
+    }
+    slice_group(0, st);
+    GPZ_KERNEL_CHECK();
+    for (int gidx = 0; gidx < ngroups; ++gidx) {
+        const int c0 = gidx * cpg;
+        const int c1 = (c0 + cpg < nch) ? c0 + cpg : nch;
+        if (c1 <= c0) break;
+        if (gidx > 0) GPZ_CUDA(cudaStreamWaitEvent(st, ev[gidx], 0));
+        for (int e = 2; e <= s + 1; ++e) {
+            const int K = (e - 1) * OZG_CH;
+            for (int J = 0; J * 256 < MP; ++J) {
+                const int n0 = J * 256;
+                const int N = (MP - n0 < 256) ? (MP - n0) : 256;
+                const int M = MP - n0;
+                int rc = i8gemm_tn_batched(F + static_cast<int64_t>(c0) * bstride + static_cast<int64_t>(n0) * rowstride, rowstride, bstride,
+                                           R + static_cast<int64_t>(c0) * bstride + static_cast<int64_t>(n0) * rowstride +
+                                               static_cast<int64_t>(s - e + 1) * OZG_CH,
+                                           rowstride, bstride,
+                                           Dbuf[e] + static_cast<int64_t>(c0) * MP * MP + static_cast<int64_t>(n0) * MP + n0, MP,
+                                           static_cast<int64_t>(MP) * MP, M, N, K, c1 - c0, cws, 64 << 20, st);
+                if (rc) return rc;
+                ++*launches;
+            }
         }
     }
     dim3 gc(static_cast<unsigned>(ceil_div(MP, 256)), static_cast<unsigned>(MP));
