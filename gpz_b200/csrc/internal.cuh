@@ -158,3 +158,16 @@ int ozaki_tgemm(const double* Phi, int64_t ld, const double* Sinv, int MP, int m
                 cudaStream_t st, cudaStream_t aux, cudaEvent_t* ev6, cudaEvent_t tev0, cudaEvent_t tev1, int64_t* launches);
 
 }  // namespace gpz
+
+namespace gpz {
+// ---- ozmma.cu: hand-written tcgen05 (cta_group::2, TMA, TMEM) digit-level GEMM with on-chip level folding
+bool ozmma_available();
+int ozmma_pairs();
+int64_t ozmma_partial_doubles(int rowsA, int rowsB, int lower, int nchunks, int pairs_limit);
+int ozmma_gemm_nt(const int8_t* A, const int64_t strA[3], int rowsA, const int8_t* B, const int64_t strB[3], int rowsB, int s, int emax,
+                  int kchunk, int nchunks, int lower, double* partial, const double* sr, const double* sc, double scale, int accumulate,
+                  double* out, int64_t ldo, int pairs_limit, cudaStream_t st, int64_t* launches);
+int ozmma_tgemm(const int8_t* A8, const int8_t* B8, int MP, int s, int emax, int64_t rows, const double* ea, const double* eb,
+                const double* Phi, int64_t ld, const double* rw, double* H, int accumulate, double* nupart, int64_t nu_ld, int aug_col,
+                double* pred, cudaStream_t st, int64_t* launches);
+}  // namespace gpz

@@ -1,0 +1,588 @@
+// Hand-written tcgen05 kernel for the error-free int8-digit (Ozaki) fp64 GEMMs of the NLML evaluation:
+//     T = PHI * iSigma          (GPz/GPz.m:69,72)   epilogue: nu_i = sum_j PHI_ij T_ij, H = rw_i PHI .* T, spare column -> PHI*w
+//     S = PHI' diag(w) PHI      (GPz/GPz.m:63-65)   epilogue: fp64 partial tiles, reduced in fixed order by ozmma_gram_reduce
+//
+// Both operands are given as s signed 8-bit digits (two's-complement digit extraction, ozaki.cu):
+//     a = sa * sum_t A_t 256^-(t-1),   b = sb * sum_u B_u 256^-(u-1),   A_t, B_u in [-128, 127].
+// The product is sum over levels e = t+u of 256^-(e-2) * (A_t . B_u); every digit product is an EXACT int8 x int8 -> int32
+// tensor-core GEMM (tcgen05.mma kind::i8, accumulators in TMEM).  Unlike a chain of library GEMMs (one int32 output per
+// level, summed by a separate kernel) this kernel keeps the whole level loop on chip:
+//   * one CTA PAIR (cta_group::2, UMMA 256 x 128 x 32) owns a 256 x 128 output tile; each CTA holds 128 rows;
+//   * warp 0 (one lane) streams the digit tiles with TMA (4-D tensor maps {k, digit, row, chunk}, 128B swizzle) through an
+//     8-stage mbarrier pipeline; warp 1 of the leader CTA (one lane) issues the MMAs of all digit pairs of a level into
+//     one TMEM accumulator; TMEM holds two accumulators so level e-1 is multiplied while level e is folded;
+//   * 8 epilogue warps read the finished level with tcgen05.ld and fold it into an fp64 running sum held in REGISTERS
+//     (128 x 128 doubles per CTA = 64 per thread), smallest level first, so the int32 level results never touch HBM;
+//   * after the last level of the tile the same warps apply the GEMM-specific epilogue directly from registers.
+// Work is partitioned statically (tile-major, K-chunk-minor units split evenly over the CTA pairs, "stream-K"), so results
+// are bit-reproducible.  K per chunk is bounded by the caller so that no int32 accumulator can overflow.
+#include <cuda.h>
+
+#include "internal.cuh"
+
+namespace gpz {
+namespace {
+
+constexpr int OM_STAGES = 8;
+constexpr int OM_A_BYTES = 128 * 128;                 // 128 rows x 128 K-bytes per CTA
+constexpr int OM_B_BYTES = 64 * 128;                  // this CTA's half of the 128 B rows
+constexpr int OM_STAGE_BYTES = OM_A_BYTES + OM_B_BYTES;
+constexpr int OM_BAR_OFF = OM_STAGES * OM_STAGE_BYTES;
+constexpr int OM_SMEM_BYTES = OM_BAR_OFF + 256 + 1024;   // barriers + tmem slot, + slack for the 1024-byte alignment
+constexpr int OM_THREADS = 320;                       // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue
+constexpr uint32_t OM_TMEM_COLS = 256;                // two 128-column int32 accumulators
+// instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D = S32, A = B = signed 8 bit, both K-major,
+// N = 128 (>>3 at bit 17), M = 256 (>>4 at bit 24)
+constexpr uint32_t OM_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
+
+struct OzmmaArgs {
+    int s, emin, emax;        // digits per operand; levels emax, emax-1, .., emin are accumulated (weight 256^-(e-emin))
+    int kblocks;              // K bytes per chunk / 128
+    int tiles_n;              // 128-column tiles
+    int ntiles;               // number of (256-row, 128-column) tiles in the list
+    int nchunks;              // K chunks (fp64-folded one after the other)
+    int lower;                // tile list = tiles touching the lower triangle (Gram); else all tiles_m x tiles_n
+    int mode;                 // 0: fp64 partial tiles, 1: T-GEMM epilogue
+    // mode 1
+    const double* ea;         // [rows] row scales (including 256^-1 .. see ozaki.cu)
+    const double* eb;         // [cols] column scales
+    const double* Phi;        // [rows][ld]
+    int64_t ld, rows;
+    const double* rw;         // [rows] or null
+    double* H;                // [rows][ld] or null
+    int accumulate;
+    double* nupart;           // [2*tiles_n][nu_ld]
+    int64_t nu_ld;
+    int aug_col;              // -1: none
+    double* pred;             // [rows]
+    // mode 0
+    double* partial;          // [npairs*maxseg][256*128]
+    int maxseg;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_cta(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// bounded wait: a protocol bug traps (the launch fails) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity)) {
+        if (clock64() - t0 > 20000000000LL) __trap();     // ~10 s
+    }
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t smem_dst, uint32_t bar_cluster, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc2(uint32_t slot_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], 256 x 128 x 32 int8, both CTAs of the pair
+__device__ __forceinline__ void umma_i8_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    const uint32_t z = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z)
+        : "memory");
+}
+// arrive (once) on the mbarrier at the same smem offset in both CTAs when all MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+        "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile written by TMA with the 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart
+// (cute/arch/mma_sm100_desc.hpp SmemDescriptor: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 | SWIZZLE_128B (2) <<61)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+
+__device__ __forceinline__ void decode_tile(const OzmmaArgs& a, int tile, int& mt, int& nt) {
+    if (!a.lower) {
+        mt = tile / a.tiles_n;
+        nt = tile - mt * a.tiles_n;
+        return;
+    }
+    int acc = 0;
+    for (mt = 0;; ++mt) {
+        const int cnt = min(a.tiles_n, 2 * (mt + 1));
+        if (tile < acc + cnt) {
+            nt = tile - acc;
+            return;
+        }
+        acc += cnt;
+    }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OM_THREADS, 1)
+ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const OzmmaArgs a) {
+    extern __shared__ uint8_t om_smem_raw[];
+    const uint32_t raw = smem_u32(om_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* gbase = om_smem_raw + (base - raw);
+    const uint32_t bar0 = base + OM_BAR_OFF;
+    // full[i] = bar0 + 8 i (leader's are used), empty[i] = bar0 + 64 + 8 i, tfull[b] = bar0 + 128 + 8 b, tempty[b] = bar0 + 144 + 8 b
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + OM_BAR_OFF + 192);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+
+    cluster_sync_all();                                   // both CTAs resident before the pair-wide TMEM allocation
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < OM_STAGES; ++i) {
+            mbar_init(bar0 + 8 * i, 2);                   // one arrive per CTA's producer (+ 2 x stage bytes of TMA)
+            mbar_init(bar0 + 64 + 8 * i, 1);              // one MMA commit
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar0 + 128 + 8 * b, 1);             // one MMA commit
+            mbar_init(bar0 + 144 + 8 * b, 16);            // 8 epilogue warps x 2 CTAs
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc2(smem_u32(const_cast<uint32_t*>(tmem_slot)), OM_TMEM_COLS);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int64_t U = static_cast<int64_t>(a.ntiles) * a.nchunks;
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int64_t u0 = U * pair / npairs, u1 = U * (pair + 1) / npairs;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (one lane per CTA)
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t u = u0; u < u1; ++u) {
+                const int tile = static_cast<int>(u / a.nchunks), chunk = static_cast<int>(u - static_cast<int64_t>(tile) * a.nchunks);
+                int mt, nt;
+                decode_tile(a, tile, mt, nt);
+                const int rowA = mt * 256 + static_cast<int>(rank) * 128, rowB = nt * 128 + static_cast<int>(rank) * 64;
+                for (int e = a.emax; e >= a.emin; --e) {
+                    const int tlo = max(1, e - a.s), thi = min(a.s, e - 1);
+                    for (int t = tlo; t <= thi; ++t) {
+                        const int uu = e - t;
+                        for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
+                            const uint32_t stage = it % OM_STAGES, ph = (it / OM_STAGES) & 1u;
+                            mbar_wait(bar0 + 64 + 8 * stage, ph ^ 1u);
+                            const uint32_t sA = base + stage * OM_STAGE_BYTES, sB = sA + OM_A_BYTES;
+                            const uint32_t full_leader = mapa_cta(bar0 + 8 * stage, 0);
+                            if (rank == 0) mbar_arrive_expect_tx(bar0 + 8 * stage, 2 * OM_STAGE_BYTES);
+                            else mbar_arrive_cluster(full_leader);
+                            tma_load_4d(&mapA, sA, full_leader, kb * 128, t - 1, rowA, chunk);
+                            tma_load_4d(&mapB, sB, full_leader, kb * 128, uu - 1, rowB, chunk);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (one lane of the leader CTA)
+        if (rank == 0 && lane == 0) {
+            uint32_t it = 0, L = 0;
+            for (int64_t u = u0; u < u1; ++u) {
+                for (int e = a.emax; e >= a.emin; --e, ++L) {
+                    const uint32_t buf = L & 1u;
+                    mbar_wait(bar0 + 144 + 8 * buf, ((L >> 1) & 1u) ^ 1u);       // epilogue has drained this accumulator
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + buf * 128u;
+                    const int npair = min(a.s, e - 1) - max(1, e - a.s) + 1;
+                    uint32_t acc = 0;
+                    for (int j = 0; j < npair * a.kblocks; ++j, ++it) {
+                        const uint32_t stage = it % OM_STAGES, ph = (it / OM_STAGES) & 1u;
+                        mbar_wait(bar0 + 8 * stage, ph);                          // both CTAs' tiles have landed
+                        tc_fence_after();
+                        const uint32_t sA = base + stage * OM_STAGE_BYTES, sB = sA + OM_A_BYTES;
+                        const uint64_t ad = umma_desc_sw128(sA), bd = umma_desc_sw128(sB);
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) {                         // 4 x 32 K-bytes inside the swizzle atom
+                            umma_i8_2cta(d_tmem, ad + 2 * k4, bd + 2 * k4, OM_IDESC, acc);
+                            acc = 1;
+                        }
+                        umma_commit_pair(bar0 + 64 + 8 * stage);                 // frees the smem stage in both CTAs
+                    }
+                    umma_commit_pair(bar0 + 128 + 8 * buf);                       // level finished -> epilogue warps
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ epilogue warps: fold levels in fp64 registers
+        const int q = warp & 3;                 // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;       // which 64 of the 128 accumulator columns
+        const int rloc = q * 32 + lane;         // row inside this CTA's 128 rows
+        double st[64];
+        uint32_t L = 0;
+        int cur_tile = -1;
+        const uint32_t tempty_leader0 = mapa_cta(bar0 + 144, 0);
+        for (int64_t u = u0; u < u1; ++u) {
+            __syncwarp();
+            const int tile = static_cast<int>(u / a.nchunks);
+            if (tile != cur_tile) {
+#pragma unroll
+                for (int c = 0; c < 64; ++c) st[c] = 0.0;
+                cur_tile = tile;
+            }
+            for (int e = a.emax; e >= a.emin; --e, ++L) {
+                const uint32_t buf = L & 1u;
+                mbar_wait(bar0 + 128 + 8 * buf, (L >> 1) & 1u);
+                tc_fence_after();
+                const double wgt = __longlong_as_double(static_cast<long long>(1023 - 8 * (e - a.emin)) << 52);   // 256^-(e-emin)
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 128u + static_cast<uint32_t>(half * 64);
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + hh * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) st[hh * 32 + c] = fma(static_cast<double>(static_cast<int>(v[c])), wgt, st[hh * 32 + c]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(tempty_leader0 + 8 * buf);
+            }
+            const bool last = (u + 1 == u1) || (static_cast<int>((u + 1) / a.nchunks) != tile);
+            if (!last) continue;
+            int mt, nt;
+            decode_tile(a, tile, mt, nt);
+            if (a.mode == 0) {
+                const int seg = tile - static_cast<int>(u0 / a.nchunks);
+                double* out = a.partial + (static_cast<int64_t>(pair) * a.maxseg + seg) * (256 * 128) +
+                              static_cast<int64_t>(static_cast<int>(rank) * 128 + rloc) * 128 + half * 64;
+#pragma unroll
+                for (int c = 0; c < 64; c += 2) *reinterpret_cast<double2*>(out + c) = make_double2(st[c], st[c + 1]);
+            } else {
+                const int64_t gi = static_cast<int64_t>(mt) * 256 + static_cast<int64_t>(rank) * 128 + rloc;
+                if (gi < a.rows) {
+                    const double sa = a.ea[gi];
+                    const double wrow = a.rw != nullptr ? a.rw[gi] : 1.0;
+                    const int col0 = nt * 128 + half * 64;
+                    const double* ph = a.Phi + gi * a.ld + col0;
+                    double* hp = a.H != nullptr ? a.H + gi * a.ld + col0 : nullptr;
+                    const double* sbp = a.eb + col0;
+                    double rs = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 64; c += 2) {
+                        const double2 sb = *reinterpret_cast<const double2*>(sbp + c);
+                        const double2 p = *reinterpret_cast<const double2*>(ph + c);
+                        const double t0 = st[c] * (sa * sb.x), t1 = st[c + 1] * (sa * sb.y);
+                        double h0 = p.x * t0, h1 = p.y * t1;
+                        if (col0 + c == a.aug_col) { a.pred[gi] = t0; h0 = 0.0; }
+                        if (col0 + c + 1 == a.aug_col) { a.pred[gi] = t1; h1 = 0.0; }
+                        rs += h0 + h1;
+                        if (hp != nullptr) {
+                            double2 o = make_double2(wrow * h0, wrow * h1);
+                            if (a.accumulate) {
+                                const double2 old = *reinterpret_cast<const double2*>(hp + c);
+                                o.x += old.x;
+                                o.y += old.y;
+                            }
+                            *reinterpret_cast<double2*>(hp + c) = o;
+                        }
+                    }
+                    a.nupart[static_cast<int64_t>(nt * 2 + half) * a.nu_ld + gi] = rs;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc2(tmem_base, OM_TMEM_COLS);
+}
+
+// out[r][c] (+)= scale_r[r] * scale_c[c] * sum over the pairs that hold a segment of the tile, in pair order (fixed).
+// lower != 0: only c <= r is produced, and mirrored to out[c][r].
+__global__ void __launch_bounds__(256)
+ozmma_reduce_kernel(const double* __restrict__ partial, int maxseg, int npairs, int ntiles, int nchunks, int tiles_n, int lower, int R,
+                    int C, const double* __restrict__ scale_r, const double* __restrict__ scale_c, double scale, int accumulate,
+                    double* __restrict__ out, int64_t ldo) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    const int r = blockIdx.y;
+    if (c >= C || r >= R) return;
+    if (lower && c > r) return;
+    const int mt = r >> 8, nt = c >> 7;
+    int tile;
+    if (!lower) tile = mt * tiles_n + nt;
+    else {
+        int acc = 0;
+        for (int q = 0; q < mt; ++q) acc += min(tiles_n, 2 * (q + 1));
+        tile = acc + nt;
+    }
+    const int64_t U = static_cast<int64_t>(ntiles) * nchunks;
+    const int64_t x0 = static_cast<int64_t>(tile) * nchunks, x1 = x0 + nchunks;
+    int p = static_cast<int>(x0 * npairs / U);
+    while (p + 1 < npairs && U * (p + 1) / npairs <= x0) ++p;
+    while (p > 0 && U * p / npairs > x0) --p;
+    double sum = 0.0;
+    for (; p < npairs; ++p) {
+        const int64_t u0 = U * p / npairs, u1 = U * (p + 1) / npairs;
+        if (u0 >= x1) break;
+        if (u1 <= x0 || u1 == u0) continue;
+        const int seg = tile - static_cast<int>(u0 / nchunks);
+        sum += partial[(static_cast<int64_t>(p) * maxseg + seg) * (256 * 128) + static_cast<int64_t>(r & 255) * 128 + (c & 127)];
+    }
+    double v = sum * scale;
+    if (scale_r != nullptr) v *= scale_r[r];
+    if (scale_c != nullptr) v *= scale_c[c];
+    const int64_t o = static_cast<int64_t>(r) * ldo + c;
+    out[o] = (accumulate ? out[o] : 0.0) + v;
+    if (lower && c != r) {
+        const int64_t oT = static_cast<int64_t>(c) * ldo + r;
+        out[oT] = (accumulate ? out[oT] : 0.0) + v;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// int8 digits addressed as {k, digit, row, chunk}; strides in bytes (multiples of 16); box = 128 k-bytes x box_rows rows
+int make_map(CUtensorMap* map, const int8_t* ptr, const int64_t dims[4], const int64_t strides[3], int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (fn == nullptr) {
+        set_error("ozmma: cuTensorMapEncodeTiled is not available from this driver");
+        return GPZ_ERR_CUDA;
+    }
+    cuuint64_t gd[4] = {static_cast<cuuint64_t>(dims[0]), static_cast<cuuint64_t>(dims[1]), static_cast<cuuint64_t>(dims[2]),
+                        static_cast<cuuint64_t>(dims[3])};
+    cuuint64_t gs[3] = {static_cast<cuuint64_t>(strides[0]), static_cast<cuuint64_t>(strides[1]), static_cast<cuuint64_t>(strides[2])};
+    cuuint32_t box[4] = {128, 1, static_cast<cuuint32_t>(box_rows), 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<int8_t*>(ptr), gd, gs, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("ozmma: cuTensorMapEncodeTiled failed (%d) dims %lld %lld %lld %lld strides %lld %lld %lld", static_cast<int>(r),
+                  static_cast<long long>(dims[0]), static_cast<long long>(dims[1]), static_cast<long long>(dims[2]),
+                  static_cast<long long>(dims[3]), static_cast<long long>(strides[0]), static_cast<long long>(strides[1]),
+                  static_cast<long long>(strides[2]));
+        return GPZ_ERR_CUDA;
+    }
+    return GPZ_OK;
+}
+
+int g_pairs = -1;       // CTA pairs that can be co-resident (one CTA per SM)
+
+int resident_pairs() {
+    if (g_pairs > 0) return g_pairs;
+    if (cudaFuncSetAttribute(ozmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OM_SMEM_BYTES) != cudaSuccess) return -1;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(sms / 2 * 2));
+    cfg.blockDim = dim3(OM_THREADS);
+    cfg.dynamicSmemBytes = OM_SMEM_BYTES;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int ncl = 0;
+    if (cudaOccupancyMaxActiveClusters(&ncl, ozmma_kernel, &cfg) != cudaSuccess || ncl <= 0) {
+        cudaGetLastError();
+        ncl = sms / 2;
+    }
+    if (ncl > sms / 2) ncl = sms / 2;
+    g_pairs = ncl;
+    return g_pairs;
+}
+
+int count_tiles(int tiles_m, int tiles_n, int lower) {
+    if (!lower) return tiles_m * tiles_n;
+    int t = 0;
+    for (int mt = 0; mt < tiles_m; ++mt) t += (tiles_n < 2 * (mt + 1)) ? tiles_n : 2 * (mt + 1);
+    return t;
+}
+
+int launch(const CUtensorMap& mA, const CUtensorMap& mB, const OzmmaArgs& a, int npairs, cudaStream_t st) {
+    ozmma_kernel<<<dim3(static_cast<unsigned>(2 * npairs)), dim3(OM_THREADS), OM_SMEM_BYTES, st>>>(mA, mB, a);
+    GPZ_KERNEL_CHECK();
+    return GPZ_OK;
+}
+
+}  // namespace
+
+bool ozmma_available() { return encode_fn() != nullptr; }
+
+int ozmma_pairs() { return resident_pairs(); }
+
+int64_t ozmma_partial_doubles(int rowsA, int rowsB, int lower, int nchunks, int pairs_limit) {
+    int np = resident_pairs();
+    if (np <= 0) np = 1;
+    if (pairs_limit > 0 && pairs_limit < np) np = pairs_limit;
+    const int nt = count_tiles((rowsA + 255) / 256, (rowsB + 127) / 128, lower);
+    const int64_t U = static_cast<int64_t>(nt) * nchunks;
+    const int maxseg = static_cast<int>(ceil_div(ceil_div(U, np), nchunks)) + 1;
+    return static_cast<int64_t>(np) * maxseg * 256 * 128;
+}
+
+// Generic form (also the self-test entry): out[rowsA][rowsB] (+)= scale * sr[r] * sc[c] * sum_chunks sum_e 256^-(e-2) sum_{t+u=e} A_t B_u'
+// A, B: int8 digits addressed {k, digit, row, chunk} with byte strides strX = {digit, row, chunk}.
+int ozmma_gemm_nt(const int8_t* A, const int64_t strA[3], int rowsA, const int8_t* B, const int64_t strB[3], int rowsB, int s, int emax,
+                  int kchunk, int nchunks, int lower, double* partial, const double* sr, const double* sc, double scale, int accumulate,
+                  double* out, int64_t ldo, int pairs_limit, cudaStream_t st, int64_t* launches) {
+    if (s < 1 || s > 8 || kchunk % 128 != 0 || kchunk <= 0 || nchunks <= 0 || emax < 2 || emax > 2 * s) {
+        set_error("ozmma_gemm_nt: bad arguments (s=%d kchunk=%d nchunks=%d emax=%d)", s, kchunk, nchunks, emax);
+        return GPZ_ERR_USAGE;
+    }
+    int maxpairs = 0;
+    for (int e = 2; e <= emax; ++e) {
+        const int np = (s < e - 1 ? s : e - 1) - (1 > e - s ? 1 : e - s) + 1;
+        if (np > maxpairs) maxpairs = np;
+    }
+    if (static_cast<int64_t>(maxpairs) * kchunk * 16384 >= 2147483648LL) {
+        set_error("ozmma_gemm_nt: K chunk %d too long for exact int32 accumulation of %d digit pairs", kchunk, maxpairs);
+        return GPZ_ERR_USAGE;
+    }
+    int np = resident_pairs();                                           // also sets the dynamic smem attribute
+    if (np <= 0) {
+        set_error("ozmma: cannot configure the tcgen05 kernel: %s", cudaGetErrorString(cudaGetLastError()));
+        return GPZ_ERR_CUDA;
+    }
+    if (pairs_limit > 0 && pairs_limit < np) np = pairs_limit;
+    CUtensorMap mA, mB;
+    const int64_t dA[4] = {kchunk, s, rowsA, nchunks}, dB[4] = {kchunk, s, rowsB, nchunks};
+    int rc;
+    if ((rc = make_map(&mA, A, dA, strA, 128))) return rc;
+    if ((rc = make_map(&mB, B, dB, strB, 64))) return rc;
+    OzmmaArgs a = {};
+    a.s = s;
+    a.emin = 2;
+    a.emax = emax;
+    a.kblocks = kchunk / 128;
+    a.tiles_n = (rowsB + 127) / 128;
+    a.ntiles = count_tiles((rowsA + 255) / 256, a.tiles_n, lower);
+    a.nchunks = nchunks;
+    a.lower = lower;
+    a.mode = 0;
+    a.partial = partial;
+    const int64_t U = static_cast<int64_t>(a.ntiles) * nchunks;
+    a.maxseg = static_cast<int>(ceil_div(ceil_div(U, np), nchunks)) + 1;
+    if ((rc = launch(mA, mB, a, np, st))) return rc;
+    dim3 g(static_cast<unsigned>(ceil_div(rowsB, 256)), static_cast<unsigned>(rowsA));
+    ozmma_reduce_kernel<<<g, 256, 0, st>>>(partial, a.maxseg, np, a.ntiles, nchunks, a.tiles_n, lower, rowsA, rowsB, sr, sc, scale,
+                                           accumulate, out, ldo);
+    GPZ_KERNEL_CHECK();
+    if (launches) *launches += 2;
+    return GPZ_OK;
+}
+
+// T-GEMM with the fused epilogue over `rows` rows.  A8: [rows][s][MP] digits of PHI (row scales ea), B8: [s][MP][MP] digits of
+// iSigma columns, B8[j][u][l] = digit u of iSigma[l][j] (column scales eb).  nupart: [2*MP/128][nu_ld].
+int ozmma_tgemm(const int8_t* A8, const int8_t* B8, int MP, int s, int emax, int64_t rows, const double* ea, const double* eb,
+                const double* Phi, int64_t ld, const double* rw, double* H, int accumulate, double* nupart, int64_t nu_ld, int aug_col,
+                double* pred, cudaStream_t st, int64_t* launches) {
+    if (s < 1 || s > 8 || MP % 128 != 0 || static_cast<int64_t>(s) * MP * 16384 >= 2147483648LL) {
+        set_error("ozmma_tgemm: unsupported s=%d MP=%d", s, MP);
+        return GPZ_ERR_USAGE;
+    }
+    const int np = resident_pairs();
+    if (np <= 0) {
+        set_error("ozmma: cannot configure the tcgen05 kernel: %s", cudaGetErrorString(cudaGetLastError()));
+        return GPZ_ERR_CUDA;
+    }
+    CUtensorMap mA, mB;
+    const int64_t dA[4] = {MP, s, rows, 1}, sA[3] = {MP, static_cast<int64_t>(s) * MP, round_up(rows * s * MP, 16)};
+    const int64_t dB[4] = {MP, s, MP, 1}, sB[3] = {MP, static_cast<int64_t>(s) * MP, static_cast<int64_t>(s) * MP * MP};
+    int rc;
+    if ((rc = make_map(&mA, A8, dA, sA, 128))) return rc;
+    if ((rc = make_map(&mB, B8, dB, sB, 64))) return rc;
+    OzmmaArgs a = {};
+    a.s = s;
+    a.emin = 2;
+    a.emax = emax;
+    a.kblocks = MP / 128;
+    a.tiles_n = MP / 128;
+    a.ntiles = static_cast<int>(ceil_div(rows, 256)) * a.tiles_n;
+    a.nchunks = 1;
+    a.lower = 0;
+    a.mode = 1;
+    a.ea = ea;
+    a.eb = eb;
+    a.Phi = Phi;
+    a.ld = ld;
+    a.rows = rows;
+    a.rw = rw;
+    a.H = H;
+    a.accumulate = accumulate;
+    a.nupart = nupart;
+    a.nu_ld = nu_ld;
+    a.aug_col = aug_col;
+    a.pred = pred;
+    a.maxseg = 1;
+    if ((rc = launch(mA, mB, a, np, st))) return rc;
+    if (launches) ++*launches;
+    return GPZ_OK;
+}
+
+}  // namespace gpz
