@@ -461,7 +461,7 @@ struct gpz_ctx {
     int opt_tensor_phi = 1;         // 1: PHI = exp(F W) on the DMMA pipe; 0: direct-difference kernels
     int opt_fused_bp = 1;           // 1: fused dPHI + back-projection GEMM; 0: materialise dPHI first
     int opt_aug = 1;                // 1: spare-column trick (see aug)
-    int opt_ozaki = -1;             // >0: T-GEMM through the int8 tensor cores with this many 7-bit slices (ozaki.cu);
+    int opt_ozaki = -1;             // >0: T-GEMM through the int8 tensor cores with this many base-256 digits (ozaki.cu);
                                     // -1: default = 8 when the tcgen05 int8 GEMM was built in, else 0 (fp64 DMMA)
     void* oz_ws = nullptr;
     int64_t oz_chunk = 0, opt_oz_chunk = 0;
@@ -798,10 +798,10 @@ int ensure_workspace(gpz_ctx* c) {
         const int64_t sc = 2 * dd * MP + dd * P.m + static_cast<int64_t>(P.m) * P.d + 64;
         if ((rc = A(&c->scratch, sc))) return rc;
     }
-    if (c->opt_ozaki < 0) c->opt_ozaki = i8gemm_available() ? 8 : 0;
+    if (c->opt_ozaki < 0) c->opt_ozaki = ozmma_available() ? 7 : 0;
     if (c->opt_ozaki > 0) {
-        if (!i8gemm_available()) {
-            set_error("ozaki_slices: this build has no tcgen05 int8 GEMM (CUTLASS headers were not found at build time)");
+        if (!ozmma_available()) {
+            set_error("ozaki_slices: the driver does not export cuTensorMapEncodeTiled (needed by the tcgen05 digit GEMM)");
             return GPZ_ERR_USAGE;
         }
         if (c->opt_oz_chunk <= 0) c->opt_oz_chunk = 131072;
@@ -813,7 +813,7 @@ int ensure_workspace(gpz_ctx* c) {
         c->oz_ws = tmp;
     }
     if (c->opt_ozaki_gram < 0) c->opt_ozaki_gram = (c->opt_ozaki > 0 && k == 1) ? 1 : 0;
-    if (c->opt_ozaki_gram > 0 && (c->opt_ozaki <= 0 || c->opt_ozaki > 8 || k != 1)) c->opt_ozaki_gram = 0;   // 9 slices: T-GEMM only
+    if (c->opt_ozaki_gram > 0 && (c->opt_ozaki <= 0 || k != 1)) c->opt_ozaki_gram = 0;
     if ((rc = A(&c->d_scal, 8))) return rc;
     if (c->opt_ozaki_gram > 0) {
         double* tmp = nullptr;
@@ -990,7 +990,7 @@ int eval_device(gpz_ctx* c, const double* d_theta, double* d_out) {
             if (timed) GPZ_CUDA(cudaEventRecord(c->kev[2], st));
             if (c->opt_ozaki > 0) {
                 if ((rc = ozaki_tgemm(phi, MP, c->Sinv + static_cast<int64_t>(o) * MP * MP, static_cast<int>(MP), P.m, rows, c->opt_ozaki,
-                                      c->oz_chunk, c->ob + o * n + r0, c->H, o > 0, c->nupart + r0, c->aug ? c->w + o * MP : nullptr,
+                                      c->oz_chunk, c->ob + o * n + r0, c->H, o > 0, c->nupart + r0, n, c->aug ? c->w + o * MP : nullptr,
                                       c->aug ? c->pred + r0 : nullptr, c->oz_ws, st, c->aux, c->oz_ev, timed ? c->kev[4] : nullptr,
                                       timed ? c->kev[5] : nullptr, &c->launches))) return rc;
             } else {
@@ -999,7 +999,7 @@ int eval_device(gpz_ctx* c, const double* d_theta, double* d_out) {
             }
             if (timed) GPZ_CUDA(cudaEventRecord(c->kev[3], st));
             rows2_kernel<<<static_cast<unsigned>(ceil_div(rows, RB)), RB, 0, st>>>(P, o, c->tr.Y, c->tr.omega, n, r0, r1, c->pred,
-                                                                                 c->nupart, c->opt_ozaki > 0 ? 1 : ntn, c->lnbi, c->beta,
+                                                                                 c->nupart, ntn, c->lnbi, c->beta,
                                                                                  c->ob, c->nu, c->cw, c->dbeta, c->part2, 2 * k + 2);
             GPZ_KERNEL_CHECK();
             ++c->launches;
@@ -1935,8 +1935,8 @@ int gpz_set_option(gpz_ctx* c, const char* name, double value) {
             set_error("%s must be set before the first evaluation", name);
             return GPZ_ERR_USAGE;
         }
-        if (value != 0.0 && (value < 4.0 || value > 9.0)) {
-            set_error("ozaki_slices must be 0 (off) or 4..9");
+        if (value != 0.0 && (value < 3.0 || value > 7.0)) {
+            set_error("ozaki_slices must be 0 (off) or 3..7 (base-256 digits per operand)");
             return GPZ_ERR_USAGE;
         }
         c->opt_ozaki = static_cast<int>(value);

@@ -140,13 +140,7 @@ int predict_missing_diag(const Params& P, const double* X, const double* Psi, in
                          const double* prior, const double* w, const double* Sinv, double* mu, double* nu, double* beta_i,
                          double* gamma, double* Phi, cudaStream_t st, int64_t* launches);
 
-// ---- i8gemm_cutlass.cu / ozaki.cu
-bool i8gemm_available();
-int i8gemm_tn(const int8_t* A, int64_t lda, const int8_t* B, int64_t ldb, int32_t* D, int64_t ldd, int M, int N, int K,
-              void* workspace, size_t ws_bytes, cudaStream_t st);
-int i8gemm_tn_batched(const int8_t* A, int64_t lda, int64_t bsA, const int8_t* B, int64_t ldb, int64_t bsB, int32_t* D,
-                      int64_t ldd, int64_t bsD, int M, int N, int K, int batches, void* workspace, size_t ws_bytes,
-                      cudaStream_t st);
+// ---- ozaki.cu
 int64_t oz_workspace_bytes(int MP, int s, int64_t chunk_rows);
 int64_t oz_gram_workspace_bytes(int MP, int s, int64_t rows);
 // S (+)= PHI' diag(wgt) PHI over `rows` rows through the int8 tensor cores; scal[0] >= max wgt, scal[1] >= max |PHI[:, aug]|
@@ -154,7 +148,7 @@ int ozaki_gram(const double* Phi, int64_t ld, int MP, int m, int64_t rows, int s
                int aug, int accumulate, double* S, void* ws, cudaStream_t st, cudaStream_t aux, cudaEvent_t* ev4,
                int64_t* launches);
 int ozaki_tgemm(const double* Phi, int64_t ld, const double* Sinv, int MP, int m, int64_t n, int s, int64_t chunk_rows,
-                const double* rw, double* H, int accumulate, double* nu, const double* waug, double* pred, void* ws,
+                const double* rw, double* H, int accumulate, double* nupart, int64_t nu_ld, const double* waug, double* pred, void* ws,
                 cudaStream_t st, cudaStream_t aux, cudaEvent_t* ev6, cudaEvent_t tev0, cudaEvent_t tev1, int64_t* launches);
 
 }  // namespace gpz

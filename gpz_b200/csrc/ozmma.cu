@@ -14,8 +14,10 @@
 //   * 8 epilogue warps read the finished level with tcgen05.ld and fold it into an fp64 running sum held in REGISTERS
 //     (128 x 128 doubles per CTA = 64 per thread), smallest level first, so the int32 level results never touch HBM;
 //   * after the last level of the tile the same warps apply the GEMM-specific epilogue directly from registers.
-// Work is partitioned statically (tile-major, K-chunk-minor units split evenly over the CTA pairs, "stream-K"), so results
-// are bit-reproducible.  K per chunk is bounded by the caller so that no int32 accumulator can overflow.
+// Work units are (group of K chunks, tile), chunk-group major, dealt round-robin to the CTA pairs: at any time the pairs
+// work on neighbouring tiles of the same K window, so every digit byte is fetched from HBM once and re-streamed from L2
+// (a contiguous per-pair partition measured 21 GB of DRAM reads for 3 GB of operands).  The assignment is static, so
+// results are bit-reproducible.  K per chunk is bounded by the caller so that no int32 accumulator can overflow.
 #include <cuda.h>
 
 #include "internal.cuh"
@@ -28,7 +30,7 @@ constexpr int OM_A_BYTES = 128 * 128;                 // 128 rows x 128 K-bytes 
 constexpr int OM_B_BYTES = 64 * 128;                  // this CTA's half of the 128 B rows
 constexpr int OM_STAGE_BYTES = OM_A_BYTES + OM_B_BYTES;
 constexpr int OM_BAR_OFF = OM_STAGES * OM_STAGE_BYTES;
-constexpr int OM_SMEM_BYTES = OM_BAR_OFF + 256 + 1024;   // barriers + tmem slot, + slack for the 1024-byte alignment
+constexpr int OM_SMEM_BYTES = OM_BAR_OFF + 256 + 1024 + 1024;   // barriers + tmem slot, row sums, + slack for the 1024-byte alignment
 constexpr int OM_THREADS = 320;                       // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue
 constexpr uint32_t OM_TMEM_COLS = 256;                // two 128-column int32 accumulators
 // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D = S32, A = B = signed 8 bit, both K-major,
@@ -40,7 +42,9 @@ struct OzmmaArgs {
     int kblocks;              // K bytes per chunk / 128
     int tiles_n;              // 128-column tiles
     int ntiles;               // number of (256-row, 128-column) tiles in the list
-    int nchunks;              // K chunks (fp64-folded one after the other)
+    int nchunks;              // K chunks in total
+    int gchunks;              // K chunks per work unit (folded one after the other into the fp64 registers)
+    int ngroups;              // ceil(nchunks / gchunks); work unit u = group * ntiles + tile
     int lower;                // tile list = tiles touching the lower triangle (Gram); else all tiles_m x tiles_n
     int mode;                 // 0: fp64 partial tiles, 1: T-GEMM epilogue
     // mode 1
@@ -51,13 +55,12 @@ struct OzmmaArgs {
     const double* rw;         // [rows] or null
     double* H;                // [rows][ld] or null
     int accumulate;
-    double* nupart;           // [2*tiles_n][nu_ld]
+    double* nupart;           // [tiles_n][nu_ld]
     int64_t nu_ld;
     int aug_col;              // -1: none
     double* pred;             // [rows]
     // mode 0
-    double* partial;          // [npairs*maxseg][256*128]
-    int maxseg;
+    double* partial;          // [ngroups*ntiles][256*128]
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -179,6 +182,7 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const uint32_t bar0 = base + OM_BAR_OFF;
     // full[i] = bar0 + 8 i (leader's are used), empty[i] = bar0 + 64 + 8 i, tfull[b] = bar0 + 128 + 8 b, tempty[b] = bar0 + 144 + 8 b
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + OM_BAR_OFF + 192);
+    double* rowsum_sm = reinterpret_cast<double*>(gbase + OM_BAR_OFF + 256);      // [128]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
 
@@ -200,19 +204,20 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int64_t U = static_cast<int64_t>(a.ntiles) * a.nchunks;
+    const int U = a.ntiles * a.ngroups;
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-    const int64_t u0 = U * pair / npairs, u1 = U * (pair + 1) / npairs;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (one lane per CTA)
         if (lane == 0) {
             uint32_t it = 0;
-            for (int64_t u = u0; u < u1; ++u) {
-                const int tile = static_cast<int>(u / a.nchunks), chunk = static_cast<int>(u - static_cast<int64_t>(tile) * a.nchunks);
+            for (int u = pair; u < U; u += npairs) {
+                const int group = u / a.ntiles, tile = u - group * a.ntiles;
                 int mt, nt;
                 decode_tile(a, tile, mt, nt);
                 const int rowA = mt * 256 + static_cast<int>(rank) * 128, rowB = nt * 128 + static_cast<int>(rank) * 64;
+                const int c1 = min(a.nchunks, (group + 1) * a.gchunks);
+                for (int chunk = group * a.gchunks; chunk < c1; ++chunk)
                 for (int e = a.emax; e >= a.emin; --e) {
                     const int tlo = max(1, e - a.s), thi = min(a.s, e - 1);
                     for (int t = tlo; t <= thi; ++t) {
@@ -236,8 +241,10 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         // ------------------------------------------------------------------ MMA issuer (one lane of the leader CTA)
         if (rank == 0 && lane == 0) {
             uint32_t it = 0, L = 0;
-            for (int64_t u = u0; u < u1; ++u) {
-                for (int e = a.emax; e >= a.emin; --e, ++L) {
+            for (int u = pair; u < U; u += npairs) {
+                const int group = u / a.ntiles;
+                const int nlev = (min(a.nchunks, (group + 1) * a.gchunks) - group * a.gchunks) * (a.emax - a.emin + 1);
+                for (int lv = 0, e = a.emax; lv < nlev; ++lv, ++L, e = (e == a.emin ? a.emax : e - 1)) {
                     const uint32_t buf = L & 1u;
                     mbar_wait(bar0 + 144 + 8 * buf, ((L >> 1) & 1u) ^ 1u);       // epilogue has drained this accumulator
                     tc_fence_after();
@@ -269,17 +276,14 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         const int rloc = q * 32 + lane;         // row inside this CTA's 128 rows
         double st[64];
         uint32_t L = 0;
-        int cur_tile = -1;
         const uint32_t tempty_leader0 = mapa_cta(bar0 + 144, 0);
-        for (int64_t u = u0; u < u1; ++u) {
+        for (int u = pair; u < U; u += npairs) {
             __syncwarp();
-            const int tile = static_cast<int>(u / a.nchunks);
-            if (tile != cur_tile) {
+            const int group = u / a.ntiles, tile = u - group * a.ntiles;
 #pragma unroll
-                for (int c = 0; c < 64; ++c) st[c] = 0.0;
-                cur_tile = tile;
-            }
-            for (int e = a.emax; e >= a.emin; --e, ++L) {
+            for (int c = 0; c < 64; ++c) st[c] = 0.0;
+            const int nlev = (min(a.nchunks, (group + 1) * a.gchunks) - group * a.gchunks) * (a.emax - a.emin + 1);
+            for (int lv = 0, e = a.emax; lv < nlev; ++lv, ++L, e = (e == a.emin ? a.emax : e - 1)) {
                 const uint32_t buf = L & 1u;
                 mbar_wait(bar0 + 128 + 8 * buf, (L >> 1) & 1u);
                 tc_fence_after();
@@ -297,18 +301,16 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(tempty_leader0 + 8 * buf);
             }
-            const bool last = (u + 1 == u1) || (static_cast<int>((u + 1) / a.nchunks) != tile);
-            if (!last) continue;
             int mt, nt;
             decode_tile(a, tile, mt, nt);
             if (a.mode == 0) {
-                const int seg = tile - static_cast<int>(u0 / a.nchunks);
-                double* out = a.partial + (static_cast<int64_t>(pair) * a.maxseg + seg) * (256 * 128) +
+                double* out = a.partial + static_cast<int64_t>(u) * (256 * 128) +
                               static_cast<int64_t>(static_cast<int>(rank) * 128 + rloc) * 128 + half * 64;
 #pragma unroll
                 for (int c = 0; c < 64; c += 2) *reinterpret_cast<double2*>(out + c) = make_double2(st[c], st[c + 1]);
             } else {
                 const int64_t gi = static_cast<int64_t>(mt) * 256 + static_cast<int64_t>(rank) * 128 + rloc;
+                double rs = 0.0;
                 if (gi < a.rows) {
                     const double sa = a.ea[gi];
                     const double wrow = a.rw != nullptr ? a.rw[gi] : 1.0;
@@ -316,7 +318,6 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                     const double* ph = a.Phi + gi * a.ld + col0;
                     double* hp = a.H != nullptr ? a.H + gi * a.ld + col0 : nullptr;
                     const double* sbp = a.eb + col0;
-                    double rs = 0.0;
 #pragma unroll
                     for (int c = 0; c < 64; c += 2) {
                         const double2 sb = *reinterpret_cast<const double2*>(sbp + c);
@@ -336,8 +337,13 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                             *reinterpret_cast<double2*>(hp + c) = o;
                         }
                     }
-                    a.nupart[static_cast<int64_t>(nt * 2 + half) * a.nu_ld + gi] = rs;
                 }
+                // the two column halves of a row live in warps w and w+4: combine through smem (fixed order)
+                __syncwarp();
+                if (half == 1) rowsum_sm[rloc] = rs;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (half == 0 && gi < a.rows) a.nupart[static_cast<int64_t>(nt) * a.nu_ld + gi] = rs + rowsum_sm[rloc];
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
         }
     }
@@ -346,11 +352,11 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     if (warp == 2) tmem_dealloc2(tmem_base, OM_TMEM_COLS);
 }
 
-// out[r][c] (+)= scale_r[r] * scale_c[c] * sum over the pairs that hold a segment of the tile, in pair order (fixed).
+// out[r][c] (+)= scale * scale_r[r] * scale_c[c] * sum over the chunk groups of the tile's partials, in group order (fixed).
 // lower != 0: only c <= r is produced, and mirrored to out[c][r].
 __global__ void __launch_bounds__(256)
-ozmma_reduce_kernel(const double* __restrict__ partial, int maxseg, int npairs, int ntiles, int nchunks, int tiles_n, int lower, int R,
-                    int C, const double* __restrict__ scale_r, const double* __restrict__ scale_c, double scale, int accumulate,
+ozmma_reduce_kernel(const double* __restrict__ partial, int ngroups, int ntiles, int tiles_n, int lower, int R, int C,
+                    const double* __restrict__ scale_r, const double* __restrict__ scale_c, double scale, int accumulate,
                     double* __restrict__ out, int64_t ldo) {
     const int c = blockIdx.x * 256 + threadIdx.x;
     const int r = blockIdx.y;
@@ -364,19 +370,18 @@ ozmma_reduce_kernel(const double* __restrict__ partial, int maxseg, int npairs, 
         for (int q = 0; q < mt; ++q) acc += min(tiles_n, 2 * (q + 1));
         tile = acc + nt;
     }
-    const int64_t U = static_cast<int64_t>(ntiles) * nchunks;
-    const int64_t x0 = static_cast<int64_t>(tile) * nchunks, x1 = x0 + nchunks;
-    int p = static_cast<int>(x0 * npairs / U);
-    while (p + 1 < npairs && U * (p + 1) / npairs <= x0) ++p;
-    while (p > 0 && U * p / npairs > x0) --p;
+    const double* src = partial + static_cast<int64_t>(tile) * (256 * 128) + static_cast<int64_t>(r & 255) * 128 + (c & 127);
+    const int64_t gstride = static_cast<int64_t>(ntiles) * (256 * 128);
     double sum = 0.0;
-    for (; p < npairs; ++p) {
-        const int64_t u0 = U * p / npairs, u1 = U * (p + 1) / npairs;
-        if (u0 >= x1) break;
-        if (u1 <= x0 || u1 == u0) continue;
-        const int seg = tile - static_cast<int>(u0 / nchunks);
-        sum += partial[(static_cast<int64_t>(p) * maxseg + seg) * (256 * 128) + static_cast<int64_t>(r & 255) * 128 + (c & 127)];
+    int g = 0;
+    for (; g + 4 <= ngroups; g += 4) {
+        const double v0 = src[g * gstride], v1 = src[(g + 1) * gstride], v2 = src[(g + 2) * gstride], v3 = src[(g + 3) * gstride];
+        sum += v0;
+        sum += v1;
+        sum += v2;
+        sum += v3;
     }
+    for (; g < ngroups; ++g) sum += src[g * gstride];
     double v = sum * scale;
     if (scale_r != nullptr) v *= scale_r[r];
     if (scale_c != nullptr) v *= scale_c[c];
@@ -476,14 +481,22 @@ bool ozmma_available() { return encode_fn() != nullptr; }
 
 int ozmma_pairs() { return resident_pairs(); }
 
+// chunks per work unit: as many as keep >= ~12 rounds of units per CTA pair (load balance), at most 64
+static int group_chunks(int ntiles, int nchunks, int np) {
+    int g = static_cast<int>(static_cast<int64_t>(ntiles) * nchunks / (12LL * np));
+    if (g < 1) g = 1;
+    if (g > 64) g = 64;
+    if (g > nchunks) g = nchunks;
+    return g;
+}
+
 int64_t ozmma_partial_doubles(int rowsA, int rowsB, int lower, int nchunks, int pairs_limit) {
     int np = resident_pairs();
     if (np <= 0) np = 1;
     if (pairs_limit > 0 && pairs_limit < np) np = pairs_limit;
     const int nt = count_tiles((rowsA + 255) / 256, (rowsB + 127) / 128, lower);
-    const int64_t U = static_cast<int64_t>(nt) * nchunks;
-    const int maxseg = static_cast<int>(ceil_div(ceil_div(U, np), nchunks)) + 1;
-    return static_cast<int64_t>(np) * maxseg * 256 * 128;
+    const int g = group_chunks(nt, nchunks, np);
+    return static_cast<int64_t>(nt) * ceil_div(nchunks, g) * 256 * 128;
 }
 
 // Generic form (also the self-test entry): out[rowsA][rowsB] (+)= scale * sr[r] * sc[c] * sum_chunks sum_e 256^-(e-2) sum_{t+u=e} A_t B_u'
@@ -523,22 +536,22 @@ int ozmma_gemm_nt(const int8_t* A, const int64_t strA[3], int rowsA, const int8_
     a.tiles_n = (rowsB + 127) / 128;
     a.ntiles = count_tiles((rowsA + 255) / 256, a.tiles_n, lower);
     a.nchunks = nchunks;
+    a.gchunks = group_chunks(a.ntiles, nchunks, np);
+    a.ngroups = static_cast<int>(ceil_div(nchunks, a.gchunks));
     a.lower = lower;
     a.mode = 0;
     a.partial = partial;
-    const int64_t U = static_cast<int64_t>(a.ntiles) * nchunks;
-    a.maxseg = static_cast<int>(ceil_div(ceil_div(U, np), nchunks)) + 1;
     if ((rc = launch(mA, mB, a, np, st))) return rc;
     dim3 g(static_cast<unsigned>(ceil_div(rowsB, 256)), static_cast<unsigned>(rowsA));
-    ozmma_reduce_kernel<<<g, 256, 0, st>>>(partial, a.maxseg, np, a.ntiles, nchunks, a.tiles_n, lower, rowsA, rowsB, sr, sc, scale,
-                                           accumulate, out, ldo);
+    ozmma_reduce_kernel<<<g, 256, 0, st>>>(partial, a.ngroups, a.ntiles, a.tiles_n, lower, rowsA, rowsB, sr, sc, scale, accumulate, out,
+                                           ldo);
     GPZ_KERNEL_CHECK();
     if (launches) *launches += 2;
     return GPZ_OK;
 }
 
 // T-GEMM with the fused epilogue over `rows` rows.  A8: [rows][s][MP] digits of PHI (row scales ea), B8: [s][MP][MP] digits of
-// iSigma columns, B8[j][u][l] = digit u of iSigma[l][j] (column scales eb).  nupart: [2*MP/128][nu_ld].
+// iSigma columns, B8[j][u][l] = digit u of iSigma[l][j] (column scales eb).  nupart: [MP/128][nu_ld].
 int ozmma_tgemm(const int8_t* A8, const int8_t* B8, int MP, int s, int emax, int64_t rows, const double* ea, const double* eb,
                 const double* Phi, int64_t ld, const double* rw, double* H, int accumulate, double* nupart, int64_t nu_ld, int aug_col,
                 double* pred, cudaStream_t st, int64_t* launches) {
@@ -565,6 +578,8 @@ int ozmma_tgemm(const int8_t* A8, const int8_t* B8, int MP, int s, int emax, int
     a.tiles_n = MP / 128;
     a.ntiles = static_cast<int>(ceil_div(rows, 256)) * a.tiles_n;
     a.nchunks = 1;
+    a.gchunks = 1;
+    a.ngroups = 1;
     a.lower = 0;
     a.mode = 1;
     a.ea = ea;
@@ -579,7 +594,6 @@ int ozmma_tgemm(const int8_t* A8, const int8_t* B8, int MP, int s, int emax, int
     a.nu_ld = nu_ld;
     a.aug_col = aug_col;
     a.pred = pred;
-    a.maxseg = 1;
     if ((rc = launch(mA, mB, a, np, st))) return rc;
     if (launches) ++*launches;
     return GPZ_OK;

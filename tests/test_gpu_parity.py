@@ -285,9 +285,10 @@ def test_predict_with_missing_inputs(method, psi):
         L.predict_core(gm, theta, r.w, r.iSigma_w, Xt, Psi)          # missing rows without priors: loud failure
 
 
-@pytest.mark.parametrize("method,slices,tol", [("VC", 8, 1e-9), ("VD", 8, 1e-9), ("GL", 9, 1e-7), ("VC", 7, 1e-7)])
+@pytest.mark.parametrize("method,slices,tol", [("VC", 7, 1e-9), ("VD", 7, 1e-9), ("GL", 7, 1e-7), ("VC", 6, 1e-7)])
 def test_int8_tensor_core_tgemm_matches_fp64(method, slices, tol):
-    """T = PHI*iSigma as error-free int8 slice GEMMs on tcgen05 (ozaki.cu) against the fp64 DMMA path and the oracle."""
+    """T = PHI*iSigma and the Gram as error-free base-256 digit GEMMs on tcgen05 (ozaki.cu, ozmma.cu) against the fp64
+    DMMA path and the oracle."""
     model, theta, X, Y, Psi, omega, tr, va = problem(method, True, False, False, n=3000, d=5, m=140, seed=21)
     ref = O.GPz(theta, model, X, Y, None, omega, tr, va)
     gm = L.make_model(model.d, 1, model.m, method, True)
