@@ -296,11 +296,11 @@ def run_gpu(args):
                 bf16, src = 1400.0, "2 x 1.4 PFLOP/s: fallback sustained bf16 figure of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
             ach = tm["i8_gemms_ops"] / (tm["i8_gemms_ms"] * 1e-3) / 1e12
             roof = {"bound": "tensor",
-                    "kernel": "cutlass i8gemm (tcgen05.mma kind::i8, TMEM accumulators, TMA): the %d level GEMMs of T = PHI*iSigma, "
-                              "first row chunk" % tm["int8_slices"],
+                    "kernel": "ozmma_kernel (hand-written tcgen05.mma kind::i8 cta_group::2, TMA, TMEM double buffer; %d base-256 digits, "
+                              "levels folded in fp64 registers, fused nu/H epilogue): T = PHI*iSigma, one launch over all rows" % tm["int8_slices"],
                     "achieved": ach, "peak": 2.0 * bf16, "unit": "TFLOP/s", "frac": ach / (2.0 * bf16),
-                    "ops": "int8 multiply-adds x2 actually executed by those launches (K-concatenated slice pairs)",
-                    "traffic": prof.get("i8gemm_dram_bytes_first_chunk"), "peak_source": src,
+                    "ops": "int8 multiply-adds x2 executed by that launch (2 n MP^2 per digit pair, s(s+1)/2 pairs)",
+                    "traffic": prof.get("ozmma_tgemm_dram_bytes_per_launch"), "peak_source": src,
                     "kernel_ms": tm["i8_gemms_ms"], "executed_ops": tm["i8_gemms_ops"],
                     "int8_slices": tm["int8_slices"], "int8_gram": tm["int8_gram"]}
         else:

@@ -464,6 +464,9 @@ struct gpz_ctx {
     int opt_ozaki = -1;             // >0: T-GEMM through the int8 tensor cores with this many base-256 digits (ozaki.cu);
                                     // -1: default = 8 when the tcgen05 int8 GEMM was built in, else 0 (fp64 DMMA)
     void* oz_ws = nullptr;
+    int8_t *oz_D8 = nullptr, *oz_F8 = nullptr;     // base-256 digits of PHI (plain, row-scaled) and of w .* PHI (ozaki.cu)
+    double* oz_ea = nullptr;        // [rows] row scales of D8
+    int opt_ozaki_gs = -1;          // digits used by the Gram (<= opt_ozaki)
     int64_t oz_chunk = 0, opt_oz_chunk = 0;
     cudaStream_t aux = nullptr;     // second stream of the int8 T-GEMM pipeline
     cudaEvent_t oz_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -702,7 +705,9 @@ int ensure_workspace(gpz_ctx* c) {
     // row chunking: keep PHI and H (2 x rows x MP doubles) within ~55% of the free memory
     size_t free_b = 0, total_b = 0;
     GPZ_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    int64_t max_rows = static_cast<int64_t>(0.55 * static_cast<double>(free_b) / (16.0 * MP));
+    if (c->opt_ozaki < 0) c->opt_ozaki = ozmma_available() ? 7 : 0;
+    const double bytes_per_elt = 16.0 + (c->opt_ozaki > 0 ? 2.0 * c->opt_ozaki : 0.0);     // PHI, H (+ two digit sets)
+    int64_t max_rows = static_cast<int64_t>(0.55 * static_cast<double>(free_b) / (bytes_per_elt * MP));
     max_rows = max_rows / 1024 * 1024;
     if (max_rows < 1024) max_rows = 1024;
     int64_t need = n > nv ? n : nv;
@@ -798,28 +803,33 @@ int ensure_workspace(gpz_ctx* c) {
         const int64_t sc = 2 * dd * MP + dd * P.m + static_cast<int64_t>(P.m) * P.d + 64;
         if ((rc = A(&c->scratch, sc))) return rc;
     }
-    if (c->opt_ozaki < 0) c->opt_ozaki = ozmma_available() ? 7 : 0;
     if (c->opt_ozaki > 0) {
         if (!ozmma_available()) {
             set_error("ozaki_slices: the driver does not export cuTensorMapEncodeTiled (needed by the tcgen05 digit GEMM)");
             return GPZ_ERR_USAGE;
         }
-        if (c->opt_oz_chunk <= 0) c->opt_oz_chunk = 131072;
-        c->oz_chunk = nn < c->opt_oz_chunk ? nn : c->opt_oz_chunk;
-        GPZ_CUDA(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
-        for (auto& e : c->oz_ev) GPZ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        const int64_t rows = n < c->chunk_rows ? (n > 0 ? n : 1) : c->chunk_rows;
         double* tmp = nullptr;
-        if ((rc = A(&tmp, oz_workspace_bytes(static_cast<int>(MP), c->opt_ozaki, c->oz_chunk) / 8 + 1))) return rc;
+        if ((rc = A(&tmp, oz_workspace_bytes(static_cast<int>(MP), c->opt_ozaki) / 8 + 1))) return rc;
         c->oz_ws = tmp;
+        if ((rc = A(&tmp, oz_digit_bytes(static_cast<int>(MP), c->opt_ozaki, rows) / 8 + 1))) return rc;
+        c->oz_D8 = reinterpret_cast<int8_t*>(tmp);
+        if ((rc = A(&c->oz_ea, oz_padded_rows(rows)))) return rc;
     }
     if (c->opt_ozaki_gram < 0) c->opt_ozaki_gram = (c->opt_ozaki > 0 && k == 1) ? 1 : 0;
     if (c->opt_ozaki_gram > 0 && (c->opt_ozaki <= 0 || k != 1)) c->opt_ozaki_gram = 0;
+    // the Gram sums ~n terms per entry, so its digit truncation averages out: 6 digits (48 bits, 21 digit products) stay below
+    // the rounding of an fp64 accumulation; T = PHI iSigma (K = m terms) keeps all 7 (tools/oz_accuracy.py)
+    if (c->opt_ozaki_gs < 0) c->opt_ozaki_gs = 6;
+    if (c->opt_ozaki_gs > c->opt_ozaki) c->opt_ozaki_gs = c->opt_ozaki;
     if ((rc = A(&c->d_scal, 8))) return rc;
     if (c->opt_ozaki_gram > 0) {
         double* tmp = nullptr;
         const int64_t rows = n < c->chunk_rows ? (n > 0 ? n : 1) : c->chunk_rows;
-        if ((rc = A(&tmp, oz_gram_workspace_bytes(static_cast<int>(MP), c->opt_ozaki, rows) / 8 + 1))) return rc;
+        if ((rc = A(&tmp, oz_gram_workspace_bytes(static_cast<int>(MP), rows) / 8 + 1))) return rc;
         c->ozg_ws = tmp;
+        if ((rc = A(&tmp, oz_digit_bytes(static_cast<int>(MP), c->opt_ozaki, rows) / 8 + 1))) return rc;
+        c->oz_F8 = reinterpret_cast<int8_t*>(tmp);
         max_abs_kernel<<<1, 1024, 0, c->st>>>(c->tr.Y, n, c->d_scal + 1);
         GPZ_KERNEL_CHECK();
     }
@@ -878,8 +888,10 @@ int forward_and_solve(gpz_ctx* c, const double* d_theta) {
                     GPZ_KERNEL_CHECK();
                     ++c->launches;
                 }
-                if ((rc = ozaki_gram(phi, MP, static_cast<int>(MP), P.m, r1 - r0, c->opt_ozaki, c->ob + r0, c->d_scal, c->aug ? 1 : 0,
-                                     nchunks > 0, c->S, c->ozg_ws, st, c->aux, c->oz_ev, &c->launches))) return rc;
+                if ((rc = ozaki_digits(phi, MP, static_cast<int>(MP), P.m, r1 - r0, c->opt_ozaki, c->ob + r0, c->d_scal, c->aug ? 1 : 0,
+                                       c->oz_D8, c->oz_F8, c->oz_ea, st, &c->launches))) return rc;
+                if ((rc = ozaki_gram(c->oz_F8, c->oz_D8, static_cast<int>(MP), P.m, r1 - r0, c->opt_ozaki, c->opt_ozaki_gs, c->d_scal,
+                                     c->aug ? 1 : 0, nchunks > 0, c->S, c->ozg_ws, st, &c->launches))) return rc;
                 if (timed) GPZ_CUDA(cudaEventRecord(c->kev[1], st));
                 continue;
             }
@@ -989,10 +1001,14 @@ int eval_device(gpz_ctx* c, const double* d_theta, double* d_out) {
             const bool timed = (nchunks == 0 && o == 0);
             if (timed) GPZ_CUDA(cudaEventRecord(c->kev[2], st));
             if (c->opt_ozaki > 0) {
-                if ((rc = ozaki_tgemm(phi, MP, c->Sinv + static_cast<int64_t>(o) * MP * MP, static_cast<int>(MP), P.m, rows, c->opt_ozaki,
-                                      c->oz_chunk, c->ob + o * n + r0, c->H, o > 0, c->nupart + r0, n, c->aug ? c->w + o * MP : nullptr,
-                                      c->aug ? c->pred + r0 : nullptr, c->oz_ws, st, c->aux, c->oz_ev, timed ? c->kev[4] : nullptr,
-                                      timed ? c->kev[5] : nullptr, &c->launches))) return rc;
+                // the plain digits of this chunk are still there when PHI is resident and the Gram went through them
+                if (o == 0 && !(c->resident && c->opt_ozaki_gram > 0))
+                    if ((rc = ozaki_digits(phi, MP, static_cast<int>(MP), P.m, rows, c->opt_ozaki, nullptr, c->d_scal, 0, c->oz_D8, nullptr,
+                                           c->oz_ea, st, &c->launches))) return rc;
+                if ((rc = ozaki_tgemm(phi, MP, c->oz_D8, c->oz_ea, c->Sinv + static_cast<int64_t>(o) * MP * MP, static_cast<int>(MP), P.m,
+                                      rows, c->opt_ozaki, c->ob + o * n + r0, c->H, o > 0, c->nupart + r0, n,
+                                      c->aug ? c->w + o * MP : nullptr, c->aug ? c->pred + r0 : nullptr, c->oz_ws, st,
+                                      timed ? c->kev[4] : nullptr, timed ? c->kev[5] : nullptr, &c->launches))) return rc;
             } else {
                 if ((rc = tgemm(phi, MP, c->Sinv + static_cast<int64_t>(o) * MP * MP, static_cast<int>(MP), P.m, rows, c->ob + o * n + r0,
                                 c->H, o > 0, c->nupart + r0, n, c->aug ? c->pred + r0 : nullptr, st, &c->launches))) return rc;
@@ -1893,8 +1909,8 @@ int gpz_last_timing(gpz_ctx* c, double ms[12]) {
     ms[8] = ms[9] = ms[10] = ms[11] = 0.0;
     if (c->opt_ozaki > 0) {
         GPZ_CUDA(cudaEventElapsedTime(&t, c->kev[4], c->kev[5]));
-        ms[8] = t;                                              // the s int8 level GEMMs of row chunk 0
-        const double rows = static_cast<double>(c->tr.n < c->oz_chunk ? c->tr.n : c->oz_chunk);
+        ms[8] = t;                                              // the tcgen05 digit-GEMM launch of T = PHI iSigma (first chunk)
+        const double rows = static_cast<double>(c->tr.n < c->chunk_rows ? c->tr.n : c->chunk_rows);
         double levels = 0.0;
         for (int e = 2; e <= c->opt_ozaki + 1; ++e) levels += e - 1;
         ms[9] = 2.0 * rows * c->P.MP * c->P.MP * levels;        // int8 operations those GEMMs executed
@@ -1942,12 +1958,16 @@ int gpz_set_option(gpz_ctx* c, const char* name, double value) {
         c->opt_ozaki = static_cast<int>(value);
         return GPZ_OK;
     }
-    if (strcmp(name, "ozaki_chunk_rows") == 0) {
+    if (strcmp(name, "ozaki_gram_slices") == 0) {
         if (c->ws_ready) {
             set_error("%s must be set before the first evaluation", name);
             return GPZ_ERR_USAGE;
         }
-        c->opt_oz_chunk = static_cast<int64_t>(round_up(static_cast<int64_t>(value), 1024));
+        if (value < 2.0 || value > 7.0) {
+            set_error("ozaki_gram_slices must be 2..7 (and is capped by ozaki_slices)");
+            return GPZ_ERR_USAGE;
+        }
+        c->opt_ozaki_gs = static_cast<int>(value);
         return GPZ_OK;
     }
     if (strcmp(name, "ozaki_gram") == 0) {

@@ -140,16 +140,19 @@ int predict_missing_diag(const Params& P, const double* X, const double* Psi, in
                          const double* prior, const double* w, const double* Sinv, double* mu, double* nu, double* beta_i,
                          double* gamma, double* Phi, cudaStream_t st, int64_t* launches);
 
-// ---- ozaki.cu
-int64_t oz_workspace_bytes(int MP, int s, int64_t chunk_rows);
-int64_t oz_gram_workspace_bytes(int MP, int s, int64_t rows);
-// S (+)= PHI' diag(wgt) PHI over `rows` rows through the int8 tensor cores; scal[0] >= max wgt, scal[1] >= max |PHI[:, aug]|
-int ozaki_gram(const double* Phi, int64_t ld, int MP, int m, int64_t rows, int s, const double* wgt, const double* d_scal,
-               int aug, int accumulate, double* S, void* ws, cudaStream_t st, cudaStream_t aux, cudaEvent_t* ev4,
-               int64_t* launches);
-int ozaki_tgemm(const double* Phi, int64_t ld, const double* Sinv, int MP, int m, int64_t n, int s, int64_t chunk_rows,
+// ---- ozaki.cu: fp64 operands -> base-256 digits; the two n x m x m products through ozmma.cu
+int64_t oz_padded_rows(int64_t rows);
+int64_t oz_digit_bytes(int MP, int s, int64_t rows);
+int64_t oz_workspace_bytes(int MP, int s);
+int64_t oz_gram_workspace_bytes(int MP, int64_t rows);
+int ozaki_digits(const double* Phi, int64_t ld, int MP, int m, int64_t rows, int s, const double* wgt, const double* d_scal, int aug,
+                 int8_t* D8, int8_t* F8, double* ea, cudaStream_t st, int64_t* launches);
+// S (+)= PHI' diag(wgt) PHI over `rows` rows through the int8 tensor cores (digits from ozaki_digits)
+int ozaki_gram(const int8_t* F8, const int8_t* D8, int MP, int m, int64_t rows, int s, int gs, const double* d_scal, int aug,
+               int accumulate, double* S, void* ws, cudaStream_t st, int64_t* launches);
+int ozaki_tgemm(const double* Phi, int64_t ld, const int8_t* D8, const double* ea, const double* Sinv, int MP, int m, int64_t n, int s,
                 const double* rw, double* H, int accumulate, double* nupart, int64_t nu_ld, const double* waug, double* pred, void* ws,
-                cudaStream_t st, cudaStream_t aux, cudaEvent_t* ev6, cudaEvent_t tev0, cudaEvent_t tev1, int64_t* launches);
+                cudaStream_t st, cudaEvent_t tev0, cudaEvent_t tev1, int64_t* launches);
 
 }  // namespace gpz
 
@@ -159,8 +162,8 @@ bool ozmma_available();
 int ozmma_pairs();
 int64_t ozmma_partial_doubles(int rowsA, int rowsB, int lower, int nchunks, int pairs_limit);
 int ozmma_gemm_nt(const int8_t* A, const int64_t strA[3], int rowsA, const int8_t* B, const int64_t strB[3], int rowsB, int s, int emax,
-                  int kchunk, int nchunks, int lower, double* partial, const double* sr, const double* sc, double scale, int accumulate,
-                  double* out, int64_t ldo, int pairs_limit, cudaStream_t st, int64_t* launches);
+                  int kchunk, int nchunks, int lower, int mn_major, double* partial, const double* sr, const double* sc, double scale,
+                  int accumulate, double* out, int64_t ldo, int pairs_limit, cudaStream_t st, int64_t* launches);
 int ozmma_tgemm(const int8_t* A8, const int8_t* B8, int MP, int s, int emax, int64_t rows, const double* ea, const double* eb,
                 const double* Phi, int64_t ld, const double* rw, double* H, int accumulate, double* nupart, int64_t nu_ld, int aug_col,
                 double* pred, cudaStream_t st, int64_t* launches);

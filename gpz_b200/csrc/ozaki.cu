@@ -30,13 +30,35 @@ __device__ __forceinline__ int oz_digit(long long& I) {
     return d;
 }
 
-// ---- PHI rows -> digits A8[i][t][j] (K = j contiguous).  warp per row; lane handles 4 consecutive columns per step ----
+__device__ __forceinline__ double pow2_ceil(double v) {
+    int ex = 0;
+    if (v > 0.0) frexp(v, &ex);
+    return ldexp(1.0, ex);                      // v < 2^ex
+}
+
+// ---- one pass over the PHI rows -> both digit sets, row-major [i][t][j].  warp per row; lane handles 4 columns per step.
+//   D8: plain digits of PHI_ij 2^-E_i (per-row exponent E_i from the row maximum, ea[i] = 2^(E_i - 8)); columns >= m are 0.
+//       They are the A operand of T = PHI iSigma (K = j contiguous) AND the B operand of the Gram (MN-major, K = i).
+//   F8: digits of w_i 2^E_i PHI_ij 2^-Ef with the fixed exponent 2^Ef = 16 2^ceil(log2 max w) -- the A operand of the Gram:
+//       sum_i F_ij D_il = 2^-Ef sum_i w_i PHI_ij PHI_il, the row scale cancels inside the product.  Column m (aug) carries
+//       w_i 2^E_i y_i / (2^Ef cy), cy = 2^ceil(log2 max|y|), so that row m of the Gram is PHI'(w y)  (GPz/GPz.m:70).
+//   Rows in [n, n_pad) are zero-filled (the Gram contracts over whole 1024-row chunks).
 __global__ void __launch_bounds__(256)
-oz_slice_rows_kernel(const double* __restrict__ Phi, int64_t ld, int m, int MP, int64_t n, int s, int8_t* __restrict__ A8,
-                     double* __restrict__ ea) {
+oz_digits_kernel(const double* __restrict__ Phi, int64_t ld, int m, int MP, int64_t n, int64_t n_pad, int s, const double* __restrict__ wgt,
+                 const double* __restrict__ scal, int aug, int8_t* __restrict__ D8, int8_t* __restrict__ F8, double* __restrict__ ea) {
     const int lane = threadIdx.x & 31;
     const int64_t i = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-    if (i >= n) return;
+    if (i >= n_pad) return;
+    int8_t* dout = D8 + i * static_cast<int64_t>(s) * MP;
+    int8_t* fout = F8 != nullptr ? F8 + i * static_cast<int64_t>(s) * MP : nullptr;
+    if (i >= n) {
+        const int4 z = make_int4(0, 0, 0, 0);
+        for (int b = lane * 16; b < s * MP; b += 512) {
+            *reinterpret_cast<int4*>(dout + b) = z;
+            if (fout != nullptr) *reinterpret_cast<int4*>(fout + b) = z;
+        }
+        return;
+    }
     const double* row = Phi + i * ld;
     double mx = 0.0;
     for (int j = lane * 4; j < MP; j += 128) {
@@ -49,21 +71,40 @@ oz_slice_rows_kernel(const double* __restrict__ Phi, int64_t ld, int m, int MP, 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     const int E = oz_exponent(mx);
-    if (lane == 0) ea[i] = ldexp(1.0, E - 8);          // a = ea * sum_t d_t 256^-(t-1)
+    if (lane == 0) ea[i] = ldexp(1.0, E - 8);          // PHI_ij = ea_i * sum_t d_t 256^-(t-1)
     const double sc = ldexp(1.0, 8 * s - E);
-    int8_t* out = A8 + i * static_cast<int64_t>(s) * MP;
+    double fs = 0.0, fy = 0.0;
+    if (fout != nullptr) {
+        fs = wgt[i] * ldexp(1.0, 8 * s + E - 4) / pow2_ceil(scal[0]);       // w_i 2^E_i 2^-Ef 2^(8s)
+        fy = fs / pow2_ceil(scal[1]);
+    }
     for (int j = lane * 4; j < MP; j += 128) {
         const double4 v = *reinterpret_cast<const double4*>(row + j);
-        long long I[4] = {j < m ? __double2ll_rn(v.x * sc) : 0, j + 1 < m ? __double2ll_rn(v.y * sc) : 0,
-                          j + 2 < m ? __double2ll_rn(v.z * sc) : 0, j + 3 < m ? __double2ll_rn(v.w * sc) : 0};
+        const double x[4] = {v.x, v.y, v.z, v.w};
+        long long I[4], J[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const bool in = j + q < m;
+            I[q] = in ? __double2ll_rn(x[q] * sc) : 0;
+            J[q] = in ? __double2ll_rn(x[q] * fs) : ((aug && j + q == m) ? __double2ll_rn(x[q] * fy) : 0);
+        }
         for (int t = s - 1; t >= 0; --t) {
             char4 q;
             q.x = static_cast<signed char>(oz_digit(I[0]));
             q.y = static_cast<signed char>(oz_digit(I[1]));
             q.z = static_cast<signed char>(oz_digit(I[2]));
             q.w = static_cast<signed char>(oz_digit(I[3]));
-            *reinterpret_cast<char4*>(out + static_cast<int64_t>(t) * MP + j) = q;
+            *reinterpret_cast<char4*>(dout + static_cast<int64_t>(t) * MP + j) = q;
         }
+        if (fout != nullptr)
+            for (int t = s - 1; t >= 0; --t) {
+                char4 q;
+                q.x = static_cast<signed char>(oz_digit(J[0]));
+                q.y = static_cast<signed char>(oz_digit(J[1]));
+                q.z = static_cast<signed char>(oz_digit(J[2]));
+                q.w = static_cast<signed char>(oz_digit(J[3]));
+                *reinterpret_cast<char4*>(fout + static_cast<int64_t>(t) * MP + j) = q;
+            }
     }
 }
 
@@ -100,195 +141,87 @@ oz_slice_cols_kernel(const double* __restrict__ Sinv, int MP, int m, const doubl
 
 static int64_t al256(int64_t b) { return (b + 255) / 256 * 256; }
 
-int64_t oz_workspace_bytes(int MP, int s, int64_t chunk_rows) {
-    return 2 * al256(chunk_rows * static_cast<int64_t>(s) * MP) + al256(static_cast<int64_t>(MP) * s * MP) + 2 * al256(chunk_rows * 8) +
-           al256(static_cast<int64_t>(MP) * 8);
+constexpr int OZG_CH = 1024;      // rows per K chunk of the Gram: the digits of the ~4 chunks in flight (x all tiles) stay in L2
+
+int64_t oz_padded_rows(int64_t rows) { return round_up(rows > 0 ? rows : 1, OZG_CH); }
+
+// bytes of ONE digit set for `rows` rows (D8 or F8)
+int64_t oz_digit_bytes(int MP, int s, int64_t rows) { return al256(oz_padded_rows(rows) * static_cast<int64_t>(s) * MP); }
+
+// PHI rows -> D8 (and F8 when wgt != nullptr) + ea.  d_scal: [0] >= max w, [1] >= max |y| (device).
+int ozaki_digits(const double* Phi, int64_t ld, int MP, int m, int64_t rows, int s, const double* wgt, const double* d_scal, int aug,
+                 int8_t* D8, int8_t* F8, double* ea, cudaStream_t st, int64_t* launches) {
+    if (s < 2 || s > OZ_MAXS) {
+        set_error("ozaki: digits per operand must be in [2, %d]", OZ_MAXS);
+        return GPZ_ERR_USAGE;
+    }
+    const int64_t np = oz_padded_rows(rows);
+    oz_digits_kernel<<<static_cast<unsigned>(ceil_div(np, 8)), 256, 0, st>>>(Phi, ld, m, MP, rows, np, s, wgt, d_scal, aug, D8,
+                                                                             wgt != nullptr ? F8 : nullptr, ea);
+    GPZ_KERNEL_CHECK();
+    ++*launches;
+    return GPZ_OK;
 }
 
-// T-GEMM with fused epilogue through the int8 tensor cores.  ws: oz_workspace_bytes(MP, s, chunk_rows) bytes.
-// Row chunks are software-pipelined over two streams: the digit extraction of chunk c+1 (HBM bound, stream aux) runs
-// under the tcgen05 kernel of chunk c (stream st).  ev: 4 events.  nupart: [MP/128][nu_ld] row-sum partials of PHI .* T.
-int ozaki_tgemm(const double* Phi, int64_t ld, const double* Sinv, int MP, int m, int64_t n, int s, int64_t chunk_rows,
+int64_t oz_workspace_bytes(int MP, int s) { return al256(static_cast<int64_t>(MP) * s * MP) + al256(static_cast<int64_t>(MP) * 8); }
+
+// T = PHI iSigma with the fused epilogue (nu partials, H, PHI w) through the int8 tensor cores: one tcgen05 launch over all
+// rows.  D8 / ea: from ozaki_digits.  ws: oz_workspace_bytes.  nupart: [MP/128][nu_ld] row-sum partials of PHI .* T.
+int ozaki_tgemm(const double* Phi, int64_t ld, const int8_t* D8, const double* ea, const double* Sinv, int MP, int m, int64_t n, int s,
                 const double* rw, double* H, int accumulate, double* nupart, int64_t nu_ld, const double* waug, double* pred, void* ws,
-                cudaStream_t st, cudaStream_t aux, cudaEvent_t* ev, cudaEvent_t tev0, cudaEvent_t tev1, int64_t* launches) {
+                cudaStream_t st, cudaEvent_t tev0, cudaEvent_t tev1, int64_t* launches) {
     if (s < 2 || s > OZ_MAXS) {
         set_error("ozaki_tgemm: digits must be in [2, %d]", OZ_MAXS);
         return GPZ_ERR_USAGE;
     }
     unsigned char* p = static_cast<unsigned char*>(ws);
-    auto take = [&](int64_t bytes) {
-        unsigned char* r = p;
-        p += al256(bytes);
-        return r;
-    };
-    int8_t* A8[2];
-    double* ea[2];
-    for (int b = 0; b < 2; ++b) A8[b] = reinterpret_cast<int8_t*>(take(chunk_rows * static_cast<int64_t>(s) * MP));
-    int8_t* B8 = reinterpret_cast<int8_t*>(take(static_cast<int64_t>(MP) * s * MP));
-    for (int b = 0; b < 2; ++b) ea[b] = reinterpret_cast<double*>(take(chunk_rows * 8));
-    double* eb = reinterpret_cast<double*>(take(static_cast<int64_t>(MP) * 8));
-    cudaEvent_t* evS = ev;          // [2] digits of buffer b ready
-    cudaEvent_t* evG = ev + 2;      // [2] kernel reading A8[b] done
-
+    int8_t* B8 = reinterpret_cast<int8_t*>(p);
+    double* eb = reinterpret_cast<double*>(p + al256(static_cast<int64_t>(MP) * s * MP));
     oz_slice_cols_kernel<<<MP, 256, 0, st>>>(Sinv, MP, m, waug, s, B8, eb);
     GPZ_KERNEL_CHECK();
     ++*launches;
-    const int nchunks = static_cast<int>(ceil_div(n, chunk_rows));
-    auto rows_of = [&](int c) { return (static_cast<int64_t>(c + 1) * chunk_rows <= n) ? chunk_rows : n - static_cast<int64_t>(c) * chunk_rows; };
-    auto slice = [&](int c, cudaStream_t sx) {
-        const int64_t r0 = static_cast<int64_t>(c) * chunk_rows;
-        oz_slice_rows_kernel<<<static_cast<unsigned>(ceil_div(rows_of(c), 8)), 256, 0, sx>>>(Phi + r0 * ld, ld, m, MP, rows_of(c), s,
-                                                                                             A8[c & 1], ea[c & 1]);
-        ++*launches;
-    };
-    // everything enqueued so far on st (PHI, iSigma) must be visible to aux
-    GPZ_CUDA(cudaEventRecord(evS[1], st));
-    GPZ_CUDA(cudaStreamWaitEvent(aux, evS[1], 0));
-    slice(0, st);
-    GPZ_CUDA(cudaEventRecord(evS[0], st));
+    if (tev0) GPZ_CUDA(cudaEventRecord(tev0, st));
     int rc;
-    for (int c = 0; c < nchunks; ++c) {
-        const int b = c & 1;
-        const int64_t r0 = static_cast<int64_t>(c) * chunk_rows;
-        const int64_t rows = rows_of(c);
-        if (c + 1 < nchunks) {                       // digits of chunk c+1 on aux while the kernel of chunk c runs
-            if (c >= 1) GPZ_CUDA(cudaStreamWaitEvent(aux, evG[b ^ 1], 0));      // A8[b^1] was read by the kernel of chunk c-1
-            slice(c + 1, aux);
-            GPZ_CUDA(cudaEventRecord(evS[b ^ 1], aux));
-        }
-        GPZ_CUDA(cudaStreamWaitEvent(st, evS[b], 0));
-        if (c == 0 && tev0) GPZ_CUDA(cudaEventRecord(tev0, st));
-        if ((rc = ozmma_tgemm(A8[b], B8, MP, s, s + 1, rows, ea[b], eb, Phi + r0 * ld, ld, rw != nullptr ? rw + r0 : nullptr,
-                              H != nullptr ? H + r0 * ld : nullptr, accumulate, nupart + r0, nu_ld, waug != nullptr ? m : -1,
-                              pred != nullptr ? pred + r0 : nullptr, st, launches)))
-            return rc;
-        if (c == 0 && tev1) GPZ_CUDA(cudaEventRecord(tev1, st));
-        GPZ_CUDA(cudaEventRecord(evG[b], st));
-    }
+    if ((rc = ozmma_tgemm(D8, B8, MP, s, s + 1, n, ea, eb, Phi, ld, rw, H, accumulate, nupart, nu_ld, waug != nullptr ? m : -1, pred, st,
+                          launches)))
+        return rc;
+    if (tev1) GPZ_CUDA(cudaEventRecord(tev1, st));
     return GPZ_OK;
 }
 
-}  // namespace gpz
-
-// ================================================================================================
-// Gram  S = PHI' diag(w) PHI  (GPz/GPz.m:63-65) through the int8 tensor cores.
-//   A side = (w .* PHI)' , B side = PHI' ; contraction over the rows i.  Rows are cut into chunks of OZG_CH rows
-//   (s * OZG_CH * 2^14 < 2^31 keeps every int32 level accumulator exact, and a chunk's digits stay L2-resident while
-//   its 28 digit pairs re-stream them); the tcgen05 kernel folds groups of chunks into its fp64 registers and a small
-//   kernel adds the group partials in fixed order.  Digits are stored transposed, chunk-major:  F[c][j][t][i] (weighted), G[c][j][t][i] (plain),
-//   so that a digit of a 128-row x 128-byte tile is one TMA box.  Only tiles touching the lower triangle are computed
-//   and the result is mirrored.  Scales are fixed powers of two: PHI <= 1 -> 4, the weights -> 2^ceil(log2 max w),
-//   the spare column (y) -> 4 * 2^ceil(log2 max|y|).
-// ================================================================================================
-namespace gpz {
-
-constexpr int OZG_CH = 1024;      // rows per K chunk: the digits of ~4 chunks in flight (x all tiles) stay in L2
-
-__device__ __forceinline__ double pow2_ceil(double v) {
-    int ex = 0;
-    if (v > 0.0) frexp(v, &ex);
-    return ldexp(1.0, ex);                      // v < 2^ex
-}
-
-// tile: 128 rows (i) x 32 columns (j) of PHI -> transposed digits.  A thread owns 4 consecutive rows of a column and
-// emits one char4 per digit, a warp writes 128 contiguous bytes of one (column, digit) row.
-__global__ void __launch_bounds__(256)
-ozg_slice_kernel(const double* __restrict__ Phi, int64_t ld, int MP, int m, int64_t rows, int s, const double* __restrict__ wgt,
-                 const double* __restrict__ scal, int aug, int8_t* __restrict__ F, int8_t* __restrict__ G) {
-    __shared__ double tile[128][33];
-    __shared__ double wsm[128];
-    const int64_t i0 = static_cast<int64_t>(blockIdx.x) * 128;
-    const int j0 = blockIdx.y * 32;
-    const int tid = threadIdx.x;
-    for (int e = tid; e < 128 * 32; e += 256) {
-        const int r = e >> 5, c = e & 31;
-        const int64_t gi = i0 + r;
-        tile[r][c] = (gi < rows) ? Phi[gi * ld + j0 + c] : 0.0;
-    }
-    if (tid < 128) wsm[tid] = (i0 + tid < rows) ? wgt[i0 + tid] : 0.0;
-    __syncthreads();
-    const double sw = 1.0 / pow2_ceil(scal[0]);                    // weight scale: w * sw < 1
-    const double sy = 1.0 / (4.0 * pow2_ceil(scal[1]));            // spare-column scale
-    const double two8s = ldexp(1.0, 8 * s);
-    const int64_t c = i0 / OZG_CH;                                 // chunk (128 divides OZG_CH)
-    const int il = static_cast<int>(i0 % OZG_CH);
-    const int ig = (tid & 31) * 4;                                 // 4 consecutive rows per thread
-    for (int jj = tid >> 5; jj < 32; jj += 8) {
-        const int j = j0 + jj;
-        const double sp = (j < m) ? 0.25 : ((j == m && aug) ? sy : 0.0);
-        long long IA[4], IB[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const double rb = tile[ig + q][jj] * sp;
-            const double ra = rb * (wsm[ig + q] * sw);
-            IB[q] = __double2ll_rn(rb * two8s);
-            IA[q] = __double2ll_rn(ra * two8s);
-        }
-        int8_t* fo = F + ((c * MP + j) * static_cast<int64_t>(s)) * OZG_CH + il + ig;
-        int8_t* go = G + ((c * MP + j) * static_cast<int64_t>(s)) * OZG_CH + il + ig;
-        for (int t = s - 1; t >= 0; --t) {
-            char4 qa, qb;
-            qa.x = static_cast<signed char>(oz_digit(IA[0]));
-            qa.y = static_cast<signed char>(oz_digit(IA[1]));
-            qa.z = static_cast<signed char>(oz_digit(IA[2]));
-            qa.w = static_cast<signed char>(oz_digit(IA[3]));
-            qb.x = static_cast<signed char>(oz_digit(IB[0]));
-            qb.y = static_cast<signed char>(oz_digit(IB[1]));
-            qb.z = static_cast<signed char>(oz_digit(IB[2]));
-            qb.w = static_cast<signed char>(oz_digit(IB[3]));
-            *reinterpret_cast<char4*>(fo + static_cast<int64_t>(t) * OZG_CH) = qa;
-            *reinterpret_cast<char4*>(go + static_cast<int64_t>(t) * OZG_CH) = qb;
-        }
-    }
-}
-
-// sr[j] = (weight scale) * (column scale) / 256, sc[l] = (column scale) / 256: value = 2^E sum_t d_t 256^-t
-__global__ void ozg_scales_kernel(const double* __restrict__ scal, int MP, int m, int aug, double* __restrict__ sr, double* __restrict__ sc) {
+// sr[j] = 2^Ef 256^-2 (x cy for the spare column): S_jl = sr_j sum_e 256^-(e-2) acc_e
+__global__ void ozg_scales_kernel(const double* __restrict__ scal, int MP, int m, int aug, double* __restrict__ sr) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= MP) return;
-    const double cw = pow2_ceil(scal[0]);
-    const double cy = 4.0 * pow2_ceil(scal[1]);
-    const double sj = (j < m) ? 4.0 : ((j == m && aug) ? cy : 0.0);
-    sr[j] = cw * sj * (1.0 / 256.0);
-    sc[j] = sj * (1.0 / 256.0);
+    const double f = 16.0 * pow2_ceil(scal[0]) * (1.0 / 65536.0);
+    sr[j] = (j < m) ? f : ((j == m && aug) ? f * pow2_ceil(scal[1]) : 0.0);
 }
 
-int64_t oz_gram_workspace_bytes(int MP, int s, int64_t rows) {
-    const int64_t nch = ceil_div(rows > 0 ? rows : 1, OZG_CH);
-    return 2 * al256(nch * MP * static_cast<int64_t>(s) * OZG_CH) + al256(ozmma_partial_doubles(MP, MP, 1, static_cast<int>(nch), 0) * 8) +
-           2 * al256(static_cast<int64_t>(MP) * 8);
+int64_t oz_gram_workspace_bytes(int MP, int64_t rows) {
+    const int64_t nch = oz_padded_rows(rows) / OZG_CH;
+    return al256(ozmma_partial_doubles(MP, MP, 1, static_cast<int>(nch), 0) * 8) + al256(static_cast<int64_t>(MP) * 8);
 }
 
-int ozaki_gram(const double* Phi, int64_t ld, int MP, int m, int64_t rows, int s, const double* wgt, const double* d_scal,
-               int aug, int accumulate, double* S, void* ws, cudaStream_t st, cudaStream_t aux, cudaEvent_t* ev, int64_t* launches) {
-    if (s < 2 || s > OZ_MAXS) {
-        set_error("ozaki_gram: unsupported digit count %d", s);
+// S (+)= PHI' diag(w) PHI over `rows` rows: F8' D8 as a digit GEMM contracting over the rows (MN-major operands, K chunks of
+// OZG_CH rows so that s * OZG_CH * 2^14 < 2^31 keeps every int32 level accumulator exact).  Only tiles touching the lower
+// triangle are computed; the result is mirrored.  gs: digits used by the Gram (<= s, the leading ones of the stored digits).
+int ozaki_gram(const int8_t* F8, const int8_t* D8, int MP, int m, int64_t rows, int s, int gs, const double* d_scal, int aug,
+               int accumulate, double* S, void* ws, cudaStream_t st, int64_t* launches) {
+    if (gs < 2 || gs > s) {
+        set_error("ozaki_gram: unsupported digit count %d (stored %d)", gs, s);
         return GPZ_ERR_USAGE;
     }
-    (void)aux;
-    (void)ev;
-    const int nch = static_cast<int>(ceil_div(rows > 0 ? rows : 1, OZG_CH));
+    const int nch = static_cast<int>(oz_padded_rows(rows) / OZG_CH);
     unsigned char* p = static_cast<unsigned char*>(ws);
-    auto take = [&](int64_t bytes) {
-        unsigned char* r = p;
-        p += al256(bytes);
-        return r;
-    };
-    const int64_t slab = static_cast<int64_t>(nch) * MP * s * OZG_CH;
-    int8_t* F = reinterpret_cast<int8_t*>(take(slab));
-    int8_t* G = reinterpret_cast<int8_t*>(take(slab));
-    double* partial = reinterpret_cast<double*>(take(ozmma_partial_doubles(MP, MP, 1, nch, 0) * 8));
-    double* sr = reinterpret_cast<double*>(take(static_cast<int64_t>(MP) * 8));
-    double* sc = reinterpret_cast<double*>(take(static_cast<int64_t>(MP) * 8));
-    // digits (the tail of the last chunk is zero-filled by the kernel: rows beyond `rows` read as 0)
-    dim3 gs(static_cast<unsigned>(static_cast<int64_t>(nch) * OZG_CH / 128), static_cast<unsigned>(MP / 32));
-    ozg_slice_kernel<<<gs, 256, 0, st>>>(Phi, ld, MP, m, rows, s, wgt, d_scal, aug, F, G);
+    double* partial = reinterpret_cast<double*>(p);
+    double* sr = reinterpret_cast<double*>(p + al256(ozmma_partial_doubles(MP, MP, 1, nch, 0) * 8));
+    ozg_scales_kernel<<<static_cast<unsigned>(ceil_div(MP, 256)), 256, 0, st>>>(d_scal, MP, m, aug, sr);
     GPZ_KERNEL_CHECK();
-    ozg_scales_kernel<<<static_cast<unsigned>(ceil_div(MP, 256)), 256, 0, st>>>(d_scal, MP, m, aug, sr, sc);
-    GPZ_KERNEL_CHECK();
-    *launches += 2;
-    const int64_t str[3] = {OZG_CH, static_cast<int64_t>(s) * OZG_CH, static_cast<int64_t>(MP) * s * OZG_CH};
-    return ozmma_gemm_nt(F, str, MP, G, str, MP, s, s + 1, OZG_CH, nch, 1, partial, sr, sc, 1.0, accumulate, S, MP, 0, st, launches);
+    ++*launches;
+    // addressed {row index j, digit, k = i within chunk, chunk}
+    const int64_t str[3] = {MP, static_cast<int64_t>(s) * MP, static_cast<int64_t>(OZG_CH) * s * MP};
+    return ozmma_gemm_nt(F8, str, MP, D8, str, MP, gs, gs + 1, OZG_CH, nch, 1, 1, partial, sr, nullptr, 1.0, accumulate, S, MP, 0, st,
+                         launches);
 }
 
 }  // namespace gpz

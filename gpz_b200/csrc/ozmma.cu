@@ -47,6 +47,11 @@ struct OzmmaArgs {
     int ngroups;              // ceil(nchunks / gchunks); work unit u = group * ntiles + tile
     int lower;                // tile list = tiles touching the lower triangle (Gram); else all tiles_m x tiles_n
     int mode;                 // 0: fp64 partial tiles, 1: T-GEMM epilogue
+    int mn_major;             // operands stored [k][row] (row index contiguous) instead of [row][k]
+    uint32_t idesc;           // UMMA instruction descriptor
+    uint32_t deschiA, deschiB;   // high words of the smem matrix descriptors
+    uint32_t desclo0A, desclo0B; // low-word bits above the start address (LBO field)
+    uint32_t kadvA, kadvB;    // descriptor start-address step per 32 K-bytes
     // mode 1
     const double* ea;         // [rows] row scales (including 256^-1 .. see ozaki.cu)
     const double* eb;         // [cols] column scales
@@ -71,6 +76,13 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// one lane of the (converged) warp; the surrounding code stays warp-uniform so that barrier addresses, descriptors and
+// coordinates live in uniform registers (a single-lane loop costs a R2UR waterfall per tcgen05 / TMA instruction)
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred;
 }
 __device__ __forceinline__ uint32_t mapa_cta(uint32_t addr, uint32_t rank) {
     uint32_t r;
@@ -149,12 +161,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major operand tile written by TMA with the 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart
-// (cute/arch/mma_sm100_desc.hpp SmemDescriptor: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 | SWIZZLE_128B (2) <<61)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    return static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) |
-           (2ull << 61);
-}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lo_bits) { return ((smem_addr >> 4) & 0x3FFFu) | lo_bits; }
 
 __device__ __forceinline__ void decode_tile(const OzmmaArgs& a, int tile, int& mt, int& nt) {
     if (!a.lower) {
@@ -208,16 +215,15 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer (one lane per CTA)
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int u = pair; u < U; u += npairs) {
-                const int group = u / a.ntiles, tile = u - group * a.ntiles;
-                int mt, nt;
-                decode_tile(a, tile, mt, nt);
-                const int rowA = mt * 256 + static_cast<int>(rank) * 128, rowB = nt * 128 + static_cast<int>(rank) * 64;
-                const int c1 = min(a.nchunks, (group + 1) * a.gchunks);
-                for (int chunk = group * a.gchunks; chunk < c1; ++chunk)
+        // ------------------------------------------------------------------ TMA producer (warp-uniform loop, one lane issues)
+        uint32_t it = 0;
+        for (int u = pair; u < U; u += npairs) {
+            const int group = u / a.ntiles, tile = u - group * a.ntiles;
+            int mt, nt;
+            decode_tile(a, tile, mt, nt);
+            const int rowA = mt * 256 + static_cast<int>(rank) * 128, rowB = nt * 128 + static_cast<int>(rank) * 64;
+            const int c1 = min(a.nchunks, (group + 1) * a.gchunks);
+            for (int chunk = group * a.gchunks; chunk < c1; ++chunk)
                 for (int e = a.emax; e >= a.emin; --e) {
                     const int tlo = max(1, e - a.s), thi = min(a.s, e - 1);
                     for (int t = tlo; t <= thi; ++t) {
@@ -225,21 +231,27 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                         for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
                             const uint32_t stage = it % OM_STAGES, ph = (it / OM_STAGES) & 1u;
                             mbar_wait(bar0 + 64 + 8 * stage, ph ^ 1u);
-                            const uint32_t sA = base + stage * OM_STAGE_BYTES, sB = sA + OM_A_BYTES;
-                            const uint32_t full_leader = mapa_cta(bar0 + 8 * stage, 0);
-                            if (rank == 0) mbar_arrive_expect_tx(bar0 + 8 * stage, 2 * OM_STAGE_BYTES);
-                            else mbar_arrive_cluster(full_leader);
-                            tma_load_4d(&mapA, sA, full_leader, kb * 128, t - 1, rowA, chunk);
-                            tma_load_4d(&mapB, sB, full_leader, kb * 128, uu - 1, rowB, chunk);
+                            if (elect_one()) {
+                                const uint32_t sA = base + stage * OM_STAGE_BYTES, sB = sA + OM_A_BYTES;
+                                const uint32_t full_leader = mapa_cta(bar0 + 8 * stage, 0);
+                                if (rank == 0) mbar_arrive_expect_tx(bar0 + 8 * stage, 2 * OM_STAGE_BYTES);
+                                else mbar_arrive_cluster(full_leader);
+                                if (a.mn_major) {
+                                    tma_load_4d(&mapA, sA, full_leader, rowA, t - 1, kb * 128, chunk);
+                                    tma_load_4d(&mapB, sB, full_leader, rowB, uu - 1, kb * 128, chunk);
+                                } else {
+                                    tma_load_4d(&mapA, sA, full_leader, kb * 128, t - 1, rowA, chunk);
+                                    tma_load_4d(&mapB, sB, full_leader, kb * 128, uu - 1, rowB, chunk);
+                                }
+                            }
+                            __syncwarp();
                         }
                     }
                 }
-            }
         }
-        __syncwarp();
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer (one lane of the leader CTA)
-        if (rank == 0 && lane == 0) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA; warp-uniform loop, one lane issues)
+        if (rank == 0) {
             uint32_t it = 0, L = 0;
             for (int u = pair; u < U; u += npairs) {
                 const int group = u / a.ntiles;
@@ -249,26 +261,26 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                     mbar_wait(bar0 + 144 + 8 * buf, ((L >> 1) & 1u) ^ 1u);       // epilogue has drained this accumulator
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + buf * 128u;
-                    const int npair = min(a.s, e - 1) - max(1, e - a.s) + 1;
-                    uint32_t acc = 0;
-                    for (int j = 0; j < npair * a.kblocks; ++j, ++it) {
+                    const int nkb = (min(a.s, e - 1) - max(1, e - a.s) + 1) * a.kblocks;
+                    for (int j = 0; j < nkb; ++j, ++it) {
                         const uint32_t stage = it % OM_STAGES, ph = (it / OM_STAGES) & 1u;
                         mbar_wait(bar0 + 8 * stage, ph);                          // both CTAs' tiles have landed
                         tc_fence_after();
-                        const uint32_t sA = base + stage * OM_STAGE_BYTES, sB = sA + OM_A_BYTES;
-                        const uint64_t ad = umma_desc_sw128(sA), bd = umma_desc_sw128(sB);
+                        if (elect_one()) {
+                            const uint32_t sA = base + stage * OM_STAGE_BYTES;
+                            const uint32_t alo = desc_lo(sA, a.desclo0A), blo = desc_lo(sA + OM_A_BYTES, a.desclo0B);
 #pragma unroll
-                        for (int k4 = 0; k4 < 4; ++k4) {                         // 4 x 32 K-bytes inside the swizzle atom
-                            umma_i8_2cta(d_tmem, ad + 2 * k4, bd + 2 * k4, OM_IDESC, acc);
-                            acc = 1;
+                            for (int k4 = 0; k4 < 4; ++k4)                        // 4 x 32 K-bytes of the stage
+                                umma_i8_2cta(d_tmem, (static_cast<uint64_t>(a.deschiA) << 32) | (alo + a.kadvA * k4),
+                                             (static_cast<uint64_t>(a.deschiB) << 32) | (blo + a.kadvB * k4), a.idesc, (j | k4) != 0 ? 1u : 0u);
+                            umma_commit_pair(bar0 + 64 + 8 * stage);             // frees the smem stage in both CTAs
+                            if (j + 1 == nkb) umma_commit_pair(bar0 + 128 + 8 * buf);   // level finished -> epilogue warps
                         }
-                        umma_commit_pair(bar0 + 64 + 8 * stage);                 // frees the smem stage in both CTAs
+                        __syncwarp();
                     }
-                    umma_commit_pair(bar0 + 128 + 8 * buf);                       // level finished -> epilogue warps
                 }
             }
         }
-        __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue warps: fold levels in fp64 registers
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
@@ -409,8 +421,32 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// int8 digits addressed as {k, digit, row, chunk}; strides in bytes (multiples of 16); box = 128 k-bytes x box_rows rows
-int make_map(CUtensorMap* map, const int8_t* ptr, const int64_t dims[4], const int64_t strides[3], int box_rows) {
+// smem matrix descriptor constants (cute/arch/mma_sm100_desc.hpp SmemDescriptor; deep_gemm make_umma_desc):
+//   K-major, 128B swizzle:  rows of 128 K-bytes, 8-row groups 1024 B apart (SBO); LBO unused (1); 32 K-bytes = +32 B
+//   MN-major: the tile is [128 k-rows][W bytes of the row index], W = 128 (A, SWIZZLE_128B) or 64 (B, SWIZZLE_64B: each CTA
+//   of the pair holds 64 of the 128 N columns); 8-k-row groups 8 W bytes apart (SBO), LBO = stride between W-wide atoms
+//   (one atom here); 32 K-rows = +32 W bytes
+void set_operand_layout(OzmmaArgs& a, int mn_major) {
+    a.mn_major = mn_major;
+    const uint32_t ver = 1u << 14;       // descriptor version 1 at bit 46
+    if (!mn_major) {
+        a.idesc = OM_IDESC;
+        a.desclo0A = a.desclo0B = 1u << 16;
+        a.deschiA = a.deschiB = (1024u >> 4) | ver | (2u << 29);
+        a.kadvA = a.kadvB = 32u >> 4;
+    } else {
+        a.idesc = OM_IDESC | (1u << 15) | (1u << 16);
+        a.desclo0A = ((128u * 128u) >> 4) << 16;
+        a.desclo0B = ((128u * 64u) >> 4) << 16;
+        a.deschiA = (1024u >> 4) | ver | (2u << 29);          // SWIZZLE_128B
+        a.deschiB = (512u >> 4) | ver | (4u << 29);           // SWIZZLE_64B
+        a.kadvA = (32u * 128u) >> 4;
+        a.kadvB = (32u * 64u) >> 4;
+    }
+}
+
+// int8 digits addressed by 4 coordinates (inner first); strides in bytes (multiples of 16) of coordinates 1..3
+int make_map(CUtensorMap* map, const int8_t* ptr, const int64_t dims[4], const int64_t strides[3], int box_rows, int mn_major = 0) {
     EncodeTiledFn fn = encode_fn();
     if (fn == nullptr) {
         set_error("ozmma: cuTensorMapEncodeTiled is not available from this driver");
@@ -419,10 +455,16 @@ int make_map(CUtensorMap* map, const int8_t* ptr, const int64_t dims[4], const i
     cuuint64_t gd[4] = {static_cast<cuuint64_t>(dims[0]), static_cast<cuuint64_t>(dims[1]), static_cast<cuuint64_t>(dims[2]),
                         static_cast<cuuint64_t>(dims[3])};
     cuuint64_t gs[3] = {static_cast<cuuint64_t>(strides[0]), static_cast<cuuint64_t>(strides[1]), static_cast<cuuint64_t>(strides[2])};
+    // K-major: box = 128 K-bytes x box_rows rows; MN-major: box = box_rows row-bytes x 128 k-rows
     cuuint32_t box[4] = {128, 1, static_cast<cuuint32_t>(box_rows), 1};
+    if (mn_major) {
+        box[0] = static_cast<cuuint32_t>(box_rows);
+        box[2] = 128;
+    }
     cuuint32_t es[4] = {1, 1, 1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<int8_t*>(ptr), gd, gs, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          (mn_major && box_rows == 64) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("ozmma: cuTensorMapEncodeTiled failed (%d) dims %lld %lld %lld %lld strides %lld %lld %lld", static_cast<int>(r),
                   static_cast<long long>(dims[0]), static_cast<long long>(dims[1]), static_cast<long long>(dims[2]),
@@ -500,10 +542,11 @@ int64_t ozmma_partial_doubles(int rowsA, int rowsB, int lower, int nchunks, int 
 }
 
 // Generic form (also the self-test entry): out[rowsA][rowsB] (+)= scale * sr[r] * sc[c] * sum_chunks sum_e 256^-(e-2) sum_{t+u=e} A_t B_u'
-// A, B: int8 digits addressed {k, digit, row, chunk} with byte strides strX = {digit, row, chunk}.
+// mn_major == 0: A, B are int8 digits addressed {k, digit, row, chunk} with byte strides strX = {digit, row, chunk};
+// mn_major == 1: addressed {row, digit, k, chunk} (the row index is the contiguous one), strides = {digit, k, chunk}.
 int ozmma_gemm_nt(const int8_t* A, const int64_t strA[3], int rowsA, const int8_t* B, const int64_t strB[3], int rowsB, int s, int emax,
-                  int kchunk, int nchunks, int lower, double* partial, const double* sr, const double* sc, double scale, int accumulate,
-                  double* out, int64_t ldo, int pairs_limit, cudaStream_t st, int64_t* launches) {
+                  int kchunk, int nchunks, int lower, int mn_major, double* partial, const double* sr, const double* sc, double scale,
+                  int accumulate, double* out, int64_t ldo, int pairs_limit, cudaStream_t st, int64_t* launches) {
     if (s < 1 || s > 8 || kchunk % 128 != 0 || kchunk <= 0 || nchunks <= 0 || emax < 2 || emax > 2 * s) {
         set_error("ozmma_gemm_nt: bad arguments (s=%d kchunk=%d nchunks=%d emax=%d)", s, kchunk, nchunks, emax);
         return GPZ_ERR_USAGE;
@@ -525,10 +568,12 @@ int ozmma_gemm_nt(const int8_t* A, const int64_t strA[3], int rowsA, const int8_
     if (pairs_limit > 0 && pairs_limit < np) np = pairs_limit;
     CUtensorMap mA, mB;
     const int64_t dA[4] = {kchunk, s, rowsA, nchunks}, dB[4] = {kchunk, s, rowsB, nchunks};
+    const int64_t tA[4] = {rowsA, s, kchunk, nchunks}, tB[4] = {rowsB, s, kchunk, nchunks};
     int rc;
-    if ((rc = make_map(&mA, A, dA, strA, 128))) return rc;
-    if ((rc = make_map(&mB, B, dB, strB, 64))) return rc;
+    if ((rc = make_map(&mA, A, mn_major ? tA : dA, strA, 128, mn_major))) return rc;
+    if ((rc = make_map(&mB, B, mn_major ? tB : dB, strB, 64, mn_major))) return rc;
     OzmmaArgs a = {};
+    set_operand_layout(a, mn_major);
     a.s = s;
     a.emin = 2;
     a.emax = emax;
@@ -571,6 +616,7 @@ int ozmma_tgemm(const int8_t* A8, const int8_t* B8, int MP, int s, int emax, int
     if ((rc = make_map(&mA, A8, dA, sA, 128))) return rc;
     if ((rc = make_map(&mB, B8, dB, sB, 64))) return rc;
     OzmmaArgs a = {};
+    set_operand_layout(a, 0);
     a.s = s;
     a.emin = 2;
     a.emax = emax;

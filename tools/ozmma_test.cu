@@ -26,8 +26,8 @@ static inline uint32_t rnd() {
     return rng_state >> 8;
 }
 
-// digits laid out [chunk][row][digit][k]
-static int run_case(int rowsA, int rowsB, int s, int emax, int kchunk, int nchunks, int lower, int pairs_limit) {
+// digits laid out [chunk][row][digit][k]  (mn: [chunk][k][digit][row])
+static int run_case(int rowsA, int rowsB, int s, int emax, int kchunk, int nchunks, int lower, int pairs_limit, int mn = 0) {
     const int64_t szA = static_cast<int64_t>(nchunks) * rowsA * s * kchunk, szB = static_cast<int64_t>(nchunks) * rowsB * s * kchunk;
     std::vector<int8_t> hA(szA), hB(szB);
     for (auto& v : hA) v = static_cast<int8_t>(static_cast<int>(rnd() % 256) - 128);
@@ -43,10 +43,14 @@ static int run_case(int rowsA, int rowsB, int s, int emax, int kchunk, int nchun
     CK(cudaMalloc(&dP, np * 8));
     CK(cudaMalloc(&dO, static_cast<int64_t>(rowsA) * rowsB * 8));
     CK(cudaMemset(dO, 0xff, static_cast<int64_t>(rowsA) * rowsB * 8));
-    const int64_t strA[3] = {kchunk, static_cast<int64_t>(s) * kchunk, static_cast<int64_t>(rowsA) * s * kchunk};
-    const int64_t strB[3] = {kchunk, static_cast<int64_t>(s) * kchunk, static_cast<int64_t>(rowsB) * s * kchunk};
+    int64_t strA[3] = {kchunk, static_cast<int64_t>(s) * kchunk, static_cast<int64_t>(rowsA) * s * kchunk};
+    int64_t strB[3] = {kchunk, static_cast<int64_t>(s) * kchunk, static_cast<int64_t>(rowsB) * s * kchunk};
+    if (mn) {
+        strA[0] = rowsA; strA[1] = static_cast<int64_t>(s) * rowsA;
+        strB[0] = rowsB; strB[1] = static_cast<int64_t>(s) * rowsB;
+    }
     int64_t launches = 0;
-    int rc = ozmma_gemm_nt(dA, strA, rowsA, dB, strB, rowsB, s, emax, kchunk, nchunks, lower, dP, nullptr, nullptr, 1.0, 0, dO, rowsB,
+    int rc = ozmma_gemm_nt(dA, strA, rowsA, dB, strB, rowsB, s, emax, kchunk, nchunks, lower, mn, dP, nullptr, nullptr, 1.0, 0, dO, rowsB,
                            pairs_limit, 0, &launches);
     if (rc) {
         printf("ozmma_gemm_nt failed rc=%d: %s\n", rc, gpz_last_error());
@@ -73,9 +77,15 @@ static int run_case(int rowsA, int rowsB, int s, int emax, int kchunk, int nchun
                 for (int t = 1; t <= s; ++t) {
                     const int u = e - t;
                     if (u < 1 || u > s) continue;
-                    const int8_t* pa = hA.data() + ((static_cast<int64_t>(ch) * rowsA + r) * s + (t - 1)) * kchunk;
-                    const int8_t* pb = hB.data() + ((static_cast<int64_t>(ch) * rowsB + c) * s + (u - 1)) * kchunk;
-                    for (int k = 0; k < kchunk; ++k) acc += static_cast<int>(pa[k]) * static_cast<int>(pb[k]);
+                    if (!mn) {
+                        const int8_t* pa = hA.data() + ((static_cast<int64_t>(ch) * rowsA + r) * s + (t - 1)) * kchunk;
+                        const int8_t* pb = hB.data() + ((static_cast<int64_t>(ch) * rowsB + c) * s + (u - 1)) * kchunk;
+                        for (int k = 0; k < kchunk; ++k) acc += static_cast<int>(pa[k]) * static_cast<int>(pb[k]);
+                    } else {
+                        for (int k = 0; k < kchunk; ++k)
+                            acc += static_cast<int>(hA[((static_cast<int64_t>(ch) * kchunk + k) * s + (t - 1)) * rowsA + r]) *
+                                   static_cast<int>(hB[((static_cast<int64_t>(ch) * kchunk + k) * s + (u - 1)) * rowsB + c]);
+                    }
                 }
                 ref += static_cast<double>(acc) * ldexp(1.0, -8 * (e - 2));
             }
@@ -92,8 +102,8 @@ static int run_case(int rowsA, int rowsB, int s, int emax, int kchunk, int nchun
             if (gotT != got) { if (bad < 10) printf("  mirror mismatch at (%d,%d)\n", r, c); ++bad; }
         }
     }
-    printf("case rowsA=%d rowsB=%d s=%d emax=%d kchunk=%d nchunks=%d lower=%d pairs=%d: %d/%d bad, max rel %.2e\n", rowsA, rowsB, s, emax,
-           kchunk, nchunks, lower, pairs_limit, bad, checked, maxrel);
+    printf("case rowsA=%d rowsB=%d s=%d emax=%d kchunk=%d nchunks=%d lower=%d pairs=%d mn=%d: %d/%d bad, max rel %.2e\n", rowsA, rowsB, s,
+           emax, kchunk, nchunks, lower, pairs_limit, mn, bad, checked, maxrel);
     cudaFree(dA);
     cudaFree(dB);
     cudaFree(dP);
@@ -152,7 +162,7 @@ static void time_tgemm(int64_t rows, int MP, int s, int random) {
            ops / ms * 1e-9, 2.0 * rows * MP * static_cast<double>(MP) / ms * 1e-9);
 }
 
-static void time_gram(int64_t nrows, int MP, int s, int kchunk) {
+static void time_gram(int64_t nrows, int MP, int s, int kchunk, int mn = 0) {
     const int nch = static_cast<int>((nrows + kchunk - 1) / kchunk);
     const int64_t sz = static_cast<int64_t>(nch) * MP * s * kchunk;
     int8_t *dA, *dB;
@@ -164,14 +174,15 @@ static void time_gram(int64_t nrows, int MP, int s, int kchunk) {
     double *dP, *dO;
     CK(cudaMalloc(&dP, np * 8));
     CK(cudaMalloc(&dO, static_cast<int64_t>(MP) * MP * 8));
-    const int64_t str[3] = {kchunk, static_cast<int64_t>(s) * kchunk, static_cast<int64_t>(MP) * s * kchunk};
+    int64_t str[3] = {kchunk, static_cast<int64_t>(s) * kchunk, static_cast<int64_t>(MP) * s * kchunk};
+    if (mn) { str[0] = MP; str[1] = static_cast<int64_t>(s) * MP; }
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     int64_t launches = 0;
     for (int rep = 0; rep < 3; ++rep) {
         if (rep == 1) cudaEventRecord(e0, 0);
-        int rc = ozmma_gemm_nt(dA, str, MP, dB, str, MP, s, s + 1, kchunk, nch, 1, dP, nullptr, nullptr, 1.0, 0, dO, MP, 0, 0, &launches);
+        int rc = ozmma_gemm_nt(dA, str, MP, dB, str, MP, s, s + 1, kchunk, nch, 1, mn, dP, nullptr, nullptr, 1.0, 0, dO, MP, 0, 0, &launches);
         if (rc) {
             printf("gram failed: %s\n", gpz_last_error());
             return;
@@ -186,8 +197,8 @@ static void time_gram(int64_t nrows, int MP, int s, int kchunk) {
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     ms /= 2;
-    printf("gram rows=%lld MP=%d s=%d kchunk=%d (partials %.2f GB): %.3f ms -> fp64-equivalent %.1f TFLOP/s (2 n m^2)\n",
-           static_cast<long long>(nrows), MP, s, kchunk, np * 8e-9, ms, 2.0 * nrows * MP * static_cast<double>(MP) / ms * 1e-9);
+    printf("gram mn=%d rows=%lld MP=%d s=%d kchunk=%d (partials %.2f GB): %.3f ms -> fp64-equivalent %.1f TFLOP/s (2 n m^2)\n",
+           mn, static_cast<long long>(nrows), MP, s, kchunk, np * 8e-9, ms, 2.0 * nrows * MP * static_cast<double>(MP) / ms * 1e-9);
     cudaFree(dA); cudaFree(dB); cudaFree(dP); cudaFree(dO);
 }
 
@@ -202,6 +213,10 @@ int main(int argc, char** argv) {
     if (!fail) fail |= run_case(1024, 1024, 7, 8, 1024, 1, 0, 0);
     if (!fail) fail |= run_case(1024, 1024, 3, 4, 2048, 5, 1, 0);   // Gram-like: lower tiles
     if (!fail) fail |= run_case(512, 512, 2, 3, 256, 300, 1, 0);    // many chunks: grouped units + ordered reduction
+    if (!fail) fail |= run_case(256, 128, 1, 2, 128, 1, 0, 1, 1);       // MN-major operands: one tile, one k-block
+    if (!fail) fail |= run_case(256, 128, 2, 3, 512, 2, 0, 1, 1);
+    if (!fail) fail |= run_case(1024, 1024, 3, 4, 1024, 7, 1, 0, 1);    // Gram layout
+    if (!fail) fail |= run_case(1024, 1024, 7, 8, 1024, 3, 1, 0, 1);
     if (fail) {
         printf("FAILED\n");
         return 1;
@@ -212,8 +227,9 @@ int main(int argc, char** argv) {
         time_tgemm(131072, 1024, 7, 1);
         time_tgemm(1000192, 1024, 7, 1);
         time_gram(1000000, 1024, 7, 1024);
-        time_gram(1000000, 1024, 7, 2048);
-        time_gram(1000000, 512, 7, 1024);
+        time_gram(1000000, 1024, 7, 1024, 1);
+        time_gram(1000000, 1024, 6, 1024, 1);
+        time_gram(1000000, 512, 7, 1024, 1);
     }
     return 0;
 }

@@ -22,7 +22,7 @@ for meth, n, d, m in cfgs:
     th = synth.make_theta0(X, Y, meth, m, het=True, seed=1)
     t0 = time.time(); ctx = L.Context(L.make_model(d, 1, m, meth, True), X, Y); t1 = time.time()
     if os.environ.get("GEMM_WARPS"): ctx.set_option("gemm_warps", float(os.environ["GEMM_WARPS"]))
-    for opt in ("spare_column", "tensor_phi", "fused_backproj", "ozaki_slices", "ozaki_gram", "ozaki_chunk_rows"):
+    for opt in ("spare_column", "tensor_phi", "fused_backproj", "ozaki_slices", "ozaki_gram", "ozaki_gram_slices"):
         if os.environ.get(opt.upper()): ctx.set_option(opt, float(os.environ[opt.upper()]))
     f, g, st = ctx.eval(th)
     ts = []
