@@ -133,12 +133,13 @@ __device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
 // D[tmem] (+)= A[smem desc] * B[smem desc], 256 x 128 x 32 int8, both CTAs of the pair
-__device__ __forceinline__ void umma_i8_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_i8_2cta(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                             uint32_t accumulate) {
     const uint32_t z = 0;
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z)
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], da, db, %5, {%7, %7, %7, %7, %7, %7, %7, %7}, p;\n\t}"
+        ::"r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate), "r"(z)
         : "memory");
 }
 // arrive (once) on the mbarrier at the same smem offset in both CTAs when all MMAs issued so far have completed
@@ -215,25 +216,26 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer (warp-uniform loop, one lane issues)
-        uint32_t it = 0;
-        for (int u = pair; u < U; u += npairs) {
-            const int group = u / a.ntiles, tile = u - group * a.ntiles;
-            int mt, nt;
-            decode_tile(a, tile, mt, nt);
-            const int rowA = mt * 256 + static_cast<int>(rank) * 128, rowB = nt * 128 + static_cast<int>(rank) * 64;
-            const int c1 = min(a.nchunks, (group + 1) * a.gchunks);
-            for (int chunk = group * a.gchunks; chunk < c1; ++chunk)
-                for (int e = a.emax; e >= a.emin; --e) {
-                    const int tlo = max(1, e - a.s), thi = min(a.s, e - 1);
-                    for (int t = tlo; t <= thi; ++t) {
-                        const int uu = e - t;
-                        for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
-                            const uint32_t stage = it % OM_STAGES, ph = (it / OM_STAGES) & 1u;
-                            mbar_wait(bar0 + 64 + 8 * stage, ph ^ 1u);
-                            if (elect_one()) {
+        // ------------------------------------------------------------------ TMA producer: one elected lane runs the whole loop
+        if (elect_one()) {
+            uint32_t it = 0;
+            const uint32_t full_leader0 = mapa_cta(bar0, 0);
+            for (int u = pair; u < U; u += npairs) {
+                const int group = u / a.ntiles, tile = u - group * a.ntiles;
+                int mt, nt;
+                decode_tile(a, tile, mt, nt);
+                const int rowA = mt * 256 + static_cast<int>(rank) * 128, rowB = nt * 128 + static_cast<int>(rank) * 64;
+                const int c1 = min(a.nchunks, (group + 1) * a.gchunks);
+                for (int chunk = group * a.gchunks; chunk < c1; ++chunk)
+                    for (int e = a.emax; e >= a.emin; --e) {
+                        const int tlo = max(1, e - a.s), thi = min(a.s, e - 1);
+                        for (int t = tlo; t <= thi; ++t) {
+                            const int uu = e - t;
+                            for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
+                                const uint32_t stage = it % OM_STAGES, ph = (it / OM_STAGES) & 1u;
+                                mbar_wait(bar0 + 64 + 8 * stage, ph ^ 1u);
                                 const uint32_t sA = base + stage * OM_STAGE_BYTES, sB = sA + OM_A_BYTES;
-                                const uint32_t full_leader = mapa_cta(bar0 + 8 * stage, 0);
+                                const uint32_t full_leader = full_leader0 + 8 * stage;
                                 if (rank == 0) mbar_arrive_expect_tx(bar0 + 8 * stage, 2 * OM_STAGE_BYTES);
                                 else mbar_arrive_cluster(full_leader);
                                 if (a.mn_major) {
@@ -244,15 +246,16 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                                     tma_load_4d(&mapB, sB, full_leader, kb * 128, uu - 1, rowB, chunk);
                                 }
                             }
-                            __syncwarp();
                         }
                     }
-                }
+            }
         }
+        __syncwarp();
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer (leader CTA; warp-uniform loop, one lane issues)
-        if (rank == 0) {
+        // ------------------------------------------------------------------ MMA issuer: one elected lane of the leader CTA
+        if (rank == 0 && elect_one()) {
             uint32_t it = 0, L = 0;
+            const uint32_t alo0 = desc_lo(base, a.desclo0A), blo0 = desc_lo(base + OM_A_BYTES, a.desclo0B);
             for (int u = pair; u < U; u += npairs) {
                 const int group = u / a.ntiles;
                 const int nlev = (min(a.nchunks, (group + 1) * a.gchunks) - group * a.gchunks) * (a.emax - a.emin + 1);
@@ -262,25 +265,24 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + buf * 128u;
                     const int nkb = (min(a.s, e - 1) - max(1, e - a.s) + 1) * a.kblocks;
+                    uint32_t acc = 0;
                     for (int j = 0; j < nkb; ++j, ++it) {
                         const uint32_t stage = it % OM_STAGES, ph = (it / OM_STAGES) & 1u;
                         mbar_wait(bar0 + 8 * stage, ph);                          // both CTAs' tiles have landed
                         tc_fence_after();
-                        if (elect_one()) {
-                            const uint32_t sA = base + stage * OM_STAGE_BYTES;
-                            const uint32_t alo = desc_lo(sA, a.desclo0A), blo = desc_lo(sA + OM_A_BYTES, a.desclo0B);
-#pragma unroll
-                            for (int k4 = 0; k4 < 4; ++k4)                        // 4 x 32 K-bytes of the stage
-                                umma_i8_2cta(d_tmem, (static_cast<uint64_t>(a.deschiA) << 32) | (alo + a.kadvA * k4),
-                                             (static_cast<uint64_t>(a.deschiB) << 32) | (blo + a.kadvB * k4), a.idesc, (j | k4) != 0 ? 1u : 0u);
-                            umma_commit_pair(bar0 + 64 + 8 * stage);             // frees the smem stage in both CTAs
-                            if (j + 1 == nkb) umma_commit_pair(bar0 + 128 + 8 * buf);   // level finished -> epilogue warps
-                        }
-                        __syncwarp();
+                        const uint32_t alo = alo0 + stage * (OM_STAGE_BYTES >> 4), blo = blo0 + stage * (OM_STAGE_BYTES >> 4);
+                        umma_i8_2cta(d_tmem, alo, a.deschiA, blo, a.deschiB, a.idesc, acc);       // 4 x 32 K-bytes of the stage
+                        umma_i8_2cta(d_tmem, alo + a.kadvA, a.deschiA, blo + a.kadvB, a.deschiB, a.idesc, 1u);
+                        umma_i8_2cta(d_tmem, alo + 2 * a.kadvA, a.deschiA, blo + 2 * a.kadvB, a.deschiB, a.idesc, 1u);
+                        umma_i8_2cta(d_tmem, alo + 3 * a.kadvA, a.deschiA, blo + 3 * a.kadvB, a.deschiB, a.idesc, 1u);
+                        acc = 1u;
+                        umma_commit_pair(bar0 + 64 + 8 * stage);                 // frees the smem stage in both CTAs
                     }
+                    umma_commit_pair(bar0 + 128 + 8 * buf);                       // level finished -> epilogue warps
                 }
             }
         }
+        __syncwarp();
     } else {
         // ------------------------------------------------------------------ epilogue warps: fold levels in fp64 registers
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
