@@ -18,7 +18,7 @@ EXPORTS = [
     "gpz_last_error", "gpz_version", "gpz_theta_len", "gpz_g_dim", "gpz_create", "gpz_destroy",
     "gpz_comm_unique_id", "gpz_comm_init", "gpz_eval", "gpz_eval_dev", "gpz_fit", "gpz_phi", "gpz_get_prior", "gpz_rows",
     "gpz_predict", "gpz_inv_logdet", "gpz_dxy", "gpz_stream", "gpz_sync", "gpz_launch_count",
-    "gpz_last_timing", "gpz_set_option",
+    "gpz_last_timing", "gpz_set_option", "gpz_dgemm_nt",
 ]
 
 
@@ -83,6 +83,8 @@ def load():
     lib.gpz_sync.argtypes = [C.c_void_p]
     lib.gpz_launch_count.restype = C.c_int64
     lib.gpz_launch_count.argtypes = [C.c_void_p]
+    lib.gpz_dgemm_nt.restype = C.c_int
+    lib.gpz_dgemm_nt.argtypes = [C.c_int64, C.c_int64, C.c_int64, _dp, C.c_int64, _dp, C.c_int64, _dp, C.c_int64, C.c_int32, C.c_int]
     lib.gpz_last_timing.restype = C.c_int
     lib.gpz_last_timing.argtypes = [C.c_void_p, _dp]
     lib.gpz_set_option.restype = C.c_int
@@ -257,3 +259,15 @@ def dxy(X, Y, device=0):
     D = np.empty((n, m), order="F")
     check(load().gpz_dxy(n, m, d, ptr(X), ptr(Y), ptr(D), int(device)))
     return D
+
+
+def dgemm_nt(A, B, digits=7, device=0):
+    """C = A @ B.T in fp64 through the int8 tensor cores (gpz_dgemm_nt): A (M x K), B (N x K) C-contiguous."""
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    B = np.ascontiguousarray(B, dtype=np.float64)
+    M, K = A.shape
+    N, K2 = B.shape
+    assert K == K2
+    Cm = np.empty((M, N), dtype=np.float64)
+    check(load().gpz_dgemm_nt(M, N, K, ptr(A), K, ptr(B), K, ptr(Cm), N, int(digits), int(device)))
+    return Cm

@@ -889,9 +889,9 @@ int forward_and_solve(gpz_ctx* c, const double* d_theta) {
                     ++c->launches;
                 }
                 if ((rc = ozaki_digits(phi, MP, static_cast<int>(MP), P.m, r1 - r0, c->opt_ozaki, c->ob + r0, c->d_scal, c->aug ? 1 : 0,
-                                       c->oz_D8, c->oz_F8, c->oz_ea, st, &c->launches))) return rc;
+                                       c->oz_D8, c->oz_F8, c->oz_ea, c->sws.flag, st, &c->launches))) return rc;
                 if ((rc = ozaki_gram(c->oz_F8, c->oz_D8, static_cast<int>(MP), P.m, r1 - r0, c->opt_ozaki, c->opt_ozaki_gs, c->d_scal,
-                                     c->aug ? 1 : 0, nchunks > 0, c->S, c->ozg_ws, st, &c->launches))) return rc;
+                                     c->aug ? 1 : 0, nchunks > 0, c->S, c->ozg_ws, c->sws.flag, st, &c->launches))) return rc;
                 if (timed) GPZ_CUDA(cudaEventRecord(c->kev[1], st));
                 continue;
             }
@@ -1004,7 +1004,7 @@ int eval_device(gpz_ctx* c, const double* d_theta, double* d_out) {
                 // the plain digits of this chunk are still there when PHI is resident and the Gram went through them
                 if (o == 0 && !(c->resident && c->opt_ozaki_gram > 0))
                     if ((rc = ozaki_digits(phi, MP, static_cast<int>(MP), P.m, rows, c->opt_ozaki, nullptr, c->d_scal, 0, c->oz_D8, nullptr,
-                                           c->oz_ea, st, &c->launches))) return rc;
+                                           c->oz_ea, c->sws.flag, st, &c->launches))) return rc;
                 if ((rc = ozaki_tgemm(phi, MP, c->oz_D8, c->oz_ea, c->Sinv + static_cast<int64_t>(o) * MP * MP, static_cast<int>(MP), P.m,
                                       rows, c->opt_ozaki, c->ob + o * n + r0, c->H, o > 0, c->nupart + r0, n,
                                       c->aug ? c->w + o * MP : nullptr, c->aug ? c->pred + r0 : nullptr, c->oz_ws, st,
@@ -1873,6 +1873,91 @@ int gpz_dxy(int64_t n, int32_t m, int32_t d, const double* X, const double* Y, d
     cudaFree(dX);
     cudaFree(dY);
     cudaFree(dD);
+    return rc;
+}
+
+namespace {
+__global__ void pad_rows_kernel(const double* __restrict__ src, int64_t ld, int64_t rows, int64_t K, int64_t Kp, double* __restrict__ dst) {
+    const int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (e >= rows * Kp) return;
+    const int64_t r = e / Kp, c = e - r * Kp;
+    dst[e] = c < K ? src[r * ld + c] : 0.0;
+}
+}  // namespace
+
+int gpz_dgemm_nt(int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
+                 int32_t digits, int device) {
+    if (M < 1 || N < 1 || K < 1 || K > 16384 || M > (1 << 30) || N > (1 << 30) || !A || !B || !C || lda < K || ldb < K || ldc < N ||
+        digits < 3 || digits > 7) {
+        set_error("gpz_dgemm_nt: bad arguments (1 <= K <= 16384, digits 3..7)");
+        return GPZ_ERR_USAGE;
+    }
+    int rc;
+    if ((rc = check_device(device))) return rc;
+    if (!ozmma_available()) {
+        set_error("gpz_dgemm_nt: the driver does not export cuTensorMapEncodeTiled");
+        return GPZ_ERR_USAGE;
+    }
+    const int64_t Kp = round_up(K, 128);
+    const int Kpi = static_cast<int>(Kp);
+    std::vector<void*> bufs;
+    auto D = [&](void** p, size_t bytes) {
+        cudaError_t e = cudaMalloc(p, bytes);
+        if (e == cudaSuccess) bufs.push_back(*p);
+        return e;
+    };
+    auto cleanup = [&]() { for (void* b : bufs) cudaFree(b); };
+    double *dA = nullptr, *dB = nullptr, *pA = nullptr, *pB = nullptr, *dC = nullptr, *ea = nullptr, *eb = nullptr, *partial = nullptr;
+    int8_t *A8 = nullptr, *B8 = nullptr;
+    int* flag = nullptr;
+    const int64_t Mp = oz_padded_rows(M), Np = oz_padded_rows(N);
+    const int64_t npart = ozmma_partial_doubles(static_cast<int>(M), static_cast<int>(N), 0, 1, 0);
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = D(reinterpret_cast<void**>(&dA), sizeof(double) * M * lda);
+    if (e == cudaSuccess) e = D(reinterpret_cast<void**>(&dB), sizeof(double) * N * ldb);
+    if (e == cudaSuccess) e = D(reinterpret_cast<void**>(&pA), sizeof(double) * M * Kp);
+    if (e == cudaSuccess) e = D(reinterpret_cast<void**>(&pB), sizeof(double) * N * Kp);
+    if (e == cudaSuccess) e = D(reinterpret_cast<void**>(&dC), sizeof(double) * M * N);
+    if (e == cudaSuccess) e = D(reinterpret_cast<void**>(&ea), sizeof(double) * Mp);
+    if (e == cudaSuccess) e = D(reinterpret_cast<void**>(&eb), sizeof(double) * Np);
+    if (e == cudaSuccess) e = D(reinterpret_cast<void**>(&partial), sizeof(double) * npart);
+    if (e == cudaSuccess) e = D(reinterpret_cast<void**>(&A8), static_cast<size_t>(Mp) * digits * Kp);
+    if (e == cudaSuccess) e = D(reinterpret_cast<void**>(&B8), static_cast<size_t>(Np) * digits * Kp);
+    if (e == cudaSuccess) e = D(reinterpret_cast<void**>(&flag), sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(dA, A, sizeof(double) * M * lda, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dB, B, sizeof(double) * N * ldb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(flag, 0, sizeof(int));
+    if (e != cudaSuccess) {
+        set_error("gpz_dgemm_nt: CUDA error %s", cudaGetErrorString(e));
+        cleanup();
+        return GPZ_ERR_CUDA;
+    }
+    int64_t launches = 0;
+    pad_rows_kernel<<<static_cast<unsigned>(ceil_div(M * Kp, 256)), 256>>>(dA, lda, M, K, Kp, pA);
+    pad_rows_kernel<<<static_cast<unsigned>(ceil_div(N * Kp, 256)), 256>>>(dB, ldb, N, K, Kp, pB);
+    rc = ozaki_digits(pA, Kp, Kpi, static_cast<int>(K), M, digits, nullptr, nullptr, 0, A8, nullptr, ea, flag, nullptr, &launches);
+    if (!rc) rc = ozaki_digits(pB, Kp, Kpi, static_cast<int>(K), N, digits, nullptr, nullptr, 0, B8, nullptr, eb, flag, nullptr, &launches);
+    if (!rc) {
+        // digits addressed {k, digit, row, chunk}; the row scales ea, eb carry the 256^-1 of the digit convention
+        const int64_t str[3] = {Kp, static_cast<int64_t>(digits) * Kp, static_cast<int64_t>(digits) * Kp * Mp};
+        const int64_t strB[3] = {Kp, static_cast<int64_t>(digits) * Kp, static_cast<int64_t>(digits) * Kp * Np};
+        rc = ozmma_gemm_nt(A8, str, static_cast<int>(M), B8, strB, static_cast<int>(N), digits, digits + 1, Kpi, 1, 0, 0, partial, ea, eb,
+                           1.0, 0, dC, N, 0, nullptr, &launches);
+    }
+    int hflag = 0;
+    if (!rc) {
+        e = cudaMemcpy(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy2D(C, sizeof(double) * ldc, dC, sizeof(double) * N, sizeof(double) * N, M, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            set_error("gpz_dgemm_nt: CUDA error %s", cudaGetErrorString(e));
+            rc = GPZ_ERR_CUDA;
+        }
+    }
+    cleanup();
+    if (!rc && hflag) {          // non-finite inputs: propagate NaN (error convention)
+        for (int64_t i = 0; i < M; ++i)
+            for (int64_t j = 0; j < N; ++j) C[i * ldc + j] = nan("");
+    }
     return rc;
 }
 

@@ -146,10 +146,10 @@ int64_t oz_digit_bytes(int MP, int s, int64_t rows);
 int64_t oz_workspace_bytes(int MP, int s);
 int64_t oz_gram_workspace_bytes(int MP, int64_t rows);
 int ozaki_digits(const double* Phi, int64_t ld, int MP, int m, int64_t rows, int s, const double* wgt, const double* d_scal, int aug,
-                 int8_t* D8, int8_t* F8, double* ea, cudaStream_t st, int64_t* launches);
+                 int8_t* D8, int8_t* F8, double* ea, int* flag, cudaStream_t st, int64_t* launches);
 // S (+)= PHI' diag(wgt) PHI over `rows` rows through the int8 tensor cores (digits from ozaki_digits)
 int ozaki_gram(const int8_t* F8, const int8_t* D8, int MP, int m, int64_t rows, int s, int gs, const double* d_scal, int aug,
-               int accumulate, double* S, void* ws, cudaStream_t st, int64_t* launches);
+               int accumulate, double* S, void* ws, const int* flag, cudaStream_t st, int64_t* launches);
 int ozaki_tgemm(const double* Phi, int64_t ld, const int8_t* D8, const double* ea, const double* Sinv, int MP, int m, int64_t n, int s,
                 const double* rw, double* H, int accumulate, double* nupart, int64_t nu_ld, const double* waug, double* pred, void* ws,
                 cudaStream_t st, cudaEvent_t tev0, cudaEvent_t tev1, int64_t* launches);

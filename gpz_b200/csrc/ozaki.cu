@@ -45,7 +45,8 @@ __device__ __forceinline__ double pow2_ceil(double v) {
 //   Rows in [n, n_pad) are zero-filled (the Gram contracts over whole 1024-row chunks).
 __global__ void __launch_bounds__(256)
 oz_digits_kernel(const double* __restrict__ Phi, int64_t ld, int m, int MP, int64_t n, int64_t n_pad, int s, const double* __restrict__ wgt,
-                 const double* __restrict__ scal, int aug, int8_t* __restrict__ D8, int8_t* __restrict__ F8, double* __restrict__ ea) {
+                 const double* __restrict__ scal, int aug, int8_t* __restrict__ D8, int8_t* __restrict__ F8, double* __restrict__ ea,
+                 int* __restrict__ flag) {
     const int lane = threadIdx.x & 31;
     const int64_t i = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
     if (i >= n_pad) return;
@@ -61,8 +62,14 @@ oz_digits_kernel(const double* __restrict__ Phi, int64_t ld, int m, int MP, int6
     }
     const double* row = Phi + i * ld;
     double mx = 0.0;
+    bool bad = false;                                   // NaN / Inf cannot be expressed in digits: raise the failure flag instead
     for (int j = lane * 4; j < MP; j += 128) {
         const double4 v = *reinterpret_cast<const double4*>(row + j);
+        const int lim = (aug && fout != nullptr) ? m + 1 : m;
+        if (j < lim) bad |= !(fabs(v.x) <= 1.7e308);
+        if (j + 1 < lim) bad |= !(fabs(v.y) <= 1.7e308);
+        if (j + 2 < lim) bad |= !(fabs(v.z) <= 1.7e308);
+        if (j + 3 < lim) bad |= !(fabs(v.w) <= 1.7e308);
         if (j < m) mx = fmax(mx, fabs(v.x));
         if (j + 1 < m) mx = fmax(mx, fabs(v.y));
         if (j + 2 < m) mx = fmax(mx, fabs(v.z));
@@ -70,6 +77,8 @@ oz_digits_kernel(const double* __restrict__ Phi, int64_t ld, int m, int MP, int6
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (fout != nullptr) bad |= !(fabs(wgt[i]) <= 1.7e308);
+    if (__any_sync(0xffffffffu, bad) && lane == 0 && flag != nullptr) atomicExch(flag, 1);
     const int E = oz_exponent(mx);
     if (lane == 0) ea[i] = ldexp(1.0, E - 8);          // PHI_ij = ea_i * sum_t d_t 256^-(t-1)
     const double sc = ldexp(1.0, 8 * s - E);
@@ -150,14 +159,14 @@ int64_t oz_digit_bytes(int MP, int s, int64_t rows) { return al256(oz_padded_row
 
 // PHI rows -> D8 (and F8 when wgt != nullptr) + ea.  d_scal: [0] >= max w, [1] >= max |y| (device).
 int ozaki_digits(const double* Phi, int64_t ld, int MP, int m, int64_t rows, int s, const double* wgt, const double* d_scal, int aug,
-                 int8_t* D8, int8_t* F8, double* ea, cudaStream_t st, int64_t* launches) {
+                 int8_t* D8, int8_t* F8, double* ea, int* flag, cudaStream_t st, int64_t* launches) {
     if (s < 2 || s > OZ_MAXS) {
         set_error("ozaki: digits per operand must be in [2, %d]", OZ_MAXS);
         return GPZ_ERR_USAGE;
     }
     const int64_t np = oz_padded_rows(rows);
     oz_digits_kernel<<<static_cast<unsigned>(ceil_div(np, 8)), 256, 0, st>>>(Phi, ld, m, MP, rows, np, s, wgt, d_scal, aug, D8,
-                                                                             wgt != nullptr ? F8 : nullptr, ea);
+                                                                             wgt != nullptr ? F8 : nullptr, ea, flag);
     GPZ_KERNEL_CHECK();
     ++*launches;
     return GPZ_OK;
@@ -189,6 +198,12 @@ int ozaki_tgemm(const double* Phi, int64_t ld, const int8_t* D8, const double* e
     return GPZ_OK;
 }
 
+// non-finite inputs were seen while extracting digits: make the Gram (and with it the Cholesky pivot test on every rank of a
+// sharded run, after the allreduce) non-finite, so that NaN is returned like on the fp64 path (error convention)
+__global__ void ozg_poison_kernel(double* __restrict__ S, const int* __restrict__ flag) {
+    if (*flag) S[0] = nan("");
+}
+
 // sr[j] = 2^Ef 256^-2 (x cy for the spare column): S_jl = sr_j sum_e 256^-(e-2) acc_e
 __global__ void ozg_scales_kernel(const double* __restrict__ scal, int MP, int m, int aug, double* __restrict__ sr) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -206,7 +221,7 @@ int64_t oz_gram_workspace_bytes(int MP, int64_t rows) {
 // OZG_CH rows so that s * OZG_CH * 2^14 < 2^31 keeps every int32 level accumulator exact).  Only tiles touching the lower
 // triangle are computed; the result is mirrored.  gs: digits used by the Gram (<= s, the leading ones of the stored digits).
 int ozaki_gram(const int8_t* F8, const int8_t* D8, int MP, int m, int64_t rows, int s, int gs, const double* d_scal, int aug,
-               int accumulate, double* S, void* ws, cudaStream_t st, int64_t* launches) {
+               int accumulate, double* S, void* ws, const int* flag, cudaStream_t st, int64_t* launches) {
     if (gs < 2 || gs > s) {
         set_error("ozaki_gram: unsupported digit count %d (stored %d)", gs, s);
         return GPZ_ERR_USAGE;
@@ -220,8 +235,16 @@ int ozaki_gram(const int8_t* F8, const int8_t* D8, int MP, int m, int64_t rows, 
     ++*launches;
     // addressed {row index j, digit, k = i within chunk, chunk}
     const int64_t str[3] = {MP, static_cast<int64_t>(s) * MP, static_cast<int64_t>(OZG_CH) * s * MP};
-    return ozmma_gemm_nt(F8, str, MP, D8, str, MP, gs, gs + 1, OZG_CH, nch, 1, 1, partial, sr, nullptr, 1.0, accumulate, S, MP, 0, st,
-                         launches);
+    int rc;
+    if ((rc = ozmma_gemm_nt(F8, str, MP, D8, str, MP, gs, gs + 1, OZG_CH, nch, 1, 1, partial, sr, nullptr, 1.0, accumulate, S, MP, 0, st,
+                            launches)))
+        return rc;
+    if (flag != nullptr) {
+        ozg_poison_kernel<<<1, 1, 0, st>>>(S, flag);
+        GPZ_KERNEL_CHECK();
+        ++*launches;
+    }
+    return GPZ_OK;
 }
 
 }  // namespace gpz

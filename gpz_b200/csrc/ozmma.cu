@@ -52,6 +52,7 @@ struct OzmmaArgs {
     uint32_t deschiA, deschiB;   // high words of the smem matrix descriptors
     uint32_t desclo0A, desclo0B; // low-word bits above the start address (LBO field)
     uint32_t kadvA, kadvB;    // descriptor start-address step per 32 K-bytes
+    uint64_t hintA, hintB;    // L2 eviction policy of the operand loads
     // mode 1
     const double* ea;         // [rows] row scales (including 256^-1 .. see ozaki.cu)
     const double* eb;         // [cols] column scales
@@ -116,12 +117,25 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// L2 eviction policies (the encodings createpolicy.fractional.L2::evict_{normal,first,last} produces; cute TMA::CacheHintSm90)
+constexpr uint64_t OM_EVICT_NORMAL = 0x1000000000000000ull, OM_EVICT_FIRST = 0x12F0000000000000ull, OM_EVICT_LAST = 0x14F0000000000000ull;
+
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t smem_dst, uint32_t bar_cluster, int c0, int c1, int c2,
-                                            int c3) {
+                                            int c3, uint64_t hint) {
     asm volatile(
-        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, "
+        "%6}], [%2], %7;"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(hint)
         : "memory");
+}
+// streaming epilogue traffic (PHI in, H / partials out) must not push the operand digits out of L2
+__device__ __forceinline__ double2 ld_stream2(const double* p) {
+    double2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(OM_EVICT_FIRST));
+    return v;
+}
+__device__ __forceinline__ void st_stream2(double* p, double x, double y) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(x), "d"(y), "l"(OM_EVICT_FIRST) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -239,11 +253,11 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                                 if (rank == 0) mbar_arrive_expect_tx(bar0 + 8 * stage, 2 * OM_STAGE_BYTES);
                                 else mbar_arrive_cluster(full_leader);
                                 if (a.mn_major) {
-                                    tma_load_4d(&mapA, sA, full_leader, rowA, t - 1, kb * 128, chunk);
-                                    tma_load_4d(&mapB, sB, full_leader, rowB, uu - 1, kb * 128, chunk);
+                                    tma_load_4d(&mapA, sA, full_leader, rowA, t - 1, kb * 128, chunk, a.hintA);
+                                    tma_load_4d(&mapB, sB, full_leader, rowB, uu - 1, kb * 128, chunk, a.hintB);
                                 } else {
-                                    tma_load_4d(&mapA, sA, full_leader, kb * 128, t - 1, rowA, chunk);
-                                    tma_load_4d(&mapB, sB, full_leader, kb * 128, uu - 1, rowB, chunk);
+                                    tma_load_4d(&mapA, sA, full_leader, kb * 128, t - 1, rowA, chunk, a.hintA);
+                                    tma_load_4d(&mapB, sB, full_leader, kb * 128, uu - 1, rowB, chunk, a.hintB);
                                 }
                             }
                         }
@@ -321,7 +335,7 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                 double* out = a.partial + static_cast<int64_t>(u) * (256 * 128) +
                               static_cast<int64_t>(static_cast<int>(rank) * 128 + rloc) * 128 + half * 64;
 #pragma unroll
-                for (int c = 0; c < 64; c += 2) *reinterpret_cast<double2*>(out + c) = make_double2(st[c], st[c + 1]);
+                for (int c = 0; c < 64; c += 2) st_stream2(out + c, st[c], st[c + 1]);
             } else {
                 const int64_t gi = static_cast<int64_t>(mt) * 256 + static_cast<int64_t>(rank) * 128 + rloc;
                 double rs = 0.0;
@@ -335,7 +349,7 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 #pragma unroll
                     for (int c = 0; c < 64; c += 2) {
                         const double2 sb = *reinterpret_cast<const double2*>(sbp + c);
-                        const double2 p = *reinterpret_cast<const double2*>(ph + c);
+                        const double2 p = ld_stream2(ph + c);
                         const double t0 = st[c] * (sa * sb.x), t1 = st[c + 1] * (sa * sb.y);
                         double h0 = p.x * t0, h1 = p.y * t1;
                         if (col0 + c == a.aug_col) { a.pred[gi] = t0; h0 = 0.0; }
@@ -344,11 +358,11 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                         if (hp != nullptr) {
                             double2 o = make_double2(wrow * h0, wrow * h1);
                             if (a.accumulate) {
-                                const double2 old = *reinterpret_cast<const double2*>(hp + c);
+                                const double2 old = ld_stream2(hp + c);
                                 o.x += old.x;
                                 o.y += old.y;
                             }
-                            *reinterpret_cast<double2*>(hp + c) = o;
+                            st_stream2(hp + c, o.x, o.y);
                         }
                     }
                 }
@@ -430,6 +444,7 @@ EncodeTiledFn encode_fn() {
 //   (one atom here); 32 K-rows = +32 W bytes
 void set_operand_layout(OzmmaArgs& a, int mn_major) {
     a.mn_major = mn_major;
+    a.hintA = a.hintB = OM_EVICT_NORMAL;
     const uint32_t ver = 1u << 14;       // descriptor version 1 at bit 46
     if (!mn_major) {
         a.idesc = OM_IDESC;
@@ -619,6 +634,7 @@ int ozmma_tgemm(const int8_t* A8, const int8_t* B8, int MP, int s, int emax, int
     if ((rc = make_map(&mB, B8, dB, sB, 64))) return rc;
     OzmmaArgs a = {};
     set_operand_layout(a, 0);
+    a.hintB = OM_EVICT_LAST;          // the iSigma digits are read by every tile
     a.s = s;
     a.emin = 2;
     a.emax = emax;

@@ -117,6 +117,14 @@ int gpz_inv_logdet(int32_t m, const double* X, double* Xi, double* logdet, int d
 /* ---- D = Dxy(X,Y)  (GPz/Dxy.m:1-10): X n x d, Y m x d -> D n x m -------------------------------- */
 int gpz_dxy(int64_t n, int32_t m, int32_t d, const double* X, const double* Y, double* D, int device);
 
+/* ---- C = A * B'  in fp64 through the int8 tensor cores (the engine of the Gram and T-GEMM steps of GPz.m:63-72,
+ * exposed for testing and reuse): A is M x K, B is N x K, C is M x N, all ROW-major with leading dimensions lda, ldb, ldc.
+ * Every row of A and B is scaled by a power of two and cut into `digits` (3..7) balanced base-256 digits; the digit
+ * products are exact int8 tcgen05 GEMMs, digit pairs below 256^-digits of (row scale x row scale) are dropped.
+ * digits = 7 is more accurate than an fp64 GEMM (error <= ~K 2^-56 max|A_i| max|B_j|).  K <= 16384.              */
+int gpz_dgemm_nt(int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+                 int64_t ldc, int32_t digits, int device);
+
 /* ---- plumbing / measurement ------------------------------------------------------------------- */
 void* gpz_stream(gpz_ctx* ctx);                 /* cudaStream_t the context enqueues on            */
 int   gpz_sync(gpz_ctx* ctx);
@@ -124,9 +132,9 @@ int64_t gpz_launch_count(const gpz_ctx* ctx);   /* kernels launched by this cont
 /* device time (ms, CUDA events on the context stream) of the phases of the LAST eval:
  * [0] phi build  [1] row weights + Gram + PHI'Wy (+allreduce #1)  [2] solve  [3] PHI w + T-GEMM + row gradients
  * [4] dPHI + back-projection + validation + finish (+allreduce #2)  [5] total
- * [6] the Gram step alone  [7] the T-GEMM step alone (fp64 DMMA kernel, or slicing + int8 level GEMMs + combine)
- * [8] the int8 level GEMMs of row chunk 0 (ms)  [9] int8 operations those GEMMs executed
- * [10] int8 slices in use (0 = fp64 DMMA path)  [11] 1 if the Gram also runs on the int8 tensor cores   */
+ * [6] the Gram step alone  [7] the T-GEMM step alone (fp64 DMMA kernel, or column digits + the tcgen05 digit GEMM)
+ * [8] the tcgen05 digit-GEMM launch of T = PHI iSigma (ms)  [9] int8 operations that launch executed
+ * [10] base-256 digits in use (0 = fp64 DMMA path)  [11] 1 if the Gram also runs on the int8 tensor cores   */
 int gpz_last_timing(gpz_ctx* ctx, double ms[12]);
 int gpz_set_option(gpz_ctx* ctx, const char* name, double value);
 

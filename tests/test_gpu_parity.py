@@ -311,3 +311,61 @@ def test_int8_tensor_core_tgemm_matches_fp64(method, slices, tol):
         gb0, gb1 = grad_blocks(model, g0), grad_blocks(model, g1)
         for nm in gb0:
             assert rel(gb1[nm], gb0[nm]) <= tol, (key, nm, rel(gb1[nm], gb0[nm]))
+
+
+def _exact_matmul_nt(A, B):
+    """A @ B.T in exact rational arithmetic (every double is an integer times a power of two)."""
+    from fractions import Fraction
+    fa = [[Fraction(float(v)) for v in row] for row in A]
+    fb = [[Fraction(float(v)) for v in row] for row in B]
+    return [[sum(x * y for x, y in zip(ra, rb)) for rb in fb] for ra in fa]
+
+
+@pytest.mark.parametrize("M,N,K,digits", [(37, 29, 200, 7), (300, 130, 128, 7), (64, 48, 1000, 6), (20, 260, 333, 5)])
+def test_digit_gemm_against_exact_arithmetic(M, N, K, digits):
+    """gpz_dgemm_nt (digit extraction + the hand-written tcgen05 kernel of ozmma.cu) against exact rational arithmetic:
+    ragged sizes (TMA zero fill), rows of very different magnitude (per-row scales), sign changes."""
+    rng = np.random.default_rng(100 + digits)
+    A = rng.standard_normal((M, K)) * np.exp(rng.uniform(-20, 20, (M, 1)))
+    B = rng.standard_normal((N, K)) * np.exp(rng.uniform(-20, 20, (N, 1)))
+    A[:, ::7] *= 1e-6                      # wide dynamic range inside the rows as well
+    C = L.dgemm_nt(A, B, digits=digits)
+    exact = _exact_matmul_nt(A[:12], B[:10])                     # a corner is enough for the exact check (pure Python)
+    amax, bmax = np.max(np.abs(A), axis=1), np.max(np.abs(B), axis=1)
+    bound = 2.0 ** (-8 * digits + 4) * K                        # dropped digit pairs + digit rounding, relative to the scales
+    for i in range(12):
+        for j in range(10):
+            err = abs(float(exact[i][j] - __import__("fractions").Fraction(float(C[i, j]))))
+            assert err <= bound * amax[i] * bmax[j] + 2.0 ** -52 * abs(float(exact[i][j])), (i, j, err)
+    ref = A @ B.T                                               # and the whole matrix against the fp64 BLAS result
+    tol = max(2.0 ** (-8 * digits + 4), 1e-15) * K
+    assert np.all(np.abs(C - ref) <= tol * np.outer(amax, bmax) + 1e-13 * np.abs(ref))
+    C2 = L.dgemm_nt(A, B, digits=digits)
+    assert np.array_equal(C, C2)                                # static work partition: bit-reproducible
+
+
+def test_digit_gemm_propagates_non_finite_inputs():
+    A = np.ones((8, 128)); B = np.ones((8, 128))
+    A[3, 5] = np.nan
+    assert np.all(np.isnan(L.dgemm_nt(A, B)))
+    with pytest.raises(L.GpzError):
+        L.dgemm_nt(np.ones((4, 20000)), np.ones((4, 20000)))    # K beyond the exact-accumulation bound
+
+
+@pytest.mark.parametrize("slices", [0, 7])
+def test_non_finite_parameters_return_nan(slices):
+    """Error convention: numerical trouble returns NaN with status 0, minFunc's isLegal handles it
+    (WolfeLineSearch.m:53) -- also on the int8 digit path, where NaN cannot be expressed in digits."""
+    model, theta, X, Y, Psi, omega, tr, va = problem("VC", True, False, False, n=2000, d=4, m=60, seed=5)
+    gm = L.make_model(model.d, 1, model.m, "VC", True)
+    ctx = L.Context(gm, X, Y, None, omega, tr, va)
+    ctx.set_option("ozaki_slices", slices)
+    f, g, st = ctx.eval(theta)
+    assert np.isfinite(f) and np.all(np.isfinite(g))
+    bad = theta.copy()
+    bad[3] = np.nan
+    f, g, st = ctx.eval(bad)
+    assert np.isnan(f) and np.all(np.isnan(g))
+    f2, g2, _ = ctx.eval(theta)                                  # and the context recovers
+    assert np.isfinite(f2) and np.all(np.isfinite(g2))
+    ctx.close()
