@@ -300,7 +300,8 @@ def run_gpu(args):
                               "levels folded in fp64 registers, fused nu/H epilogue): T = PHI*iSigma, one launch over all rows" % tm["int8_slices"],
                     "achieved": ach, "peak": 2.0 * bf16, "unit": "TFLOP/s", "frac": ach / (2.0 * bf16),
                     "ops": "int8 multiply-adds x2 executed by that launch (2 n MP^2 per digit pair, s(s+1)/2 pairs)",
-                    "traffic": prof.get("ozmma_tgemm_dram_bytes_per_launch"), "peak_source": src,
+                    "traffic": prof.get("ozmma_tgemm_dram_bytes_per_launch") if n_loc == 1000000 and name == "target" else None,
+                    "peak_source": src,
                     "kernel_ms": tm["i8_gemms_ms"], "executed_ops": tm["i8_gemms_ops"],
                     "int8_slices": tm["int8_slices"], "int8_gram": tm["int8_gram"]}
         else:
