@@ -2,36 +2,13 @@
 // GPz/GPz.m:67).  The reference pseudo-inverts by SVD; SIGMA = PHI' W PHI + diag(alpha) is SPD by
 // construction (alpha > 0), so this is a blocked right-looking Cholesky (64-wide panels: diagonal
 // block factored and inverted by one CTA in shared memory, panel solve and trailing update as DMMA
-// GEMMs), a blocked triangular inverse and one W'W product.  A non-positive pivot raises a device
+// GEMMs), a blocked triangular inverse (recursive doubling) and one W'W product.  A non-positive pivot raises a device
 // flag; the caller turns that into NaN outputs (SURVEY.md 8b "error convention", H3).
 #include "internal.cuh"
 
 namespace gpz {
 
 constexpr int NB = 64;
-
-// warp-synchronous Cholesky of the 32 x 32 block at (o,o) of the smem tile A (lower, in place); lane = row.
-// (A register/shuffle variant was measured slower: 2.7 vs 2.2 ms for the whole m=1000 solve.)
-// returns false (uniformly) on a non-positive pivot; *ld2 accumulates 2*sum(log L_cc)
-__device__ __forceinline__ bool chol32(double (*A)[NB + 1], int o, double* ld2) {
-    const int lane = threadIdx.x & 31;
-    for (int c = 0; c < 32; ++c) {
-        const double piv = A[o + c][o + c];
-        if (!(piv > 0.0)) return false;
-        const double l = sqrt(piv);
-        *ld2 += 2.0 * log(l);
-        __syncwarp();
-        if (lane == c) A[o + c][o + c] = l;
-        else if (lane > c) A[o + lane][o + c] /= l;
-        __syncwarp();
-        if (lane > c) {
-            const double arc = A[o + lane][o + c];
-            for (int q = c + 1; q <= lane; ++q) A[o + lane][o + q] -= arc * A[o + q][o + c];
-        }
-        __syncwarp();
-    }
-    return true;
-}
 
 // W(o..o+32, o..o+32) = inverse of the lower-triangular 32 x 32 block of A at (o,o); lane = column (forward substitution
 // by rows, no cross-lane traffic: L[r][q] is a broadcast read)
@@ -49,10 +26,10 @@ __device__ __forceinline__ void trinv32(double (*A)[NB + 1], double (*W)[NB + 1]
 }
 
 // C(32x32 at (ro,co) of Cm) = alpha * sum_k X[xr+i][xc+k] * Y(k,j) + beta*C, Y(k,j) = Yt ? Ym[yr+j][yc+k] : Ym[yr+k][yc+j];
-// all 128 threads, 8 outputs each
+// all threads of the CTA
 __device__ __forceinline__ void mm32(double (*Cm)[NB + 1], int ro, int co, double alpha, double (*X)[NB + 1], int xr, int xc,
                                      double (*Ym)[NB + 1], int yr, int yc, bool Yt, double beta, bool lower_only) {
-    for (int e = threadIdx.x; e < 1024; e += 128) {
+    for (int e = threadIdx.x; e < 1024; e += blockDim.x) {
         const int i = e >> 5, j = e & 31;
         if (lower_only && j > i) continue;
         double s = 0.0;
@@ -62,64 +39,89 @@ __device__ __forceinline__ void mm32(double (*Cm)[NB + 1], int ro, int co, doubl
     }
 }
 
+// right-looking Cholesky of the 64 x 64 smem tile A (lower, in place) by the whole CTA (256 threads).  Thread (r, q0) keeps
+// the entries A[r][q], q = q0 (mod 4), q <= r, in REGISTERS for the whole factorisation; per column c the owners publish the
+// (unscaled) column through a double-buffered smem vector, every thread derives the pivot's reciprocal square root itself
+// (no broadcast, no fp64 division or log in the serial chain) and applies the rank-1 update to its registers.
+// One barrier per column.  returns false (uniformly) on a non-positive / non-finite pivot.
+__device__ __forceinline__ bool chol64(double (*A)[NB + 1], double (*colbuf)[NB]) {
+    const int tid = threadIdx.x;
+    const int r = tid >> 2, q0 = tid & 3;
+    double reg[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int q = q0 + 4 * k;
+        reg[k] = (q <= r) ? A[r][q] : 0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {                         // fully unrolled: register indices and the update range are static
+        double* col = colbuf[c & 1];
+        if ((c & 3) == q0 && r >= c) {                     // owner of (r, c): publish the finished, unscaled column entry
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                if (k == (c >> 2)) col[r] = reg[k];
+        }
+        __syncthreads();
+        const double piv = col[c];
+        if (!(piv > 0.0) || !(piv < 1.7e308)) return false;
+        const double rl = rsqrt(piv);
+        if (r >= c) {
+            const double arc = col[r] * rl;                // L[r][c]
+            if ((c & 3) == q0) A[r][c] = (r == c) ? piv * rl : arc;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int q = q0 + 4 * k;
+                if (q > c && q <= r) reg[k] -= arc * (col[q] * rl);
+            }
+        }
+    }
+    __syncthreads();
+    return true;
+}
+
 // factor the nb x nb diagonal block at (k0,k0) in place (lower), invert the factor into Linv (row-major 64 x 64, zero
-// upper triangle), accumulate logdet.  The 64 x 64 block is handled as 2 x 2 blocks of 32: warp-level Cholesky and
-// triangular inverse on the diagonal blocks, 32^3 products by the whole CTA in between.  Rows/cols >= nb are padded
+// upper triangle), accumulate logdet.  Cholesky of the 64 x 64 block by the whole CTA; the inverse as 2 x 2 blocks of 32:
+// two warps invert the diagonal blocks concurrently, W21 = -W22 L21 W11 by the whole CTA.  Rows/cols >= nb are padded
 // with the identity.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 potf2_trti_kernel(double* __restrict__ S, int64_t ld, int k0, int nb, double* __restrict__ Linv,
                   double* __restrict__ logdet, int* __restrict__ flag, int first) {
     extern __shared__ double sm_potf[];
     double (*A)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm_potf);
     double (*W)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm_potf + NB * (NB + 1));
     double (*T)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm_potf + 2 * NB * (NB + 1));
-    __shared__ int bad;
-    __shared__ double ldsum;
     const int tid = threadIdx.x, warp = tid >> 5;
-    if (tid == 0) { bad = 0; ldsum = 0.0; }
-    for (int e = tid; e < NB * NB; e += 128) {
+    for (int e = tid; e < NB * NB; e += 256) {
         const int r = e / NB, c = e % NB;
         A[r][c] = (r < nb && c < nb && c <= r) ? S[static_cast<int64_t>(k0 + r) * ld + k0 + c] : (r == c ? 1.0 : 0.0);
         W[r][c] = 0.0;
     }
     __syncthreads();
-    double ld2 = 0.0;
-    if (warp == 0) {                              // L11, W11
-        const bool ok = chol32(A, 0, &ld2);
-        if (!ok && tid == 0) bad = 1;
-        if (ok) trinv32(A, W, 0);
-    }
-    __syncthreads();
-    if (!bad) {
-        mm32(T, 32, 0, 1.0, A, 32, 0, W, 0, 0, true, 0.0, false);       // T21 = A21 * W11'  (= L21)
-        __syncthreads();
-        for (int e = tid; e < 1024; e += 128) A[32 + (e >> 5)][e & 31] = T[32 + (e >> 5)][e & 31];
-        __syncthreads();
-        mm32(A, 32, 32, -1.0, A, 32, 0, A, 32, 0, true, 1.0, true);     // A22 -= L21 L21'  (lower)
-        __syncthreads();
-        if (warp == 0) {                          // L22, W22
-            const bool ok = chol32(A, 32, &ld2);
-            if (!ok && tid == 0) bad = 1;
-            if (ok) trinv32(A, W, 32);
-        }
-        __syncthreads();
-    }
-    if (bad) {
+    __shared__ double colbuf[2][NB];
+    if (!chol64(A, colbuf)) {
         if (tid == 0) *flag = 1;
         return;
     }
+    __shared__ double ldsh[2];
+    if (warp < 2) {                               // 2 * sum_c log L_cc, fixed order
+        double v = 2.0 * log(A[tid][tid]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((tid & 31) == 0) ldsh[warp] = v;
+    }
+    if (warp == 0) trinv32(A, W, 0);              // W11
+    else if (warp == 1) trinv32(A, W, 32);        // W22
+    __syncthreads();
     mm32(T, 32, 0, 1.0, A, 32, 0, W, 0, 0, false, 0.0, false);          // T21 = L21 * W11
     __syncthreads();
     mm32(W, 32, 0, -1.0, W, 32, 32, T, 32, 0, false, 0.0, false);       // W21 = -W22 * T21
     __syncthreads();
-    if (tid == 0) ldsum = ld2;                    // both chol32 calls ran on warp 0: lane 0 holds the full sum
-    __syncthreads();
-    for (int e = tid; e < NB * NB; e += 128) {
+    for (int e = tid; e < NB * NB; e += 256) {
         const int r = e / NB, c = e % NB;
         Linv[e] = (r < nb && c < nb && c <= r) ? W[r][c] : 0.0;
         if (r < nb && c < nb && c <= r) S[static_cast<int64_t>(k0 + r) * ld + k0 + c] = A[r][c];
     }
-    if (tid == 0) *logdet = (first ? 0.0 : *logdet) + ldsum;
+    if (tid == 0) *logdet = (first ? 0.0 : *logdet) + (ldsh[0] + ldsh[1]);
 }
 
 __global__ void zero_kernel(double* p, int64_t n) {
@@ -170,7 +172,7 @@ int spd_inverse(double* S, int m, int MP, double* Sinv, double* d_logdet, SolveW
         const int k0 = kb * NB;
         const int nb = (m - k0 < NB) ? (m - k0) : NB;
         double* Lk = ws.Linv + static_cast<int64_t>(kb) * NB * NB;
-        potf2_trti_kernel<<<1, 128, kPotfSmem, st>>>(S, ld, k0, nb, Lk, d_logdet, ws.flag, kb == 0);
+        potf2_trti_kernel<<<1, 256, kPotfSmem, st>>>(S, ld, k0, nb, Lk, d_logdet, ws.flag, kb == 0);
         GPZ_KERNEL_CHECK();
         ++*launches;
         const int rem = m - k0 - nb;
