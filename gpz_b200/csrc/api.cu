@@ -458,7 +458,7 @@ struct gpz_ctx {
     int rank = 0, world = 1;
     // options
     int64_t opt_chunk_rows = 0;     // 0 = auto
-    int opt_tensor_phi = 1;         // 1: PHI = exp(F W) on the DMMA pipe; 0: direct-difference kernels
+    int opt_tensor_phi = -1;        // 2: PHI = exp(F W) with F W on the int8 tensor cores; 1: on the DMMA pipe; 0: direct-difference kernels
     int opt_fused_bp = 1;           // 1: fused dPHI + back-projection GEMM; 0: materialise dPHI first
     int opt_aug = 1;                // 1: spare-column trick (see aug)
     int opt_ozaki = -1;             // >0: T-GEMM through the int8 tensor cores with this many base-256 digits (ozaki.cu);
@@ -796,6 +796,24 @@ int ensure_workspace(gpz_ctx* c) {
     }
     c->Wc_alloc = P.Wc;
     if (!c->opt_tensor_phi) P.Wc = nullptr;
+    // measured (n=1e6): the int8 variant is epilogue-instruction bound (7 level folds + exp per element: VD m=500 4.6 ms, VC m=1000
+    // 10.9 ms) and does not beat the DMMA kernel (2.9 / 10.0 ms), so the DMMA path stays the default; tensor_phi=2 selects it
+    if (c->opt_tensor_phi < 0) c->opt_tensor_phi = 1;
+    if (c->opt_tensor_phi == 2 && P.Wc != nullptr && P.KQ <= 128 && ozmma_available()) {
+        // PHI = exp(F W) with the quadratic forms on the int8 tensor cores: the digits of the row features are dataset constants
+        for (RowData* R : {&c->tr, &c->va}) {
+            if (R->F == nullptr || R->n <= 0) continue;
+            double* tmp = nullptr;
+            if ((rc = A(&tmp, oz_padded_rows(R->n) * 7 * 128 / 8 + 1))) return rc;
+            R->FD8 = reinterpret_cast<int8_t*>(tmp);
+            if ((rc = A(&R->eaF, oz_padded_rows(R->n)))) return rc;
+            if ((rc = A(&tmp, MP * 7 * 128 / 8 + 1))) return rc;
+            R->WD8 = reinterpret_cast<int8_t*>(tmp);
+            if ((rc = A(&R->ebW, MP))) return rc;
+            R->phi_digits = 7;
+            if ((rc = ozaki_feature_digits(R->F, c->QP, P.q, R->n, 7, R->FD8, R->eaF, nullptr, c->st, &c->launches))) return rc;
+        }
+    }
     c->aug = fast_bp && P.Wc != nullptr && k == 1 && P.m < MP && c->opt_aug;
     if (c->aug) c->tr.ycol = c->tr.Y;
     {
@@ -834,6 +852,7 @@ int ensure_workspace(gpz_ctx* c) {
         GPZ_KERNEL_CHECK();
     }
     if ((rc = solve_ws_alloc(c->sws, static_cast<int>(MP)))) return rc;
+    c->tr.flag = c->va.flag = c->sws.flag;          // non-finite coefficients seen by the int8 PHI build raise the same failure flag
     for (auto& e : c->ev) GPZ_CUDA(cudaEventCreate(&e));
     for (auto& e : c->kev) GPZ_CUDA(cudaEventCreate(&e));
     GPZ_CUDA(cudaMallocHost(&c->h_out, sizeof(double) * (P.p + 5)));
@@ -2028,7 +2047,7 @@ int gpz_set_option(gpz_ctx* c, const char* name, double value) {
             set_error("%s must be set before the first evaluation", name);
             return GPZ_ERR_USAGE;
         }
-        if (name[0] == 't') c->opt_tensor_phi = value != 0.0; else c->opt_fused_bp = value != 0.0;
+        if (name[0] == 't') c->opt_tensor_phi = static_cast<int>(value); else c->opt_fused_bp = value != 0.0;
         return GPZ_OK;
     }
     if (strcmp(name, "ozaki_slices") == 0) {

@@ -50,6 +50,13 @@ struct RowData {          // one resident row set (training or validation rows o
     int has_nan = 0;
     double* F = nullptr;      // [n][QP] monomial row features (fast path only)
     const double* ycol = nullptr;   // set (to Y) when PHI's spare column m should carry y (see api.cu "aug")
+    // int8 PHI build (ozaki.cu ozaki_phi): digits of F (dataset constants) and per-call scratch for the digits of W
+    int8_t* FD8 = nullptr;
+    double* eaF = nullptr;
+    int8_t* WD8 = nullptr;
+    double* ebW = nullptr;
+    int phi_digits = 0;
+    int* flag = nullptr;
     // covariance modes with missing inputs: rows are stored sorted by NaN pattern (NaN entries zero-filled),
     // group g = rows [g_r0[g], g_r1[g]) with pattern g_pat[g]; perm[sorted position] = position in selection order
     std::vector<int64_t> g_r0, g_r1, perm;
@@ -147,6 +154,11 @@ int64_t oz_workspace_bytes(int MP, int s);
 int64_t oz_gram_workspace_bytes(int MP, int64_t rows);
 int ozaki_digits(const double* Phi, int64_t ld, int MP, int m, int64_t rows, int s, const double* wgt, const double* d_scal, int aug,
                  int8_t* D8, int8_t* F8, double* ea, int* flag, cudaStream_t st, int64_t* launches);
+int ozaki_feature_digits(const double* F, int64_t ldf, int q, int64_t rows, int s, int8_t* FD8, double* eaF, int* flag, cudaStream_t st,
+                         int64_t* launches);
+int ozaki_phi(const int8_t* FD8, const double* eaF, const double* W, int kq, int MP, int m, int s, int64_t rows, int8_t* WD8, double* ebW,
+              double* Phi, int ndot, const double* vec0, const double* vec1, double* part0, double* part1, int64_t part_ld,
+              const double* ycol, int* flag, cudaStream_t st, int64_t* launches);
 // S (+)= PHI' diag(wgt) PHI over `rows` rows through the int8 tensor cores (digits from ozaki_digits)
 int ozaki_gram(const int8_t* F8, const int8_t* D8, int MP, int m, int64_t rows, int s, int gs, const double* d_scal, int aug,
                int accumulate, double* S, void* ws, const int* flag, cudaStream_t st, int64_t* launches);
@@ -164,6 +176,9 @@ int64_t ozmma_partial_doubles(int rowsA, int rowsB, int lower, int nchunks, int 
 int ozmma_gemm_nt(const int8_t* A, const int64_t strA[3], int rowsA, const int8_t* B, const int64_t strB[3], int rowsB, int s, int emax,
                   int kchunk, int nchunks, int lower, int mn_major, double* partial, const double* sr, const double* sc, double scale,
                   int accumulate, double* out, int64_t ldo, int pairs_limit, cudaStream_t st, int64_t* launches);
+int ozmma_phi(const int8_t* FD8, const double* eaF, const int8_t* WD8, const double* ebW, int kq, int MP, int m, int s, int64_t rows,
+              double* Phi, int ndot, const double* vec0, const double* vec1, double* part0, double* part1, int64_t part_ld,
+              const double* ycol, cudaStream_t st, int64_t* launches);
 int ozmma_tgemm(const int8_t* A8, const int8_t* B8, int MP, int s, int emax, int64_t rows, const double* ea, const double* eb,
                 const double* Phi, int64_t ld, const double* rw, double* H, int accumulate, double* nupart, int64_t nu_ld, int aug_col,
                 double* pred, cudaStream_t st, int64_t* launches);

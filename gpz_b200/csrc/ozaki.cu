@@ -44,7 +44,8 @@ __device__ __forceinline__ double pow2_ceil(double v) {
 //       w_i 2^E_i y_i / (2^Ef cy), cy = 2^ceil(log2 max|y|), so that row m of the Gram is PHI'(w y)  (GPz/GPz.m:70).
 //   Rows in [n, n_pad) are zero-filled (the Gram contracts over whole 1024-row chunks).
 __global__ void __launch_bounds__(256)
-oz_digits_kernel(const double* __restrict__ Phi, int64_t ld, int m, int MP, int64_t n, int64_t n_pad, int s, const double* __restrict__ wgt,
+oz_digits_kernel(const double* __restrict__ Phi, int64_t ld, int src_cols, int m, int MP, int64_t n, int64_t n_pad, int s,
+                 const double* __restrict__ wgt,
                  const double* __restrict__ scal, int aug, int8_t* __restrict__ D8, int8_t* __restrict__ F8, double* __restrict__ ea,
                  int* __restrict__ flag) {
     const int lane = threadIdx.x & 31;
@@ -63,8 +64,9 @@ oz_digits_kernel(const double* __restrict__ Phi, int64_t ld, int m, int MP, int6
     const double* row = Phi + i * ld;
     double mx = 0.0;
     bool bad = false;                                   // NaN / Inf cannot be expressed in digits: raise the failure flag instead
+    const double4 zero4 = make_double4(0.0, 0.0, 0.0, 0.0);
     for (int j = lane * 4; j < MP; j += 128) {
-        const double4 v = *reinterpret_cast<const double4*>(row + j);
+        const double4 v = j < src_cols ? *reinterpret_cast<const double4*>(row + j) : zero4;
         const int lim = (aug && fout != nullptr) ? m + 1 : m;
         if (j < lim) bad |= !(fabs(v.x) <= 1.7e308);
         if (j + 1 < lim) bad |= !(fabs(v.y) <= 1.7e308);
@@ -88,7 +90,7 @@ oz_digits_kernel(const double* __restrict__ Phi, int64_t ld, int m, int MP, int6
         fy = fs / pow2_ceil(scal[1]);
     }
     for (int j = lane * 4; j < MP; j += 128) {
-        const double4 v = *reinterpret_cast<const double4*>(row + j);
+        const double4 v = j < src_cols ? *reinterpret_cast<const double4*>(row + j) : zero4;
         const double x[4] = {v.x, v.y, v.z, v.w};
         long long I[4], J[4];
 #pragma unroll
@@ -165,7 +167,7 @@ int ozaki_digits(const double* Phi, int64_t ld, int MP, int m, int64_t rows, int
         return GPZ_ERR_USAGE;
     }
     const int64_t np = oz_padded_rows(rows);
-    oz_digits_kernel<<<static_cast<unsigned>(ceil_div(np, 8)), 256, 0, st>>>(Phi, ld, m, MP, rows, np, s, wgt, d_scal, aug, D8,
+    oz_digits_kernel<<<static_cast<unsigned>(ceil_div(np, 8)), 256, 0, st>>>(Phi, ld, MP, m, MP, rows, np, s, wgt, d_scal, aug, D8,
                                                                              wgt != nullptr ? F8 : nullptr, ea, flag);
     GPZ_KERNEL_CHECK();
     ++*launches;
@@ -245,6 +247,61 @@ int ozaki_gram(const int8_t* F8, const int8_t* D8, int MP, int m, int64_t rows, 
         ++*launches;
     }
     return GPZ_OK;
+}
+
+// ---- PHI = exp(F W) through the int8 tensor cores (ozmma_phi) ---------------------------------------------------------
+// digits of the monomial row features F [rows][ldf] (q valid columns, dataset constants: done once) -> FD8 [rows_pad][s][128]
+int ozaki_feature_digits(const double* F, int64_t ldf, int q, int64_t rows, int s, int8_t* FD8, double* eaF, int* flag, cudaStream_t st,
+                         int64_t* launches) {
+    if (q > 128 || ldf % 4 != 0) {
+        set_error("ozaki_feature_digits: feature width %d (ld %lld) not supported", q, static_cast<long long>(ldf));
+        return GPZ_ERR_USAGE;
+    }
+    const int64_t np = oz_padded_rows(rows);
+    oz_digits_kernel<<<static_cast<unsigned>(ceil_div(np, 8)), 256, 0, st>>>(F, ldf, static_cast<int>(ldf < 128 ? ldf : 128), q, 128, rows, np, s,
+                                                                             nullptr, nullptr, 0, FD8, nullptr, eaF, flag);
+    GPZ_KERNEL_CHECK();
+    ++*launches;
+    return GPZ_OK;
+}
+
+// coefficient columns W [kq][MP] (row k, basis j) -> WD8 [j][u][128] (K = k contiguous, zero padded), scales ebW[j]
+__global__ void __launch_bounds__(128)
+oz_wdigits_kernel(const double* __restrict__ W, int kq, int MP, int m, int s, int8_t* __restrict__ WD8, double* __restrict__ ebW,
+                  int* __restrict__ flag) {
+    __shared__ double sh[4];
+    __shared__ int Esh;
+    const int j = blockIdx.x, k = threadIdx.x;
+    const double v = (k < kq && j < m) ? W[static_cast<int64_t>(k) * MP + j] : 0.0;
+    if (!(fabs(v) <= 1.7e308) && flag != nullptr) atomicExch(flag, 1);
+    double mx = fabs(v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((k & 31) == 0) sh[k >> 5] = mx;
+    __syncthreads();
+    if (k == 0) {
+        mx = fmax(fmax(sh[0], sh[1]), fmax(sh[2], sh[3]));
+        const int E = oz_exponent(mx);
+        Esh = E;
+        ebW[j] = ldexp(1.0, E - 8);
+    }
+    __syncthreads();
+    long long I = __double2ll_rn(v * ldexp(1.0, 8 * s - Esh));
+    int8_t* out = WD8 + static_cast<int64_t>(j) * s * 128 + k;
+    for (int u = s - 1; u >= 0; --u) out[u * 128] = static_cast<int8_t>(oz_digit(I));
+}
+
+int ozaki_phi(const int8_t* FD8, const double* eaF, const double* W, int kq, int MP, int m, int s, int64_t rows, int8_t* WD8, double* ebW,
+              double* Phi, int ndot, const double* vec0, const double* vec1, double* part0, double* part1, int64_t part_ld,
+              const double* ycol, int* flag, cudaStream_t st, int64_t* launches) {
+    if (kq > 128) {
+        set_error("ozaki_phi: K = %d > 128", kq);
+        return GPZ_ERR_USAGE;
+    }
+    oz_wdigits_kernel<<<MP, 128, 0, st>>>(W, kq, MP, m, s, WD8, ebW, flag);
+    GPZ_KERNEL_CHECK();
+    ++*launches;
+    return ozmma_phi(FD8, eaF, WD8, ebW, kq, MP, m, s, rows, Phi, ndot, vec0, vec1, part0, part1, part_ld, ycol, st, launches);
 }
 
 }  // namespace gpz

@@ -11,8 +11,8 @@
 //   * warp 0 (one lane) streams the digit tiles with TMA (4-D tensor maps {k, digit, row, chunk}, 128B swizzle) through an
 //     8-stage mbarrier pipeline; warp 1 of the leader CTA (one lane) issues the MMAs of all digit pairs of a level into
 //     one TMEM accumulator; TMEM holds two accumulators so level e-1 is multiplied while level e is folded;
-//   * 8 epilogue warps read the finished level with tcgen05.ld and fold it into an fp64 running sum held in REGISTERS
-//     (128 x 128 doubles per CTA = 64 per thread), smallest level first, so the int32 level results never touch HBM;
+//   * 16 epilogue warps read the finished level with tcgen05.ld and fold it into an fp64 running sum held in REGISTERS
+//     (128 x 128 doubles per CTA = 32 per thread), smallest level first, so the int32 level results never touch HBM;
 //   * after the last level of the tile the same warps apply the GEMM-specific epilogue directly from registers.
 // Work units are (group of K chunks, tile), chunk-group major, dealt round-robin to the CTA pairs: at any time the pairs
 // work on neighbouring tiles of the same K window, so every digit byte is fetched from HBM once and re-streamed from L2
@@ -30,8 +30,8 @@ constexpr int OM_A_BYTES = 128 * 128;                 // 128 rows x 128 K-bytes 
 constexpr int OM_B_BYTES = 64 * 128;                  // this CTA's half of the 128 B rows
 constexpr int OM_STAGE_BYTES = OM_A_BYTES + OM_B_BYTES;
 constexpr int OM_BAR_OFF = OM_STAGES * OM_STAGE_BYTES;
-constexpr int OM_SMEM_BYTES = OM_BAR_OFF + 256 + 1024 + 1024;   // barriers + tmem slot, row sums, + slack for the 1024-byte alignment
-constexpr int OM_THREADS = 320;                       // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue
+constexpr int OM_SMEM_BYTES = OM_BAR_OFF + 256 + 6144 + 1024;   // barriers + tmem slot, row sums, + slack for the 1024-byte alignment
+constexpr int OM_THREADS = 576;                       // warp 0: TMA, warp 1: MMA, warps 2..17: epilogue (4 lane quarters x 4 column groups)
 constexpr uint32_t OM_TMEM_COLS = 256;                // two 128-column int32 accumulators
 // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D = S32, A = B = signed 8 bit, both K-major,
 // N = 128 (>>3 at bit 17), M = 256 (>>4 at bit 24)
@@ -46,7 +46,8 @@ struct OzmmaArgs {
     int gchunks;              // K chunks per work unit (folded one after the other into the fp64 registers)
     int ngroups;              // ceil(nchunks / gchunks); work unit u = group * ntiles + tile
     int lower;                // tile list = tiles touching the lower triangle (Gram); else all tiles_m x tiles_n
-    int mode;                 // 0: fp64 partial tiles, 1: T-GEMM epilogue
+    int mode;                 // 0: fp64 partial tiles, 1: T-GEMM epilogue, 2: PHI = exp(.) epilogue
+    int k4;                   // 32-byte K steps issued per 128-byte k-block (1..4; < 4 when the K padding is known to be zero)
     int mn_major;             // operands stored [k][row] (row index contiguous) instead of [row][k]
     uint32_t idesc;           // UMMA instruction descriptor
     uint32_t deschiA, deschiB;   // high words of the smem matrix descriptors
@@ -65,6 +66,14 @@ struct OzmmaArgs {
     int64_t nu_ld;
     int aug_col;              // -1: none
     double* pred;             // [rows]
+    // mode 2: PHI_ij = exp(ea_i eb_j sum) for j < m, spare column m <- ycol, fused row dots with vec0 / vec1
+    int m;
+    const double* ycol;
+    int ndot;
+    const double* vec0;
+    const double* vec1;
+    double* part0;            // [tiles_n][nu_ld]
+    double* part1;
     // mode 0
     double* partial;          // [ngroups*ntiles][256*128]
 };
@@ -134,6 +143,14 @@ __device__ __forceinline__ double2 ld_stream2(const double* p) {
     asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(OM_EVICT_FIRST));
     return v;
 }
+__device__ __forceinline__ double ld_stream1(const double* p) {
+    double v;
+    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(OM_EVICT_FIRST));
+    return v;
+}
+__device__ __forceinline__ void st_stream1(double* p, double x) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(x), "l"(OM_EVICT_FIRST) : "memory");
+}
 __device__ __forceinline__ void st_stream2(double* p, double x, double y) {
     asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(x), "d"(y), "l"(OM_EVICT_FIRST) : "memory");
 }
@@ -174,6 +191,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lo_bits) { return ((smem_addr >> 4) & 0x3FFFu) | lo_bits; }
@@ -204,7 +229,7 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const uint32_t bar0 = base + OM_BAR_OFF;
     // full[i] = bar0 + 8 i (leader's are used), empty[i] = bar0 + 64 + 8 i, tfull[b] = bar0 + 128 + 8 b, tempty[b] = bar0 + 144 + 8 b
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + OM_BAR_OFF + 192);
-    double* rowsum_sm = reinterpret_cast<double*>(gbase + OM_BAR_OFF + 256);      // [128]
+    double* rowsum_sm = reinterpret_cast<double*>(gbase + OM_BAR_OFF + 256);      // [2][3][128]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
 
@@ -216,7 +241,7 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar0 + 128 + 8 * b, 1);             // one MMA commit
-            mbar_init(bar0 + 144 + 8 * b, 16);            // 8 epilogue warps x 2 CTAs
+            mbar_init(bar0 + 144 + 8 * b, 32);            // 16 epilogue warps x 2 CTAs
         }
         fence_mbar_init();
     }
@@ -285,10 +310,10 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                         mbar_wait(bar0 + 8 * stage, ph);                          // both CTAs' tiles have landed
                         tc_fence_after();
                         const uint32_t alo = alo0 + stage * (OM_STAGE_BYTES >> 4), blo = blo0 + stage * (OM_STAGE_BYTES >> 4);
-                        umma_i8_2cta(d_tmem, alo, a.deschiA, blo, a.deschiB, a.idesc, acc);       // 4 x 32 K-bytes of the stage
-                        umma_i8_2cta(d_tmem, alo + a.kadvA, a.deschiA, blo + a.kadvB, a.deschiB, a.idesc, 1u);
-                        umma_i8_2cta(d_tmem, alo + 2 * a.kadvA, a.deschiA, blo + 2 * a.kadvB, a.deschiB, a.idesc, 1u);
-                        umma_i8_2cta(d_tmem, alo + 3 * a.kadvA, a.deschiA, blo + 3 * a.kadvB, a.deschiB, a.idesc, 1u);
+                        umma_i8_2cta(d_tmem, alo, a.deschiA, blo, a.deschiB, a.idesc, acc);       // up to 4 x 32 K-bytes of the stage
+                        if (a.k4 > 1) umma_i8_2cta(d_tmem, alo + a.kadvA, a.deschiA, blo + a.kadvB, a.deschiB, a.idesc, 1u);
+                        if (a.k4 > 2) umma_i8_2cta(d_tmem, alo + 2 * a.kadvA, a.deschiA, blo + 2 * a.kadvB, a.deschiB, a.idesc, 1u);
+                        if (a.k4 > 3) umma_i8_2cta(d_tmem, alo + 3 * a.kadvA, a.deschiA, blo + 3 * a.kadvB, a.deschiB, a.idesc, 1u);
                         acc = 1u;
                         umma_commit_pair(bar0 + 64 + 8 * stage);                 // frees the smem stage in both CTAs
                     }
@@ -300,30 +325,30 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     } else {
         // ------------------------------------------------------------------ epilogue warps: fold levels in fp64 registers
         const int q = warp & 3;                 // TMEM lane quarter this warp may read
-        const int half = (warp - 2) >> 2;       // which 64 of the 128 accumulator columns
+        const int cg = (warp - 2) >> 2;         // which 32 of the 128 accumulator columns
         const int rloc = q * 32 + lane;         // row inside this CTA's 128 rows
-        double st[64];
+        double st[32];
         uint32_t L = 0;
         const uint32_t tempty_leader0 = mapa_cta(bar0 + 144, 0);
         for (int u = pair; u < U; u += npairs) {
             __syncwarp();
             const int group = u / a.ntiles, tile = u - group * a.ntiles;
 #pragma unroll
-            for (int c = 0; c < 64; ++c) st[c] = 0.0;
+            for (int c = 0; c < 32; ++c) st[c] = 0.0;
             const int nlev = (min(a.nchunks, (group + 1) * a.gchunks) - group * a.gchunks) * (a.emax - a.emin + 1);
             for (int lv = 0, e = a.emax; lv < nlev; ++lv, ++L, e = (e == a.emin ? a.emax : e - 1)) {
                 const uint32_t buf = L & 1u;
                 mbar_wait(bar0 + 128 + 8 * buf, (L >> 1) & 1u);
                 tc_fence_after();
                 const double wgt = __longlong_as_double(static_cast<long long>(1023 - 8 * (e - a.emin)) << 52);   // 256^-(e-emin)
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 128u + static_cast<uint32_t>(half * 64);
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 128u + static_cast<uint32_t>(cg * 32);
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + hh * 32, v);
+                    uint32_t v[16];
+                    tmem_ld16(taddr + hh * 16, v);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) st[hh * 32 + c] = fma(static_cast<double>(static_cast<int>(v[c])), wgt, st[hh * 32 + c]);
+                    for (int c = 0; c < 16; ++c) st[hh * 16 + c] = fma(static_cast<double>(static_cast<int>(v[c])), wgt, st[hh * 16 + c]);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -331,48 +356,121 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             }
             int mt, nt;
             decode_tile(a, tile, mt, nt);
+            // Transpose the warp's 32 x 32 block in registers (5 butterfly stages of shuffles): before, lane = row and st[c] =
+            // column c; after, lane = column and st[r] = row r.  Every global access below is then one 256-byte row segment
+            // per warp instruction instead of 32 rows x 16 bytes.
+#pragma unroll
+            for (int K = 16; K > 0; K >>= 1) {
+                const bool up = (lane & K) != 0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (i & K) continue;
+                    const double give = up ? st[i] : st[i | K];
+                    const double got = __shfl_xor_sync(0xffffffffu, give, K);
+                    if (up) st[i] = got;
+                    else st[i | K] = got;
+                }
+            }
+            const int64_t gi0 = static_cast<int64_t>(mt) * 256 + static_cast<int64_t>(rank) * 128 + q * 32;   // first row of this warp
+            const int col = nt * 128 + cg * 32 + lane;                                                          // this lane's column
             if (a.mode == 0) {
-                double* out = a.partial + static_cast<int64_t>(u) * (256 * 128) +
-                              static_cast<int64_t>(static_cast<int>(rank) * 128 + rloc) * 128 + half * 64;
+                double* out = a.partial + static_cast<int64_t>(u) * (256 * 128) + static_cast<int64_t>(static_cast<int>(rank) * 128 + q * 32) * 128 +
+                              cg * 32 + lane;
 #pragma unroll
-                for (int c = 0; c < 64; c += 2) st_stream2(out + c, st[c], st[c + 1]);
-            } else {
-                const int64_t gi = static_cast<int64_t>(mt) * 256 + static_cast<int64_t>(rank) * 128 + rloc;
-                double rs = 0.0;
-                if (gi < a.rows) {
-                    const double sa = a.ea[gi];
-                    const double wrow = a.rw != nullptr ? a.rw[gi] : 1.0;
-                    const int col0 = nt * 128 + half * 64;
-                    const double* ph = a.Phi + gi * a.ld + col0;
-                    double* hp = a.H != nullptr ? a.H + gi * a.ld + col0 : nullptr;
-                    const double* sbp = a.eb + col0;
+                for (int r = 0; r < 32; ++r) st_stream1(out + r * 128, st[r]);
+                continue;
+            }
+            // st[r] is overwritten by this lane's contribution to the row sum of row r (T-GEMM: PHI .* T; PHI build: PHI * vec0);
+            // the PHI build's optional second dot is reduced first, from the PHI values still in st
+            double second = 0.0;
+            const int ndots = a.mode == 2 ? a.ndot : 1;
+            if (a.mode == 2) {
+                const double sb = a.eb[col];
+                const double v0 = a.ndot > 0 ? a.vec0[col] : 0.0;
+                double* pp = a.H != nullptr ? a.H + gi0 * a.ld + col : nullptr;
 #pragma unroll
-                    for (int c = 0; c < 64; c += 2) {
-                        const double2 sb = *reinterpret_cast<const double2*>(sbp + c);
-                        const double2 p = ld_stream2(ph + c);
-                        const double t0 = st[c] * (sa * sb.x), t1 = st[c + 1] * (sa * sb.y);
-                        double h0 = p.x * t0, h1 = p.y * t1;
-                        if (col0 + c == a.aug_col) { a.pred[gi] = t0; h0 = 0.0; }
-                        if (col0 + c + 1 == a.aug_col) { a.pred[gi] = t1; h1 = 0.0; }
-                        rs += h0 + h1;
-                        if (hp != nullptr) {
-                            double2 o = make_double2(wrow * h0, wrow * h1);
-                            if (a.accumulate) {
-                                const double2 old = ld_stream2(hp + c);
-                                o.x += old.x;
-                                o.y += old.y;
-                            }
-                            st_stream2(hp + c, o.x, o.y);
+                for (int r = 0; r < 32; ++r) {
+                    double p = 0.0;
+                    if (gi0 + r < a.rows) {
+                        if (col < a.m) p = exp(st[r] * (a.ea[gi0 + r] * sb));
+                        else if (a.ycol != nullptr && col == a.m) p = a.ycol[gi0 + r];
+                        if (pp != nullptr) pp[r * a.ld] = p;
+                    }
+                    st[r] = p;
+                }
+                if (a.ndot > 1) {
+                    const double v1 = a.vec1[col];
+                    double red[16];
+                    {
+                        const bool up = (lane & 16) != 0;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const double give = (up ? st[i] : st[i + 16]) * v1, keep = (up ? st[i + 16] : st[i]) * v1;
+                            red[i] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
                         }
                     }
+#pragma unroll
+                    for (int K = 8; K > 0; K >>= 1) {
+                        const bool up = (lane & K) != 0;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            if (i >= K) continue;
+                            const double give = up ? red[i] : red[i + K], keep = up ? red[i + K] : red[i];
+                            red[i] = keep + __shfl_xor_sync(0xffffffffu, give, K);
+                        }
+                    }
+                    second = red[0];
                 }
-                // the two column halves of a row live in warps w and w+4: combine through smem (fixed order)
-                __syncwarp();
-                if (half == 1) rowsum_sm[rloc] = rs;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (half == 0 && gi < a.rows) a.nupart[static_cast<int64_t>(nt) * a.nu_ld + gi] = rs + rowsum_sm[rloc];
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+                for (int r = 0; r < 32; ++r) st[r] *= v0;
+            } else {
+                const double sb = a.eb[col];
+                const double* ph = a.Phi + gi0 * a.ld + col;
+                double* hp = a.H != nullptr ? a.H + gi0 * a.ld + col : nullptr;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    double h = 0.0;
+                    if (gi0 + r < a.rows) {
+                        const double t = st[r] * (a.ea[gi0 + r] * sb);
+                        h = ld_stream1(ph + r * a.ld) * t;
+                        if (col == a.aug_col) {
+                            a.pred[gi0 + r] = t;
+                            h = 0.0;
+                        }
+                        if (hp != nullptr) {
+                            double o = (a.rw != nullptr ? a.rw[gi0 + r] : 1.0) * h;
+                            if (a.accumulate) o += ld_stream1(hp + r * a.ld);
+                            st_stream1(hp + r * a.ld, o);
+                        }
+                    }
+                    st[r] = h;
+                }
             }
+            // row sums over the 32 columns of the warp: butterfly multi-reduction, the total of row r ends in lane r (fixed order)
+#pragma unroll
+            for (int K = 16; K > 0; K >>= 1) {
+                const bool up = (lane & K) != 0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (i >= K) continue;
+                    const double give = up ? st[i] : st[i + K], keep = up ? st[i + K] : st[i];
+                    st[i] = keep + __shfl_xor_sync(0xffffffffu, give, K);
+                }
+            }
+            // the four column groups of a row live in warps w, w+4, w+8, w+12: combine through smem (fixed order)
+            const int64_t gi = gi0 + lane;
+            if (cg > 0) {
+                rowsum_sm[(cg - 1) * 128 + rloc] = st[0];
+                if (ndots > 1) rowsum_sm[384 + (cg - 1) * 128 + rloc] = second;
+            }
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            if (cg == 0 && gi < a.rows) {
+                double* o0 = a.mode == 2 ? a.part0 : a.nupart;
+                if (ndots > 0) o0[static_cast<int64_t>(nt) * a.nu_ld + gi] = ((st[0] + rowsum_sm[rloc]) + rowsum_sm[128 + rloc]) + rowsum_sm[256 + rloc];
+                if (ndots > 1)
+                    a.part1[static_cast<int64_t>(nt) * a.nu_ld + gi] = ((second + rowsum_sm[384 + rloc]) + rowsum_sm[512 + rloc]) + rowsum_sm[640 + rloc];
+            }
+            asm volatile("bar.sync 1, 512;" ::: "memory");
         }
     }
     tc_fence_before();
@@ -444,6 +542,7 @@ EncodeTiledFn encode_fn() {
 //   (one atom here); 32 K-rows = +32 W bytes
 void set_operand_layout(OzmmaArgs& a, int mn_major) {
     a.mn_major = mn_major;
+    a.k4 = 4;
     a.hintA = a.hintB = OM_EVICT_NORMAL;
     const uint32_t ver = 1u << 14;       // descriptor version 1 at bit 46
     if (!mn_major) {
@@ -658,6 +757,60 @@ int ozmma_tgemm(const int8_t* A8, const int8_t* B8, int MP, int s, int emax, int
     a.nu_ld = nu_ld;
     a.aug_col = aug_col;
     a.pred = pred;
+    if ((rc = launch(mA, mB, a, np, st))) return rc;
+    if (launches) ++*launches;
+    return GPZ_OK;
+}
+
+// PHI = exp(F W) (GPz/getPHI.m:60-113 through the monomial expansion of the quadratic forms): FD8 [rows][s][128] digits of
+// the row features (row scales eaF), WD8 [MP][s][128] digits of the per-basis coefficient columns (scales ebW), K = kq <= 128.
+// Fused: spare column m <- ycol, up to two row dots sum_j PHI_ij vec_q[j] as partials [MP/128][part_ld].
+int ozmma_phi(const int8_t* FD8, const double* eaF, const int8_t* WD8, const double* ebW, int kq, int MP, int m, int s, int64_t rows,
+              double* Phi, int ndot, const double* vec0, const double* vec1, double* part0, double* part1, int64_t part_ld,
+              const double* ycol, cudaStream_t st, int64_t* launches) {
+    if (s < 1 || s > 8 || MP % 128 != 0 || kq < 1 || kq > 128 || ndot < 0 || ndot > 2) {
+        set_error("ozmma_phi: unsupported s=%d MP=%d kq=%d", s, MP, kq);
+        return GPZ_ERR_USAGE;
+    }
+    const int np = resident_pairs();
+    if (np <= 0) {
+        set_error("ozmma: cannot configure the tcgen05 kernel: %s", cudaGetErrorString(cudaGetLastError()));
+        return GPZ_ERR_CUDA;
+    }
+    CUtensorMap mA, mB;
+    const int64_t dA[4] = {128, s, rows, 1}, sA[3] = {128, static_cast<int64_t>(s) * 128, round_up(rows * s * 128, 16)};
+    const int64_t dB[4] = {128, s, MP, 1}, sB[3] = {128, static_cast<int64_t>(s) * 128, static_cast<int64_t>(s) * 128 * MP};
+    int rc;
+    if ((rc = make_map(&mA, FD8, dA, sA, 128))) return rc;
+    if ((rc = make_map(&mB, WD8, dB, sB, 64))) return rc;
+    OzmmaArgs a = {};
+    set_operand_layout(a, 0);
+    a.hintB = OM_EVICT_LAST;
+    a.k4 = (kq + 31) / 32;
+    a.s = s;
+    a.emin = 2;
+    a.emax = s + 1;
+    a.kblocks = 1;
+    a.tiles_n = MP / 128;
+    a.ntiles = static_cast<int>(ceil_div(rows, 256)) * a.tiles_n;
+    a.nchunks = 1;
+    a.gchunks = 1;
+    a.ngroups = 1;
+    a.lower = 0;
+    a.mode = 2;
+    a.ea = eaF;
+    a.eb = ebW;
+    a.H = Phi;
+    a.ld = MP;
+    a.rows = rows;
+    a.m = m;
+    a.ycol = ycol;
+    a.ndot = ndot;
+    a.vec0 = vec0;
+    a.vec1 = vec1;
+    a.part0 = part0;
+    a.part1 = part1;
+    a.nu_ld = part_ld;
     if ((rc = launch(mA, mB, a, np, st))) return rc;
     if (launches) ++*launches;
     return GPZ_OK;

@@ -426,9 +426,14 @@ int phi_build(const Params& P, const RowData& R, int64_t r0, int64_t r1, double*
             const int64_t rows = s1 - s0;
             double* p0 = dot_scratch;
             double* p1 = dot_scratch + static_cast<int64_t>(ntn) * rows;
-            rc = phi_gemm(R.F + s0 * P.QP, P.QP, P.KQ, P.Wc + static_cast<int64_t>(pat) * P.KQ * P.MP, P.MP, P.m, rows,
-                          Phi != nullptr ? Phi + (s0 - r0) * P.MP : nullptr, dots.n, dots.vec[0], dots.vec[1], p0, p1, rows,
-                          R.ycol != nullptr ? R.ycol + s0 : nullptr, st, launches);
+            if (R.FD8 != nullptr && P.KQ <= 128)       // quadratic forms on the int8 tensor cores (ozmma.cu), exp in its epilogue
+                rc = ozaki_phi(R.FD8 + s0 * R.phi_digits * 128, R.eaF + s0, P.Wc + static_cast<int64_t>(pat) * P.KQ * P.MP, P.KQ, P.MP, P.m,
+                               R.phi_digits, rows, R.WD8, R.ebW, Phi != nullptr ? Phi + (s0 - r0) * P.MP : nullptr, dots.n, dots.vec[0],
+                               dots.vec[1], p0, p1, rows, R.ycol != nullptr ? R.ycol + s0 : nullptr, R.flag, st, launches);
+            else
+                rc = phi_gemm(R.F + s0 * P.QP, P.QP, P.KQ, P.Wc + static_cast<int64_t>(pat) * P.KQ * P.MP, P.MP, P.m, rows,
+                              Phi != nullptr ? Phi + (s0 - r0) * P.MP : nullptr, dots.n, dots.vec[0], dots.vec[1], p0, p1, rows,
+                              R.ycol != nullptr ? R.ycol + s0 : nullptr, st, launches);
             if (rc) return rc;
             for (int q = 0; q < dots.n; ++q) {
                 sum_parts_kernel<<<static_cast<unsigned>(ceil_div(rows, 256)), 256, 0, st>>>(q == 0 ? p0 : p1, ntn, rows, rows, dots.out[q] + s0);

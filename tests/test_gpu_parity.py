@@ -207,14 +207,14 @@ def test_large_n_properties():
 
 @pytest.mark.parametrize("method", ["VD", "VC", "GL", "GC"])
 def test_tensor_core_phi_and_fused_backproj_agree_with_direct_kernels(method):
-    """The fast path (PHI = exp(F W) on the DMMA pipe, fused dPHI back-projection GEMM) against the
-    direct-difference kernels + materialised dPHI, and both against the oracle."""
+    """The fast paths (PHI = exp(F W) with F W on the int8 tensor cores [2] or on the DMMA pipe [1], fused dPHI
+    back-projection GEMM) against the direct-difference kernels + materialised dPHI, and all against the oracle."""
     model, theta, X, Y, Psi, omega, tr, va = problem(method, True, False, False, n=3000, d=5, m=140, seed=21)
     ref = O.GPz(theta, model, X, Y, None, omega, tr, va)
     ref_fit = O.GPz(theta, model, X, Y, None, omega, tr, None, fit_only=True)
     gm = L.make_model(model.d, 1, model.m, method, True)
     out = {}
-    for tp, fb, sc in ((1, 1, 1), (0, 0, 1), (1, 0, 1), (0, 1, 1), (1, 1, 0)):
+    for tp, fb, sc in ((1, 1, 1), (2, 1, 1), (0, 0, 1), (1, 0, 1), (0, 1, 1), (1, 1, 0), (2, 0, 0)):
         ctx = L.Context(gm, X, Y, None, omega, tr, va)
         ctx.set_option("tensor_phi", tp)
         ctx.set_option("fused_backproj", fb)
