@@ -685,7 +685,15 @@ int upload_rows(gpz_ctx* c, RowData& R, const std::vector<int64_t>& idx, int64_t
         if (mode_is_cov(P.mode)) {
             const int64_t dd = static_cast<int64_t>(P.d) * P.d;
             buf.resize(static_cast<size_t>(n * dd));
-            for (int64_t i = 0; i < n; ++i) memcpy(buf.data() + i * dd, Psi + idx[i] * dd, sizeof(double) * dd);
+            for (int64_t i = 0; i < n; ++i) {
+                memcpy(buf.data() + i * dd, Psi + idx[i] * dd, sizeof(double) * dd);
+                if (zero_fill_nan)               // only Psi(o,o) enters (getPHI.m:84): rows / columns of the missing dims may hold anything
+                    for (int a = 0; a < P.d; ++a) {
+                        const double xv = X[static_cast<int64_t>(a) * n_all + idx[i]];
+                        if (xv == xv) continue;
+                        for (int b = 0; b < P.d; ++b) buf[i * dd + a + b * P.d] = buf[i * dd + b + a * P.d] = 0.0;
+                    }
+            }
             if ((rc = dev_alloc(c->allocs, &R.Psi, n * dd))) return rc;
         } else {
             gather_cols(Psi, n_all, P.d, idx, buf);
@@ -818,7 +826,7 @@ int ensure_workspace(gpz_ctx* c) {
     if (c->aug) c->tr.ycol = c->tr.Y;
     {
         const int64_t dd = static_cast<int64_t>(P.d) * P.d;
-        const int64_t sc = 2 * dd * MP + dd * P.m + static_cast<int64_t>(P.m) * P.d + 64;
+        const int64_t sc = 3 * dd * MP + dd * P.m + static_cast<int64_t>(P.m) * P.d + 64;
         if ((rc = A(&c->scratch, sc))) return rc;
     }
     if (c->opt_ozaki > 0) {
@@ -1098,7 +1106,7 @@ int eval_device(gpz_ctx* c, const double* d_theta, double* d_out) {
         if (!rc) rc = mode_reduce(P, c->scratch, dG, st, &c->launches);
     }
     else if (!mode_is_cov(P.mode)) rc = backproj_diag_generic_finish(P, c->bp_partial, c->nslab, dP, dG, c->scratch, st, &c->launches);
-    else rc = backproj_cov_psi_finish(P, c->bp_partial, c->nslab, dP, dG, c->scratch, st, &c->launches);
+    else rc = backproj_cov_psi_finish(P, c->tr, c->bp_partial, c->nslab, dP, dG, c->scratch, st, &c->launches);
     if (rc) return rc;
     colsum_reduce_kernel<<<static_cast<unsigned>(ceil_div(2LL * k * MP, 256)), 256, 0, st>>>(c->colp, colp_slabs, 2 * k, static_cast<int>(MP), qcol);
     GPZ_KERNEL_CHECK();
@@ -1232,10 +1240,6 @@ int gpz_create(gpz_ctx** out, const gpz_model* model, int64_t n_all, const doubl
         };
         scan(itr, pat_tr);
         scan(iva, pat_va);
-        if (grouped && Psi) {
-            set_error("covariance modes with missing inputs AND input noise Psi are not supported yet");
-            return fail(GPZ_ERR_USAGE);
-        }
         if (grouped && pats.size() > 4096) {
             set_error("too many distinct missing-input patterns (%zu)", pats.size());
             return fail(GPZ_ERR_USAGE);

@@ -273,7 +273,7 @@ backproj_diag_finish_kernel(Params P, const double* __restrict__ partial, int ns
 }
 
 int64_t backproj_partial_doubles(const Params& P, int nslab, int has_psi, int has_nan) {
-    if (mode_is_cov(P.mode)) return has_psi ? static_cast<int64_t>(nslab) * (1 + P.d + P.d * P.d) * P.MP : 0;
+    if (mode_is_cov(P.mode)) return has_psi ? static_cast<int64_t>(P.npat) * nslab * (1 + P.d + P.d * P.d) * P.MP : 0;
     return (has_psi || has_nan) ? static_cast<int64_t>(nslab) * 2 * P.d * P.MP : 0;
 }
 
@@ -300,13 +300,14 @@ int backproj_diag_generic_finish(const Params& P, const double* partial, int nsl
 }
 
 // ------------------------------------------------------------------------------------------------
-// cov modes + Psi: partial[slab][1 + d + d*d][MP]  (s0, u, Q)  with, per (i,j):
-//   iPS = (Sigma_j + Psi_i)^{-1}, z = iPS Delta',  u += dPHI z,  Q += dPHI (z z' - iPS),  s0 += dPHI
+// cov modes + Psi: partial[group][slab][1 + d + d*d][MP]  (s0, u, Q)  with, per (i,j) on the observed dims o of the row's pattern:
+//   iPS = (Sigma_j(o,o) + Psi_i(o,o))^{-1}, z = iPS Delta_o',  u += dPHI z,  Q += dPHI (z z' - iPS),  s0 += dPHI   (GPz.m:166-184)
+// (o,o) blocks are embedded in d x d (identity on the missing dims while inverting, zero in the accumulators).
 // ------------------------------------------------------------------------------------------------
 template <int DMAX>
 __global__ void __launch_bounds__(128)
 backproj_cov_psi_kernel(Params P, const double* __restrict__ X, const double* __restrict__ Psi, int64_t n, int64_t r0,
-                        int64_t r1, int64_t rows_per_slab, const double* __restrict__ dPhi, int64_t ld,
+                        int64_t r1, int64_t rows_per_slab, int pat, const double* __restrict__ dPhi, int64_t ld, int64_t row_off,
                         double* __restrict__ partial, int accumulate) {
     const int d = P.d, MP = P.MP, m = P.m;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -319,14 +320,16 @@ backproj_cov_psi_kernel(Params P, const double* __restrict__ X, const double* __
     if (!accumulate)
         for (int e = 0; e < nacc; ++e) out[static_cast<int64_t>(e) * MP] = 0.0;
     if (j >= m) return;
+    const unsigned char* ob = P.obs + pat * d;
     double S[DMAX * DMAX], dl[DMAX], z[DMAX];
     LocalMat Sm{S, d};
     for (int64_t gi = sb; gi < se; ++gi) {
-        const double dphi = dPhi[(gi - r0) * ld + j];
+        const double dphi = dPhi[(gi - row_off) * ld + j];
         const double* psi = Psi + gi * d * d;
         for (int a = 0; a < d; ++a) {
-            for (int b = 0; b <= a; ++b) Sm(a, b) = psi[a + b * d] + P.Sj[(static_cast<int64_t>(a) * d + b) * MP + j];
-            dl[a] = X[a * n + gi] - P.Pt[a * MP + j];
+            for (int b = 0; b <= a; ++b)
+                Sm(a, b) = (ob[a] && ob[b]) ? psi[a + b * d] + P.Sj[(static_cast<int64_t>(a) * d + b) * MP + j] : (a == b ? 1.0 : 0.0);
+            dl[a] = ob[a] ? X[a * n + gi] - P.Pt[a * MP + j] : 0.0;
         }
         double hl;
         if (!spd_inv(Sm, d, &hl)) {
@@ -340,82 +343,138 @@ backproj_cov_psi_kernel(Params P, const double* __restrict__ X, const double* __
         }
         out[0] += dphi;
         for (int a = 0; a < d; ++a) {
+            if (!ob[a]) continue;
             out[static_cast<int64_t>(1 + a) * MP] += dphi * z[a];
             for (int b = 0; b < d; ++b)
-                out[static_cast<int64_t>(1 + d + a * d + b) * MP] += dphi * (z[a] * z[b] - Sm(a, b));
+                if (ob[b]) out[static_cast<int64_t>(1 + d + a * d + b) * MP] += dphi * (z[a] * z[b] - Sm(a, b));
         }
     }
 }
 
-// per basis: B = 1/2 (A_j s0 + Q);  dGamma_j = -2 Gamma_j Sigma_j B Sigma_j;  dP_j = u        (GPz.m:172-181)
-// scratch: [2][d*d][MP] + full gradient [g_full]
+// per basis and pattern (o observed, u missing):  dSoo = 1/2 (Sigma_oo^-1 s0 + Q);  diSoo = -Sigma_oo dSoo Sigma_oo;
+//   dGo = 2 (Gamma(:,o) - Gamma(:,u) G) diSoo,  dGamma(:,o) += dGo,  dGamma(:,u) -= dGo G',  dP(o) += u      (GPz.m:172-181)
+// with G = iSigma(u,u)^-1 iSigma(u,o) (P.Gg) and Sigma_oo^-1 the marginal precision (P.Mg).  Without missing dims this is
+// dGamma_j = -2 Gamma_j Sigma_j B Sigma_j.  scratch: [3][d*d][MP] + full gradient [g_full]
 __global__ void __launch_bounds__(128)
-backproj_cov_psi_finish_kernel(Params P, const double* __restrict__ partial, int nslab, double* __restrict__ dP,
+backproj_cov_psi_finish_kernel(Params P, int pat, const double* __restrict__ partial, int nslab, int accumulate, double* __restrict__ dP,
                                double* __restrict__ work, double* __restrict__ full) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int d = P.d, m = P.m, MP = P.MP, dp = P.dp;
     if (j >= m) return;
+    const unsigned char* ob = P.obs + pat * d;
+    const double* Mg = P.Mg + static_cast<int64_t>(pat) * d * d * MP;
+    const double* Gg = P.Gg + static_cast<int64_t>(pat) * d * d * MP;
     const int nacc = 1 + d + d * d;
     StridedMat B{work + j, MP, d};
     StridedMat T{work + static_cast<int64_t>(d) * d * MP + j, MP, d};
+    StridedMat E{work + 2LL * d * d * MP + j, MP, d};
     double s0 = 0.0;
     for (int s = 0; s < nslab; ++s) s0 += partial[(static_cast<int64_t>(s) * nacc) * MP + j];
     for (int a = 0; a < d; ++a) {
         double u = 0.0;
         for (int s = 0; s < nslab; ++s) u += partial[(static_cast<int64_t>(s) * nacc + 1 + a) * MP + j];
-        dP[a * m + j] = u;
+        dP[a * m + j] = (accumulate ? dP[a * m + j] : 0.0) + u;
         for (int b = 0; b < d; ++b) {
             double q = 0.0;
             for (int s = 0; s < nslab; ++s) q += partial[(static_cast<int64_t>(s) * nacc + 1 + d + a * d + b) * MP + j];
-            B(a, b) = 0.5 * (P.Aj[(static_cast<int64_t>(a) * d + b) * MP + j] * s0 + q);
+            B(a, b) = 0.5 * (Mg[(static_cast<int64_t>(a) * d + b) * MP + j] * s0 + q);       // dSoo (zero outside (o,o))
         }
     }
-    // T = B * Sigma_j
+    // T = dSoo * Sigma_oo ;  B = -Sigma_oo * T = diSoo   (Sigma_oo = Sigma_j restricted to the observed dims)
     for (int a = 0; a < d; ++a)
         for (int b = 0; b < d; ++b) {
             double s = 0.0;
-            for (int c = 0; c < d; ++c) s += B(a, c) * P.Sj[(static_cast<int64_t>(c) * d + b) * MP + j];
+            if (ob[b])
+                for (int c = 0; c < d; ++c)
+                    if (ob[c]) s += B(a, c) * P.Sj[(static_cast<int64_t>(c) * d + b) * MP + j];
             T(a, b) = s;
         }
-    // B = Sigma_j * T
     for (int a = 0; a < d; ++a)
         for (int b = 0; b < d; ++b) {
             double s = 0.0;
-            for (int c = 0; c < d; ++c) s += P.Sj[(static_cast<int64_t>(a) * d + c) * MP + j] * T(c, b);
-            B(a, b) = s;
+            if (ob[a])
+                for (int c = 0; c < d; ++c)
+                    if (ob[c]) s += P.Sj[(static_cast<int64_t>(a) * d + c) * MP + j] * T(c, b);
+            B(a, b) = -s;
         }
-    // dGamma_j(c,a) = -2 sum_b Gamma_j(c,b) B(b,a)
+    // E(c,a) = dGo(c,a) = 2 sum_{b in o} (Gamma(c,b) - sum_{e in u} Gamma(c,e) G(e,b)) diSoo(b,a),  a in o
+    for (int c = 0; c < d; ++c)
+        for (int a = 0; a < d; ++a) {
+            double s = 0.0;
+            if (ob[a])
+                for (int b = 0; b < d; ++b) {
+                    if (!ob[b]) continue;
+                    double ge = P.Gam[(static_cast<int64_t>(c) * dp + b) * MP + j];
+                    for (int e = 0; e < d; ++e)
+                        if (!ob[e]) ge -= P.Gam[(static_cast<int64_t>(c) * dp + e) * MP + j] * Gg[(static_cast<int64_t>(e) * d + b) * MP + j];
+                    s += ge * B(b, a);
+                }
+            E(c, a) = 2.0 * s;
+        }
     for (int a = 0; a < d; ++a)
         for (int c = 0; c < d; ++c) {
-            double s = 0.0;
-            for (int b = 0; b < d; ++b) s += P.Gam[(static_cast<int64_t>(c) * dp + b) * MP + j] * B(b, a);
-            full[c + a * d + static_cast<int64_t>(d) * d * j] = -2.0 * s;
+            double v;
+            if (ob[a]) v = E(c, a);
+            else {                                   // missing dim e = a: - sum_{b in o} dGo(c,b) G(e,b)
+                v = 0.0;
+                for (int b = 0; b < d; ++b)
+                    if (ob[b]) v -= E(c, b) * Gg[(static_cast<int64_t>(a) * d + b) * MP + j];
+            }
+            const int64_t o = c + a * d + static_cast<int64_t>(d) * d * j;
+            full[o] = (accumulate ? full[o] : 0.0) + v;
         }
 }
 
+static void group_range(const RowData& R, size_t g, int64_t r0, int64_t r1, int64_t* s0, int64_t* s1, int* pat) {
+    *s0 = r0;
+    *s1 = r1;
+    *pat = 0;
+    if (!R.g_pat.empty()) {
+        *s0 = R.g_r0[g] > r0 ? R.g_r0[g] : r0;
+        *s1 = R.g_r1[g] < r1 ? R.g_r1[g] : r1;
+        *pat = R.g_pat[g];
+    }
+}
+
+// partial: [groups][nslab][1 + d + d*d][MP]; rows r0..r1 of this chunk, dPhi row 0 = row r0
 int backproj_cov_psi(const Params& P, const RowData& R, int64_t r0, int64_t r1, const double* dPhi, int64_t ld,
                      double* partial, int nslab, int accumulate, cudaStream_t st, int64_t* launches) {
-    int64_t rps = ceil_div(r1 - r0 > 0 ? r1 - r0 : 1, nslab);
-    dim3 grid(static_cast<unsigned>(ceil_div(P.MP, 128)), static_cast<unsigned>(nslab));
-    if (P.d <= 8)
-        backproj_cov_psi_kernel<8><<<grid, 128, 0, st>>>(P, R.X, R.Psi, R.n, r0, r1, rps, dPhi, ld, partial, accumulate);
-    else if (P.d <= 16)
-        backproj_cov_psi_kernel<16><<<grid, 128, 0, st>>>(P, R.X, R.Psi, R.n, r0, r1, rps, dPhi, ld, partial, accumulate);
-    else
-        backproj_cov_psi_kernel<32><<<grid, 128, 0, st>>>(P, R.X, R.Psi, R.n, r0, r1, rps, dPhi, ld, partial, accumulate);
-    GPZ_KERNEL_CHECK();
-    ++*launches;
+    const size_t ng = R.g_pat.empty() ? 1 : R.g_pat.size();
+    const int64_t gstride = static_cast<int64_t>(nslab) * (1 + P.d + P.d * P.d) * P.MP;
+    for (size_t g = 0; g < ng; ++g) {
+        int64_t s0, s1;
+        int pat;
+        group_range(R, g, r0, r1, &s0, &s1, &pat);
+        if (s1 < s0) s1 = s0;                                    // empty intersection: still zero / keep the accumulators
+        int64_t rps = ceil_div(s1 - s0 > 0 ? s1 - s0 : 1, nslab);
+        dim3 grid(static_cast<unsigned>(ceil_div(P.MP, 128)), static_cast<unsigned>(nslab));
+        double* pg = partial + static_cast<int64_t>(g) * gstride;
+        if (P.d <= 8)
+            backproj_cov_psi_kernel<8><<<grid, 128, 0, st>>>(P, R.X, R.Psi, R.n, s0, s1, rps, pat, dPhi, ld, r0, pg, accumulate);
+        else if (P.d <= 16)
+            backproj_cov_psi_kernel<16><<<grid, 128, 0, st>>>(P, R.X, R.Psi, R.n, s0, s1, rps, pat, dPhi, ld, r0, pg, accumulate);
+        else
+            backproj_cov_psi_kernel<32><<<grid, 128, 0, st>>>(P, R.X, R.Psi, R.n, s0, s1, rps, pat, dPhi, ld, r0, pg, accumulate);
+        GPZ_KERNEL_CHECK();
+        ++*launches;
+    }
     return GPZ_OK;
 }
 
-int backproj_cov_psi_finish(const Params& P, const double* partial, int nslab, double* dP, double* dG, double* scratch,
+int backproj_cov_psi_finish(const Params& P, const RowData& R, const double* partial, int nslab, double* dP, double* dG, double* scratch,
                             cudaStream_t st, int64_t* launches) {
-    // scratch layout: work [2*d*d*MP] | full [d*d*m]
+    // scratch layout: work [3*d*d*MP] | full [d*d*m]
     double* work = scratch;
-    double* full = scratch + 2LL * P.d * P.d * P.MP;
-    backproj_cov_psi_finish_kernel<<<static_cast<unsigned>(ceil_div(P.m, 128)), 128, 0, st>>>(P, partial, nslab, dP, work, full);
-    GPZ_KERNEL_CHECK();
-    ++*launches;
+    double* full = scratch + 3LL * P.d * P.d * P.MP;
+    const size_t ng = R.g_pat.empty() ? 1 : R.g_pat.size();
+    const int64_t gstride = static_cast<int64_t>(nslab) * (1 + P.d + P.d * P.d) * P.MP;
+    for (size_t g = 0; g < ng; ++g) {
+        const int pat = R.g_pat.empty() ? 0 : R.g_pat[g];
+        backproj_cov_psi_finish_kernel<<<static_cast<unsigned>(ceil_div(P.m, 128)), 128, 0, st>>>(
+            P, pat, partial + static_cast<int64_t>(g) * gstride, nslab, g > 0, dP, work, full);
+        GPZ_KERNEL_CHECK();
+        ++*launches;
+    }
     return mode_reduce(P, full, dG, st, launches);
 }
 

@@ -132,7 +132,7 @@ int backproj_diag_generic_finish(const Params& P, const double* partial, int nsl
                                  double* scratch, cudaStream_t st, int64_t* launches);
 int backproj_cov_psi(const Params& P, const RowData& R, int64_t r0, int64_t r1, const double* dPhi, int64_t ld,
                      double* partial, int nslab, int accumulate, cudaStream_t st, int64_t* launches);
-int backproj_cov_psi_finish(const Params& P, const double* partial, int nslab, double* dP, double* dG, double* scratch,
+int backproj_cov_psi_finish(const Params& P, const RowData& R, const double* partial, int nslab, double* dP, double* dG, double* scratch,
                             cudaStream_t st, int64_t* launches);
 int64_t backproj_partial_doubles(const Params& P, int nslab, int has_psi, int has_nan);
 

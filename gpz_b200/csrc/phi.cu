@@ -347,20 +347,26 @@ phi_kernel(Params P, const double* __restrict__ X, const double* __restrict__ Ps
 template <int DMAX>
 __global__ void __launch_bounds__(128)
 phi_cov_psi_kernel(Params P, const double* __restrict__ X, const double* __restrict__ Psi, int64_t n, int64_t r0,
-                   int64_t r1, double* __restrict__ Phi) {
+                   int64_t r1, int pat, double* __restrict__ Phi) {
     const int d = P.d, MP = P.MP, m = P.m;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t gi = r0 + blockIdx.y;
     if (j >= MP || gi >= r1) return;
     double val = 0.0;
     if (j < m) {
+        // rows with missing inputs (getPHI.m:80-88 on the observed dims o): the (o,o) blocks are embedded in d x d with the
+        // identity on the missing dims, so the factorisation below needs no gather and ln|S| = ln|S(o,o)|
+        const unsigned char* ob = P.obs + pat * d;
         double S[DMAX * DMAX];
         double z[DMAX];
         LocalMat Sm{S, d};
         const double* psi = Psi + gi * d * d;
+        int nu = 0;
         for (int a = 0; a < d; ++a) {
-            for (int b = 0; b <= a; ++b) Sm(a, b) = psi[a + b * d] + P.Sj[(static_cast<int64_t>(a) * d + b) * MP + j];
-            z[a] = X[a * n + gi] - P.Pt[a * MP + j];
+            for (int b = 0; b <= a; ++b)
+                Sm(a, b) = (ob[a] && ob[b]) ? psi[a + b * d] + P.Sj[(static_cast<int64_t>(a) * d + b) * MP + j] : (a == b ? 1.0 : 0.0);
+            z[a] = ob[a] ? X[a * n + gi] - P.Pt[a * MP + j] : 0.0;
+            nu += !ob[a];
         }
         double hl = 0.0;
         if (chol_lower(Sm, d, &hl)) {
@@ -372,7 +378,8 @@ phi_cov_psi_kernel(Params P, const double* __restrict__ X, const double* __restr
                 z[a] = s;
                 q += s * s;
             }
-            val = exp(-0.5 * q + 0.5 * P.lndS[j] - hl);
+            // + 1/2 ln|Sigma_j(o,o)| = - 1/2 ln det of the marginal precision (prep_patterns_kernel)
+            val = exp(-0.5 * q - 0.5 * P.lndM[static_cast<int64_t>(pat) * MP + j] - hl - 0.5 * nu * kLn2);
         } else {
             val = nan("");
         }
@@ -450,8 +457,9 @@ int phi_build(const Params& P, const RowData& R, int64_t r0, int64_t r1, double*
         ++*launches;
         return rc;
     }
-    if (R.has_nan || R.g_pat.size() > 1 || (R.g_pat.size() == 1 && R.g_pat[0] != 0)) {
-        set_error("covariance modes with missing inputs need the tensor-core PHI path (no Psi, option tensor_phi=1)");
+    const bool patterned = R.has_nan || R.g_pat.size() > 1 || (R.g_pat.size() == 1 && R.g_pat[0] != 0);
+    if (patterned && !psi) {
+        set_error("covariance modes with missing inputs need the tensor-core PHI path (option tensor_phi=1) when there is no Psi");
         return GPZ_ERR_USAGE;
     }
     if (!psi) {
@@ -464,15 +472,25 @@ int phi_build(const Params& P, const RowData& R, int64_t r0, int64_t r1, double*
         return GPZ_ERR_USAGE;
     }
     const int64_t rows = r1 - r0;
-    for (int64_t c0 = 0; c0 < rows; c0 += 65535) {     // gridDim.y limit
-        const int64_t c1 = (c0 + 65535 < rows) ? c0 + 65535 : rows;
-        dim3 grid(static_cast<unsigned>(ceil_div(P.MP, 128)), static_cast<unsigned>(c1 - c0));
-        double* out = Phi + c0 * P.MP;
-        if (P.d <= 8) phi_cov_psi_kernel<8><<<grid, 128, 0, st>>>(P, R.X, R.Psi, R.n, r0 + c0, r0 + c1, out);
-        else if (P.d <= 16) phi_cov_psi_kernel<16><<<grid, 128, 0, st>>>(P, R.X, R.Psi, R.n, r0 + c0, r0 + c1, out);
-        else phi_cov_psi_kernel<32><<<grid, 128, 0, st>>>(P, R.X, R.Psi, R.n, r0 + c0, r0 + c1, out);
-        GPZ_KERNEL_CHECK();
-        ++*launches;
+    const size_t ng = R.g_pat.empty() ? 1 : R.g_pat.size();
+    for (size_t g = 0; g < ng; ++g) {             // one pass per missing-input pattern group (one group without NaN)
+        int64_t s0 = r0, s1 = r1;
+        int pat = 0;
+        if (!R.g_pat.empty()) {
+            s0 = R.g_r0[g] > r0 ? R.g_r0[g] : r0;
+            s1 = R.g_r1[g] < r1 ? R.g_r1[g] : r1;
+            pat = R.g_pat[g];
+        }
+        for (int64_t c0 = s0; c0 < s1; c0 += 65535) {     // gridDim.y limit
+            const int64_t c1 = (c0 + 65535 < s1) ? c0 + 65535 : s1;
+            dim3 grid(static_cast<unsigned>(ceil_div(P.MP, 128)), static_cast<unsigned>(c1 - c0));
+            double* out = Phi + (c0 - r0) * P.MP;
+            if (P.d <= 8) phi_cov_psi_kernel<8><<<grid, 128, 0, st>>>(P, R.X, R.Psi, R.n, c0, c1, pat, out);
+            else if (P.d <= 16) phi_cov_psi_kernel<16><<<grid, 128, 0, st>>>(P, R.X, R.Psi, R.n, c0, c1, pat, out);
+            else phi_cov_psi_kernel<32><<<grid, 128, 0, st>>>(P, R.X, R.Psi, R.n, c0, c1, pat, out);
+            GPZ_KERNEL_CHECK();
+            ++*launches;
+        }
     }
     if (dots.n > 0) return rowdot(Phi, P.MP, P.m, rows, DotSpec{dots.n, {dots.vec[0], dots.vec[1]},
                                   {dots.out[0] + r0, dots.n > 1 ? dots.out[1] + r0 : nullptr}}, st, launches);

@@ -71,9 +71,9 @@ def assert_eval_matches(model, ref, f, g, st, tol=TOL):
             assert abs(st[key] - ref.stats[key]) <= tol * max(1.0, abs(ref.stats[key])), key
 
 
-COMBOS = [(meth, het, psi, nan) for meth, het, psi, nan in
-          itertools.product(synth.METHODS, (True, False), (False, True), (False, True))
-          if not (meth[1] == "C" and nan and psi)]       # cov modes + NaN + Psi: rejected loudly (not supported yet)
+# all 48 combinations, including covariance modes with missing inputs AND input noise (getPHI.m:80-88 on the observed dims,
+# GPz.m:166-184 with the GuuGuo correction)
+COMBOS = list(itertools.product(synth.METHODS, (True, False), (False, True), (False, True)))
 
 
 @pytest.mark.parametrize("method,het,psi,nan", COMBOS)
@@ -162,13 +162,22 @@ def test_predict_matches_oracle(method, psi):
     assert rel(PHI2, PHI) <= 1e-12
 
 
-def test_unsupported_combinations_fail_loudly():
-    model, theta, X, Y, Psi, omega, tr, va = problem("VC", True, True, False)
-    X = X.copy()
-    X[3, 1] = np.nan
+def test_cov_mode_with_missing_inputs_and_psi_ignores_psi_of_missing_dims():
+    """Only Psi(o,o) enters (getPHI.m:84): garbage in the rows / columns of the missing dims must not matter."""
+    model, theta, X, Y, Psi, omega, tr, va = problem("VC", True, True, True, n=400, d=3, m=12, seed=4)
     gm = L.make_model(model.d, 1, model.m, "VC", True)
-    with pytest.raises(L.GpzError):
-        L.Context(gm, X, Y, Psi, omega, tr, va)
+    ctx = L.Context(gm, X, Y, Psi, omega, tr, va)
+    f, g, st = ctx.eval(theta)
+    ctx.close()
+    Psi2 = np.array(Psi, copy=True)
+    for i in range(X.shape[0]):
+        for a in np.nonzero(np.isnan(X[i]))[0]:
+            Psi2[a, :, i] = 1e300
+            Psi2[:, a, i] = np.nan
+    ctx = L.Context(gm, X, Y, Psi2, omega, tr, va)
+    f2, g2, st2 = ctx.eval(theta)
+    ctx.close()
+    assert f2 == f and np.array_equal(g2, g)
 
 
 @pytest.mark.parametrize("method", ["VC", "GC"])
