@@ -1563,7 +1563,8 @@ int gpz_get_prior(gpz_ctx* c, const double* theta, double* prior) {
     return GPZ_OK;
 }
 
-// one group of rows sharing a missing-input pattern, diagonal modes (predictDiag.m:127-295); host buffers in/out
+// one group of rows sharing a missing-input pattern (predictDiag.m:127-295, predictCov.m:134-336); host buffers in/out;
+// Psig: diagonal modes [n x d] column-major, covariance modes [n][d*d]
 static int predict_missing_group(const gpz_model* model, const double* theta, const double* w, const double* iSigma_w,
                                  int64_t n, const double* Xg, const double* Psig, const double* priors,
                                  const std::vector<unsigned char>& ob, double* mu, double* nu, double* beta_i, double* gamma,
@@ -1589,14 +1590,16 @@ static int predict_missing_group(const gpz_model* model, const double* theta, co
     }
     const int64_t MP = P.MP;
     const int k = P.k, d = P.d;
-    if ((rc = alloc_params(P, allocs, 0))) return cleanup(rc);
+    const bool cov = mode_is_cov(P.mode);
+    const int64_t psi_w = cov ? static_cast<int64_t>(P.d) * P.d : P.d;
+    if ((rc = alloc_params(P, allocs, cov ? 1 : 0))) return cleanup(rc);
     double *d_theta, *d_w, *d_Sinv, *d_prior, *d_X, *d_Psi = nullptr, *d_out, *d_Phi, *d_col = nullptr;
     unsigned char* d_ob;
     if ((rc = dev_alloc(allocs, &d_theta, P.p)) || (rc = dev_alloc(allocs, &d_w, k * MP)) || (rc = dev_alloc(allocs, &d_Sinv, k * MP * MP)) ||
         (rc = dev_alloc(allocs, &d_prior, MP)) || (rc = dev_alloc(allocs, &d_X, n * d)) || (rc = dev_alloc(allocs, &d_out, 4 * k * n)) ||
         (rc = dev_alloc(allocs, &d_Phi, n * MP)) || (rc = dev_alloc(allocs, &d_ob, d)))
         return cleanup(rc);
-    if (Psig && (rc = dev_alloc(allocs, &d_Psi, n * d))) return cleanup(rc);
+    if (Psig && (rc = dev_alloc(allocs, &d_Psi, n * psi_w))) return cleanup(rc);
     if (PHI && (rc = dev_alloc(allocs, &d_col, n * P.m))) return cleanup(rc);
     std::vector<double> hx(Xg, Xg + n * d);
     for (double& v : hx)
@@ -1611,15 +1614,16 @@ static int predict_missing_group(const gpz_model* model, const double* theta, co
     ok = ok && cudaMemcpy(d_prior, priors, sizeof(double) * P.m, cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaMemcpy(d_X, hx.data(), sizeof(double) * n * d, cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaMemcpy(d_ob, ob.data(), d, cudaMemcpyHostToDevice) == cudaSuccess;
-    if (Psig) ok = ok && cudaMemcpy(d_Psi, Psig, sizeof(double) * n * d, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (Psig) ok = ok && cudaMemcpy(d_Psi, Psig, sizeof(double) * n * psi_w, cudaMemcpyHostToDevice) == cudaSuccess;
     if (!ok) {
         set_error("predict_missing_group: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         return cleanup(GPZ_ERR_CUDA);
     }
-    if ((rc = prep_params(d_theta, P, 0, st, &launches))) return cleanup(rc);
+    if ((rc = prep_params(d_theta, P, cov ? 1 : 0, st, &launches))) return cleanup(rc);
     double *d_mu = d_out, *d_nu = d_out + k * n, *d_be = d_out + 2 * k * n, *d_ga = d_out + 3 * k * n;
-    if ((rc = predict_missing_diag(P, d_X, d_Psi, n, d_ob, d_prior, d_w, d_Sinv, d_mu, d_nu, d_be, d_ga, d_Phi, st, &launches)))
-        return cleanup(rc);
+    rc = cov ? predict_missing_cov(P, d_X, d_Psi, n, d_ob, d_prior, d_w, d_Sinv, d_mu, d_nu, d_be, d_ga, d_Phi, st, &launches)
+             : predict_missing_diag(P, d_X, d_Psi, n, d_ob, d_prior, d_w, d_Sinv, d_mu, d_nu, d_be, d_ga, d_Phi, st, &launches);
+    if (rc) return cleanup(rc);
     if (PHI) {
         if ((rc = transpose_out(d_Phi, MP, n, P.m, d_col, st))) return cleanup(rc);
         ok = cudaMemcpyAsync(PHI, d_col, sizeof(double) * n * P.m, cudaMemcpyDeviceToHost, st) == cudaSuccess;
@@ -1651,10 +1655,6 @@ int gpz_predict(const gpz_model* model, const double* theta, const double* w, co
         bool any_nan = false;
         for (int64_t i = 0; i < n * P.d && !any_nan; ++i) any_nan = Xz[i] != Xz[i];
         if (any_nan) {
-            if (mode_is_cov(P.mode)) {
-                set_error("gpz_predict: rows with missing inputs are not supported for covariance modes yet (predictCov.m:134-336)");
-                return GPZ_ERR_USAGE;
-            }
             if (!priors) {
                 set_error("gpz_predict: rows with missing inputs need the basis priors (model.best.priors, getPrior.m)");
                 return GPZ_ERR_USAGE;
@@ -1679,7 +1679,17 @@ int gpz_predict(const gpz_model* model, const double* theta, const double* w, co
                     o_be(o_mu.size()), o_ga(o_mu.size()), o_phi(PHI ? static_cast<size_t>(ng) * P.m : 0);
                 for (int a = 0; a < P.d; ++a)
                     for (int64_t r = 0; r < ng; ++r) Xg[static_cast<size_t>(a) * ng + r] = Xz[static_cast<int64_t>(a) * n + rows[r]];
-                if (Psi) {
+                if (Psi && mode_is_cov(P.mode)) {         // d x d x n: one contiguous d*d block per row
+                    const size_t dd = static_cast<size_t>(P.d) * P.d;
+                    Pg.resize(static_cast<size_t>(ng) * dd);
+                    for (int64_t r = 0; r < ng; ++r) {
+                        memcpy(Pg.data() + r * dd, Psi + rows[r] * dd, sizeof(double) * dd);
+                    }
+                    for (int64_t r = 0; r < ng; ++r)         // only Psi(o,o) enters: whatever sits in the missing rows / columns is dropped
+                        for (int a = 0; a < P.d; ++a)
+                            if (pk[a] != '1')
+                                for (int b = 0; b < P.d; ++b) Pg[r * dd + a + b * P.d] = Pg[r * dd + b + a * P.d] = 0.0;
+                } else if (Psi) {
                     Pg.resize(static_cast<size_t>(ng) * P.d);
                     for (int a = 0; a < P.d; ++a)
                         for (int64_t r = 0; r < ng; ++r) Pg[static_cast<size_t>(a) * ng + r] = Psi[static_cast<int64_t>(a) * n + rows[r]];

@@ -147,6 +147,10 @@ int predict_missing_diag(const Params& P, const double* X, const double* Psi, in
                          const double* prior, const double* w, const double* Sinv, double* mu, double* nu, double* beta_i,
                          double* gamma, double* Phi, cudaStream_t st, int64_t* launches);
 
+int predict_missing_cov(const Params& P, const double* X, const double* Psi, int64_t n, const unsigned char* ob, const double* prior,
+                        const double* w, const double* Sinv, double* mu, double* nu, double* beta_i, double* gamma, double* Phi,
+                        cudaStream_t st, int64_t* launches);
+
 // ---- ozaki.cu: fp64 operands -> base-256 digits; the two n x m x m products through ozmma.cu
 int64_t oz_padded_rows(int64_t rows);
 int64_t oz_digit_bytes(int MP, int s, int64_t rows);

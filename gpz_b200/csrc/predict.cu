@@ -566,4 +566,328 @@ int predict_noisy_cov(const Params& P, const RowData& R, const double* w, const 
     return GPZ_OK;
 }
 
+// ================================================================================================
+// predictMissing / predictNoisyMissing for the covariance modes (GPz/predictCov.m:134-336), one group of rows sharing a
+// missing-input pattern (o observed, u missing).  Per basis l: R_l = Sigma_l(o,o)^-1 Sigma_l(o,u), the Schur complement
+// Sigma_l(u,u) - Sigma_l(u,o) R_l; per (sample t, basis l): responsibility Pio, completed input X_hat, its covariance
+// Psi_hat = T Psi_oo T' + Schur (T = [I; R']); then PHI_ti = e^{lnz_i} sum_j N(X_hat_tj; p_i, Sigma_i + Psi_hat_tj) Pio_tj and,
+// per basis pair, Z = e^{lnZ_ij} sum_l N(X_hat_tl; c_ij, C_ij + Psi_hat_tl) Pio_tl.  All (o,o)/(u,u) blocks are embedded
+// in d x d arrays.  Cost O(n m^3 d^3): correct, sized for the reference's use (demo-scale m), not optimised.
+// ================================================================================================
+template <int DMAX>
+__global__ void __launch_bounds__(64)
+pmc_basis_kernel(Params P, const unsigned char* __restrict__ ob, double* __restrict__ Rt, double* __restrict__ Sch) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    const int d = P.d, MP = P.MP;
+    if (l >= P.m) return;
+    double S[DMAX * DMAX];
+    LocalMat Sm{S, d};
+    for (int a = 0; a < d; ++a)
+        for (int b = 0; b < d; ++b)
+            Sm(a, b) = (ob[a] && ob[b]) ? P.Sj[(static_cast<int64_t>(a) * d + b) * MP + l] : (a == b ? 1.0 : 0.0);
+    double hl;
+    const bool ok = spd_inv(Sm, d, &hl);
+    for (int a = 0; a < d; ++a)
+        for (int e = 0; e < d; ++e) {
+            double r = 0.0;
+            if (ob[a] && !ob[e])
+                for (int b = 0; b < d; ++b)
+                    if (ob[b]) r += Sm(a, b) * P.Sj[(static_cast<int64_t>(b) * d + e) * MP + l];
+            Rt[(static_cast<int64_t>(a) * d + e) * MP + l] = ok ? r : nan("");
+        }
+    for (int e = 0; e < d; ++e)
+        for (int f = 0; f < d; ++f) {
+            double v = 0.0;
+            if (!ob[e] && !ob[f]) {
+                v = P.Sj[(static_cast<int64_t>(e) * d + f) * MP + l];
+                for (int a = 0; a < d; ++a)
+                    if (ob[a]) v -= P.Sj[(static_cast<int64_t>(e) * d + a) * MP + l] * Rt[(static_cast<int64_t>(a) * d + f) * MP + l];
+            }
+            Sch[(static_cast<int64_t>(e) * d + f) * MP + l] = v;
+        }
+}
+
+// Ex [rows][MP] (un-normalised responsibilities), XH [rows][MP][d], PH [rows][MP][d*d] (only with Psi)
+template <int DMAX>
+__global__ void __launch_bounds__(128)
+pmc_rows_kernel(Params P, const double* __restrict__ X, const double* __restrict__ Psi, int64_t n, int64_t r0, int64_t r1,
+                const unsigned char* __restrict__ ob, const double* __restrict__ prior, const double* __restrict__ Rt,
+                const double* __restrict__ Sch, double* __restrict__ Ex, double* __restrict__ XH, double* __restrict__ PH) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t t = r0 + blockIdx.y;
+    const int d = P.d, MP = P.MP;
+    if (l >= MP || t >= r1) return;
+    const int64_t tl = (t - r0) * MP + l;
+    if (l >= P.m) {
+        Ex[tl] = 0.0;
+        return;
+    }
+    double S[DMAX * DMAX], dl[DMAX], z[DMAX];
+    LocalMat Sm{S, d};
+    const double* psi = Psi != nullptr ? Psi + t * d * d : nullptr;
+    for (int a = 0; a < d; ++a) {
+        for (int b = 0; b <= a; ++b)
+            Sm(a, b) = (ob[a] && ob[b]) ? P.Sj[(static_cast<int64_t>(a) * d + b) * MP + l] + (psi != nullptr ? psi[a + b * d] : 0.0)
+                                        : (a == b ? 1.0 : 0.0);
+        dl[a] = ob[a] ? X[a * n + t] - P.Pt[a * MP + l] : 0.0;
+        z[a] = dl[a];
+    }
+    double hl = 0.0, q = 0.0;
+    const bool ok = chol_lower(Sm, d, &hl);
+    for (int a = 0; a < d; ++a) {
+        double s = z[a];
+        for (int b = 0; b < a; ++b) s -= Sm(a, b) * z[b];
+        s /= Sm(a, a);
+        z[a] = s;
+        q += s * s;
+    }
+    Ex[tl] = ok ? exp(-0.5 * q - hl) * prior[l] : nan("");                         // predictCov.m:163 / :267
+    double* xh = XH + tl * d;
+    for (int a = 0; a < d; ++a) {
+        double v;
+        if (ob[a]) v = X[a * n + t];
+        else {
+            v = P.Pt[a * MP + l];                                                   // :169-170 / :277-278
+            for (int b = 0; b < d; ++b)
+                if (ob[b]) v += dl[b] * Rt[(static_cast<int64_t>(b) * d + a) * MP + l];
+        }
+        xh[a] = v;
+    }
+    if (PH == nullptr) return;
+    // Psi_hat = [Psi_oo, Psi_oo R; R' Psi_oo, R' Psi_oo R + Schur]                 :270-275
+    double* ph = PH + tl * d * d;
+    for (int a = 0; a < d; ++a)            // Q(a,e) = sum_{b in o} Psi(a,b) R(b,e), a in o, e in u  (kept in S)
+        for (int e = 0; e < d; ++e) {
+            double s = 0.0;
+            if (ob[a] && !ob[e])
+                for (int b = 0; b < d; ++b)
+                    if (ob[b]) s += psi[a + b * d] * Rt[(static_cast<int64_t>(b) * d + e) * MP + l];
+            Sm(a, e) = s;
+        }
+    for (int a = 0; a < d; ++a)
+        for (int b = 0; b < d; ++b) {
+            double v;
+            if (ob[a] && ob[b]) v = psi[a + b * d];
+            else if (ob[a]) v = Sm(a, b);
+            else if (ob[b]) v = Sm(b, a);
+            else {
+                v = Sch[(static_cast<int64_t>(a) * d + b) * MP + l];
+                for (int c = 0; c < d; ++c)
+                    if (ob[c]) v += Rt[(static_cast<int64_t>(c) * d + a) * MP + l] * Sm(c, b);
+            }
+            ph[a * d + b] = v;
+        }
+}
+
+__global__ void pmc_norm_kernel(double* __restrict__ Ex, int64_t rows, int m, int MP) {
+    const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= rows) return;
+    double s = 0.0;
+    for (int l = 0; l < m; ++l) s += Ex[t * MP + l];
+    for (int l = 0; l < m; ++l) Ex[t * MP + l] /= s;                                // :175 / :282
+}
+
+// ln N(delta; 0, S) with S(a,b) = A(a,b) + B(a,b) given through accessors; thread-local Cholesky
+template <int DMAX, class FA, class FB, class FD>
+__device__ __forceinline__ double pmc_lnN(int d, FA A, FB B, FD delta, bool* ok) {
+    double S[DMAX * DMAX], z[DMAX];
+    LocalMat Sm{S, d};
+    for (int a = 0; a < d; ++a) {
+        for (int b = 0; b <= a; ++b) Sm(a, b) = A(a, b) + B(a, b);
+        z[a] = delta(a);
+    }
+    double hl = 0.0, q = 0.0;
+    if (!chol_lower(Sm, d, &hl)) {
+        *ok = false;
+        return 0.0;
+    }
+    for (int a = 0; a < d; ++a) {
+        double s = z[a];
+        for (int b = 0; b < a; ++b) s -= Sm(a, b) * z[b];
+        s /= Sm(a, a);
+        q += s * s;
+        z[a] = s;
+    }
+    return -0.5 * q - hl;
+}
+
+// PHI_ti = exp(lnz_i) sum_j N(X_hat_tj - p_i; Sigma_i + Psi_hat_tj) Pio_tj                    :186-199,224 / :293-305,328
+template <int DMAX>
+__global__ void __launch_bounds__(128)
+pmc_phi_kernel(Params P, int64_t rows, const double* __restrict__ Pio, const double* __restrict__ XH, const double* __restrict__ PH,
+               const double* __restrict__ Sch, double* __restrict__ Phi) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t t = blockIdx.y;
+    const int d = P.d, MP = P.MP, m = P.m;
+    if (i >= MP || t >= rows) return;
+    double acc = 0.0;
+    bool ok = true;
+    if (i < m) {
+        for (int j = 0; j < m; ++j) {
+            const int64_t tj = t * MP + j;
+            const double* xh = XH + tj * d;
+            const double* ph = PH != nullptr ? PH + tj * d * d : nullptr;
+            const double ln = pmc_lnN<DMAX>(
+                d, [&](int a, int b) { return P.Sj[(static_cast<int64_t>(a) * d + b) * MP + i]; },
+                [&](int a, int b) { return ph != nullptr ? ph[a * d + b] : Sch[(static_cast<int64_t>(a) * d + b) * MP + j]; },
+                [&](int a) { return xh[a] - P.Pt[a * MP + i]; }, &ok);
+            acc += exp(ln) * Pio[tj];
+        }
+        acc *= exp(0.5 * P.lndS[i]);
+    }
+    Phi[t * MP + i] = ok ? acc : nan("");
+}
+
+// one block per sample: threads walk the basis pairs, fixed-order block reduction                 :179-222 / :286-326
+template <int DMAX, int KMAX>
+__global__ void __launch_bounds__(128)
+pmc_pairs_kernel(Params P, int64_t n, int64_t r0, int64_t rows, CPairTab T, const double* __restrict__ Pio, const double* __restrict__ XH,
+                 const double* __restrict__ PH, const double* __restrict__ Sch, const double* __restrict__ elns0,
+                 const double* __restrict__ mu, double* __restrict__ nu, double* __restrict__ beta_i, double* __restrict__ gamma) {
+    __shared__ double red[8];
+    const int64_t t = blockIdx.x;
+    if (t >= rows) return;
+    const int d = P.d, MP = P.MP, m = P.m, k = P.k;
+    double g[KMAX], vl[KMAX], nv[KMAX];
+#pragma unroll
+    for (int o = 0; o < KMAX; ++o) g[o] = vl[o] = nv[o] = 0.0;
+    bool ok = true;
+    for (int64_t q = threadIdx.x; q < T.npairs; q += 128) {
+        double Ec = 0.0;
+        for (int l = 0; l < m; ++l) {
+            const int64_t tl = t * MP + l;
+            const double* xh = XH + tl * d;
+            const double* ph = PH != nullptr ? PH + tl * d * d : nullptr;
+            const double ln = pmc_lnN<DMAX>(
+                d, [&](int a, int b) { return T.C[(static_cast<int64_t>(a) * d + b) * T.npairs + q]; },
+                [&](int a, int b) { return ph != nullptr ? ph[a * d + b] : Sch[(static_cast<int64_t>(a) * d + b) * MP + l]; },
+                [&](int a) { return xh[a] - T.c[a * T.npairs + q]; }, &ok);
+            Ec += exp(ln) * Pio[tl];
+        }
+        const double Z = exp(T.lnZ[q]) * Ec;
+#pragma unroll
+        for (int o = 0; o < KMAX; ++o)
+            if (o < k) {
+                g[o] = fma(Z, T.ww[o * T.npairs + q], g[o]);
+                vl[o] = fma(Z, T.vv[o * T.npairs + q], vl[o]);
+                nv[o] = fma(Z, T.ss[o * T.npairs + q], nv[o]);
+            }
+    }
+    const int64_t gt = r0 + t;
+#pragma unroll
+    for (int o = 0; o < KMAX; ++o) {
+        if (o >= k) break;
+        const double G = block_sum<128>(ok ? g[o] : nan(""), red);
+        const double V = block_sum<128>(vl[o], red);
+        const double N = block_sum<128>(nv[o], red);
+        if (threadIdx.x == 0) {
+            const double e0 = elns0[o * n + gt], m_ = mu[o * n + gt];
+            gamma[o * n + gt] = G - m_ * m_;
+            beta_i[o * n + gt] = exp(e0 + P.bk[o]) * (1.0 + 0.5 * (V - e0 * e0));
+            nu[o * n + gt] = N;
+        }
+    }
+}
+
+template <int DMAX>
+static void pmc_launch(const Params& P, const double* X, const double* Psi, int64_t n, int64_t r0, int64_t r1, const unsigned char* ob,
+                       const double* prior, const double* Rt, const double* Sch, double* Ex, double* XH, double* PH, double* Phi,
+                       const CPairTab& T, const double* elns0, const double* mu, double* nu, double* beta_i, double* gamma, int stage,
+                       cudaStream_t st) {
+    const int64_t rows = r1 - r0;
+    const unsigned gm = static_cast<unsigned>(ceil_div(P.MP, 128));
+    if (stage == 0) {              // per-(sample, basis) tables of this chunk
+        pmc_rows_kernel<DMAX><<<dim3(gm, static_cast<unsigned>(rows)), 128, 0, st>>>(P, X, Psi, n, r0, r1, ob, prior, Rt, Sch, Ex, XH, PH);
+        pmc_norm_kernel<<<static_cast<unsigned>(ceil_div(rows, 128)), 128, 0, st>>>(Ex, rows, P.m, P.MP);
+    } else if (stage == 1) {
+        pmc_phi_kernel<DMAX><<<dim3(gm, static_cast<unsigned>(rows)), 128, 0, st>>>(P, rows, Ex, XH, PH, Sch, Phi + r0 * P.MP);
+    } else {
+        pmc_pairs_kernel<DMAX, 4><<<static_cast<unsigned>(rows), 128, 0, st>>>(P, n, r0, rows, T, Ex, XH, PH, Sch, elns0, mu, nu, beta_i, gamma);
+    }
+}
+
+// needs P.Sj / P.lndS (prep_params with need_sigma = 1); X [d][n] NaN-free (missing dims zero-filled); Psi [n][d*d] or null;
+// ob: device [d] observed mask; Phi [n][MP] out
+int predict_missing_cov(const Params& P, const double* X, const double* Psi, int64_t n, const unsigned char* ob, const double* prior,
+                        const double* w, const double* Sinv, double* mu, double* nu, double* beta_i, double* gamma, double* Phi,
+                        cudaStream_t st, int64_t* launches) {
+    if (P.k > 4 || P.d > 32) {
+        set_error("predictMissing (cov): k <= 4 and d <= 32 supported");
+        return GPZ_ERR_USAGE;
+    }
+    const int64_t MP = P.MP, dd = static_cast<int64_t>(P.d) * P.d;
+    std::vector<void*> bufs;
+    auto A = [&](double** p, int64_t cnt) {
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), sizeof(double) * static_cast<size_t>(cnt > 0 ? cnt : 1));
+        if (e != cudaSuccess) {
+            set_error("predict_missing_cov: cudaMalloc: %s", cudaGetErrorString(e));
+            return static_cast<int>(GPZ_ERR_CUDA);
+        }
+        bufs.push_back(*p);
+        return static_cast<int>(GPZ_OK);
+    };
+    auto done = [&](int rc) {
+        cudaStreamSynchronize(st);
+        for (void* b : bufs) cudaFree(b);
+        return rc;
+    };
+    // rows per pass: keep the per-(sample, basis) tables below ~1 GB; gridDim.y limit
+    int64_t chunk = static_cast<int64_t>(1.0e9 / (8.0 * static_cast<double>(MP) * static_cast<double>(dd + P.d + 1)));
+    if (chunk < 1) chunk = 1;
+    if (chunk > 65535) chunk = 65535;
+    if (chunk > n) chunk = n;
+    CPairTab T;
+    T.npairs = static_cast<int64_t>(P.m) * (P.m + 1) / 2;
+    const int64_t per = dd + P.d + 1 + 3LL * P.k;
+    double *tab = nullptr, *Rt = nullptr, *Sch = nullptr, *Ex = nullptr, *XH = nullptr, *PH = nullptr, *elns0 = nullptr;
+    int rc;
+    if ((rc = A(&tab, per * T.npairs)) || (rc = A(&Rt, dd * MP)) || (rc = A(&Sch, dd * MP)) || (rc = A(&Ex, chunk * MP)) ||
+        (rc = A(&XH, chunk * MP * P.d)) || (rc = A(&elns0, P.k * n)))
+        return done(rc);
+    if (Psi != nullptr && (rc = A(&PH, chunk * MP * dd))) return done(rc);
+    T.C = tab;
+    T.c = T.C + dd * T.npairs;
+    T.lnZ = T.c + static_cast<int64_t>(P.d) * T.npairs;
+    T.ww = T.lnZ + T.npairs;
+    T.vv = T.ww + static_cast<int64_t>(P.k) * T.npairs;
+    T.ss = T.vv + static_cast<int64_t>(P.k) * T.npairs;
+    const unsigned nbp = static_cast<unsigned>(ceil_div(T.npairs, 64)), nbb = static_cast<unsigned>(ceil_div(P.m, 64));
+    if (P.d <= 8) {
+        cpair_table_kernel<8><<<nbp, 64, 0, st>>>(P, w, Sinv, T);
+        pmc_basis_kernel<8><<<nbb, 64, 0, st>>>(P, ob, Rt, Sch);
+    } else if (P.d <= 16) {
+        cpair_table_kernel<16><<<nbp, 64, 0, st>>>(P, w, Sinv, T);
+        pmc_basis_kernel<16><<<nbb, 64, 0, st>>>(P, ob, Rt, Sch);
+    } else {
+        cpair_table_kernel<32><<<nbp, 64, 0, st>>>(P, w, Sinv, T);
+        pmc_basis_kernel<32><<<nbb, 64, 0, st>>>(P, ob, Rt, Sch);
+    }
+    *launches += 2;
+    auto run = [&](int stage, int64_t r0, int64_t r1) {
+        if (P.d <= 8) pmc_launch<8>(P, X, Psi, n, r0, r1, ob, prior, Rt, Sch, Ex, XH, PH, Phi, T, elns0, mu, nu, beta_i, gamma, stage, st);
+        else if (P.d <= 16) pmc_launch<16>(P, X, Psi, n, r0, r1, ob, prior, Rt, Sch, Ex, XH, PH, Phi, T, elns0, mu, nu, beta_i, gamma, stage, st);
+        else pmc_launch<32>(P, X, Psi, n, r0, r1, ob, prior, Rt, Sch, Ex, XH, PH, Phi, T, elns0, mu, nu, beta_i, gamma, stage, st);
+        *launches += stage == 0 ? 2 : 1;
+    };
+    const bool one_pass = chunk >= n;
+    for (int64_t r0 = 0; r0 < n; r0 += chunk) {          // PHI for all rows
+        const int64_t r1 = (r0 + chunk < n) ? r0 + chunk : n;
+        run(0, r0, r1);
+        run(1, r0, r1);
+    }
+    for (int o = 0; o < P.k; ++o)                        // mu = PHI w, E ln S = PHI v: the pair sums need them
+        if ((rc = rowdot(Phi, MP, P.m, n, DotSpec{2, {w + o * MP, P.v + o * MP}, {mu + o * n, elns0 + o * n}}, st, launches))) return done(rc);
+    for (int64_t r0 = 0; r0 < n; r0 += chunk) {
+        const int64_t r1 = (r0 + chunk < n) ? r0 + chunk : n;
+        if (!one_pass) run(0, r0, r1);                   // the tables of this chunk were overwritten: rebuild (cheap next to the pair sums)
+        run(2, r0, r1);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("predict_missing_cov: %s", cudaGetErrorString(e));
+        return done(GPZ_ERR_CUDA);
+    }
+    return done(GPZ_OK);
+}
+
 }  // namespace gpz

@@ -576,10 +576,89 @@ def _predictMissingDiag(X, Psi, Gamma, w, v, b, P, iSigma_w, priors):
     return mu, nu, beta_i, gamma, PHI
 
 
+def _lnN(delta, S):
+    """-1/2 delta S^-1 delta' - 1/2 ln det S (the reference writes ln det as sum(log(svd(S))))."""
+    return -0.5 * delta @ np.linalg.solve(S.T, delta) - 0.5 * np.sum(np.log(np.linalg.svd(S, compute_uv=False)))
+
+
+def _predictMissingCov(X, Psi, Gamma, w, v, b, P, iSigma_w, priors):
+    """predictMissing (Psi is None, predictCov.m:134-232) and predictNoisyMissing (predictCov.m:233-336) for one group of rows
+    sharing a NaN pattern.  The two reference functions differ in Psi(o,o) being added to Sigma(o,o) in the responsibilities
+    (:267) and propagated into Psi_hat = T Psi_oo T' + Schur complement (:270-275)."""
+    o = ~np.isnan(X[0, :])
+    u = ~o
+    io, iu = np.nonzero(o)[0], np.nonzero(u)[0]
+    n, d = X.shape
+    m, k = w.shape
+    pri = np.asarray(priors, dtype=np.float64).reshape(-1)
+    iSigma = np.zeros((m, d, d))
+    Sigma = np.zeros((m, d, d))
+    lnz = np.zeros(m)
+    R = []
+    Schur = np.zeros((m, d, d))
+    for i in range(m):                                                  # :156-172 / :257-279
+        iSigma[i] = Gamma[:, :, i].T @ Gamma[:, :, i]
+        Sigma[i] = np.linalg.inv(iSigma[i])
+        lnz[i] = -0.5 * np.sum(np.log(np.linalg.svd(iSigma[i], compute_uv=False)))
+        Soo = Sigma[i][np.ix_(io, io)]
+        R.append(np.linalg.solve(Soo, Sigma[i][np.ix_(io, iu)]))
+        Schur[i][np.ix_(iu, iu)] = Sigma[i][np.ix_(iu, iu)] - Sigma[i][np.ix_(iu, io)] @ R[i]
+    Ex = np.zeros((n, m))
+    X_hat = np.zeros((n, m, d))
+    Psi_hat = np.zeros((n, m, d, d))
+    for t in range(n):
+        for i in range(m):
+            Soo = Sigma[i][np.ix_(io, io)]
+            Delta = X[t, io] - P[i, io]
+            PS = Soo if Psi is None else Soo + Psi[np.ix_(io, io, [t])][:, :, 0]
+            Ex[t, i] = math.exp(_lnN(Delta, PS)) * pri[i]               # :163 / :267
+            X_hat[t, i, iu] = Delta @ R[i] + P[i, iu]                   # :169-170 / :277-278
+            X_hat[t, i, io] = X[t, io]
+            Psi_hat[t, i] = Schur[i]
+            if Psi is not None:                                         # :270-275
+                T = np.vstack([np.eye(len(io)), R[i].T])
+                full = T @ Psi[np.ix_(io, io, [t])][:, :, 0] @ T.T
+                idx = np.concatenate([io, iu])
+                Psi_hat[t, i][np.ix_(idx, idx)] += full
+    Pio = Ex / np.sum(Ex, axis=1, keepdims=True)                        # :175 / :282
+    PHI = np.zeros((n, m))
+    gamma = np.zeros((n, k))
+    nu = np.zeros((n, k))
+    VlnS = np.zeros((n, k))
+    for i in range(m):                                                  # :177-222 / :284-326
+        for j in range(i + 1):
+            iCij = iSigma[i] + iSigma[j]
+            Cij = np.linalg.inv(iCij)
+            cij = np.linalg.solve(iCij.T, P[i, :] @ iSigma[i] + P[j, :] @ iSigma[j])
+            Dp = P[i, :] - P[j, :]
+            lnZij = lnz[i] + lnz[j] + _lnN(Dp, Sigma[i] + Sigma[j])
+            for t in range(n):
+                # each ordered pair once: the reference adds both orders for j < i and adds-then-subtracts the j == i term
+                PHI[t, i] += math.exp(_lnN(X_hat[t, j] - P[i, :], Sigma[i] + Psi_hat[t, j])) * Pio[t, j]
+                if j < i:
+                    PHI[t, j] += math.exp(_lnN(X_hat[t, i] - P[j, :], Sigma[j] + Psi_hat[t, i])) * Pio[t, i]
+                Ec = 0.0
+                for l in range(m):
+                    Ec += math.exp(_lnN(X_hat[t, l] - cij, Cij + Psi_hat[t, l])) * Pio[t, l]
+                Z = math.exp(lnZij) * Ec
+                f = 2.0 if j < i else 1.0
+                gamma[t, :] += f * Z * (w[i, :] * w[j, :])
+                VlnS[t, :] += f * Z * (v[i, :] * v[j, :])
+                nu[t, :] += f * Z * iSigma_w[i, j, :]
+    PHI = PHI * np.exp(lnz)[None, :]                                    # :224 / :328
+    mu = PHI @ w
+    ElnS = PHI @ v
+    VlnS = VlnS - ElnS ** 2
+    ElnS = ElnS + b.reshape(1, k)
+    beta_i = np.exp(ElnS) * (1.0 + 0.5 * VlnS)
+    gamma = gamma - mu ** 2
+    return mu, nu, beta_i, gamma, PHI
+
+
 def predict(X, model: Model, which="best", Psi=None, selection=None):
     """predict.m:1-75: rows grouped by NaN pattern; Full / Noisy for complete rows (both mode families),
-    Missing / NoisyMissing for the diagonal modes (predictDiag.m:127-295).  Missing rows with a covariance
-    mode (predictCov.m:134-336) are not restated."""
+    Missing / NoisyMissing for the diagonal modes (predictDiag.m:127-295) and the covariance modes
+    (predictCov.m:134-336)."""
     st = model.best if which == "best" else model.last
     n_all = X.shape[0]
     if selection is None:
@@ -614,7 +693,7 @@ def predict(X, model: Model, which="best", Psi=None, selection=None):
         elif full:
             r = _predictNoisyDiag(Xg, Psi[grp], Gamma, w, v, b, P, iSigma_w, theta, model)
         elif meth[1] == "C":
-            raise NotImplementedError("predictMissing for covariance modes (predictCov.m:134-336): SURVEY 8(f)")
+            r = _predictMissingCov(Xg, None if Psi is None else Psi[:, :, grp], Gamma, w, v, b, P, iSigma_w, st["priors"])
         else:
             r = _predictMissingDiag(Xg, None if Psi is None else Psi[grp], Gamma, w, v, b, P, iSigma_w, st["priors"])
         mu[grp], nu[grp], beta_i[grp], gamma[grp], PHI[grp] = r

@@ -268,9 +268,11 @@ def test_densities_and_get_prior(method, psi, nan):
     ctx.close()
 
 
-@pytest.mark.parametrize("method,psi", [("VD", False), ("VD", True), ("GL", False), ("VL", True), ("GD", False)])
+@pytest.mark.parametrize("method,psi", [("VD", False), ("VD", True), ("GL", False), ("VL", True), ("GD", False),
+                                        ("VC", False), ("VC", True), ("GC", False), ("GC", True)])
 def test_predict_with_missing_inputs(method, psi):
-    """predict.m:45-69 grouping; predictMissing / predictNoisyMissing (predictDiag.m:127-295) with priors from getPrior."""
+    """predict.m:45-69 grouping; predictMissing / predictNoisyMissing for the diagonal (predictDiag.m:127-295) and the
+    covariance modes (predictCov.m:134-336) with priors from getPrior."""
     n, d, m = 300, 3, 9
     model, theta, X, Y, _, omega, tr, _ = problem(method, True, False, False, n=n, d=d, m=m, seed=23)
     r = O.GPz(theta, model, X, Y, None, omega, tr, None, fit_only=True)
