@@ -192,3 +192,43 @@ def test_validation_stats_and_nan_groups():
         assert np.isfinite(r.stats[key])
     g = O.nan_groups(np.isnan(X))
     assert sum(int(x.sum()) for x in g) == 80 and len(g) >= 2
+
+
+@pytest.mark.parametrize("with_psi", [False, True])
+def test_T7_missing_input_prediction_cov_equals_diag_for_diagonal_gamma(with_psi):
+    """predictMissing / predictNoisyMissing of the covariance family (predictCov.m:134-336) and of the diagonal family
+    (predictDiag.m:127-295) are two independent restatements; with diagonal Gamma_j (and diagonal Psi) they describe the same
+    model, so every output must agree.  Also: Psi -> 0 reduces predictNoisyMissing to predictMissing."""
+    rng = np.random.default_rng(3)
+    n, d, m, k = 6, 3, 4, 2
+    X = rng.standard_normal((n, d))
+    X[:, 1] = np.nan                                         # one group: dim 1 missing
+    P = rng.standard_normal((m, d))
+    gd = np.abs(rng.standard_normal((m, d))) + 0.5
+    G = np.zeros((d, d, m))
+    for j in range(m):
+        G[:, :, j] = np.diag(gd[j])
+    w, v, b = rng.standard_normal((m, k)), 0.3 * rng.standard_normal((m, k)), rng.standard_normal(k)
+    iS = np.zeros((m, m, k))
+    for o in range(k):
+        A = rng.standard_normal((m, m))
+        iS[:, :, o] = A @ A.T
+    pri = np.abs(rng.standard_normal(m)) + 0.1
+    pri /= pri.sum()
+    Psi_d = Psi_c = None
+    if with_psi:
+        Psi_d = np.abs(rng.standard_normal((n, d))) * 0.2
+        Psi_c = np.zeros((d, d, n))
+        for t in range(n):
+            Psi_c[:, :, t] = np.diag(Psi_d[t])
+    rc = O._predictMissingCov(X, Psi_c, G, w, v, b, P, iS, pri)
+    rd = O._predictMissingDiag(X, Psi_d, gd, w, v, b, P, iS, pri)
+    for a, bb in zip(rc, rd):
+        assert np.max(np.abs(a - bb)) <= 1e-12 * max(1.0, np.max(np.abs(bb)))
+    if not with_psi:
+        tiny = np.zeros((d, d, n))
+        for t in range(n):
+            tiny[:, :, t] = 1e-13 * np.eye(d)
+        r0 = O._predictMissingCov(X, tiny, G, w, v, b, P, iS, pri)
+        for a, bb in zip(r0, rc):
+            assert np.max(np.abs(a - bb)) <= 1e-9 * max(1.0, np.max(np.abs(bb)))
