@@ -36,6 +36,34 @@ __device__ __forceinline__ double pow2_ceil(double v) {
     return ldexp(1.0, ex);                      // v < 2^ex
 }
 
+// All s balanced digits of I at once: adding the bias 0x80 to every byte below the leading one turns the signed-digit
+// expansion into the plain unsigned byte expansion (d_k = u_k - 128), and u - 128 as a two's-complement byte is u ^ 0x80;
+// the leading byte is the leading digit itself.  Byte k of the result is the digit of weight 256^k.
+__device__ __forceinline__ unsigned long long oz_digit_bytes(long long I, unsigned long long bias) {
+    return (static_cast<unsigned long long>(I) + bias) ^ bias;
+}
+// digit k (weight 256^k) of 4 neighbouring elements -> one 32-bit store: a 4 x 4 byte transpose in 8 PRMT
+__device__ __forceinline__ void oz_transpose4(unsigned w0, unsigned w1, unsigned w2, unsigned w3, unsigned (&o)[4]) {
+    const unsigned a = __byte_perm(w0, w1, 0x5140), b = __byte_perm(w0, w1, 0x7362);
+    const unsigned c = __byte_perm(w2, w3, 0x5140), d = __byte_perm(w2, w3, 0x7362);
+    o[0] = __byte_perm(a, c, 0x5410);
+    o[1] = __byte_perm(a, c, 0x7632);
+    o[2] = __byte_perm(b, d, 0x5410);
+    o[3] = __byte_perm(b, d, 0x7632);
+}
+// store the s digit rows of 4 consecutive columns (K[q] from oz_digit_bytes): digit t (0 = leading) is byte s-1-t
+__device__ __forceinline__ void oz_store_digits4(const unsigned long long (&K)[4], int s, int8_t* out, int64_t digit_stride) {
+    unsigned lo[4], hi[4];
+    oz_transpose4(static_cast<unsigned>(K[0]), static_cast<unsigned>(K[1]), static_cast<unsigned>(K[2]), static_cast<unsigned>(K[3]), lo);
+    oz_transpose4(static_cast<unsigned>(K[0] >> 32), static_cast<unsigned>(K[1] >> 32), static_cast<unsigned>(K[2] >> 32),
+                  static_cast<unsigned>(K[3] >> 32), hi);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (k >= s) break;
+        *reinterpret_cast<unsigned*>(out + static_cast<int64_t>(s - 1 - k) * digit_stride) = k < 4 ? lo[k] : hi[k - 4];
+    }
+}
+
 // ---- one pass over the PHI rows -> both digit sets, row-major [i][t][j].  warp per row; lane handles 4 columns per step.
 //   D8: plain digits of PHI_ij 2^-E_i (per-row exponent E_i from the row maximum, ea[i] = 2^(E_i - 8)); columns >= m are 0.
 //       They are the A operand of T = PHI iSigma (K = j contiguous) AND the B operand of the Gram (MN-major, K = i).
@@ -84,6 +112,7 @@ oz_digits_kernel(const double* __restrict__ Phi, int64_t ld, int src_cols, int m
     const int E = oz_exponent(mx);
     if (lane == 0) ea[i] = ldexp(1.0, E - 8);          // PHI_ij = ea_i * sum_t d_t 256^-(t-1)
     const double sc = ldexp(1.0, 8 * s - E);
+    const unsigned long long bias = 0x0080808080808080ull >> (8 * (8 - s));      // 0x80 in bytes 0 .. s-2
     double fs = 0.0, fy = 0.0;
     if (fout != nullptr) {
         fs = wgt[i] * ldexp(1.0, 8 * s + E - 4) / pow2_ceil(scal[0]);       // w_i 2^E_i 2^-Ef 2^(8s)
@@ -92,30 +121,15 @@ oz_digits_kernel(const double* __restrict__ Phi, int64_t ld, int src_cols, int m
     for (int j = lane * 4; j < MP; j += 128) {
         const double4 v = j < src_cols ? *reinterpret_cast<const double4*>(row + j) : zero4;
         const double x[4] = {v.x, v.y, v.z, v.w};
-        long long I[4], J[4];
+        unsigned long long I[4], J[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const bool in = j + q < m;
-            I[q] = in ? __double2ll_rn(x[q] * sc) : 0;
-            J[q] = in ? __double2ll_rn(x[q] * fs) : ((aug && j + q == m) ? __double2ll_rn(x[q] * fy) : 0);
+            I[q] = oz_digit_bytes(in ? __double2ll_rn(x[q] * sc) : 0, bias);
+            J[q] = oz_digit_bytes(in ? __double2ll_rn(x[q] * fs) : ((aug && j + q == m) ? __double2ll_rn(x[q] * fy) : 0), bias);
         }
-        for (int t = s - 1; t >= 0; --t) {
-            char4 q;
-            q.x = static_cast<signed char>(oz_digit(I[0]));
-            q.y = static_cast<signed char>(oz_digit(I[1]));
-            q.z = static_cast<signed char>(oz_digit(I[2]));
-            q.w = static_cast<signed char>(oz_digit(I[3]));
-            *reinterpret_cast<char4*>(dout + static_cast<int64_t>(t) * MP + j) = q;
-        }
-        if (fout != nullptr)
-            for (int t = s - 1; t >= 0; --t) {
-                char4 q;
-                q.x = static_cast<signed char>(oz_digit(J[0]));
-                q.y = static_cast<signed char>(oz_digit(J[1]));
-                q.z = static_cast<signed char>(oz_digit(J[2]));
-                q.w = static_cast<signed char>(oz_digit(J[3]));
-                *reinterpret_cast<char4*>(fout + static_cast<int64_t>(t) * MP + j) = q;
-            }
+        oz_store_digits4(I, s, dout + j, MP);
+        if (fout != nullptr) oz_store_digits4(J, s, fout + j, MP);
     }
 }
 
