@@ -214,6 +214,36 @@ def test_large_n_properties():
     ctx.close()
 
 
+def test_headline_workload_properties_at_full_size():
+    """BASELINE.json's headline size (n=1e6, d=10, m=1000, VC), where the oracle cannot run: size-independent properties.
+    (1) bit-reproducibility; (2) the analytic gradient against a central difference of the objective along a random
+    direction; (3) the int8-digit tensor-core path against the pure fp64 DMMA path within the stated 1e-5 (cond(SIGMA) ~ 1e8-1e9
+    here, so two fp64-accurate evaluations differ at the 1e-7 level in the gradient; the objective itself to 1e-12)."""
+    n, d, m = 1_000_000, 10, 1000
+    X, Y = synth.make_data(n, d, seed=0)
+    theta = synth.perturb_theta(synth.make_theta0(X, Y, "VC", m, het=True, seed=1), 0.01, 5)
+    gm = L.make_model(d, 1, m, "VC", True)
+    ctx = L.Context(gm, X, Y)
+    f1, g1, st = ctx.eval(theta)
+    f2, g2, _ = ctx.eval(theta)
+    assert np.isfinite(f1) and np.isfinite(g1).all() and f1 == f2 and np.array_equal(g1, g2)
+    u = np.random.default_rng(0).standard_normal(theta.size)
+    u /= np.linalg.norm(u)
+    h = 1e-5
+    fp, _, _ = ctx.eval(theta + h * u)
+    fm, _, _ = ctx.eval(theta - h * u)
+    assert abs((fp - fm) / (2 * h) - g1 @ u) <= 1e-5 * max(1.0, np.linalg.norm(g1))
+    ctx.close()
+    ctx = L.Context(gm, X, Y)
+    ctx.set_option("ozaki_slices", 0)
+    f0, g0, _ = ctx.eval(theta)
+    ctx.close()
+    assert abs(f1 - f0) <= 1e-11 * abs(f0)
+    md = m * d
+    for sl in (slice(0, md), slice(md, md + d * d * m), slice(md + d * d * m, None)):
+        assert np.max(np.abs(g1[sl] - g0[sl])) <= 1e-5 * np.max(np.abs(g0[sl]))
+
+
 @pytest.mark.parametrize("method", ["VD", "VC", "GL", "GC"])
 def test_tensor_core_phi_and_fused_backproj_agree_with_direct_kernels(method):
     """The fast paths (PHI = exp(F W) with F W on the int8 tensor cores [2] or on the DMMA pipe [1], fused dPHI
