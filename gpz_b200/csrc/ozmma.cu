@@ -47,7 +47,6 @@ struct OzmmaArgs {
     int ngroups;              // ceil(nchunks / gchunks); work unit u = group * ntiles + tile
     int lower;                // tile list = tiles touching the lower triangle (Gram); else all tiles_m x tiles_n
     int mode;                 // 0: fp64 partial tiles, 1: T-GEMM epilogue, 2: PHI = exp(.) epilogue
-    int k4;                   // 32-byte K steps issued per 128-byte k-block (1..4; < 4 when the K padding is known to be zero)
     int mn_major;             // operands stored [k][row] (row index contiguous) instead of [row][k]
     uint32_t idesc;           // UMMA instruction descriptor
     uint32_t deschiA, deschiB;   // high words of the smem matrix descriptors
@@ -143,13 +142,15 @@ __device__ __forceinline__ double2 ld_stream2(const double* p) {
     asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(OM_EVICT_FIRST));
     return v;
 }
+// (not volatile / no memory clobber: the compiler may batch the 32 row loads of an epilogue; nothing in the kernel re-reads
+// what these stores write)
 __device__ __forceinline__ double ld_stream1(const double* p) {
     double v;
-    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(OM_EVICT_FIRST));
+    asm("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(OM_EVICT_FIRST));
     return v;
 }
 __device__ __forceinline__ void st_stream1(double* p, double x) {
-    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(x), "l"(OM_EVICT_FIRST) : "memory");
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(x), "l"(OM_EVICT_FIRST));
 }
 __device__ __forceinline__ void st_stream2(double* p, double x, double y) {
     asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(x), "d"(y), "l"(OM_EVICT_FIRST) : "memory");
@@ -220,6 +221,7 @@ __device__ __forceinline__ void decode_tile(const OzmmaArgs& a, int tile, int& m
     }
 }
 
+template <int MNMAJOR>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OM_THREADS, 1)
 ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const OzmmaArgs a) {
     extern __shared__ uint8_t om_smem_raw[];
@@ -277,7 +279,7 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                                 const uint32_t full_leader = full_leader0 + 8 * stage;
                                 if (rank == 0) mbar_arrive_expect_tx(bar0 + 8 * stage, 2 * OM_STAGE_BYTES);
                                 else mbar_arrive_cluster(full_leader);
-                                if (a.mn_major) {
+                                if (MNMAJOR) {
                                     tma_load_4d(&mapA, sA, full_leader, rowA, t - 1, kb * 128, chunk, a.hintA);
                                     tma_load_4d(&mapB, sB, full_leader, rowB, uu - 1, kb * 128, chunk, a.hintB);
                                 } else {
@@ -293,8 +295,18 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer: one elected lane of the leader CTA
         if (rank == 0 && elect_one()) {
-            uint32_t it = 0, L = 0;
-            const uint32_t alo0 = desc_lo(base, a.desclo0A), blo0 = desc_lo(base + OM_A_BYTES, a.desclo0B);
+            // descriptor constants (set_operand_layout documents the fields); immediates, so the loop below is ~25 instructions
+            constexpr uint32_t VER = 1u << 14;
+            constexpr uint32_t HI_A = (1024u >> 4) | VER | (2u << 29);
+            constexpr uint32_t HI_B = MNMAJOR ? ((512u >> 4) | VER | (4u << 29)) : HI_A;
+            constexpr uint32_t LO_A = MNMAJOR ? (((128u * 128u) >> 4) << 16) : (1u << 16);
+            constexpr uint32_t LO_B = MNMAJOR ? (((128u * 64u) >> 4) << 16) : (1u << 16);
+            constexpr uint32_t KA = MNMAJOR ? ((32u * 128u) >> 4) : (32u >> 4), KB = MNMAJOR ? ((32u * 64u) >> 4) : (32u >> 4);
+            constexpr uint32_t IDESC = OM_IDESC | (MNMAJOR ? ((1u << 15) | (1u << 16)) : 0u);
+            constexpr uint32_t STG = OM_STAGE_BYTES >> 4;
+            const uint32_t alo0 = desc_lo(base, LO_A), blo0 = desc_lo(base + OM_A_BYTES, LO_B);
+            uint32_t L = 0, stage = 0, ph = 0;
+            uint32_t alo = alo0, blo = blo0, fullbar = bar0, emptybar = bar0 + 64;
             for (int u = pair; u < U; u += npairs) {
                 const int group = u / a.ntiles;
                 const int nlev = (min(a.nchunks, (group + 1) * a.gchunks) - group * a.gchunks) * (a.emax - a.emin + 1);
@@ -305,17 +317,28 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                     const uint32_t d_tmem = tmem_base + buf * 128u;
                     const int nkb = (min(a.s, e - 1) - max(1, e - a.s) + 1) * a.kblocks;
                     uint32_t acc = 0;
-                    for (int j = 0; j < nkb; ++j, ++it) {
-                        const uint32_t stage = it % OM_STAGES, ph = (it / OM_STAGES) & 1u;
-                        mbar_wait(bar0 + 8 * stage, ph);                          // both CTAs' tiles have landed
+                    for (int j = 0; j < nkb; ++j) {
+                        mbar_wait(fullbar, ph);                                   // both CTAs' tiles have landed
                         tc_fence_after();
-                        const uint32_t alo = alo0 + stage * (OM_STAGE_BYTES >> 4), blo = blo0 + stage * (OM_STAGE_BYTES >> 4);
-                        umma_i8_2cta(d_tmem, alo, a.deschiA, blo, a.deschiB, a.idesc, acc);       // up to 4 x 32 K-bytes of the stage
-                        if (a.k4 > 1) umma_i8_2cta(d_tmem, alo + a.kadvA, a.deschiA, blo + a.kadvB, a.deschiB, a.idesc, 1u);
-                        if (a.k4 > 2) umma_i8_2cta(d_tmem, alo + 2 * a.kadvA, a.deschiA, blo + 2 * a.kadvB, a.deschiB, a.idesc, 1u);
-                        if (a.k4 > 3) umma_i8_2cta(d_tmem, alo + 3 * a.kadvA, a.deschiA, blo + 3 * a.kadvB, a.deschiB, a.idesc, 1u);
+                        umma_i8_2cta(d_tmem, alo, HI_A, blo, HI_B, IDESC, acc);   // 4 x 32 K-bytes of the stage
+                        umma_i8_2cta(d_tmem, alo + KA, HI_A, blo + KB, HI_B, IDESC, 1u);
+                        umma_i8_2cta(d_tmem, alo + 2 * KA, HI_A, blo + 2 * KB, HI_B, IDESC, 1u);
+                        umma_i8_2cta(d_tmem, alo + 3 * KA, HI_A, blo + 3 * KB, HI_B, IDESC, 1u);
                         acc = 1u;
-                        umma_commit_pair(bar0 + 64 + 8 * stage);                 // frees the smem stage in both CTAs
+                        umma_commit_pair(emptybar);                               // frees the smem stage in both CTAs
+                        ++stage;
+                        alo += STG;
+                        blo += STG;
+                        fullbar += 8;
+                        emptybar += 8;
+                        if (stage == OM_STAGES) {
+                            stage = 0;
+                            ph ^= 1u;
+                            alo = alo0;
+                            blo = blo0;
+                            fullbar = bar0;
+                            emptybar = bar0 + 64;
+                        }
                     }
                     umma_commit_pair(bar0 + 128 + 8 * buf);                       // level finished -> epilogue warps
                 }
@@ -427,23 +450,35 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                 const double sb = a.eb[col];
                 const double* ph = a.Phi + gi0 * a.ld + col;
                 double* hp = a.H != nullptr ? a.H + gi0 * a.ld + col : nullptr;
+                const bool rowok = gi0 + lane < a.rows;
+                const double sa_l = rowok ? a.ea[gi0 + lane] : 0.0;                       // row scale / weight of row gi0 + lane
+                const double rw_l = (rowok && a.rw != nullptr) ? a.rw[gi0 + lane] : 1.0;
 #pragma unroll
-                for (int r = 0; r < 32; ++r) {
-                    double h = 0.0;
-                    if (gi0 + r < a.rows) {
-                        const double t = st[r] * (a.ea[gi0 + r] * sb);
-                        h = ld_stream1(ph + r * a.ld) * t;
-                        if (col == a.aug_col) {
-                            a.pred[gi0 + r] = t;
+                for (int r0 = 0; r0 < 32; r0 += 8) {                                       // 8 rows at a time: loads first
+                    double phv[8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) phv[r] = (gi0 + r0 + r < a.rows) ? ld_stream1(ph + (r0 + r) * a.ld) : 0.0;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        const int rr = r0 + r;
+                        const double t = st[rr] * (__shfl_sync(0xffffffffu, sa_l, rr) * sb);
+                        const double wr = __shfl_sync(0xffffffffu, rw_l, rr);
+                        double h = phv[r] * t;
+                        if (gi0 + rr < a.rows) {
+                            if (col == a.aug_col) {
+                                a.pred[gi0 + rr] = t;
+                                h = 0.0;
+                            }
+                            if (hp != nullptr) {
+                                double o = wr * h;
+                                if (a.accumulate) o += ld_stream1(hp + rr * a.ld);
+                                st_stream1(hp + rr * a.ld, o);
+                            }
+                        } else {
                             h = 0.0;
                         }
-                        if (hp != nullptr) {
-                            double o = (a.rw != nullptr ? a.rw[gi0 + r] : 1.0) * h;
-                            if (a.accumulate) o += ld_stream1(hp + r * a.ld);
-                            st_stream1(hp + r * a.ld, o);
-                        }
+                        st[rr] = h;
                     }
-                    st[r] = h;
                 }
             }
             // row sums over the 32 columns of the warp: butterfly multi-reduction, the total of row r ends in lane r (fixed order)
@@ -542,7 +577,6 @@ EncodeTiledFn encode_fn() {
 //   (one atom here); 32 K-rows = +32 W bytes
 void set_operand_layout(OzmmaArgs& a, int mn_major) {
     a.mn_major = mn_major;
-    a.k4 = 4;
     a.hintA = a.hintB = OM_EVICT_NORMAL;
     const uint32_t ver = 1u << 14;       // descriptor version 1 at bit 46
     if (!mn_major) {
@@ -595,7 +629,8 @@ int g_pairs = -1;       // CTA pairs that can be co-resident (one CTA per SM)
 
 int resident_pairs() {
     if (g_pairs > 0) return g_pairs;
-    if (cudaFuncSetAttribute(ozmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OM_SMEM_BYTES) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(ozmma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, OM_SMEM_BYTES) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(ozmma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, OM_SMEM_BYTES) != cudaSuccess) return -1;
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -611,7 +646,7 @@ int resident_pairs() {
     cfg.attrs = at;
     cfg.numAttrs = 1;
     int ncl = 0;
-    if (cudaOccupancyMaxActiveClusters(&ncl, ozmma_kernel, &cfg) != cudaSuccess || ncl <= 0) {
+    if (cudaOccupancyMaxActiveClusters(&ncl, ozmma_kernel<0>, &cfg) != cudaSuccess || ncl <= 0) {
         cudaGetLastError();
         ncl = sms / 2;
     }
@@ -628,7 +663,8 @@ int count_tiles(int tiles_m, int tiles_n, int lower) {
 }
 
 int launch(const CUtensorMap& mA, const CUtensorMap& mB, const OzmmaArgs& a, int npairs, cudaStream_t st) {
-    ozmma_kernel<<<dim3(static_cast<unsigned>(2 * npairs)), dim3(OM_THREADS), OM_SMEM_BYTES, st>>>(mA, mB, a);
+    if (a.mn_major) ozmma_kernel<1><<<dim3(static_cast<unsigned>(2 * npairs)), dim3(OM_THREADS), OM_SMEM_BYTES, st>>>(mA, mB, a);
+    else ozmma_kernel<0><<<dim3(static_cast<unsigned>(2 * npairs)), dim3(OM_THREADS), OM_SMEM_BYTES, st>>>(mA, mB, a);
     GPZ_KERNEL_CHECK();
     return GPZ_OK;
 }
@@ -786,7 +822,6 @@ int ozmma_phi(const int8_t* FD8, const double* eaF, const int8_t* WD8, const dou
     OzmmaArgs a = {};
     set_operand_layout(a, 0);
     a.hintB = OM_EVICT_LAST;
-    a.k4 = (kq + 31) / 32;
     a.s = s;
     a.emin = 2;
     a.emax = s + 1;
