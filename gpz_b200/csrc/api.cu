@@ -467,6 +467,10 @@ struct gpz_ctx {
     int8_t *oz_D8 = nullptr, *oz_F8 = nullptr;     // base-256 digits of PHI (plain, row-scaled) and of w .* PHI (ozaki.cu)
     double* oz_ea = nullptr;        // [rows] row scales of D8
     int opt_ozaki_gs = -1;          // digits used by the Gram (<= opt_ozaki)
+    int opt_gc_fast = 1;            // GC + Psi through per-row factorisations + GEMMs (gcpsi.cu); 0: generic per-(i,j) kernels
+    bool gc_fast = false;
+    int gc_ns = 1;
+    double* gc_ws = nullptr;
     int64_t oz_chunk = 0, opt_oz_chunk = 0;
     cudaStream_t aux = nullptr;     // second stream of the int8 T-GEMM pipeline
     cudaEvent_t oz_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -745,6 +749,7 @@ int ensure_workspace(gpz_ctx* c) {
         if ((rc = A(&c->ones, no))) return rc;
         std::vector<double> one(static_cast<size_t>(no), 1.0);
         GPZ_CUDA(cudaMemcpy(c->ones, one.data(), sizeof(double) * no, cudaMemcpyHostToDevice));
+        c->tr.gc_ones = c->va.gc_ones = c->ones;
     }
     if ((rc = A(&c->dotv_va, k * (nv > 0 ? nv : 1)))) return rc;
     if ((rc = A(&c->pred_va, k * (nv > 0 ? nv : 1)))) return rc;
@@ -791,6 +796,19 @@ int ensure_workspace(gpz_ctx* c) {
     }
     const int64_t bpd = backproj_partial_doubles(P, c->nslab, c->has_psi, c->tr.has_nan);
     if ((rc = A(&c->bp_partial, bpd))) return rc;
+    // GC + Psi without missing inputs: per-row factorisation + GEMMs instead of the per-(i,j) kernels (gcpsi.cu)
+    c->gc_fast = P.mode == GC && c->has_psi && c->opt_gc_fast && c->tr.g_pat.size() <= 1 && !c->tr.has_nan &&
+                 (c->tr.g_pat.empty() || c->tr.g_pat[0] == 0) && c->va.g_pat.size() <= 1 && (c->va.g_pat.empty() || c->va.g_pat[0] == 0);
+    if (c->gc_fast) {
+        const int KQ = gc_feature_width(P.d);
+        for (RowData* R : {&c->tr, &c->va}) {
+            if (R->n <= 0) continue;
+            R->gc_chunk = R->n < c->chunk_rows ? R->n : c->chunk_rows;
+            if ((rc = A(&R->gcF, R->gc_chunk * KQ)) || (rc = A(&R->gcW, static_cast<int64_t>(KQ) * MP)) || (rc = A(&R->gcG, MP * KQ))) return rc;
+        }
+        c->gc_ns = c->sm_count / (static_cast<int>(MP / TILE) * (KQ / 32)) > 0 ? c->sm_count / (static_cast<int>(MP / TILE) * (KQ / 32)) : 1;
+        if ((rc = A(&c->gc_ws, gc_backproj_ws_doubles(P, c->tr.gc_chunk > 0 ? c->tr.gc_chunk : 1, c->gc_ns, c->sm_count)))) return rc;
+    }
     const bool fast_bp = !c->has_psi && !c->tr.has_nan;
     if (fast_bp) {
         if ((rc = A(&c->Rm, MP * c->QP))) return rc;
@@ -1090,6 +1108,8 @@ int eval_device(gpz_ctx* c, const double* d_theta, double* d_out) {
             }
         } else if (!mode_is_cov(P.mode)) {
             if ((rc = backproj_diag_generic(P, c->tr, r0, r1, c->H, MP, c->bp_partial, c->nslab, nchunks > 0, st, &c->launches))) return rc;
+        } else if (c->gc_fast) {
+            if ((rc = gc_backproj(P, c->tr, r0, r1, c->H, MP, c->gc_ws, c->gc_ns, c->sm_count, nchunks > 0, last, st, &c->launches))) return rc;
         } else {
             if ((rc = backproj_cov_psi(P, c->tr, r0, r1, c->H, MP, c->bp_partial, c->nslab, nchunks > 0, st, &c->launches))) return rc;
         }
@@ -1106,6 +1126,7 @@ int eval_device(gpz_ctx* c, const double* d_theta, double* d_out) {
         if (!rc) rc = mode_reduce(P, c->scratch, dG, st, &c->launches);
     }
     else if (!mode_is_cov(P.mode)) rc = backproj_diag_generic_finish(P, c->bp_partial, c->nslab, dP, dG, c->scratch, st, &c->launches);
+    else if (c->gc_fast) rc = gc_backproj_finish(P, c->tr, c->gc_ws, c->gc_ns, c->sm_count, dP, dG, st, &c->launches);
     else rc = backproj_cov_psi_finish(P, c->tr, c->bp_partial, c->nslab, dP, dG, c->scratch, st, &c->launches);
     if (rc) return rc;
     colsum_reduce_kernel<<<static_cast<unsigned>(ceil_div(2LL * k * MP, 256)), 256, 0, st>>>(c->colp, colp_slabs, 2 * k, static_cast<int>(MP), qcol);
@@ -2074,6 +2095,14 @@ int gpz_set_option(gpz_ctx* c, const char* name, double value) {
             return GPZ_ERR_USAGE;
         }
         c->opt_ozaki = static_cast<int>(value);
+        return GPZ_OK;
+    }
+    if (strcmp(name, "gc_fast") == 0) {
+        if (c->ws_ready) {
+            set_error("%s must be set before the first evaluation", name);
+            return GPZ_ERR_USAGE;
+        }
+        c->opt_gc_fast = value != 0.0;
         return GPZ_OK;
     }
     if (strcmp(name, "ozaki_gram_slices") == 0) {

@@ -1,0 +1,282 @@
+// Global-covariance mode with per-sample input noise (method GC + Psi; BASELINE config 5).
+//
+// The reference (GPz/getPHI.m:80-88, GPz/GPz.m:166-184) loops over every (sample i, basis j) pair with a d x d inverse of
+// Psi_i + Sigma_j: n m d^3.  With ONE covariance for all bases (GC) that matrix, S_i = Psi_i + Sigma, depends on the row
+// only, so everything reduces to one d x d factorisation per row plus GEMMs:
+//   forward   ln PHI_ij = -1/2 (x_i-p_j)' M_i (x_i-p_j) + 1/2 ln|Sigma| - 1/2 ln|S_i|,  M_i = S_i^-1
+//             = F_i . W_j  with row features  F_i = [ -1/2 x'M x + 1/2 ln|Sigma| - 1/2 ln|S_i|,  z_i = M_i x_i,  M_i(a,b) a<=b ]
+//             and basis columns               W_j = [ 1,  p_j,  -1/2 p_a^2 (a=b) / -p_a p_b (a<b) ]          K = 1 + d + d(d+1)/2
+//             -> the same tensor-core kernel as the no-Psi path (PHI = exp(F W), gemm.cu), F rebuilt per evaluation;
+//   backward  dP_j = sum_i dPHI_ij (x_i-p_j)' M_i = (dPHI' Z)_j - p_j' mat((dPHI' vech M)_j)      = the moment GEMM dPHI' F
+//             dGamma = -2 Gamma Sigma B Sigma,  B = 1/2 (s Sigma^-1 + sum_i [M_i Q_i M_i - a_i M_i]),
+//             Q_i = sum_j dPHI_ij (x_i-p_j)(x_i-p_j)' = a_i x x' - x u' - u x' + V_i  with  [a_i, u_i, vech V_i] = (dPHI G)_i,
+//             G_j = [1, p_j, p_a p_b (a<=b)]  -> one row-tile GEMM dPHI G and a per-row kernel (2 d^3 per row).
+// Cost 2 n m K per GEMM instead of n m d^3 (d = 32: K = 561 against d^3 = 32768).
+#include "internal.cuh"
+#include "smallmat.cuh"
+
+namespace gpz {
+
+int gc_feature_width(int d) { return static_cast<int>(round_up(1 + d + d * (d + 1) / 2, 32)); }
+
+// thread per row: S = Psi_i + Sigma -> M = S^-1, features
+template <int DMAX>
+__global__ void __launch_bounds__(64)
+gc_features_kernel(Params P, const double* __restrict__ X, const double* __restrict__ Psi, int64_t n, int64_t r0, int64_t r1, int KQ,
+                   double* __restrict__ F) {
+    const int64_t i = r0 + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= r1) return;
+    const int d = P.d, MP = P.MP;
+    double S[DMAX * DMAX], x[DMAX];
+    LocalMat Sm{S, d};
+    const double* psi = Psi + i * d * d;
+    for (int a = 0; a < d; ++a) {
+        for (int b = 0; b < d; ++b) Sm(a, b) = psi[a + b * d] + P.Sj[(static_cast<int64_t>(a) * d + b) * MP];   // basis 0: GC shares Sigma
+        x[a] = X[a * n + i];
+    }
+    double* f = F + (i - r0) * KQ;
+    double hl = 0.0;
+    if (!spd_inv(Sm, d, &hl)) {
+        for (int c = 0; c < KQ; ++c) f[c] = nan("");
+        return;
+    }
+    double q = 0.0;
+    for (int a = 0; a < d; ++a) {
+        double z = 0.0;
+        for (int b = 0; b < d; ++b) z += Sm(a, b) * x[b];
+        f[1 + a] = z;
+        q += z * x[a];
+    }
+    f[0] = -0.5 * q + 0.5 * P.lndS[0] - hl;
+    int idx = 1 + d;
+    for (int a = 0; a < d; ++a)
+        for (int b = a; b < d; ++b) f[idx++] = Sm(a, b);
+    for (; idx < KQ; ++idx) f[idx] = 0.0;
+}
+
+// W [KQ][MP] (forward coefficients) and G [MP][KQ] (plain monomials of p_j for the back-projection GEMM)
+__global__ void gc_basis_kernel(Params P, int KQ, double* __restrict__ W, double* __restrict__ G) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int d = P.d, MP = P.MP;
+    if (j >= MP) return;
+    const bool in = j < P.m;
+    W[j] = in ? 1.0 : 0.0;
+    G[static_cast<int64_t>(j) * KQ] = in ? 1.0 : 0.0;
+    int idx = 1 + d;
+    for (int a = 0; a < d; ++a) {
+        const double pa = in ? P.Pt[a * MP + j] : 0.0;
+        W[static_cast<int64_t>(1 + a) * MP + j] = pa;
+        G[static_cast<int64_t>(j) * KQ + 1 + a] = pa;
+        for (int b = a; b < d; ++b, ++idx) {
+            const double pb = in ? P.Pt[b * MP + j] : 0.0;
+            W[static_cast<int64_t>(idx) * MP + j] = (a == b) ? -0.5 * pa * pa : -pa * pb;
+            G[static_cast<int64_t>(j) * KQ + idx] = pa * pb;
+        }
+    }
+    for (; idx < KQ; ++idx) {
+        W[static_cast<int64_t>(idx) * MP + j] = 0.0;
+        G[static_cast<int64_t>(j) * KQ + idx] = 0.0;
+    }
+}
+
+// features of rows [r0, r1) into R.gcF (row r0 at index 0) and the basis tables R.gcW / R.gcG; phi.cu then runs PHI = exp(F W)
+int gc_features(const Params& P, const RowData& R, int64_t r0, int64_t r1, cudaStream_t st, int64_t* launches) {
+    const int KQ = gc_feature_width(P.d);
+    const int64_t rows = r1 - r0;
+    if (rows > R.gc_chunk) {
+        set_error("gc_features: chunk of %lld rows exceeds the feature buffer (%lld)", static_cast<long long>(rows),
+                  static_cast<long long>(R.gc_chunk));
+        return GPZ_ERR_USAGE;
+    }
+    const unsigned nb = static_cast<unsigned>(ceil_div(rows, 64));
+    if (P.d <= 8) gc_features_kernel<8><<<nb, 64, 0, st>>>(P, R.X, R.Psi, R.n, r0, r1, KQ, R.gcF);
+    else if (P.d <= 16) gc_features_kernel<16><<<nb, 64, 0, st>>>(P, R.X, R.Psi, R.n, r0, r1, KQ, R.gcF);
+    else gc_features_kernel<32><<<nb, 64, 0, st>>>(P, R.X, R.Psi, R.n, r0, r1, KQ, R.gcF);
+    gc_basis_kernel<<<static_cast<unsigned>(ceil_div(P.MP, 128)), 128, 0, st>>>(P, KQ, R.gcW, R.gcG);
+    GPZ_KERNEL_CHECK();
+    *launches += 2;
+    return GPZ_OK;
+}
+
+// one warp per row at a time, lane = matrix column b; per-warp accumulators  acc[a] (column b = lane) of
+//   sum_i [ a_i z z' - z y' - y z' + M V M - a_i M ],  y = M u        and (lane 0) s = sum_i a_i
+// smem per warp: M (d x d), V then T = M V (d x d), u, z.   partial: [warps_total][d*d + 1]
+template <int DMAX>
+__global__ void __launch_bounds__(256)
+gc_rows_backproj_kernel(int d, int KQ, int64_t rows, const double* __restrict__ F, const double* __restrict__ G1,
+                        double* __restrict__ partial, int accumulate) {
+    extern __shared__ double gc_sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * 8 + warp, nw = gridDim.x * 8;
+    double* Ms = gc_sm + static_cast<int64_t>(warp) * (2 * DMAX * DMAX + 2 * DMAX);
+    double* Vs = Ms + DMAX * DMAX;
+    double* us = Vs + DMAX * DMAX;
+    double* zs = us + DMAX;
+    double acc[DMAX];
+#pragma unroll
+    for (int a = 0; a < DMAX; ++a) acc[a] = 0.0;
+    double ssum = 0.0;
+    const int nv = d * (d + 1) / 2;
+    for (int64_t i = gw; i < rows; i += nw) {
+        const double* f = F + i * KQ;
+        const double* g = G1 + i * KQ;
+        __syncwarp();
+        for (int e = lane; e < nv; e += 32) {          // unpack the packed symmetric matrices
+            int a = 0, rem = e;
+            while (rem >= d - a) { rem -= d - a; ++a; }
+            const int b = a + rem;
+            const double mv = f[1 + d + e], vv = g[1 + d + e];
+            Ms[a * DMAX + b] = Ms[b * DMAX + a] = mv;
+            Vs[a * DMAX + b] = Vs[b * DMAX + a] = vv;
+        }
+        if (lane < d) {
+            us[lane] = g[1 + lane];
+            zs[lane] = f[1 + lane];
+        }
+        const double ai = g[0];
+        __syncwarp();
+        double tcol[DMAX];
+        double yb = 0.0;
+        if (lane < d) {
+            for (int c = 0; c < d; ++c) yb += Ms[lane * DMAX + c] * us[c];          // y_b, b = lane
+            for (int a = 0; a < d; ++a) {                                            // T[a][b] = sum_c M[a][c] V[c][b]
+                double s = 0.0;
+                for (int c = 0; c < d; ++c) s += Ms[a * DMAX + c] * Vs[c * DMAX + lane];
+                tcol[a] = s;
+            }
+        }
+        __syncwarp();
+        if (lane < d)
+            for (int a = 0; a < d; ++a) Vs[a * DMAX + lane] = tcol[a];               // V <- T
+        // y as a shared vector for the z y' term
+        __syncwarp();
+        if (lane < d) us[lane] = yb;                                                 // u <- y
+        __syncwarp();
+        if (lane < d) {
+            const double zb = zs[lane];
+            for (int a = 0; a < d; ++a) {
+                double r = 0.0;
+                for (int c = 0; c < d; ++c) r += Vs[a * DMAX + c] * Ms[c * DMAX + lane];     // (T M)[a][b]
+                acc[a] += ai * zs[a] * zb - zs[a] * yb - us[a] * zb + r - ai * Ms[a * DMAX + lane];
+            }
+        }
+        ssum += ai;
+    }
+    double* out = partial + static_cast<int64_t>(gw) * (d * d + 1);
+    if (lane < d)
+        for (int a = 0; a < d; ++a) out[a * d + lane] = (accumulate ? out[a * d + lane] : 0.0) + acc[a];
+    if (lane == 0) out[d * d] = (accumulate ? out[d * d] : 0.0) + ssum;
+}
+
+// single block: B = 1/2 (s A + sum of the partials); dGamma = -2 Gamma Sigma B Sigma  (GC: one d x d matrix, theta layout
+// dG[c + a d]); then thread per basis: dP_j = R2[j][1..d] - mat(R2[j][1+d..]) p_j
+__global__ void __launch_bounds__(256)
+gc_finish_kernel(Params P, int KQ, const double* __restrict__ partial, int nw, const double* __restrict__ R2, double* __restrict__ dP,
+                 double* __restrict__ dG, double* __restrict__ work) {
+    const int d = P.d, MP = P.MP, m = P.m, dp = P.dp;
+    const int tid = threadIdx.x;
+    double* B = work;                 // [d*d]
+    double* T = work + d * d;         // [d*d]
+    __shared__ double s_tot;
+    if (tid == 0) {
+        double s = 0.0;
+        for (int w = 0; w < nw; ++w) s += partial[static_cast<int64_t>(w) * (d * d + 1) + d * d];
+        s_tot = s;
+    }
+    __syncthreads();
+    for (int e = tid; e < d * d; e += 256) {
+        double v = 0.0;
+        for (int w = 0; w < nw; ++w) v += partial[static_cast<int64_t>(w) * (d * d + 1) + e];
+        const int a = e / d, b = e % d;
+        B[e] = 0.5 * (s_tot * P.Aj[(static_cast<int64_t>(a) * d + b) * MP] + v);
+    }
+    __syncthreads();
+    for (int e = tid; e < d * d; e += 256) {          // T = B Sigma
+        const int a = e / d, b = e % d;
+        double s = 0.0;
+        for (int c = 0; c < d; ++c) s += B[a * d + c] * P.Sj[(static_cast<int64_t>(c) * d + b) * MP];
+        T[e] = s;
+    }
+    __syncthreads();
+    for (int e = tid; e < d * d; e += 256) {          // B = Sigma T
+        const int a = e / d, b = e % d;
+        double s = 0.0;
+        for (int c = 0; c < d; ++c) s += P.Sj[(static_cast<int64_t>(a) * d + c) * MP] * T[c * d + b];
+        B[e] = s;
+    }
+    __syncthreads();
+    for (int e = tid; e < d * d; e += 256) {          // dGamma(c,a) = -2 sum_b Gamma(c,b) B(b,a)
+        const int a = e / d, c = e % d;
+        double s = 0.0;
+        for (int b = 0; b < d; ++b) s += P.Gam[(static_cast<int64_t>(c) * dp + b) * MP] * B[b * d + a];
+        dG[c + a * d] = -2.0 * s;
+    }
+    for (int j = tid; j < m; j += 256) {
+        const double* r = R2 + static_cast<int64_t>(j) * KQ;
+        for (int a = 0; a < d; ++a) {
+            double v = r[1 + a];
+            for (int b = 0; b < d; ++b) {
+                const int lo = a < b ? a : b, hi = a < b ? b : a;
+                const int idx = 1 + d + lo * d - lo * (lo - 1) / 2 + (hi - lo);
+                v -= r[idx] * P.Pt[b * MP + j];
+            }
+            dP[a * m + j] = v;
+        }
+    }
+}
+
+int64_t gc_backproj_ws_doubles(const Params& P, int64_t chunk_rows, int nsplit, int sm_count) {
+    const int KQ = gc_feature_width(P.d);
+    const int64_t nw = static_cast<int64_t>(sm_count) * 8;
+    return chunk_rows * KQ /*G1*/ + static_cast<int64_t>(nsplit) * (P.MP / TILE) * (KQ / 32) * TILE * 32 /*atb partial*/ +
+           static_cast<int64_t>(P.MP) * KQ /*R2*/ + nw * (P.d * P.d + 1) + 2LL * P.d * P.d;
+}
+
+// one chunk of rows: dPhi row 0 = row r0; R.gcF holds this chunk's features (row r0 at index 0)
+int gc_backproj(const Params& P, const RowData& R, int64_t r0, int64_t r1, const double* dPhi, int64_t ld, double* ws, int nsplit,
+                int sm_count, int accumulate, int last, cudaStream_t st, int64_t* launches) {
+    const int KQ = gc_feature_width(P.d), d = P.d;
+    const int64_t rows = r1 - r0;
+    double* G1 = ws;
+    double* atbp = G1 + R.gc_chunk * KQ;
+    double* R2 = atbp + static_cast<int64_t>(nsplit) * (P.MP / TILE) * (KQ / 32) * TILE * 32;
+    double* partial = R2 + static_cast<int64_t>(P.MP) * KQ;
+    int rc;
+    // moment GEMM  R2 = dPHI' F
+    if ((rc = atb_general(dPhi, ld, P.MP, R.gcF, KQ, KQ, R.gc_ones, 0, rows, nsplit, atbp, accumulate, last, R2, st, launches))) return rc;
+    // G1 = dPHI G   (rows x KQ)
+    if ((rc = sgemm(static_cast<int>(rows), KQ, P.m, 1.0, dPhi, ld, 1, R.gcG, KQ, 1, 0.0, G1, KQ, 0, st, launches))) return rc;
+    const int nblk = sm_count;
+    const size_t smem = sizeof(double) * 8 * (2 * 32 * 32 + 2 * 32);
+    if (d <= 8) {
+        gc_rows_backproj_kernel<8><<<nblk, 256, sizeof(double) * 8 * (2 * 8 * 8 + 2 * 8), st>>>(d, KQ, rows, R.gcF, G1, partial, accumulate);
+    } else if (d <= 16) {
+        gc_rows_backproj_kernel<16><<<nblk, 256, sizeof(double) * 8 * (2 * 16 * 16 + 2 * 16), st>>>(d, KQ, rows, R.gcF, G1, partial, accumulate);
+    } else {
+        static bool configured = false;
+        if (!configured) {
+            GPZ_CUDA(cudaFuncSetAttribute(gc_rows_backproj_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            configured = true;
+        }
+        gc_rows_backproj_kernel<32><<<nblk, 256, smem, st>>>(d, KQ, rows, R.gcF, G1, partial, accumulate);
+    }
+    GPZ_KERNEL_CHECK();
+    ++*launches;
+    return GPZ_OK;
+}
+
+int gc_backproj_finish(const Params& P, const RowData& R, double* ws, int nsplit, int sm_count, double* dP, double* dG, cudaStream_t st,
+                       int64_t* launches) {
+    const int KQ = gc_feature_width(P.d);
+    double* G1 = ws;
+    double* atbp = G1 + R.gc_chunk * KQ;
+    double* R2 = atbp + static_cast<int64_t>(nsplit) * (P.MP / TILE) * (KQ / 32) * TILE * 32;
+    double* partial = R2 + static_cast<int64_t>(P.MP) * KQ;
+    double* work = partial + static_cast<int64_t>(sm_count) * 8 * (P.d * P.d + 1);
+    gc_finish_kernel<<<1, 256, 0, st>>>(P, KQ, partial, sm_count * 8, R2, dP, dG, work);
+    GPZ_KERNEL_CHECK();
+    ++*launches;
+    return GPZ_OK;
+}
+
+}  // namespace gpz

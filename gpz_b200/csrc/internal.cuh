@@ -57,6 +57,10 @@ struct RowData {          // one resident row set (training or validation rows o
     double* ebW = nullptr;
     int phi_digits = 0;
     int* flag = nullptr;
+    // GC + Psi fast path (gcpsi.cu): per-evaluation row features [gc_chunk][KQ], basis tables W [KQ][MP], G [MP][KQ]
+    double *gcF = nullptr, *gcW = nullptr, *gcG = nullptr;
+    const double* gc_ones = nullptr;
+    int64_t gc_chunk = 0;
     // covariance modes with missing inputs: rows are stored sorted by NaN pattern (NaN entries zero-filled),
     // group g = rows [g_r0[g], g_r1[g]) with pattern g_pat[g]; perm[sorted position] = position in selection order
     std::vector<int64_t> g_r0, g_r1, perm;
@@ -135,6 +139,15 @@ int backproj_cov_psi(const Params& P, const RowData& R, int64_t r0, int64_t r1, 
 int backproj_cov_psi_finish(const Params& P, const RowData& R, const double* partial, int nslab, double* dP, double* dG, double* scratch,
                             cudaStream_t st, int64_t* launches);
 int64_t backproj_partial_doubles(const Params& P, int nslab, int has_psi, int has_nan);
+
+// ---- gcpsi.cu: GC + Psi through one d x d factorisation per row and GEMMs
+int gc_feature_width(int d);
+int gc_features(const Params& P, const RowData& R, int64_t r0, int64_t r1, cudaStream_t st, int64_t* launches);
+int64_t gc_backproj_ws_doubles(const Params& P, int64_t chunk_rows, int nsplit, int sm_count);
+int gc_backproj(const Params& P, const RowData& R, int64_t r0, int64_t r1, const double* dPhi, int64_t ld, double* ws, int nsplit,
+                int sm_count, int accumulate, int last, cudaStream_t st, int64_t* launches);
+int gc_backproj_finish(const Params& P, const RowData& R, double* ws, int nsplit, int sm_count, double* dP, double* dG, cudaStream_t st,
+                       int64_t* launches);
 
 // ---- predict.cu
 int predict_noisy_diag(const Params& P, const RowData& R, const double* w /*[k][MP]*/, const double* Sinv /*[k][MP][MP]*/,

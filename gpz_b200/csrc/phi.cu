@@ -472,6 +472,21 @@ int phi_build(const Params& P, const RowData& R, int64_t r0, int64_t r1, double*
         return GPZ_ERR_USAGE;
     }
     const int64_t rows = r1 - r0;
+    if (P.mode == GC && !patterned && R.gcF != nullptr) {
+        // one covariance for all bases: Psi_i + Sigma depends on the row only -> per-row features, then PHI = exp(F W) (gcpsi.cu)
+        if ((rc = gc_features(P, R, r0, r1, st, launches))) return rc;
+        const int KQ = gc_feature_width(P.d), ntn = P.MP / TILE;
+        double* p0 = dot_scratch;
+        double* p1 = dot_scratch + static_cast<int64_t>(ntn) * rows;
+        if ((rc = phi_gemm(R.gcF, KQ, KQ, R.gcW, P.MP, P.m, rows, Phi, dots.n, dots.vec[0], dots.vec[1], p0, p1, rows, nullptr, st, launches)))
+            return rc;
+        for (int q = 0; q < dots.n; ++q) {
+            sum_parts_kernel<<<static_cast<unsigned>(ceil_div(rows, 256)), 256, 0, st>>>(q == 0 ? p0 : p1, ntn, rows, rows, dots.out[q] + r0);
+            GPZ_KERNEL_CHECK();
+            ++*launches;
+        }
+        return GPZ_OK;
+    }
     const size_t ng = R.g_pat.empty() ? 1 : R.g_pat.size();
     for (size_t g = 0; g < ng; ++g) {             // one pass per missing-input pattern group (one group without NaN)
         int64_t s0 = r0, s1 = r1;

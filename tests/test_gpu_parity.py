@@ -410,3 +410,32 @@ def test_non_finite_parameters_return_nan(slices):
     f2, g2, _ = ctx.eval(theta)                                  # and the context recovers
     assert np.isfinite(f2) and np.all(np.isfinite(g2))
     ctx.close()
+
+
+@pytest.mark.parametrize("d,chunk", [(3, None), (6, 1024), (12, None)])
+def test_gc_psi_fast_path_matches_generic_kernels_and_oracle(d, chunk):
+    """GC + Psi (BASELINE config 5): one d x d factorisation per row + GEMMs (gcpsi.cu) against the per-(i,j) kernels that
+    follow getPHI.m:80-88 / GPz.m:166-184 literally, and against the oracle; also row-chunked (features rebuilt per chunk)."""
+    n, m = 2600, 40
+    model, theta, X, Y, Psi, omega, tr, va = problem("GC", True, True, False, n=n, d=d, m=m, seed=31)
+    gm = L.make_model(d, 1, m, "GC", True)
+    out = {}
+    for fast in (1, 0):
+        ctx = L.Context(gm, X, Y, Psi, omega, tr, va)
+        ctx.set_option("gc_fast", fast)
+        if chunk:
+            ctx.set_option("chunk_rows", chunk)
+        out[fast] = ctx.eval(theta)
+        f2, g2, _ = ctx.eval(theta)
+        assert f2 == out[fast][0] and np.array_equal(g2, out[fast][1])
+        ctx.close()
+    (f1, g1, s1), (f0, g0, s0) = out[1], out[0]
+    assert abs(f1 - f0) <= 1e-11 * abs(f0)
+    gb1, gb0 = grad_blocks(model, g1), grad_blocks(model, g0)
+    for nm in gb0:
+        assert rel(gb1[nm], gb0[nm]) <= 1e-8, (nm, rel(gb1[nm], gb0[nm]))
+    for key in s0:
+        assert abs(s1[key] - s0[key]) <= 1e-10 * max(1.0, abs(s0[key]))
+    if d <= 6:
+        ref = O.GPz(theta, model, X, Y, Psi, omega, tr, va)
+        assert_eval_matches(model, ref, f1, g1, s1, tol=1e-8)
