@@ -862,9 +862,11 @@ int ensure_workspace(gpz_ctx* c) {
     }
     if (c->opt_ozaki_gram < 0) c->opt_ozaki_gram = (c->opt_ozaki > 0 && k == 1) ? 1 : 0;
     if (c->opt_ozaki_gram > 0 && (c->opt_ozaki <= 0 || k != 1)) c->opt_ozaki_gram = 0;
-    // the Gram sums ~n terms per entry, so its digit truncation averages out: 6 digits (48 bits, 21 digit products) stay below
-    // the rounding of an fp64 accumulation; T = PHI iSigma (K = m terms) keeps all 7 (tools/oz_accuracy.py)
-    if (c->opt_ozaki_gs < 0) c->opt_ozaki_gs = 6;
+    // measured on a Gram-like product of real PHI values (tools/gram_digits_accuracy.py, K = 16384, long-double reference):
+    // max error / max|S| = 9.6e-17 with 7 digits, 8.8e-15 with 6, 1.7e-12 with 5; fp64 BLAS 7.5e-16.  cond(SIGMA) ~ 1e8-1e9
+    // amplifies the error of S into the gradient, so the Gram keeps all 7 digits (6 would save ~3.5 ms of 64 at the headline size
+    // and still match the fp64 DMMA path, but not the 1e-5 tolerance with margin); "ozaki_gram_slices" overrides
+    if (c->opt_ozaki_gs < 0) c->opt_ozaki_gs = c->opt_ozaki;
     if (c->opt_ozaki_gs > c->opt_ozaki) c->opt_ozaki_gs = c->opt_ozaki;
     if ((rc = A(&c->d_scal, 8))) return rc;
     if (c->opt_ozaki_gram > 0) {
