@@ -95,6 +95,15 @@ def test_eval_multi_tile_m(method):
     ctx.close()
 
 
+def test_eval_m_not_a_multiple_of_the_gram_tile():
+    """m = 300 -> MP = 384: the second 256-row tile of the digit GEMMs hangs over the end of the operand (TMA zero fill),
+    3 column tiles, ragged Cholesky panels."""
+    model, theta, X, Y, Psi, omega, tr, va = problem("VC", True, False, False, n=6000, d=3, m=300, seed=9)
+    ref, f, g, st, ctx = run_both(model, theta, X, Y, Psi, omega, tr, va)
+    assert_eval_matches(model, ref, f, g, st, tol=2e-8)       # m=300 bases in 3-d: cond(SIGMA) is large
+    ctx.close()
+
+
 @pytest.mark.parametrize("method,psi", [("VD", False), ("VC", False), ("VD", True)])
 def test_eval_row_chunked_equals_resident(method, psi):
     model, theta, X, Y, Psi, omega, tr, va = problem(method, True, psi, False, n=5000, d=3, m=20, seed=3)
