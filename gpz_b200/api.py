@@ -300,7 +300,7 @@ def train(model, X, Y, maxIter=200, maxAttempts=np.inf, omega=None, training=Non
 
 def predict(X, model, whichSet="best", Psi=None, selection=None, device=0):
     """[mu,sigma,nu,beta_i,gamma,PHI,w,iSigma_w] = predict(X,model,...) (GPz/predict.m:1-75).  Rows with missing
-    values go through predictMissing / predictNoisyMissing (diagonal modes; covariance modes raise)."""
+    values go through predictMissing / predictNoisyMissing (both mode families; they need model.best['priors'])."""
     st = model["best"] if whichSet == "best" else model["last"]
     X = np.asarray(X, dtype=np.float64)
     n_all = X.shape[0]

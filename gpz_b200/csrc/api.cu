@@ -471,9 +471,6 @@ struct gpz_ctx {
     bool gc_fast = false;
     int gc_ns = 1;
     double* gc_ws = nullptr;
-    int64_t oz_chunk = 0, opt_oz_chunk = 0;
-    cudaStream_t aux = nullptr;     // second stream of the int8 T-GEMM pipeline
-    cudaEvent_t oz_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int opt_ozaki_gram = -1;        // Gram through the int8 tensor cores too (-1: follows ozaki_slices > 0, k == 1)
     void* ozg_ws = nullptr;
     double* d_scal = nullptr;       // [0] max row weight of this eval, [1] max |y| (constant)
@@ -1320,9 +1317,6 @@ void gpz_destroy(gpz_ctx* c) {
         if (e) cudaEventDestroy(e);
     for (auto& e : c->kev)
         if (e) cudaEventDestroy(e);
-    for (auto& e : c->oz_ev)
-        if (e) cudaEventDestroy(e);
-    if (c->aux) cudaStreamDestroy(c->aux);
     if (c->h_out) cudaFreeHost(c->h_out);
     if (c->h_theta) cudaFreeHost(c->h_theta);
     if (c->st) cudaStreamDestroy(c->st);
