@@ -801,7 +801,7 @@ int ensure_workspace(gpz_ctx* c) {
         for (RowData* R : {&c->tr, &c->va}) {
             if (R->n <= 0) continue;
             R->gc_chunk = R->n < c->chunk_rows ? R->n : c->chunk_rows;
-            if ((rc = A(&R->gcF, R->gc_chunk * KQ)) || (rc = A(&R->gcW, static_cast<int64_t>(KQ) * MP)) || (rc = A(&R->gcG, MP * KQ))) return rc;
+            if ((rc = A(&R->gcF, R->gc_chunk * KQ)) || (rc = A(&R->gcW, static_cast<int64_t>(KQ) * MP)) || (rc = A(&R->gcG, MP * round_up(KQ, TILE)))) return rc;
         }
         c->gc_ns = c->sm_count / (static_cast<int>(MP / TILE) * (KQ / 32)) > 0 ? c->sm_count / (static_cast<int>(MP / TILE) * (KQ / 32)) : 1;
         if ((rc = A(&c->gc_ws, gc_backproj_ws_doubles(P, c->tr.gc_chunk > 0 ? c->tr.gc_chunk : 1, c->gc_ns, c->sm_count)))) return rc;

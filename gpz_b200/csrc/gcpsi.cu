@@ -18,6 +18,7 @@
 namespace gpz {
 
 int gc_feature_width(int d) { return static_cast<int>(round_up(1 + d + d * (d + 1) / 2, 32)); }
+static int gc_gwidth(int d) { return static_cast<int>(round_up(gc_feature_width(d), TILE)); }      // N of the row-tile GEMM dPHI G
 
 // thread per row: S = Psi_i + Sigma -> M = S^-1, features
 template <int DMAX>
@@ -55,28 +56,26 @@ gc_features_kernel(Params P, const double* __restrict__ X, const double* __restr
 }
 
 // W [KQ][MP] (forward coefficients) and G [MP][KQ] (plain monomials of p_j for the back-projection GEMM)
-__global__ void gc_basis_kernel(Params P, int KQ, double* __restrict__ W, double* __restrict__ G) {
+__global__ void gc_basis_kernel(Params P, int KQ, int KN, double* __restrict__ W, double* __restrict__ G) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int d = P.d, MP = P.MP;
     if (j >= MP) return;
     const bool in = j < P.m;
     W[j] = in ? 1.0 : 0.0;
-    G[static_cast<int64_t>(j) * KQ] = in ? 1.0 : 0.0;
+    G[static_cast<int64_t>(j) * KN] = in ? 1.0 : 0.0;
     int idx = 1 + d;
     for (int a = 0; a < d; ++a) {
         const double pa = in ? P.Pt[a * MP + j] : 0.0;
         W[static_cast<int64_t>(1 + a) * MP + j] = pa;
-        G[static_cast<int64_t>(j) * KQ + 1 + a] = pa;
+        G[static_cast<int64_t>(j) * KN + 1 + a] = pa;
         for (int b = a; b < d; ++b, ++idx) {
             const double pb = in ? P.Pt[b * MP + j] : 0.0;
             W[static_cast<int64_t>(idx) * MP + j] = (a == b) ? -0.5 * pa * pa : -pa * pb;
-            G[static_cast<int64_t>(j) * KQ + idx] = pa * pb;
+            G[static_cast<int64_t>(j) * KN + idx] = pa * pb;
         }
     }
-    for (; idx < KQ; ++idx) {
-        W[static_cast<int64_t>(idx) * MP + j] = 0.0;
-        G[static_cast<int64_t>(j) * KQ + idx] = 0.0;
-    }
+    for (int e = idx; e < KQ; ++e) W[static_cast<int64_t>(e) * MP + j] = 0.0;
+    for (int e = idx; e < KN; ++e) G[static_cast<int64_t>(j) * KN + e] = 0.0;
 }
 
 // features of rows [r0, r1) into R.gcF (row r0 at index 0) and the basis tables R.gcW / R.gcG; phi.cu then runs PHI = exp(F W)
@@ -92,7 +91,7 @@ int gc_features(const Params& P, const RowData& R, int64_t r0, int64_t r1, cudaS
     if (P.d <= 8) gc_features_kernel<8><<<nb, 64, 0, st>>>(P, R.X, R.Psi, R.n, r0, r1, KQ, R.gcF);
     else if (P.d <= 16) gc_features_kernel<16><<<nb, 64, 0, st>>>(P, R.X, R.Psi, R.n, r0, r1, KQ, R.gcF);
     else gc_features_kernel<32><<<nb, 64, 0, st>>>(P, R.X, R.Psi, R.n, r0, r1, KQ, R.gcF);
-    gc_basis_kernel<<<static_cast<unsigned>(ceil_div(P.MP, 128)), 128, 0, st>>>(P, KQ, R.gcW, R.gcG);
+    gc_basis_kernel<<<static_cast<unsigned>(ceil_div(P.MP, 128)), 128, 0, st>>>(P, KQ, gc_gwidth(P.d), R.gcW, R.gcG);
     GPZ_KERNEL_CHECK();
     *launches += 2;
     return GPZ_OK;
@@ -103,7 +102,7 @@ int gc_features(const Params& P, const RowData& R, int64_t r0, int64_t r1, cudaS
 // smem per warp: M (d x d), V then T = M V (d x d), u, z.   partial: [warps_total][d*d + 1]
 template <int DMAX>
 __global__ void __launch_bounds__(256)
-gc_rows_backproj_kernel(int d, int KQ, int64_t rows, const double* __restrict__ F, const double* __restrict__ G1,
+gc_rows_backproj_kernel(int d, int KQ, int KN, int64_t rows, const double* __restrict__ F, const double* __restrict__ G1,
                         double* __restrict__ partial, int accumulate) {
     extern __shared__ double gc_sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -119,7 +118,7 @@ gc_rows_backproj_kernel(int d, int KQ, int64_t rows, const double* __restrict__ 
     const int nv = d * (d + 1) / 2;
     for (int64_t i = gw; i < rows; i += nw) {
         const double* f = F + i * KQ;
-        const double* g = G1 + i * KQ;
+        const double* g = G1 + i * KN;
         __syncwarp();
         for (int e = lane; e < nv; e += 32) {          // unpack the packed symmetric matrices
             int a = 0, rem = e;
@@ -228,7 +227,7 @@ gc_finish_kernel(Params P, int KQ, const double* __restrict__ partial, int nw, c
 int64_t gc_backproj_ws_doubles(const Params& P, int64_t chunk_rows, int nsplit, int sm_count) {
     const int KQ = gc_feature_width(P.d);
     const int64_t nw = static_cast<int64_t>(sm_count) * 8;
-    return chunk_rows * KQ /*G1*/ + static_cast<int64_t>(nsplit) * (P.MP / TILE) * (KQ / 32) * TILE * 32 /*atb partial*/ +
+    return chunk_rows * gc_gwidth(P.d) /*G1*/ + static_cast<int64_t>(nsplit) * (P.MP / TILE) * (KQ / 32) * TILE * 32 /*atb partial*/ +
            static_cast<int64_t>(P.MP) * KQ /*R2*/ + nw * (P.d * P.d + 1) + 2LL * P.d * P.d;
 }
 
@@ -238,27 +237,28 @@ int gc_backproj(const Params& P, const RowData& R, int64_t r0, int64_t r1, const
     const int KQ = gc_feature_width(P.d), d = P.d;
     const int64_t rows = r1 - r0;
     double* G1 = ws;
-    double* atbp = G1 + R.gc_chunk * KQ;
+    double* atbp = G1 + R.gc_chunk * gc_gwidth(P.d);
     double* R2 = atbp + static_cast<int64_t>(nsplit) * (P.MP / TILE) * (KQ / 32) * TILE * 32;
     double* partial = R2 + static_cast<int64_t>(P.MP) * KQ;
     int rc;
     // moment GEMM  R2 = dPHI' F
     if ((rc = atb_general(dPhi, ld, P.MP, R.gcF, KQ, KQ, R.gc_ones, 0, rows, nsplit, atbp, accumulate, last, R2, st, launches))) return rc;
     // G1 = dPHI G   (rows x KQ)
-    if ((rc = sgemm(static_cast<int>(rows), KQ, P.m, 1.0, dPhi, ld, 1, R.gcG, KQ, 1, 0.0, G1, KQ, 0, st, launches))) return rc;
+    const int KN = gc_gwidth(d);
+    if ((rc = gemm_rows(dPhi, ld, static_cast<int>(round_up(P.m, KSTEP)), R.gcG, KN, rows, G1, st, launches))) return rc;
     const int nblk = sm_count;
     const size_t smem = sizeof(double) * 8 * (2 * 32 * 32 + 2 * 32);
     if (d <= 8) {
-        gc_rows_backproj_kernel<8><<<nblk, 256, sizeof(double) * 8 * (2 * 8 * 8 + 2 * 8), st>>>(d, KQ, rows, R.gcF, G1, partial, accumulate);
+        gc_rows_backproj_kernel<8><<<nblk, 256, sizeof(double) * 8 * (2 * 8 * 8 + 2 * 8), st>>>(d, KQ, KN, rows, R.gcF, G1, partial, accumulate);
     } else if (d <= 16) {
-        gc_rows_backproj_kernel<16><<<nblk, 256, sizeof(double) * 8 * (2 * 16 * 16 + 2 * 16), st>>>(d, KQ, rows, R.gcF, G1, partial, accumulate);
+        gc_rows_backproj_kernel<16><<<nblk, 256, sizeof(double) * 8 * (2 * 16 * 16 + 2 * 16), st>>>(d, KQ, KN, rows, R.gcF, G1, partial, accumulate);
     } else {
         static bool configured = false;
         if (!configured) {
             GPZ_CUDA(cudaFuncSetAttribute(gc_rows_backproj_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
             configured = true;
         }
-        gc_rows_backproj_kernel<32><<<nblk, 256, smem, st>>>(d, KQ, rows, R.gcF, G1, partial, accumulate);
+        gc_rows_backproj_kernel<32><<<nblk, 256, smem, st>>>(d, KQ, KN, rows, R.gcF, G1, partial, accumulate);
     }
     GPZ_KERNEL_CHECK();
     ++*launches;
@@ -269,7 +269,7 @@ int gc_backproj_finish(const Params& P, const RowData& R, double* ws, int nsplit
                        int64_t* launches) {
     const int KQ = gc_feature_width(P.d);
     double* G1 = ws;
-    double* atbp = G1 + R.gc_chunk * KQ;
+    double* atbp = G1 + R.gc_chunk * gc_gwidth(P.d);
     double* R2 = atbp + static_cast<int64_t>(nsplit) * (P.MP / TILE) * (KQ / 32) * TILE * 32;
     double* partial = R2 + static_cast<int64_t>(P.MP) * KQ;
     double* work = partial + static_cast<int64_t>(sm_count) * 8 * (P.d * P.d + 1);

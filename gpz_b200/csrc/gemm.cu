@@ -278,6 +278,7 @@ struct PEpi {
     double* part[2];        // [ntn][part_ld]
     int64_t part_ld;
     const double* ycol;     // non-null: PHI[:, m] := y (spare padded column), so the Gram also yields PHI'(w y) (GPz.m:70)
+    int plain;              // != 0: store the product itself (no exp): C = A B, used by the GC+Psi back-projection (gcpsi.cu)
 };
 
 template <int EPI, int WARPS_M>
@@ -413,8 +414,8 @@ tgemm_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
                 const int64_t gj = j0 + wn0 + j * 8 + 2 * t;
-                double p0 = (gj < pe.m) ? exp(acc[i][j][0]) : 0.0;
-                double p1 = (gj + 1 < pe.m) ? exp(acc[i][j][1]) : 0.0;
+                double p0 = (gj < pe.m) ? (pe.plain ? acc[i][j][0] : exp(acc[i][j][0])) : 0.0;
+                double p1 = (gj + 1 < pe.m) ? (pe.plain ? acc[i][j][1] : exp(acc[i][j][1])) : 0.0;
                 if (pe.ycol != nullptr && ok) {
                     if (gj == pe.m) p0 = pe.ycol[gi];
                     if (gj + 1 == pe.m) p1 = pe.ycol[gi];
@@ -491,6 +492,20 @@ int phi_gemm(const double* F, int64_t ldf, int kq, const double* W, int MP, int 
     PEpi pe{m, Phi, ndot, {vec0, vec1}, {part0, part1}, part_ld, ycol};
     int rc = g_gemm_warps != 8 ? launch_tgemm<1, 4>(F, ldf, W, MP, kq / KSTEP, n, te, pe, st)
                                 : launch_tgemm<1, 2>(F, ldf, W, MP, kq / KSTEP, n, te, pe, st);
+    if (!rc) ++*launches;
+    return rc;
+}
+
+// C[n][N] = A[n][K] B[K][N]  (N a multiple of 128, K a multiple of 16; A rows of stride lda): the PHI kernel without the exp
+int gemm_rows(const double* A, int64_t lda, int K, const double* B, int N, int64_t n, double* C, cudaStream_t st, int64_t* launches) {
+    if (n <= 0) return GPZ_OK;
+    if (N % TILE != 0 || K % KSTEP != 0) {
+        set_error("gemm_rows: N=%d must be a multiple of %d and K=%d of %d", N, TILE, K, KSTEP);
+        return GPZ_ERR_USAGE;
+    }
+    TEpi te{};
+    PEpi pe{N, C, 0, {nullptr, nullptr}, {nullptr, nullptr}, 0, nullptr, 1};
+    int rc = g_gemm_warps != 8 ? launch_tgemm<1, 4>(A, lda, B, N, K / KSTEP, n, te, pe, st) : launch_tgemm<1, 2>(A, lda, B, N, K / KSTEP, n, te, pe, st);
     if (!rc) ++*launches;
     return rc;
 }

@@ -99,6 +99,7 @@ int tgemm(const double* Phi, int64_t ld, const double* Sinv, int MP, int m, int6
 int phi_gemm(const double* F, int64_t ldf, int kq, const double* W, int MP, int m, int64_t n, double* Phi, int ndot,
              const double* vec0, const double* vec1, double* part0, double* part1, int64_t part_ld, const double* ycol,
              cudaStream_t st, int64_t* launches);
+int gemm_rows(const double* A, int64_t lda, int K, const double* B, int N, int64_t n, double* C, cudaStream_t st, int64_t* launches);
 int atb_dphi(const double* Phi, const double* H, int64_t ld, int MP, const double* F, int QP, int q, const double* cw,
              const double* dbeta, const double* w, const double* v, int64_t row0, int64_t row1, int nsplit, double* partial,
              double* colp, int accumulate, int col_accumulate, int reduce, double* R, cudaStream_t st, int64_t* launches);
