@@ -313,6 +313,13 @@ def run_gpu(args):
                                    "(MEASURED_PEAKS.json has no fp64 figure; tcgen05 has no fp64 kind, DMMA is the fp64 tensor path)",
                     "algorithmic_flops_per_launch": flops_tgemm, "kernel_ms": tm["tgemm_kernel"]}
         roof["fp64_equivalent"] = fp64_equiv
+        # the PHI build against the HBM roofline (north star: ">= 60 %"; SURVEY 8d: B_PHI = 8 (n m + n d + m d + g_dim) bytes).
+        # phase_ms["phi"] = prep + PHI = exp(F W) + row weights; the kernel is fp64-pipe bound at d = 10
+        hbm = measured.get("hbm_gbs") or 6650.0
+        b_phi = 8.0 * (n_loc * m + n_loc * d + m * d + (int(p) - m * d - 3 * m - 1))
+        roof["phi_path"] = {"algorithmic_bytes": b_phi, "ms": tm["phi"], "achieved_gbs": b_phi / (tm["phi"] * 1e-3) / 1e9,
+                            "peak_gbs": hbm, "frac": b_phi / (tm["phi"] * 1e-3) / 1e9 / hbm,
+                            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if measured.get("hbm_gbs") else "fallback 6.65 TB/s"}
         roof["phase_ms"] = {k_: round(float(v), 3) for k_, v in tm.items() if k_ not in ("i8_gemms_ops", "int8_slices", "int8_gram")}
         cpu = None
         if world == 1 and not args.no_cpu:
