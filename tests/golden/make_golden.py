@@ -22,6 +22,9 @@ CASES = {
     "GL_nan": (300, 4, 16, "GL", True, False, True, 1),
     "GD_psi_nan_k2": (300, 3, 12, "GD", False, True, True, 2),
     "VC_nan": (400, 4, 24, "VC", True, False, True, 1),
+    "VC_psi_nan": (300, 3, 12, "VC", True, True, True, 1),        # covariance mode + missing inputs + input noise
+    "VC_predict_missing": (240, 3, 8, "VC", True, True, False, 1),  # + predictMissing / predictNoisyMissing (predictCov.m:134-336)
+    "VD_predict_missing": (240, 3, 8, "VD", True, True, False, 1),  # + the diagonal family (predictDiag.m:127-295)
 }
 
 
@@ -60,11 +63,24 @@ def build(name):
             Pt = Psi[:, :, va][:, :, :40] if method[1] == "C" else Psi[va][:40]
             mu, sigma, nu, be, ga, _ = O.predict(Xt, model, Psi=Pt)
             out.update(predn_Psi=Pt, predn_mu=mu, predn_nu=nu, predn_beta_i=be, predn_gamma=ga)
+    if name.endswith("predict_missing"):
+        model.best["priors"] = O.getPrior(X, None, theta, model, tr)
+        Xm = X[va][:24].copy()
+        Xm[4:14, 1] = np.nan
+        Xm[10:20, 2] = np.nan
+        Pm = Psi[:, :, va][:, :, :24] if method[1] == "C" else Psi[va][:24]
+        mu, sigma, nu, be, ga, ph = O.predict(Xm, model, Psi=None)
+        out.update(pm_X=Xm, pm_priors=model.best["priors"], pm_mu=mu, pm_nu=nu, pm_beta_i=be, pm_gamma=ga, pm_PHI=ph)
+        mu, sigma, nu, be, ga, ph = O.predict(Xm, model, Psi=Pm)
+        out.update(pmn_Psi=Pm, pmn_mu=mu, pmn_nu=nu, pmn_beta_i=be, pmn_gamma=ga, pmn_PHI=ph)
     return out
 
 
 if __name__ == "__main__":
+    only = sys.argv[1:]
     here = os.path.dirname(os.path.abspath(__file__))
     for name in CASES:
+        if only and name not in only:
+            continue
         np.savez_compressed(os.path.join(here, name + ".npz"), **build(name))
         print("wrote", name)
