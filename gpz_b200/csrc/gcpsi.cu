@@ -20,39 +20,112 @@ namespace gpz {
 int gc_feature_width(int d) { return static_cast<int>(round_up(1 + d + d * (d + 1) / 2, 32)); }
 static int gc_gwidth(int d) { return static_cast<int>(round_up(gc_feature_width(d), TILE)); }      // N of the row-tile GEMM dPHI G
 
-// thread per row: S = Psi_i + Sigma -> M = S^-1, features
+// warp per row: S = Psi_i + Sigma is factored in shared memory (lane = matrix row), L is inverted in place (lane = column),
+// M = L^-T L^-1 is formed column by column in registers, then the features are written.  One d x d array per warp.
 template <int DMAX>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(256)
 gc_features_kernel(Params P, const double* __restrict__ X, const double* __restrict__ Psi, int64_t n, int64_t r0, int64_t r1, int KQ,
                    double* __restrict__ F) {
-    const int64_t i = r0 + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= r1) return;
+    extern __shared__ double gcf_sm[];
+    constexpr int LD = DMAX + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int d = P.d, MP = P.MP;
-    double S[DMAX * DMAX], x[DMAX];
-    LocalMat Sm{S, d};
-    const double* psi = Psi + i * d * d;
-    for (int a = 0; a < d; ++a) {
-        for (int b = 0; b < d; ++b) Sm(a, b) = psi[a + b * d] + P.Sj[(static_cast<int64_t>(a) * d + b) * MP];   // basis 0: GC shares Sigma
-        x[a] = X[a * n + i];
-    }
-    double* f = F + (i - r0) * KQ;
-    double hl = 0.0;
-    if (!spd_inv(Sm, d, &hl)) {
-        for (int c = 0; c < KQ; ++c) f[c] = nan("");
-        return;
-    }
-    double q = 0.0;
-    for (int a = 0; a < d; ++a) {
+    double* S = gcf_sm + static_cast<int64_t>(warp) * (DMAX * LD + 2 * DMAX);
+    double* xs = S + DMAX * LD;
+    double* zs = xs + DMAX;
+    const int nv = d * (d + 1) / 2;
+    for (int64_t i = r0 + static_cast<int64_t>(blockIdx.x) * 8 + warp; i < r1; i += static_cast<int64_t>(gridDim.x) * 8) {
+        const double* psi = Psi + i * d * d;
+        __syncwarp();
+        for (int e = lane; e < d * d; e += 32) {
+            const int a = e / d, b = e - a * d;
+            S[a * LD + b] = psi[a + b * d] + P.Sj[(static_cast<int64_t>(a) * d + b) * MP];      // basis 0: GC shares Sigma
+        }
+        if (lane < d) xs[lane] = X[lane * n + i];
+        __syncwarp();
+        // Cholesky, lower, in place: lane = row
+        double hl = 0.0;
+        bool ok = true;
+        for (int c = 0; c < d; ++c) {
+            const double piv = S[c * LD + c];
+            if (!(piv > 0.0)) {
+                ok = false;
+                break;
+            }
+            const double l = sqrt(piv), il = 1.0 / l;
+            hl += log(l);
+            __syncwarp();
+            if (lane == c) S[c * LD + c] = l;
+            else if (lane > c && lane < d) S[lane * LD + c] *= il;
+            __syncwarp();
+            if (lane > c && lane < d) {
+                const double arc = S[lane * LD + c];
+                for (int q = c + 1; q <= lane; ++q) S[lane * LD + q] -= arc * S[q * LD + c];
+            }
+            __syncwarp();
+        }
+        double* f = F + (i - r0) * KQ;
+        if (!ok) {
+            for (int c = lane; c < KQ; c += 32) f[c] = nan("");
+            continue;
+        }
+        // W = L^-1 in place (lower): lane = column c, forward substitution down the rows; the column is kept in registers until
+        // every lane has finished reading L
+        double col[DMAX];
+#pragma unroll
+        for (int r = 0; r < DMAX; ++r) {
+            double sacc = (r == lane) ? 1.0 : 0.0;
+            if (r < d && lane < d && r >= lane) {
+#pragma unroll
+                for (int q = 0; q < DMAX; ++q)
+                    if (q < r && q >= lane) sacc -= S[r * LD + q] * col[q];
+                col[r] = sacc / S[r * LD + r];
+            } else {
+                col[r] = 0.0;
+            }
+        }
+        __syncwarp();
+        if (lane < d) {
+#pragma unroll
+            for (int r = 0; r < DMAX; ++r)
+                if (r < d && r >= lane) S[r * LD + lane] = col[r];
+        }
+        __syncwarp();
+        // M[a][b] = sum_{c >= max(a,b)} W[c][a] W[c][b]: lane = b, all a <= b in registers, then stored in the upper triangle
+#pragma unroll
+        for (int a = 0; a < DMAX; ++a) {
+            double sacc = 0.0;
+            if (a < d && lane < d && a <= lane)
+                for (int c = lane; c < d; ++c) sacc += S[c * LD + a] * S[c * LD + lane];
+            col[a] = sacc;
+        }
+        __syncwarp();
+        if (lane < d) {
+#pragma unroll
+            for (int a = 0; a < DMAX; ++a)
+                if (a <= lane && a < d) S[a * LD + lane] = col[a];               // upper triangle incl. diagonal now holds M
+        }
+        __syncwarp();
+        // z = M x (lane = a), q = x' z
         double z = 0.0;
-        for (int b = 0; b < d; ++b) z += Sm(a, b) * x[b];
-        f[1 + a] = z;
-        q += z * x[a];
+        if (lane < d)
+            for (int b = 0; b < d; ++b) z += (b >= lane ? S[lane * LD + b] : S[b * LD + lane]) * xs[b];
+        double q = (lane < d) ? z * xs[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        if (lane < d) f[1 + lane] = z;
+        if (lane == 0) f[0] = -0.5 * q + 0.5 * P.lndS[0] - hl;
+        for (int e = lane; e < KQ - 1 - d; e += 32) {
+            double v = 0.0;
+            if (e < nv) {
+                int a = 0, rem = e;
+                while (rem >= d - a) { rem -= d - a; ++a; }
+                v = S[a * LD + a + rem];
+            }
+            f[1 + d + e] = v;
+        }
+        (void)zs;
     }
-    f[0] = -0.5 * q + 0.5 * P.lndS[0] - hl;
-    int idx = 1 + d;
-    for (int a = 0; a < d; ++a)
-        for (int b = a; b < d; ++b) f[idx++] = Sm(a, b);
-    for (; idx < KQ; ++idx) f[idx] = 0.0;
 }
 
 // W [KQ][MP] (forward coefficients) and G [MP][KQ] (plain monomials of p_j for the back-projection GEMM)
@@ -87,10 +160,27 @@ int gc_features(const Params& P, const RowData& R, int64_t r0, int64_t r1, cudaS
                   static_cast<long long>(R.gc_chunk));
         return GPZ_ERR_USAGE;
     }
-    const unsigned nb = static_cast<unsigned>(ceil_div(rows, 64));
-    if (P.d <= 8) gc_features_kernel<8><<<nb, 64, 0, st>>>(P, R.X, R.Psi, R.n, r0, r1, KQ, R.gcF);
-    else if (P.d <= 16) gc_features_kernel<16><<<nb, 64, 0, st>>>(P, R.X, R.Psi, R.n, r0, r1, KQ, R.gcF);
-    else gc_features_kernel<32><<<nb, 64, 0, st>>>(P, R.X, R.Psi, R.n, r0, r1, KQ, R.gcF);
+    int sms = 148;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int64_t want = ceil_div(rows, 8);
+    const unsigned nb = static_cast<unsigned>(want < 3LL * sms ? want : 3LL * sms);
+    if (P.d <= 8) {
+        gc_features_kernel<8><<<nb, 256, sizeof(double) * 8 * (8 * 9 + 16), st>>>(P, R.X, R.Psi, R.n, r0, r1, KQ, R.gcF);
+    } else if (P.d <= 16) {
+        gc_features_kernel<16><<<nb, 256, sizeof(double) * 8 * (16 * 17 + 32), st>>>(P, R.X, R.Psi, R.n, r0, r1, KQ, R.gcF);
+    } else {
+        const size_t smem = sizeof(double) * 8 * (32 * 33 + 64);
+        static bool configured = false;
+        if (!configured) {
+            GPZ_CUDA(cudaFuncSetAttribute(gc_features_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            configured = true;
+        }
+        gc_features_kernel<32><<<nb, 256, smem, st>>>(P, R.X, R.Psi, R.n, r0, r1, KQ, R.gcF);
+    }
     gc_basis_kernel<<<static_cast<unsigned>(ceil_div(P.MP, 128)), 128, 0, st>>>(P, KQ, gc_gwidth(P.d), R.gcW, R.gcG);
     GPZ_KERNEL_CHECK();
     *launches += 2;
