@@ -394,6 +394,18 @@ def test_digit_gemm_against_exact_arithmetic(M, N, K, digits):
     assert np.array_equal(C, C2)                                # static work partition: bit-reproducible
 
 
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (257, 129, 130), (3, 1000, 16384), (1025, 7, 127), (2, 2, 4097)])
+def test_digit_gemm_extreme_shapes(M, N, K):
+    """Single rows / columns, one-past-a-tile sizes, the largest K one int32 level accumulator may take (16384)."""
+    rng = np.random.default_rng(M * 7919 + N * 31 + K)
+    A = rng.standard_normal((M, K))
+    B = rng.standard_normal((N, K))
+    C = L.dgemm_nt(A, B)
+    ref = A @ B.T
+    amax, bmax = np.max(np.abs(A), axis=1), np.max(np.abs(B), axis=1)
+    assert np.all(np.abs(C - ref) <= 1e-15 * K * np.outer(amax, bmax) + 1e-13 * np.abs(ref))
+
+
 def test_digit_gemm_propagates_non_finite_inputs():
     A = np.ones((8, 128)); B = np.ones((8, 128))
     A[3, 5] = np.nan
