@@ -8,8 +8,8 @@
 // tensor-core GEMM (tcgen05.mma kind::i8, accumulators in TMEM).  Unlike a chain of library GEMMs (one int32 output per
 // level, summed by a separate kernel) this kernel keeps the whole level loop on chip:
 //   * one CTA PAIR (cta_group::2, UMMA 256 x 128 x 32) owns a 256 x 128 output tile; each CTA holds 128 rows;
-//   * warp 0 (one lane) streams the digit tiles with TMA (4-D tensor maps {k, digit, row, chunk}, 128B swizzle) through an
-//     8-stage mbarrier pipeline; warp 1 of the leader CTA (one lane) issues the MMAs of all digit pairs of a level into
+//   * warp 0 (one lane) streams the digit tiles with TMA (4-D tensor maps {k, digit, row, chunk} or, for operands stored with the
+//     row index contiguous (MN-major), {row, digit, k, chunk}; 128B / 64B swizzle) through an 8-stage mbarrier pipeline; warp 1 of the leader CTA (one lane) issues the MMAs of all digit pairs of a level into
 //     one TMEM accumulator; TMEM holds two accumulators so level e-1 is multiplied while level e is folded;
 //   * 16 epilogue warps read the finished level with tcgen05.ld and fold it into an fp64 running sum held in REGISTERS
 //     (128 x 128 doubles per CTA = 32 per thread), smallest level first, so the int32 level results never touch HBM;
@@ -48,10 +48,6 @@ struct OzmmaArgs {
     int lower;                // tile list = tiles touching the lower triangle (Gram); else all tiles_m x tiles_n
     int mode;                 // 0: fp64 partial tiles, 1: T-GEMM epilogue, 2: PHI = exp(.) epilogue
     int mn_major;             // operands stored [k][row] (row index contiguous) instead of [row][k]
-    uint32_t idesc;           // UMMA instruction descriptor
-    uint32_t deschiA, deschiB;   // high words of the smem matrix descriptors
-    uint32_t desclo0A, desclo0B; // low-word bits above the start address (LBO field)
-    uint32_t kadvA, kadvB;    // descriptor start-address step per 32 K-bytes
     uint64_t hintA, hintB;    // L2 eviction policy of the operand loads
     // mode 1
     const double* ea;         // [rows] row scales (including 256^-1 .. see ozaki.cu)
@@ -295,7 +291,12 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer: one elected lane of the leader CTA
         if (rank == 0 && elect_one()) {
-            // descriptor constants (set_operand_layout documents the fields); immediates, so the loop below is ~25 instructions
+            // smem matrix descriptors (cute/arch/mma_sm100_desc.hpp SmemDescriptor: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1
+            // <<46 | layout <<61; the values follow deep_gemm's make_umma_desc).  K-major, 128B swizzle: rows of 128 K-bytes, 8-row
+            // groups 1024 B apart (SBO), LBO unused (1), 32 K-bytes = +32 B.  MN-major: the tile is [128 k-rows][W bytes of the row
+            // index], W = 128 (A, SWIZZLE_128B = 2) or 64 (B, SWIZZLE_64B = 4: each CTA of the pair holds 64 of the 128 N columns);
+            // 8-k-row groups 8 W bytes apart (SBO), LBO = stride between W-wide atoms (one atom here), 32 K-rows = +32 W bytes.
+            // All immediates, so the loop below is ~25 instructions
             constexpr uint32_t VER = 1u << 14;
             constexpr uint32_t HI_A = (1024u >> 4) | VER | (2u << 29);
             constexpr uint32_t HI_B = MNMAJOR ? ((512u >> 4) | VER | (4u << 29)) : HI_A;
@@ -570,29 +571,9 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// smem matrix descriptor constants (cute/arch/mma_sm100_desc.hpp SmemDescriptor; deep_gemm make_umma_desc):
-//   K-major, 128B swizzle:  rows of 128 K-bytes, 8-row groups 1024 B apart (SBO); LBO unused (1); 32 K-bytes = +32 B
-//   MN-major: the tile is [128 k-rows][W bytes of the row index], W = 128 (A, SWIZZLE_128B) or 64 (B, SWIZZLE_64B: each CTA
-//   of the pair holds 64 of the 128 N columns); 8-k-row groups 8 W bytes apart (SBO), LBO = stride between W-wide atoms
-//   (one atom here); 32 K-rows = +32 W bytes
 void set_operand_layout(OzmmaArgs& a, int mn_major) {
     a.mn_major = mn_major;
     a.hintA = a.hintB = OM_EVICT_NORMAL;
-    const uint32_t ver = 1u << 14;       // descriptor version 1 at bit 46
-    if (!mn_major) {
-        a.idesc = OM_IDESC;
-        a.desclo0A = a.desclo0B = 1u << 16;
-        a.deschiA = a.deschiB = (1024u >> 4) | ver | (2u << 29);
-        a.kadvA = a.kadvB = 32u >> 4;
-    } else {
-        a.idesc = OM_IDESC | (1u << 15) | (1u << 16);
-        a.desclo0A = ((128u * 128u) >> 4) << 16;
-        a.desclo0B = ((128u * 64u) >> 4) << 16;
-        a.deschiA = (1024u >> 4) | ver | (2u << 29);          // SWIZZLE_128B
-        a.deschiB = (512u >> 4) | ver | (4u << 29);           // SWIZZLE_64B
-        a.kadvA = (32u * 128u) >> 4;
-        a.kadvB = (32u * 64u) >> 4;
-    }
 }
 
 // int8 digits addressed by 4 coordinates (inner first); strides in bytes (multiples of 16) of coordinates 1..3
