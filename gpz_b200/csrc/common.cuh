@@ -35,6 +35,21 @@ void set_error(const char* fmt, ...);
         }                                                                                   \
     } while (0)
 
+// cudaFuncSetAttribute (opt-in shared memory) is per device: `need()` is true the first time a call site runs on a device.
+// The library is single-caller, so no locking.
+struct PerDeviceOnce {
+    unsigned long long mask[2] = {0ull, 0ull};
+    bool need() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 128) return true;
+        unsigned long long& m = mask[dev >> 6];
+        const unsigned long long bit = 1ull << (dev & 63);
+        if (m & bit) return false;
+        m |= bit;
+        return true;
+    }
+};
+
 static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -174,10 +174,9 @@ int gc_features(const Params& P, const RowData& R, int64_t r0, int64_t r1, cudaS
         gc_features_kernel<16><<<nb, 256, sizeof(double) * 8 * (16 * 17 + 32), st>>>(P, R.X, R.Psi, R.n, r0, r1, KQ, R.gcF);
     } else {
         const size_t smem = sizeof(double) * 8 * (32 * 33 + 64);
-        static bool configured = false;
-        if (!configured) {
+        static PerDeviceOnce once;
+        if (once.need()) {
             GPZ_CUDA(cudaFuncSetAttribute(gc_features_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            configured = true;
         }
         gc_features_kernel<32><<<nb, 256, smem, st>>>(P, R.X, R.Psi, R.n, r0, r1, KQ, R.gcF);
     }
@@ -343,10 +342,9 @@ int gc_backproj(const Params& P, const RowData& R, int64_t r0, int64_t r1, const
     } else if (d <= 16) {
         gc_rows_backproj_kernel<16><<<nblk, 256, sizeof(double) * 8 * (2 * 16 * 16 + 2 * 16), st>>>(d, KQ, KN, rows, R.gcF, G1, partial, accumulate);
     } else {
-        static bool configured = false;
-        if (!configured) {
+        static PerDeviceOnce once;
+        if (once.need()) {
             GPZ_CUDA(cudaFuncSetAttribute(gc_rows_backproj_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            configured = true;
         }
         gc_rows_backproj_kernel<32><<<nblk, 256, smem, st>>>(d, KQ, KN, rows, R.gcF, G1, partial, accumulate);
     }

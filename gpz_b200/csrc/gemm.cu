@@ -192,11 +192,10 @@ static int launch_atb(const double* A, int64_t lda, const double* B, int64_t ldb
                       cudaStream_t st) {
     constexpr int TN = WARPS_N * 32;
     const size_t smem = sizeof(double) * (STAGES * KSTEP * LDT + STAGES * KSTEP * (TN + 4) + STAGES * KSTEP);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.need()) {
         GPZ_CUDA(cudaFuncSetAttribute(atb_kernel<WARPS_M, WARPS_N, SYRK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));
-        configured = true;
     }
     int64_t rps = ceil_div(row1 - row0, nsplit);
     rps = round_up(rps > 0 ? rps : 1, KSTEP);
@@ -457,10 +456,9 @@ template <int EPI, int WARPS_M>
 static int launch_tgemm(const double* A, int64_t lda, const double* B, int MP, int nk, int64_t n, const TEpi& te,
                         const PEpi& pe, cudaStream_t st) {
     const size_t smem = sizeof(double) * (STAGES * TILE * LDK + STAGES * KSTEP * LDT);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.need()) {
         GPZ_CUDA(cudaFuncSetAttribute(tgemm_kernel<EPI, WARPS_M>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        configured = true;
     }
     const int64_t nblk = ceil_div(n, TILE) * (MP / TILE);
     if (nblk > 2147483647LL) {
@@ -683,10 +681,9 @@ static int launch_atb_dphi(const double* Phi, const double* H, int64_t ld, const
                            double* partial, double* colp, int MP, int accumulate, int col_accumulate, cudaStream_t st) {
     constexpr int TN = 8 * NT;
     const size_t smem = sizeof(double) * (DSTAGES * KSTEP * LDT + DSTAGES * KSTEP * (TN + 4));
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.need()) {
         GPZ_CUDA(cudaFuncSetAttribute(atb_dphi_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        configured = true;
     }
     int64_t rps = ceil_div(row1 - row0, nsplit);
     rps = round_up(rps > 0 ? rps : 1, KSTEP);

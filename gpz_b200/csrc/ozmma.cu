@@ -606,10 +606,12 @@ int make_map(CUtensorMap* map, const int8_t* ptr, const int64_t dims[4], const i
     return GPZ_OK;
 }
 
-int g_pairs = -1;       // CTA pairs that can be co-resident (one CTA per SM)
+int g_pairs_dev[128];   // per device: CTA pairs that can be co-resident (one CTA per SM); 0 = not queried yet
 
 int resident_pairs() {
-    if (g_pairs > 0) return g_pairs;
+    int dev_id = 0;
+    if (cudaGetDevice(&dev_id) != cudaSuccess || dev_id < 0 || dev_id >= 128) dev_id = 0;
+    if (g_pairs_dev[dev_id] > 0) return g_pairs_dev[dev_id];
     if (cudaFuncSetAttribute(ozmma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, OM_SMEM_BYTES) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(ozmma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, OM_SMEM_BYTES) != cudaSuccess) return -1;
     int dev = 0, sms = 0;
@@ -632,8 +634,8 @@ int resident_pairs() {
         ncl = sms / 2;
     }
     if (ncl > sms / 2) ncl = sms / 2;
-    g_pairs = ncl;
-    return g_pairs;
+    g_pairs_dev[dev_id] = ncl;
+    return ncl;
 }
 
 int count_tiles(int tiles_m, int tiles_n, int lower) {

@@ -392,10 +392,9 @@ static int launch_phi(const Params& P, const RowData& R, int64_t r0, int64_t r1,
                       cudaStream_t st) {
     const size_t smem = sizeof(double) * PHI_ROWS * P.dp * 2;
     if (smem > 48 * 1024) {
-        static bool done = false;
-        if (!done) {
+        static PerDeviceOnce once;
+        if (once.need()) {
             GPZ_CUDA(cudaFuncSetAttribute(phi_kernel<KIND, PSI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            done = true;
         }
     }
     const int64_t nblk = ceil_div(r1 - r0, PHI_ROWS);

@@ -162,10 +162,9 @@ int spd_inverse(double* S, int m, int MP, double* Sinv, double* d_logdet, SolveW
     const int64_t ld = MP;
     int rc;
     constexpr size_t kPotfSmem = sizeof(double) * 3 * NB * (NB + 1);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    if (once.need()) {
         GPZ_CUDA(cudaFuncSetAttribute(potf2_trti_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kPotfSmem)));
-        configured = true;
     }
     // ---- blocked Cholesky: S(lower) <- L
     for (int kb = 0; kb < nblk; ++kb) {

@@ -460,3 +460,19 @@ def test_gc_psi_fast_path_matches_generic_kernels_and_oracle(d, chunk):
     if d <= 6:
         ref = O.GPz(theta, model, X, Y, Psi, omega, tr, va)
         assert_eval_matches(model, ref, f1, g1, s1, tol=1e-8)
+
+
+def test_two_devices_in_one_process():
+    """Opt-in shared-memory attributes and the resident-cluster count are per device: a second context on another GPU of the
+    same process must give the same bits."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    model, theta, X, Y, Psi, omega, tr, va = problem("VC", True, False, False, n=3000, d=4, m=150, seed=17)
+    gm = L.make_model(model.d, 1, model.m, "VC", True)
+    out = []
+    for dev in (0, 1):
+        ctx = L.Context(gm, X, Y, None, omega, tr, va, device=dev)
+        out.append(ctx.eval(theta))
+        ctx.close()
+    assert out[0][0] == out[1][0] and np.array_equal(out[0][1], out[1][1])
