@@ -1,7 +1,7 @@
 function [mu,sigma,nu,beta_i,gamma,PHI,w,iSigma_w] = predict(X,model,varargin)
 % Drop-in for GPz/predict.m:1-75: host-side selection / z-scoring / fixPsi as in the reference, the
-% per-row work on the GPU: predictFull (all methods), predictNoisy / predictMissing / predictNoisyMissing for the
-% diagonal methods (predictDiag.m:58-295).  Missing values with a covariance method raise an error.
+% per-row work on the GPU: predictFull / predictNoisy / predictMissing / predictNoisyMissing for the diagonal and the
+% covariance methods (predictDiag.m:58-295, predictCov.m:53-336).  Rows with missing values need set.priors (getPrior.m).
 pnames = {'whichSet' 'Psi' 'selection'};
 defaults = {'best' [] true(size(X,1),1)};
 [whichSet,Psi,selection] = internal.stats.parseArgs(pnames,defaults,varargin{:});
