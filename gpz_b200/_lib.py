@@ -19,12 +19,35 @@ EXPORTS = [
     "gpz_comm_unique_id", "gpz_comm_init", "gpz_eval", "gpz_eval_dev", "gpz_fit", "gpz_phi", "gpz_get_prior", "gpz_rows",
     "gpz_predict", "gpz_inv_logdet", "gpz_dxy", "gpz_stream", "gpz_sync", "gpz_launch_count",
     "gpz_last_timing", "gpz_set_option", "gpz_dgemm_nt",
+    "gpz_train", "gpz_minimize_dev", "gpz_train_default_options", "gpz_train_reason",
 ]
 
 
 class GpzModel(C.Structure):
     _fields_ = [("d", C.c_int32), ("k", C.c_int32), ("m", C.c_int32), ("method", C.c_char * 4),
                 ("heteroscedastic", C.c_int32)]
+
+
+class TrainOptions(C.Structure):
+    _fields_ = [("max_iter", C.c_int32), ("training_only", C.c_int32), ("max_attempts", C.c_double),
+                ("corrections", C.c_int32), ("max_ls", C.c_int32), ("opt_tol", C.c_double), ("prog_tol", C.c_double),
+                ("c1", C.c_double), ("c2", C.c_double), ("max_fun_evals", C.c_double)]
+
+
+class TrainIter(C.Structure):
+    _fields_ = [("iter", C.c_int32), ("fun_evals", C.c_int32), ("improved", C.c_int32), ("attempts", C.c_int32),
+                ("f", C.c_double), ("t", C.c_double), ("gtd", C.c_double), ("opt_cond", C.c_double),
+                ("stats", C.c_double * 4)]
+
+
+class TrainResult(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("fun_evals", C.c_int32), ("exitflag", C.c_int32), ("reason", C.c_int32),
+                ("attempts", C.c_int32), ("skipped_pairs", C.c_int32), ("f", C.c_double), ("opt_cond", C.c_double),
+                ("best_valid", C.c_double), ("ms_total", C.c_double), ("ms_eval", C.c_double)]
+
+
+TRAIN_CALLBACK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(TrainIter))
+OBJECTIVE_DEV = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
 
 
 class GpzError(RuntimeError):
@@ -89,6 +112,16 @@ def load():
     lib.gpz_last_timing.argtypes = [C.c_void_p, _dp]
     lib.gpz_set_option.restype = C.c_int
     lib.gpz_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+    lib.gpz_train_default_options.restype = None
+    lib.gpz_train_default_options.argtypes = [C.POINTER(TrainOptions)]
+    lib.gpz_train_reason.restype = C.c_char_p
+    lib.gpz_train_reason.argtypes = [C.c_int]
+    lib.gpz_train.restype = C.c_int
+    lib.gpz_train.argtypes = [C.c_void_p, C.POINTER(TrainOptions), _dp, _dp, _dp, TRAIN_CALLBACK, C.c_void_p,
+                              C.POINTER(TrainResult)]
+    lib.gpz_minimize_dev.restype = C.c_int
+    lib.gpz_minimize_dev.argtypes = [C.c_int64, OBJECTIVE_DEV, C.c_void_p, C.POINTER(TrainOptions), _dp, _dp, _dp,
+                                     TRAIN_CALLBACK, C.c_void_p, C.POINTER(TrainResult), C.c_int]
     _lib = lib
     return lib
 
@@ -203,6 +236,15 @@ class Context:
         check(self._lib.gpz_get_prior(self._h, ptr(th), ptr(pr)))
         return pr
 
+    def train(self, theta, best_theta, best_valid, callback=None, **options):
+        """theta = minFunc(f, theta, options) + callBack.m on the device (gpz_train).  Returns theta_last, best_theta,
+        best_valid, result dict.  callback(dict) -> truthy stops the run."""
+        th = f64(theta).reshape(-1).copy()
+        bt = f64(best_theta).reshape(-1).copy()
+        assert th.size == self.p and bt.size == self.p
+        return _run_train(lambda o, cb, bv, res: self._lib.gpz_train(self._h, C.byref(o), ptr(th), ptr(bt), C.byref(bv), cb,
+                                                                     None, C.byref(res)), th, bt, best_valid, callback, options)
+
     def stream(self) -> int:
         return int(self._lib.gpz_stream(self._h) or 0)
 
@@ -218,6 +260,56 @@ class Context:
         return dict(phi=ms[0], gram=ms[1], solve=ms[2], tgemm=ms[3], backproj=ms[4], total=ms[5],
                     gram_kernel=ms[6], tgemm_kernel=ms[7], i8_gemms_ms=ms[8], i8_gemms_ops=ms[9],
                     int8_slices=int(ms[10]), int8_gram=int(ms[11]))
+
+
+def train_options(**kw) -> TrainOptions:
+    o = TrainOptions()
+    load().gpz_train_default_options(C.byref(o))
+    for name, value in kw.items():
+        if not hasattr(o, name):
+            raise GpzError(f"unknown train option {name!r}")
+        setattr(o, name, value)
+    return o
+
+
+def _run_train(call, th, bt, best_valid, callback, options):
+    lib = load()
+    o = train_options(**options)
+    raised = []
+
+    def _cb(_user, it):
+        if callback is None:
+            return 0
+        i = it.contents
+        try:
+            return 1 if callback(dict(iter=i.iter, fun_evals=i.fun_evals, improved=bool(i.improved), attempts=i.attempts,
+                                      f=i.f, t=i.t, gtd=i.gtd, opt_cond=i.opt_cond, trainRMSE=i.stats[0],
+                                      trainLL=i.stats[1], validRMSE=i.stats[2], validLL=i.stats[3])) else 0
+        except BaseException as e:        # never unwind through the C frames
+            raised.append(e)
+            return 1
+
+    cb = TRAIN_CALLBACK(_cb)
+    bv = C.c_double(np.nan if best_valid is None else float(best_valid))
+    res = TrainResult()
+    check(call(o, cb, bv, res))
+    if raised:
+        raise raised[0]
+    info = {name: getattr(res, name) for name, _ in TrainResult._fields_}
+    info["message"] = lib.gpz_train_reason(res.reason).decode()
+    return th, bt, bv.value, info
+
+
+def minimize_dev(p, objective, theta, best_theta=None, best_valid=None, callback=None, device=0, **options):
+    """gpz_minimize_dev: the optimiser on a caller-supplied objective(d_x_ptr, d_out_ptr, stream_ptr) -> rc that fills
+    the DEVICE buffer d_out = [f, g[p], stats[4]] (used by the tests to run it on analytic functions)."""
+    lib = load()
+    th = f64(theta).reshape(-1).copy()
+    bt = th.copy() if best_theta is None else f64(best_theta).reshape(-1).copy()
+    fn = OBJECTIVE_DEV(lambda _u, dx, do, st: int(objective(dx, do, st) or 0))
+    return _run_train(lambda o, cb, bv, res: lib.gpz_minimize_dev(int(p), fn, None, C.byref(o), ptr(th), ptr(bt), C.byref(bv),
+                                                                  cb, None, C.byref(res), int(device)),
+                      th, bt, best_valid, callback, options)
 
 
 def comm_unique_id() -> bytes:

@@ -226,11 +226,10 @@ def init(X, Y, method, m, heteroscedastic=True, normalize=True, omega=None, trai
 
 def train(model, X, Y, maxIter=200, maxAttempts=np.inf, omega=None, training=None, validation=None, Psi=None,
           display=True, device=0, priors_wanted=True):
-    """model = train(model,X,Y,...) (GPz/train.m:1-81).  The optimiser is a host L-BFGS (SciPy's L-BFGS-B in
-    place of minFunc's, SURVEY.md 2.1: out of scope, stays on the host); the callback follows
-    GPz/callBack.m: best theta by validation log-likelihood, stop after maxAttempts non-improving iterations."""
-    from scipy.optimize import minimize
-
+    """model = train(model,X,Y,...) (GPz/train.m:1-81).  The optimiser is minFunc's L-BFGS as train.m:42-48 configures
+    it, run device-resident by gpz_train (gpz_b200/csrc/train.cu) together with the best-theta / early-stopping rule of
+    GPz/callBack.m; this function only prints callBack.m's table and re-fits w / iSigma_w / priors for the last and
+    the best theta (train.m:53-79)."""
     X = np.asarray(X, dtype=np.float64)
     Y = np.asarray(Y, dtype=np.float64).reshape(X.shape[0], -1)
     n, d = X.shape
@@ -239,60 +238,38 @@ def train(model, X, Y, maxIter=200, maxAttempts=np.inf, omega=None, training=Non
     Xz = (X - model["muX"][None, :]) / model["sdX"][None, :]
     Psi = fixPsi(Psi, n, model["sdX"], model["method"])
     obj = Objective(model, Xz, Yc, Psi, omega, training, validation, device=device)
-    state = dict(best_theta=model["best"]["theta"].copy(), best_valid=model["best"]["LL"], attempts=0, it=0, t=time.time())
     training_only = validation is None
+    clock = dict(t=time.time())
 
-    class _Stop(Exception):
-        pass
-
-    last = {}
-
-    def fun(th):
-        f, g = obj(th)
-        last["f"], last["stats"], last["theta"] = f, dict(obj.stats), th.copy()
-        if not (np.isfinite(f) and np.all(np.isfinite(g))):       # minFunc tolerates illegal values by backtracking
-            return 1e300, np.zeros_like(g)
-        return f, g
-
-    def callback(th):
-        state["it"] += 1
-        if not np.array_equal(th, last.get("theta")):
-            fun(th)
-        f, st = last["f"], last["stats"]
-        if training_only:
-            state["best_valid"], state["best_theta"] = st["trainLL"], th.copy()
-            mark = ""
-        elif st["validLL"] >= state["best_valid"]:
-            state["best_valid"], state["best_theta"], state["attempts"] = st["validLL"], th.copy(), 0
-            mark = "*"
-        else:
-            state["attempts"] += 1
-            mark = ""
+    def callback(it):                                               # the table of callBack.m:14-34
         if display:
-            print(f"\t{state['it']}\t{-f:1.5e}\t{st['trainRMSE']:1.5e}\t{st['trainLL']:1.5e}\t{st['validRMSE']:1.5e}\t"
-                  f"{st['validLL']:1.5e}{mark}\t{time.time() - state['t']:.3f}")
-        state["t"] = time.time()
-        if state["attempts"] >= maxAttempts:
-            raise _Stop()
+            if it["iter"] == 1:
+                print("\tIter\tlogML/n\t\tTrain RMSE\tTrain MLL\t" + ("" if training_only else "Valid RMSE\tValid MLL\t") + "Time")
+            row = f"\t{it['iter']}\t{-it['f']:1.5e}\t{it['trainRMSE']:1.5e}\t{it['trainLL']:1.5e}"
+            if not training_only:
+                mark = ("[", "]") if it["improved"] else (" ", "")
+                row += f"\t{it['validRMSE']:1.5e}\t{mark[0]}{it['validLL']:1.5e}{mark[1]}"
+            print(row + f"\t{time.time() - clock['t']:f}")
+        clock["t"] = time.time()
+        return False
 
-    theta = model["last"]["theta"].copy()
     try:
-        res = minimize(fun, theta, jac=True, method="L-BFGS-B", callback=callback,
-                       options=dict(maxiter=int(maxIter), maxcor=100, gtol=1e-5, ftol=2.2e-9))
-        theta = res.x
-    except _Stop:
-        theta = last["theta"]
-    try:
+        theta, best_theta, best_valid, info = obj.ctx.train(
+            model["last"]["theta"], model["best"]["theta"], model["best"]["LL"], callback=callback, max_iter=int(maxIter),
+            max_attempts=float(maxAttempts), training_only=1 if training_only else 0)
+        if display:
+            print(info["message"] if info["reason"] != 7 else "No improvment after maximum number of attempts")
         oG, oA, oB, oV, oT = _theta_offsets(model)
-        for name, th in (("last", theta), ("best", state["best_theta"])):
+        for name, th in (("last", theta), ("best", best_theta)):
             w, iS = obj.fit(th)                                     # train.m:53,69
             priors = obj.ctx.get_prior(th) if priors_wanted else np.ones(m) / m          # train.m:59,74 (getPrior.m)
             model[name].update(theta=th.copy(), w=w, iSigma_w=iS, priors=priors,
                                P=th[:m * d].reshape((m, d), order="F"))
             if model["heteroscedastic"]:
                 model[name]["v"] = th[oV:oV + m * k].reshape((m, k), order="F")
-        model["best"]["LL"] = state["best_valid"]
-        model["evals"] = obj.evals
+        info["best_valid"] = best_valid                            # train.m never writes best.LL back (it stays init's -inf)
+        model["evals"] = obj.evals + info["fun_evals"]
+        model["train_info"] = info
     finally:
         obj.close()
     return model

@@ -1379,6 +1379,28 @@ int gpz_eval(gpz_ctx* c, const double* theta, double* nlogML, double* grad, doub
     return GPZ_OK;
 }
 
+static int train_objective(void* user, const double* d_x, double* d_out, void* /*stream*/) {
+    return eval_device(static_cast<gpz_ctx*>(user), d_x, d_out);
+}
+
+int gpz_train(gpz_ctx* c, const gpz_train_options* opt, double* theta, double* best_theta, double* best_valid,
+              gpz_train_callback cb, void* user, gpz_train_result* res) {
+    if (!c || !theta || !best_theta || !best_valid) {
+        set_error("gpz_train: NULL argument");
+        return GPZ_ERR_USAGE;
+    }
+    GPZ_CUDA(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure_workspace(c))) return rc;
+    gpz_train_options o;
+    if (opt)
+        o = *opt;
+    else
+        gpz_train_default_options(&o);
+    if (o.training_only < 0) o.training_only = c->va.n == 0 ? 1 : 0;
+    return gpz::lbfgs_train(c->P.p, train_objective, c, &o, theta, best_theta, best_valid, cb, user, res, c->st, &c->launches);
+}
+
 int gpz_fit(gpz_ctx* c, const double* theta, double* nlogML_k, double* w, double* iSigma_w) {
     if (!c || !theta) {
         set_error("gpz_fit: NULL argument");

@@ -200,4 +200,9 @@ int ozmma_phi(const int8_t* FD8, const double* eaF, const int8_t* WD8, const dou
 int ozmma_tgemm(const int8_t* A8, const int8_t* B8, int MP, int s, int emax, int64_t rows, const double* ea, const double* eb,
                 const double* Phi, int64_t ld, const double* rw, double* H, int accumulate, double* nupart, int64_t nu_ld, int aug_col,
                 double* pred, cudaStream_t st, int64_t* launches);
+// train.cu: minFunc's L-BFGS + Wolfe line search + GPz/callBack.m, device-resident (see gpz_train in gpz_b200.h)
+int lbfgs_train(int64_t p, gpz_objective_dev fn, void* fn_user, const gpz_train_options* opt, double* theta,
+                double* best_theta, double* best_valid, gpz_train_callback cb, void* user, gpz_train_result* res,
+                cudaStream_t st, int64_t* launches);
+
 }  // namespace gpz

@@ -125,6 +125,56 @@ int gpz_dxy(int64_t n, int32_t m, int32_t d, const double* X, const double* Y, d
 int gpz_dgemm_nt(int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                  int64_t ldc, int32_t digits, int device);
 
+/* ---- theta = minFunc(f,theta,options) as GPz/train.m:38-48 configures it, with GPz/callBack.m -----
+ * Replaces, for this one configuration, minFunc_2012/minFunc/minFunc.m:258-1170 (method 'lbfgs'),
+ * WolfeLineSearch.m:32-263, ArmijoBacktrack.m:32-143, polyinterp.m:41-58, lbfgsAdd.m / lbfgsProd.m (and the MEX
+ * lbfgsAddC.c / lbfgsProdC.c) and the best-theta / early-stopping logic of GPz/callBack.m:21-48.
+ * theta, the gradients, the search direction and the (S,Y) history stay on the device; per evaluation only
+ * nine scalars cross PCIe.  Defaults are minFunc's (minFunc_processInputOptions.m:62-67,117-146).             */
+typedef struct gpz_train_options {
+    int32_t max_iter;         /* train.m 'maxIter' (200)                                                   */
+    int32_t training_only;    /* 1: no validation set (callBack.m:21-24); 0: best theta by validLL; -1: auto
+                                 from this context's validation rows (sharded callers must set it)         */
+    double  max_attempts;     /* train.m 'maxAttempts' (inf): stop after this many non-improving iterations */
+    int32_t corrections;      /* 100 */
+    int32_t max_ls;           /* 25 line-search evaluations (minFunc.m:1066)                               */
+    double  opt_tol;          /* 1e-5 */
+    double  prog_tol;         /* 1e-9 */
+    double  c1, c2;           /* 1e-4, 0.9 */
+    double  max_fun_evals;    /* inf (train.m:45)                                                          */
+} gpz_train_options;
+typedef struct gpz_train_iter {   /* what callBack.m prints per iteration                                  */
+    int32_t iter, fun_evals;
+    int32_t improved;         /* this iterate became best_theta                                            */
+    int32_t attempts;         /* -1 while the reference's `attempts` global is still unset                 */
+    double  f, t, gtd, opt_cond;
+    double  stats[4];         /* trainRMSE, trainLL, validRMSE, validLL of the LAST evaluation (the globals) */
+} gpz_train_iter;
+typedef int (*gpz_train_callback)(void* user, const gpz_train_iter* it);    /* non-zero return stops the run */
+typedef struct gpz_train_result {
+    int32_t iterations, fun_evals;
+    int32_t exitflag;         /* minFunc's: 1 optTol, 2 progTol family, 0 limits, -1 stopped by callback/attempts,
+                                 -3 illegal direction                                                      */
+    int32_t reason;           /* index for gpz_train_reason()                                              */
+    int32_t attempts, skipped_pairs;
+    double  f, opt_cond, best_valid;
+    double  ms_total;         /* host wall time of the call                                                */
+    double  ms_eval;          /* device time inside the objective evaluations (CUDA events)                */
+} gpz_train_result;
+void gpz_train_default_options(gpz_train_options* o);
+const char* gpz_train_reason(int reason);
+/* theta [p]: in = start (model.last.theta), out = final iterate.  best_theta [p] / best_valid: in = model.best.theta /
+ * model.best.LL (NaN = empty), out = updated as callBack.m does.  cb may be NULL.                           */
+int gpz_train(gpz_ctx* ctx, const gpz_train_options* opt, double* theta, double* best_theta, double* best_valid,
+              gpz_train_callback cb, void* user, gpz_train_result* res);
+/* the same optimiser on a caller-supplied objective (host callback that fills f and g for a DEVICE x): exposed so the
+ * optimiser can be tested on analytic functions.  fn(user, d_x, d_out) must enqueue on `stream` (a cudaStream_t) and
+ * leave d_out = [f, g[p], stats[4]].                                                                        */
+typedef int (*gpz_objective_dev)(void* user, const double* d_x, double* d_out, void* stream);
+int gpz_minimize_dev(int64_t p, gpz_objective_dev fn, void* fn_user, const gpz_train_options* opt, double* theta,
+                     double* best_theta, double* best_valid, gpz_train_callback cb, void* user, gpz_train_result* res,
+                     int device);
+
 /* ---- plumbing / measurement ------------------------------------------------------------------- */
 void* gpz_stream(gpz_ctx* ctx);                 /* cudaStream_t the context enqueues on            */
 int   gpz_sync(gpz_ctx* ctx);

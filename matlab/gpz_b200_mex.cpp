@@ -11,10 +11,14 @@
 //     [nl, w, iSigma_w] = gpz_b200_mex('fit', h, theta)
 //     [PHI, lnBeta_i, N] = gpz_b200_mex('phi', h, theta, which, model)
 //     prior = gpz_b200_mex('get_prior', h, theta, model)
+//     [theta, best_theta, best_valid, info] = gpz_b200_mex('train', h, theta, best_theta, best_valid, maxIter,
+//                                                          maxAttempts, trainingOnly, display)
+//         info = [iterations funEvals exitflag reason attempts skippedPairs f optCond msTotal msEval]
 //     [mu, nu, beta_i, gamma, PHI] = gpz_b200_mex('predict', model, theta, w, iSigma_w, Xz, Psi, priors)
 //     [Xi, logdet] = gpz_b200_mex('inv_logdet', X)
 //     D = gpz_b200_mex('dxy', X, Y)
 //     gpz_b200_mex('destroy', h)
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <string>
@@ -71,6 +75,25 @@ gpz_ctx* lookup(const mxArray* h) {
     auto it = g_ctx.find(id);
     if (it == g_ctx.end()) mexErrMsgIdAndTxt("gpz_b200:usage", "invalid context handle");
     return it->second;
+}
+
+// the table GPz/callBack.m:14-34 prints, one row per iteration
+struct TrainPrint {
+    bool display, training_only;
+};
+int train_row(void* user, const gpz_train_iter* it) {
+    const TrainPrint* tp = static_cast<const TrainPrint*>(user);
+    if (!tp->display) return 0;
+    if (it->iter == 1)
+        mexPrintf(tp->training_only ? "\tIter\tlogML/n\t\tTrain RMSE\tTrain MLL\n"
+                                    : "\tIter\tlogML/n\t\tTrain RMSE\tTrain MLL\tValid RMSE\tValid MLL\n");
+    if (tp->training_only)
+        mexPrintf("\t%d\t%1.5e\t%1.5e\t %1.5e\n", it->iter, -it->f, it->stats[0], it->stats[1]);
+    else
+        mexPrintf(it->improved ? "\t%d\t%1.5e\t%1.5e\t%1.5e\t%1.5e\t[%1.5e]\n" : "\t%d\t%1.5e\t%1.5e\t%1.5e\t%1.5e\t %1.5e\n",
+                  it->iter, -it->f, it->stats[0], it->stats[1], it->stats[2], it->stats[3]);
+    mexEvalString("drawnow;");
+    return 0;
 }
 
 }  // namespace
@@ -142,6 +165,34 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         gpz_model m = read_model(prhs[3]);
         plhs[0] = mxCreateDoubleMatrix(1, m.m, mxREAL);
         if (gpz_get_prior(ctx, mxGetPr(prhs[2]), mxGetPr(plhs[0]))) fail("gpz_get_prior");
+    } else if (c == "train") {
+        if (nrhs < 8) mexErrMsgIdAndTxt("gpz_b200:usage", "train(h,theta,best_theta,best_valid,maxIter,maxAttempts,trainingOnly[,display])");
+        gpz_ctx* ctx = lookup(prhs[1]);
+        const size_t p = mxGetNumberOfElements(prhs[2]);
+        if (mxGetNumberOfElements(prhs[3]) != p) mexErrMsgIdAndTxt("gpz_b200:usage", "theta and best_theta differ in length");
+        plhs[0] = mxCreateDoubleMatrix(p, 1, mxREAL);                 // inputs are never written: work on copies
+        mxArray* best = mxCreateDoubleMatrix(p, 1, mxREAL);
+        std::memcpy(mxGetPr(plhs[0]), mxGetPr(prhs[2]), sizeof(double) * p);
+        std::memcpy(mxGetPr(best), mxGetPr(prhs[3]), sizeof(double) * p);
+        double bv = mxIsEmpty(prhs[4]) ? NAN : mxGetScalar(prhs[4]);  // isempty(best_valid), callBack.m:26
+        gpz_train_options o;
+        gpz_train_default_options(&o);
+        o.max_iter = static_cast<int32_t>(mxGetScalar(prhs[5]));
+        o.max_attempts = mxGetScalar(prhs[6]);
+        o.training_only = mxGetScalar(prhs[7]) != 0;
+        TrainPrint tp{nrhs > 8 && mxGetScalar(prhs[8]) != 0, o.training_only != 0};
+        gpz_train_result r;
+        std::memset(&r, 0, sizeof(r));
+        if (gpz_train(ctx, &o, mxGetPr(plhs[0]), mxGetPr(best), &bv, train_row, &tp, &r)) fail("gpz_train");
+        if (tp.display) mexPrintf("%s\n", r.reason == 7 ? "No improvment after maximum number of attempts" : gpz_train_reason(r.reason));
+        if (nlhs > 1) plhs[1] = best; else mxDestroyArray(best);
+        if (nlhs > 2) plhs[2] = mxCreateDoubleScalar(bv);
+        if (nlhs > 3) {
+            plhs[3] = mxCreateDoubleMatrix(1, 10, mxREAL);
+            double* q = mxGetPr(plhs[3]);
+            q[0] = r.iterations, q[1] = r.fun_evals, q[2] = r.exitflag, q[3] = r.reason, q[4] = r.attempts;
+            q[5] = r.skipped_pairs, q[6] = r.f, q[7] = r.opt_cond, q[8] = r.ms_total, q[9] = r.ms_eval;
+        }
     } else if (c == "predict") {
         gpz_model m = read_model(prhs[1]);
         const size_t n = mxGetM(prhs[5]);

@@ -27,6 +27,8 @@ mxArray* mxCreateDoubleScalar(double);
 mxArray* mxCreateNumericArray(size_t, const mwSize*, mxClassID, mxComplexity);
 void mxDestroyArray(mxArray*);
 void mexErrMsgIdAndTxt(const char*, const char*, ...);
+int mexPrintf(const char*, ...);
+int mexEvalString(const char*);
 void mexLock(void);
 int mexAtExit(void (*)(void));
 }

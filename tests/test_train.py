@@ -1,0 +1,344 @@
+"""The optimiser of GPz/train.m (minFunc L-BFGS + Wolfe line search + callBack.m).
+
+CPU part: properties of the oracle restatement (oracle/minfunc_oracle.py; parity unpinned, see its header).
+GPU part: the device-resident optimiser (gpz_train / gpz_minimize_dev, gpz_b200/csrc/train.cu) against that
+oracle, iteration by iteration, on analytic objectives and on the GPz objective itself."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import minfunc_oracle as MO
+
+# ----------------------------------------------------------------------------------------------------------------
+# analytic objectives
+
+
+def rosenbrock(x):
+    f = 100.0 * (x[1] - x[0] ** 2) ** 2 + (1.0 - x[0]) ** 2
+    g = np.array([-400.0 * x[0] * (x[1] - x[0] ** 2) - 2.0 * (1.0 - x[0]), 200.0 * (x[1] - x[0] ** 2)])
+    return float(f), g
+
+
+def chained_rosenbrock(x):
+    a, b = x[:-1], x[1:]
+    f = np.sum(100.0 * (b - a ** 2) ** 2 + (1.0 - a) ** 2)
+    g = np.zeros_like(x)
+    g[:-1] += -400.0 * a * (b - a ** 2) - 2.0 * (1.0 - a)
+    g[1:] += 200.0 * (b - a ** 2)
+    return float(f), g
+
+
+def make_logistic(n=400, p=60, seed=0):
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((n, p))
+    y = np.sign(A @ rng.standard_normal(p) + 0.3 * rng.standard_normal(n))
+
+    def fun(w):
+        z = y * (A @ w)
+        f = np.sum(np.logaddexp(0.0, -z)) + 0.5 * 1e-2 * (w @ w)
+        g = A.T @ (-y / (1.0 + np.exp(z))) + 1e-2 * w
+        return float(f), g
+
+    return fun, p
+
+
+def barrier(x):
+    """finite only for x > 0: a unit first step from x = 3 lands outside, the search must back off (NaN region)."""
+    if np.any(x <= 0):
+        return float("nan"), np.full_like(x, np.nan)
+    c = np.arange(1, x.size + 1, dtype=np.float64)
+    return float(np.sum(c * x - np.log(x))), c - 1.0 / x
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU: the oracle
+
+
+def test_oracle_converges_and_every_step_satisfies_wolfe():
+    for fun, x0 in ((rosenbrock, np.zeros(2)), (chained_rosenbrock, np.full(30, -1.2)), (make_logistic()[0], np.zeros(60))):
+        steps = []
+
+        def wrapped(x, _f=fun):
+            return _f(x)
+
+        x_prev = [np.array(x0, dtype=np.float64)]
+
+        def cb(x, kind, i, fe, f, t, gtd, g, d, oc):
+            if kind == "iter":
+                steps.append((x_prev[0].copy(), x.copy(), t, gtd, d.copy()))
+                x_prev[0] = x.copy()
+            return False
+
+        x, f, flag, info = MO.minfunc_lbfgs(wrapped, x0, max_iter=500, output_fcn=cb)
+        assert flag in (1, 2), info
+        assert info["firstorderopt"] < 1e-3
+        for xa, xb, t, gtd, d in steps:
+            fa, ga = fun(xa)
+            fb, gb = fun(xb)
+            assert np.allclose(xb, xa + t * d, rtol=0, atol=1e-12 * (1 + np.abs(xa).max()))
+            assert fb <= fa + 1e-4 * t * gtd + 1e-12 * abs(fa)              # sufficient decrease (c1)
+            assert abs(gb @ d) <= 0.9 * abs(gtd) * (1 + 1e-9)               # strong curvature (c2)
+
+
+def test_oracle_two_loop_equals_dense_bfgs_inverse():
+    """lbfgsProd's recursion over the circular store == the explicit BFGS inverse built from the same pairs in
+    the same (oldest first) order, also after the store has wrapped."""
+    rng = np.random.default_rng(3)
+    p, cor = 12, 5
+    mem = MO.LbfgsMemory(p, cor)
+    pairs = []
+    for it in range(13):
+        s = rng.standard_normal(p)
+        y = s * rng.uniform(0.5, 2.0, p) + 0.05 * rng.standard_normal(p)
+        skipped = mem.add(y, s)
+        assert not skipped
+        pairs.append((s, y))
+        H = np.eye(p) * mem.Hdiag
+        for s_, y_ in pairs[-cor:]:
+            rho = 1.0 / (y_ @ s_)
+            V = np.eye(p) - rho * np.outer(s_, y_)
+            H = V @ H @ V.T + rho * np.outer(s_, s_)
+        g = rng.standard_normal(p)
+        assert np.allclose(mem.prod(g), -H @ g, rtol=1e-10, atol=1e-12)
+        assert len(mem.order()) == min(it + 1, cor)
+    assert mem.add(-pairs[0][0], pairs[0][0]) is True                       # negative curvature: pair skipped
+
+
+def test_oracle_backs_out_of_a_nan_region():
+    x, f, flag, info = MO.minfunc_lbfgs(barrier, np.full(4, 3.0))
+    c = np.arange(1, 5, dtype=np.float64)
+    assert flag in (1, 2) and np.allclose(x, 1.0 / c, rtol=1e-4)
+
+
+def test_oracle_callback_tracks_best_and_stops_after_max_attempts():
+    """callBack.m:21-35,48 with a validation score that peaks at iteration 3."""
+    valid = {1: -4.0, 2: -3.0, 3: -1.0}
+    log = []
+
+    def fun_stats(th):
+        f, g = chained_rosenbrock(th)
+        it = len(log) + 1                                                   # the iteration this evaluation belongs to
+        return f, g, (0.0, -f, 0.0, valid.get(it, -2.0 - 0.01 * it))
+
+    x, best, bv, flag, info = MO.train_loop(fun_stats, np.full(8, -1.2), np.full(8, -1.2), -np.inf, max_iter=100,
+                                            max_attempts=4, training_only=False, log=log)
+    assert flag == -1 and info["iterations"] == 7                           # 3 improving + 4 failed attempts
+    assert bv == -1.0 and [e["improved"] for e in log] == [True, True, True, False, False, False, False]
+    assert not np.array_equal(best, x)
+    # training only: the last iterate is always the best one and the run never stops early
+    log2 = []
+    x2, best2, bv2, flag2, info2 = MO.train_loop(fun_stats, np.full(8, -1.2), np.full(8, -1.2), -np.inf, max_iter=15,
+                                                 max_attempts=1, training_only=True, log=log2)
+    assert flag2 == 0 and info2["iterations"] == 15 and np.array_equal(best2, x2) and bv2 == log2[-1]["stats"][1]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GPU: the device-resident optimiser
+
+
+class _Cudart:
+    def __init__(self):
+        lib = None
+        for name in ("libcudart.so.12", "libcudart.so", "/usr/local/cuda/lib64/libcudart.so"):
+            try:
+                lib = C.CDLL(name)
+                break
+            except OSError:
+                continue
+        if lib is None:
+            import glob
+            import os
+
+            import torch
+
+            hits = glob.glob(os.path.join(os.path.dirname(os.path.dirname(torch.__file__)), "nvidia", "cuda_runtime", "lib",
+                                          "libcudart.so*"))
+            lib = C.CDLL(hits[0])
+        lib.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        lib.cudaMemcpy.restype = C.c_int
+        lib.cudaDeviceSynchronize.restype = C.c_int
+        self.lib = lib
+
+
+class DevObjective:
+    """Adapts a host f(x) -> (f, g[, stats]) to the gpz_objective_dev callback (device x in, device [f,g,stats] out)."""
+
+    def __init__(self, fun, p):
+        self.rt = _Cudart().lib
+        self.fun, self.p = fun, p
+        self.hx = np.empty(p)
+        self.ho = np.empty(p + 5)
+        self.calls = 0
+
+    def __call__(self, dx, do, st):
+        assert self.rt.cudaDeviceSynchronize() == 0
+        assert self.rt.cudaMemcpy(self.hx.ctypes.data, dx, 8 * self.p, 2) == 0
+        r = self.fun(self.hx.copy())
+        self.ho[0] = r[0]
+        self.ho[1:1 + self.p] = r[1]
+        self.ho[1 + self.p:] = r[2] if len(r) > 2 else np.nan
+        assert self.rt.cudaMemcpy(do, self.ho.ctypes.data, 8 * (self.p + 5), 1) == 0
+        self.calls += 1
+        return 0
+
+
+def _run_both(fun, x0, **opt):
+    from gpz_b200 import _lib
+
+    p = x0.size
+    names = dict(max_iter="max_iter", corrections="corrections")
+    tr = []
+    xo, fo, flag_o, info_o = MO.minfunc_lbfgs(fun, x0, trace=tr, **opt)
+    its = []
+    obj = DevObjective(fun, p)
+    xd, best, bv, info = _lib.minimize_dev(p, obj, x0, callback=lambda it: its.append(it) and False,
+                                           **{names[k]: v for k, v in opt.items()})
+    return (xo, fo, flag_o, info_o, tr), (xd, best, bv, info, its, obj)
+
+
+def _assert_same_run(o, d, rtol=1e-9, first=None):
+    xo, fo, flag_o, info_o, tr = o
+    xd, best, bv, info, its, obj = d
+    n = min(len(tr), len(its)) if first is None else first
+    for a, b in list(zip(tr, its))[:n]:
+        assert a["i"] == b["iter"]
+        assert abs(a["f"] - b["f"]) <= rtol * max(1.0, abs(a["f"])), (a, b)
+        if a["gtd"] < -1e-6:              # near convergence the interpolated step is ill-conditioned (f differences cancel)
+            assert abs(a["t"] - b["t"]) <= 1e-6 * max(1.0, abs(a["t"])), (a, b)
+    if first is None:
+        assert info["exitflag"] == flag_o and info["iterations"] == info_o["iterations"], (info, info_o)
+        assert info["fun_evals"] == info_o["funcCount"] == obj.calls
+        assert info["message"].startswith(info_o["message"][:20])
+        assert np.allclose(xd, xo, rtol=1e-6, atol=1e-8)
+
+
+@pytest.mark.gpu
+def test_device_optimiser_matches_oracle_on_analytic_objectives():
+    o, d = _run_both(rosenbrock, np.zeros(2))
+    _assert_same_run(o, d)
+    assert d[3]["exitflag"] == 1 and np.allclose(d[0], 1.0, atol=1e-4)
+    fun, p = make_logistic()
+    o, d = _run_both(fun, np.zeros(p))
+    _assert_same_run(o, d)
+    o, d = _run_both(chained_rosenbrock, np.full(200, -1.2), max_iter=3000)
+    _assert_same_run(o, d, rtol=1e-7, first=60)                              # then the two trajectories separate slowly
+    assert d[3]["exitflag"] in (1, 2) and d[3]["f"] < 1e-8 and np.allclose(d[0], 1.0, atol=1e-4)     # both reach x = 1
+    assert abs(d[3]["iterations"] - o[3]["iterations"]) < 0.2 * o[3]["iterations"]
+
+
+@pytest.mark.gpu
+def test_device_optimiser_wraps_its_history_like_the_reference():
+    """5 corrections and > 5 iterations: the circular (start, end) bookkeeping of lbfgsAdd.m:6-17."""
+    fun, p = make_logistic(300, 40, seed=2)
+    o, d = _run_both(fun, np.zeros(p), corrections=5)
+    assert o[3]["iterations"] > 12
+    _assert_same_run(o, d)
+
+
+@pytest.mark.gpu
+def test_device_optimiser_backs_out_of_nan_region_and_stops_at_max_iter():
+    o, d = _run_both(barrier, np.full(4, 3.0))
+    _assert_same_run(o, d)
+    assert np.allclose(d[0], 1.0 / np.arange(1, 5), rtol=1e-4)
+    o, d = _run_both(chained_rosenbrock, np.full(50, -1.2), max_iter=7)
+    _assert_same_run(o, d)
+    assert d[3]["exitflag"] == 0 and d[3]["iterations"] == 7 and "Maximum Number of Iterations" in d[3]["message"]
+
+
+@pytest.mark.gpu
+def test_device_optimiser_large_vector_and_reproducible():
+    """p larger than one reduction block and one rows segment; two runs are bit-identical."""
+    p = 50_000
+    rng = np.random.default_rng(5)
+    c = rng.uniform(0.5, 50.0, p)
+    b = rng.standard_normal(p)
+
+    def fun(x):
+        r = x - b
+        return float(0.5 * np.sum(c * r * r) + 0.25 * np.sum(r ** 4)), c * r + r ** 3
+
+    o, d = _run_both(fun, np.zeros(p), max_iter=40)
+    _assert_same_run(o, d, rtol=1e-8)
+    o2, d2 = _run_both(fun, np.zeros(p), max_iter=40)
+    assert np.array_equal(d[0], d2[0]) and [i["f"] for i in d[4]] == [i["f"] for i in d2[4]]
+
+
+def _gpz_case(method="VD", n=1500, d=3, m=20, seed=0):
+    from gpz_b200 import _lib
+    from oracle import gpz_oracle as O
+
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, d))
+    Y = (np.sin(X[:, 0]) + 0.3 * X[:, 1] ** 2 + (0.1 + 0.1 * np.abs(X[:, 2])) * rng.standard_normal(n)).reshape(n, 1)
+    Y = Y - Y.mean()
+    tr = np.arange(n) % 4 < 2
+    va = np.arange(n) % 4 == 2
+    P = X[rng.choice(n, m, replace=False)] + 0.1 * rng.standard_normal((m, d))
+    gam = O.init_gamma(X, P, m)
+    theta0 = O.pack_theta_init(P, gam, float(np.var(Y)), method, True)
+    cm = _lib.make_model(d, 1, m, method, True)
+    ctx = _lib.Context(cm, X, Y, training=tr, validation=va)
+    return ctx, theta0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", ["VD", "GL", "VC"])
+def test_gpz_train_follows_oracle_optimiser_on_the_gpu_objective(method):
+    """gpz_train (everything on the device) against the oracle's minFunc + callBack.m driving the SAME objective
+    through gpz_eval: same iterates, same best theta, same early stop."""
+    ctx, theta0 = _gpz_case(method)
+    try:
+        def fun_stats(th):
+            f, g, st = ctx.eval(th)
+            return f, g, (st["trainRMSE"], st["trainLL"], st["validRMSE"], st["validLL"])
+
+        log = []
+        xo, best_o, bv_o, flag_o, info_o = MO.train_loop(fun_stats, theta0, theta0, -np.inf, max_iter=40, max_attempts=6,
+                                                         training_only=False, log=log)
+        its = []
+        xd, best_d, bv_d, info = ctx.train(theta0, theta0, -np.inf, callback=lambda it: its.append(it) and False,
+                                           max_iter=40, max_attempts=6.0, training_only=0)
+        # The two runs evaluate at thetas that differ in the last bits (the direction is summed in another order).  The
+        # line search amplifies that: the cubic step of polyinterp.m:52-54 has a square root of a difference, so when
+        # the discriminant nearly cancels a 1e-16 change moves t by ~1e-8 (seen with GL at iteration 2: 4 evaluations,
+        # f differs by 1.6e-8; the objective itself moves by <= 1.1e-16 under 1-ulp changes of theta,
+        # tools/objective_sensitivity.py).  Any implementation of minFunc, MATLAB's included, has this sensitivity.
+        n = min(len(log), len(its), 8 if method == "GL" else 15)
+        assert n >= 8
+        for a, b in list(zip(log, its))[:n]:
+            assert abs(a["f"] - b["f"]) <= (1e-5 if method == "GL" else 1e-7) * max(1.0, abs(a["f"])), (a, b)
+            assert abs(a["stats"][3] - b["validLL"]) <= 1e-4 * max(1.0, abs(a["stats"][3]))
+            assert a["improved"] == b["improved"] and a["fun_evals"] == b["fun_evals"]
+        if method != "GL":
+            assert info["exitflag"] == flag_o and abs(info["iterations"] - info_o["iterations"]) <= 1
+        assert abs(bv_d - bv_o) <= 1e-3 * max(1.0, abs(bv_o))
+        assert info["ms_eval"] > 0 and info["ms_total"] >= info["ms_eval"] * 0.5
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpz_train_training_only_keeps_last_iterate_as_best():
+    from gpz_b200 import _lib
+
+    ctx, theta0 = _gpz_case("VL", n=800, m=12)
+    ctx.close()
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((600, 2))
+    Y = np.cos(X[:, :1]) + 0.1 * rng.standard_normal((600, 1))
+    from oracle import gpz_oracle as O
+
+    P = X[:10].copy()
+    theta0 = O.pack_theta_init(P, O.init_gamma(X, P, 10), float(np.var(Y)), "VD", True)
+    ctx = _lib.Context(_lib.make_model(2, 1, 10, "VD", True), X, Y)
+    try:
+        xd, best, bv, info = ctx.train(theta0, theta0, -np.inf, max_iter=12)
+        assert info["iterations"] == 12 and info["exitflag"] == 0 and info["attempts"] == -1
+        assert np.array_equal(xd, best)
+        f, g, st = ctx.eval(xd)
+        assert abs(f - info["f"]) <= 1e-10 * max(1.0, abs(f))
+        f0 = ctx.eval(theta0)[0]
+        assert f < f0
+    finally:
+        ctx.close()
