@@ -68,6 +68,67 @@ def test_sharded_two_allreduce_decomposition_gloo(method):
     assert abs(st["trainRMSE"] - str_["trainRMSE"]) <= 1e-12 and abs(st["trainLL"] - str_["trainLL"]) <= 1e-12
 
 
+def _gloo_train_worker(rank, world, port, q):
+    """The optimiser replicated on every rank over the sharded objective: the control flow needs no extra exchange
+    because f and g are identical on all ranks after the two all-reduces."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import sharded_oracle as S
+    from gpz_b200 import synth
+    from oracle import gpz_oracle as O
+    from oracle import minfunc_oracle as MO
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, d, m, k = 240, 2, 7, 1
+    X, Y = synth.make_data(n, d, seed=8, k=k)
+    X, Y = np.array(X), np.array(Y)
+    theta0 = synth.make_theta0(X, Y, "VD", m, het=True, seed=9)
+    omega = np.ones((n, 1))
+    model = O.Model(d=d, k=k, m=m, method="VD", heteroscedastic=True)
+    lo, hi = S.shard_bounds(n, rank, world)
+
+    def fun_stats(theta):
+        loc, p1 = S.sweep1(theta, model, X[lo:hi], Y[lo:hi], omega[lo:hi])
+        t = torch.from_numpy(p1)
+        dist.all_reduce(t)
+        sol = S.solve(theta, model, t.numpy())
+        t2 = torch.from_numpy(S.sweep2(theta, model, X[lo:hi], Y[lo:hi], omega[lo:hi], loc, sol))
+        dist.all_reduce(t2)
+        f, g, st = S.assemble(theta, model, sol, t2.numpy())
+        return f, g, (st["trainRMSE"], st["trainLL"], np.nan, np.nan)
+
+    x, best, bv, flag, info = MO.train_loop(fun_stats, theta0, theta0, -np.inf, max_iter=6, training_only=True)
+    out = dict(rank=rank, x=x, bv=bv, evals=info["funcCount"])
+    if rank == 0:
+        def ref_stats(theta):
+            r = O.GPz(theta, model, X, Y, None, omega)
+            return r.nlogML, r.grad, (r.stats["trainRMSE"], r.stats["trainLL"], np.nan, np.nan)
+        xr, _, bvr, _, infor = MO.train_loop(ref_stats, theta0, theta0, -np.inf, max_iter=6, training_only=True)
+        out.update(xr=xr, bvr=bvr, evals_r=infor["funcCount"])
+    q.put(out)
+    dist.destroy_process_group()
+
+
+def test_sharded_training_loop_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted([q.get(timeout=300) for _ in range(2)], key=lambda o: o["rank"])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    a, b = outs
+    assert np.array_equal(a["x"], b["x"]) and a["bv"] == b["bv"] and a["evals"] == b["evals"]      # replicas agree bit for bit
+    assert a["evals"] == a["evals_r"] and abs(a["bv"] - a["bvr"]) <= 1e-9 * abs(a["bvr"])
+    assert np.max(np.abs(a["x"] - a["xr"])) <= 1e-7 * np.max(np.abs(a["xr"]))
+
+
 def test_shard_bounds_partition():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import sharded_oracle as S
