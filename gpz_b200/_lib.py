@@ -19,7 +19,7 @@ EXPORTS = [
     "gpz_comm_unique_id", "gpz_comm_init", "gpz_eval", "gpz_eval_dev", "gpz_fit", "gpz_phi", "gpz_get_prior", "gpz_rows",
     "gpz_predict", "gpz_inv_logdet", "gpz_dxy", "gpz_stream", "gpz_sync", "gpz_launch_count",
     "gpz_last_timing", "gpz_set_option", "gpz_dgemm_nt",
-    "gpz_train", "gpz_minimize_dev", "gpz_train_default_options", "gpz_train_reason",
+    "gpz_dxy_colmean", "gpz_train", "gpz_minimize_dev", "gpz_train_default_options", "gpz_train_reason",
 ]
 
 
@@ -100,6 +100,8 @@ def load():
     lib.gpz_inv_logdet.argtypes = [C.c_int32, _dp, _dp, _dp, C.c_int]
     lib.gpz_dxy.restype = C.c_int
     lib.gpz_dxy.argtypes = [C.c_int64, C.c_int32, C.c_int32, _dp, _dp, _dp, C.c_int]
+    lib.gpz_dxy_colmean.restype = C.c_int
+    lib.gpz_dxy_colmean.argtypes = [C.c_int64, C.c_int32, C.c_int32, _dp, _dp, _dp, C.c_int]
     lib.gpz_stream.restype = C.c_void_p
     lib.gpz_stream.argtypes = [C.c_void_p]
     lib.gpz_sync.restype = C.c_int
@@ -351,6 +353,16 @@ def dxy(X, Y, device=0):
     D = np.empty((n, m), order="F")
     check(load().gpz_dxy(n, m, d, ptr(X), ptr(Y), ptr(D), int(device)))
     return D
+
+
+def dxy_colmean(X, Y, device=0):
+    """mean(Dxy(X,Y)) over the rows of X (init.m:62), reduced on the device."""
+    X, Y = f64(X), f64(Y)
+    n, d = X.shape
+    m = Y.shape[0]
+    out = np.empty(m)
+    check(load().gpz_dxy_colmean(n, m, d, ptr(X), ptr(Y), ptr(out), int(device)))
+    return out
 
 
 def dgemm_nt(A, B, digits=7, device=0):

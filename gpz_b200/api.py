@@ -185,10 +185,7 @@ def init(X, Y, method, m, heteroscedastic=True, normalize=True, omega=None, trai
     P = (rng.random((m, d)) - 0.5) * np.sqrt(12.0)                 # init.m:58
     P = P @ Vi + mu[None, :]                                       # init.m:59
     Xl = _fill_linear(Xz[training], mu, sigmas)                    # init.m:61
-    if Xl.shape[0] * m <= 20_000_000:
-        meanD = L.dxy(Xl, P, device).mean(axis=0)                  # init.m:62 (Dxy on the GPU)
-    else:                                                          # same expansion as Dxy.m:3-7, column means only
-        meanD = float(np.mean(np.sum(Xl * Xl, axis=1))) - 2.0 * (P @ Xl.mean(axis=0)) + np.sum(P * P, axis=1)
+    meanD = L.dxy_colmean(Xl, P, device)                           # init.m:62: mean(Dxy(Xl,P)), reduced on the GPU
     gamma = np.sqrt(0.5 * m ** (1.0 / d) / meanD)
     if method == "GL":
         G = np.array([gamma.mean()])

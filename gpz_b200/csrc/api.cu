@@ -1948,6 +1948,29 @@ int gpz_dxy(int64_t n, int32_t m, int32_t d, const double* X, const double* Y, d
     return rc;
 }
 
+int gpz_dxy_colmean(int64_t n, int32_t m, int32_t d, const double* X, const double* Y, double* mean, int device) {
+    if (n < 1 || m < 1 || d < 1 || !X || !Y || !mean) {
+        set_error("gpz_dxy_colmean: bad arguments");
+        return GPZ_ERR_USAGE;
+    }
+    int rc;
+    if ((rc = check_device(device))) return rc;
+    double *dX = nullptr, *dY = nullptr, *dP = nullptr, *dM = nullptr;
+    GPZ_CUDA(cudaMalloc(&dX, sizeof(double) * n * d));
+    GPZ_CUDA(cudaMalloc(&dY, sizeof(double) * m * d));
+    GPZ_CUDA(cudaMalloc(&dP, sizeof(double) * m * dxy_colmean_chunks(n)));
+    GPZ_CUDA(cudaMalloc(&dM, sizeof(double) * m));
+    GPZ_CUDA(cudaMemcpy(dX, X, sizeof(double) * n * d, cudaMemcpyHostToDevice));
+    GPZ_CUDA(cudaMemcpy(dY, Y, sizeof(double) * m * d, cudaMemcpyHostToDevice));
+    rc = dxy_colmean_device(dX, n, dY, m, d, dP, dM, nullptr);
+    if (!rc) GPZ_CUDA(cudaMemcpy(mean, dM, sizeof(double) * m, cudaMemcpyDeviceToHost));
+    cudaFree(dX);
+    cudaFree(dY);
+    cudaFree(dP);
+    cudaFree(dM);
+    return rc;
+}
+
 namespace {
 __global__ void pad_rows_kernel(const double* __restrict__ src, int64_t ld, int64_t rows, int64_t K, int64_t Kp, double* __restrict__ dst) {
     const int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;

@@ -83,6 +83,8 @@ int phi_to_density(const Params& P, const RowData& R, int64_t r0, int64_t r1, co
                    int64_t* launches);
 int rowdot(const double* Phi, int64_t ld, int m, int64_t n, const DotSpec& dots, cudaStream_t st, int64_t* launches);
 int dxy_device(const double* X, int64_t n, const double* Y, int m, int d, double* D, cudaStream_t st);
+int dxy_colmean_device(const double* X, int64_t n, const double* Y, int m, int d, double* part, double* mean, cudaStream_t st);
+int64_t dxy_colmean_chunks(int64_t n);
 int transpose_out(const double* src_rowmajor, int64_t ld, int64_t n, int m, double* dst_colmajor, cudaStream_t st);
 
 // ---- gemm.cu

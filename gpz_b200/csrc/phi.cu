@@ -628,6 +628,45 @@ int dxy_device(const double* X, int64_t n, const double* Y, int m, int d, double
     return GPZ_OK;
 }
 
+// mean(Dxy(X,Y)) (init.m:62) without materialising the n x m matrix: block (c, j) sums |xx + yy - 2xy| over a chunk of
+// rows in a fixed order, the finish kernel adds the chunks in order and divides by n.
+constexpr int DXM_ROWS = 4096;
+__global__ void __launch_bounds__(256) dxy_colsum_kernel(const double* __restrict__ X, int64_t n, const double* __restrict__ Y, int m,
+                                                         int d, double* __restrict__ part) {
+    __shared__ double sh[8];
+    const int j = blockIdx.y;
+    const int64_t i0 = static_cast<int64_t>(blockIdx.x) * DXM_ROWS, i1 = min(n, i0 + DXM_ROWS);
+    double acc = 0.0;
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += 256) {
+        double xx = 0.0, yy = 0.0, xy = 0.0;
+        for (int a = 0; a < d; ++a) {
+            const double x = X[a * n + i], y = Y[a * m + j];
+            xx = fma(x, x, xx);
+            yy = fma(y, y, yy);
+            xy = fma(x, y, xy);
+        }
+        acc += fabs(yy + (xx - 2.0 * xy));
+    }
+    const double r = block_sum<256>(acc, sh);
+    if (threadIdx.x == 0) part[static_cast<int64_t>(j) * gridDim.x + blockIdx.x] = r;
+}
+__global__ void dxy_colmean_finish_kernel(const double* __restrict__ part, int m, int nchunk, int64_t n, double* __restrict__ mean) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    double s = 0.0;
+    for (int c = 0; c < nchunk; ++c) s += part[static_cast<int64_t>(j) * nchunk + c];
+    mean[j] = s / static_cast<double>(n);
+}
+int dxy_colmean_device(const double* X, int64_t n, const double* Y, int m, int d, double* part, double* mean, cudaStream_t st) {
+    const int nchunk = static_cast<int>(ceil_div(n, DXM_ROWS));
+    dxy_colsum_kernel<<<dim3(nchunk, m), 256, 0, st>>>(X, n, Y, m, d, part);
+    GPZ_KERNEL_CHECK();
+    dxy_colmean_finish_kernel<<<static_cast<int>(ceil_div(m, 128)), 128, 0, st>>>(part, m, nchunk, n, mean);
+    GPZ_KERNEL_CHECK();
+    return GPZ_OK;
+}
+int64_t dxy_colmean_chunks(int64_t n) { return ceil_div(n, DXM_ROWS); }
+
 // row-major [n][ld] -> column-major n x m (MATLAB) through a 32x32 smem tile
 __global__ void transpose_kernel(const double* __restrict__ src, int64_t ld, int64_t n, int m, double* __restrict__ dst) {
     __shared__ double tile[32][33];

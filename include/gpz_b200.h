@@ -100,10 +100,11 @@ int gpz_phi(gpz_ctx* ctx, const double* theta, int which, double* PHI, double* l
 int gpz_get_prior(gpz_ctx* ctx, const double* theta, double* prior);
 int64_t gpz_rows(const gpz_ctx* ctx, int which);
 
-/* ---- predict core (GPz/predict.m:45-73 grouping + dispatch; predictDiag.m:58-295, predictCov.m:53-69) ---
- * Xz n x d z-scored rows (NaN = missing); Psi NULL or n x d fixPsi-normalised (methods ?L/?D).
- * Complete rows: predictFull (all methods) / predictNoisy (?L/?D).  Rows with NaN: predictMissing /
- * predictNoisyMissing (?L/?D only), which need priors (m doubles, model.best.priors; may be NULL otherwise).
+/* ---- predict core (GPz/predict.m:45-73 grouping + dispatch; predictDiag.m:58-295, predictCov.m:53-336) ---
+ * Xz n x d z-scored rows (NaN = missing); Psi NULL, n x d (methods ?L/?D) or d x d x n (methods ?C), fixPsi-normalised.
+ * Rows are grouped by NaN pattern (predict.m:45-52).  Complete rows: predictFull / predictNoisy.  Rows with NaN:
+ * predictMissing / predictNoisyMissing, which need priors (m doubles, model.best.priors; may be NULL otherwise).
+ * All four branches exist for the diagonal and for the covariance methods.
  * theta/w/iSigma_w as stored in model.best / model.last.
  * Outputs n x k each: mu (WITHOUT muY), nu, beta_i, gamma; PHI n x m (may be NULL).
  * sigma = nu + beta_i + gamma and mu += muY stay on the host (predict.m:72-73).                  */
@@ -116,6 +117,9 @@ int gpz_inv_logdet(int32_t m, const double* X, double* Xi, double* logdet, int d
 
 /* ---- D = Dxy(X,Y)  (GPz/Dxy.m:1-10): X n x d, Y m x d -> D n x m -------------------------------- */
 int gpz_dxy(int64_t n, int32_t m, int32_t d, const double* X, const double* Y, double* D, int device);
+/* mean(Dxy(X,Y)) -- the 1 x m column means init.m:62 takes for its length-scale heuristic -- without forming the
+ * n x m matrix (8 GB at the headline size).  Same per-entry formula and fma order as gpz_dxy.                   */
+int gpz_dxy_colmean(int64_t n, int32_t m, int32_t d, const double* X, const double* Y, double* mean, int device);
 
 /* ---- C = A * B'  in fp64 through the int8 tensor cores (the engine of the Gram and T-GEMM steps of GPz.m:63-72,
  * exposed for testing and reuse): A is M x K, B is N x K, C is M x N, all ROW-major with leading dimensions lda, ldb, ldc.

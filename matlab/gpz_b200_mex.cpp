@@ -17,6 +17,7 @@
 //     [mu, nu, beta_i, gamma, PHI] = gpz_b200_mex('predict', model, theta, w, iSigma_w, Xz, Psi, priors)
 //     [Xi, logdet] = gpz_b200_mex('inv_logdet', X)
 //     D = gpz_b200_mex('dxy', X, Y)
+//     mD = gpz_b200_mex('dxy_colmean', X, Y)                  % mean(Dxy(X,Y)) without the n x m matrix (init.m:62)
 //     gpz_b200_mex('destroy', h)
 #include <cmath>
 #include <cstring>
@@ -218,6 +219,12 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         if (gpz_dxy(static_cast<int64_t>(n), static_cast<int32_t>(m), static_cast<int32_t>(d), mxGetPr(prhs[1]), mxGetPr(prhs[2]),
                     mxGetPr(plhs[0]), 0))
             fail("gpz_dxy");
+    } else if (c == "dxy_colmean") {                                  // mean(Dxy(X,Y)), init.m:62
+        const size_t n = mxGetM(prhs[1]), d = mxGetN(prhs[1]), m = mxGetM(prhs[2]);
+        plhs[0] = mxCreateDoubleMatrix(1, m, mxREAL);
+        if (gpz_dxy_colmean(static_cast<int64_t>(n), static_cast<int32_t>(m), static_cast<int32_t>(d), mxGetPr(prhs[1]),
+                            mxGetPr(prhs[2]), mxGetPr(plhs[0]), 0))
+            fail("gpz_dxy_colmean");
     } else {
         mexErrMsgIdAndTxt("gpz_b200:usage", "unknown command '%s'", cmd);
     }

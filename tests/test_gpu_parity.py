@@ -150,6 +150,10 @@ def test_inv_logdet_and_dxy():
     assert np.isnan(ld) and np.isnan(Xi).all()
     X, P = rng.standard_normal((300, 4)), rng.standard_normal((17, 4))
     assert rel(L.dxy(X, P), O.Dxy(X, P)) <= 1e-13
+    # init.m:62 takes the column means; gpz_dxy_colmean reduces them on the device (ragged chunk: 9001 rows)
+    X2 = rng.standard_normal((9001, 4))
+    assert rel(L.dxy_colmean(X2, P), O.Dxy(X2, P).mean(axis=0)) <= 1e-13
+    assert rel(L.dxy_colmean(X[:1], P), O.Dxy(X[:1], P)[0]) <= 1e-13
 
 
 @pytest.mark.parametrize("method,psi", [(m, p) for m in synth.METHODS for p in (False, True)])
