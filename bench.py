@@ -266,6 +266,20 @@ def run_gpu(args):
     e2e_step = float(t.item()) / K
     assert abs(f_e2e - f_last) <= 1e-12 * abs(f_last), (f_e2e, f_last)   # same theta -> same answer on both arms
 
+    # ---- a few iterations of the training loop (gpz_train: minFunc L-BFGS + line search on the device) -- reported
+    # beside the metric, outside every timed region; all ranks take part (the objective all-reduces)
+    train = None
+    if args.train_iters > 0:
+        try:
+            barrier()
+            _, _, _, ti = ctx.train(theta0, theta0, -np.inf, max_iter=args.train_iters, training_only=1)
+            train = {"iterations": ti["iterations"], "fun_evals": ti["fun_evals"], "ms_total": ti["ms_total"],
+                     "ms_in_evals": ti["ms_eval"], "optimizer_ms_per_iteration": (ti["ms_total"] - ti["ms_eval"]) / max(1, ti["iterations"]),
+                     "nlogML_start": float(ctx.eval(theta0)[0]), "nlogML_end": ti["f"], "exit": ti["message"]}
+        except Exception as e:                                           # never lose the bench line to the extra leg
+            train = {"error": str(e)[:200]}
+        barrier()
+
     # ---- roofline of the dominant kernel -------------------------------------------------------------
     peak = fp64_peak_tflops(torch, dev) if rank == 0 else None
     line = None
@@ -343,6 +357,7 @@ def run_gpu(args):
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "train": train,
             "check": {"nlogML_last": f_last, "trainRMSE": float(st["trainRMSE"])},
         }
         print(json.dumps(line), flush=True)
@@ -361,6 +376,7 @@ def main():
     ap.add_argument("--workload", default="target", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=0, help="rows of the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--train-iters", type=int, default=5, help="iterations of the device-resident training loop reported in 'train' (0 = skip)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
