@@ -714,7 +714,11 @@ int ensure_workspace(gpz_ctx* c) {
     // row chunking: keep PHI and H (2 x rows x MP doubles) within ~55% of the free memory
     size_t free_b = 0, total_b = 0;
     GPZ_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    if (c->opt_ozaki < 0) c->opt_ozaki = ozmma_available() ? 7 : 0;
+    // default GEMM engine: the int8 digit GEMMs (ozmma.cu), except for a single 128-wide basis tile on few rows, where half
+    // of every 256-row UMMA tile is padding and the launch is latency-bound: there the fp64 DMMA kernels win
+    // (tools/small_latency.py: m=100, 2.4e3..1.6e5 rows: 0.38/0.41/1.03 ms against 0.43/0.48/1.19 ms per evaluation;
+    // m>=500 is faster on the int8 path from a few thousand rows on)
+    if (c->opt_ozaki < 0) c->opt_ozaki = (ozmma_available() && !(MP <= 128 && n < 250000)) ? 7 : 0;
     const double bytes_per_elt = 16.0 + (c->opt_ozaki > 0 ? 2.0 * c->opt_ozaki : 0.0);     // PHI, H (+ two digit sets)
     int64_t max_rows = static_cast<int64_t>(0.55 * static_cast<double>(free_b) / (bytes_per_elt * MP));
     max_rows = max_rows / 1024 * 1024;

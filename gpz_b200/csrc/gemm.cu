@@ -176,7 +176,8 @@ __global__ void atb_reduce_kernel(const double* __restrict__ partial, int nsplit
         jt = tile / ntiles_n;
         ct = tile % ntiles_n;
     }
-    for (int e = threadIdx.x; e < TILE * TN; e += blockDim.x) {
+    // blockIdx.y splits the tile's elements, so that few-tile problems (small m) still fill the machine
+    for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < TILE * TN; e += blockDim.x * gridDim.y) {
         double s = 0.0;
         for (int sp = 0; sp < nsplit; ++sp) s += partial[(static_cast<int64_t>(sp) * ntiles + tile) * (TILE * TN) + e];
         const int r = e / TN, c = e % TN;
@@ -184,6 +185,12 @@ __global__ void atb_reduce_kernel(const double* __restrict__ partial, int nsplit
         C[gr * ldc + gc] = s;
         if (SYRK && jt != ct) C[gc * ldc + gr] = s;
     }
+}
+
+static dim3 atb_reduce_grid(int ntiles, int TN) {
+    const int per_tile = static_cast<int>(ceil_div(static_cast<int64_t>(TILE) * TN, 256));
+    const int want = static_cast<int>(ceil_div(592, ntiles));
+    return dim3(ntiles, want < per_tile ? want : per_tile);
 }
 
 template <int WARPS_M, int WARPS_N, bool SYRK>
@@ -223,7 +230,7 @@ int gram_syrk_finish(const double* partial, int nsplit, int MP, int reduce, doub
     if (!reduce) return GPZ_OK;
     const int T = MP / TILE;
     const int ntri = T * (T + 1) / 2;
-    atb_reduce_kernel<true><<<ntri, 256, 0, st>>>(partial, nsplit, ntri, T, TILE, S, MP);
+    atb_reduce_kernel<true><<<atb_reduce_grid(ntri, TILE), 256, 0, st>>>(partial, nsplit, ntri, T, TILE, S, MP);
     GPZ_KERNEL_CHECK();
     ++*launches;
     return GPZ_OK;
@@ -245,7 +252,7 @@ int atb_general(const double* A, int64_t lda, int MP, const double* B, int64_t l
     if (rc) return rc;
     ++*launches;
     if (reduce) {
-        atb_reduce_kernel<false><<<tm * tn, 256, 0, st>>>(partial, nsplit, tm * tn, tn, 32, R, QP);
+        atb_reduce_kernel<false><<<atb_reduce_grid(tm * tn, 32), 256, 0, st>>>(partial, nsplit, tm * tn, tn, 32, R, QP);
         GPZ_KERNEL_CHECK();
         ++*launches;
     }
@@ -720,7 +727,7 @@ int atb_dphi(const double* Phi, const double* H, int64_t ld, int MP, const doubl
     ++*launches;
     if (reduce) {
         const int tm = MP / TILE;
-        atb_reduce_kernel<false><<<tm, 256, 0, st>>>(partial, nsplit, tm, 1, TN, R, QP);
+        atb_reduce_kernel<false><<<atb_reduce_grid(tm, TN), 256, 0, st>>>(partial, nsplit, tm, 1, TN, R, QP);
         GPZ_KERNEL_CHECK();
         ++*launches;
     }

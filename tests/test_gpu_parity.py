@@ -47,12 +47,16 @@ def problem(method, het, psi, nan, n=300, d=3, m=20, k=1, seed=0, valid=True):
     return model, theta, X, np.array(Y), Psi, omega, tr, va
 
 
-def run_both(model, theta, X, Y, Psi, omega, tr, va, chunk_rows=None):
+def run_both(model, theta, X, Y, Psi, omega, tr, va, chunk_rows=None, digits=None):
+    """digits: None = the library's automatic choice of GEMM engine (fp64 DMMA kernels for one 128-wide basis tile on few
+    rows, int8 digit GEMMs otherwise); 7 = force the int8 tcgen05 path; 0 = force the fp64 DMMA path."""
     ref = O.GPz(theta, model, X, Y, Psi, omega, tr, va)
     gm = L.make_model(model.d, model.k, model.m, model.method, model.heteroscedastic)
     ctx = L.Context(gm, X, Y, Psi, omega, tr, va)
     if chunk_rows:
         ctx.set_option("chunk_rows", chunk_rows)
+    if digits is not None:
+        ctx.set_option("ozaki_slices", digits)
     f, g, st = ctx.eval(theta)
     f2, g2, _ = ctx.eval(theta)
     assert f == f2 and np.array_equal(g, g2), "evaluation is not bit-reproducible"
@@ -76,10 +80,13 @@ def assert_eval_matches(model, ref, f, g, st, tol=TOL):
 COMBOS = list(itertools.product(synth.METHODS, (True, False), (False, True), (False, True)))
 
 
+@pytest.mark.parametrize("engine", ["int8", "auto"])
 @pytest.mark.parametrize("method,het,psi,nan", COMBOS)
-def test_eval_matches_oracle(method, het, psi, nan):
+def test_eval_matches_oracle(method, het, psi, nan, engine):
+    """engine int8: the tcgen05 digit GEMMs forced on (what large problems use); auto: at this size the fp64 DMMA kernels."""
     model, theta, X, Y, Psi, omega, tr, va = problem(method, het, psi, nan)
-    ref, f, g, st, ctx = run_both(model, theta, X, Y, Psi, omega, tr, va)
+    ref, f, g, st, ctx = run_both(model, theta, X, Y, Psi, omega, tr, va, digits=7 if engine == "int8" else None)
+    assert ctx.last_timing()["int8_slices"] == (7 if engine == "int8" else 0)
     assert_eval_matches(model, ref, f, g, st)
     ctx.close()
 
@@ -100,14 +107,16 @@ def test_eval_m_not_a_multiple_of_the_gram_tile():
     3 column tiles, ragged Cholesky panels."""
     model, theta, X, Y, Psi, omega, tr, va = problem("VC", True, False, False, n=6000, d=3, m=300, seed=9)
     ref, f, g, st, ctx = run_both(model, theta, X, Y, Psi, omega, tr, va)
+    assert ctx.last_timing()["int8_slices"] == 7              # more than one basis tile: the digit GEMMs are the default
     assert_eval_matches(model, ref, f, g, st, tol=2e-8)       # m=300 bases in 3-d: cond(SIGMA) is large
     ctx.close()
 
 
+@pytest.mark.parametrize("digits", [7, None])
 @pytest.mark.parametrize("method,psi", [("VD", False), ("VC", False), ("VD", True)])
-def test_eval_row_chunked_equals_resident(method, psi):
+def test_eval_row_chunked_equals_resident(method, psi, digits):
     model, theta, X, Y, Psi, omega, tr, va = problem(method, True, psi, False, n=5000, d=3, m=20, seed=3)
-    ref, f, g, st, ctx = run_both(model, theta, X, Y, Psi, omega, tr, va, chunk_rows=1024)
+    ref, f, g, st, ctx = run_both(model, theta, X, Y, Psi, omega, tr, va, chunk_rows=1024, digits=digits)
     assert_eval_matches(model, ref, f, g, st)
     ctx.close()
 
