@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("GPZ_B200_LIB") or os.path.join(_HERE, "libgpz_b200.so
 EXPORTS = [
     "gpz_last_error", "gpz_version", "gpz_theta_len", "gpz_g_dim", "gpz_create", "gpz_destroy",
     "gpz_comm_unique_id", "gpz_comm_init", "gpz_eval", "gpz_eval_dev", "gpz_fit", "gpz_phi", "gpz_get_prior", "gpz_rows",
-    "gpz_predict", "gpz_inv_logdet", "gpz_dxy", "gpz_stream", "gpz_sync", "gpz_launch_count",
+    "gpz_predict", "gpz_inv_logdet", "gpz_dxy", "gpz_stream", "gpz_sync", "gpz_launch_count", "gpz_graph_replays",
     "gpz_last_timing", "gpz_set_option", "gpz_dgemm_nt",
     "gpz_dxy_colmean", "gpz_train", "gpz_minimize_dev", "gpz_train_default_options", "gpz_train_reason",
 ]
@@ -108,6 +108,8 @@ def load():
     lib.gpz_sync.argtypes = [C.c_void_p]
     lib.gpz_launch_count.restype = C.c_int64
     lib.gpz_launch_count.argtypes = [C.c_void_p]
+    lib.gpz_graph_replays.restype = C.c_int64
+    lib.gpz_graph_replays.argtypes = [C.c_void_p]
     lib.gpz_dgemm_nt.restype = C.c_int
     lib.gpz_dgemm_nt.argtypes = [C.c_int64, C.c_int64, C.c_int64, _dp, C.c_int64, _dp, C.c_int64, _dp, C.c_int64, C.c_int32, C.c_int]
     lib.gpz_last_timing.restype = C.c_int
@@ -255,6 +257,9 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self._lib.gpz_launch_count(self._h))
+
+    def graph_replays(self) -> int:
+        return int(self._lib.gpz_graph_replays(self._h))
 
     def last_timing(self):
         ms = np.empty(12)

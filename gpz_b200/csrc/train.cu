@@ -65,7 +65,7 @@ struct RedArgs {
 
 // One pass over a p-vector pair, four reductions, finished by the last block in block order.
 //   OP_DIR : a = g, b = d            -> res = { g'd, sum|g|, max|d|, d non-finite }
-//   OP_EVAL: a = g_new, b = d        -> res = { g_new'd, 0, max|g_new|, g_new non-finite, f, stats[4] }
+//   OP_EVAL: a = g_new, b = d, o1 = copy of g_new -> res = { g_new'd, 0, max|g_new|, g_new non-finite, f, stats[4] }
 //   OP_PAIR: a = g_new, b = g_old, c = d: o1 = s = t d, o2 = y = g_new - g_old -> res = { y's, y'y }
 template <int OP>
 __global__ void __launch_bounds__(RT) reduce_kernel(const RedArgs A) {
@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(RT) reduce_kernel(const RedArgs A) {
             if (!isfinite(d)) m3 = 1.0;
         } else if (OP == OP_EVAL) {
             const double g = A.a[i], d = A.b[i];
+            A.o1[i] = g;                          // keep this point's gradient (the objective always writes one fixed buffer)
             s0 += g * d;
             m2 = fmax(m2, fabs(g));
             if (!isfinite(g)) m3 = 1.0;
@@ -244,7 +245,9 @@ struct Trainer {
     int64_t own_launches = 0;
     // device
     double *x = nullptr, *xt = nullptr, *d = nullptr, *s_tmp = nullptr, *y_tmp = nullptr, *best = nullptr;
-    double* out[4] = {nullptr, nullptr, nullptr, nullptr};
+    double* out[4] = {nullptr, nullptr, nullptr, nullptr};     // gradients of the line-search points ([0] unused, g at [1..p])
+    double* out_eval = nullptr;    // the objective always reads xt and writes here: one fixed pointer pair, so a context can
+                                   // replay its evaluation as a CUDA graph (api.cu eval_device)
     double *S = nullptr, *Y = nullptr, *partial = nullptr, *res = nullptr, *rows_part = nullptr, *rows_out = nullptr, *delta = nullptr;
     unsigned int* ticket = nullptr;
     // pinned host
@@ -300,6 +303,7 @@ struct Trainer {
             return rc;
         for (int b = 0; b < 4; ++b)
             if ((rc = dalloc(&out[b], p + 5))) return rc;
+        if ((rc = dalloc(&out_eval, p + 5))) return rc;
         if ((rc = dalloc(&S, ldp * cols)) || (rc = dalloc(&Y, ldp * cols))) return rc;
         nb = 2 * cols + 1;
         const int nseg = static_cast<int>(ceil_div(p, RSEG));
@@ -310,6 +314,7 @@ struct Trainer {
         if ((rc = dalloc(&tk, 1))) return rc;
         ticket = reinterpret_cast<unsigned int*>(tk);
         GPZ_CUDA(cudaMemsetAsync(ticket, 0, sizeof(double), st));
+        GPZ_CUDA(cudaMemsetAsync(d, 0, sizeof(double) * p, st));       // the first evaluation forms x + 0 * d
         if ((rc = halloc(&h_res, 16)) || (rc = halloc(&h_rows, 3ll * nb)) || (rc = halloc(&h_delta, nb))) return rc;
         GPZ_CUDA(cudaEventCreate(&ev0));
         GPZ_CUDA(cudaEventCreate(&ev1));
@@ -320,27 +325,24 @@ struct Trainer {
         return GPZ_OK;
     }
 
-    // f, g at x + t d into buffer `buf` (t == 0 with d == nullptr: at x itself)
+    // f, g at x + t d (at_x: at x itself); the gradient lands in buffer `buf`
     int eval(double t, int buf, bool at_x, Pt* pt) {
-        const double* xe = x;
-        if (!at_x) {
-            axpy_kernel<<<blocks(), RT, 0, st>>>(xt, x, d, t, p);
-            GPZ_KERNEL_CHECK();
-            count();
-            xe = xt;
-        }
+        axpy_kernel<<<blocks(), RT, 0, st>>>(xt, x, d, at_x ? 0.0 : t, p);
+        GPZ_KERNEL_CHECK();
+        count();
         GPZ_CUDA(cudaEventRecord(ev0, st));
-        const int rc = fn(fn_user, xe, out[buf], st);
+        const int rc = fn(fn_user, xt, out_eval, st);
         if (rc) return rc;
         GPZ_CUDA(cudaEventRecord(ev1, st));
         RedArgs A{};
-        A.a = grad(buf);
-        A.b = at_x ? grad(buf) : d;
+        A.a = out_eval + 1;
+        A.b = at_x ? out_eval + 1 : d;
+        A.o1 = grad(buf);
         A.p = p;
         A.partial = partial;
         A.ticket = ticket;
         A.res = res;
-        A.out = out[buf];
+        A.out = out_eval;
         reduce_kernel<OP_EVAL><<<rblocks(), RT, 0, st>>>(A);
         GPZ_KERNEL_CHECK();
         count();

@@ -183,6 +183,9 @@ int gpz_minimize_dev(int64_t p, gpz_objective_dev fn, void* fn_user, const gpz_t
 void* gpz_stream(gpz_ctx* ctx);                 /* cudaStream_t the context enqueues on            */
 int   gpz_sync(gpz_ctx* ctx);
 int64_t gpz_launch_count(const gpz_ctx* ctx);   /* kernels launched by this context so far         */
+int64_t gpz_graph_replays(const gpz_ctx* ctx);  /* evaluations replayed as one CUDA graph (small, launch-bound problems:
+                                                   the evaluation is captured the second time it runs on the same
+                                                   (theta, out) buffers -- always the case for gpz_eval and gpz_train) */
 /* device time (ms, CUDA events on the context stream) of the phases of the LAST eval:
  * [0] phi build  [1] row weights + Gram + PHI'Wy (+allreduce #1)  [2] solve  [3] PHI w + T-GEMM + row gradients
  * [4] dPHI + back-projection + validation + finish (+allreduce #2)  [5] total

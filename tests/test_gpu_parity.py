@@ -489,3 +489,29 @@ def test_two_devices_in_one_process():
         out.append(ctx.eval(theta))
         ctx.close()
     assert out[0][0] == out[1][0] and np.array_equal(out[0][1], out[1][1])
+
+
+@pytest.mark.parametrize("method,psi,nan", [("VD", False, False), ("VC", True, True), ("GL", False, True)])
+def test_small_problem_graph_replay_is_bit_identical(method, psi, nan):
+    """Launch-bound sizes replay the whole evaluation as one CUDA graph (api.cu eval_device): same bits as plain launches,
+    for a sequence of different thetas, including a non-finite one in the middle."""
+    model, theta, X, Y, Psi, omega, tr, va = problem(method, True, psi, nan, n=400, d=3, m=20, seed=21)
+    gm = L.make_model(model.d, model.k, model.m, model.method, model.heteroscedastic)
+    thetas = [synth.perturb_theta(theta, 0.05, s) for s in range(6)]
+    thetas[3] = thetas[3].copy()
+    thetas[3][0] = np.nan
+    outs = {}
+    for graph in (0, 1, -1):
+        ctx = L.Context(gm, X, Y, Psi, omega, tr, va)
+        ctx.set_option("graph", graph)
+        outs[graph] = [ctx.eval(th) for th in thetas]
+        replays = ctx.graph_replays()
+        assert replays == (0 if graph == 0 else len(thetas) - 1), (graph, replays)
+        assert ctx.last_timing()["total"] > 0
+        ctx.close()
+    for a, b, c in zip(outs[0], outs[1], outs[-1]):
+        assert np.array_equal(a[0], b[0], equal_nan=True) and np.array_equal(a[1], b[1], equal_nan=True)
+        assert np.array_equal(a[0], c[0], equal_nan=True) and np.array_equal(a[1], c[1], equal_nan=True)
+        assert all(np.array_equal(a[2][k], b[2][k], equal_nan=True) for k in a[2])
+    ref = O.GPz(thetas[5], model, X, Y, Psi, omega, tr, va)
+    assert abs(outs[1][5][0] - ref.nlogML) <= TOL * abs(ref.nlogML)
