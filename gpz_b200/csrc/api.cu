@@ -83,6 +83,15 @@ static int nccl_load() {
         }                                                                                                \
     } while (0)
 
+// A synchronous cudaMemcpy from pageable host memory returns once the data is STAGED, not once it has landed in device
+// memory (CUDA "API synchronization behavior"), and the context streams are non-blocking: order the upload explicitly
+// before any kernel on those streams can read it.  Only used at context creation / predict set-up, never per evaluation.
+static inline cudaError_t h2d(void* dst, const void* src, size_t bytes) {
+    cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    return e;
+}
+
 // ------------------------------------------------------------------------------------------------
 // O(n) row kernels and small assembly kernels
 // ------------------------------------------------------------------------------------------------
@@ -685,11 +694,11 @@ int upload_rows(gpz_ctx* c, RowData& R, const std::vector<int64_t>& idx, int64_t
             if (v != v) v = 0.0;
         R.has_nan = 0;
     }
-    GPZ_CUDA(cudaMemcpy(R.X, buf.data(), sizeof(double) * buf.size(), cudaMemcpyHostToDevice));
+    GPZ_CUDA(h2d(R.X, buf.data(), sizeof(double) * buf.size()));
     if ((rc = dev_alloc(c->allocs, &R.Y, n * P.k))) return rc;
     if (Y) {
         gather_cols(Y, n_all, P.k, idx, buf);
-        GPZ_CUDA(cudaMemcpy(R.Y, buf.data(), sizeof(double) * buf.size(), cudaMemcpyHostToDevice));
+        GPZ_CUDA(h2d(R.Y, buf.data(), sizeof(double) * buf.size()));
     } else {
         GPZ_CUDA(cudaMemset(R.Y, 0, sizeof(double) * (n * P.k > 0 ? n * P.k : 1)));
     }
@@ -697,7 +706,7 @@ int upload_rows(gpz_ctx* c, RowData& R, const std::vector<int64_t>& idx, int64_t
     buf.assign(static_cast<size_t>(n), 1.0);
     if (omega)
         for (int64_t i = 0; i < n; ++i) buf[i] = omega[idx[i]];
-    GPZ_CUDA(cudaMemcpy(R.omega, buf.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+    GPZ_CUDA(h2d(R.omega, buf.data(), sizeof(double) * n));
     R.Psi = nullptr;
     if (Psi) {
         if (mode_is_cov(P.mode)) {
@@ -717,7 +726,7 @@ int upload_rows(gpz_ctx* c, RowData& R, const std::vector<int64_t>& idx, int64_t
             gather_cols(Psi, n_all, P.d, idx, buf);
             if ((rc = dev_alloc(c->allocs, &R.Psi, n * P.d))) return rc;
         }
-        GPZ_CUDA(cudaMemcpy(R.Psi, buf.data(), sizeof(double) * buf.size(), cudaMemcpyHostToDevice));
+        GPZ_CUDA(h2d(R.Psi, buf.data(), sizeof(double) * buf.size()));
     }
     return GPZ_OK;
 }
@@ -766,7 +775,7 @@ int ensure_workspace(gpz_ctx* c) {
         const int64_t no = need;
         if ((rc = A(&c->ones, no))) return rc;
         std::vector<double> one(static_cast<size_t>(no), 1.0);
-        GPZ_CUDA(cudaMemcpy(c->ones, one.data(), sizeof(double) * no, cudaMemcpyHostToDevice));
+        GPZ_CUDA(h2d(c->ones, one.data(), sizeof(double) * no));
         c->tr.gc_ones = c->va.gc_ones = c->ones;
     }
     if ((rc = A(&c->dotv_va, k * (nv > 0 ? nv : 1)))) return rc;
@@ -791,6 +800,8 @@ int ensure_workspace(gpz_ctx* c) {
     }
     c->nslab = (2 * c->sm_count) / T > 0 ? (2 * c->sm_count) / T : 1;
     c->dphi_slabs = 16 * c->nslab;
+    // (capping these split factors for few rows was tried: 4 splits instead of 148 at 2 400 rows makes the Gram 2.4x
+    // slower -- the serial K loop per CTA costs more than adding up 148 partial tiles, tools/small_latency.py)
     if ((rc = A(&c->dot_scratch, 2 * (MP / TILE) * c->chunk_rows))) return rc;
     // allreduce payloads
     c->red1_len = k * MP * MP + MP * 32 + (k + 2);
@@ -1356,7 +1367,7 @@ int gpz_create(gpz_ctx** out, const gpz_model* model, int64_t n_all, const doubl
     }
     if (grouped) c->P.npat = static_cast<int>(pats.size());
     if ((rc = alloc_params(c->P, c->allocs, c->has_psi))) return fail(rc);
-    if (cudaMemcpy(c->P.xshift, c->h_shift.data(), sizeof(double) * P.d, cudaMemcpyHostToDevice) != cudaSuccess) {
+    if (h2d(c->P.xshift, c->h_shift.data(), sizeof(double) * P.d) != cudaSuccess) {
         set_error("gpz_create: upload of the shift failed");
         return fail(GPZ_ERR_CUDA);
     }
@@ -1384,7 +1395,7 @@ int gpz_create(gpz_ctx** out, const gpz_model* model, int64_t n_all, const doubl
     if (grouped) {
         std::vector<unsigned char> flat;
         for (auto& ob : pats) flat.insert(flat.end(), ob.begin(), ob.end());
-        if (cudaMemcpy(c->P.obs, flat.data(), flat.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        if (h2d(c->P.obs, flat.data(), flat.size()) != cudaSuccess) {
             set_error("gpz_create: upload of the patterns failed");
             return fail(GPZ_ERR_CUDA);
         }
@@ -1733,17 +1744,17 @@ static int predict_missing_group(const gpz_model* model, const double* theta, co
     std::vector<double> hx(Xg, Xg + n * d);
     for (double& v : hx)
         if (v != v) v = 0.0;                      // missing dims are never read (ob mask); keep the buffer NaN-free
-    bool ok = cudaMemcpy(d_theta, theta, sizeof(double) * P.p, cudaMemcpyHostToDevice) == cudaSuccess;
+    bool ok = h2d(d_theta, theta, sizeof(double) * P.p) == cudaSuccess;
     ok = ok && cudaMemset(d_w, 0, sizeof(double) * k * MP) == cudaSuccess && cudaMemset(d_Sinv, 0, sizeof(double) * k * MP * MP) == cudaSuccess;
     ok = ok && cudaMemset(d_prior, 0, sizeof(double) * MP) == cudaSuccess;
     ok = ok && cudaMemcpy2D(d_w, sizeof(double) * MP, w, sizeof(double) * P.m, sizeof(double) * P.m, k, cudaMemcpyHostToDevice) == cudaSuccess;
     for (int o = 0; o < k && ok; ++o)
         ok = cudaMemcpy2D(d_Sinv + static_cast<int64_t>(o) * MP * MP, sizeof(double) * MP, iSigma_w + static_cast<int64_t>(o) * P.m * P.m,
                           sizeof(double) * P.m, sizeof(double) * P.m, P.m, cudaMemcpyHostToDevice) == cudaSuccess;
-    ok = ok && cudaMemcpy(d_prior, priors, sizeof(double) * P.m, cudaMemcpyHostToDevice) == cudaSuccess;
-    ok = ok && cudaMemcpy(d_X, hx.data(), sizeof(double) * n * d, cudaMemcpyHostToDevice) == cudaSuccess;
-    ok = ok && cudaMemcpy(d_ob, ob.data(), d, cudaMemcpyHostToDevice) == cudaSuccess;
-    if (Psig) ok = ok && cudaMemcpy(d_Psi, Psig, sizeof(double) * n * psi_w, cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && h2d(d_prior, priors, sizeof(double) * P.m) == cudaSuccess;
+    ok = ok && h2d(d_X, hx.data(), sizeof(double) * n * d) == cudaSuccess;
+    ok = ok && h2d(d_ob, ob.data(), d) == cudaSuccess;
+    if (Psig) ok = ok && h2d(d_Psi, Psig, sizeof(double) * n * psi_w) == cudaSuccess;
     if (!ok) {
         set_error("predict_missing_group: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         return cleanup(GPZ_ERR_CUDA);
@@ -1921,8 +1932,8 @@ int gpz_predict(const gpz_model* model, const double* theta, const double* w, co
             sh[a] = cnt > 0 ? sum / static_cast<double>(cnt) : 0.0;
             for (int64_t i = 0; i < n; ++i) hx[static_cast<size_t>(a) * n + i] = col[i] - sh[a];
         }
-        PR(cuda_ok(cudaMemcpy(d_X, hx.data(), sizeof(double) * n * P.d, cudaMemcpyHostToDevice), "H2D X"));
-        PR(cuda_ok(cudaMemcpy(P.xshift, sh.data(), sizeof(double) * P.d, cudaMemcpyHostToDevice), "H2D shift"));
+        PR(cuda_ok(h2d(d_X, hx.data(), sizeof(double) * n * P.d), "H2D X"));
+        PR(cuda_ok(h2d(P.xshift, sh.data(), sizeof(double) * P.d), "H2D shift"));
     }
     if (Psi) PR(cuda_ok(cudaMemcpyAsync(d_Psi, Psi, sizeof(double) * n * P.d * (cov_psi ? P.d : 1), cudaMemcpyHostToDevice, st), "H2D Psi"));
     PR(prep_params(d_theta, P, cov_psi ? 1 : 0, st, &launches));
@@ -2028,8 +2039,8 @@ int gpz_dxy(int64_t n, int32_t m, int32_t d, const double* X, const double* Y, d
     GPZ_CUDA(cudaMalloc(&dX, sizeof(double) * n * d));
     GPZ_CUDA(cudaMalloc(&dY, sizeof(double) * m * d));
     GPZ_CUDA(cudaMalloc(&dD, sizeof(double) * n * m));
-    GPZ_CUDA(cudaMemcpy(dX, X, sizeof(double) * n * d, cudaMemcpyHostToDevice));
-    GPZ_CUDA(cudaMemcpy(dY, Y, sizeof(double) * m * d, cudaMemcpyHostToDevice));
+    GPZ_CUDA(h2d(dX, X, sizeof(double) * n * d));
+    GPZ_CUDA(h2d(dY, Y, sizeof(double) * m * d));
     rc = dxy_device(dX, n, dY, m, d, dD, nullptr);
     if (!rc) GPZ_CUDA(cudaMemcpy(D, dD, sizeof(double) * n * m, cudaMemcpyDeviceToHost));
     cudaFree(dX);
@@ -2050,8 +2061,8 @@ int gpz_dxy_colmean(int64_t n, int32_t m, int32_t d, const double* X, const doub
     GPZ_CUDA(cudaMalloc(&dY, sizeof(double) * m * d));
     GPZ_CUDA(cudaMalloc(&dP, sizeof(double) * m * dxy_colmean_chunks(n)));
     GPZ_CUDA(cudaMalloc(&dM, sizeof(double) * m));
-    GPZ_CUDA(cudaMemcpy(dX, X, sizeof(double) * n * d, cudaMemcpyHostToDevice));
-    GPZ_CUDA(cudaMemcpy(dY, Y, sizeof(double) * m * d, cudaMemcpyHostToDevice));
+    GPZ_CUDA(h2d(dX, X, sizeof(double) * n * d));
+    GPZ_CUDA(h2d(dY, Y, sizeof(double) * m * d));
     rc = dxy_colmean_device(dX, n, dY, m, d, dP, dM, nullptr);
     if (!rc) GPZ_CUDA(cudaMemcpy(mean, dM, sizeof(double) * m, cudaMemcpyDeviceToHost));
     cudaFree(dX);
@@ -2109,8 +2120,8 @@ int gpz_dgemm_nt(int64_t M, int64_t N, int64_t K, const double* A, int64_t lda, 
     if (e == cudaSuccess) e = D(reinterpret_cast<void**>(&A8), static_cast<size_t>(Mp) * digits * Kp);
     if (e == cudaSuccess) e = D(reinterpret_cast<void**>(&B8), static_cast<size_t>(Np) * digits * Kp);
     if (e == cudaSuccess) e = D(reinterpret_cast<void**>(&flag), sizeof(int));
-    if (e == cudaSuccess) e = cudaMemcpy(dA, A, sizeof(double) * M * lda, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(dB, B, sizeof(double) * N * ldb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = h2d(dA, A, sizeof(double) * M * lda);
+    if (e == cudaSuccess) e = h2d(dB, B, sizeof(double) * N * ldb);
     if (e == cudaSuccess) e = cudaMemset(flag, 0, sizeof(int));
     if (e != cudaSuccess) {
         set_error("gpz_dgemm_nt: CUDA error %s", cudaGetErrorString(e));

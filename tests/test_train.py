@@ -179,6 +179,7 @@ class DevObjective:
         self.ho[1:1 + self.p] = r[1]
         self.ho[1 + self.p:] = r[2] if len(r) > 2 else np.nan
         assert self.rt.cudaMemcpy(do, self.ho.ctypes.data, 8 * (self.p + 5), 1) == 0
+        assert self.rt.cudaDeviceSynchronize() == 0      # pageable H2D returns when staged; the optimiser's stream is non-blocking
         self.calls += 1
         return 0
 
