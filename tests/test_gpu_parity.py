@@ -515,3 +515,22 @@ def test_small_problem_graph_replay_is_bit_identical(method, psi, nan):
         assert all(np.array_equal(a[2][k], b[2][k], equal_nan=True) for k in a[2])
     ref = O.GPz(thetas[5], model, X, Y, Psi, omega, tr, va)
     assert abs(outs[1][5][0] - ref.nlogML) <= TOL * abs(ref.nlogML)
+
+
+@pytest.mark.parametrize("n,d,m", [(2, 1, 1), (3, 2, 1), (7, 2, 3), (33, 1, 5), (40, 2, 129), (129, 3, 128), (1025, 2, 7)])
+@pytest.mark.parametrize("method", ["VL", "VD", "GC", "VC"])
+def test_eval_edge_shapes(n, d, m, method):
+    """Tiny and ragged extents: fewer rows than a warp / a tile / bases (m > n: SIGMA carried by the prior), one basis, one
+    input dimension, m on both sides of the 128-wide tile, n one past the 1024-row digit chunk; no validation set."""
+    rng = np.random.default_rng(100 + n + m)
+    X = rng.standard_normal((n, d))
+    Y = (np.sin(X[:, :1]) + 0.1 * rng.standard_normal((n, 1)))
+    Y = Y - Y.mean()
+    theta = synth.perturb_theta(synth.make_theta0(X, Y + 1e-3 * np.arange(n)[:, None], method, m, het=True, seed=1), 0.05, 2)
+    model = O.Model(d=d, k=1, m=m, method=method, heteroscedastic=True)
+    for digits in ((None, 7) if m > 1 else (None,)):
+        ref, f, g, st, ctx = run_both(model, theta, X, Y, None, None, None, None, digits=digits)
+        # m >= n: SIGMA = alpha + a rank-n Gram, conditioning set by the prior; the SVD pseudo-inverse of the oracle and the
+        # Cholesky inverse differ by cond * eps there
+        assert_eval_matches(model, ref, f, g, st, tol=1e-9 if m < n else 1e-7)
+        ctx.close()
