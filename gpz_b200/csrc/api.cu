@@ -15,6 +15,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <numeric>
 #include <string>
@@ -284,6 +285,32 @@ __global__ void colsum_reduce_kernel(const double* __restrict__ colp, int nslab,
     out[e] = s;
 }
 
+// one block per column: mean of the non-NaN entries (fixed summation order), then x -= mean in place; shift[a] = mean
+__global__ void __launch_bounds__(1024) colmean_shift_kernel(double* __restrict__ X, int64_t n, double* __restrict__ shift) {
+    __shared__ double sh[32];
+    __shared__ double mean;
+    double* col = X + static_cast<int64_t>(blockIdx.x) * n;
+    double s = 0.0, c = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) {
+        const double v = col[i];
+        if (v == v) s += v, c += 1.0;
+    }
+    const double S = gpz::block_sum<1024>(s, sh);
+    const double Cn = gpz::block_sum<1024>(c, sh);
+    if (threadIdx.x == 0) {
+        mean = Cn > 0.0 ? S / Cn : 0.0;
+        shift[blockIdx.x] = mean;
+    }
+    __syncthreads();
+    const double mu = mean;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) col[i] -= mu;
+}
+
+__global__ void nan_if_flag_kernel(double* __restrict__ v, int64_t n, const int* __restrict__ flag) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n && *flag != 0) v[i] = nan("");
+}
+
 __global__ void add_diag_kernel(double* __restrict__ S, int MP, int m, const double* __restrict__ alpha) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < MP) S[static_cast<int64_t>(j) * MP + j] += (j < m) ? alpha[j] : 1.0;
@@ -529,6 +556,8 @@ struct gpz_ctx {
     double* seen_out = nullptr;
     int64_t g_launches = 0;
     int64_t graph_replays = 0;
+    bool last_was_replay = false;
+    cudaEvent_t gev[2] = {nullptr, nullptr};       // around the last graph launch
 };
 
 namespace {
@@ -912,6 +941,7 @@ int ensure_workspace(gpz_ctx* c) {
     c->tr.flag = c->va.flag = c->sws.flag;          // non-finite coefficients seen by the int8 PHI build raise the same failure flag
     for (auto& e : c->ev) GPZ_CUDA(cudaEventCreate(&e));
     for (auto& e : c->kev) GPZ_CUDA(cudaEventCreate(&e));
+    for (auto& e : c->gev) GPZ_CUDA(cudaEventCreate(&e));
     GPZ_CUDA(cudaMallocHost(&c->h_out, sizeof(double) * (P.p + 5)));
     GPZ_CUDA(cudaMallocHost(&c->h_theta, sizeof(double) * P.p));
     c->ws_ready = true;
@@ -1223,11 +1253,15 @@ int eval_device(gpz_ctx* c, const double* d_theta, double* d_out) {
     if ((rc = ensure_workspace(c))) return rc;
     if (!graph_wanted(c)) return eval_device_enqueue(c, d_theta, d_out);
     if (c->g_exec && c->g_theta == d_theta && c->g_out == d_out) {
+        GPZ_CUDA(cudaEventRecord(c->gev[0], c->st));
         GPZ_CUDA(cudaGraphLaunch(c->g_exec, c->st));
+        GPZ_CUDA(cudaEventRecord(c->gev[1], c->st));
         c->launches += c->g_launches;
         ++c->graph_replays;
+        c->last_was_replay = true;
         return GPZ_OK;
     }
+    c->last_was_replay = false;
     if (c->seen_theta != d_theta || c->seen_out != d_out) {        // first sight of this pointer pair: plain run
         c->seen_theta = d_theta;
         c->seen_out = d_out;
@@ -1261,9 +1295,12 @@ int eval_device(gpz_ctx* c, const double* d_theta, double* d_out) {
     }
     c->g_theta = d_theta;
     c->g_out = d_out;
+    GPZ_CUDA(cudaEventRecord(c->gev[0], c->st));
     GPZ_CUDA(cudaGraphLaunch(c->g_exec, c->st));
+    GPZ_CUDA(cudaEventRecord(c->gev[1], c->st));
     c->launches += c->g_launches;
     ++c->graph_replays;
+    c->last_was_replay = true;
     return GPZ_OK;
 }
 
@@ -1416,6 +1453,8 @@ void gpz_destroy(gpz_ctx* c) {
     for (auto& e : c->ev)
         if (e) cudaEventDestroy(e);
     for (auto& e : c->kev)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : c->gev)
         if (e) cudaEventDestroy(e);
     if (c->g_exec) cudaGraphExecDestroy(c->g_exec);
     if (c->h_out) cudaFreeHost(c->h_out);
@@ -1887,6 +1926,16 @@ int gpz_predict(const gpz_model* model, const double* theta, const double* w, co
     }
     const int64_t MP = P.MP;
     const int k = P.k;
+    const bool dbg = getenv("GPZ_B200_DEBUG") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tdbg = now();
+    auto lap = [&](const char* what, bool sync = true) {
+        if (!dbg) return;
+        if (sync) cudaStreamSynchronize(st);
+        const double t1 = now();
+        fprintf(stderr, "gpz_predict: %-18s %8.2f ms\n", what, t1 - tdbg);
+        tdbg = t1;
+    };
     PR(alloc_params(P, allocs, cov_psi ? 1 : 0));
     double *d_theta, *d_w, *d_Sinv, *d_X, *d_Psi = nullptr, *d_Phi, *d_dotv, *d_mu, *d_nupart, *d_nu, *d_elns, *d_beta, *d_gamma, *d_col = nullptr;
     PR(dev_alloc(allocs, &d_theta, P.p));
@@ -1894,8 +1943,21 @@ int gpz_predict(const gpz_model* model, const double* theta, const double* w, co
     PR(dev_alloc(allocs, &d_Sinv, k * MP * MP));
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    int64_t chunk = static_cast<int64_t>(0.4 * static_cast<double>(free_b) / (8.0 * (MP + (PHI ? P.m : 0))));
+    // nu = rowsum((PHI iSigma) .* PHI) (predictDiag.m:66 / predictCov.m:61) is the same n m^2 product as T in the objective:
+    // same engine choice (int8 digit GEMM unless one basis tile on few rows, see ensure_workspace)
+    const int oz_s = (!Psi && ozmma_available() && !(MP <= 128 && n < 250000)) ? 7 : 0;
+    int64_t chunk = static_cast<int64_t>(0.4 * static_cast<double>(free_b) / (8.0 * (MP + (PHI ? P.m : 0)) + static_cast<double>(oz_s) * MP));
     chunk = chunk / 1024 * 1024;
+    // predict is a stateless call: its buffers are allocated and freed every time, and multi-GB cudaMalloc / cudaFree cost
+    // far more than the kernels (1e6 rows x 1000 bases: 45 ms of kernels).  Row chunks of at most ~2 GB of PHI keep every
+    // launch large enough to fill the machine and the allocations small.
+    {
+        const char* env = getenv("GPZ_B200_PREDICT_CHUNK");
+        int64_t cap = env ? atoll(env) : (int64_t{1} << 31) / (8 * MP);
+        cap = cap / 1024 * 1024;
+        if (cap < 1024) cap = 1024;
+        if (chunk > cap) chunk = cap;
+    }
     if (chunk < 1024) chunk = 1024;
     if (chunk > n) chunk = n;
     PR(dev_alloc(allocs, &d_X, n * P.d));
@@ -1909,6 +1971,13 @@ int gpz_predict(const gpz_model* model, const double* theta, const double* w, co
     PR(dev_alloc(allocs, &d_elns, k * n));
     PR(dev_alloc(allocs, &d_beta, k * n));
     PR(dev_alloc(allocs, &d_gamma, k * n));
+    double *oz_D8 = nullptr, *oz_ea = nullptr, *oz_ws = nullptr, *oz_flag = nullptr;
+    if (oz_s > 0) {
+        PR(dev_alloc(allocs, &oz_D8, oz_digit_bytes(static_cast<int>(MP), oz_s, chunk) / 8 + 1));
+        PR(dev_alloc(allocs, &oz_ea, oz_padded_rows(chunk)));
+        PR(dev_alloc(allocs, &oz_ws, oz_workspace_bytes(static_cast<int>(MP), oz_s) / 8 + 1));
+        PR(dev_alloc(allocs, &oz_flag, 1));
+    }
     auto cuda_ok = [&](cudaError_t e, const char* what) -> int {
         if (e == cudaSuccess) return GPZ_OK;
         set_error("gpz_predict: %s: %s", what, cudaGetErrorString(e));
@@ -1921,21 +1990,14 @@ int gpz_predict(const gpz_model* model, const double* theta, const double* w, co
     for (int o = 0; o < k; ++o)
         PR(cuda_ok(cudaMemcpy2DAsync(d_Sinv + static_cast<int64_t>(o) * MP * MP, sizeof(double) * MP, iSigma_w + static_cast<int64_t>(o) * P.m * P.m,
                                      sizeof(double) * P.m, sizeof(double) * P.m, P.m, cudaMemcpyHostToDevice, st), "H2D iSigma_w"));
-    {   // store X relative to its column means (only x - p matters); prep_params shifts P by the same constant
-        std::vector<double> hx(static_cast<size_t>(n) * P.d), sh(static_cast<size_t>(P.d), 0.0);
-        for (int a = 0; a < P.d; ++a) {
-            const double* col = Xz + static_cast<int64_t>(a) * n;
-            double sum = 0.0;
-            int64_t cnt = 0;
-            for (int64_t i = 0; i < n; ++i)
-                if (col[i] == col[i]) { sum += col[i]; ++cnt; }
-            sh[a] = cnt > 0 ? sum / static_cast<double>(cnt) : 0.0;
-            for (int64_t i = 0; i < n; ++i) hx[static_cast<size_t>(a) * n + i] = col[i] - sh[a];
-        }
-        PR(cuda_ok(h2d(d_X, hx.data(), sizeof(double) * n * P.d), "H2D X"));
-        PR(cuda_ok(h2d(P.xshift, sh.data(), sizeof(double) * P.d), "H2D shift"));
-    }
+    // store X relative to its column means (only x - p matters; prep_params shifts P by the same constant): raw upload,
+    // NaN-aware column means and the subtraction on the device (the host pass over n x d cost more than all the kernels)
+    PR(cuda_ok(h2d(d_X, Xz, sizeof(double) * n * P.d), "H2D X"));
+    colmean_shift_kernel<<<P.d, 1024, 0, st>>>(d_X, n, P.xshift);
+    PR(cuda_ok(cudaGetLastError(), "colmean_shift_kernel"));
+    ++launches;
     if (Psi) PR(cuda_ok(cudaMemcpyAsync(d_Psi, Psi, sizeof(double) * n * P.d * (cov_psi ? P.d : 1), cudaMemcpyHostToDevice, st), "H2D Psi"));
+    lap("alloc + upload");
     PR(prep_params(d_theta, P, cov_psi ? 1 : 0, st, &launches));
     RowData R;
     R.n = n;
@@ -1956,9 +2018,19 @@ int gpz_predict(const gpz_model* model, const double* theta, const double* w, co
             for (int o = 0; o < k; ++o)
                 PR(rowdot(d_Phi, MP, P.m, r1 - r0, DotSpec{2, {P.v + o * MP, d_w + o * MP}, {d_dotv + o * n + r0, d_mu + o * n + r0}}, st, &launches));
         if (!Psi) {
+            if (oz_s > 0) {
+                if (r0 == 0) PR(cuda_ok(cudaMemsetAsync(oz_flag, 0, sizeof(double), st), "memset"));
+                PR(ozaki_digits(d_Phi, MP, static_cast<int>(MP), P.m, r1 - r0, oz_s, nullptr, nullptr, 0, reinterpret_cast<int8_t*>(oz_D8),
+                                nullptr, oz_ea, reinterpret_cast<int*>(oz_flag), st, &launches));
+            }
             for (int o = 0; o < k; ++o) {
-                PR(tgemm(d_Phi, MP, d_Sinv + static_cast<int64_t>(o) * MP * MP, static_cast<int>(MP), P.m, r1 - r0, nullptr, nullptr, 0,
-                         d_nupart + r0, n, nullptr, st, &launches));
+                if (oz_s > 0)
+                    PR(ozaki_tgemm(d_Phi, MP, reinterpret_cast<const int8_t*>(oz_D8), oz_ea, d_Sinv + static_cast<int64_t>(o) * MP * MP,
+                                   static_cast<int>(MP), P.m, r1 - r0, oz_s, nullptr, nullptr, 0, d_nupart + r0, n, nullptr, nullptr, oz_ws, st,
+                                   nullptr, nullptr, &launches));
+                else
+                    PR(tgemm(d_Phi, MP, d_Sinv + static_cast<int64_t>(o) * MP * MP, static_cast<int>(MP), P.m, r1 - r0, nullptr, nullptr, 0,
+                             d_nupart + r0, n, nullptr, st, &launches));
                 sum_cols_kernel<<<static_cast<unsigned>(ceil_div(r1 - r0, 256)), 256, 0, st>>>(d_nupart + r0, static_cast<int>(MP / TILE), n, r1 - r0, d_nu + o * n + r0);
             }
         }
@@ -1969,6 +2041,11 @@ int gpz_predict(const gpz_model* model, const double* theta, const double* w, co
             PR(cuda_ok(cudaStreamSynchronize(st), "sync"));
         }
     }
+    if (oz_s > 0) {                  // non-finite PHI has no digits: the affected answer is NaN, as the fp64 path would give
+        nan_if_flag_kernel<<<static_cast<unsigned>(ceil_div(k * n, 256)), 256, 0, st>>>(d_nu, k * n, reinterpret_cast<const int*>(oz_flag));
+        ++launches;
+    }
+    lap("row chunks");
     exp_rows_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, st>>>(d_dotv, P.bk, P.het, k, n, d_elns, d_beta);
     PR(cuda_ok(cudaMemsetAsync(d_gamma, 0, sizeof(double) * k * n, st), "memset"));
     if (cov_psi) PR(predict_noisy_cov(P, R, d_w, d_Sinv, d_elns, d_mu, d_nu, d_beta, d_gamma, st, &launches));
@@ -1980,7 +2057,9 @@ int gpz_predict(const gpz_model* model, const double* theta, const double* w, co
     PR(cuda_ok(cudaStreamSynchronize(st), "sync"));
     PR(cuda_ok(cudaGetLastError(), "kernel"));
 #undef PR
+    lap("tail + download");
     cleanup();
+    lap("free", false);
     return GPZ_OK;
 }
 
@@ -2183,6 +2262,10 @@ int gpz_last_timing(gpz_ctx* c, double ms[12]) {
     }
     GPZ_CUDA(cudaEventElapsedTime(&t, c->ev[0], c->ev[5]));
     ms[5] = t;
+    if (c->last_was_replay) {                                     // phases: last plain run; total: this replay
+        GPZ_CUDA(cudaEventElapsedTime(&t, c->gev[0], c->gev[1]));
+        ms[5] = t;
+    }
     GPZ_CUDA(cudaEventElapsedTime(&t, c->kev[0], c->kev[1]));
     ms[6] = t;
     GPZ_CUDA(cudaEventElapsedTime(&t, c->kev[2], c->kev[3]));

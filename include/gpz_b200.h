@@ -191,7 +191,9 @@ int64_t gpz_graph_replays(const gpz_ctx* ctx);  /* evaluations replayed as one C
  * [4] dPHI + back-projection + validation + finish (+allreduce #2)  [5] total
  * [6] the Gram step alone  [7] the T-GEMM step alone (fp64 DMMA kernel, or column digits + the tcgen05 digit GEMM)
  * [8] the tcgen05 digit-GEMM launch of T = PHI iSigma (ms)  [9] int8 operations that launch executed
- * [10] base-256 digits in use (0 = fp64 DMMA path)  [11] 1 if the Gram also runs on the int8 tensor cores   */
+ * [10] base-256 digits in use (0 = fp64 DMMA path)  [11] 1 if the Gram also runs on the int8 tensor cores
+ * When the last evaluation was a CUDA-graph replay, [5] is the time of that replay and the phases are those of the
+ * last evaluation that ran as plain launches.                                                                  */
 int gpz_last_timing(gpz_ctx* ctx, double ms[12]);
 int gpz_set_option(gpz_ctx* ctx, const char* name, double value);
 

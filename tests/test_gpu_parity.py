@@ -534,3 +534,27 @@ def test_eval_edge_shapes(n, d, m, method):
         # Cholesky inverse differ by cond * eps there
         assert_eval_matches(model, ref, f, g, st, tol=1e-9 if m < n else 1e-7)
         ctx.close()
+
+
+@pytest.mark.parametrize("method", ["VD", "VC"])
+def test_predict_full_through_the_int8_engine(method):
+    """m > 128: nu = rowsum((PHI iSigma) .* PHI) of predictFull runs through the tcgen05 digit GEMM, as T does in the
+    objective (ragged: 700 rows, 150 of 256 padded bases); a non-finite theta gives NaN, not garbage digits."""
+    n, d, m = 1500, 3, 150
+    model, theta, X, Y, _, omega, tr, _ = problem(method, True, False, False, n=n, d=d, m=m, seed=13)
+    r = O.GPz(theta, model, X, Y, None, omega, tr, None, fit_only=True)
+    model.muX, model.sdX, model.muY = np.zeros(d), np.ones(d), np.zeros(1)
+    o2 = m * d + model.g_dim + m + 1
+    model.best = dict(theta=theta, w=r.w, iSigma_w=r.iSigma_w, P=theta[:m * d].reshape((m, d), order="F"),
+                      v=theta[o2:o2 + m].reshape(m, 1))
+    Xt = X[:700]
+    mu, sigma, nu, be, ga, PHI = O.predict(Xt, model)
+    gm = L.make_model(d, 1, m, method, True)
+    mu2, nu2, be2, ga2, PHI2 = L.predict_core(gm, theta, r.w, r.iSigma_w, Xt, None, want_phi=True)
+    # m = 150 bases in 3-d: iSigma_w has entries of mixed sign up to ~1e7 while nu ~ 1e-2: nu is a cancelling sum and the
+    # fp64 oracle itself only carries it to cond * eps
+    assert rel(mu2, mu) <= 1e-8 and rel(nu2, nu) <= 1e-6 and rel(be2, be) <= TOL and rel(PHI2, PHI) <= 1e-12
+    bad = theta.copy()
+    bad[0] = np.nan
+    _, nu3, _, _, _ = L.predict_core(gm, bad, r.w, r.iSigma_w, Xt, None)
+    assert np.isnan(nu3).all()
