@@ -558,3 +558,54 @@ def test_predict_full_through_the_int8_engine(method):
     bad[0] = np.nan
     _, nu3, _, _, _ = L.predict_core(gm, bad, r.w, r.iSigma_w, Xt, None)
     assert np.isnan(nu3).all()
+
+
+def test_demo_sinc_script_size_against_oracle():
+    """Config 1' (SURVEY 8): demo_sinc.m as the script really runs it -- ~5 250 training rows of 7 500, d = 1 (so VL),
+    m = 100, heteroscedastic, input noise Psi n x 1 -- at FULL size against the oracle."""
+    rng = np.random.default_rng(11)
+    n, m = 7500, 100
+    X = rng.uniform(-10, 10, (n, 1))
+    Y = (np.sinc(X[:, 0] / np.pi) + (0.05 + 0.2 * (1 + np.sin(X[:, 0] / 3)) / 2) * rng.standard_normal(n)).reshape(n, 1)
+    Xz, Yc = (X - X.mean()) / X.std(), Y - Y.mean()
+    Psi = rng.gamma(1.0, 0.25, (n, 1)) ** 2 / X.var()
+    tr = rng.random(n) < 0.7
+    va = ~tr & (rng.random(n) < 0.5)
+    theta = synth.perturb_theta(synth.make_theta0(Xz, Yc, "VL", m, het=True, seed=3), 0.05, 4)
+    model = O.Model(d=1, k=1, m=m, method="VL", heteroscedastic=True)
+    ref, f, g, st, ctx = run_both(model, theta, Xz, Yc, Psi, None, tr, va)
+    assert_eval_matches(model, ref, f, g, st, tol=1e-8)       # 100 bases on a line: cond(SIGMA) ~ 1e9
+    ctx.close()
+
+
+def test_demo_photoz_full_size_properties():
+    """Config 2 at FULL size (60 000 training + 60 000 validation rows, d = 5, m = 100, VC, Psi 5 x 5 x n), where the oracle needs
+    a quarter of an hour: (1) bit-reproducibility; (2) analytic gradient against a central difference of the objective;
+    (3) with Psi -> 0 the per-(sample, basis) Cholesky kernels of getPHI.m:80-88 / GPz.m:166-184 must agree with the
+    tensor-core no-Psi path (identity T4 of the oracle pins, here between two unrelated kernel families)."""
+    n, d, m = 120_000, 5, 100
+    X, Y = synth.make_data(n, d, seed=0)
+    theta = synth.perturb_theta(synth.make_theta0(X, Y, "VC", m, het=True, seed=1), 0.05, 2)
+    Psi = synth.make_psi(n, d, "VC", seed=3)
+    tr = np.arange(n) % 2 == 0
+    gm = L.make_model(d, 1, m, "VC", True)
+    ctx = L.Context(gm, X, Y, Psi, None, tr, ~tr)
+    f1, g1, st1 = ctx.eval(theta)
+    f2, g2, _ = ctx.eval(theta)
+    assert np.isfinite(f1) and np.isfinite(g1).all() and f1 == f2 and np.array_equal(g1, g2)
+    assert np.isfinite(st1["validLL"]) and st1["validRMSE"] > 0
+    u = np.random.default_rng(0).standard_normal(theta.size)
+    u /= np.linalg.norm(u)
+    h = 1e-5
+    fp, _, _ = ctx.eval(theta + h * u)
+    fm, _, _ = ctx.eval(theta - h * u)
+    assert abs((fp - fm) / (2 * h) - g1 @ u) <= 1e-6 * max(1.0, np.linalg.norm(g1))
+    ctx.close()
+    ctx = L.Context(gm, X, Y, Psi * 1e-30, None, tr, ~tr)
+    fa, ga, sta = ctx.eval(theta)
+    ctx.close()
+    ctx = L.Context(gm, X, Y, None, None, tr, ~tr)
+    fb, gb, stb = ctx.eval(theta)
+    ctx.close()
+    assert abs(fa - fb) <= 1e-10 * abs(fb) and rel(ga, gb) <= 1e-8
+    assert abs(sta["validLL"] - stb["validLL"]) <= 1e-10 * abs(stb["validLL"])
