@@ -280,6 +280,44 @@ def run_gpu(args):
             train = {"error": str(e)[:200]}
         barrier()
 
+    # ---- second run with a 10 % validation mask: the evaluation also builds PHI on the validation rows and
+    # returns validRMSE / validLL (GPz.m:239-259); reported beside the metric, not part of it
+    valid_run = None
+    m_bases = ctx.model.m
+    if args.valid_frac > 0:
+        try:
+            ctx.close()
+            ctx = None
+            va_mask = (np.arange(lo, hi) % max(2, int(round(1.0 / args.valid_frac)))) == 0
+            ctx2 = L.Context(L.make_model(d, 1, m, method, True), X[lo:hi], Y[lo:hi], None, None, ~va_mask, va_mask, device=local)
+            if world > 1:
+                uid = [L.comm_unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(uid, src=0)
+                ctx2.comm_init(rank, world, uid[0])
+            st2 = torch.cuda.ExternalStream(ctx2.stream(), device=dev)
+            for i in range(2):
+                ctx2.eval_dev(d_th[i].data_ptr(), d_out.data_ptr())
+            ctx2.sync()
+            barrier()
+            kv = min(K, 5)
+            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            v0.record(st2)
+            for i in range(kv):
+                ctx2.eval_dev(d_th[W + i].data_ptr(), d_out.data_ptr())
+            v1.record(st2)
+            ctx2.sync()
+            barrier()
+            tv = torch.tensor([v0.elapsed_time(v1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+            stats_v = d_out[-4:].tolist()
+            valid_run = {"valid_fraction": float(va_mask.mean()), "steps": kv, "ms_per_step": float(tv.item()) / kv,
+                         "value": 1e3 * kv / float(tv.item()), "unit": "evals/s", "validRMSE": stats_v[2], "validLL": stats_v[3]}
+            ctx2.close()
+        except Exception as e:
+            valid_run = {"error": str(e)[:200]}
+        barrier()
+
     # ---- roofline of the dominant kernel -------------------------------------------------------------
     peak = fp64_peak_tflops(torch, dev) if rank == 0 else None
     line = None
@@ -349,7 +387,7 @@ def run_gpu(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_desc(name, n, d, m, method), "rows_per_gpu": hi - lo,
                        "parallelism": f"rows sharded over {world} GPU(s), 2 NCCL allreduces per eval" if world > 1 else "1 GPU",
-                       "cache": "inputs larger than L2: PHI/H working set %.1f GB per GPU" % (16.0 * (hi - lo) * ctx.model.m / 1e9),
+                       "cache": "inputs larger than L2: PHI/H working set %.1f GB per GPU" % (16.0 * (hi - lo) * m_bases / 1e9),
                        "dataset_upload_s": round(upload_s, 3), "theta_len": int(p)},
             "e2e": {"value": 1.0 / e2e_step, "unit": "evals/s", "h2d_bytes_per_step": 8 * int(p), "d2h_bytes_per_step": 8 * (int(p) + 5),
                     "ms_per_step": e2e_step * 1e3},
@@ -358,10 +396,12 @@ def run_gpu(args):
             "roofline": roof,
             "cpu_baseline": cpu,
             "train": train,
+            "with_validation": valid_run,
             "check": {"nlogML_last": f_last, "trainRMSE": float(st["trainRMSE"])},
         }
         print(json.dumps(line), flush=True)
-    ctx.close()
+    if ctx is not None:
+        ctx.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -376,6 +416,7 @@ def main():
     ap.add_argument("--workload", default="target", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=0, help="rows of the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--valid-frac", type=float, default=0.1, help="validation share of the extra 'with_validation' run (0 = skip)")
     ap.add_argument("--train-iters", type=int, default=5, help="iterations of the device-resident training loop reported in 'train' (0 = skip)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
