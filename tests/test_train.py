@@ -346,3 +346,55 @@ def test_gpz_train_training_only_keeps_last_iterate_as_best():
         assert f < f0
     finally:
         ctx.close()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# golden trajectory (tests/golden/train_VD.npz, made by tests/golden/make_golden_train.py from the two oracles)
+
+
+def _golden_train():
+    import os
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "train_VD.npz"))
+    n, d, m, k, het, max_iter, max_attempts = (int(v) for v in z["meta"])
+    return z, d, m, str(z["method"]), max_iter, max_attempts
+
+
+def test_oracle_reproduces_golden_training_run():
+    from oracle import gpz_oracle as O
+
+    z, d, m, method, max_iter, max_attempts = _golden_train()
+    model = O.Model(d=d, k=1, m=m, method=method, heteroscedastic=True)
+
+    def fun_stats(th):
+        r = O.GPz(th, model, z["X"], z["Y"], None, None, z["training"], z["validation"])
+        return r.nlogML, r.grad, tuple(r.stats[s] for s in ("trainRMSE", "trainLL", "validRMSE", "validLL"))
+
+    log = []
+    x, best, bv, flag, info = MO.train_loop(fun_stats, z["theta0"], z["theta0"], -np.inf, max_iter=max_iter,
+                                            max_attempts=max_attempts, training_only=False, log=log)
+    assert flag == int(z["exitflag"]) and info["iterations"] == int(z["iterations"]) and info["funcCount"] == int(z["fun_evals"])
+    assert np.allclose([e["f"] for e in log], z["f"], rtol=1e-9, atol=0) and np.allclose(x, z["theta_last"], rtol=1e-7, atol=1e-9)
+    assert [e["improved"] for e in log] == list(z["improved"]) and abs(bv - float(z["best_valid"])) <= 1e-9
+
+
+@pytest.mark.gpu
+def test_cuda_training_run_reproduces_golden():
+    from gpz_b200 import _lib
+
+    z, d, m, method, max_iter, max_attempts = _golden_train()
+    ctx = _lib.Context(_lib.make_model(d, 1, m, method, True), z["X"], z["Y"], training=z["training"], validation=z["validation"])
+    try:
+        its = []
+        x, best, bv, info = ctx.train(z["theta0"], z["theta0"], -np.inf, callback=lambda it: its.append(it) and False,
+                                      max_iter=max_iter, max_attempts=float(max_attempts), training_only=0)
+        assert info["exitflag"] == int(z["exitflag"]) and info["iterations"] == int(z["iterations"])
+        assert info["fun_evals"] == int(z["fun_evals"])
+        assert np.allclose([i["f"] for i in its], z["f"], rtol=1e-7, atol=1e-9)
+        assert np.allclose([i["validLL"] for i in its], z["validLL"], rtol=1e-6, atol=1e-9)
+        assert [i["improved"] for i in its] == list(z["improved"]) and [i["fun_evals"] for i in its] == list(z["evals"])
+        assert np.allclose(x, z["theta_last"], rtol=1e-5, atol=1e-7) and np.allclose(best, z["theta_best"], rtol=1e-5, atol=1e-7)
+        assert abs(bv - float(z["best_valid"])) <= 1e-7
+        assert ctx.graph_replays() >= info["fun_evals"] - 2          # launch-bound size: the evaluations were graph replays
+    finally:
+        ctx.close()
