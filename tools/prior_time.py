@@ -4,7 +4,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from gpz_b200 import _lib as L, synth
 
-n, d, m, meth = (int(sys.argv[1]) if len(sys.argv) > 1 else 1000000), 10, 1000, "VC"
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
+d, m = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (10, 1000)
+meth = "VC"
 X, Y = synth.make_data(n, d, seed=0)
 th = synth.make_theta0(X, Y, meth, m, het=True, seed=1)
 ctx = L.Context(L.make_model(d, 1, m, meth, True), X, Y)
