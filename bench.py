@@ -123,10 +123,20 @@ def thetas_for(theta0, count, seed=100):
 
 
 # ----------------------------------------------------------------------------------------------
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU legs are meant to use every host core."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
+
+
 def cpu_oracle_time(name, n_sample, reps, seed=0):
     """Seconds per evaluation of the NumPy restatement on an n_sample-row sample of the workload."""
     from gpz_b200 import synth
     from oracle import gpz_oracle as O
+    use_all_host_threads()
     n, d, m, method = WORKLOADS[name]
     ns = min(n, n_sample)
     X, Y = synth.make_data(ns, d, seed=seed)
