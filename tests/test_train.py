@@ -105,6 +105,23 @@ def test_oracle_two_loop_equals_dense_bfgs_inverse():
     assert mem.add(-pairs[0][0], pairs[0][0]) is True                       # negative curvature: pair skipped
 
 
+def test_oracle_reaches_the_same_minimiser_as_an_independent_optimiser():
+    """Not a trajectory pin (none exists), but an independent implementation: SciPy's L-BFGS-B on strictly convex problems
+    must end at the same point as the minFunc restatement."""
+    from scipy.optimize import minimize
+
+    fun, p = make_logistic(500, 30, seed=5)
+    x, f, flag, info = MO.minfunc_lbfgs(fun, np.zeros(p), opt_tol=1e-9, prog_tol=1e-14, max_iter=2000)
+    r = minimize(fun, np.zeros(p), jac=True, method="L-BFGS-B", options=dict(gtol=1e-10, ftol=1e-15, maxiter=5000))
+    assert abs(f - r.fun) <= 1e-9 * abs(r.fun) and np.allclose(x, r.x, rtol=1e-4, atol=1e-6)
+    rng = np.random.default_rng(8)
+    A = rng.standard_normal((80, 40))
+    H = A.T @ A + 0.5 * np.eye(40)
+    b = rng.standard_normal(40)
+    x, f, flag, info = MO.minfunc_lbfgs(lambda v: (0.5 * v @ H @ v - b @ v, H @ v - b), np.zeros(40), opt_tol=1e-10, prog_tol=1e-15)
+    assert np.allclose(x, np.linalg.solve(H, b), rtol=1e-6, atol=1e-8)
+
+
 def test_oracle_backs_out_of_a_nan_region():
     x, f, flag, info = MO.minfunc_lbfgs(barrier, np.full(4, 3.0))
     c = np.arange(1, 5, dtype=np.float64)
