@@ -142,6 +142,15 @@ def getPHI(X, Psi, theta, model, selection=None, device=0):
         ctx.close()
 
 
+def getPrior(X, Psi, theta, model, selection=None, device=0):
+    """prior = getPrior(X,Sx,theta,model,set) (GPz/getPrior.m:1): EM for the mixture weights of the bases, on the device."""
+    ctx = L.Context(_c_model(model), X, np.zeros((X.shape[0], model["k"])), Psi, None, selection, None, device=device)
+    try:
+        return ctx.get_prior(theta)
+    finally:
+        ctx.close()
+
+
 def inv_logdet(X, device=0):
     """[Xi,logdet] = inv_logdet(X) (GPz/inv_logdet.m:1) for symmetric positive definite X."""
     return L.inv_logdet(X, device)

@@ -54,6 +54,10 @@ def test_sinc_demo_flow():
     om.best = dict(model["best"])
     mu2, sigma2, *_ = O.predict(X, om, selection=te)
     assert np.max(np.abs(mu - mu2)) <= 1e-9 * max(1.0, np.max(np.abs(mu2))) and np.max(np.abs(sigma - sigma2)) <= 1e-8 * np.max(sigma2)
+    # getPrior through its reference-named wrapper = the priors train() stored (train.m:74)
+    pr = api.getPrior((X - model["muX"]) / model["sdX"], None, model["best"]["theta"], model, tr)
+    assert np.allclose(pr, model["best"]["priors"], rtol=1e-9, atol=1e-12) and abs(pr.sum() - 1.0) < 1e-12
+    assert model["train_info"]["fun_evals"] >= model["train_info"]["iterations"] >= 1
     # noisy-input prediction runs and adds variance
     mu3, sigma3, _, _, gamma3, *_ = api.predict(X, model, selection=te, Psi=np.full((n, 1), 0.05))
     assert np.all(np.isfinite(sigma3)) and float(np.mean(gamma3)) > 0
