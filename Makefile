@@ -7,7 +7,14 @@ HDR := $(wildcard gpz_b200/csrc/*.cuh) include/gpz_b200.h
 OBJ := $(patsubst gpz_b200/csrc/%.cu,build/%.o,$(SRC))
 LIB := gpz_b200/libgpz_b200.so
 
-all: $(LIB)
+HARNESS := tests/mex_stub/libgpz_mex_harness.so
+
+all: $(LIB) $(HARNESS)
+
+# test infrastructure: the MEX gateway linked against a minimal libmx mock, so that it can be executed without MATLAB
+$(HARNESS): matlab/gpz_b200_mex.cpp tests/mex_stub/mex_mock.cpp tests/mex_stub/mex.h include/gpz_b200.h $(LIB)
+	g++ -std=c++17 -O1 -fPIC -shared -Wall -Iinclude -Itests/mex_stub matlab/gpz_b200_mex.cpp tests/mex_stub/mex_mock.cpp \
+	    -Lgpz_b200 -lgpz_b200 -Wl,-rpath,'$$ORIGIN/../../gpz_b200' -o $@
 
 build/%.o: gpz_b200/csrc/%.cu $(HDR)
 	@mkdir -p build
@@ -17,5 +24,5 @@ $(LIB): $(OBJ)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -ldl
 
 clean:
-	rm -rf build $(LIB)
+	rm -rf build $(LIB) $(HARNESS)
 .PHONY: all clean

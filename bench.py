@@ -31,17 +31,22 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (n, d, m, method)
-    "target": (1_000_000, 10, 1000, "VC"),
-    "cfg3": (1_000_000, 10, 500, "VD"),
-    "photoz": (60_000, 5, 100, "VC"),
-    "small": (20_000, 10, 256, "VC"),
+    # name: (n, d, m, method, extras).  "gpus": the GPU count BASELINE.json states the config on -- those workloads are WEAK
+    # scaling (rows per GPU fixed at n / gpus, every rank generates its own rows), the others shard a fixed n (strong).
+    "target": (1_000_000, 10, 1000, "VC", {}),                         # north-star headline; = configs[3] per GPU shape
+    "cfg3": (1_000_000, 10, 500, "VD", {}),                            # configs[2]: 1-GPU roofline capture
+    "cfg4": (10_000_000, 10, 1000, "VC", {"gpus": 8}),                 # configs[3]: n = 1e7 sharded over 8 GPUs
+    "cfg5": (1_000_000, 32, 2000, "GC", {"gpus": 4, "psi": True}),     # configs[4]: GC + input noise over 4 GPUs
+    "photoz": (60_000, 5, 100, "VC", {}),
+    "small": (20_000, 10, 256, "VC", {}),
 }
 METRIC = "NLML+grad evals/sec at (n,d,m) per covariance mode"
 
 
 def workload_desc(name, n, d, m, method):
-    return f"synthetic n={n} d={d} m={m} {method} heteroscedastic k=1 ({name})"
+    ex = WORKLOADS[name][4]
+    return (f"synthetic n={n} d={d} m={m} {method}{' + input noise Psi (d x d x n)' if ex.get('psi') else ''} heteroscedastic k=1 ({name}"
+            + (f": {WORKLOADS[name][0] // ex['gpus']} rows per GPU, BASELINE states it on {ex['gpus']} GPUs" if ex.get("gpus") else "") + ")")
 
 
 # ----------------------------------------------------------------------------------------------
@@ -111,10 +116,29 @@ def fp64_peak_tflops(torch, dev, reps=10, N=8192):
 
 def make_problem(name, seed=0):
     from gpz_b200 import synth
-    n, d, m, method = WORKLOADS[name]
+    n, d, m, method, _ = WORKLOADS[name]
     X, Y = synth.make_data(n, d, seed=seed)
     theta0 = synth.make_theta0(X, Y, method, m, het=True, seed=seed + 1)
     return n, d, m, method, X, Y, theta0
+
+
+def make_shard(name, rank, world, seed=0):
+    """This rank's rows.  Strong workloads: the contiguous block [n rank / world, n (rank+1) / world) of the one seeded data
+    set.  Weak workloads ("gpus" set): n / gpus rows generated by this rank alone (seed + 1000 + rank: no 800 MB host array
+    per process), theta0 from a fixed 100 000-row sample so that it is the same on every rank."""
+    from gpz_b200 import synth
+    n, d, m, method, ex = WORKLOADS[name]
+    if not ex.get("gpus"):
+        X, Y = synth.make_data(n, d, seed=seed)
+        theta0 = synth.make_theta0(X, Y, method, m, het=True, seed=seed + 1)
+        lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+        return dict(n_total=n, rows=hi - lo, X=X[lo:hi], Y=Y[lo:hi], Psi=None, theta0=theta0, scaling="strong")
+    rows = n // ex["gpus"]
+    Xs, Ys = synth.make_data(100_000, d, seed=seed)
+    theta0 = synth.make_theta0(Xs, Ys, method, m, het=True, seed=seed + 1)
+    X, Y = synth.make_data(rows, d, seed=seed + 1000 + rank)
+    Psi = synth.make_psi(rows, d, method, seed=seed + 2000 + rank) if ex.get("psi") else None
+    return dict(n_total=rows * world, rows=rows, X=X, Y=Y, Psi=Psi, theta0=theta0, scaling="weak")
 
 
 def thetas_for(theta0, count, seed=100):
@@ -137,17 +161,18 @@ def cpu_oracle_time(name, n_sample, reps, seed=0):
     from gpz_b200 import synth
     from oracle import gpz_oracle as O
     use_all_host_threads()
-    n, d, m, method = WORKLOADS[name]
+    n, d, m, method, ex = WORKLOADS[name]
     ns = min(n, n_sample)
     X, Y = synth.make_data(ns, d, seed=seed)
     theta0 = synth.make_theta0(X, Y, method, m, het=True, seed=seed + 1)
     model = O.Model(d=d, k=1, m=m, method=method, heteroscedastic=True)
     X, Y = np.array(X), np.array(Y)
+    Psi = np.array(synth.make_psi(ns, d, method, seed=seed + 2000)) if ex.get("psi") else None
     ths = thetas_for(theta0, reps)
     ts = []
     for th in ths:
         t0 = time.perf_counter()
-        O.GPz(th, model, X, Y)
+        O.GPz(th, model, X, Y, Psi)
         ts.append(time.perf_counter() - t0)
     # the m x m SVD pseudo-inverse does not grow with n: time it alone so only the n-proportional part is scaled
     A = np.random.default_rng(0).standard_normal((m, m + 8))
@@ -164,13 +189,24 @@ def scale_cpu_time(sec_sample, t_svd, n, ns):
     return (sec_sample - t_svd) * (n / ns) + t_svd
 
 
+def cpu_sample_rows(name, budget):
+    """Rows of the bounded CPU sample: ~budget 'flop-like units' per evaluation (dense paths: 4 GEMMs of 2 n m^2 plus the
+    per-basis loops; C modes + Psi: the reference's scalar loop over n x m with d x d solves, ~25 000 (i, j) pairs per second)."""
+    n, d, m, method, ex = WORKLOADS[name]
+    if ex.get("psi") and method[1] == "C":
+        return max(16, min(n, int(budget / 4.0e10 * 1.0e5 / m)))
+    return max(2000, min(n, int(budget / (m * m + 40.0 * m * d * d))))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     name = args.workload
-    n, d, m, method = WORKLOADS[name]
-    ns = args.cpu_sample or max(2000, min(n, int(4.0e10 / (m * m + 40.0 * m * d * d))))   # ~4-6 s per step
+    n, d, m, method, ex = WORKLOADS[name]
+    if ex.get("gpus"):                                   # weak workloads: the job the GPU arm runs at this GPU count
+        n = n // ex["gpus"] * max(1, args.gpus)
+    ns = args.cpu_sample or cpu_sample_rows(name, 4.0e10)                                   # ~4-6 s per step
     total = args.warmup + args.steps
     ns, ts, t_svd = cpu_oracle_time(name, ns, total)
     timed = ts[args.warmup:] if len(ts) > args.warmup else ts
@@ -178,10 +214,19 @@ def run_reference(args):
     sec_full = scale_cpu_time(sec_sample, t_svd, n, ns)
     value = 1.0 / sec_full
     cores = os.cpu_count() or 1
+    # linearity of t(n) = a n + c on this box: one more evaluation at half the sample
+    _, th, _ = cpu_oracle_time(name, max(1, ns // 2), 1)
+    half_pred = (sec_sample - min(t_svd, 0.5 * sec_sample)) * 0.5 + min(t_svd, 0.5 * sec_sample)
+    lin = {"rows": [max(1, ns // 2), ns], "seconds": [th[0], sec_sample], "residual_at_half": (th[0] - half_pred) / th[0]}
+    try:
+        lin["tracked_run_at_5e4_1e5_rows"] = json.load(open(os.path.join(ROOT, "profiles", "r02_cpu_linearity.json")))
+    except Exception:
+        pass
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_full * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "weak" if ex.get("gpus") else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "linearity": lin,
         "config": {"workload": workload_desc(name, n, d, m, method),
                    "note": "reference is MATLAB (no MATLAB/Octave here): NumPy restatement of GPz.m/getPHI.m/inv_logdet.m, "
                            "same operation sequence, OpenBLAS threads = all host cores"},
@@ -212,10 +257,13 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=dev)
 
     name = args.workload
-    n, d, m, method, X, Y, theta0 = make_problem(name)
-    lo, hi = (n * rank) // world, (n * (rank + 1)) // world          # contiguous row shard of this rank
+    _, d, m, method, wex = WORKLOADS[name]
+    sh = make_shard(name, rank, world)                               # this rank's rows (strong: a block of the one data set)
+    n, theta0, scaling = sh["n_total"], sh["theta0"], sh["scaling"]
+    Xs, Ys, Psis = sh["X"], sh["Y"], sh["Psi"]
+    lo, hi = 0, sh["rows"]
     t0 = time.perf_counter()
-    ctx = L.Context(L.make_model(d, 1, m, method, True), X[lo:hi], Y[lo:hi], device=local)
+    ctx = L.Context(L.make_model(d, 1, m, method, True), Xs, Ys, Psis, device=local)
     if world > 1:
         uid = [L.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -254,6 +302,7 @@ def run_gpu(args):
     ms_total = e0.elapsed_time(e1)
     launches = ctx.launch_count() - l0
     tm = ctx.last_timing()            # CUDA events recorded inside the last timed evaluation
+    kt = ctx.kernel_timing()          # ... and around single kernels of it
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -299,7 +348,7 @@ def run_gpu(args):
             ctx.close()
             ctx = None
             va_mask = (np.arange(lo, hi) % max(2, int(round(1.0 / args.valid_frac)))) == 0
-            ctx2 = L.Context(L.make_model(d, 1, m, method, True), X[lo:hi], Y[lo:hi], None, None, ~va_mask, va_mask, device=local)
+            ctx2 = L.Context(L.make_model(d, 1, m, method, True), Xs, Ys, Psis, None, ~va_mask, va_mask, device=local)
             if world > 1:
                 uid = [L.comm_unique_id() if rank == 0 else None]
                 dist.broadcast_object_list(uid, src=0)
@@ -351,16 +400,24 @@ def run_gpu(args):
                       "note": "algorithmic fp64 flops (2nm^2 per GEMM, 4nm^2 per eval) per second; the fp64 DMMA pipe ceiling is "
                               "the cuBLAS DGEMM 8192^3 figure measured in this run -- values above it come from the error-free "
                               "int8-slice (Ozaki) GEMMs on the tcgen05 tensor cores"}
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "profiles", "peaks.json")))
+        except Exception:
+            pass
         if tm["int8_slices"] > 0:
-            bf16 = measured.get("bf16_tflops_sustained")
-            src = "2 x MEASURED_PEAKS.json bf16_tflops_sustained (tcgen05 kind::i8 issues at twice the bf16 rate; kernel timed inside a long step)"
-            if not bf16:
-                bf16, src = 1400.0, "2 x 1.4 PFLOP/s: fallback sustained bf16 figure of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+            i8 = peaks.get("int8_tops_sustained")
+            src = ("profiles/peaks.json int8_tops_sustained: cuBLASLt IGEMM 8192^3 (torch._int_mm) back to back for 4 s on this pool's B200 "
+                   "(tools/measure_peaks.py; the kernel is timed inside a long step, so the sustained figure; burst: %s)" % peaks.get("int8_tops"))
+            if not i8:
+                bf16 = measured.get("bf16_tflops_sustained") or 1400.0
+                i8, src = 2.0 * bf16, "2 x sustained bf16 (profiles/peaks.json absent: kind::i8 issues at twice the bf16 rate)"
             ach = tm["i8_gemms_ops"] / (tm["i8_gemms_ms"] * 1e-3) / 1e12
             roof = {"bound": "tensor",
-                    "kernel": "ozmma_kernel (hand-written tcgen05.mma kind::i8 cta_group::2, TMA, TMEM double buffer; %d base-256 digits, "
-                              "levels folded in fp64 registers, fused nu/H epilogue): T = PHI*iSigma, one launch over all rows" % tm["int8_slices"],
-                    "achieved": ach, "peak": 2.0 * bf16, "unit": "TFLOP/s", "frac": ach / (2.0 * bf16),
+                    "kernel": "ozmma_kernel (hand-written tcgen05.mma kind::i8 cta_group::2 N=256 over two digit levels, TMA, TMEM double "
+                              "buffer; %d base-256 digits, levels folded in fp64 registers, fused nu/H epilogue): T = PHI*iSigma, one launch "
+                              "over all rows" % tm["int8_slices"],
+                    "achieved": ach, "peak": i8, "unit": "TFLOP/s", "frac": ach / i8,
                     "ops": "int8 multiply-adds x2 executed by that launch (2 n MP^2 per digit pair, s(s+1)/2 pairs)",
                     "traffic": prof.get("ozmma_tgemm_dram_bytes_per_launch") if n_loc == 1000000 and name == "target" else None,
                     "peak_source": src,
@@ -375,17 +432,21 @@ def run_gpu(args):
                                    "(MEASURED_PEAKS.json has no fp64 figure; tcgen05 has no fp64 kind, DMMA is the fp64 tensor path)",
                     "algorithmic_flops_per_launch": flops_tgemm, "kernel_ms": tm["tgemm_kernel"]}
         roof["fp64_equivalent"] = fp64_equiv
-        # the PHI build against the HBM roofline (north star: ">= 60 %"; SURVEY 8d: B_PHI = 8 (n m + n d + m d + g_dim) bytes).
-        # phase_ms["phi"] = prep + PHI = exp(F W) + row weights; the kernel is fp64-pipe bound at d = 10
+        # the PHI build against the HBM roofline (north star: ">= 60 %"; SURVEY 8d: B_PHI = 8 (n m + n d [+ Psi] + m d + g_dim) bytes),
+        # on the PHI kernel's OWN CUDA-event time (gpz_kernel_timing[0]); the kernel is fp64-pipe bound at d = 10
         hbm = measured.get("hbm_gbs") or 6650.0
-        b_phi = 8.0 * (n_loc * m + n_loc * d + m * d + (int(p) - m * d - 3 * m - 1))
-        roof["phi_path"] = {"algorithmic_bytes": b_phi, "ms": tm["phi"], "achieved_gbs": b_phi / (tm["phi"] * 1e-3) / 1e9,
-                            "peak_gbs": hbm, "frac": b_phi / (tm["phi"] * 1e-3) / 1e9 / hbm,
+        g_dim = int(p) - m * d - 3 * m - 1
+        b_phi = 8.0 * (n_loc * m + n_loc * d + (n_loc * d * d if wex.get("psi") else 0) + m * d + g_dim)
+        t_phi = kt["phi_build"] if kt["phi_build"] > 0 else tm["phi"]
+        roof["phi_path"] = {"algorithmic_bytes": b_phi, "ms": t_phi, "achieved_gbs": b_phi / (t_phi * 1e-3) / 1e9,
+                            "peak_gbs": hbm, "frac": b_phi / (t_phi * 1e-3) / 1e9 / hbm,
+                            "timed": "the PHI kernel (+ the ordered sum of its row-dot partials), CUDA events" if kt["phi_build"] > 0 else "the phi phase",
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if measured.get("hbm_gbs") else "fallback 6.65 TB/s"}
+        roof["kernel_ms"] = {k_: round(float(v), 3) for k_, v in kt.items() if v >= 0}
         roof["phase_ms"] = {k_: round(float(v), 3) for k_, v in tm.items() if k_ not in ("i8_gemms_ops", "int8_slices", "int8_gram")}
         cpu = None
         if world == 1 and not args.no_cpu:
-            ns = args.cpu_sample or max(2000, min(n, int(1.2e11 / (m * m + 40.0 * m * d * d))))   # ~10-20 s of CPU work
+            ns = args.cpu_sample or cpu_sample_rows(name, 1.2e11)                                  # ~10-20 s of CPU work
             ns, ts, t_svd = cpu_oracle_time(name, ns, 2)
             sec = scale_cpu_time(min(ts), t_svd, n, ns)
             cpu = {"value": 1.0 / sec, "unit": "evals/s", "cores": os.cpu_count() or 1, "kind": "port",
@@ -393,10 +454,11 @@ def run_gpu(args):
                              f"a*n scaled x{n / ns:.1f}; NumPy restatement of the MATLAB reference, {min(ts):.2f} s on the sample"}
         line = {
             "metric": METRIC, "value": 1e3 / ms_step, "unit": "evals/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_desc(name, n, d, m, method), "rows_per_gpu": hi - lo,
                        "parallelism": f"rows sharded over {world} GPU(s), 2 NCCL allreduces per eval" if world > 1 else "1 GPU",
+                       "n_total": int(n),
                        "cache": "inputs larger than L2: PHI/H working set %.1f GB per GPU" % (16.0 * (hi - lo) * m_bases / 1e9),
                        "dataset_upload_s": round(upload_s, 3), "theta_len": int(p)},
             "e2e": {"value": 1.0 / e2e_step, "unit": "evals/s", "h2d_bytes_per_step": 8 * int(p), "d2h_bytes_per_step": 8 * (int(p) + 5),

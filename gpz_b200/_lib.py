@@ -18,7 +18,7 @@ EXPORTS = [
     "gpz_last_error", "gpz_version", "gpz_theta_len", "gpz_g_dim", "gpz_create", "gpz_destroy",
     "gpz_comm_unique_id", "gpz_comm_init", "gpz_eval", "gpz_eval_dev", "gpz_fit", "gpz_phi", "gpz_get_prior", "gpz_rows",
     "gpz_predict", "gpz_inv_logdet", "gpz_dxy", "gpz_stream", "gpz_sync", "gpz_launch_count", "gpz_graph_replays",
-    "gpz_last_timing", "gpz_set_option", "gpz_dgemm_nt",
+    "gpz_last_timing", "gpz_kernel_timing", "gpz_set_option", "gpz_dgemm_nt",
     "gpz_dxy_colmean", "gpz_train", "gpz_minimize_dev", "gpz_train_default_options", "gpz_train_reason",
 ]
 
@@ -114,6 +114,8 @@ def load():
     lib.gpz_dgemm_nt.argtypes = [C.c_int64, C.c_int64, C.c_int64, _dp, C.c_int64, _dp, C.c_int64, _dp, C.c_int64, C.c_int32, C.c_int]
     lib.gpz_last_timing.restype = C.c_int
     lib.gpz_last_timing.argtypes = [C.c_void_p, _dp]
+    lib.gpz_kernel_timing.restype = C.c_int
+    lib.gpz_kernel_timing.argtypes = [C.c_void_p, _dp]
     lib.gpz_set_option.restype = C.c_int
     lib.gpz_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
     lib.gpz_train_default_options.restype = None
@@ -267,6 +269,11 @@ class Context:
         return dict(phi=ms[0], gram=ms[1], solve=ms[2], tgemm=ms[3], backproj=ms[4], total=ms[5],
                     gram_kernel=ms[6], tgemm_kernel=ms[7], i8_gemms_ms=ms[8], i8_gemms_ops=ms[9],
                     int8_slices=int(ms[10]), int8_gram=int(ms[11]))
+
+    def kernel_timing(self):
+        ms = np.empty(4)
+        check(self._lib.gpz_kernel_timing(self._h, ptr(ms)))
+        return dict(phi_build=ms[0], digits=ms[1], gram_gemm=ms[2], moment_gemm=ms[3])
 
 
 def train_options(**kw) -> TrainOptions:

@@ -553,6 +553,8 @@ struct gpz_ctx {
     SolveWs sws;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t kev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // + [4,5] around the int8 level GEMMs of row chunk 0   // [0,1] around the first Gram launch, [2,3] around the first T-GEMM launch
+    cudaEvent_t kt[12] = {};   // pairs around single kernels of row chunk 0 (gpz_kernel_timing): PHI build, digits, Gram GEMM, moment GEMM
+    bool kt_valid[6] = {};
     double* h_out = nullptr;   // pinned
     double* h_theta = nullptr; // pinned
     std::vector<void*> allocs;
@@ -823,7 +825,7 @@ int ensure_workspace(gpz_ctx* c) {
     const int T = static_cast<int>(MP / TILE);
     const int ntri = T * (T + 1) / 2;
     c->gram_ns = gram_nsplit(static_cast<int>(MP), c->sm_count);
-    if ((rc = A(&c->gram_partial, static_cast<int64_t>(c->gram_ns) * ntri * TILE * TILE))) return rc;
+    if ((rc = A(&c->gram_partial, static_cast<int64_t>(k) * c->gram_ns * ntri * TILE * TILE))) return rc;   // per output: row chunks accumulate
     c->QP = P.QP;
     const int tn = c->QP / 32;
     c->atb_ns = c->sm_count / (T * tn) > 0 ? c->sm_count / (T * tn) : 1;
@@ -952,6 +954,7 @@ int ensure_workspace(gpz_ctx* c) {
     for (auto& e : c->ev) GPZ_CUDA(cudaEventCreate(&e));
     for (auto& e : c->kev) GPZ_CUDA(cudaEventCreate(&e));
     for (auto& e : c->gev) GPZ_CUDA(cudaEventCreate(&e));
+    for (auto& e : c->kt) GPZ_CUDA(cudaEventCreate(&e));
     GPZ_CUDA(cudaMallocHost(&c->h_out, sizeof(double) * (P.p + 5)));
     GPZ_CUDA(cudaMallocHost(&c->h_theta, sizeof(double) * P.p));
     c->ws_ready = true;
@@ -984,7 +987,13 @@ int forward_and_solve(gpz_ctx* c, const double* d_theta) {
         if (n > 0) {
             DotSpec ds{0, {nullptr, nullptr}, {nullptr, nullptr}};
             if (P.het && k == 1) ds = DotSpec{1, {P.v, nullptr}, {c->lnbi, nullptr}};
+            const bool kt_on = r0 == 0 && !c->capturing;
+            if (kt_on) GPZ_CUDA(cudaEventRecord(c->kt[0], st));
             if ((rc = phi_build(P, c->tr, r0, r1, phi, ds, c->dot_scratch, st, &c->launches))) return rc;
+            if (kt_on) {
+                GPZ_CUDA(cudaEventRecord(c->kt[1], st));
+                c->kt_valid[0] = true;
+            }
             if (P.het && k > 1)
                 for (int o = 0; o < k; ++o)
                     if ((rc = rowdot(phi, MP, P.m, r1 - r0, DotSpec{1, {P.v + o * MP, nullptr}, {c->lnbi + o * n + r0, nullptr}}, st, &c->launches))) return rc;
@@ -1004,22 +1013,29 @@ int forward_and_solve(gpz_ctx* c, const double* d_theta) {
                     GPZ_KERNEL_CHECK();
                     ++c->launches;
                 }
+                const bool kt_on = nchunks == 0 && !c->capturing;
+                if (kt_on) GPZ_CUDA(cudaEventRecord(c->kt[2], st));
                 if ((rc = ozaki_digits(phi, MP, static_cast<int>(MP), P.m, r1 - r0, c->opt_ozaki, c->ob + r0, c->d_scal, c->aug ? 1 : 0,
                                        c->oz_D8, c->oz_F8, c->oz_ea, c->sws.flag, st, &c->launches))) return rc;
+                if (kt_on) {
+                    GPZ_CUDA(cudaEventRecord(c->kt[3], st));
+                    GPZ_CUDA(cudaEventRecord(c->kt[4], st));
+                }
                 if ((rc = ozaki_gram(c->oz_F8, c->oz_D8, static_cast<int>(MP), P.m, r1 - r0, c->opt_ozaki, c->opt_ozaki_gs, c->d_scal,
                                      c->aug ? 1 : 0, nchunks > 0, c->S, c->ozg_ws, c->sws.flag, st, &c->launches))) return rc;
+                if (kt_on) {
+                    GPZ_CUDA(cudaEventRecord(c->kt[5], st));
+                    c->kt_valid[1] = c->kt_valid[2] = true;
+                }
                 if (timed) GPZ_EVREC(c->kev[1]);
                 continue;
             }
-            if ((rc = gram_syrk_main(phi, MP, static_cast<int>(MP), c->ob + o * n + r0, 0, r1 - r0, c->gram_ns,
-                                     c->gram_partial, nchunks > 0, st, &c->launches))) return rc;
+            double* gp = c->gram_partial + static_cast<int64_t>(o) * c->gram_ns * (T * (T + 1) / 2) * TILE * TILE;
+            if ((rc = gram_syrk_main(phi, MP, static_cast<int>(MP), c->ob + o * n + r0, 0, r1 - r0, c->gram_ns, gp, nchunks > 0, st,
+                                     &c->launches))) return rc;
             if (timed) GPZ_EVREC(c->kev[1]);
-            if ((rc = gram_syrk_finish(c->gram_partial, c->gram_ns, static_cast<int>(MP), last, c->S + static_cast<int64_t>(o) * MP * MP, st,
+            if ((rc = gram_syrk_finish(gp, c->gram_ns, static_cast<int>(MP), last, c->S + static_cast<int64_t>(o) * MP * MP, st,
                                        &c->launches))) return rc;
-            if (k > 1 && !last) {
-                set_error("row chunking with k > 1 outputs is not supported (raise the memory budget)");
-                return GPZ_ERR_USAGE;
-            }
         }
         if (!c->aug)
             if ((rc = atb_general(phi, MP, static_cast<int>(MP), c->yw + r0 * 32, 32, 32, c->ones, 0, r1 - r0, ns1, c->atb_partial,
@@ -1105,7 +1121,7 @@ int eval_device_enqueue(gpz_ctx* c, const double* d_theta, double* d_out) {
     double* sc2 = qcol + 2LL * k * MP;
     const bool fast_bp = !c->has_psi && !c->tr.has_nan;
     const int T = static_cast<int>(MP / TILE);
-    int nchunks = 0, colp_slabs = 1;
+    int nchunks = 0, colp_slabs = 1, pieces = 0;      // pieces: (row chunk, pattern group) parts of the moment GEMM done so far
     bool ev4 = false;
     for (int64_t r0 = 0; r0 < n; r0 += c->chunk_rows) {
         const int64_t r1 = (r0 + c->chunk_rows < n) ? r0 + c->chunk_rows : n;
@@ -1143,10 +1159,6 @@ int eval_device_enqueue(gpz_ctx* c, const double* d_theta, double* d_out) {
         }
         const bool fused = fast_bp && c->opt_fused_bp && k == 1 && c->QP <= 128;
         const size_t ng = c->tr.g_pat.empty() ? 1 : c->tr.g_pat.size();
-        if (ng > 1 && !c->resident) {
-            set_error("missing-input pattern groups need PHI resident in HBM (raise the memory budget / lower n per GPU)");
-            return GPZ_ERR_USAGE;
-        }
         if (!fused) {
             const int64_t rps = ceil_div(rows, c->dphi_slabs);
             dim3 grid(static_cast<unsigned>(T), static_cast<unsigned>(c->dphi_slabs));
@@ -1161,22 +1173,30 @@ int eval_device_enqueue(gpz_ctx* c, const double* d_theta, double* d_out) {
             // one moment GEMM per missing-input pattern group (a single group when the data have no NaN)
             for (size_t g = 0; g < ng; ++g) {
                 int64_t s0 = r0, s1 = r1;
-                if (ng > 1) {
-                    s0 = c->tr.g_r0[g];
-                    s1 = c->tr.g_r1[g];
+                if (ng > 1) {                  // the part of this pattern group inside the row chunk
+                    s0 = c->tr.g_r0[g] > r0 ? c->tr.g_r0[g] : r0;
+                    s1 = c->tr.g_r1[g] < r1 ? c->tr.g_r1[g] : r1;
+                    if (s1 <= s0) continue;
                 }
                 const int acc = ng > 1 ? 0 : (nchunks > 0);
                 const int red = ng > 1 ? 1 : (last ? 1 : 0);
+                const bool kt_on = nchunks == 0 && g == 0 && !c->capturing;
+                if (kt_on) GPZ_CUDA(cudaEventRecord(c->kt[6], st));
                 if (fused) {
                     if ((rc = atb_dphi(phi + (s0 - r0) * MP, c->H + (s0 - r0) * MP, MP, static_cast<int>(MP), c->tr.F + s0 * c->QP, c->QP, P.q,
                                        c->cw + s0, c->dbeta + s0, c->w, P.v, 0, s1 - s0, c->fused_ns, c->atb_partial, c->colp, acc,
-                                       ng > 1 ? (g > 0) : (nchunks > 0), red, c->Rm, st, &c->launches))) return rc;
+                                       pieces > 0, red, c->Rm, st, &c->launches))) return rc;
                 } else {
                     if ((rc = atb_general(c->H + (s0 - r0) * MP, MP, static_cast<int>(MP), c->tr.F + s0 * c->QP, c->QP, c->QP, c->ones, 0,
                                           s1 - s0, c->atb_ns, c->atb_partial, acc, red, c->Rm, st, &c->launches))) return rc;
                 }
+                if (kt_on) {
+                    GPZ_CUDA(cudaEventRecord(c->kt[7], st));
+                    c->kt_valid[3] = true;
+                }
                 if (ng > 1)
-                    if ((rc = moments_to_grad(P, c->tr.g_pat[g], c->Rm, c->QP, dP, c->scratch, g > 0, st, &c->launches))) return rc;
+                    if ((rc = moments_to_grad(P, c->tr.g_pat[g], c->Rm, c->QP, dP, c->scratch, pieces > 0, st, &c->launches))) return rc;
+                ++pieces;
             }
         } else if (!mode_is_cov(P.mode)) {
             if ((rc = backproj_diag_generic(P, c->tr, r0, r1, c->H, MP, c->bp_partial, c->nslab, nchunks > 0, st, &c->launches))) return rc;
@@ -1716,14 +1736,20 @@ int gpz_get_prior(gpz_ctx* c, const double* theta, double* prior) {
     Params& P = c->P;
     const int64_t n = c->tr.n, MP = P.MP;
     cudaStream_t st = c->st;
-    if (!c->resident) {
-        set_error("gpz_get_prior needs PHI resident in HBM (lower n per GPU)");
-        return GPZ_ERR_USAGE;
-    }
     GPZ_CUDA(cudaMemcpyAsync(c->d_theta, theta, sizeof(double) * P.p, cudaMemcpyHostToDevice, st));
     if ((rc = prep_params(c->d_theta, P, c->has_psi, st, &c->launches))) return rc;
-    if ((rc = phi_build(P, c->tr, 0, n, c->Phi, DotSpec{0, {nullptr, nullptr}, {nullptr, nullptr}}, c->dot_scratch, st, &c->launches))) return rc;
-    if ((rc = phi_to_density(P, c->tr, 0, n, c->Phi, c->H, st, &c->launches))) return rc;       // N lives in the H buffer
+    // N (getPHI's 4th output) of the rows [r0, r1) into the H buffer.  PHI resident: all rows once, before the EM loop; otherwise
+    // rebuilt per row chunk in every iteration -- which is what the reference does for ALL rows (getPrior.m:10 calls getPHI
+    // inside the loop although N does not depend on the prior)
+    auto build_N = [&](int64_t r0, int64_t r1) -> int {
+        double* phi = c->resident ? c->Phi + r0 * MP : c->Phi;
+        double* Nn = c->resident ? c->H + r0 * MP : c->H;
+        int e = phi_build(P, c->tr, r0, r1, phi, DotSpec{0, {nullptr, nullptr}, {nullptr, nullptr}}, c->dot_scratch, st, &c->launches);
+        if (!e) e = phi_to_density(P, c->tr, r0, r1, phi, Nn, st, &c->launches);
+        return e;
+    };
+    if (c->resident && n > 0)
+        if ((rc = build_N(0, n))) return rc;
     double* d_prior = c->dwda;             // [MP] scratch vectors of the eval path are free here
     double* d_s = c->pred;
     double* d_R = c->Rvec;                 // [MP][32]
@@ -1737,14 +1763,25 @@ int gpz_get_prior(gpz_ctx* c, const double* theta, double* prior) {
     const int T = static_cast<int>(MP / TILE);
     const int ns1 = c->sm_count / T > 0 ? c->sm_count / T : 1;
     for (int iter = 0; iter < 100; ++iter) {                                                      // getPrior.m:7
-        if ((rc = rowdot(c->H, MP, P.m, n, DotSpec{1, {d_prior, nullptr}, {d_s, nullptr}}, st, &c->launches))) return rc;
-        prior_inv_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, st>>>(d_s, n, c->yw);
-        GPZ_KERNEL_CHECK();
-        if ((rc = atb_general(c->H, MP, static_cast<int>(MP), c->yw, 32, 32, c->ones, 0, n, ns1, c->atb_partial, 0, 1, d_R, st, &c->launches))) return rc;
+        if (n == 0) GPZ_CUDA(cudaMemsetAsync(d_R, 0, sizeof(double) * MP * 32, st));
+        int nchunks = 0;
+        for (int64_t r0 = 0; r0 < n; r0 += c->chunk_rows, ++nchunks) {
+            const int64_t r1 = (r0 + c->chunk_rows < n) ? r0 + c->chunk_rows : n;
+            const int64_t rows = r1 - r0;
+            if (!c->resident)
+                if ((rc = build_N(r0, r1))) return rc;
+            const double* Nn = c->resident ? c->H + r0 * MP : c->H;
+            if ((rc = rowdot(Nn, MP, P.m, rows, DotSpec{1, {d_prior, nullptr}, {d_s + r0, nullptr}}, st, &c->launches))) return rc;
+            prior_inv_kernel<<<static_cast<unsigned>(ceil_div(rows, 256)), 256, 0, st>>>(d_s + r0, rows, c->yw + r0 * 32);
+            GPZ_KERNEL_CHECK();
+            ++c->launches;
+            if ((rc = atb_general(Nn, MP, static_cast<int>(MP), c->yw + r0 * 32, 32, 32, c->ones, 0, rows, ns1, c->atb_partial, nchunks > 0,
+                                  r1 >= n, d_R, st, &c->launches))) return rc;
+        }
         if ((rc = allreduce(c, d_R, MP * 32))) return rc;
         prior_update_kernel<<<1, 256, 0, st>>>(d_prior, d_R, d_cnt, P.m, c->d_out);
         GPZ_KERNEL_CHECK();
-        c->launches += 2;
+        ++c->launches;
         double nr[2];
         GPZ_CUDA(cudaMemcpyAsync(nr, c->d_out, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
         GPZ_CUDA(cudaStreamSynchronize(st));
@@ -2297,6 +2334,23 @@ int gpz_last_timing(gpz_ctx* c, double ms[12]) {
     return GPZ_OK;
 }
 
+int gpz_kernel_timing(gpz_ctx* c, double ms[4]) {
+    if (!c || !c->ws_ready) {
+        set_error("gpz_kernel_timing: no evaluation yet");
+        return GPZ_ERR_USAGE;
+    }
+    GPZ_CUDA(cudaSetDevice(c->device));
+    GPZ_CUDA(cudaStreamSynchronize(c->st));
+    for (int i = 0; i < 4; ++i) {
+        ms[i] = -1.0;
+        if (!c->kt_valid[i]) continue;
+        float t;
+        GPZ_CUDA(cudaEventElapsedTime(&t, c->kt[2 * i], c->kt[2 * i + 1]));
+        ms[i] = t;
+    }
+    return GPZ_OK;
+}
+
 int64_t gpz_graph_replays(const gpz_ctx* c) { return c ? c->graph_replays : -1; }
 
 int gpz_set_option(gpz_ctx* c, const char* name, double value) {
@@ -2322,6 +2376,14 @@ int gpz_set_option(gpz_ctx* c, const char* name, double value) {
             return GPZ_ERR_USAGE;
         }
         g_gemm_warps = static_cast<int>(value);
+        return GPZ_OK;
+    }
+    if (strcmp(name, "ozaki_prefetch") == 0) {      // process-wide: L2 prefetch of the T-GEMM epilogue's PHI block (ozmma.cu), 1 = default
+        ozmma_set_prefetch(static_cast<int>(value));
+        return GPZ_OK;
+    }
+    if (strcmp(name, "ozaki_level_group") == 0) {   // process-wide: schedule of the digit GEMMs (ozmma.cu), 2 = default
+        ozmma_set_level_group(static_cast<int>(value));
         return GPZ_OK;
     }
     if (strcmp(name, "tensor_phi") == 0 || strcmp(name, "fused_backproj") == 0) {

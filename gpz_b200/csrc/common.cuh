@@ -76,6 +76,42 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N));
 }
 
+// ---- exp for the PHI-build epilogue (one exp per (row, basis): 1e9 per evaluation at the headline size; the kernel is bound by
+// the fp64 pipe, which DMMA and DFMA share, and libm's exp is ~22 fp64 operations).  Table-driven: x = (32 e + j) ln2/32 + r,
+// |r| <= ln2/64, exp(x) = 2^e * T[j] * (1 + r + r^2/2 + .. + r^6/720) -- 11 fp64 operations, truncation error 3e-18, about one
+// ulp overall (T[j] and the final FMA round once each).  T = 2^(j/32), correctly rounded, staged in shared memory by the
+// caller (32 doubles; two entries per bank, so a lookup is at most a 2-way conflict).  Outside |x| <= 708 (underflow into
+// subnormals, overflow, NaN) it defers to libm.
+__constant__ static double c_exp2_32[32] = {
+    0x1.0000000000000p+0, 0x1.059b0d3158574p+0, 0x1.0b5586cf9890fp+0, 0x1.11301d0125b51p+0, 0x1.172b83c7d517bp+0, 0x1.1d4873168b9aap+0,
+    0x1.2387a6e756238p+0, 0x1.29e9df51fdee1p+0, 0x1.306fe0a31b715p+0, 0x1.371a7373aa9cbp+0, 0x1.3dea64c123422p+0, 0x1.44e086061892dp+0,
+    0x1.4bfdad5362a27p+0, 0x1.5342b569d4f82p+0, 0x1.5ab07dd485429p+0, 0x1.6247eb03a5585p+0, 0x1.6a09e667f3bcdp+0, 0x1.71f75e8ec5f74p+0,
+    0x1.7a11473eb0187p+0, 0x1.82589994cce13p+0, 0x1.8ace5422aa0dbp+0, 0x1.93737b0cdc5e5p+0, 0x1.9c49182a3f090p+0, 0x1.a5503b23e255dp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0, 0x1.d5818dcfba487p+0, 0x1.dfc97337b9b5fp+0,
+    0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};
+
+__device__ __forceinline__ void exp_tab_stage(double* tab_sm /* 32 doubles */) {
+    if (threadIdx.x < 32) tab_sm[threadIdx.x] = c_exp2_32[threadIdx.x];
+}
+
+__device__ __forceinline__ double exp_tab(double x, const double* __restrict__ tab_sm) {
+    if (!(fabs(x) <= 708.0)) return exp(x);
+    const double MAGIC = 6755399441055744.0;                                  // 1.5 * 2^52: the sum's low word is rint(.) as an int
+    const double t = fma(x, 46.16624130844683, MAGIC);                        // 32 / ln 2
+    const int n = __double2loint(t);
+    const double nd = t - MAGIC;
+    double r = fma(nd, -0x1.62e42fefa0000p-6, x);                             // ln2/32, leading 37 bits: n * hi is exact
+    r = fma(nd, -0x1.cf79abc9e3b3ap-45, r);
+    double q = fma(r, 1.0 / 720.0, 1.0 / 120.0);
+    q = fma(q, r, 1.0 / 24.0);
+    q = fma(q, r, 1.0 / 6.0);
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    const double T = tab_sm[n & 31];
+    const double v = fma(T, q * r, T);                                        // in [0.98, 2.1)
+    return __hiloint2double(__double2hiint(v) + ((n >> 5) << 20), __double2loint(v));
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

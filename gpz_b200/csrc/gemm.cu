@@ -289,7 +289,7 @@ struct PEpi {
 
 template <int EPI, int WARPS_M>
 __global__ void __launch_bounds__(WARPS_M * 128, 1)
-tgemm_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int MP, int nk, int64_t n,
+tgemm_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int MP, int nk, int klast, int64_t n,
              TEpi te, PEpi pe) {
     constexpr int NTHR = WARPS_M * 128;
     constexpr int WM = TILE / WARPS_M, MT = WM / 8, NT = 4;
@@ -297,6 +297,7 @@ tgemm_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict
     double* As = reinterpret_cast<double*>(smem_raw);          // [STAGES][TILE][LDK]
     double* Bs = As + STAGES * TILE * LDK;                     // [STAGES][KSTEP][LDT]
     __shared__ double red[2][4][TILE];
+    __shared__ double exp_sm[32];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -304,6 +305,7 @@ tgemm_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict
     const int wm0 = (warp >> 2) * WM;
     const int wn0 = (warp & 3) * 32;
     const int ntn = MP / TILE;
+    if (EPI == 1) exp_tab_stage(exp_sm);              // visible after the first __syncthreads of the K loop
     const int ct = blockIdx.x % ntn;
     const int64_t rt = blockIdx.x / ntn;
     const int64_t i0 = rt * TILE;
@@ -351,8 +353,12 @@ tgemm_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict
         const int stage = kt % STAGES;
         const double* as = As + stage * TILE * LDK;
         const double* bs = Bs + stage * KSTEP * LDT;
+        // the last stage only runs the 4-deep K steps that hold non-zero operand columns (PHI build: q = 21 or 66 features,
+        // not a multiple of 16)
+        const int kend = (kt == nk - 1) ? klast : KSTEP / 4;
 #pragma unroll
         for (int kk = 0; kk < KSTEP / 4; ++kk) {
+            if (kk >= kend) break;
             const int kc = kk * 4 + t;
             double bf[NT];
 #pragma unroll
@@ -420,8 +426,8 @@ tgemm_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
                 const int64_t gj = j0 + wn0 + j * 8 + 2 * t;
-                double p0 = (gj < pe.m) ? (pe.plain ? acc[i][j][0] : exp(acc[i][j][0])) : 0.0;
-                double p1 = (gj + 1 < pe.m) ? (pe.plain ? acc[i][j][1] : exp(acc[i][j][1])) : 0.0;
+                double p0 = (gj < pe.m) ? (pe.plain ? acc[i][j][0] : exp_tab(acc[i][j][0], exp_sm)) : 0.0;
+                double p1 = (gj + 1 < pe.m) ? (pe.plain ? acc[i][j][1] : exp_tab(acc[i][j][1], exp_sm)) : 0.0;
                 if (pe.ycol != nullptr && ok) {
                     if (gj == pe.m) p0 = pe.ycol[gi];
                     if (gj + 1 == pe.m) p1 = pe.ycol[gi];
@@ -460,7 +466,7 @@ tgemm_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict
 }
 
 template <int EPI, int WARPS_M>
-static int launch_tgemm(const double* A, int64_t lda, const double* B, int MP, int nk, int64_t n, const TEpi& te,
+static int launch_tgemm(const double* A, int64_t lda, const double* B, int MP, int nk, int klast, int64_t n, const TEpi& te,
                         const PEpi& pe, cudaStream_t st) {
     const size_t smem = sizeof(double) * (STAGES * TILE * LDK + STAGES * KSTEP * LDT);
     static PerDeviceOnce once;
@@ -472,7 +478,7 @@ static int launch_tgemm(const double* A, int64_t lda, const double* B, int MP, i
         set_error("tgemm: grid too large");
         return GPZ_ERR_USAGE;
     }
-    tgemm_kernel<EPI, WARPS_M><<<static_cast<unsigned>(nblk), WARPS_M * 128, smem, st>>>(A, lda, B, MP, nk, n, te, pe);
+    tgemm_kernel<EPI, WARPS_M><<<static_cast<unsigned>(nblk), WARPS_M * 128, smem, st>>>(A, lda, B, MP, nk, klast, n, te, pe);
     GPZ_KERNEL_CHECK();
     return GPZ_OK;
 }
@@ -483,20 +489,24 @@ int tgemm(const double* Phi, int64_t ld, const double* Sinv, int MP, int m, int6
     const int nk = static_cast<int>(round_up(m, KSTEP) / KSTEP);
     TEpi te{Phi, rw, H, accumulate, nupart, nu_ld, pred_aug != nullptr ? m : -1, pred_aug};
     PEpi pe{};
-    int rc = g_gemm_warps == 16 ? launch_tgemm<0, 4>(Phi, ld, Sinv, MP, nk, n, te, pe, st) : launch_tgemm<0, 2>(Phi, ld, Sinv, MP, nk, n, te, pe, st);
+    int rc = g_gemm_warps == 16 ? launch_tgemm<0, 4>(Phi, ld, Sinv, MP, nk, KSTEP / 4, n, te, pe, st) : launch_tgemm<0, 2>(Phi, ld, Sinv, MP, nk, KSTEP / 4, n, te, pe, st);
     if (!rc) ++*launches;
     return rc;
 }
 
-// PHI = exp(F W): F [n][ldf] row features (K = kq columns used, kq % 16 == 0), W [kq][MP] coefficients
-int phi_gemm(const double* F, int64_t ldf, int kq, const double* W, int MP, int m, int64_t n, double* Phi, int ndot,
+// PHI = exp(F W): F [n][ldf] row features, W [kq][MP] coefficients (kq % 16 == 0); only the first kvalid of the kq operand
+// columns / rows are non-zero, so the K loop stops at the 4-deep step that holds column kvalid - 1
+int phi_gemm(const double* F, int64_t ldf, int kq, int kvalid, const double* W, int MP, int m, int64_t n, double* Phi, int ndot,
              const double* vec0, const double* vec1, double* part0, double* part1, int64_t part_ld, const double* ycol,
              cudaStream_t st, int64_t* launches) {
     if (n <= 0) return GPZ_OK;
     TEpi te{};
     PEpi pe{m, Phi, ndot, {vec0, vec1}, {part0, part1}, part_ld, ycol};
-    int rc = g_gemm_warps != 8 ? launch_tgemm<1, 4>(F, ldf, W, MP, kq / KSTEP, n, te, pe, st)
-                                : launch_tgemm<1, 2>(F, ldf, W, MP, kq / KSTEP, n, te, pe, st);
+    if (kvalid < 1 || kvalid > kq) kvalid = kq;
+    const int nk = static_cast<int>(ceil_div(kvalid, KSTEP));
+    const int klast = static_cast<int>(ceil_div(kvalid - (nk - 1) * KSTEP, 4));
+    int rc = g_gemm_warps != 8 ? launch_tgemm<1, 4>(F, ldf, W, MP, nk, klast, n, te, pe, st)
+                                : launch_tgemm<1, 2>(F, ldf, W, MP, nk, klast, n, te, pe, st);
     if (!rc) ++*launches;
     return rc;
 }
@@ -510,7 +520,7 @@ int gemm_rows(const double* A, int64_t lda, int K, const double* B, int N, int64
     }
     TEpi te{};
     PEpi pe{N, C, 0, {nullptr, nullptr}, {nullptr, nullptr}, 0, nullptr, 1};
-    int rc = g_gemm_warps != 8 ? launch_tgemm<1, 4>(A, lda, B, N, K / KSTEP, n, te, pe, st) : launch_tgemm<1, 2>(A, lda, B, N, K / KSTEP, n, te, pe, st);
+    int rc = g_gemm_warps != 8 ? launch_tgemm<1, 4>(A, lda, B, N, K / KSTEP, KSTEP / 4, n, te, pe, st) : launch_tgemm<1, 2>(A, lda, B, N, K / KSTEP, KSTEP / 4, n, te, pe, st);
     if (!rc) ++*launches;
     return rc;
 }

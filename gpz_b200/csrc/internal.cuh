@@ -98,7 +98,7 @@ int atb_general(const double* A, int64_t lda, int MP, const double* B, int64_t l
                 cudaStream_t st, int64_t* launches);
 int tgemm(const double* Phi, int64_t ld, const double* Sinv, int MP, int m, int64_t n, const double* rw, double* H,
           int accumulate, double* nupart, int64_t nu_ld, double* pred_aug, cudaStream_t st, int64_t* launches);
-int phi_gemm(const double* F, int64_t ldf, int kq, const double* W, int MP, int m, int64_t n, double* Phi, int ndot,
+int phi_gemm(const double* F, int64_t ldf, int kq, int kvalid, const double* W, int MP, int m, int64_t n, double* Phi, int ndot,
              const double* vec0, const double* vec1, double* part0, double* part1, int64_t part_ld, const double* ycol,
              cudaStream_t st, int64_t* launches);
 int gemm_rows(const double* A, int64_t lda, int K, const double* B, int N, int64_t n, double* C, cudaStream_t st, int64_t* launches);
@@ -191,6 +191,8 @@ int ozaki_tgemm(const double* Phi, int64_t ld, const int8_t* D8, const double* e
 namespace gpz {
 // ---- ozmma.cu: hand-written tcgen05 (cta_group::2, TMA, TMEM) digit-level GEMM with on-chip level folding
 bool ozmma_available();
+void ozmma_set_prefetch(int on);
+void ozmma_set_level_group(int g);   // 2 (default): two levels share their operand tiles; 1: one level at a time (A/B measurements)
 int ozmma_pairs();
 int64_t ozmma_partial_doubles(int rowsA, int rowsB, int lower, int nchunks, int pairs_limit);
 int ozmma_gemm_nt(const int8_t* A, const int64_t strA[3], int rowsA, const int8_t* B, const int64_t strB[3], int rowsB, int s, int emax,

@@ -25,17 +25,20 @@
 namespace gpz {
 namespace {
 
-constexpr int OM_STAGES = 8;
-constexpr int OM_A_BYTES = 128 * 128;                 // 128 rows x 128 K-bytes per CTA
-constexpr int OM_B_BYTES = 64 * 128;                  // this CTA's half of the 128 B rows
+constexpr int OM_STAGES = 6;
+constexpr int OM_A_BYTES = 128 * 128;                 // A digit tile: 128 rows x 128 K-bytes per CTA
+constexpr int OM_B_BYTES = 128 * 128;                 // B digit tile of a two-level step: 128 rows per CTA (a one-level step fills half of it)
 constexpr int OM_STAGE_BYTES = OM_A_BYTES + OM_B_BYTES;
 constexpr int OM_BAR_OFF = OM_STAGES * OM_STAGE_BYTES;
+// barrier block (8 bytes each): full[8] @0, empty[8] @64, tfull[4] @128, tempty[4] @160, tmem slot @192
+constexpr int OM_FULL = 0, OM_EMPTY = 64, OM_TFULL = 128, OM_TEMPTY = 160, OM_SLOT = 192;
 constexpr int OM_SMEM_BYTES = OM_BAR_OFF + 256 + 6144 + 1024;   // barriers + tmem slot, row sums, + slack for the 1024-byte alignment
 constexpr int OM_THREADS = 576;                       // warp 0: TMA, warp 1: MMA, warps 2..17: epilogue (4 lane quarters x 4 column groups)
-constexpr uint32_t OM_TMEM_COLS = 256;                // two 128-column int32 accumulators
+constexpr uint32_t OM_TMEM_COLS = 512;                // two regions of 256 columns = two levels each: one region multiplied, one folded
 // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D = S32, A = B = signed 8 bit, both K-major,
-// N = 128 (>>3 at bit 17), M = 256 (>>4 at bit 24)
-constexpr uint32_t OM_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
+// N = 128 or 256 (>>3 at bit 17), M = 256 (>>4 at bit 24)
+constexpr uint32_t OM_IDESC0 = (2u << 4) | (1u << 7) | (1u << 10) | ((256u >> 4) << 24);
+constexpr uint32_t OM_IDESC_N128 = OM_IDESC0 | ((128u >> 3) << 17), OM_IDESC_N256 = OM_IDESC0 | ((256u >> 3) << 17);
 
 struct OzmmaArgs {
     int s, emin, emax;        // digits per operand; levels emax, emax-1, .., emin are accumulated (weight 256^-(e-emin))
@@ -48,6 +51,8 @@ struct OzmmaArgs {
     int lower;                // tile list = tiles touching the lower triangle (Gram); else all tiles_m x tiles_n
     int mode;                 // 0: fp64 partial tiles, 1: T-GEMM epilogue, 2: PHI = exp(.) epilogue
     int mn_major;             // operands stored [k][row] (row index contiguous) instead of [row][k]
+    int lgroup;               // levels multiplied together: 2 (default, shared operand tiles) or 1 (one level at a time)
+    int prefetch;             // mode 1: prefetch the epilogue's PHI block into L2 (default 1; 0 for A/B measurements)
     uint64_t hintA, hintB;    // L2 eviction policy of the operand loads
     // mode 1
     const double* ea;         // [rows] row scales (including 256^-1 .. see ozaki.cu)
@@ -217,16 +222,27 @@ __device__ __forceinline__ void decode_tile(const OzmmaArgs& a, int tile, int& m
     }
 }
 
+// Schedule of one (work unit, K chunk): the levels are taken two at a time from the top, {emax, emax-1}, {emax-2, emax-3}, ..
+// (a last single level when their number is odd).  Inside a group, for every 128-byte K block, the A digits t are swept in
+// ascending order: A_t meets B_{eh-t} (level eh) and B_{el-t} (level el = eh-1).  Both products are ONE tcgen05.mma with
+// N = 256: CTA 0 of the pair holds the 128 rows of B_{eh-t}, CTA 1 those of B_{el-t} (with cta_group::2 each CTA supplies half
+// of the N extent), and the two levels' accumulators are the two 128-column halves of one 256-column TMEM region.  Against one
+// level at a time (N = 128, every digit pair fetching its own A tile) this halves the A traffic and the number of MMA, TMA and
+// barrier instructions per digit pair: that schedule sat on the L2 -> SM bandwidth (profiles/r01h: 57-66 % of the L2 peak at
+// 52 % tensor-pipe activity), and its single issuing thread was busy 60 % of the time (profiles/r02c).  Steps where only one of
+// the two levels has a partner digit (the ends of a sweep, the last single level) run as N = 128 into their half.
+// Requires emax <= s + 1 (every caller: products below 256^-s of row scale x column scale are dropped), so that a group's
+// first step is a two-level step and initialises both halves; lgroup = 1 selects one level at a time (all steps N = 128).
 template <int MNMAJOR>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OM_THREADS, 1)
-ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const OzmmaArgs a) {
+ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapB2,
+             const OzmmaArgs a) {
     extern __shared__ uint8_t om_smem_raw[];
     const uint32_t raw = smem_u32(om_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* gbase = om_smem_raw + (base - raw);
     const uint32_t bar0 = base + OM_BAR_OFF;
-    // full[i] = bar0 + 8 i (leader's are used), empty[i] = bar0 + 64 + 8 i, tfull[b] = bar0 + 128 + 8 b, tempty[b] = bar0 + 144 + 8 b
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + OM_BAR_OFF + 192);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + OM_BAR_OFF + OM_SLOT);
     double* rowsum_sm = reinterpret_cast<double*>(gbase + OM_BAR_OFF + 256);      // [2][3][128]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -234,12 +250,12 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     cluster_sync_all();                                   // both CTAs resident before the pair-wide TMEM allocation
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < OM_STAGES; ++i) {
-            mbar_init(bar0 + 8 * i, 2);                   // one arrive per CTA's producer (+ 2 x stage bytes of TMA)
-            mbar_init(bar0 + 64 + 8 * i, 1);              // one MMA commit
+            mbar_init(bar0 + OM_FULL + 8 * i, 2);         // one arrive per CTA's producer (+ the TMA bytes of both CTAs)
+            mbar_init(bar0 + OM_EMPTY + 8 * i, 1);        // one MMA commit
         }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(bar0 + 128 + 8 * b, 1);             // one MMA commit
-            mbar_init(bar0 + 144 + 8 * b, 32);            // 16 epilogue warps x 2 CTAs
+        for (int b = 0; b < 4; ++b) {
+            mbar_init(bar0 + OM_TFULL + 8 * b, 1);        // one MMA commit
+            mbar_init(bar0 + OM_TEMPTY + 8 * b, 32);      // 16 epilogue warps x 2 CTAs
         }
         fence_mbar_init();
     }
@@ -255,35 +271,45 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer: one elected lane runs the whole loop
         if (elect_one()) {
-            uint32_t it = 0;
-            const uint32_t full_leader0 = mapa_cta(bar0, 0);
+            uint32_t stage = 0, ph = 0;
+            const uint32_t full_leader0 = mapa_cta(bar0 + OM_FULL, 0);
             for (int u = pair; u < U; u += npairs) {
                 const int group = u / a.ntiles, tile = u - group * a.ntiles;
                 int mt, nt;
                 decode_tile(a, tile, mt, nt);
-                const int rowA = mt * 256 + static_cast<int>(rank) * 128, rowB = nt * 128 + static_cast<int>(rank) * 64;
+                const int rowA = mt * 256 + static_cast<int>(rank) * 128, rowB = nt * 128, rowBh = rowB + static_cast<int>(rank) * 64;
                 const int c1 = min(a.nchunks, (group + 1) * a.gchunks);
                 for (int chunk = group * a.gchunks; chunk < c1; ++chunk)
-                    for (int e = a.emax; e >= a.emin; --e) {
-                        const int tlo = max(1, e - a.s), thi = min(a.s, e - 1);
-                        for (int t = tlo; t <= thi; ++t) {
-                            const int uu = e - t;
-                            for (int kb = 0; kb < a.kblocks; ++kb, ++it) {
-                                const uint32_t stage = it % OM_STAGES, ph = (it / OM_STAGES) & 1u;
-                                mbar_wait(bar0 + 64 + 8 * stage, ph ^ 1u);
+                    for (int eh = a.emax; eh >= a.emin; eh -= a.lgroup) {
+                        const int el = eh - 1;
+                        const bool hasl = a.lgroup == 2 && el >= a.emin;
+                        const int t0 = max(1, (hasl ? el : eh) - a.s), t1 = min(a.s, eh - 1);
+                        for (int kb = 0; kb < a.kblocks; ++kb)
+                            for (int t = t0; t <= t1; ++t) {
+                                const int uh = eh - t, ul = el - t;
+                                const bool vh = uh <= a.s, vl = hasl && ul >= 1;
+                                const bool dual = vh && vl;
+                                mbar_wait(bar0 + OM_EMPTY + 8 * stage, ph ^ 1u);
+                                const uint32_t fl = full_leader0 + 8 * stage;
                                 const uint32_t sA = base + stage * OM_STAGE_BYTES, sB = sA + OM_A_BYTES;
-                                const uint32_t full_leader = full_leader0 + 8 * stage;
-                                if (rank == 0) mbar_arrive_expect_tx(bar0 + 8 * stage, 2 * OM_STAGE_BYTES);
-                                else mbar_arrive_cluster(full_leader);
-                                if (MNMAJOR) {
-                                    tma_load_4d(&mapA, sA, full_leader, rowA, t - 1, kb * 128, chunk, a.hintA);
-                                    tma_load_4d(&mapB, sB, full_leader, rowB, uu - 1, kb * 128, chunk, a.hintB);
-                                } else {
-                                    tma_load_4d(&mapA, sA, full_leader, kb * 128, t - 1, rowA, chunk, a.hintA);
-                                    tma_load_4d(&mapB, sB, full_leader, kb * 128, uu - 1, rowB, chunk, a.hintB);
+                                if (rank == 0) mbar_arrive_expect_tx(bar0 + OM_FULL + 8 * stage, dual ? 2 * OM_STAGE_BYTES : 2 * OM_A_BYTES + OM_B_BYTES);
+                                else mbar_arrive_cluster(fl);
+                                if (MNMAJOR) tma_load_4d(&mapA, sA, fl, rowA, t - 1, kb * 128, chunk, a.hintA);
+                                else tma_load_4d(&mapA, sA, fl, kb * 128, t - 1, rowA, chunk, a.hintA);
+                                if (dual) {                 // this CTA's 128 rows of the N = 256 operand: CTA 0 level eh, CTA 1 level el
+                                    const int dg = (rank == 0 ? uh : ul) - 1;
+                                    if (MNMAJOR) tma_load_4d(&mapB2, sB, fl, rowB, dg, kb * 128, chunk, a.hintB);
+                                    else tma_load_4d(&mapB2, sB, fl, kb * 128, dg, rowB, chunk, a.hintB);
+                                } else {                    // this CTA's 64 rows of the N = 128 operand
+                                    const int dg = (vh ? uh : ul) - 1;
+                                    if (MNMAJOR) tma_load_4d(&mapB, sB, fl, rowBh, dg, kb * 128, chunk, a.hintB);
+                                    else tma_load_4d(&mapB, sB, fl, kb * 128, dg, rowBh, chunk, a.hintB);
+                                }
+                                if (++stage == OM_STAGES) {
+                                    stage = 0;
+                                    ph ^= 1u;
                                 }
                             }
-                        }
                     }
             }
         }
@@ -294,55 +320,79 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             // smem matrix descriptors (cute/arch/mma_sm100_desc.hpp SmemDescriptor: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1
             // <<46 | layout <<61; the values follow deep_gemm's make_umma_desc).  K-major, 128B swizzle: rows of 128 K-bytes, 8-row
             // groups 1024 B apart (SBO), LBO unused (1), 32 K-bytes = +32 B.  MN-major: the tile is [128 k-rows][W bytes of the row
-            // index], W = 128 (A, SWIZZLE_128B = 2) or 64 (B, SWIZZLE_64B = 4: each CTA of the pair holds 64 of the 128 N columns);
-            // 8-k-row groups 8 W bytes apart (SBO), LBO = stride between W-wide atoms (one atom here), 32 K-rows = +32 W bytes.
-            // All immediates, so the loop below is ~25 instructions
+            // index], W = 128 (A and the two-level B, SWIZZLE_128B = 2) or 64 (one-level B, SWIZZLE_64B = 4: each CTA of the pair
+            // holds 64 of the 128 N columns); 8-k-row groups 8 W bytes apart (SBO), LBO = stride between W-wide atoms (one atom
+            // here), 32 K-rows = +32 W bytes.
             constexpr uint32_t VER = 1u << 14;
             constexpr uint32_t HI_A = (1024u >> 4) | VER | (2u << 29);
             constexpr uint32_t HI_B = MNMAJOR ? ((512u >> 4) | VER | (4u << 29)) : HI_A;
             constexpr uint32_t LO_A = MNMAJOR ? (((128u * 128u) >> 4) << 16) : (1u << 16);
             constexpr uint32_t LO_B = MNMAJOR ? (((128u * 64u) >> 4) << 16) : (1u << 16);
             constexpr uint32_t KA = MNMAJOR ? ((32u * 128u) >> 4) : (32u >> 4), KB = MNMAJOR ? ((32u * 64u) >> 4) : (32u >> 4);
-            constexpr uint32_t IDESC = OM_IDESC | (MNMAJOR ? ((1u << 15) | (1u << 16)) : 0u);
+            constexpr uint32_t TR = MNMAJOR ? ((1u << 15) | (1u << 16)) : 0u;
+            constexpr uint32_t IDESC1 = OM_IDESC_N128 | TR, IDESC2 = OM_IDESC_N256 | TR;
             constexpr uint32_t STG = OM_STAGE_BYTES >> 4;
-            const uint32_t alo0 = desc_lo(base, LO_A), blo0 = desc_lo(base + OM_A_BYTES, LO_B);
-            uint32_t L = 0, stage = 0, ph = 0;
-            uint32_t alo = alo0, blo = blo0, fullbar = bar0, emptybar = bar0 + 64;
+            const uint32_t a0 = (base >> 4) & 0x3FFFu;
+            uint32_t G = 0, ubits = 0, stage = 0, ph = 0, aoff = a0, fullbar = bar0 + OM_FULL, emptybar = bar0 + OM_EMPTY;
             for (int u = pair; u < U; u += npairs) {
                 const int group = u / a.ntiles;
-                const int nlev = (min(a.nchunks, (group + 1) * a.gchunks) - group * a.gchunks) * (a.emax - a.emin + 1);
-                for (int lv = 0, e = a.emax; lv < nlev; ++lv, ++L, e = (e == a.emin ? a.emax : e - 1)) {
-                    const uint32_t buf = L & 1u;
-                    mbar_wait(bar0 + 144 + 8 * buf, ((L >> 1) & 1u) ^ 1u);       // epilogue has drained this accumulator
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + buf * 128u;
-                    const int nkb = (min(a.s, e - 1) - max(1, e - a.s) + 1) * a.kblocks;
-                    uint32_t acc = 0;
-                    for (int j = 0; j < nkb; ++j) {
-                        mbar_wait(fullbar, ph);                                   // both CTAs' tiles have landed
+                const int nch = min(a.nchunks, (group + 1) * a.gchunks) - group * a.gchunks;
+                for (int ch = 0; ch < nch; ++ch)
+                    for (int eh = a.emax; eh >= a.emin; eh -= a.lgroup, ++G) {
+                        const int el = eh - 1;
+                        const bool hasl = a.lgroup == 2 && el >= a.emin;
+                        const int t0 = max(1, (hasl ? el : eh) - a.s), t1 = min(a.s, eh - 1);
+                        // accumulator b = 2 (G & 1) + half; ubits bit b = parity of the number of times b has been used (a
+                        // single-level group leaves its region's second half unused, so the halves need their own counts)
+                        const uint32_t reg = G & 1u, bh = 2u * reg, bl = bh + 1u;
+                        mbar_wait(bar0 + OM_TEMPTY + 8 * bh, ((ubits >> bh) & 1u) ^ 1u);      // the epilogue has drained it
+                        if (hasl) mbar_wait(bar0 + OM_TEMPTY + 8 * bl, ((ubits >> bl) & 1u) ^ 1u);
                         tc_fence_after();
-                        umma_i8_2cta(d_tmem, alo, HI_A, blo, HI_B, IDESC, acc);   // 4 x 32 K-bytes of the stage
-                        umma_i8_2cta(d_tmem, alo + KA, HI_A, blo + KB, HI_B, IDESC, 1u);
-                        umma_i8_2cta(d_tmem, alo + 2 * KA, HI_A, blo + 2 * KB, HI_B, IDESC, 1u);
-                        umma_i8_2cta(d_tmem, alo + 3 * KA, HI_A, blo + 3 * KB, HI_B, IDESC, 1u);
-                        acc = 1u;
-                        umma_commit_pair(emptybar);                               // frees the smem stage in both CTAs
-                        ++stage;
-                        alo += STG;
-                        blo += STG;
-                        fullbar += 8;
-                        emptybar += 8;
-                        if (stage == OM_STAGES) {
-                            stage = 0;
-                            ph ^= 1u;
-                            alo = alo0;
-                            blo = blo0;
-                            fullbar = bar0;
-                            emptybar = bar0 + 64;
+                        const uint32_t dreg = tmem_base + reg * 256u;
+                        uint32_t acch = 0, accl = 0;
+                        for (int kb = 0; kb < a.kblocks; ++kb)
+                            for (int t = t0; t <= t1; ++t) {
+                                const bool vh = eh - t <= a.s, vl = hasl && el - t >= 1;
+                                mbar_wait(fullbar, ph);                             // both CTAs' tiles have landed
+                                tc_fence_after();
+                                const uint32_t alo = aoff | LO_A;
+                                if (vh && vl) {
+                                    const uint32_t blo = (aoff + (OM_A_BYTES >> 4)) | LO_A;    // 128 rows per CTA: A's layout
+                                    umma_i8_2cta(dreg, alo, HI_A, blo, HI_A, IDESC2, acch);     // 4 x 32 K-bytes of the stage
+                                    umma_i8_2cta(dreg, alo + KA, HI_A, blo + KA, HI_A, IDESC2, 1u);
+                                    umma_i8_2cta(dreg, alo + 2 * KA, HI_A, blo + 2 * KA, HI_A, IDESC2, 1u);
+                                    umma_i8_2cta(dreg, alo + 3 * KA, HI_A, blo + 3 * KA, HI_A, IDESC2, 1u);
+                                    acch = accl = 1u;
+                                } else {
+                                    const uint32_t blo = (aoff + (OM_A_BYTES >> 4)) | LO_B;
+                                    const uint32_t d1 = vh ? dreg : dreg + 128u, acc1 = vh ? acch : accl;
+                                    umma_i8_2cta(d1, alo, HI_A, blo, HI_B, IDESC1, acc1);
+                                    umma_i8_2cta(d1, alo + KA, HI_A, blo + KB, HI_B, IDESC1, 1u);
+                                    umma_i8_2cta(d1, alo + 2 * KA, HI_A, blo + 2 * KB, HI_B, IDESC1, 1u);
+                                    umma_i8_2cta(d1, alo + 3 * KA, HI_A, blo + 3 * KB, HI_B, IDESC1, 1u);
+                                    if (vh) acch = 1u;
+                                    else accl = 1u;
+                                }
+                                umma_commit_pair(emptybar);                         // frees the smem stage in both CTAs
+                                ++stage;
+                                aoff += STG;
+                                fullbar += 8;
+                                emptybar += 8;
+                                if (stage == OM_STAGES) {
+                                    stage = 0;
+                                    ph ^= 1u;
+                                    aoff = a0;
+                                    fullbar = bar0 + OM_FULL;
+                                    emptybar = bar0 + OM_EMPTY;
+                                }
+                            }
+                        umma_commit_pair(bar0 + OM_TFULL + 8 * bh);                 // levels finished -> epilogue warps
+                        ubits ^= 1u << bh;
+                        if (hasl) {
+                            umma_commit_pair(bar0 + OM_TFULL + 8 * bl);
+                            ubits ^= 1u << bl;
                         }
                     }
-                    umma_commit_pair(bar0 + 128 + 8 * buf);                       // level finished -> epilogue warps
-                }
             }
         }
         __syncwarp();
@@ -352,18 +402,39 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         const int cg = (warp - 2) >> 2;         // which 32 of the 128 accumulator columns
         const int rloc = q * 32 + lane;         // row inside this CTA's 128 rows
         double st[32];
-        uint32_t L = 0;
-        const uint32_t tempty_leader0 = mapa_cta(bar0 + 144, 0);
+        uint32_t G = 0, half = 0, ebits = 0;      // ebits: per accumulator, parity of its number of uses (as in the MMA issuer)
+        const uint32_t tempty_leader0 = mapa_cta(bar0 + OM_TEMPTY, 0);
         for (int u = pair; u < U; u += npairs) {
             __syncwarp();
             const int group = u / a.ntiles, tile = u - group * a.ntiles;
 #pragma unroll
             for (int c = 0; c < 32; ++c) st[c] = 0.0;
             const int nlev = (min(a.nchunks, (group + 1) * a.gchunks) - group * a.gchunks) * (a.emax - a.emin + 1);
-            for (int lv = 0, e = a.emax; lv < nlev; ++lv, ++L, e = (e == a.emin ? a.emax : e - 1)) {
-                const uint32_t buf = L & 1u;
-                mbar_wait(bar0 + 128 + 8 * buf, (L >> 1) & 1u);
+            int mt, nt;
+            decode_tile(a, tile, mt, nt);
+            const int lv_prefetch = nlev > 5 ? nlev - 5 : 0;
+            for (int lv = 0, e = a.emax; lv < nlev; ++lv, e = (e == a.emin ? a.emax : e - 1)) {
+                if (a.mode == 1 && a.prefetch && lv == lv_prefetch) {
+                    // the T-GEMM epilogue multiplies by this warp's 32 x 32 block of PHI: pull it into L2 while the last levels are
+                    // still being multiplied (r02e capture: those loads, straight from HBM, were half of all stall samples and
+                    // kept the epilogue warps -- and through the TMEM hand-shake the tensor pipe -- waiting)
+                    const int64_t gr = static_cast<int64_t>(mt) * 256 + static_cast<int64_t>(rank) * 128 + q * 32 + lane;
+                    if (gr < a.rows) {
+                        const double* pp = a.Phi + gr * a.ld + nt * 128 + cg * 32;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(pp));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + 16));
+                    }
+                }
+                // level e is half `half` of group G (the MMA issuer's numbering): TMEM region G & 1, columns half * 128
+                const uint32_t buf = 2u * (G & 1u) + half;
+                mbar_wait(bar0 + OM_TFULL + 8 * buf, (ebits >> buf) & 1u);
+                ebits ^= 1u << buf;
                 tc_fence_after();
+                if (a.lgroup == 2 && half == 0u && e > a.emin) half = 1u;
+                else {
+                    half = 0u;
+                    ++G;
+                }
                 const double wgt = __longlong_as_double(static_cast<long long>(1023 - 8 * (e - a.emin)) << 52);   // 256^-(e-emin)
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 128u + static_cast<uint32_t>(cg * 32);
 #pragma unroll
@@ -378,8 +449,6 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(tempty_leader0 + 8 * buf);
             }
-            int mt, nt;
-            decode_tile(a, tile, mt, nt);
             // Transpose the warp's 32 x 32 block in registers (5 butterfly stages of shuffles): before, lane = row and st[c] =
             // column c; after, lane = column and st[r] = row r.  Every global access below is then one 256-byte row segment
             // per warp instruction instead of 32 rows x 16 bytes.
@@ -571,8 +640,12 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
+int g_lgroup = 2, g_prefetch = 1;
+
 void set_operand_layout(OzmmaArgs& a, int mn_major) {
     a.mn_major = mn_major;
+    a.lgroup = g_lgroup;
+    a.prefetch = g_prefetch;
     a.hintA = a.hintB = OM_EVICT_NORMAL;
 }
 
@@ -645,9 +718,9 @@ int count_tiles(int tiles_m, int tiles_n, int lower) {
     return t;
 }
 
-int launch(const CUtensorMap& mA, const CUtensorMap& mB, const OzmmaArgs& a, int npairs, cudaStream_t st) {
-    if (a.mn_major) ozmma_kernel<1><<<dim3(static_cast<unsigned>(2 * npairs)), dim3(OM_THREADS), OM_SMEM_BYTES, st>>>(mA, mB, a);
-    else ozmma_kernel<0><<<dim3(static_cast<unsigned>(2 * npairs)), dim3(OM_THREADS), OM_SMEM_BYTES, st>>>(mA, mB, a);
+int launch(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mB2, const OzmmaArgs& a, int npairs, cudaStream_t st) {
+    if (a.mn_major) ozmma_kernel<1><<<dim3(static_cast<unsigned>(2 * npairs)), dim3(OM_THREADS), OM_SMEM_BYTES, st>>>(mA, mB, mB2, a);
+    else ozmma_kernel<0><<<dim3(static_cast<unsigned>(2 * npairs)), dim3(OM_THREADS), OM_SMEM_BYTES, st>>>(mA, mB, mB2, a);
     GPZ_KERNEL_CHECK();
     return GPZ_OK;
 }
@@ -655,6 +728,9 @@ int launch(const CUtensorMap& mA, const CUtensorMap& mB, const OzmmaArgs& a, int
 }  // namespace
 
 bool ozmma_available() { return encode_fn() != nullptr; }
+
+void ozmma_set_level_group(int g) { g_lgroup = g == 1 ? 1 : 2; }
+void ozmma_set_prefetch(int on) { g_prefetch = on != 0; }
 
 int ozmma_pairs() { return resident_pairs(); }
 
@@ -701,12 +777,13 @@ int ozmma_gemm_nt(const int8_t* A, const int64_t strA[3], int rowsA, const int8_
         return GPZ_ERR_CUDA;
     }
     if (pairs_limit > 0 && pairs_limit < np) np = pairs_limit;
-    CUtensorMap mA, mB;
+    CUtensorMap mA, mB, mB2;
     const int64_t dA[4] = {kchunk, s, rowsA, nchunks}, dB[4] = {kchunk, s, rowsB, nchunks};
     const int64_t tA[4] = {rowsA, s, kchunk, nchunks}, tB[4] = {rowsB, s, kchunk, nchunks};
     int rc;
     if ((rc = make_map(&mA, A, mn_major ? tA : dA, strA, 128, mn_major))) return rc;
     if ((rc = make_map(&mB, B, mn_major ? tB : dB, strB, 64, mn_major))) return rc;
+    if ((rc = make_map(&mB2, B, mn_major ? tB : dB, strB, 128, mn_major))) return rc;
     OzmmaArgs a = {};
     set_operand_layout(a, mn_major);
     a.s = s;
@@ -721,7 +798,8 @@ int ozmma_gemm_nt(const int8_t* A, const int64_t strA[3], int rowsA, const int8_
     a.lower = lower;
     a.mode = 0;
     a.partial = partial;
-    if ((rc = launch(mA, mB, a, np, st))) return rc;
+    if (emax > s + 1) a.lgroup = 1;                // a group's first step must be a two-level step (see ozmma_kernel)
+    if ((rc = launch(mA, mB, mB2, a, np, st))) return rc;
     dim3 g(static_cast<unsigned>(ceil_div(rowsB, 256)), static_cast<unsigned>(rowsA));
     ozmma_reduce_kernel<<<g, 256, 0, st>>>(partial, a.ngroups, a.ntiles, a.tiles_n, lower, rowsA, rowsB, sr, sc, scale, accumulate, out,
                                            ldo);
@@ -744,12 +822,13 @@ int ozmma_tgemm(const int8_t* A8, const int8_t* B8, int MP, int s, int emax, int
         set_error("ozmma: cannot configure the tcgen05 kernel: %s", cudaGetErrorString(cudaGetLastError()));
         return GPZ_ERR_CUDA;
     }
-    CUtensorMap mA, mB;
+    CUtensorMap mA, mB, mB2;
     const int64_t dA[4] = {MP, s, rows, 1}, sA[3] = {MP, static_cast<int64_t>(s) * MP, round_up(rows * s * MP, 16)};
     const int64_t dB[4] = {MP, s, MP, 1}, sB[3] = {MP, static_cast<int64_t>(s) * MP, static_cast<int64_t>(s) * MP * MP};
     int rc;
     if ((rc = make_map(&mA, A8, dA, sA, 128))) return rc;
     if ((rc = make_map(&mB, B8, dB, sB, 64))) return rc;
+    if ((rc = make_map(&mB2, B8, dB, sB, 128))) return rc;
     OzmmaArgs a = {};
     set_operand_layout(a, 0);
     a.hintB = OM_EVICT_LAST;          // the iSigma digits are read by every tile
@@ -776,7 +855,7 @@ int ozmma_tgemm(const int8_t* A8, const int8_t* B8, int MP, int s, int emax, int
     a.nu_ld = nu_ld;
     a.aug_col = aug_col;
     a.pred = pred;
-    if ((rc = launch(mA, mB, a, np, st))) return rc;
+    if ((rc = launch(mA, mB, mB2, a, np, st))) return rc;
     if (launches) ++*launches;
     return GPZ_OK;
 }
@@ -796,12 +875,13 @@ int ozmma_phi(const int8_t* FD8, const double* eaF, const int8_t* WD8, const dou
         set_error("ozmma: cannot configure the tcgen05 kernel: %s", cudaGetErrorString(cudaGetLastError()));
         return GPZ_ERR_CUDA;
     }
-    CUtensorMap mA, mB;
+    CUtensorMap mA, mB, mB2;
     const int64_t dA[4] = {128, s, rows, 1}, sA[3] = {128, static_cast<int64_t>(s) * 128, round_up(rows * s * 128, 16)};
     const int64_t dB[4] = {128, s, MP, 1}, sB[3] = {128, static_cast<int64_t>(s) * 128, static_cast<int64_t>(s) * 128 * MP};
     int rc;
     if ((rc = make_map(&mA, FD8, dA, sA, 128))) return rc;
     if ((rc = make_map(&mB, WD8, dB, sB, 64))) return rc;
+    if ((rc = make_map(&mB2, WD8, dB, sB, 128))) return rc;
     OzmmaArgs a = {};
     set_operand_layout(a, 0);
     a.hintB = OM_EVICT_LAST;
@@ -829,7 +909,7 @@ int ozmma_phi(const int8_t* FD8, const double* eaF, const int8_t* WD8, const dou
     a.part0 = part0;
     a.part1 = part1;
     a.nu_ld = part_ld;
-    if ((rc = launch(mA, mB, a, np, st))) return rc;
+    if ((rc = launch(mA, mB, mB2, a, np, st))) return rc;
     if (launches) ++*launches;
     return GPZ_OK;
 }

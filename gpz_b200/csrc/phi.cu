@@ -437,7 +437,7 @@ int phi_build(const Params& P, const RowData& R, int64_t r0, int64_t r1, double*
                                R.phi_digits, rows, R.WD8, R.ebW, Phi != nullptr ? Phi + (s0 - r0) * P.MP : nullptr, dots.n, dots.vec[0],
                                dots.vec[1], p0, p1, rows, R.ycol != nullptr ? R.ycol + s0 : nullptr, R.flag, st, launches);
             else
-                rc = phi_gemm(R.F + s0 * P.QP, P.QP, P.KQ, P.Wc + static_cast<int64_t>(pat) * P.KQ * P.MP, P.MP, P.m, rows,
+                rc = phi_gemm(R.F + s0 * P.QP, P.QP, P.KQ, P.q, P.Wc + static_cast<int64_t>(pat) * P.KQ * P.MP, P.MP, P.m, rows,
                               Phi != nullptr ? Phi + (s0 - r0) * P.MP : nullptr, dots.n, dots.vec[0], dots.vec[1], p0, p1, rows,
                               R.ycol != nullptr ? R.ycol + s0 : nullptr, st, launches);
             if (rc) return rc;
@@ -477,7 +477,7 @@ int phi_build(const Params& P, const RowData& R, int64_t r0, int64_t r1, double*
         const int KQ = gc_feature_width(P.d), ntn = P.MP / TILE;
         double* p0 = dot_scratch;
         double* p1 = dot_scratch + static_cast<int64_t>(ntn) * rows;
-        if ((rc = phi_gemm(R.gcF, KQ, KQ, R.gcW, P.MP, P.m, rows, Phi, dots.n, dots.vec[0], dots.vec[1], p0, p1, rows, nullptr, st, launches)))
+        if ((rc = phi_gemm(R.gcF, KQ, KQ, 1 + P.d + P.d * (P.d + 1) / 2, R.gcW, P.MP, P.m, rows, Phi, dots.n, dots.vec[0], dots.vec[1], p0, p1, rows, nullptr, st, launches)))
             return rc;
         for (int q = 0; q < dots.n; ++q) {
             sum_parts_kernel<<<static_cast<unsigned>(ceil_div(rows, 256)), 256, 0, st>>>(q == 0 ? p0 : p1, ntn, rows, rows, dots.out[q] + r0);

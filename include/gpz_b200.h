@@ -195,6 +195,10 @@ int64_t gpz_graph_replays(const gpz_ctx* ctx);  /* evaluations replayed as one C
  * When the last evaluation was a CUDA-graph replay, [5] is the time of that replay and the phases are those of the
  * last evaluation that ran as plain launches.                                                                  */
 int gpz_last_timing(gpz_ctx* ctx, double ms[12]);
+/* device time (ms) of single kernels of the last evaluation that ran as plain launches, first row chunk; -1 = not run:
+ * [0] PHI build (the PHI kernel + the ordered sum of its row-dot partials)   [1] digit extraction of PHI
+ * [2] Gram digit GEMM + its fixed-order reduce   [3] moment GEMM of the back-projection (dPHI' F)             */
+int gpz_kernel_timing(gpz_ctx* ctx, double ms[4]);
 int gpz_set_option(gpz_ctx* ctx, const char* name, double value);
 
 #ifdef __cplusplus

@@ -1,5 +1,6 @@
-/* Minimal declarations of the MEX C API -- ONLY so that matlab/gpz_b200_mex.cpp can be syntax-checked in a
- * container without MATLAB (tests/test_abi.py).  Not a MATLAB header; nothing links against it. */
+/* Minimal declarations of the MEX C API -- the part matlab/gpz_b200_mex.cpp uses -- so that the gateway can be compiled and,
+ * linked with the mock implementation in mex_mock.cpp, EXECUTED in a container without MATLAB (tests/test_mex_gateway.py).
+ * Not a MATLAB header. */
 #ifndef MEX_STUB_H
 #define MEX_STUB_H
 #include <stddef.h>
@@ -31,5 +32,6 @@ int mexPrintf(const char*, ...);
 int mexEvalString(const char*);
 void mexLock(void);
 int mexAtExit(void (*)(void));
+void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]);   /* as MATLAB's mex.h declares it: C linkage */
 }
 #endif
