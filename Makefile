@@ -21,7 +21,7 @@ build/%.o: gpz_b200/csrc/%.cu $(HDR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; false)
 
 $(LIB): $(OBJ)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -ldl
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -ldl -lpthread
 
 clean:
 	rm -rf build $(LIB) $(HARNESS)

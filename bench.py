@@ -479,6 +479,51 @@ def run_gpu(args):
     return 0
 
 
+def run_single_process(args):
+    """The same metric through gpz_create_multi / gpz_multi_eval: ONE process, one caller thread, N GPUs (the way one MATLAB
+    interpreter would drive them) -- no torchrun.  Host theta in, host (f, g, stats) out every step, so the
+    whole line is an end-to-end number; the per-rank device times of the last evaluation are reported beside it."""
+    import torch
+
+    from gpz_b200 import _lib as L
+    N = args.gpus
+    if torch.cuda.device_count() < N:
+        raise SystemExit(f"--single-process --gpus {N}: only {torch.cuda.device_count()} device(s) visible")
+    name = args.workload
+    n, d, m, method, wex = WORKLOADS[name]
+    if wex.get("gpus"):
+        raise SystemExit("--single-process takes the strong-scaling workloads (one host data set split inside the library)")
+    n, d, m, method, X, Y, theta0 = make_problem(name)
+    t0 = time.perf_counter()
+    mc = L.MultiContext(L.make_model(d, 1, m, method, True), X, Y, ngpus=N)
+    upload_s = time.perf_counter() - t0
+    W, K = args.warmup, args.steps
+    ths = thetas_for(theta0, W + K)
+    for i in range(W):
+        mc.eval(ths[i])
+    sampler = ClockSampler(0)
+    sampler.start()
+    t0 = time.perf_counter()
+    for i in range(K):
+        f, g, st = mc.eval(ths[W + i])
+    sec = (time.perf_counter() - t0) / K
+    clocks = sampler.stop()
+    ranks = [mc.rank_timing(r) for r in range(N)]
+    p = int(theta0.size)
+    line = {"metric": METRIC, "value": 1.0 / sec, "unit": "evals/s", "n_gpus": N, "steps": K, "warmup": W, "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "mode": "single-process: gpz_create_multi, one caller thread, one worker thread + NCCL rank per device",
+            "config": {"workload": workload_desc(name, n, d, m, method), "n_total": int(n), "dataset_upload_s": round(upload_s, 3),
+                       "theta_len": p, "timing": "host wall clock around gpz_multi_eval (blocking): theta H2D and f/g/stats D2H included"},
+            "e2e": {"value": 1.0 / sec, "unit": "evals/s", "h2d_bytes_per_step": 8 * p * N, "d2h_bytes_per_step": 8 * (p + 5) * N,
+                    "ms_per_step": sec * 1e3},
+            "clocks": clocks, "rank_device_ms": [round(float(r["total"]), 3) for r in ranks],
+            "check": {"nlogML_last": f, "trainRMSE": float(st["trainRMSE"])}}
+    print(json.dumps(line), flush=True)
+    mc.close()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -490,11 +535,14 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--valid-frac", type=float, default=0.1, help="validation share of the extra 'with_validation' run (0 = skip)")
     ap.add_argument("--train-iters", type=int, default=5, help="iterations of the device-resident training loop reported in 'train' (0 = skip)")
+    ap.add_argument("--single-process", action="store_true", help="drive --gpus N devices from this one process (gpz_create_multi), no torchrun")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
         return run_reference(args)
+    if args.single_process:
+        return run_single_process(args)
     return run_gpu(args)
 
 

@@ -20,6 +20,8 @@ EXPORTS = [
     "gpz_predict", "gpz_inv_logdet", "gpz_dxy", "gpz_stream", "gpz_sync", "gpz_launch_count", "gpz_graph_replays",
     "gpz_last_timing", "gpz_kernel_timing", "gpz_set_option", "gpz_dgemm_nt",
     "gpz_dxy_colmean", "gpz_train", "gpz_minimize_dev", "gpz_train_default_options", "gpz_train_reason",
+    "gpz_create_multi", "gpz_destroy_multi", "gpz_multi_devices", "gpz_multi_ctx", "gpz_multi_eval", "gpz_multi_fit",
+    "gpz_multi_get_prior", "gpz_multi_set_option", "gpz_multi_train",
 ]
 
 
@@ -128,6 +130,26 @@ def load():
     lib.gpz_minimize_dev.restype = C.c_int
     lib.gpz_minimize_dev.argtypes = [C.c_int64, OBJECTIVE_DEV, C.c_void_p, C.POINTER(TrainOptions), _dp, _dp, _dp,
                                      TRAIN_CALLBACK, C.c_void_p, C.POINTER(TrainResult), C.c_int]
+    lib.gpz_create_multi.restype = C.c_int
+    lib.gpz_create_multi.argtypes = [C.POINTER(C.c_void_p), C.POINTER(GpzModel), C.c_int64, _dp, _dp, _dp, _dp, _u8p, _u8p, C.c_int,
+                                     C.POINTER(C.c_int)]
+    lib.gpz_destroy_multi.restype = None
+    lib.gpz_destroy_multi.argtypes = [C.c_void_p]
+    lib.gpz_multi_devices.restype = C.c_int
+    lib.gpz_multi_devices.argtypes = [C.c_void_p]
+    lib.gpz_multi_ctx.restype = C.c_void_p
+    lib.gpz_multi_ctx.argtypes = [C.c_void_p, C.c_int]
+    lib.gpz_multi_eval.restype = C.c_int
+    lib.gpz_multi_eval.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
+    lib.gpz_multi_fit.restype = C.c_int
+    lib.gpz_multi_fit.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
+    lib.gpz_multi_get_prior.restype = C.c_int
+    lib.gpz_multi_get_prior.argtypes = [C.c_void_p, _dp, _dp]
+    lib.gpz_multi_set_option.restype = C.c_int
+    lib.gpz_multi_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+    lib.gpz_multi_train.restype = C.c_int
+    lib.gpz_multi_train.argtypes = [C.c_void_p, C.POINTER(TrainOptions), _dp, _dp, _dp, TRAIN_CALLBACK, C.c_void_p,
+                                    C.POINTER(TrainResult)]
     _lib = lib
     return lib
 
@@ -274,6 +296,80 @@ class Context:
         ms = np.empty(4)
         check(self._lib.gpz_kernel_timing(self._h, ptr(ms)))
         return dict(phi_build=ms[0], digits=ms[1], gram_gemm=ms[2], moment_gemm=ms[3])
+
+
+class MultiContext:
+    """One caller thread driving several GPUs (gpz_create_multi): the same closure object as Context, rows split over
+    `ngpus` devices inside the library, NCCL allreduces inside every call."""
+
+    def __init__(self, model: GpzModel, X, Y, Psi=None, omega=None, training=None, validation=None, ngpus=2, devices=None):
+        lib = load()
+        X = f64(X)
+        n_all, d = X.shape
+        assert d == model.d
+        Y = f64(Y).reshape(n_all, -1, order="F")
+        self.model = model
+        self.p = int(lib.gpz_theta_len(C.byref(model)))
+        psi = None if Psi is None else f64(Psi)
+        om = None if omega is None else f64(omega).reshape(-1)
+        tr = None if training is None else np.ascontiguousarray(np.asarray(training).reshape(-1) != 0, dtype=np.uint8)
+        va = None if validation is None else np.ascontiguousarray(np.asarray(validation).reshape(-1) != 0, dtype=np.uint8)
+        dv = None if devices is None else (C.c_int * int(ngpus))(*[int(x) for x in devices])
+        h = C.c_void_p()
+        check(lib.gpz_create_multi(C.byref(h), C.byref(model), n_all, ptr(X), ptr(Y), ptr(psi), ptr(om),
+                                   None if tr is None else tr.ctypes.data_as(_u8p),
+                                   None if va is None else va.ctypes.data_as(_u8p), int(ngpus), dv))
+        self._h = h
+        self._lib = lib
+        self.ngpus = int(ngpus)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gpz_destroy_multi(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def set_option(self, name: str, value: float):
+        check(self._lib.gpz_multi_set_option(self._h, name.encode(), float(value)))
+
+    def eval(self, theta):
+        th = f64(theta).reshape(-1)
+        assert th.size == self.p, (th.size, self.p)
+        f = C.c_double()
+        g = np.empty(self.p)
+        st = np.empty(4)
+        check(self._lib.gpz_multi_eval(self._h, ptr(th), C.cast(C.byref(f), _dp), ptr(g), ptr(st)))
+        return f.value, g, dict(trainRMSE=st[0], trainLL=st[1], validRMSE=st[2], validLL=st[3])
+
+    def fit(self, theta):
+        th = f64(theta).reshape(-1)
+        m, k = self.model.m, self.model.k
+        nl = np.empty(k)
+        w = np.empty((m, k), order="F")
+        iS = np.empty((m, m, k), order="F")
+        check(self._lib.gpz_multi_fit(self._h, ptr(th), ptr(nl), ptr(w), ptr(iS)))
+        return nl, w, iS
+
+    def get_prior(self, theta):
+        th = f64(theta).reshape(-1)
+        pr = np.empty(self.model.m)
+        check(self._lib.gpz_multi_get_prior(self._h, ptr(th), ptr(pr)))
+        return pr
+
+    def train(self, theta, best_theta, best_valid, callback=None, **options):
+        th = f64(theta).reshape(-1).copy()
+        bt = f64(best_theta).reshape(-1).copy()
+        assert th.size == self.p and bt.size == self.p
+        return _run_train(lambda o, cb, bv, res: self._lib.gpz_multi_train(self._h, C.byref(o), ptr(th), ptr(bt), C.cast(C.byref(bv), _dp),
+                                                                           cb, None, C.byref(res)),
+                          th, bt, best_valid, callback, options)
+
+    def rank_timing(self, rank=0):
+        """gpz_last_timing of one device's context (all ranks block on the same two allreduces)."""
+        ms = np.empty(12)
+        check(self._lib.gpz_last_timing(self._lib.gpz_multi_ctx(self._h, rank), ptr(ms)))
+        return dict(phi=ms[0], gram=ms[1], solve=ms[2], tgemm=ms[3], backproj=ms[4], total=ms[5])
 
 
 def train_options(**kw) -> TrainOptions:

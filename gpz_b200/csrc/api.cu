@@ -2378,6 +2378,10 @@ int gpz_set_option(gpz_ctx* c, const char* name, double value) {
         g_gemm_warps = static_cast<int>(value);
         return GPZ_OK;
     }
+    if (strcmp(name, "ozaki_int_fold") == 0) {      // process-wide: integer folding of the lowest digit levels (ozmma.cu), 1 = default
+        ozmma_set_int_fold(static_cast<int>(value));
+        return GPZ_OK;
+    }
     if (strcmp(name, "ozaki_prefetch") == 0) {      // process-wide: L2 prefetch of the T-GEMM epilogue's PHI block (ozmma.cu), 1 = default
         ozmma_set_prefetch(static_cast<int>(value));
         return GPZ_OK;

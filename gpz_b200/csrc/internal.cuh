@@ -192,6 +192,7 @@ namespace gpz {
 // ---- ozmma.cu: hand-written tcgen05 (cta_group::2, TMA, TMEM) digit-level GEMM with on-chip level folding
 bool ozmma_available();
 void ozmma_set_prefetch(int on);
+void ozmma_set_int_fold(int on);     // 1 (default): lowest levels folded exactly in int64 where a unit is one level sweep
 void ozmma_set_level_group(int g);   // 2 (default): two levels share their operand tiles; 1: one level at a time (A/B measurements)
 int ozmma_pairs();
 int64_t ozmma_partial_doubles(int rowsA, int rowsB, int lower, int nchunks, int pairs_limit);

@@ -53,6 +53,8 @@ struct OzmmaArgs {
     int mn_major;             // operands stored [k][row] (row index contiguous) instead of [row][k]
     int lgroup;               // levels multiplied together: 2 (default, shared operand tiles) or 1 (one level at a time)
     int prefetch;             // mode 1: prefetch the epilogue's PHI block into L2 (default 1; 0 for A/B measurements)
+    int nint;                 // the first nint levels of a unit (emax, emax-1, ..) are folded EXACTLY in int64; the host picks the
+                              // largest count whose sum cannot overflow, and 0 when a unit folds more than one K chunk
     uint64_t hintA, hintB;    // L2 eviction policy of the operand loads
     // mode 1
     const double* ea;         // [rows] row scales (including 256^-1 .. see ozaki.cu)
@@ -202,6 +204,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// x * 2^e for x = 0 or a normal double, by exponent arithmetic on the integer pipe (results below 2^-1022 flush to zero):
+// while tcgen05.mma is running, fp64 instructions of the same SM issue ~20x slower than nominal (profiles/r02e: DFMA / DMUL
+// "math pipe throttle" was 60-70 % of all stall samples at 3.5 % fp64-pipe utilisation), so the epilogue avoids them where it can
+__device__ __forceinline__ double scale_pow2(double x, int e) {
+    const int hi = __double2hiint(x);
+    const int ex = ((hi >> 20) & 0x7ff);
+    const int nx = ex + e;
+    if (ex == 0 || nx <= 0) return 0.0;
+    if (nx >= 2047) return __hiloint2double((hi & 0x80000000) | 0x7ff00000, 0);
+    return __hiloint2double(hi + (e << 20), __double2loint(x));
+}
+// exponent of a power of two (the row / column scales the digit kernels of ozaki.cu produce are ldexp(1.0, .))
+__device__ __forceinline__ int pow2_exponent(double x) { return ((__double2hiint(x) >> 20) & 0x7ff) - 1023; }
 
 __device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lo_bits) { return ((smem_addr >> 4) & 0x3FFFu) | lo_bits; }
 
@@ -435,20 +451,40 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                     half = 0u;
                     ++G;
                 }
-                const double wgt = __longlong_as_double(static_cast<long long>(1023 - 8 * (e - a.emin)) << 52);   // 256^-(e-emin)
+                // running sum in units of the LOWEST level's (emax) least significant digit product: level e weighs 256^(emax-e).
+                // The first a.nint levels are added exactly as 64-bit integers (st[] holds the integer's bits), the others in fp64.
+                const int li = a.emax - e;
+                const bool ilev = li < a.nint;
+                if (li == a.nint && li > 0) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) st[c] = static_cast<double>(__double_as_longlong(st[c]));
+                }
+                const double wgt = __longlong_as_double(static_cast<long long>(1023 + 8 * li) << 52);          // 256^(emax-e)
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * 128u + static_cast<uint32_t>(cg * 32);
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                     uint32_t v[16];
                     tmem_ld16(taddr + hh * 16, v);
                     tmem_ld_wait();
+                    if (ilev) {
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) st[hh * 16 + c] = fma(static_cast<double>(static_cast<int>(v[c])), wgt, st[hh * 16 + c]);
+                        for (int c = 0; c < 16; ++c)
+                            st[hh * 16 + c] = __longlong_as_double(__double_as_longlong(st[hh * 16 + c]) +
+                                                                   (static_cast<long long>(static_cast<int>(v[c])) << (8 * li)));
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) st[hh * 16 + c] = fma(static_cast<double>(static_cast<int>(v[c])), wgt, st[hh * 16 + c]);
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(tempty_leader0 + 8 * buf);
             }
+            if (a.nint >= a.emax - a.emin + 1) {                    // every level was an integer level
+#pragma unroll
+                for (int c = 0; c < 32; ++c) st[c] = static_cast<double>(__double_as_longlong(st[c]));
+            }
+            const int efold = -8 * (a.emax - a.emin);               // back to units of the top level (emin): applied with the scales
             // Transpose the warp's 32 x 32 block in registers (5 butterfly stages of shuffles): before, lane = row and st[c] =
             // column c; after, lane = column and st[r] = row r.  Every global access below is then one 256-byte row segment
             // per warp instruction instead of 32 rows x 16 bytes.
@@ -470,7 +506,7 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                 double* out = a.partial + static_cast<int64_t>(u) * (256 * 128) + static_cast<int64_t>(static_cast<int>(rank) * 128 + q * 32) * 128 +
                               cg * 32 + lane;
 #pragma unroll
-                for (int r = 0; r < 32; ++r) st_stream1(out + r * 128, st[r]);
+                for (int r = 0; r < 32; ++r) st_stream1(out + r * 128, scale_pow2(st[r], efold));
                 continue;
             }
             // st[r] is overwritten by this lane's contribution to the row sum of row r (T-GEMM: PHI .* T; PHI build: PHI * vec0);
@@ -478,14 +514,14 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             double second = 0.0;
             const int ndots = a.mode == 2 ? a.ndot : 1;
             if (a.mode == 2) {
-                const double sb = a.eb[col];
+                const int exb = pow2_exponent(a.eb[col]) + efold;
                 const double v0 = a.ndot > 0 ? a.vec0[col] : 0.0;
                 double* pp = a.H != nullptr ? a.H + gi0 * a.ld + col : nullptr;
 #pragma unroll
                 for (int r = 0; r < 32; ++r) {
                     double p = 0.0;
                     if (gi0 + r < a.rows) {
-                        if (col < a.m) p = exp(st[r] * (a.ea[gi0 + r] * sb));
+                        if (col < a.m) p = exp(scale_pow2(st[r], pow2_exponent(a.ea[gi0 + r]) + exb));
                         else if (a.ycol != nullptr && col == a.m) p = a.ycol[gi0 + r];
                         if (pp != nullptr) pp[r * a.ld] = p;
                     }
@@ -517,11 +553,11 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 #pragma unroll
                 for (int r = 0; r < 32; ++r) st[r] *= v0;
             } else {
-                const double sb = a.eb[col];
+                const int exb = pow2_exponent(a.eb[col]) + efold;                          // column scale (a power of two) + fold units
                 const double* ph = a.Phi + gi0 * a.ld + col;
                 double* hp = a.H != nullptr ? a.H + gi0 * a.ld + col : nullptr;
                 const bool rowok = gi0 + lane < a.rows;
-                const double sa_l = rowok ? a.ea[gi0 + lane] : 0.0;                       // row scale / weight of row gi0 + lane
+                const int exa_l = rowok ? pow2_exponent(a.ea[gi0 + lane]) : 0;            // row scale (a power of two) / weight of row gi0 + lane
                 const double rw_l = (rowok && a.rw != nullptr) ? a.rw[gi0 + lane] : 1.0;
 #pragma unroll
                 for (int r0 = 0; r0 < 32; r0 += 8) {                                       // 8 rows at a time: loads first
@@ -531,7 +567,7 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 #pragma unroll
                     for (int r = 0; r < 8; ++r) {
                         const int rr = r0 + r;
-                        const double t = st[rr] * (__shfl_sync(0xffffffffu, sa_l, rr) * sb);
+                        const double t = scale_pow2(st[rr], __shfl_sync(0xffffffffu, exa_l, rr) + exb);
                         const double wr = __shfl_sync(0xffffffffu, rw_l, rr);
                         double h = phv[r] * t;
                         if (gi0 + rr < a.rows) {
@@ -640,7 +676,22 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-int g_lgroup = 2, g_prefetch = 1;
+int g_lgroup = 2, g_prefetch = 1, g_ifold = 1;
+
+// number of lowest levels (emax, emax-1, ..) whose exact integer sum sum_i L_i 256^i fits 62 bits, |L_e| <= pairs(e) K 2^14
+int int_levels(int s, int emin, int emax, int kchunk, int gchunks) {
+    if (!g_ifold || gchunks != 1) return 0;
+    double cum = 0.0;
+    int n = 0;
+    for (int e = emax; e >= emin; --e, ++n) {
+        const int li = emax - e;
+        const int pairs = (s < e - 1 ? s : e - 1) - (1 > e - s ? 1 : e - s) + 1;
+        const double b = static_cast<double>(pairs) * kchunk * 16384.0 * ldexp(1.0, 8 * li);
+        if (8 * li > 32 || cum + b >= ldexp(1.0, 62)) break;
+        cum += b;
+    }
+    return n;
+}
 
 void set_operand_layout(OzmmaArgs& a, int mn_major) {
     a.mn_major = mn_major;
@@ -731,6 +782,7 @@ bool ozmma_available() { return encode_fn() != nullptr; }
 
 void ozmma_set_level_group(int g) { g_lgroup = g == 1 ? 1 : 2; }
 void ozmma_set_prefetch(int on) { g_prefetch = on != 0; }
+void ozmma_set_int_fold(int on) { g_ifold = on != 0; }
 
 int ozmma_pairs() { return resident_pairs(); }
 
@@ -794,6 +846,7 @@ int ozmma_gemm_nt(const int8_t* A, const int64_t strA[3], int rowsA, const int8_
     a.ntiles = count_tiles((rowsA + 255) / 256, a.tiles_n, lower);
     a.nchunks = nchunks;
     a.gchunks = group_chunks(a.ntiles, nchunks, np);
+    a.nint = int_levels(s, 2, emax, kchunk, a.gchunks);
     a.ngroups = static_cast<int>(ceil_div(nchunks, a.gchunks));
     a.lower = lower;
     a.mode = 0;
@@ -840,6 +893,7 @@ int ozmma_tgemm(const int8_t* A8, const int8_t* B8, int MP, int s, int emax, int
     a.ntiles = static_cast<int>(ceil_div(rows, 256)) * a.tiles_n;
     a.nchunks = 1;
     a.gchunks = 1;
+    a.nint = int_levels(s, 2, emax, MP, 1);
     a.ngroups = 1;
     a.lower = 0;
     a.mode = 1;
@@ -893,6 +947,7 @@ int ozmma_phi(const int8_t* FD8, const double* eaF, const int8_t* WD8, const dou
     a.ntiles = static_cast<int>(ceil_div(rows, 256)) * a.tiles_n;
     a.nchunks = 1;
     a.gchunks = 1;
+    a.nint = int_levels(s, 2, s + 1, 128, 1);
     a.ngroups = 1;
     a.lower = 0;
     a.mode = 2;

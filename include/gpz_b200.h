@@ -76,6 +76,23 @@ void gpz_destroy(gpz_ctx* ctx);
 int gpz_comm_unique_id(char id[128]);
 int gpz_comm_init(gpz_ctx* ctx, int rank, int world, const char id[128]);
 
+/* ---- multi-GPU from ONE process / one caller thread (the reference's caller is a single interpreter thread holding
+ * the closure of GPz/train.m:40; SURVEY.md 8b "threading", 8e "backend"): the rows selected by the masks are split into
+ * ngpus contiguous blocks, one context per device, one NCCL communicator over all of them; every call below runs on all
+ * devices (one internal worker thread each) and returns rank 0's -- identical -- results.  devices: ngpus CUDA ordinals,
+ * NULL = 0 .. ngpus-1.  Arguments otherwise as gpz_create / gpz_eval / gpz_fit / gpz_get_prior / gpz_train.          */
+typedef struct gpz_multi gpz_multi;
+int gpz_create_multi(gpz_multi** out, const gpz_model* model, int64_t n_all,
+                     const double* X, const double* Y, const double* Psi, const double* omega,
+                     const uint8_t* training, const uint8_t* validation, int ngpus, const int* devices);
+void gpz_destroy_multi(gpz_multi* mc);
+int gpz_multi_devices(const gpz_multi* mc);
+gpz_ctx* gpz_multi_ctx(gpz_multi* mc, int rank);            /* the per-device context (timing, launch counts) */
+int gpz_multi_eval(gpz_multi* mc, const double* theta, double* nlogML, double* grad, double stats[4]);
+int gpz_multi_fit(gpz_multi* mc, const double* theta, double* nlogML_k, double* w, double* iSigma_w);
+int gpz_multi_get_prior(gpz_multi* mc, const double* theta, double* prior);
+int gpz_multi_set_option(gpz_multi* mc, const char* name, double value);
+
 /* ---- [nlogML,grad] = GPz(theta,...) with nargout<=2   (GPz/GPz.m:1-263, full path) ---------------
  * stats[4] = trainRMSE, trainLL, validRMSE, validLL  (the globals of GPz/GPz.m:3-7,236-259;
  * valid* are NaN without a validation mask).                                                     */
@@ -171,6 +188,8 @@ const char* gpz_train_reason(int reason);
  * model.best.LL (NaN = empty), out = updated as callBack.m does.  cb may be NULL.                           */
 int gpz_train(gpz_ctx* ctx, const gpz_train_options* opt, double* theta, double* best_theta, double* best_valid,
               gpz_train_callback cb, void* user, gpz_train_result* res);
+int gpz_multi_train(gpz_multi* mc, const gpz_train_options* opt, double* theta, double* best_theta, double* best_valid,
+                    gpz_train_callback cb, void* user, gpz_train_result* res);   /* opt->training_only must be 0 or 1 */
 /* the same optimiser on a caller-supplied objective (host callback that fills f and g for a DEVICE x): exposed so the
  * optimiser can be tested on analytic functions.  fn(user, d_x, d_out) must enqueue on `stream` (a cudaStream_t) and
  * leave d_out = [f, g[p], stats[4]].                                                                        */

@@ -121,6 +121,30 @@ def test_eval_row_chunked_equals_resident(method, psi, digits):
     ctx.close()
 
 
+@pytest.mark.parametrize("method,psi", [("VC", False), ("VC", True), ("GC", False)])
+def test_eval_row_chunked_with_missing_input_pattern_groups(method, psi):
+    """Covariance modes with NaN inputs: rows are grouped by missing pattern; with row chunks (PHI not resident) every
+    (chunk, pattern group) piece gets its own moment GEMM (round 1 refused this combination)."""
+    model, theta, X, Y, Psi, omega, tr, va = problem(method, True, psi, True, n=5000, d=3, m=20, seed=4)
+    ref, f, g, st, ctx = run_both(model, theta, X, Y, Psi, omega, tr, va, chunk_rows=1024)
+    assert_eval_matches(model, ref, f, g, st)
+    pr = ctx.get_prior(theta)                                   # getPrior.m with PHI rebuilt per row chunk
+    ctx.close()
+    gm = L.make_model(model.d, model.k, model.m, model.method, model.heteroscedastic)
+    ctx = L.Context(gm, X, Y, Psi, omega, tr, va)
+    assert rel(pr, ctx.get_prior(theta)) <= 1e-12
+    ctx.close()
+
+
+@pytest.mark.parametrize("digits", [7, None])
+def test_eval_two_outputs_row_chunked(digits):
+    """k = 2 outputs with row chunks: one Gram accumulation per output across the chunks (round 1 refused this combination)."""
+    model, theta, X, Y, Psi, omega, tr, va = problem("VD", True, False, False, n=5000, d=3, m=20, k=2, seed=12)
+    ref, f, g, st, ctx = run_both(model, theta, X, Y, Psi, omega, tr, va, chunk_rows=1024, digits=digits)
+    assert_eval_matches(model, ref, f, g, st)
+    ctx.close()
+
+
 def test_eval_two_outputs():
     model, theta, X, Y, Psi, omega, tr, va = problem("VD", True, False, False, k=2, seed=11)
     ref, f, g, st, ctx = run_both(model, theta, X, Y, Psi, omega, tr, va)
@@ -489,6 +513,39 @@ def test_two_devices_in_one_process():
         out.append(ctx.eval(theta))
         ctx.close()
     assert out[0][0] == out[1][0] and np.array_equal(out[0][1], out[1][1])
+
+
+@pytest.mark.parametrize("ngpus", [1, 2])
+def test_single_process_multi_gpu_context(ngpus):
+    """gpz_create_multi (one caller thread -- the MATLAB interpreter holding the closure of train.m:40 -- drives
+    N GPUs): rows split inside the library, one worker thread and one NCCL rank per device.  Against the plain one-GPU
+    context: eval, the fit exit, getPrior and a short device-resident training run."""
+    import torch
+    if torch.cuda.device_count() < ngpus:
+        pytest.skip(f"needs {ngpus} GPUs")
+    model, theta, X, Y, Psi, omega, tr, va = problem("VC", True, False, False, n=6000, d=4, m=150, seed=19)
+    gm = L.make_model(model.d, 1, model.m, "VC", True)
+    one = L.Context(gm, X, Y, None, omega, tr, va)
+    f0, g0, st0 = one.eval(theta)
+    nl0, w0, iS0 = one.fit(theta)
+    pr0 = one.get_prior(theta)
+    th0, bt0, bv0, info0 = one.train(theta, theta, float("nan"), max_iter=4, training_only=0)
+    one.close()
+    mc = L.MultiContext(gm, X, Y, None, omega, tr, va, ngpus=ngpus)
+    f, g, st = mc.eval(theta)
+    f2, g2, _ = mc.eval(theta)
+    assert f == f2 and np.array_equal(g, g2)
+    tol = 0.0 if ngpus == 1 else 1e-9          # one device: the same kernels on the same rows -> the same bits
+    assert abs(f - f0) <= tol * abs(f0) and rel(g, g0) <= max(tol, 0.0)
+    for key in st0:
+        assert abs(st[key] - st0[key]) <= max(tol, 0.0) * max(1.0, abs(st0[key])) + (0.0 if ngpus == 1 else 1e-12)
+    nl, w, iS = mc.fit(theta)
+    assert rel(nl, nl0) <= max(tol, 0.0) and rel(w, w0) <= max(10 * tol, 0.0) and rel(iS, iS0) <= max(10 * tol, 0.0)
+    assert rel(mc.get_prior(theta), pr0) <= max(tol, 0.0)
+    th, bt, bv, info = mc.train(theta, theta, float("nan"), max_iter=4, training_only=0)
+    assert info["iterations"] == info0["iterations"] and info["fun_evals"] == info0["fun_evals"]
+    assert rel(th, th0) <= max(1e3 * tol, 0.0) and abs(bv - bv0) <= max(1e3 * tol, 0.0) * abs(bv0)
+    mc.close()
 
 
 @pytest.mark.parametrize("method,psi,nan", [("VD", False, False), ("VC", True, True), ("GL", False, True)])
