@@ -39,6 +39,7 @@ WORKLOADS = {
     "cfg5": (1_000_000, 32, 2000, "GC", {"gpus": 4, "psi": True}),     # configs[4]: GC + input noise over 4 GPUs
     "photoz": (60_000, 5, 100, "VC", {}),
     "small": (20_000, 10, 256, "VC", {}),
+    "m1000_small_n": (20_000, 10, 1000, "VC", {}),                      # the m x m solve dominates: what 8 GPUs see of it
 }
 METRIC = "NLML+grad evals/sec at (n,d,m) per covariance mode"
 

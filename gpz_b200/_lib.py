@@ -243,7 +243,7 @@ class Context:
         w = np.empty((m, k), order="F")
         iS = np.empty((m, m, k), order="F")
         check(self._lib.gpz_fit(self._h, ptr(th), ptr(nl) if want_nlogML else None, ptr(w), ptr(iS)))
-        return nl.reshape(1, k), w, iS
+        return (nl.reshape(1, k) if want_nlogML else None), w, iS
 
     def rows(self, which=0):
         return int(self._lib.gpz_rows(self._h, which))

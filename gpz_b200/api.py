@@ -268,11 +268,18 @@ def train(model, X, Y, maxIter=200, maxAttempts=np.inf, omega=None, training=Non
         oG, oA, oB, oV, oT = _theta_offsets(model)
         for name, th in (("last", theta), ("best", best_theta)):
             w, iS = obj.fit(th)                                     # train.m:53,69
-            priors = obj.ctx.get_prior(th) if priors_wanted else np.ones(m) / m          # train.m:59,74 (getPrior.m)
-            model[name].update(theta=th.copy(), w=w, iSigma_w=iS, priors=priors,
-                               P=th[:m * d].reshape((m, d), order="F"))
+            # the optimised parameters are stored BEFORE the priors are computed: a failure of the EM below must not cost
+            # the training result
+            model[name].update(theta=th.copy(), w=w, iSigma_w=iS, P=th[:m * d].reshape((m, d), order="F"))
             if model["heteroscedastic"]:
                 model[name]["v"] = th[oV:oV + m * k].reshape((m, k), order="F")
+            model[name]["priors"] = np.ones(m) / m
+            if priors_wanted:
+                try:
+                    model[name]["priors"] = obj.ctx.get_prior(th)   # train.m:59,74 (getPrior.m)
+                except L.GpzError as e:
+                    import warnings
+                    warnings.warn(f"getPrior failed ({e}); model.{name}.priors left uniform")
         info["best_valid"] = best_valid                            # train.m never writes best.LL back (it stays init's -inf)
         model["evals"] = obj.evals + info["fun_evals"]
         model["train_info"] = info

@@ -1109,6 +1109,10 @@ int eval_device_enqueue(gpz_ctx* c, const double* d_theta, double* d_out) {
     Params& P = c->P;
     cudaStream_t st = c->st;
     int rc;
+    if (c->tr.n == 0) {                  // before anything collective is enqueued
+        set_error("no training rows on this rank");
+        return GPZ_ERR_USAGE;
+    }
     if ((rc = ensure_workspace(c))) return rc;
     if ((rc = forward_and_solve(c, d_theta))) return rc;
     const int64_t n = c->tr.n, nv = c->va.n, MP = P.MP;
@@ -1206,10 +1210,6 @@ int eval_device_enqueue(gpz_ctx* c, const double* d_theta, double* d_out) {
             if ((rc = backproj_cov_psi(P, c->tr, r0, r1, c->H, MP, c->bp_partial, c->nslab, nchunks > 0, st, &c->launches))) return rc;
         }
         ++nchunks;
-    }
-    if (n == 0) {
-        set_error("no training rows on this rank");
-        return GPZ_ERR_USAGE;
     }
     if (!ev4) GPZ_EVREC(c->ev[4]);
     if (fast_bp) {
@@ -1511,6 +1511,10 @@ int gpz_comm_init(gpz_ctx* c, int rank, int world, const char id[128]) {
         set_error("gpz_comm_init: bad arguments");
         return GPZ_ERR_USAGE;
     }
+    if (world > 1 && c->tr.n == 0) {     // such a rank would leave the others blocked inside an allreduce
+        set_error("gpz_comm_init: rank %d holds no training rows; every rank of a sharded run needs at least one", rank);
+        return GPZ_ERR_USAGE;
+    }
     c->rank = rank;
     c->world = world;
     if (world == 1) return GPZ_OK;
@@ -1644,6 +1648,14 @@ int gpz_phi(gpz_ctx* c, const double* theta, int which, double* PHI, double* lnB
     GPZ_CUDA(cudaMemcpyAsync(c->d_theta, theta, sizeof(double) * P.p, cudaMemcpyHostToDevice, st));
     if ((rc = prep_params(c->d_theta, P, c->has_psi, st, &c->launches))) return rc;
     double *dotv = nullptr, *colmaj = nullptr;
+    struct Scratch {                     // freed on every exit path
+        double*& a;
+        double*& b;
+        ~Scratch() {
+            if (a) cudaFree(a);
+            if (b) cudaFree(b);
+        }
+    } scratch_guard{dotv, colmaj};
     GPZ_CUDA(cudaMalloc(&dotv, sizeof(double) * n * P.k));
     if (PHI || N) GPZ_CUDA(cudaMalloc(&colmaj, sizeof(double) * c->chunk_rows * P.m));
     std::vector<double> hbuf;
@@ -1692,8 +1704,6 @@ int gpz_phi(gpz_ctx* c, const double* theta, int which, double* PHI, double* lnB
         }
     }
     GPZ_CUDA(cudaStreamSynchronize(st));
-    cudaFree(dotv);
-    if (colmaj) cudaFree(colmaj);
     return GPZ_OK;
 }
 
@@ -2376,6 +2386,10 @@ int gpz_set_option(gpz_ctx* c, const char* name, double value) {
             return GPZ_ERR_USAGE;
         }
         g_gemm_warps = static_cast<int>(value);
+        return GPZ_OK;
+    }
+    if (strcmp(name, "phi_persist") == 0) {         // process-wide: persistent column-stationary PHI kernel (gemm.cu), 1 = default
+        g_phi_persist = value != 0.0;
         return GPZ_OK;
     }
     if (strcmp(name, "ozaki_int_fold") == 0) {      // process-wide: integer folding of the lowest digit levels (ozmma.cu), 1 = default

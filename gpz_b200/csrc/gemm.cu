@@ -10,11 +10,14 @@
 // Operand tiles are staged global -> shared with cp.async in a 4-stage pipeline; the smem strides
 // (132 / 20 doubles) make every DMMA fragment load conflict-free.  All reductions have a fixed order,
 // so repeated evaluations at the same theta are bit-identical.
+#include <cuda.h>
+
 #include "internal.cuh"
 
 namespace gpz {
 
 constexpr int STAGES = 4;
+int g_phi_persist = 1;     // PHI = exp(F W) through the persistent column-stationary kernel where it applies ("phi_persist" option)
 int g_gemm_warps = 0;       // 0 = defaults (Gram / T-GEMM 8 warps, PHI build 16 warps: its exp epilogue likes more warps);
                             // 8 / 16 force all three (gpz_set_option "gemm_warps").  8 vs 16 differ by <4 % either way across boxes.
 
@@ -465,6 +468,203 @@ tgemm_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// PHI = exp(F W), persistent form for short K (the monomial features of d <= 10: K <= 72).
+// The kernel above gives every 128 x 128 tile its own CTA: operand loads start cold for each tile and its exp/store epilogue
+// overlaps nothing (one CTA per SM), so the fp64 pipe idles 35-40 % of the time (profiles/r01h, r02e: DMMA 52-57 % + FP64
+// 11-12 % active).  Here a CTA keeps ONE column tile of W in shared memory for its whole life and walks down the row tiles
+// of that column: the [128][K] row-feature tile of the next row tile arrives by TMA (one cp.async.bulk.tensor per tile,
+// double-buffered, completion on an mbarrier) while the current tile is multiplied and exponentiated, and the K loop has
+// no barrier inside (the whole K extent is resident).  Shared-memory strides LDK = 4 (mod 8) and 132 keep the DMMA fragment
+// loads conflict-free.  Same arithmetic, same order as tgemm_kernel<1>: bit-identical results.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pp_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void pp_mbar_expect(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pp_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+                     : "=r"(ok)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+        if (!ok && clock64() - t0 > 20000000000LL) __trap();      // a protocol bug fails the launch instead of hanging the GPU
+    }
+}
+__device__ __forceinline__ void pp_tma_2d(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+struct PhiPersist {
+    const double* W;        // [K][MP]
+    int MP, K4, LDK, ntn;
+    int64_t n, tiles_m;
+    PEpi pe;
+};
+
+__global__ void __launch_bounds__(512, 1)
+phi_persist_kernel(const __grid_constant__ CUtensorMap mapF, const PhiPersist a) {
+    constexpr int WARPS_M = 4, WM = TILE / WARPS_M, MT = WM / 8, NT = 4;
+    extern __shared__ __align__(128) unsigned char pp_smem[];
+    double* Ws = reinterpret_cast<double*>(pp_smem);                       // [K4][LDT]
+    double* As = Ws + a.K4 * LDT;                                           // [2][TILE][LDK]
+    __shared__ double red[2][4][TILE];
+    __shared__ double exp_sm[32];
+    __shared__ __align__(8) unsigned long long bars[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm0 = (warp >> 2) * WM, wn0 = (warp & 3) * 32;
+    const int ct = blockIdx.x % a.ntn;
+    const int64_t step = gridDim.x / a.ntn;
+    const int64_t j0 = static_cast<int64_t>(ct) * TILE;
+    const int LDK = a.LDK;
+    const uint32_t tile_bytes = static_cast<uint32_t>(TILE * LDK * sizeof(double));
+    const PEpi& pe = a.pe;
+
+    for (int c = tid; c < a.K4 * (TILE / 2); c += 512) {                    // this CTA's column tile of W, once
+        const int r = c >> 6, cc = c & 63;
+        cp_async16(Ws + r * LDT + cc * 2, a.W + static_cast<int64_t>(r) * a.MP + j0 + cc * 2, 16);
+    }
+    cp_async_commit();
+    exp_tab_stage(exp_sm);
+    if (tid == 0) {
+        pp_mbar_init(smem_u32(&bars[0]), 1);
+        pp_mbar_init(smem_u32(&bars[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    double2 v0[NT], v1[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        const int64_t gj = j0 + wn0 + j * 8 + 2 * t;
+        v0[j] = pe.ndot > 0 ? *reinterpret_cast<const double2*>(pe.vec[0] + gj) : make_double2(0.0, 0.0);
+        v1[j] = pe.ndot > 1 ? *reinterpret_cast<const double2*>(pe.vec[1] + gj) : make_double2(0.0, 0.0);
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    int64_t rt = blockIdx.x / a.ntn;
+    if (tid == 0 && rt < a.tiles_m) {
+        pp_mbar_expect(smem_u32(&bars[0]), tile_bytes);
+        pp_tma_2d(&mapF, smem_u32(As), smem_u32(&bars[0]), 0, static_cast<int>(rt * TILE));
+    }
+    for (uint32_t it = 0; rt < a.tiles_m; rt += step, ++it) {
+        const uint32_t buf = it & 1u;
+        if (tid == 0 && rt + step < a.tiles_m) {                             // next row tile into the other buffer (freed by the
+            pp_mbar_expect(smem_u32(&bars[buf ^ 1u]), tile_bytes);           // barrier that ended the previous iteration)
+            pp_tma_2d(&mapF, smem_u32(As + (buf ^ 1u) * TILE * LDK), smem_u32(&bars[buf ^ 1u]), 0, static_cast<int>((rt + step) * TILE));
+        }
+        pp_mbar_wait(smem_u32(&bars[buf]), (it >> 1) & 1u);
+        const double* as = As + buf * TILE * LDK;
+        double acc[MT][NT][2];
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int kk = 0; kk < a.K4 / 4; ++kk) {
+            const int kc = kk * 4 + t;
+            double bf[NT];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) bf[j] = Ws[kc * LDT + wn0 + j * 8 + g];
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
+                const double af = as[(wm0 + i * 8 + g) * LDK + kc];
+#pragma unroll
+                for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], af, bf[j]);
+            }
+        }
+        const int64_t i0 = rt * TILE;
+        double rs0[MT], rs1[MT];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            const int64_t gi = i0 + wm0 + i * 8 + g;
+            const bool ok = gi < a.n;
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const int64_t gj = j0 + wn0 + j * 8 + 2 * t;
+                double p0 = (gj < pe.m) ? exp_tab(acc[i][j][0], exp_sm) : 0.0;
+                double p1 = (gj + 1 < pe.m) ? exp_tab(acc[i][j][1], exp_sm) : 0.0;
+                if (pe.ycol != nullptr && ok) {
+                    if (gj == pe.m) p0 = pe.ycol[gi];
+                    if (gj + 1 == pe.m) p1 = pe.ycol[gi];
+                }
+                if (ok && pe.Phi != nullptr) *reinterpret_cast<double2*>(pe.Phi + gi * a.MP + gj) = make_double2(p0, p1);
+                s0 = fma(p0, v0[j].x, fma(p1, v0[j].y, s0));
+                s1 = fma(p0, v1[j].x, fma(p1, v1[j].y, s1));
+            }
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+            rs0[i] = s0;
+            rs1[i] = s1;
+        }
+        if (pe.ndot > 0) {
+            if (t == 0) {
+#pragma unroll
+                for (int i = 0; i < MT; ++i) {
+                    red[0][warp & 3][wm0 + i * 8 + g] = rs0[i];
+                    red[1][warp & 3][wm0 + i * 8 + g] = rs1[i];
+                }
+            }
+            __syncthreads();
+            if (tid < TILE) {
+                const int64_t gi = i0 + tid;
+                if (gi < a.n) {
+                    pe.part[0][static_cast<int64_t>(ct) * pe.part_ld + gi] = red[0][0][tid] + red[0][1][tid] + red[0][2][tid] + red[0][3][tid];
+                    if (pe.ndot > 1)
+                        pe.part[1][static_cast<int64_t>(ct) * pe.part_ld + gi] = red[1][0][tid] + red[1][1][tid] + red[1][2][tid] + red[1][3][tid];
+                }
+            }
+        }
+        __syncthreads();                                                     // everyone is done with As[buf] and red
+    }
+}
+
+static int launch_phi_persist(const double* F, int64_t ldf, int kvalid, const double* W, int MP, int64_t n, const PEpi& pe, cudaStream_t st,
+                              bool* done) {
+    *done = false;
+    const int K4 = static_cast<int>(round_up(kvalid, 4));
+    const int LDK = (K4 % 8 == 4) ? K4 : K4 + 4;
+    const size_t smem = sizeof(double) * (static_cast<size_t>(K4) * LDT + 2 * static_cast<size_t>(TILE) * LDK);
+    if (!ozmma_available() || LDK > ldf || smem > 218 * 1024 || n >= (1LL << 31) - TILE || (reinterpret_cast<uintptr_t>(F) & 15) != 0)
+        return GPZ_OK;                                                       // the tile-per-CTA kernel takes it
+    static PerDeviceOnce once;
+    static int sms_dev[128];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (once.need()) {
+        GPZ_CUDA(cudaFuncSetAttribute(phi_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024));   // + 8.4 KB static = the 227 KB a CTA may use
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        sms_dev[dev & 127] = sms;
+    }
+    alignas(64) CUtensorMap map;
+    int rc;
+    if ((rc = tensor_map_2d_f64(&map, F, ldf, n, ldf, LDK, TILE))) return rc;
+    PhiPersist a;
+    a.W = W;
+    a.MP = MP;
+    a.K4 = K4;
+    a.LDK = LDK;
+    a.ntn = MP / TILE;
+    a.n = n;
+    a.tiles_m = ceil_div(n, TILE);
+    a.pe = pe;
+    int64_t per = sms_dev[dev & 127] / a.ntn;
+    if (per < 1) per = 1;
+    if (per > a.tiles_m) per = a.tiles_m;
+    phi_persist_kernel<<<static_cast<unsigned>(per * a.ntn), 512, smem, st>>>(map, a);
+    GPZ_KERNEL_CHECK();
+    *done = true;
+    return GPZ_OK;
+}
+
 template <int EPI, int WARPS_M>
 static int launch_tgemm(const double* A, int64_t lda, const double* B, int MP, int nk, int klast, int64_t n, const TEpi& te,
                         const PEpi& pe, cudaStream_t st) {
@@ -503,6 +703,15 @@ int phi_gemm(const double* F, int64_t ldf, int kq, int kvalid, const double* W, 
     TEpi te{};
     PEpi pe{m, Phi, ndot, {vec0, vec1}, {part0, part1}, part_ld, ycol};
     if (kvalid < 1 || kvalid > kq) kvalid = kq;
+    if (g_gemm_warps == 0 && g_phi_persist) {
+        bool done = false;
+        const int rcp = launch_phi_persist(F, ldf, kvalid, W, MP, n, pe, st, &done);
+        if (rcp) return rcp;
+        if (done) {
+            ++*launches;
+            return GPZ_OK;
+        }
+    }
     const int nk = static_cast<int>(ceil_div(kvalid, KSTEP));
     const int klast = static_cast<int>(ceil_div(kvalid - (nk - 1) * KSTEP, 4));
     int rc = g_gemm_warps != 8 ? launch_tgemm<1, 4>(F, ldf, W, MP, nk, klast, n, te, pe, st)

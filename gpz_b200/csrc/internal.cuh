@@ -89,6 +89,7 @@ int transpose_out(const double* src_rowmajor, int64_t ld, int64_t n, int m, doub
 
 // ---- gemm.cu
 extern int g_gemm_warps;
+extern int g_phi_persist;
 int gram_nsplit(int MP, int sm_count);
 int gram_syrk_main(const double* Phi, int64_t ld, int MP, const double* wgt, int64_t row0, int64_t row1, int nsplit,
                    double* partial, int accumulate, cudaStream_t st, int64_t* launches);
@@ -191,6 +192,7 @@ int ozaki_tgemm(const double* Phi, int64_t ld, const int8_t* D8, const double* e
 namespace gpz {
 // ---- ozmma.cu: hand-written tcgen05 (cta_group::2, TMA, TMEM) digit-level GEMM with on-chip level folding
 bool ozmma_available();
+int tensor_map_2d_f64(void* out /*128 B, 64-byte aligned*/, const double* base, int64_t cols, int64_t rows, int64_t ld, int box_cols, int box_rows);
 void ozmma_set_prefetch(int on);
 void ozmma_set_int_fold(int on);     // 1 (default): lowest levels folded exactly in int64 where a unit is one level sweep
 void ozmma_set_level_group(int g);   // 2 (default): two levels share their operand tiles; 1: one level at a time (A/B measurements)

@@ -32,7 +32,7 @@ constexpr int OM_STAGE_BYTES = OM_A_BYTES + OM_B_BYTES;
 constexpr int OM_BAR_OFF = OM_STAGES * OM_STAGE_BYTES;
 // barrier block (8 bytes each): full[8] @0, empty[8] @64, tfull[4] @128, tempty[4] @160, tmem slot @192
 constexpr int OM_FULL = 0, OM_EMPTY = 64, OM_TFULL = 128, OM_TEMPTY = 160, OM_SLOT = 192;
-constexpr int OM_SMEM_BYTES = OM_BAR_OFF + 256 + 6144 + 1024;   // barriers + tmem slot, row sums, + slack for the 1024-byte alignment
+constexpr int OM_SMEM_BYTES = OM_BAR_OFF + 256 + 6144 + 256 + 1024;   // barriers + tmem slot, row sums, exp table, + slack for the 1024-byte alignment
 constexpr int OM_THREADS = 576;                       // warp 0: TMA, warp 1: MMA, warps 2..17: epilogue (4 lane quarters x 4 column groups)
 constexpr uint32_t OM_TMEM_COLS = 512;                // two regions of 256 columns = two levels each: one region multiplied, one folded
 // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D = S32, A = B = signed 8 bit, both K-major,
@@ -53,6 +53,7 @@ struct OzmmaArgs {
     int mn_major;             // operands stored [k][row] (row index contiguous) instead of [row][k]
     int lgroup;               // levels multiplied together: 2 (default, shared operand tiles) or 1 (one level at a time)
     int prefetch;             // mode 1: prefetch the epilogue's PHI block into L2 (default 1; 0 for A/B measurements)
+    int kmma;                 // 32-byte K steps multiplied per 128-byte stage (4; fewer when the operands' K extent is < 97: PHI build)
     int nint;                 // the first nint levels of a unit (emax, emax-1, ..) are folded EXACTLY in int64; the host picks the
                               // largest count whose sum cannot overflow, and 0 when a unit folds more than one K chunk
     uint64_t hintA, hintB;    // L2 eviction policy of the operand loads
@@ -260,6 +261,8 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const uint32_t bar0 = base + OM_BAR_OFF;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + OM_BAR_OFF + OM_SLOT);
     double* rowsum_sm = reinterpret_cast<double*>(gbase + OM_BAR_OFF + 256);      // [2][3][128]
+    double* exp_sm = rowsum_sm + 768;                                              // [32] table of exp_tab (PHI epilogue)
+    if (a.mode == 2) exp_tab_stage(exp_sm);                                        // visible after the cluster barrier below
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
 
@@ -375,17 +378,17 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                                 if (vh && vl) {
                                     const uint32_t blo = (aoff + (OM_A_BYTES >> 4)) | LO_A;    // 128 rows per CTA: A's layout
                                     umma_i8_2cta(dreg, alo, HI_A, blo, HI_A, IDESC2, acch);     // 4 x 32 K-bytes of the stage
-                                    umma_i8_2cta(dreg, alo + KA, HI_A, blo + KA, HI_A, IDESC2, 1u);
-                                    umma_i8_2cta(dreg, alo + 2 * KA, HI_A, blo + 2 * KA, HI_A, IDESC2, 1u);
-                                    umma_i8_2cta(dreg, alo + 3 * KA, HI_A, blo + 3 * KA, HI_A, IDESC2, 1u);
+                                    if (a.kmma > 1) umma_i8_2cta(dreg, alo + KA, HI_A, blo + KA, HI_A, IDESC2, 1u);
+                                    if (a.kmma > 2) umma_i8_2cta(dreg, alo + 2 * KA, HI_A, blo + 2 * KA, HI_A, IDESC2, 1u);
+                                    if (a.kmma > 3) umma_i8_2cta(dreg, alo + 3 * KA, HI_A, blo + 3 * KA, HI_A, IDESC2, 1u);
                                     acch = accl = 1u;
                                 } else {
                                     const uint32_t blo = (aoff + (OM_A_BYTES >> 4)) | LO_B;
                                     const uint32_t d1 = vh ? dreg : dreg + 128u, acc1 = vh ? acch : accl;
                                     umma_i8_2cta(d1, alo, HI_A, blo, HI_B, IDESC1, acc1);
-                                    umma_i8_2cta(d1, alo + KA, HI_A, blo + KB, HI_B, IDESC1, 1u);
-                                    umma_i8_2cta(d1, alo + 2 * KA, HI_A, blo + 2 * KB, HI_B, IDESC1, 1u);
-                                    umma_i8_2cta(d1, alo + 3 * KA, HI_A, blo + 3 * KB, HI_B, IDESC1, 1u);
+                                    if (a.kmma > 1) umma_i8_2cta(d1, alo + KA, HI_A, blo + KB, HI_B, IDESC1, 1u);
+                                    if (a.kmma > 2) umma_i8_2cta(d1, alo + 2 * KA, HI_A, blo + 2 * KB, HI_B, IDESC1, 1u);
+                                    if (a.kmma > 3) umma_i8_2cta(d1, alo + 3 * KA, HI_A, blo + 3 * KB, HI_B, IDESC1, 1u);
                                     if (vh) acch = 1u;
                                     else accl = 1u;
                                 }
@@ -521,7 +524,7 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                 for (int r = 0; r < 32; ++r) {
                     double p = 0.0;
                     if (gi0 + r < a.rows) {
-                        if (col < a.m) p = exp(scale_pow2(st[r], pow2_exponent(a.ea[gi0 + r]) + exb));
+                        if (col < a.m) p = exp_tab(scale_pow2(st[r], pow2_exponent(a.ea[gi0 + r]) + exb), exp_sm);
                         else if (a.ycol != nullptr && col == a.m) p = a.ycol[gi0 + r];
                         if (pp != nullptr) pp[r * a.ld] = p;
                     }
@@ -697,6 +700,7 @@ void set_operand_layout(OzmmaArgs& a, int mn_major) {
     a.mn_major = mn_major;
     a.lgroup = g_lgroup;
     a.prefetch = g_prefetch;
+    a.kmma = 4;
     a.hintA = a.hintB = OM_EVICT_NORMAL;
 }
 
@@ -779,6 +783,29 @@ int launch(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mB2,
 }  // namespace
 
 bool ozmma_available() { return encode_fn() != nullptr; }
+
+// 2-D fp64 tensor map {cols (contiguous), rows} with row stride ld doubles and a box of box_cols x box_rows, no swizzle;
+// out: 128 bytes, 64-byte aligned (a CUtensorMap).  Used by the persistent PHI kernel (gemm.cu) for its row-feature tiles.
+int tensor_map_2d_f64(void* out, const double* base, int64_t cols, int64_t rows, int64_t ld, int box_cols, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (fn == nullptr) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return GPZ_ERR_CUDA;
+    }
+    cuuint64_t gd[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gs[1] = {static_cast<cuuint64_t>(ld) * 8};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t es[2] = {1, 1};
+    const CUresult r = fn(static_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gd, gs, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (fp64 2-D) failed (%d): cols %lld rows %lld ld %lld box %d x %d", static_cast<int>(r),
+                  static_cast<long long>(cols), static_cast<long long>(rows), static_cast<long long>(ld), box_cols, box_rows);
+        return GPZ_ERR_CUDA;
+    }
+    return GPZ_OK;
+}
 
 void ozmma_set_level_group(int g) { g_lgroup = g == 1 ? 1 : 2; }
 void ozmma_set_prefetch(int on) { g_prefetch = on != 0; }
@@ -948,6 +975,7 @@ int ozmma_phi(const int8_t* FD8, const double* eaF, const int8_t* WD8, const dou
     a.nchunks = 1;
     a.gchunks = 1;
     a.nint = int_levels(s, 2, s + 1, 128, 1);
+    a.kmma = (kq + 31) / 32;
     a.ngroups = 1;
     a.lower = 0;
     a.mode = 2;

@@ -78,6 +78,9 @@ __device__ __forceinline__ bool chol64(double (*A)[NB + 1], double (*colbuf)[NB]
     __syncthreads();
     return true;
 }
+// (Tried in round 2 and dropped: the same factorisation by ONE warp with rows in registers and the column values exchanged by
+// shuffles -- no block barrier at all, but 105 us per 64 x 64 block against 51 us for this version in the ncu launch list of an
+// m = 1000 evaluation, gpurun_out r02k: a single warp cannot hide the shuffle -> FMA latency chain.)
 
 // factor the nb x nb diagonal block at (k0,k0) in place (lower), invert the factor into Linv (row-major 64 x 64, zero
 // upper triangle), accumulate logdet.  Cholesky of the 64 x 64 block by the whole CTA; the inverse as 2 x 2 blocks of 32:

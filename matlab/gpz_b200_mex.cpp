@@ -7,7 +7,8 @@
 // Convention follows the reference's own MEX files (minFunc_2012/minFunc/mex/lbfgsProdC.c:7-44):
 // plain mexFunction, mxGetPr in, mxCreateDoubleMatrix out, mexErrMsgIdAndTxt on misuse.  Inputs are never
 // written (unlike lbfgsAddC.c:30-33).  Usage from MATLAB (see GPz.m / getPHI.m / predict_core.m here):
-//     h = gpz_b200_mex('create', model, X, Y, Psi, omega, training, validation)    -> uint64 handle
+//     h = gpz_b200_mex('create', model, X, Y, Psi, omega, training, validation[, ngpus])    -> handle
+//         ngpus > 1: the rows are split over that many GPUs inside the library (gpz_create_multi), still one caller thread
 //     [f, g, stats] = gpz_b200_mex('eval', h, theta)
 //     [nl, w, iSigma_w] = gpz_b200_mex('fit', h, theta[, model])
 //     [PHI, lnBeta_i, N] = gpz_b200_mex('phi', h, theta[, which[, model]])
@@ -34,7 +35,8 @@
 namespace {
 
 struct Entry {
-    gpz_ctx* ctx;
+    gpz_ctx* ctx;           // one device ...
+    gpz_multi* mc;          // ... or several, driven from this one thread (create(..., ngpus) with ngpus > 1)
     gpz_model model;        // the model the context was created for: every output is sized from THIS, never from an argument
 };
 std::map<uint64_t, Entry> g_ctx;
@@ -43,8 +45,15 @@ uint64_t g_next = 1;
 void fail(const char* what) { mexErrMsgIdAndTxt("gpz_b200:error", "%s: %s", what, gpz_last_error()); }
 void usage(const char* what) { mexErrMsgIdAndTxt("gpz_b200:usage", "%s", what); }
 
+void destroy_entry(Entry& e) {
+    if (e.ctx) gpz_destroy(e.ctx);
+    if (e.mc) gpz_destroy_multi(e.mc);
+    e.ctx = nullptr;
+    e.mc = nullptr;
+}
+
 void destroy_all() {
-    for (auto& kv : g_ctx) gpz_destroy(kv.second.ctx);
+    for (auto& kv : g_ctx) destroy_entry(kv.second);
     g_ctx.clear();
 }
 
@@ -167,12 +176,19 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
             if (nrhs > q && prhs[q] != nullptr && !mxIsEmpty(prhs[q]) && mxGetNumberOfElements(prhs[q]) != n)
                 usage("create: training / validation masks must have n elements");
         std::vector<uint8_t> tr, va;
-        gpz_ctx* ctx = nullptr;
-        const int rc = gpz_create(&ctx, &m, static_cast<int64_t>(n), mxGetPr(prhs[2]), mxGetPr(prhs[3]), psi, om,
-                                  nrhs > 6 ? mask(prhs[6], tr, n) : nullptr, nrhs > 7 ? mask(prhs[7], va, n) : nullptr, 0);
-        if (rc) fail("gpz_create");
+        const int ngpus = (nrhs > 8 && !mxIsEmpty(prhs[8])) ? static_cast<int>(mxGetScalar(prhs[8])) : 1;
+        if (ngpus < 1) usage("create: ngpus must be >= 1");
+        Entry e{nullptr, nullptr, m};
+        const uint8_t* trp = nrhs > 6 ? mask(prhs[6], tr, n) : nullptr;
+        const uint8_t* vap = nrhs > 7 ? mask(prhs[7], va, n) : nullptr;
+        if (ngpus == 1) {
+            if (gpz_create(&e.ctx, &m, static_cast<int64_t>(n), mxGetPr(prhs[2]), mxGetPr(prhs[3]), psi, om, trp, vap, 0)) fail("gpz_create");
+        } else {            // one MATLAB thread, ngpus devices: rows split and NCCL set up inside the library
+            if (gpz_create_multi(&e.mc, &m, static_cast<int64_t>(n), mxGetPr(prhs[2]), mxGetPr(prhs[3]), psi, om, trp, vap, ngpus, nullptr))
+                fail("gpz_create_multi");
+        }
         const uint64_t id = g_next++;
-        g_ctx[id] = Entry{ctx, m};
+        g_ctx[id] = e;
         plhs[0] = mxCreateDoubleScalar(static_cast<double>(id));
     } else if (c == "destroy") {
         need(nrhs, 2, "gpz_b200_mex('destroy',h)");
@@ -180,7 +196,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         const uint64_t id = static_cast<uint64_t>(mxGetScalar(prhs[1]));
         auto it = g_ctx.find(id);
         if (it != g_ctx.end()) {
-            gpz_destroy(it->second.ctx);
+            destroy_entry(it->second);
             g_ctx.erase(it);
         }
     } else if (c == "eval") {
@@ -191,7 +207,9 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         plhs[0] = mxCreateDoubleMatrix(1, 1, mxREAL);
         mxArray* g = mxCreateDoubleMatrix(p, 1, mxREAL);
         mxArray* st = mxCreateDoubleMatrix(4, 1, mxREAL);
-        if (gpz_eval(e.ctx, mxGetPr(prhs[2]), mxGetPr(plhs[0]), mxGetPr(g), mxGetPr(st))) fail("gpz_eval");
+        if (e.mc ? gpz_multi_eval(e.mc, mxGetPr(prhs[2]), mxGetPr(plhs[0]), mxGetPr(g), mxGetPr(st))
+                 : gpz_eval(e.ctx, mxGetPr(prhs[2]), mxGetPr(plhs[0]), mxGetPr(g), mxGetPr(st)))
+            fail("gpz_eval");
         if (nlhs > 1) plhs[1] = g; else mxDestroyArray(g);
         if (nlhs > 2) plhs[2] = st; else mxDestroyArray(st);
     } else if (c == "fit") {
@@ -204,12 +222,15 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         mxArray* w = mxCreateDoubleMatrix(m.m, m.k, mxREAL);
         const mwSize dims[3] = {static_cast<mwSize>(m.m), static_cast<mwSize>(m.m), static_cast<mwSize>(m.k)};
         mxArray* iS = mxCreateNumericArray(3, dims, mxDOUBLE_CLASS, mxREAL);
-        if (gpz_fit(e.ctx, mxGetPr(prhs[2]), mxGetPr(plhs[0]), mxGetPr(w), mxGetPr(iS))) fail("gpz_fit");
+        if (e.mc ? gpz_multi_fit(e.mc, mxGetPr(prhs[2]), mxGetPr(plhs[0]), mxGetPr(w), mxGetPr(iS))
+                 : gpz_fit(e.ctx, mxGetPr(prhs[2]), mxGetPr(plhs[0]), mxGetPr(w), mxGetPr(iS)))
+            fail("gpz_fit");
         if (nlhs > 1) plhs[1] = w; else mxDestroyArray(w);
         if (nlhs > 2) plhs[2] = iS; else mxDestroyArray(iS);
     } else if (c == "phi") {
         need(nrhs, 3, "[PHI,lnBeta_i,N] = gpz_b200_mex('phi',h,theta[,which[,model]])");
         Entry& e = lookup(prhs[1]);
+        if (e.mc) usage("phi: not available on a multi-GPU handle (the rows live on several devices); create a one-GPU handle");
         check_theta(prhs[2], e.model, "phi");
         const int which = (nrhs > 3 && !mxIsEmpty(prhs[3])) ? static_cast<int>(mxGetScalar(prhs[3])) : 0;
         if (which != 0 && which != 1) usage("phi: which must be 0 (training rows) or 1 (validation rows)");
@@ -228,11 +249,11 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         check_theta(prhs[2], e.model, "get_prior");
         check_model_arg(nrhs, prhs, 3, e.model);
         plhs[0] = mxCreateDoubleMatrix(1, e.model.m, mxREAL);
-        if (gpz_get_prior(e.ctx, mxGetPr(prhs[2]), mxGetPr(plhs[0]))) fail("gpz_get_prior");
+        if (e.mc ? gpz_multi_get_prior(e.mc, mxGetPr(prhs[2]), mxGetPr(plhs[0])) : gpz_get_prior(e.ctx, mxGetPr(prhs[2]), mxGetPr(plhs[0])))
+            fail("gpz_get_prior");
     } else if (c == "train") {
         if (nrhs < 8) mexErrMsgIdAndTxt("gpz_b200:usage", "train(h,theta,best_theta,best_valid,maxIter,maxAttempts,trainingOnly[,display])");
         Entry& e = lookup(prhs[1]);
-        gpz_ctx* ctx = e.ctx;
         check_theta(prhs[2], e.model, "train");
         check_theta(prhs[3], e.model, "train (best_theta)");
         const size_t p = mxGetNumberOfElements(prhs[2]);
@@ -249,7 +270,9 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         TrainPrint tp{nrhs > 8 && mxGetScalar(prhs[8]) != 0, o.training_only != 0};
         gpz_train_result r;
         std::memset(&r, 0, sizeof(r));
-        if (gpz_train(ctx, &o, mxGetPr(plhs[0]), mxGetPr(best), &bv, train_row, &tp, &r)) fail("gpz_train");
+        if (e.mc ? gpz_multi_train(e.mc, &o, mxGetPr(plhs[0]), mxGetPr(best), &bv, train_row, &tp, &r)
+                 : gpz_train(e.ctx, &o, mxGetPr(plhs[0]), mxGetPr(best), &bv, train_row, &tp, &r))
+            fail("gpz_train");
         if (tp.display) mexPrintf("%s\n", r.reason == 7 ? "No improvment after maximum number of attempts" : gpz_train_reason(r.reason));
         if (nlhs > 1) plhs[1] = best; else mxDestroyArray(best);
         if (nlhs > 2) plhs[2] = mxCreateDoubleScalar(bv);

@@ -19,13 +19,18 @@ sets = {'last','best'}; thetas = {theta,best_theta};
 for s = 1:2
     th = thetas{s};
     [~,w,iSigma_w] = gpz_b200_mex('fit',h,th,model);
-    r = struct('theta',th,'w',w,'iSigma_w',iSigma_w,'priors',gpz_b200_mex('get_prior',h,th,model),'P',reshape(th(1:m*d),m,d));
+    r = struct('theta',th,'w',w,'iSigma_w',iSigma_w,'priors',ones(1,m)/m,'P',reshape(th(1:m*d),m,d));
     if model.heteroscedastic
         o = m*d+model.g_dim+m*k+k;
         r.v = reshape(th(o+1:o+m*k),m,k);
     end
     if s == 2, r.LL = model.best.LL; end          % train.m never writes best.LL back: every call restarts from init's -inf
-    model.(sets{s}) = r;
+    model.(sets{s}) = r;                          % stored before the priors: a failing EM must not cost the training result
+    try
+        model.(sets{s}).priors = gpz_b200_mex('get_prior',h,th,model);   % train.m:59,74
+    catch err
+        warning('gpz_b200:prior','getPrior failed (%s); priors left uniform',err.message);
+    end
 end
 model.train_info = [info best_valid];
 end

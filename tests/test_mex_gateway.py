@@ -114,3 +114,25 @@ def test_gateway_rejects_mismatched_sizes_instead_of_corrupting_memory():
     f = H.call("eval", h, theta)                                          # the context is still usable
     assert np.isfinite(f.item())
     H.call("destroy", h)
+
+
+@pytest.mark.gpu
+def test_gateway_multi_gpu_handle():
+    """create(..., ngpus): one caller thread, rows split over the devices inside the library (gpz_create_multi); eval / fit /
+    get_prior / train go through the same commands, phi is refused on such a handle."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    X, Y, theta, omega, tr, va = problem(n=2000)
+    h1 = H.call("create", MODEL, X, Y, None, omega, tr, va, 1.0)
+    h2 = H.call("create", MODEL, X, Y, None, omega, tr, va, 2.0)
+    f1, g1, s1 = H.call("eval", h1, theta, nlhs=3)
+    f2, g2, s2 = H.call("eval", h2, theta, nlhs=3)
+    assert abs(f1.item() - f2.item()) <= 1e-10 * abs(f1.item()) and np.max(np.abs(g1 - g2)) <= 1e-9 * np.max(np.abs(g1))
+    _, w1, _ = H.call("fit", h1, theta, nlhs=3)
+    _, w2, _ = H.call("fit", h2, theta, nlhs=3)
+    assert np.max(np.abs(w1 - w2)) <= 1e-8 * np.max(np.abs(w1))
+    with pytest.raises(H.MexError, match="multi-GPU handle"):
+        H.call("phi", h2, theta)
+    H.call("destroy", h1)
+    H.call("destroy", h2)
