@@ -2388,6 +2388,10 @@ int gpz_set_option(gpz_ctx* c, const char* name, double value) {
         g_gemm_warps = static_cast<int>(value);
         return GPZ_OK;
     }
+    if (strcmp(name, "solve_lookahead") == 0) {     // process-wide: look-ahead blocked Cholesky (solve.cu), 1 = default
+        g_solve_lookahead = value != 0.0;
+        return GPZ_OK;
+    }
     if (strcmp(name, "phi_persist") == 0) {         // process-wide: persistent column-stationary PHI kernel (gemm.cu), 1 = default
         g_phi_persist = value != 0.0;
         return GPZ_OK;

@@ -975,6 +975,7 @@ sgemm_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, in
     __shared__ double Bs[KSTEP][LB];
     const int ti = blockIdx.y, tj = blockIdx.x;
     if (lower_only && tj > ti) return;
+    if (lower_only == 2 && ti == 0 && tj == 0) return;      // look-ahead Cholesky: the next diagonal block is updated by its own kernel
     if (bt.mlim > 0) {
         const int mz = bt.mlim - static_cast<int>(blockIdx.z) * bt.mstep;
         if (mz < M) M = mz;

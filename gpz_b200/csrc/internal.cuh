@@ -119,7 +119,14 @@ struct SolveWs {
     double* Linv = nullptr;   // [nb][64*64] inverses of the diagonal blocks
     double* tmp = nullptr;    // [64][MP]
     int* flag = nullptr;      // device int: !=0 -> non-positive pivot
+    // look-ahead factorisation (solve.cu): L in its own matrix, panel GEMMs on a side stream, events between the two chains
+    static constexpr int MAXBLK = 64;
+    double* Lbuf = nullptr;   // [MP][MP]
+    cudaStream_t side = nullptr;
+    cudaEvent_t evP[MAXBLK] = {};
+    cudaEvent_t evT[MAXBLK] = {};
 };
+extern int g_solve_lookahead;
 int solve_ws_alloc(SolveWs& ws, int MP);
 void solve_ws_free(SolveWs& ws);
 // S (MP x MP row-major, lower triangle read, overwritten by L) -> Sinv (full symmetric), *d_logdet

@@ -9,6 +9,7 @@
 namespace gpz {
 
 constexpr int NB = 64;
+int g_solve_lookahead = 1;      // "solve_lookahead" option (process-wide)
 
 // W(o..o+32, o..o+32) = inverse of the lower-triangular 32 x 32 block of A at (o,o); lane = column (forward substitution
 // by rows, no cross-lane traffic: L[r][q] is a broadcast read)
@@ -83,46 +84,172 @@ __device__ __forceinline__ bool chol64(double (*A)[NB + 1], double (*colbuf)[NB]
 // m = 1000 evaluation, gpurun_out r02k: a single warp cannot hide the shuffle -> FMA latency chain.)
 
 // factor the nb x nb diagonal block at (k0,k0) in place (lower), invert the factor into Linv (row-major 64 x 64, zero
-// upper triangle), accumulate logdet.  Cholesky of the 64 x 64 block by the whole CTA; the inverse as 2 x 2 blocks of 32:
-// two warps invert the diagonal blocks concurrently, W21 = -W22 L21 W11 by the whole CTA.  Rows/cols >= nb are padded
-// with the identity.
+// upper triangle), accumulate logdet.  Rows/cols >= nb are padded with the identity.
+//
+// This kernel is the serial bottleneck of the blocked solve (16 dependent launches at m = 1000; with 8 GPUs the solve is
+// 15 % of an evaluation), so it is organised to have as few dependent steps as possible: the 64 x 64 block is factored
+// in four 16-column steps.  Per step ONE warp factors the 16 x 16 diagonal sub-block with its rows in registers (pivot and
+// column values move by shuffles: no block barrier inside) and inverts it by forward substitution with the pivots'
+// reciprocal square roots it already has (no division anywhere); then all 256 threads form the sub-panel
+// L21 = A21 L11^-T and apply the rank-16 update to the trailing sub-matrix.  The inverse of the whole factor follows from
+// the four inverted diagonal sub-blocks by block forward substitution (three levels).  ~20 block barriers in total; the
+// column-at-a-time version this replaces (chol64 above, kept for reference) needs 64 for the factorisation alone.
+constexpr int SB = 16;
+
+__device__ __forceinline__ void mm16(double (*Cm)[NB + 1], int ro, int co, double alpha, double (*X)[NB + 1], int xr, int xc,
+                                     double (*Ym)[NB + 1], int yr, int yc, bool Yt, int kdepth) {
+    // C(16 x 16 at (ro,co)) = alpha * X(16 x kdepth at (xr,xc)) * Y, Y(k,j) = Yt ? Ym[yr+j][yc+k] : Ym[yr+k][yc+j]; one thread per entry
+    const int i = threadIdx.x >> 4, j = threadIdx.x & 15;
+    double s0 = 0.0;
+    for (int k = 0; k < kdepth; ++k) s0 = fma(X[xr + i][xc + k], Yt ? Ym[yr + j][yc + k] : Ym[yr + k][yc + j], s0);
+    Cm[ro + i][co + j] = alpha * s0;
+}
+
+//
+// Look-ahead form (LinvPrev != nullptr): the block row left of this diagonal block, A_{k,k-1}, still holds the values BEFORE
+// panel k-1 was applied (the panel solve and trailing update of panel k-1 run concurrently on a side stream and leave this
+// diagonal block alone).  The kernel first forms L_{k,k-1} = A_{k,k-1} Linv_{k-1}' itself and applies its rank-64 update to
+// the diagonal block in shared memory, so that it depends only on the PREVIOUS diagonal block's kernel and on the trailing
+// update of panel k-2.  L goes to Lout (== S in the in-place form).
 __global__ void __launch_bounds__(256)
-potf2_trti_kernel(double* __restrict__ S, int64_t ld, int k0, int nb, double* __restrict__ Linv,
-                  double* __restrict__ logdet, int* __restrict__ flag, int first) {
+potf2_trti_kernel(const double* __restrict__ S, double* __restrict__ Lout, int64_t ld, int k0, int nb, double* __restrict__ Linv,
+                  const double* __restrict__ LinvPrev, double* __restrict__ logdet, int* __restrict__ flag, int first) {
     extern __shared__ double sm_potf[];
     double (*A)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm_potf);
     double (*W)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm_potf + NB * (NB + 1));
     double (*T)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm_potf + 2 * NB * (NB + 1));
-    const int tid = threadIdx.x, warp = tid >> 5;
+    __shared__ int ok_sm;
+    __shared__ double ldsh[2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int e = tid; e < NB * NB; e += 256) {
         const int r = e / NB, c = e % NB;
         A[r][c] = (r < nb && c < nb && c <= r) ? S[static_cast<int64_t>(k0 + r) * ld + k0 + c] : (r == c ? 1.0 : 0.0);
-        W[r][c] = 0.0;
+        W[r][c] = (LinvPrev != nullptr) ? LinvPrev[e] : 0.0;
+        if (LinvPrev != nullptr) T[r][c] = (r < nb) ? S[static_cast<int64_t>(k0 + r) * ld + (k0 - NB) + c] : 0.0;
     }
+    if (tid == 0) ok_sm = 1;
     __syncthreads();
-    __shared__ double colbuf[2][NB];
-    if (!chol64(A, colbuf)) {
-        if (tid == 0) *flag = 1;
-        return;
+    if (LinvPrev != nullptr) {
+        // L_{k,k-1}[r][c] = sum_{q<=c} A_{k,k-1}[r][q] Linv_{k-1}[c][q]; thread: row r = tid / 4, columns c = tid % 4 + 4 j
+        double lrow[NB / 4];
+        const int r = tid >> 2;
+#pragma unroll
+        for (int j = 0; j < NB / 4; ++j) {
+            const int c = (tid & 3) + 4 * j;
+            double s0 = 0.0;
+            for (int q = 0; q <= c; ++q) s0 = fma(T[r][q], W[c][q], s0);
+            lrow[j] = s0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < NB / 4; ++j) T[r][(tid & 3) + 4 * j] = lrow[j];
+        __syncthreads();
+        for (int e = tid; e < NB * NB; e += 256) {
+            const int i = e / NB, j = e % NB;
+            W[i][j] = 0.0;
+            if (j > i || i >= nb) continue;
+            double s0 = 0.0;
+#pragma unroll 8
+            for (int c = 0; c < NB; ++c) s0 = fma(T[i][c], T[j][c], s0);
+            A[i][j] -= s0;
+        }
+        __syncthreads();
     }
-    __shared__ double ldsh[2];
+    for (int jb = 0; jb < NB / SB; ++jb) {
+        const int o = jb * SB;
+        if (warp == 0) {
+            // ---- 16 x 16 diagonal sub-block: Cholesky with lane = row (lanes 16..31 shadow lanes 0..15), then its inverse
+            const int r = lane & 15;
+            double a[SB], rd[SB];
+#pragma unroll
+            for (int q = 0; q < SB; ++q) a[q] = (q <= r) ? A[o + r][o + q] : 0.0;
+            bool ok = true;
+#pragma unroll
+            for (int c = 0; c < SB; ++c) {
+                const double piv = __shfl_sync(0xffffffffu, a[c], c);
+                if (!(piv > 0.0) || !(piv < 1.7e308)) ok = false;
+                const double rl = rsqrt(piv);
+                rd[c] = rl;                                            // 1 / L[c][c]
+                const double l = a[c] * rl;
+                a[c] = (r == c) ? piv * rl : l;
+#pragma unroll
+                for (int q = c + 1; q < SB; ++q) {
+                    const double bq = __shfl_sync(0xffffffffu, l, q);  // L[q][c]
+                    a[q] = fma(-l, bq, a[q]);
+                }
+            }
+            if (lane < SB) {
+#pragma unroll
+                for (int q = 0; q < SB; ++q)
+                    if (q <= r) A[o + r][o + q] = a[q];
+            }
+            if (!ok && lane == 0) ok_sm = 0;
+            __syncwarp();
+            // inverse of the lower-triangular sub-block: lane = column, x_r = (delta_rc - sum_{q<r} L[r][q] x_q) / L[r][r]
+            const int c = lane & 15;
+            double x[SB];
+#pragma unroll
+            for (int rr = 0; rr < SB; ++rr) {
+                double s0 = (rr == c) ? 1.0 : 0.0;
+#pragma unroll
+                for (int q = 0; q < rr; ++q) s0 = fma(-A[o + rr][o + q], x[q], s0);
+                x[rr] = (rr >= c) ? s0 * rd[rr] : 0.0;
+                if (lane < SB) W[o + rr][o + c] = x[rr];
+            }
+        }
+        __syncthreads();
+        if (!ok_sm) {
+            if (tid == 0) *flag = 1;
+            return;
+        }
+        const int rem = NB - o - SB;                                   // rows below this sub-block
+        // ---- sub-panel L21 = A21 W11'  (W11 = L11^-1, lower): L21[r][c] = sum_{q<=c} A21[r][q] W11[c][q]  -> T, then back
+        for (int e = tid; e < rem * SB; e += 256) {
+            const int r = o + SB + e / SB, c = e % SB;
+            double s0 = 0.0;
+            for (int q = 0; q <= c; ++q) s0 = fma(A[r][o + q], W[o + c][o + q], s0);
+            T[r][c] = s0;
+        }
+        __syncthreads();
+        for (int e = tid; e < rem * SB; e += 256) {
+            const int r = o + SB + e / SB, c = e % SB;
+            A[r][o + c] = T[r][c];
+        }
+        // ---- trailing update A22 -= L21 L21' (lower triangle), from T
+        for (int e = tid; e < rem * rem; e += 256) {
+            const int i = e / rem, j = e % rem;
+            if (j > i) continue;
+            double s0 = 0.0;
+#pragma unroll
+            for (int c = 0; c < SB; ++c) s0 = fma(T[o + SB + i][c], T[o + SB + j][c], s0);
+            A[o + SB + i][o + SB + j] -= s0;
+        }
+        __syncthreads();
+    }
     if (warp < 2) {                               // 2 * sum_c log L_cc, fixed order
         double v = 2.0 * log(A[tid][tid]);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
         if ((tid & 31) == 0) ldsh[warp] = v;
     }
-    if (warp == 0) trinv32(A, W, 0);              // W11
-    else if (warp == 1) trinv32(A, W, 32);        // W22
-    __syncthreads();
-    mm32(T, 32, 0, 1.0, A, 32, 0, W, 0, 0, false, 0.0, false);          // T21 = L21 * W11
-    __syncthreads();
-    mm32(W, 32, 0, -1.0, W, 32, 32, T, 32, 0, false, 0.0, false);       // W21 = -W22 * T21
-    __syncthreads();
+    // ---- W = L^-1 by block forward substitution over the 4 x 4 grid of 16-blocks: W_ij = -W_ii (sum_{k=j}^{i-1} L_ik W_kj),
+    //      blocks with the same i - j are independent
+    for (int dist = 1; dist < NB / SB; ++dist) {
+        for (int j = 0; j + dist < NB / SB; ++j) {
+            const int i = j + dist;
+            mm16(T, i * SB, j * SB, 1.0, A, i * SB, j * SB, W, j * SB, j * SB, false, dist * SB);      // T_ij = L_i,[j..i-1] W_[j..i-1],j
+        }
+        __syncthreads();
+        for (int j = 0; j + dist < NB / SB; ++j) {
+            const int i = j + dist;
+            mm16(W, i * SB, j * SB, -1.0, W, i * SB, i * SB, T, i * SB, j * SB, false, SB);            // W_ij = -W_ii T_ij
+        }
+        __syncthreads();
+    }
     for (int e = tid; e < NB * NB; e += 256) {
         const int r = e / NB, c = e % NB;
         Linv[e] = (r < nb && c < nb && c <= r) ? W[r][c] : 0.0;
-        if (r < nb && c < nb && c <= r) S[static_cast<int64_t>(k0 + r) * ld + k0 + c] = A[r][c];
+        if (r < nb && c < nb && c <= r) Lout[static_cast<int64_t>(k0 + r) * ld + k0 + c] = A[r][c];
     }
     if (tid == 0) *logdet = (first ? 0.0 : *logdet) + (ldsh[0] + ldsh[1]);
 }
@@ -148,6 +275,13 @@ int solve_ws_alloc(SolveWs& ws, int MP) {
     GPZ_CUDA(cudaMalloc(&ws.Linv, sizeof(double) * nblk * NB * NB));
     GPZ_CUDA(cudaMalloc(&ws.tmp, sizeof(double) * NB * MP));
     GPZ_CUDA(cudaMalloc(&ws.flag, sizeof(int)));
+    // look-ahead factorisation: L is written to its own matrix, the panel GEMMs run on a side stream
+    GPZ_CUDA(cudaMalloc(&ws.Lbuf, sizeof(double) * MP * MP));
+    GPZ_CUDA(cudaStreamCreateWithFlags(&ws.side, cudaStreamNonBlocking));
+    for (int i = 0; i < SolveWs::MAXBLK; ++i) {
+        GPZ_CUDA(cudaEventCreateWithFlags(&ws.evP[i], cudaEventDisableTiming));
+        GPZ_CUDA(cudaEventCreateWithFlags(&ws.evT[i], cudaEventDisableTiming));
+    }
     return GPZ_OK;
 }
 
@@ -156,6 +290,12 @@ void solve_ws_free(SolveWs& ws) {
     cudaFree(ws.Linv);
     cudaFree(ws.tmp);
     cudaFree(ws.flag);
+    cudaFree(ws.Lbuf);
+    if (ws.side) cudaStreamDestroy(ws.side);
+    for (int i = 0; i < SolveWs::MAXBLK; ++i) {
+        if (ws.evP[i]) cudaEventDestroy(ws.evP[i]);
+        if (ws.evT[i]) cudaEventDestroy(ws.evT[i]);
+    }
     ws = SolveWs();
 }
 
@@ -169,25 +309,45 @@ int spd_inverse(double* S, int m, int MP, double* Sinv, double* d_logdet, SolveW
     if (once.need()) {
         GPZ_CUDA(cudaFuncSetAttribute(potf2_trti_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kPotfSmem)));
     }
-    // ---- blocked Cholesky: S(lower) <- L
+    // ---- blocked Cholesky.  Look-ahead form: the diagonal-block kernels form ONE dependent chain on `st` (each applies the
+    //      previous panel's update to its own block itself, see potf2_trti_kernel), the panel solves and trailing updates form a
+    //      second chain on the side stream; the two only meet through events: diagonal block k needs trailing update k-2,
+    //      panel solve k needs diagonal block k.  L is written to ws.Lbuf (the panel solve is out of place so that the next
+    //      diagonal kernel can still read A_{k+1,k}), S keeps being updated as the trailing matrix.
+    const bool la = g_solve_lookahead && ws.side != nullptr && nblk >= 3 && nblk <= SolveWs::MAXBLK;
+    double* Lm = la ? ws.Lbuf : S;
     for (int kb = 0; kb < nblk; ++kb) {
         const int k0 = kb * NB;
         const int nb = (m - k0 < NB) ? (m - k0) : NB;
         double* Lk = ws.Linv + static_cast<int64_t>(kb) * NB * NB;
-        potf2_trti_kernel<<<1, 256, kPotfSmem, st>>>(S, ld, k0, nb, Lk, d_logdet, ws.flag, kb == 0);
+        if (la && kb >= 2) GPZ_CUDA(cudaStreamWaitEvent(st, ws.evT[kb - 2], 0));
+        potf2_trti_kernel<<<1, 256, kPotfSmem, st>>>(S, Lm, ld, k0, nb, Lk, (la && kb > 0) ? Lk - NB * NB : nullptr, d_logdet, ws.flag,
+                                                     kb == 0);
         GPZ_KERNEL_CHECK();
         ++*launches;
         const int rem = m - k0 - nb;
         if (rem > 0) {
-            double* panel = S + static_cast<int64_t>(k0 + nb) * ld + k0;
-            // L_ik = A_ik * Linv_kk'   (B(k,j) = Linv[j][k])
-            rc = sgemm(rem, nb, nb, 1.0, panel, ld, 1, Lk, 1, NB, 0.0, panel, ld, 0, st, launches);
-            if (rc) return rc;
-            // trailing: A_ij -= L_ik L_jk'  (lower tiles only)
+            const double* panelA = S + static_cast<int64_t>(k0 + nb) * ld + k0;
+            double* panelL = Lm + static_cast<int64_t>(k0 + nb) * ld + k0;
             double* trail = S + static_cast<int64_t>(k0 + nb) * ld + (k0 + nb);
-            rc = sgemm(rem, rem, nb, -1.0, panel, ld, 1, panel, 1, ld, 1.0, trail, ld, 1, st, launches);
+            cudaStream_t sg = st;
+            if (la) {
+                GPZ_CUDA(cudaEventRecord(ws.evP[kb], st));
+                GPZ_CUDA(cudaStreamWaitEvent(ws.side, ws.evP[kb], 0));
+                sg = ws.side;
+            }
+            // L_ik = A_ik * Linv_kk'   (B(k,j) = Linv[j][k])
+            rc = sgemm(rem, nb, nb, 1.0, panelA, ld, 1, Lk, 1, NB, 0.0, panelL, ld, 0, sg, launches);
             if (rc) return rc;
+            // trailing: A_ij -= L_ik L_jk'  (lower tiles only; look-ahead: not the next diagonal block, its kernel does that)
+            rc = sgemm(rem, rem, nb, -1.0, panelL, ld, 1, panelL, 1, ld, 1.0, trail, ld, la ? 2 : 1, sg, launches);
+            if (rc) return rc;
+            if (la) GPZ_CUDA(cudaEventRecord(ws.evT[kb], ws.side));
         }
+    }
+    if (la) {                                        // join: everything the side stream did precedes the inverse below
+        const int last = nblk - 2;                   // the last panel with rows below it
+        GPZ_CUDA(cudaStreamWaitEvent(st, ws.evT[last], 0));
     }
     // ---- W = L^{-1} (lower triangular) by recursive doubling: the diagonal 64-blocks are already inverted; at block size b
     //      every pair of neighbouring inverted blocks [1 | 2] is merged with W21 = -W22 * (L21 * W11), all pairs in one
@@ -202,7 +362,7 @@ int spd_inverse(double* S, int m, int MP, double* Sinv, double* d_logdet, SolveW
     for (int b = NB; b < m; b *= 2) {
         const int npairs = static_cast<int>(ceil_div(m - b, 2 * b));        // pairs whose block 2 is non-empty
         const int64_t bs = static_cast<int64_t>(2 * b) * ld + 2 * b;         // pointer step from pair to pair
-        const double* L21 = S + static_cast<int64_t>(b) * ld;
+        const double* L21 = Lm + static_cast<int64_t>(b) * ld;
         const double* W11 = ws.W;
         const double* W22 = ws.W + static_cast<int64_t>(b) * ld + b;
         double* T21 = Sinv + static_cast<int64_t>(b) * ld;
