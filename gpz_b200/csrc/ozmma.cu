@@ -52,7 +52,7 @@ struct OzmmaArgs {
     int mode;                 // 0: fp64 partial tiles, 1: T-GEMM epilogue, 2: PHI = exp(.) epilogue
     int mn_major;             // operands stored [k][row] (row index contiguous) instead of [row][k]
     int lgroup;               // levels multiplied together: 2 (default, shared operand tiles) or 1 (one level at a time)
-    int prefetch;             // mode 1: prefetch the epilogue's PHI block into L2 (default 1; 0 for A/B measurements)
+    int prefetch;             // mode 1: prefetch the epilogue's PHI block into L2 (option "ozaki_prefetch", default 0)
     int kmma;                 // 32-byte K steps multiplied per 128-byte stage (4; fewer when the operands' K extent is < 97: PHI build)
     int nint;                 // the first nint levels of a unit (emax, emax-1, ..) are folded EXACTLY in int64; the host picks the
                               // largest count whose sum cannot overflow, and 0 when a unit folds more than one K chunk
@@ -679,7 +679,7 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-int g_lgroup = 2, g_prefetch = 1, g_ifold = 1;
+int g_lgroup = 2, g_prefetch = 0, g_ifold = 1;       // prefetch: +1.5 % speed but +7 GB of DRAM reads per T-GEMM (r02p capture): off
 
 // number of lowest levels (emax, emax-1, ..) whose exact integer sum sum_i L_i 256^i fits 62 bits, |L_e| <= pairs(e) K 2^14
 int int_levels(int s, int emin, int emax, int kchunk, int gchunks) {
