@@ -2147,16 +2147,37 @@ int gpz_inv_logdet(int32_t m, const double* X, double* Xi, double* logdet, int d
     int flag = 0;
     double hl = 0.0;
     if (!rc) {
-        GPZ_CUDA(cudaMemcpy2DAsync(Xi, sizeof(double) * m, Si, sizeof(double) * MP, sizeof(double) * m, m, cudaMemcpyDeviceToHost, st));
-        GPZ_CUDA(cudaMemcpyAsync(&hl, ld, sizeof(double), cudaMemcpyDeviceToHost, st));
+        double* mm = nullptr;
+        double hmm[2] = {1.0, 1.0};
+        GPZ_CUDA(cudaMalloc(&mm, sizeof(double) * (m + 2)));
+        if ((rc = chol_diag_minmax(ws, S, m, static_cast<int>(MP), mm, st))) return rc;
+        GPZ_CUDA(cudaMemcpyAsync(hmm, mm, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
         GPZ_CUDA(cudaMemcpyAsync(&flag, ws.flag, sizeof(int), cudaMemcpyDeviceToHost, st));
         GPZ_CUDA(cudaStreamSynchronize(st));
-        if (flag) {
-            const double nan_ = nan("");
-            for (int64_t i = 0; i < static_cast<int64_t>(m) * m; ++i) Xi[i] = nan_;
-            hl = nan_;
+        // The reference pseudo-inverts by SVD and drops singular values <= m eps(max s) (inv_logdet.m:7-12).  The Cholesky route is
+        // that same inverse while every singular value is kept; when the factorisation fails (not positive definite: rank
+        // deficient or indefinite) or the factor's diagonal says cond(X) >= (max L_ii / min L_ii)^2 comes within 1e3 of
+        // 1 / (m eps), the truncating SVD itself is run (one-sided Jacobi, solve.cu)
+        const double ratio = (hmm[0] > 0.0) ? hmm[1] / hmm[0] : 1e300;
+        const bool near_singular = flag || !(ratio * ratio * 1e3 < 1.0 / (static_cast<double>(m) * 2.220446049250313e-16));
+        if (near_singular) {
+            int* cnt = nullptr;
+            GPZ_CUDA(cudaMalloc(&cnt, sizeof(int)));
+            GPZ_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * MP * MP, st));
+            GPZ_CUDA(cudaMemcpy2DAsync(S, sizeof(double) * MP, X, sizeof(double) * m, sizeof(double) * m, m, cudaMemcpyHostToDevice, st));
+            rc = svd_pinv_logdet(S, m, static_cast<int>(MP), ws.W, Si, &hl, cnt, mm, st, &launches);
+            cudaFree(cnt);
+            if (!rc) {
+                GPZ_CUDA(cudaMemcpy2DAsync(Xi, sizeof(double) * m, Si, sizeof(double) * MP, sizeof(double) * m, m, cudaMemcpyDeviceToHost, st));
+                GPZ_CUDA(cudaStreamSynchronize(st));
+            }
+        } else {
+            GPZ_CUDA(cudaMemcpy2DAsync(Xi, sizeof(double) * m, Si, sizeof(double) * MP, sizeof(double) * m, m, cudaMemcpyDeviceToHost, st));
+            GPZ_CUDA(cudaMemcpyAsync(&hl, ld, sizeof(double), cudaMemcpyDeviceToHost, st));
+            GPZ_CUDA(cudaStreamSynchronize(st));
         }
-        if (logdet) *logdet = hl;
+        cudaFree(mm);
+        if (!rc && logdet) *logdet = hl;
     }
     cudaFree(S);
     cudaFree(Si);

@@ -133,6 +133,11 @@ void solve_ws_free(SolveWs& ws);
 int spd_inverse(double* S, int m, int MP, double* Sinv, double* d_logdet, SolveWs& ws, cudaStream_t st,
                 int64_t* launches);
 
+// reference semantics of inv_logdet.m (SVD pseudo-inverse with truncation) for the exported gpz_inv_logdet: one-sided Jacobi
+int svd_pinv_logdet(double* G, int m, int MP, double* V, double* Xi, double* h_logdet, int* d_counter, double* d_vec, cudaStream_t st,
+                    int64_t* launches);
+int chol_diag_minmax(const SolveWs& ws, const double* S, int m, int MP, double* d_out2, cudaStream_t st);
+
 // ---- backproj.cu
 int build_features(const Params& P, const double* X, int64_t n, int64_t r0, int64_t r1, double* F, cudaStream_t st,
                    int64_t* launches);

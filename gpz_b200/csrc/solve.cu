@@ -4,6 +4,9 @@
 // block factored and inverted by one CTA in shared memory, panel solve and trailing update as DMMA
 // GEMMs), a blocked triangular inverse (recursive doubling) and one W'W product.  A non-positive pivot raises a device
 // flag; the caller turns that into NaN outputs (SURVEY.md 8b "error convention", H3).
+#include <algorithm>
+#include <vector>
+
 #include "internal.cuh"
 
 namespace gpz {
@@ -381,6 +384,175 @@ int spd_inverse(double* S, int m, int MP, double* Sinv, double* d_logdet, SolveW
     ++*launches;
     rc = sgemm(m, m, m, 1.0, ws.W, 1, ld, ws.W, ld, 1, 0.0, Sinv, ld, 0, st, launches);
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pseudo-inverse and log-determinant with the reference's SVD semantics (GPz/inv_logdet.m:3-15):
+//     [U,S,V] = svd(X); tol = m * eps(max s); keep s > tol; Xi = V diag(1/s) U'; logdet = sum(log s) over the kept ones.
+// Used by gpz_inv_logdet when the Cholesky route fails or the factor says cond(X) is beyond 1 / (m eps) -- the regime where the
+// reference truncates.  One-sided (Hestenes) Jacobi on the ROWS of G = V X, V orthogonal: rotations make the rows of G mutually
+// orthogonal, then X = V' diag(s) W' with s_j = |g_j|, w_j = g_j / s_j, and pinv(X) = sum_j g_j v_j' / s_j^2 = G' diag(1/s^2) V.
+// Round-robin ordering: M/2 disjoint row pairs per step (one CTA each), M - 1 steps per sweep; all reductions in fixed order.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+jacobi_step_kernel(double* __restrict__ G, double* __restrict__ V, int64_t ld, int m, int M, int step, int* __restrict__ rotations) {
+    __shared__ double sh[8];
+    __shared__ double cs[2];
+    const int i = blockIdx.x;
+    int p, q;
+    if (i == 0) {
+        p = M - 1;
+        q = step;
+    } else {
+        p = (step + i) % (M - 1);
+        q = (step - i + (M - 1)) % (M - 1);
+    }
+    if (p >= m || q >= m) return;                      // padding row of an odd m
+    if (p > q) {
+        const int t = p;
+        p = q;
+        q = t;
+    }
+    double* gp = G + static_cast<int64_t>(p) * ld;
+    double* gq = G + static_cast<int64_t>(q) * ld;
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int j = threadIdx.x; j < m; j += 256) {
+        const double x = gp[j], y = gq[j];
+        a = fma(x, x, a);
+        b = fma(y, y, b);
+        c = fma(x, y, c);
+    }
+    a = block_sum<256>(a, sh);
+    b = block_sum<256>(b, sh);
+    c = block_sum<256>(c, sh);
+    if (threadIdx.x == 0) {
+        double cc = 1.0, ss = 0.0;
+        const double lim = 4.0 * 2.220446049250313e-16 * sqrt(a) * sqrt(b);
+        if (fabs(c) > lim && a > 0.0 && b > 0.0) {
+            const double zeta = (b - a) / (2.0 * c);
+            const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            cc = 1.0 / sqrt(1.0 + t * t);
+            ss = cc * t;
+            atomicAdd(rotations, 1);
+        }
+        cs[0] = cc;
+        cs[1] = ss;
+    }
+    __syncthreads();
+    const double cc = cs[0], ss = cs[1];
+    if (ss == 0.0) return;
+    double* vp = V + static_cast<int64_t>(p) * ld;
+    double* vq = V + static_cast<int64_t>(q) * ld;
+    for (int j = threadIdx.x; j < m; j += 256) {
+        const double x = gp[j], y = gq[j];
+        gp[j] = cc * x - ss * y;
+        gq[j] = ss * x + cc * y;
+        const double u = vp[j], w = vq[j];
+        vp[j] = cc * u - ss * w;
+        vq[j] = ss * u + cc * w;
+    }
+}
+
+__global__ void identity_kernel(double* __restrict__ V, int64_t ld, int m) {
+    const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= static_cast<int64_t>(m) * ld) return;
+    const int r = static_cast<int>(e / ld), c = static_cast<int>(e % ld);
+    V[e] = (r == c && c < m) ? 1.0 : 0.0;
+}
+
+__global__ void __launch_bounds__(256) row_norm2_kernel(const double* __restrict__ G, int64_t ld, int m, double* __restrict__ n2) {
+    __shared__ double sh[8];
+    const double* g = G + static_cast<int64_t>(blockIdx.x) * ld;
+    double a = 0.0;
+    for (int j = threadIdx.x; j < m; j += 256) a = fma(g[j], g[j], a);
+    a = block_sum<256>(a, sh);
+    if (threadIdx.x == 0) n2[blockIdx.x] = a;
+}
+
+__global__ void scale_rows_kernel(double* __restrict__ G, int64_t ld, int m, const double* __restrict__ f) {
+    const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= static_cast<int64_t>(m) * ld) return;
+    G[e] *= f[e / ld];
+}
+
+// G: [MP][MP] holding X (m x m valid, row-major) on entry -- destroyed; V, Xi: [MP][MP] scratch / result; *h_logdet on the host
+int svd_pinv_logdet(double* G, int m, int MP, double* V, double* Xi, double* h_logdet, int* d_counter, double* d_vec, cudaStream_t st,
+                    int64_t* launches) {
+    const int64_t ld = MP;
+    const int M = (m + 1) / 2 * 2;
+    identity_kernel<<<static_cast<unsigned>(ceil_div(static_cast<int64_t>(m) * ld, 256)), 256, 0, st>>>(V, ld, m);
+    GPZ_KERNEL_CHECK();
+    int rot = 1;
+    for (int sweep = 0; sweep < 40 && rot > 0 && M > 1; ++sweep) {
+        GPZ_CUDA(cudaMemsetAsync(d_counter, 0, sizeof(int), st));
+        for (int step = 0; step < M - 1; ++step) {
+            jacobi_step_kernel<<<M / 2, 256, 0, st>>>(G, V, ld, m, M, step, d_counter);
+            ++*launches;
+        }
+        GPZ_KERNEL_CHECK();
+        GPZ_CUDA(cudaMemcpyAsync(&rot, d_counter, sizeof(int), cudaMemcpyDeviceToHost, st));
+        GPZ_CUDA(cudaStreamSynchronize(st));
+    }
+    row_norm2_kernel<<<m, 256, 0, st>>>(G, ld, m, d_vec);
+    GPZ_KERNEL_CHECK();
+    std::vector<double> n2(static_cast<size_t>(m));
+    GPZ_CUDA(cudaMemcpyAsync(n2.data(), d_vec, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+    GPZ_CUDA(cudaStreamSynchronize(st));
+    double smax = 0.0;
+    for (double v : n2) smax = fmax(smax, sqrt(v));
+    int ex = 0;
+    frexp(smax, &ex);                                             // smax in [2^(ex-1), 2^ex): eps(smax) = 2^(ex-1-52)
+    const double tol = static_cast<double>(m) * (smax > 0.0 ? ldexp(1.0, ex - 53) : 0.0);      // inv_logdet.m:7
+    double ldet = 0.0;
+    std::vector<double> f(static_cast<size_t>(m), 0.0);
+    std::vector<double> kept;
+    for (int j = 0; j < m; ++j) {
+        const double sj = sqrt(n2[j]);
+        if (sj > tol) {
+            f[j] = 1.0 / n2[j];
+            kept.push_back(sj);
+        }
+    }
+    std::sort(kept.begin(), kept.end(), [](double a, double b) { return a > b; });             // svd order, as sum(log(s)) adds them
+    for (double sj : kept) ldet += log(sj);
+    *h_logdet = ldet;
+    GPZ_CUDA(cudaMemcpyAsync(d_vec, f.data(), sizeof(double) * m, cudaMemcpyHostToDevice, st));
+    scale_rows_kernel<<<static_cast<unsigned>(ceil_div(static_cast<int64_t>(m) * ld, 256)), 256, 0, st>>>(G, ld, m, d_vec);
+    GPZ_KERNEL_CHECK();
+    GPZ_CUDA(cudaMemsetAsync(Xi, 0, sizeof(double) * MP * MP, st));
+    // Xi = G' V  (A(i,k) = G[k][i], B(k,j) = V[k][j])
+    return sgemm(m, m, m, 1.0, G, 1, ld, V, ld, 1, 0.0, Xi, ld, 0, st, launches);
+}
+
+// (max L_ii / min L_ii)^2 <= cond(X) for the Cholesky factor L: cheap lower bound used to decide whether the reference's
+// SVD truncation would have been active
+__global__ void __launch_bounds__(256) diag_minmax_kernel(const double* __restrict__ L, int64_t ld, int m, double* __restrict__ out) {
+    __shared__ double smin[256], smax[256];
+    double lo = 1.7e308, hi = 0.0;
+    for (int j = threadIdx.x; j < m; j += 256) {
+        const double v = fabs(L[static_cast<int64_t>(j) * ld + j]);
+        lo = fmin(lo, v);
+        hi = fmax(hi, v);
+    }
+    smin[threadIdx.x] = lo;
+    smax[threadIdx.x] = hi;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int t = 1; t < 256; ++t) {
+            lo = fmin(lo, smin[t]);
+            hi = fmax(hi, smax[t]);
+        }
+        out[0] = lo;
+        out[1] = hi;
+    }
+}
+
+int chol_diag_minmax(const SolveWs& ws, const double* S, int m, int MP, double* d_out2, cudaStream_t st) {
+    const int nblk = static_cast<int>(ceil_div(m, NB));
+    const bool la = g_solve_lookahead && ws.side != nullptr && nblk >= 3 && nblk <= SolveWs::MAXBLK;
+    diag_minmax_kernel<<<1, 256, 0, st>>>(la ? ws.Lbuf : S, MP, m, d_out2);
+    GPZ_KERNEL_CHECK();
+    return GPZ_OK;
 }
 
 }  // namespace gpz

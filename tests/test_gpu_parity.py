@@ -179,8 +179,8 @@ def test_inv_logdet_and_dxy():
         Xi, ld = L.inv_logdet(S)
         Xr, ldr = O.inv_logdet(S)
         assert rel(Xi, Xr) <= 1e-9 and abs(ld - ldr) <= 1e-10 * abs(ldr)
-    Xi, ld = L.inv_logdet(-np.eye(4))           # not SPD: NaN out, status 0 (reference tolerates NaN)
-    assert np.isnan(ld) and np.isnan(Xi).all()
+    Xi, ld = L.inv_logdet(-np.eye(4))           # not SPD: the truncating SVD of inv_logdet.m:3-15 (round 1 returned NaN here)
+    assert rel(Xi, -np.eye(4)) <= 1e-14 and abs(ld) <= 1e-14
     X, P = rng.standard_normal((300, 4)), rng.standard_normal((17, 4))
     assert rel(L.dxy(X, P), O.Dxy(X, P)) <= 1e-13
     # init.m:62 takes the column means; gpz_dxy_colmean reduces them on the device (ragged chunk: 9001 rows)
@@ -449,6 +449,35 @@ def test_digit_gemm_propagates_non_finite_inputs():
     assert np.all(np.isnan(L.dgemm_nt(A, B)))
     with pytest.raises(L.GpzError):
         L.dgemm_nt(np.ones((4, 20000)), np.ones((4, 20000)))    # K beyond the exact-accumulation bound
+
+
+@pytest.mark.parametrize("case", ["rank_deficient", "gap_to_1e-18", "indefinite", "odd_m_rank_deficient"])
+def test_inv_logdet_reference_svd_semantics(case):
+    """GPz/inv_logdet.m:3-15 pseudo-inverts by SVD and DROPS singular values <= m eps(max s); logdet sums the kept ones.
+    gpz_inv_logdet takes the Cholesky route while that cannot differ and runs the truncating SVD itself (one-sided Jacobi on
+    the device) when the factorisation fails or the factor shows cond(X) near 1 / (m eps): rank-deficient, numerically
+    singular and indefinite inputs then follow the reference instead of returning NaN (round 1)."""
+    rng = np.random.default_rng(7)
+    m = 300 if case != "odd_m_rank_deficient" else 77
+    Q, _ = np.linalg.qr(rng.standard_normal((m, m)))
+    if case in ("rank_deficient", "odd_m_rank_deficient"):
+        B = rng.standard_normal((m, m // 3))
+        X = B @ B.T
+    elif case == "gap_to_1e-18":
+        lam = np.concatenate([np.logspace(0, -4, m // 2), 1e-18 * (1.0 + rng.random(m - m // 2))])
+        X = (Q * lam) @ Q.T
+    else:
+        lam = np.concatenate([np.logspace(0, -3, m // 2), -np.logspace(0, -3, m - m // 2)])
+        X = (Q * lam) @ Q.T
+    X = 0.5 * (X + X.T)
+    Xi0, ld0 = O.inv_logdet(X)
+    Xi, ld = L.inv_logdet(X)
+    assert np.all(np.isfinite(Xi)) and np.isfinite(ld)
+    s = np.linalg.svd(X, compute_uv=False)
+    kept = s[s > m * np.spacing(s.max())]
+    tol = 1e-9 * kept.max() / kept.min()          # pinv accuracy ~ cond of the KEPT part x eps, with margin
+    assert rel(Xi, Xi0) <= max(tol, 1e-10), (case, rel(Xi, Xi0), tol)
+    assert abs(ld - ld0) <= 1e-9 * max(1.0, abs(ld0)), (case, ld, ld0)
 
 
 @pytest.mark.parametrize("slices", [0, 7])
