@@ -521,6 +521,7 @@ struct gpz_ctx {
     double* oz_ea = nullptr;        // [rows] row scales of D8
     int opt_ozaki_gs = -1;          // digits used by the Gram (<= opt_ozaki)
     int opt_gc_fast = 1;            // GC + Psi through per-row factorisations + GEMMs (gcpsi.cu); 0: generic per-(i,j) kernels
+    int opt_gc_int8 = 1;            // ... with its two K-major GEMMs (F W, dPHI G) on the int8 tensor cores when K > 128 (d >= 15)
     bool gc_fast = false;
     int gc_ns = 1;
     double* gc_ws = nullptr;
@@ -948,6 +949,46 @@ int ensure_workspace(gpz_ctx* c) {
         c->oz_F8 = reinterpret_cast<int8_t*>(tmp);
         max_abs_kernel<<<1, 1024, 0, c->st>>>(c->tr.Y, n, c->d_scal + 1);
         GPZ_KERNEL_CHECK();
+    }
+    if (c->gc_fast && c->opt_gc_int8 && c->opt_ozaki > 0 && gc_feature_width(P.d) > 128) {
+        // digit GEMMs of the GC + Psi path: the left operands' digits live in the PHI digit buffer (free at those points of the
+        // evaluation: before the digits of PHI are made / after the T-GEMM consumed them)
+        const int KQ = gc_feature_width(P.d), K128 = static_cast<int>(round_up(KQ, 128)), KN = static_cast<int>(round_up(KQ, TILE));
+        double* t1 = nullptr;
+        double* t2 = nullptr;
+        double *e1 = nullptr, *e2 = nullptr;
+        if ((rc = A(&t1, MP * 7 * K128 / 8 + 1)) || (rc = A(&t2, static_cast<int64_t>(KN) * 7 * MP / 8 + 1)) || (rc = A(&e1, MP)) || (rc = A(&e2, KN))) return rc;
+        int8_t* a8 = c->oz_D8;
+        if (K128 > MP) {                      // few bases: the feature digits are wider than a PHI row's
+            const int64_t rows = n < c->chunk_rows ? (n > 0 ? n : 1) : c->chunk_rows;
+            double* t3 = nullptr;
+            if ((rc = A(&t3, oz_padded_rows(rows) * 7 * K128 / 8 + 1))) return rc;
+            a8 = reinterpret_cast<int8_t*>(t3);
+        }
+        const int64_t crow = n < c->chunk_rows ? (n > 0 ? n : 1) : c->chunk_rows;
+        double *t4 = nullptr, *e3 = nullptr, *t5 = nullptr;
+        int8_t* x8 = c->oz_F8;
+        if (x8 == nullptr) {                  // Gram not on the digit kernel: no second PHI digit buffer to borrow
+            double* t6 = nullptr;
+            if ((rc = A(&t6, oz_digit_bytes(static_cast<int>(MP), 7, crow) / 8 + 1))) return rc;
+            x8 = reinterpret_cast<int8_t*>(t6);
+        }
+        if ((rc = A(&t4, oz_padded_rows(crow) * 7 * K128 / 8 + 1)) || (rc = A(&e3, oz_padded_rows(crow))) ||
+            (rc = A(&t5, oz_moment_workspace_bytes(static_cast<int>(MP), KQ, crow) / 8 + 1))) return rc;
+        for (RowData* R : {&c->tr, &c->va}) {
+            if (R->n > n) continue;           // the digit buffer is sized for the training rows of a chunk: a larger validation set keeps the DMMA GEMMs
+            R->gc_digits = 7;
+            R->gcF8 = reinterpret_cast<int8_t*>(t4);
+            R->gcEaF = e3;
+            R->gcX8 = x8;                     // the second PHI digit buffer: free after the Gram
+            R->gcMws = t5;
+            R->gcA8 = a8;
+            R->gcEa = c->oz_ea;
+            R->gcWD8 = reinterpret_cast<int8_t*>(t1);
+            R->gcEbW = e1;
+            R->gcGD8 = reinterpret_cast<int8_t*>(t2);
+            R->gcEbG = e2;
+        }
     }
     if ((rc = solve_ws_alloc(c->sws, static_cast<int>(MP)))) return rc;
     c->tr.flag = c->va.flag = c->sws.flag;          // non-finite coefficients seen by the int8 PHI build raise the same failure flag
@@ -2447,6 +2488,14 @@ int gpz_set_option(gpz_ctx* c, const char* name, double value) {
             return GPZ_ERR_USAGE;
         }
         c->opt_ozaki = static_cast<int>(value);
+        return GPZ_OK;
+    }
+    if (strcmp(name, "gc_int8") == 0) {
+        if (c->ws_ready) {
+            set_error("%s must be set before the first evaluation", name);
+            return GPZ_ERR_USAGE;
+        }
+        c->opt_gc_int8 = value != 0.0;
         return GPZ_OK;
     }
     if (strcmp(name, "gc_fast") == 0) {

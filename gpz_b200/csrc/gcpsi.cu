@@ -17,6 +17,8 @@
 
 namespace gpz {
 
+constexpr int GC_BP_WARPS = 12;      // warps per SM of gc_rows_backproj_kernel (its partial-sum slots)
+
 int gc_feature_width(int d) { return static_cast<int>(round_up(1 + d + d * (d + 1) / 2, 32)); }
 static int gc_gwidth(int d) { return static_cast<int>(round_up(gc_feature_width(d), TILE)); }      // N of the row-tile GEMM dPHI G
 
@@ -190,12 +192,13 @@ int gc_features(const Params& P, const RowData& R, int64_t r0, int64_t r1, cudaS
 //   sum_i [ a_i z z' - z y' - y z' + M V M - a_i M ],  y = M u        and (lane 0) s = sum_i a_i
 // smem per warp: M (d x d), V then T = M V (d x d), u, z.   partial: [warps_total][d*d + 1]
 template <int DMAX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 gc_rows_backproj_kernel(int d, int KQ, int KN, int64_t rows, const double* __restrict__ F, const double* __restrict__ G1,
                         double* __restrict__ partial, int accumulate) {
     extern __shared__ double gc_sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gw = blockIdx.x * 8 + warp, nw = gridDim.x * 8;
+    const int wpb = blockDim.x >> 5;
+    const int gw = blockIdx.x * wpb + warp, nw = gridDim.x * wpb;
     double* Ms = gc_sm + static_cast<int64_t>(warp) * (2 * DMAX * DMAX + 2 * DMAX);
     double* Vs = Ms + DMAX * DMAX;
     double* us = Vs + DMAX * DMAX;
@@ -265,18 +268,11 @@ gc_finish_kernel(Params P, int KQ, const double* __restrict__ partial, int nw, c
     const int tid = threadIdx.x;
     double* B = work;                 // [d*d]
     double* T = work + d * d;         // [d*d]
-    __shared__ double s_tot;
-    if (tid == 0) {
-        double s = 0.0;
-        for (int w = 0; w < nw; ++w) s += partial[static_cast<int64_t>(w) * (d * d + 1) + d * d];
-        s_tot = s;
-    }
-    __syncthreads();
+    // partial: the per-warp partials already summed over the warps by gc_partial_sum_kernel -> [d*d + 1]
+    const double s_tot = partial[d * d];
     for (int e = tid; e < d * d; e += 256) {
-        double v = 0.0;
-        for (int w = 0; w < nw; ++w) v += partial[static_cast<int64_t>(w) * (d * d + 1) + e];
         const int a = e / d, b = e % d;
-        B[e] = 0.5 * (s_tot * P.Aj[(static_cast<int64_t>(a) * d + b) * MP] + v);
+        B[e] = 0.5 * (s_tot * P.Aj[(static_cast<int64_t>(a) * d + b) * MP] + partial[e]);
     }
     __syncthreads();
     for (int e = tid; e < d * d; e += 256) {          // T = B Sigma
@@ -299,25 +295,42 @@ gc_finish_kernel(Params P, int KQ, const double* __restrict__ partial, int nw, c
         for (int b = 0; b < d; ++b) s += P.Gam[(static_cast<int64_t>(c) * dp + b) * MP] * B[b * d + a];
         dG[c + a * d] = -2.0 * s;
     }
-    for (int j = tid; j < m; j += 256) {
-        const double* r = R2 + static_cast<int64_t>(j) * KQ;
-        for (int a = 0; a < d; ++a) {
-            double v = r[1 + a];
-            for (int b = 0; b < d; ++b) {
-                const int lo = a < b ? a : b, hi = a < b ? b : a;
-                const int idx = 1 + d + lo * d - lo * (lo - 1) / 2 + (hi - lo);
-                v -= r[idx] * P.Pt[b * MP + j];
-            }
-            dP[a * m + j] = v;
-        }
+}
+
+// out[e] = sum over the nw per-warp partials of entry e, in warp order per thread slice and a fixed-order block sum
+__global__ void __launch_bounds__(256)
+gc_partial_sum_kernel(const double* __restrict__ partial, int nw, int stride, double* __restrict__ out) {
+    __shared__ double sh[8];
+    const int e = blockIdx.x;
+    double v = 0.0;
+    for (int w = threadIdx.x; w < nw; w += 256) v += partial[static_cast<int64_t>(w) * stride + e];
+    v = block_sum<256>(v, sh);
+    if (threadIdx.x == 0) out[e] = v;
+}
+
+// dP_j = R2[j][1..d] - mat(R2[j][1+d..]) p_j : one thread per (basis, dimension) (it was a loop over the bases inside the single
+// block above: 2.7 ms of a 105 ms evaluation at m = 2000, d = 32)
+__global__ void __launch_bounds__(256)
+gc_dp_kernel(Params P, int KQ, const double* __restrict__ R2, double* __restrict__ dP) {
+    const int d = P.d, MP = P.MP, m = P.m;
+    const int64_t e = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+    if (e >= static_cast<int64_t>(m) * d) return;
+    const int j = static_cast<int>(e % m), a = static_cast<int>(e / m);
+    const double* r = R2 + static_cast<int64_t>(j) * KQ;
+    double v = r[1 + a];
+    for (int b = 0; b < d; ++b) {
+        const int lo = a < b ? a : b, hi = a < b ? b : a;
+        const int idx = 1 + d + lo * d - lo * (lo - 1) / 2 + (hi - lo);
+        v -= r[idx] * P.Pt[b * MP + j];
     }
+    dP[a * m + j] = v;
 }
 
 int64_t gc_backproj_ws_doubles(const Params& P, int64_t chunk_rows, int nsplit, int sm_count) {
     const int KQ = gc_feature_width(P.d);
-    const int64_t nw = static_cast<int64_t>(sm_count) * 8;
+    const int64_t nw = static_cast<int64_t>(sm_count) * GC_BP_WARPS;
     return chunk_rows * gc_gwidth(P.d) /*G1*/ + static_cast<int64_t>(nsplit) * (P.MP / TILE) * (KQ / 32) * TILE * 32 /*atb partial*/ +
-           static_cast<int64_t>(P.MP) * KQ /*R2*/ + nw * (P.d * P.d + 1) + 2LL * P.d * P.d;
+           static_cast<int64_t>(P.MP) * KQ /*R2*/ + nw * (P.d * P.d + 1) + 3LL * P.d * P.d + 8;
 }
 
 // one chunk of rows: dPhi row 0 = row r0; R.gcF holds this chunk's features (row r0 at index 0)
@@ -330,23 +343,36 @@ int gc_backproj(const Params& P, const RowData& R, int64_t r0, int64_t r1, const
     double* R2 = atbp + static_cast<int64_t>(nsplit) * (P.MP / TILE) * (KQ / 32) * TILE * 32;
     double* partial = R2 + static_cast<int64_t>(P.MP) * KQ;
     int rc;
-    // moment GEMM  R2 = dPHI' F
-    if ((rc = atb_general(dPhi, ld, P.MP, R.gcF, KQ, KQ, R.gc_ones, 0, rows, nsplit, atbp, accumulate, last, R2, st, launches))) return rc;
-    // G1 = dPHI G   (rows x KQ)
     const int KN = gc_gwidth(d);
-    if ((rc = gemm_rows(dPhi, ld, static_cast<int>(round_up(P.m, KSTEP)), R.gcG, KN, rows, G1, st, launches))) return rc;
-    const int nblk = sm_count;
-    const size_t smem = sizeof(double) * 8 * (2 * 32 * 32 + 2 * 32);
+    if (R.gc_digits > 0) {
+        // both products as error-free digit GEMMs.  Row digits of dPHI first: their exponents also bound the moment GEMM's operand
+        const int kvalid = 1 + d + d * (d + 1) / 2, K128 = static_cast<int>(round_up(KQ, 128));
+        if ((rc = ozaki_row_digits(dPhi, ld, P.m, P.MP, rows, R.gc_digits, R.gcA8, R.gcEa, R.flag, st, launches))) return rc;
+        // moment GEMM  R2 = dPHI' F  (contraction over the rows, MN-major operands like the Gram)
+        if ((rc = ozaki_row_digits(R.gcF, KQ, kvalid, K128, rows, R.gc_digits, R.gcF8, R.gcEaF, R.flag, st, launches))) return rc;
+        if ((rc = ozaki_moment_gemm(dPhi, ld, P.m, P.MP, rows, R.gcEa, R.gcF8, R.gcEaF, K128, KQ, R.gc_digits, R.gcX8, accumulate, R2, KQ,
+                                    R.gcMws, st, launches))) return rc;
+    } else if ((rc = atb_general(dPhi, ld, P.MP, R.gcF, KQ, KQ, R.gc_ones, 0, rows, nsplit, atbp, accumulate, last, R2, st, launches))) return rc;
+    // G1 = dPHI G   (rows x KQ)
+    if (R.gc_digits > 0) {               // K = m: the T-GEMM's engine, results stored directly
+        const int kvalid = 1 + d + d * (d + 1) / 2;
+        if ((rc = ozaki_transpose_digits(R.gcG, KN, P.m, kvalid, P.MP, KN, R.gc_digits, R.gcGD8, R.gcEbG, R.flag, st, launches))) return rc;
+        if ((rc = ozmma_gemm_rows(R.gcA8, R.gcEa, rows, R.gcGD8, R.gcEbG, kvalid, P.MP, R.gc_digits, G1, KN, st, launches))) return rc;
+    } else if ((rc = gemm_rows(dPhi, ld, static_cast<int>(round_up(P.m, KSTEP)), R.gcG, KN, rows, G1, st, launches))) return rc;
+    // 4 warps per block, 3 blocks per SM: at d = 32 a warp needs 16.9 KB of shared memory, so 12 warps per SM fit where one
+    // 8-warp block did (r02u launch list: 11 ms of a 105 ms evaluation in this kernel, latency-bound)
+    const int nblk = sm_count * (GC_BP_WARPS / 4);
+    const size_t smem = sizeof(double) * 4 * (2 * 32 * 32 + 2 * 32);
     if (d <= 8) {
-        gc_rows_backproj_kernel<8><<<nblk, 256, sizeof(double) * 8 * (2 * 8 * 8 + 2 * 8), st>>>(d, KQ, KN, rows, R.gcF, G1, partial, accumulate);
+        gc_rows_backproj_kernel<8><<<nblk, 128, sizeof(double) * 4 * (2 * 8 * 8 + 2 * 8), st>>>(d, KQ, KN, rows, R.gcF, G1, partial, accumulate);
     } else if (d <= 16) {
-        gc_rows_backproj_kernel<16><<<nblk, 256, sizeof(double) * 8 * (2 * 16 * 16 + 2 * 16), st>>>(d, KQ, KN, rows, R.gcF, G1, partial, accumulate);
+        gc_rows_backproj_kernel<16><<<nblk, 128, sizeof(double) * 4 * (2 * 16 * 16 + 2 * 16), st>>>(d, KQ, KN, rows, R.gcF, G1, partial, accumulate);
     } else {
         static PerDeviceOnce once;
         if (once.need()) {
             GPZ_CUDA(cudaFuncSetAttribute(gc_rows_backproj_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         }
-        gc_rows_backproj_kernel<32><<<nblk, 256, smem, st>>>(d, KQ, KN, rows, R.gcF, G1, partial, accumulate);
+        gc_rows_backproj_kernel<32><<<nblk, 128, smem, st>>>(d, KQ, KN, rows, R.gcF, G1, partial, accumulate);
     }
     GPZ_KERNEL_CHECK();
     ++*launches;
@@ -360,10 +386,14 @@ int gc_backproj_finish(const Params& P, const RowData& R, double* ws, int nsplit
     double* atbp = G1 + R.gc_chunk * gc_gwidth(P.d);
     double* R2 = atbp + static_cast<int64_t>(nsplit) * (P.MP / TILE) * (KQ / 32) * TILE * 32;
     double* partial = R2 + static_cast<int64_t>(P.MP) * KQ;
-    double* work = partial + static_cast<int64_t>(sm_count) * 8 * (P.d * P.d + 1);
-    gc_finish_kernel<<<1, 256, 0, st>>>(P, KQ, partial, sm_count * 8, R2, dP, dG, work);
-    GPZ_KERNEL_CHECK();
+    double* work = partial + static_cast<int64_t>(sm_count) * GC_BP_WARPS * (P.d * P.d + 1);
+    double* sums = work + 2LL * P.d * P.d;
+    gc_partial_sum_kernel<<<P.d * P.d + 1, 256, 0, st>>>(partial, sm_count * GC_BP_WARPS, P.d * P.d + 1, sums);
     ++*launches;
+    gc_finish_kernel<<<1, 256, 0, st>>>(P, KQ, sums, sm_count * GC_BP_WARPS, R2, dP, dG, work);
+    gc_dp_kernel<<<static_cast<unsigned>(ceil_div(static_cast<int64_t>(P.m) * P.d, 256)), 256, 0, st>>>(P, KQ, R2, dP);
+    GPZ_KERNEL_CHECK();
+    *launches += 2;
     return GPZ_OK;
 }
 

@@ -61,6 +61,19 @@ struct RowData {          // one resident row set (training or validation rows o
     double *gcF = nullptr, *gcW = nullptr, *gcG = nullptr;
     const double* gc_ones = nullptr;
     int64_t gc_chunk = 0;
+    // ... with its K = 1 + d + d(d+1)/2 GEMMs on the int8 tensor cores (d > 16): digit buffers (aliases of the context's
+    // digit workspaces, free at those points of the evaluation) and the digits of the basis tables
+    int gc_digits = 0;            // 0: fp64 DMMA GEMMs
+    int8_t* gcA8 = nullptr;       // [rows_pad][s][K128] row digits of the left operand (features, then dPHI)
+    double* gcEa = nullptr;       // [rows_pad]
+    int8_t* gcWD8 = nullptr;      // [MP][s][K128]   digits of the columns of gcW
+    double* gcEbW = nullptr;      // [MP]
+    int8_t* gcGD8 = nullptr;      // [KN][s][MP]     digits of the columns of gcG
+    double* gcEbG = nullptr;      // [KN]
+    int8_t* gcF8 = nullptr;       // [rows_pad][s][K128] row digits of the features, for the moment GEMM dPHI' F
+    double* gcEaF = nullptr;      // [rows_pad]
+    int8_t* gcX8 = nullptr;       // [rows_pad][s][MP]   digits of dPHI 2^(G_i - Eb) (alias of the second PHI digit buffer)
+    void* gcMws = nullptr;        // oz_moment_workspace_bytes
     // covariance modes with missing inputs: rows are stored sorted by NaN pattern (NaN entries zero-filled),
     // group g = rows [g_r0[g], g_r1[g]) with pattern g_pat[g]; perm[sorted position] = position in selection order
     std::vector<int64_t> g_r0, g_r1, perm;
@@ -187,6 +200,15 @@ int64_t oz_workspace_bytes(int MP, int s);
 int64_t oz_gram_workspace_bytes(int MP, int64_t rows);
 int ozaki_digits(const double* Phi, int64_t ld, int MP, int m, int64_t rows, int s, const double* wgt, const double* d_scal, int aug,
                  int8_t* D8, int8_t* F8, double* ea, int* flag, cudaStream_t st, int64_t* launches);
+int ozaki_row_digits(const double* A, int64_t lda, int cols, int K128, int64_t rows, int s, int8_t* A8, double* ea, int* flag,
+                     cudaStream_t st, int64_t* launches);
+int ozaki_transpose_digits(const double* src, int64_t lds, int R, int C, int Rpad, int Cpad, int s, int8_t* out, double* scale, int* flag,
+                           cudaStream_t st, int64_t* launches);
+int64_t oz_moment_workspace_bytes(int MP, int cols, int64_t rows);
+int ozaki_moment_gemm(const double* X, int64_t ld, int m, int MP, int64_t rows, const double* eaX, const int8_t* F8, const double* eaF,
+                      int K128, int cols, int s, int8_t* A8, int accumulate, double* R, int64_t ldr, void* ws, cudaStream_t st,
+                      int64_t* launches);
+int exp_rows_inplace(double* Phi, int64_t ld, int m, int MP, int64_t rows, const DotSpec& dots, cudaStream_t st, int64_t* launches);
 int ozaki_feature_digits(const double* F, int64_t ldf, int q, int64_t rows, int s, int8_t* FD8, double* eaF, int* flag, cudaStream_t st,
                          int64_t* launches);
 int ozaki_phi(const int8_t* FD8, const double* eaF, const double* W, int kq, int MP, int m, int s, int64_t rows, int8_t* WD8, double* ebW,
@@ -213,6 +235,8 @@ int64_t ozmma_partial_doubles(int rowsA, int rowsB, int lower, int nchunks, int 
 int ozmma_gemm_nt(const int8_t* A, const int64_t strA[3], int rowsA, const int8_t* B, const int64_t strB[3], int rowsB, int s, int emax,
                   int kchunk, int nchunks, int lower, int mn_major, double* partial, const double* sr, const double* sc, double scale,
                   int accumulate, double* out, int64_t ldo, int pairs_limit, cudaStream_t st, int64_t* launches);
+int ozmma_gemm_rows(const int8_t* A8, const double* ea, int64_t rows, const int8_t* B8, const double* eb, int cols, int K128, int s,
+                    double* C, int64_t ldc, cudaStream_t st, int64_t* launches);
 int ozmma_phi(const int8_t* FD8, const double* eaF, const int8_t* WD8, const double* ebW, int kq, int MP, int m, int s, int64_t rows,
               double* Phi, int ndot, const double* vec0, const double* vec1, double* part0, double* part1, int64_t part_ld,
               const double* ycol, cudaStream_t st, int64_t* launches);

@@ -285,6 +285,189 @@ int ozaki_gram(const int8_t* F8, const int8_t* D8, int MP, int m, int64_t rows, 
     return GPZ_OK;
 }
 
+// ---- general fp64 GEMM with a row-major left operand through the digit kernel: C = A B'  (GC + Psi path, gcpsi.cu) ---------
+// digits of the rows of A [rows][lda] (cols valid columns) -> A8 [rows_pad][s][K128] with per-row power-of-two scales ea
+int ozaki_row_digits(const double* A, int64_t lda, int cols, int K128, int64_t rows, int s, int8_t* A8, double* ea, int* flag,
+                     cudaStream_t st, int64_t* launches) {
+    if (K128 % 128 != 0 || cols > K128 || lda % 4 != 0 || s < 2 || s > OZ_MAXS) {
+        set_error("ozaki_row_digits: unsupported K=%d cols=%d lda=%lld", K128, cols, static_cast<long long>(lda));
+        return GPZ_ERR_USAGE;
+    }
+    const int64_t np = oz_padded_rows(rows);
+    const int src_cols = static_cast<int>(lda < K128 ? lda : K128);
+    oz_digits_kernel<<<static_cast<unsigned>(ceil_div(np, 8)), 256, 0, st>>>(A, lda, src_cols, cols, K128, rows, np, s, nullptr, nullptr, 0, A8,
+                                                                             nullptr, ea, flag);
+    GPZ_KERNEL_CHECK();
+    ++*launches;
+    return GPZ_OK;
+}
+
+// digits of the COLUMNS of src [R][lds] (C columns): out [Cpad][s][Rpad] (K = row index contiguous, zero padded), scale[c];
+// one block per column
+__global__ void __launch_bounds__(256)
+oz_transpose_digits_kernel(const double* __restrict__ src, int64_t lds, int R, int C, int Rpad, int s, int8_t* __restrict__ out,
+                           double* __restrict__ scale, int* __restrict__ flag) {
+    __shared__ double sh[8];
+    __shared__ int Esh;
+    const int c = blockIdx.x;
+    double mx = 0.0;
+    bool bad = false;
+    if (c < C)
+        for (int r = threadIdx.x; r < R; r += 256) {
+            const double v = src[static_cast<int64_t>(r) * lds + c];
+            bad |= !(fabs(v) <= 1.7e308);
+            mx = fmax(mx, fabs(v));
+        }
+    if (bad && flag != nullptr) atomicExch(flag, 1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < 8; ++q) mx = fmax(mx, sh[q]);
+        const int E = oz_exponent(mx);
+        Esh = E;
+        scale[c] = ldexp(1.0, E - 8);
+    }
+    __syncthreads();
+    const double sc = ldexp(1.0, 8 * s - Esh);
+    int8_t* o = out + static_cast<int64_t>(c) * s * Rpad;
+    for (int r = threadIdx.x; r < Rpad; r += 256) {
+        long long I = (c < C && r < R) ? __double2ll_rn(src[static_cast<int64_t>(r) * lds + c] * sc) : 0;
+        for (int u = s - 1; u >= 0; --u) o[static_cast<int64_t>(u) * Rpad + r] = static_cast<int8_t>(oz_digit(I));
+    }
+}
+
+int ozaki_transpose_digits(const double* src, int64_t lds, int R, int C, int Rpad, int Cpad, int s, int8_t* out, double* scale, int* flag,
+                           cudaStream_t st, int64_t* launches) {
+    oz_transpose_digits_kernel<<<Cpad, 256, 0, st>>>(src, lds, R, C, Rpad, s, out, scale, flag);
+    GPZ_KERNEL_CHECK();
+    ++*launches;
+    return GPZ_OK;
+}
+
+// ---- R (+)= X' F over the rows (K = row index) through the digit kernel, for two DIFFERENT matrices (GC + Psi moment GEMM) ----
+// The Gram trick generalised: the B operand carries F_iq 2^-G_i (per-row exponent G_i of F's row, its ordinary row digits), the
+// A operand carries X_ij 2^(G_i - Eb) with ONE exponent Eb = max_i (E_i + G_i) (E_i: exponent of X's row), so that the row
+// scales cancel inside the product and the contraction over rows is exact up to 2^-56 of 2^Eb.
+__global__ void __launch_bounds__(1024) oz_pair_exponent_kernel(const double* __restrict__ eaX, const double* __restrict__ eaF, int64_t n,
+                                                                int* __restrict__ Eb) {
+    __shared__ int sh[32];
+    int mx = -100000;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) {
+        const int e = ((__double2hiint(eaX[i]) >> 20) & 0x7ff) + ((__double2hiint(eaF[i]) >> 20) & 0x7ff) - 2046 + 16;   // E_i + G_i (ea = 2^(E-8))
+        mx = max(mx, e);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < 32; ++q) mx = max(mx, sh[q]);
+        *Eb = mx;
+    }
+}
+
+// A8 [n_pad][s][MP]: digits of X_ij 2^(G_i - Eb), 2^G_i = 256 eaF[i]; rows >= n zero; warp per row
+__global__ void __launch_bounds__(256)
+oz_digits_ext_kernel(const double* __restrict__ X, int64_t ld, int m, int MP, int64_t n, int64_t n_pad, int s, const double* __restrict__ eaF,
+                     const int* __restrict__ Eb, int8_t* __restrict__ A8) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (i >= n_pad) return;
+    int8_t* out = A8 + i * static_cast<int64_t>(s) * MP;
+    if (i >= n) {
+        const int4 z = make_int4(0, 0, 0, 0);
+        for (int b = lane * 16; b < s * MP; b += 512) *reinterpret_cast<int4*>(out + b) = z;
+        return;
+    }
+    const int G = ((__double2hiint(eaF[i]) >> 20) & 0x7ff) - 1023 + 8;
+    const double sc = ldexp(1.0, 8 * s + G - *Eb);
+    const unsigned long long bias = 0x0080808080808080ull >> (8 * (8 - s));
+    const double* row = X + i * ld;
+    for (int j = lane * 4; j < MP; j += 128) {
+        const double4 v = *reinterpret_cast<const double4*>(row + j);
+        const double x[4] = {v.x, v.y, v.z, v.w};
+        unsigned long long I[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) I[q] = oz_digit_bytes(j + q < m ? __double2ll_rn(x[q] * sc) : 0, bias);
+        oz_store_digits4(I, s, out + j, MP);
+    }
+}
+
+__global__ void oz_fill_scale_kernel(const int* __restrict__ Eb, int n, double* __restrict__ sr) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) sr[j] = ldexp(1.0, *Eb - 16);                     // 2^Eb 256^-2
+}
+
+int64_t oz_moment_workspace_bytes(int MP, int cols, int64_t rows) {
+    const int64_t nch = oz_padded_rows(rows) / OZG_CH;
+    return al256(ozmma_partial_doubles(MP, cols, 0, static_cast<int>(nch), 0) * 8) + al256(static_cast<int64_t>(MP) * 8) + 256;
+}
+
+// R [MP][ldr] (columns < cols) (+)= X' F.  X [rows][ld] (m valid columns) with its row scales eaX already known (from its own
+// row digits), F8 / eaF: row digits of F [rows_pad][s][K128].  A8: scratch [rows_pad][s][MP].  ws: oz_moment_workspace_bytes.
+int ozaki_moment_gemm(const double* X, int64_t ld, int m, int MP, int64_t rows, const double* eaX, const int8_t* F8, const double* eaF,
+                      int K128, int cols, int s, int8_t* A8, int accumulate, double* R, int64_t ldr, void* ws, cudaStream_t st,
+                      int64_t* launches) {
+    const int64_t np = oz_padded_rows(rows);
+    const int nch = static_cast<int>(np / OZG_CH);
+    unsigned char* p = static_cast<unsigned char*>(ws);
+    double* partial = reinterpret_cast<double*>(p);
+    double* sr = reinterpret_cast<double*>(p + al256(ozmma_partial_doubles(MP, cols, 0, nch, 0) * 8));
+    int* Eb = reinterpret_cast<int*>(p + al256(ozmma_partial_doubles(MP, cols, 0, nch, 0) * 8) + al256(static_cast<int64_t>(MP) * 8));
+    oz_pair_exponent_kernel<<<1, 1024, 0, st>>>(eaX, eaF, rows, Eb);
+    oz_digits_ext_kernel<<<static_cast<unsigned>(ceil_div(np, 8)), 256, 0, st>>>(X, ld, m, MP, rows, np, s, eaF, Eb, A8);
+    oz_fill_scale_kernel<<<static_cast<unsigned>(ceil_div(MP, 256)), 256, 0, st>>>(Eb, MP, sr);
+    GPZ_KERNEL_CHECK();
+    *launches += 3;
+    // addressed {row index, digit, k = i within chunk, chunk}
+    const int64_t strA[3] = {MP, static_cast<int64_t>(s) * MP, static_cast<int64_t>(OZG_CH) * s * MP};
+    const int64_t strB[3] = {K128, static_cast<int64_t>(s) * K128, static_cast<int64_t>(OZG_CH) * s * K128};
+    return ozmma_gemm_nt(A8, strA, MP, F8, strB, cols, s, s + 1, OZG_CH, nch, 0, 1, partial, sr, nullptr, 1.0, accumulate, R, ldr, 0, st, launches);
+}
+
+// PHI <- exp(PHI) in place for columns < m (0 beyond), fused row dots out_q[i] = sum_j PHI_ij vec_q[j]; warp per row
+__global__ void __launch_bounds__(256)
+exp_rows_inplace_kernel(double* __restrict__ Phi, int64_t ld, int m, int MP, int64_t rows, DotSpec dots) {
+    __shared__ double exp_sm[32];
+    exp_tab_stage(exp_sm);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (i >= rows) return;
+    double* row = Phi + i * ld;
+    double s0 = 0.0, s1 = 0.0;
+    for (int j = 2 * lane; j < MP; j += 64) {
+        double2 v = *reinterpret_cast<const double2*>(row + j);
+        v.x = (j < m) ? exp_tab(v.x, exp_sm) : 0.0;
+        v.y = (j + 1 < m) ? exp_tab(v.y, exp_sm) : 0.0;
+        *reinterpret_cast<double2*>(row + j) = v;
+        if (dots.n > 0) {
+            const double2 a = __ldg(reinterpret_cast<const double2*>(dots.vec[0] + j));
+            s0 = fma(v.x, a.x, fma(v.y, a.y, s0));
+        }
+        if (dots.n > 1) {
+            const double2 b = __ldg(reinterpret_cast<const double2*>(dots.vec[1] + j));
+            s1 = fma(v.x, b.x, fma(v.y, b.y, s1));
+        }
+    }
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    if (lane == 0) {
+        if (dots.n > 0) dots.out[0][i] = s0;
+        if (dots.n > 1) dots.out[1][i] = s1;
+    }
+}
+
+int exp_rows_inplace(double* Phi, int64_t ld, int m, int MP, int64_t rows, const DotSpec& dots, cudaStream_t st, int64_t* launches) {
+    if (rows <= 0) return GPZ_OK;
+    exp_rows_inplace_kernel<<<static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, st>>>(Phi, ld, m, MP, rows, dots);
+    GPZ_KERNEL_CHECK();
+    ++*launches;
+    return GPZ_OK;
+}
+
 // ---- PHI = exp(F W) through the int8 tensor cores (ozmma_phi) ---------------------------------------------------------
 // digits of the monomial row features F [rows][ldf] (q valid columns, dataset constants: done once) -> FD8 [rows_pad][s][128]
 int ozaki_feature_digits(const double* F, int64_t ldf, int q, int64_t rows, int s, int8_t* FD8, double* eaF, int* flag, cudaStream_t st,

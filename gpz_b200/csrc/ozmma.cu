@@ -49,7 +49,7 @@ struct OzmmaArgs {
     int gchunks;              // K chunks per work unit (folded one after the other into the fp64 registers)
     int ngroups;              // ceil(nchunks / gchunks); work unit u = group * ntiles + tile
     int lower;                // tile list = tiles touching the lower triangle (Gram); else all tiles_m x tiles_n
-    int mode;                 // 0: fp64 partial tiles, 1: T-GEMM epilogue, 2: PHI = exp(.) epilogue
+    int mode;                 // 0: fp64 partial tiles, 1: T-GEMM epilogue, 2: PHI = exp(.) epilogue, 3: C = scaled product, stored directly
     int mn_major;             // operands stored [k][row] (row index contiguous) instead of [row][k]
     int lgroup;               // levels multiplied together: 2 (default, shared operand tiles) or 1 (one level at a time)
     int prefetch;             // mode 1: prefetch the epilogue's PHI block into L2 (option "ozaki_prefetch", default 0)
@@ -512,6 +512,18 @@ ozmma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                 for (int r = 0; r < 32; ++r) st_stream1(out + r * 128, scale_pow2(st[r], efold));
                 continue;
             }
+            if (a.mode == 3) {                   // plain product, one K chunk per unit: out[row][col] = sum * ea_row * eb_col
+                const bool colok = col < a.m;
+                const int exb = colok ? pow2_exponent(a.eb[col]) + efold : 0;
+                const int exa_l = (gi0 + lane < a.rows) ? pow2_exponent(a.ea[gi0 + lane]) : 0;
+                double* op = a.H + gi0 * a.ld + col;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    const int ex = __shfl_sync(0xffffffffu, exa_l, r) + exb;
+                    if (colok && gi0 + r < a.rows) st_stream1(op + r * a.ld, scale_pow2(st[r], ex));
+                }
+                continue;
+            }
             // st[r] is overwritten by this lane's contribution to the row sum of row r (T-GEMM: PHI .* T; PHI build: PHI * vec0);
             // the PHI build's optional second dot is reduced first, from the PHI values still in st
             double second = 0.0;
@@ -936,6 +948,54 @@ int ozmma_tgemm(const int8_t* A8, const int8_t* B8, int MP, int s, int emax, int
     a.nu_ld = nu_ld;
     a.aug_col = aug_col;
     a.pred = pred;
+    if ((rc = launch(mA, mB, mB2, a, np, st))) return rc;
+    if (launches) ++*launches;
+    return GPZ_OK;
+}
+
+// C[rows][ldc] (columns < cols) = A B' with A8 [rows][s][K128] (row scales ea), B8 [>= cols][s][K128] (row scales eb), all
+// scales powers of two; K128 a multiple of 128.  One launch, results stored directly (no partial tiles).
+int ozmma_gemm_rows(const int8_t* A8, const double* ea, int64_t rows, const int8_t* B8, const double* eb, int cols, int K128, int s,
+                    double* C, int64_t ldc, cudaStream_t st, int64_t* launches) {
+    if (s < 1 || s > 8 || K128 % 128 != 0 || K128 <= 0 || cols < 1 || static_cast<int64_t>(s) * K128 * 16384 >= 2147483648LL ||
+        rows >= (1LL << 31) - 256) {
+        set_error("ozmma_gemm_rows: unsupported s=%d K=%d cols=%d", s, K128, cols);
+        return GPZ_ERR_USAGE;
+    }
+    const int np = resident_pairs();
+    if (np <= 0) {
+        set_error("ozmma: cannot configure the tcgen05 kernel: %s", cudaGetErrorString(cudaGetLastError()));
+        return GPZ_ERR_CUDA;
+    }
+    const int colsp = (cols + 127) / 128 * 128;
+    CUtensorMap mA, mB, mB2;
+    const int64_t dA[4] = {K128, s, rows, 1}, sA[3] = {K128, static_cast<int64_t>(s) * K128, round_up(rows * s * K128, 16)};
+    const int64_t dB[4] = {K128, s, colsp, 1}, sB[3] = {K128, static_cast<int64_t>(s) * K128, static_cast<int64_t>(s) * K128 * colsp};
+    int rc;
+    if ((rc = make_map(&mA, A8, dA, sA, 128))) return rc;
+    if ((rc = make_map(&mB, B8, dB, sB, 64))) return rc;
+    if ((rc = make_map(&mB2, B8, dB, sB, 128))) return rc;
+    OzmmaArgs a = {};
+    set_operand_layout(a, 0);
+    a.hintB = OM_EVICT_LAST;
+    a.s = s;
+    a.emin = 2;
+    a.emax = s + 1;
+    a.kblocks = K128 / 128;
+    a.tiles_n = colsp / 128;
+    a.ntiles = static_cast<int>(ceil_div(rows, 256)) * a.tiles_n;
+    a.nchunks = 1;
+    a.gchunks = 1;
+    a.ngroups = 1;
+    a.nint = int_levels(s, 2, s + 1, K128, 1);
+    a.lower = 0;
+    a.mode = 3;
+    a.ea = ea;
+    a.eb = eb;
+    a.H = C;
+    a.ld = ldc;
+    a.rows = rows;
+    a.m = cols;
     if ((rc = launch(mA, mB, mB2, a, np, st))) return rc;
     if (launches) ++*launches;
     return GPZ_OK;

@@ -477,7 +477,19 @@ int phi_build(const Params& P, const RowData& R, int64_t r0, int64_t r1, double*
         const int KQ = gc_feature_width(P.d), ntn = P.MP / TILE;
         double* p0 = dot_scratch;
         double* p1 = dot_scratch + static_cast<int64_t>(ntn) * rows;
-        if ((rc = phi_gemm(R.gcF, KQ, KQ, 1 + P.d + P.d * (P.d + 1) / 2, R.gcW, P.MP, P.m, rows, Phi, dots.n, dots.vec[0], dots.vec[1], p0, p1, rows, nullptr, st, launches)))
+        const int kvalid = 1 + P.d + P.d * (P.d + 1) / 2;
+        if (R.gc_digits > 0) {
+            // K = 561 at d = 32: the product F W as an error-free digit GEMM on the int8 tensor cores (ozmma.cu, stored directly),
+            // exp and the row dots in one memory-bound pass afterwards (an exp epilogue starves under the tensor pipe)
+            const int K128 = static_cast<int>(round_up(KQ, 128));
+            if ((rc = ozaki_row_digits(R.gcF, KQ, kvalid, K128, rows, R.gc_digits, R.gcA8, R.gcEa, R.flag, st, launches))) return rc;
+            if ((rc = ozaki_transpose_digits(R.gcW, P.MP, kvalid, P.m, K128, P.MP, R.gc_digits, R.gcWD8, R.gcEbW, R.flag, st, launches))) return rc;
+            if ((rc = ozmma_gemm_rows(R.gcA8, R.gcEa, rows, R.gcWD8, R.gcEbW, P.m, K128, R.gc_digits, Phi, P.MP, st, launches))) return rc;
+            DotSpec ds = dots;
+            for (int q = 0; q < ds.n; ++q) ds.out[q] = dots.out[q] + r0;
+            return exp_rows_inplace(Phi, P.MP, P.m, P.MP, rows, ds, st, launches);
+        }
+        if ((rc = phi_gemm(R.gcF, KQ, KQ, kvalid, R.gcW, P.MP, P.m, rows, Phi, dots.n, dots.vec[0], dots.vec[1], p0, p1, rows, nullptr, st, launches)))
             return rc;
         for (int q = 0; q < dots.n; ++q) {
             sum_parts_kernel<<<static_cast<unsigned>(ceil_div(rows, 256)), 256, 0, st>>>(q == 0 ? p0 : p1, ntn, rows, rows, dots.out[q] + r0);

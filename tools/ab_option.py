@@ -11,8 +11,10 @@ from gpz_b200 import _lib as L  # noqa: E402
 
 name, opt, va, vb = sys.argv[1], sys.argv[2], float(sys.argv[3]), float(sys.argv[4])
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 6
-n, d, m, method, X, Y, theta0 = bench.make_problem(name)
-ctx = L.Context(L.make_model(d, 1, m, method, True), X, Y)
+_, d, m, method, _ = bench.WORKLOADS[name]
+sh = bench.make_shard(name, 0, 1)
+X, Y, Psi, theta0 = sh["X"], sh["Y"], sh["Psi"], sh["theta0"]
+ctx = L.Context(L.make_model(d, 1, m, method, True), X, Y, Psi)
 ths = bench.thetas_for(theta0, 2 * reps + 2)
 ctx.eval(ths[0])
 ctx.eval(ths[1])
