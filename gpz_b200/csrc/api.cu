@@ -2176,6 +2176,20 @@ int gpz_inv_logdet(int32_t m, const double* X, double* Xi, double* logdet, int d
     SolveWs ws;
     cudaStream_t st = nullptr;
     int64_t launches = 0;
+    struct Cleanup {                      // every exit path below releases what was allocated so far
+        double*& a;
+        double*& b;
+        double*& c;
+        SolveWs& w;
+        cudaStream_t& s;
+        ~Cleanup() {
+            if (a) cudaFree(a);
+            if (b) cudaFree(b);
+            if (c) cudaFree(c);
+            solve_ws_free(w);
+            if (s) cudaStreamDestroy(s);
+        }
+    } cleanup{S, Si, ld, ws, st};
     GPZ_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     GPZ_CUDA(cudaMalloc(&S, sizeof(double) * MP * MP));
     GPZ_CUDA(cudaMalloc(&Si, sizeof(double) * MP * MP));
@@ -2220,11 +2234,6 @@ int gpz_inv_logdet(int32_t m, const double* X, double* Xi, double* logdet, int d
         cudaFree(mm);
         if (!rc && logdet) *logdet = hl;
     }
-    cudaFree(S);
-    cudaFree(Si);
-    cudaFree(ld);
-    solve_ws_free(ws);
-    cudaStreamDestroy(st);
     return rc;
 }
 

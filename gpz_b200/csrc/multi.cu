@@ -1,8 +1,8 @@
 // Single-process multi-GPU boundary (SURVEY.md 8b "threading", 8e "backend"): the reference's caller is ONE interpreter thread
 // holding one closure f = @(params) GPz(params,model,X,Y,Psi,omega,training,validation) (GPz/train.m:40), so a drop-in must be
 // able to drive N GPUs from that one thread.  gpz_create_multi splits the selected rows into N contiguous blocks, builds one
-// ordinary gpz_ctx per device and joins them into one NCCL communicator; every call is then executed by N persistent worker
-// threads (one per device), each running the unchanged per-rank entry point -- kernels, the two allreduces of an
+// ordinary gpz_ctx per device and joins them into one NCCL communicator; every call is then executed by the caller's thread
+// (rank 0) and N-1 persistent worker threads (one per further device), each running the unchanged per-rank entry point -- kernels, the two allreduces of an
 // evaluation, the replicated m x m solve -- on its own device and stream.  All ranks finish with identical results
 // (fixed-order reductions + allreduce), rank 0's are returned.  All calls block, the library stays single-caller.
 #include <condition_variable>
@@ -63,6 +63,58 @@ struct gpz_multi {
 
 namespace {
 
+// one rank's share of a job; called on a worker thread for ranks > 0 and on the CALLER's thread for rank 0, so that
+// callbacks (the callBack.m table a MEX gateway prints with mexPrintf) never run on a foreign thread
+int exec_job(gpz_multi* M, int r, const Job& j) {
+    int rc = GPZ_OK;
+    const int64_t p = M->p;
+    const int m = M->model.m, k = M->model.k;
+    switch (j.cmd) {
+        case CMD_INIT:
+            rc = gpz_comm_init(M->ctx[r], r, M->n, j.id);
+            break;
+        case CMD_EVAL: {
+            double f = 0.0, st[4];
+            double* g = r == 0 ? j.grad : M->g_scr[r].data();
+            rc = gpz_eval(M->ctx[r], j.theta, r == 0 ? j.f : &f, g, r == 0 ? j.stats : st);
+            break;
+        }
+        case CMD_FIT: {
+            if (r == 0) rc = gpz_fit(M->ctx[r], j.theta, j.nl, j.w, j.iS);
+            else {
+                std::vector<double>& b = M->big_scr[r];
+                b.resize(static_cast<size_t>(k) + static_cast<size_t>(m) * k + static_cast<size_t>(m) * m * k);
+                rc = gpz_fit(M->ctx[r], j.theta, b.data(), b.data() + k, b.data() + k + static_cast<size_t>(m) * k);
+            }
+            break;
+        }
+        case CMD_PRIOR: {
+            std::vector<double> pr(static_cast<size_t>(m));
+            rc = gpz_get_prior(M->ctx[r], j.theta, r == 0 ? j.prior : pr.data());
+            break;
+        }
+        case CMD_TRAIN: {
+            // the optimiser is replicated: same objective values on every rank -> same decisions
+            double bv = *j.best_valid;
+            gpz_train_result res;
+            std::memset(&res, 0, sizeof(res));
+            if (r == 0) rc = gpz_train(M->ctx[r], j.topt, const_cast<double*>(j.theta), j.best_theta, j.best_valid, j.cb, j.cb_user, j.res);
+            else {
+                M->th_scr[r].assign(j.theta, j.theta + p);
+                M->bt_scr[r].assign(j.best_theta, j.best_theta + p);
+                rc = gpz_train(M->ctx[r], j.topt, M->th_scr[r].data(), M->bt_scr[r].data(), &bv, nullptr, nullptr, &res);
+            }
+            break;
+        }
+        case CMD_OPTION:
+            rc = gpz_set_option(M->ctx[r], j.opt_name, j.opt_value);
+            break;
+        default:
+            break;
+    }
+    return rc;
+}
+
 void worker(gpz_multi* M, int r) {
     uint64_t seen = 0;
     for (;;) {
@@ -73,52 +125,7 @@ void worker(gpz_multi* M, int r) {
             seen = M->epoch;
             j = M->job;
         }
-        int rc = GPZ_OK;
-        const int64_t p = M->p;
-        const int m = M->model.m, k = M->model.k;
-        switch (j.cmd) {
-            case CMD_INIT:
-                rc = gpz_comm_init(M->ctx[r], r, M->n, j.id);
-                break;
-            case CMD_EVAL: {
-                double f = 0.0, st[4];
-                double* g = r == 0 ? j.grad : M->g_scr[r].data();
-                rc = gpz_eval(M->ctx[r], j.theta, r == 0 ? j.f : &f, g, r == 0 ? j.stats : st);
-                break;
-            }
-            case CMD_FIT: {
-                if (r == 0) rc = gpz_fit(M->ctx[r], j.theta, j.nl, j.w, j.iS);
-                else {
-                    std::vector<double>& b = M->big_scr[r];
-                    b.resize(static_cast<size_t>(k) + static_cast<size_t>(m) * k + static_cast<size_t>(m) * m * k);
-                    rc = gpz_fit(M->ctx[r], j.theta, b.data(), b.data() + k, b.data() + k + static_cast<size_t>(m) * k);
-                }
-                break;
-            }
-            case CMD_PRIOR: {
-                std::vector<double> pr(static_cast<size_t>(m));
-                rc = gpz_get_prior(M->ctx[r], j.theta, r == 0 ? j.prior : pr.data());
-                break;
-            }
-            case CMD_TRAIN: {
-                // the optimiser is replicated: same objective values on every rank -> same decisions
-                double bv = *j.best_valid;
-                gpz_train_result res;
-                std::memset(&res, 0, sizeof(res));
-                if (r == 0) rc = gpz_train(M->ctx[r], j.topt, const_cast<double*>(j.theta), j.best_theta, j.best_valid, j.cb, j.cb_user, j.res);
-                else {
-                    M->th_scr[r].assign(j.theta, j.theta + p);
-                    M->bt_scr[r].assign(j.best_theta, j.best_theta + p);
-                    rc = gpz_train(M->ctx[r], j.topt, M->th_scr[r].data(), M->bt_scr[r].data(), &bv, nullptr, nullptr, &res);
-                }
-                break;
-            }
-            case CMD_OPTION:
-                rc = gpz_set_option(M->ctx[r], j.opt_name, j.opt_value);
-                break;
-            default:
-                break;
-        }
+        const int rc = exec_job(M, r, j);
         {
             std::lock_guard<std::mutex> lk(M->mu);
             M->rc[r] = rc;
@@ -133,10 +140,13 @@ int run(gpz_multi* M, const Job& j) {
     {
         std::lock_guard<std::mutex> lk(M->mu);
         M->job = j;
-        M->pending = M->n;
+        M->pending = M->n - 1;
         ++M->epoch;
     }
     M->cv_go.notify_all();
+    // rank 0 on this (the caller's) thread
+    M->rc[0] = exec_job(M, 0, j);
+    if (M->rc[0]) M->err[0] = gpz_last_error();
     {
         std::unique_lock<std::mutex> lk(M->mu);
         M->cv_done.wait(lk, [&] { return M->pending == 0; });
@@ -220,7 +230,7 @@ int gpz_create_multi(gpz_multi** out, const gpz_model* model, int64_t n_all, con
         set_error("%s", e.c_str());
         return rc;
     }
-    for (int r = 0; r < ngpus; ++r) M->th.emplace_back(worker, M, r);
+    for (int r = 1; r < ngpus; ++r) M->th.emplace_back(worker, M, r);       // rank 0 runs on the caller's thread
     Job j;
     j.cmd = CMD_INIT;
     std::memset(j.id, 0, sizeof(j.id));
@@ -247,6 +257,7 @@ void gpz_destroy_multi(gpz_multi* M) {
         j.cmd = CMD_QUIT;
         run(M, j);
         for (std::thread& t : M->th) t.join();
+        M->th.clear();
     }
     for (gpz_ctx* c : M->ctx) gpz_destroy(c);
     delete M;
