@@ -49,7 +49,7 @@ pair_table_kernel(Params P, const double* __restrict__ w, const double* __restri
     for (int o = 0; o < P.k; ++o) {
         T.ww[o * T.npairs + q] = f * w[o * MP + i] * w[o * MP + j];
         T.vv[o * T.npairs + q] = f * P.v[o * MP + i] * P.v[o * MP + j];
-        T.ss[o * T.npairs + q] = f * Sinv[(static_cast<int64_t>(o) * MP + i) * MP + j];
+        T.ss[o * T.npairs + q] = f * Sinv[(static_cast<int64_t>(o) * MP + j) * MP + i];   // iSigma_w(i,j), i >= j, as the reference reads it
     }
 }
 
@@ -257,7 +257,7 @@ pm_pairs_kernel(Params P, const unsigned char* __restrict__ ob, const double* __
     for (int o = 0; o < P.k; ++o) {
         T.ww[o * T.npairs + q] = f * w[o * MP + i] * w[o * MP + j];
         T.vv[o * T.npairs + q] = f * P.v[o * MP + i] * P.v[o * MP + j];
-        T.ss[o * T.npairs + q] = f * Sinv[(static_cast<int64_t>(o) * MP + i) * MP + j];
+        T.ss[o * T.npairs + q] = f * Sinv[(static_cast<int64_t>(o) * MP + j) * MP + i];   // iSigma_w(i,j), i >= j, as the reference reads it
     }
     for (int l = 0; l < MP; ++l) {
         double val = 0.0;
@@ -467,7 +467,7 @@ cpair_table_kernel(Params P, const double* __restrict__ w, const double* __restr
     for (int o = 0; o < P.k; ++o) {
         T.ww[o * T.npairs + q] = f * w[o * MP + i] * w[o * MP + j];
         T.vv[o * T.npairs + q] = f * P.v[o * MP + i] * P.v[o * MP + j];
-        T.ss[o * T.npairs + q] = f * Sinv[(static_cast<int64_t>(o) * MP + i) * MP + j];
+        T.ss[o * T.npairs + q] = f * Sinv[(static_cast<int64_t>(o) * MP + j) * MP + i];   // iSigma_w(i,j), i >= j, as the reference reads it
     }
 }
 

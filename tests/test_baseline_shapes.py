@@ -200,3 +200,28 @@ def test_cfg2_photoz_small_live_oracle():
     f, g, st = ctx.eval(theta)
     check("cfg2_sdss_1200", model, cond, f, g, st, ref.nlogML, ref.grad, [ref.stats[s] for s in ("trainRMSE", "trainLL", "validRMSE", "validLL")])
     ctx.close()
+
+
+def test_cfg2_photoz_predict_noisy_on_reference_rows():
+    """demo_photoz.m:88 `predict(X,model,'Psi',Psi,'selection',testing)`: predictNoisy of the covariance modes
+    (predictCov.m:62-132) at config 2's m = 100, d = 5 on 24 stored rows of the reference's data file with their magnitude
+    errors, using the ORACLE's stored fit (w, iSigma_w).  24 rows: the oracle's pair loop is O(n m^2)."""
+    z, Xz, Yc, PsiC, theta, tr, va = sdss_inputs()
+    m, d = 100, 5
+    model = O.Model(d=d, k=1, m=m, method="VC", heteroscedastic=True)
+    model.muX, model.sdX, model.muY = np.zeros(d), np.ones(d), np.zeros(1)
+    o2 = m * d + model.g_dim + m + 1
+    model.best = dict(theta=theta, w=z["w"], iSigma_w=z["iSigma_w"], P=theta[:m * d].reshape((m, d), order="F"),
+                      v=theta[o2:o2 + m].reshape(m, 1))
+    pick = np.flatnonzero(va)[:24]
+    Xt, Pt = np.ascontiguousarray(Xz[pick]), np.ascontiguousarray(PsiC[:, :, pick])
+    t0 = time.time()
+    mu, sigma, nu, be, ga, PHI = O.predict(Xt, model, Psi=Pt)
+    gm = L.make_model(d, 1, m, "VC", True)
+    mu2, nu2, be2, ga2, PHI2 = L.predict_core(gm, theta, z["w"], z["iSigma_w"], Xt, Pt, want_phi=True)
+    bound = min(STATED, C_COND * float(z["cond"]) * EPS)
+    errs = dict(mu=rel(mu2, mu), nu=rel(nu2, nu), beta_i=rel(be2, be), gamma=rel(ga2, ga), sigma=rel(nu2 + be2 + ga2, sigma),
+                PHI=rel(PHI2, PHI))
+    print(f"[cfg2_sdss/predictNoisy] oracle {time.time() - t0:.0f} s; " + ", ".join(f"{k} {v:.1e}" for k, v in errs.items()))
+    assert max(errs.values()) <= bound, (errs, bound)
+    assert (sigma > 0).all() and (ga >= 0).all()

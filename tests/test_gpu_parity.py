@@ -208,6 +208,34 @@ def test_predict_matches_oracle(method, psi):
     assert rel(PHI2, PHI) <= 1e-12
 
 
+@pytest.mark.parametrize("method", ["VD", "VC"])
+def test_pairwise_predict_reads_the_lower_triangle_of_iSigma_w(method):
+    """predictDiag.m:113 / :193 / :279 and predictCov.m:119 / :209 / :313 read iSigma_w(i,j,:) with j <= i only.  The stored
+    inverse is symmetric up to rounding (cond * eps), and nu = sum 2 Z_ij iSigma_w(i,j) cancels by ~cond, so reading the
+    other triangle shows up at 1e-8 (it did, on config 2's rows).  Here the upper triangle is replaced outright."""
+    n, d, m = 200, 3, 12
+    model, theta, X, Y, _, omega, tr, _ = problem(method, True, False, False, n=n, d=d, m=m, seed=9)
+    r = O.GPz(theta, model, X, Y, None, omega, tr, None, fit_only=True)
+    pri = O.getPrior(X, None, theta, model, tr)
+    model.muX, model.sdX, model.muY = np.zeros(d), np.ones(d), np.zeros(1)
+    o2 = m * d + model.g_dim + m + 1
+    bad = r.iSigma_w.copy()
+    iu = np.triu_indices(m, 1)
+    bad[iu[0], iu[1], :] *= -3.0
+    model.best = dict(theta=theta, w=r.w, iSigma_w=bad, P=theta[:m * d].reshape((m, d), order="F"),
+                      v=theta[o2:o2 + m].reshape(m, 1), priors=pri)
+    Xt = X[:40].copy()
+    Xt[10:20, 1] = np.nan                                   # two groups: complete rows (predictNoisy) and one NaN pattern
+    Psi = synth.make_psi(40, d, method, seed=4)
+    mu, sigma, nu, be, ga, PHI = O.predict(Xt, model, Psi=Psi)
+    gm = L.make_model(d, 1, m, method, True)
+    _, nu_bad, _, _, _ = L.predict_core(gm, theta, r.w, bad, Xt, Psi, priors=pri)
+    _, nu_ok, _, _, _ = L.predict_core(gm, theta, r.w, np.tril(bad.transpose(2, 0, 1)).transpose(1, 2, 0) +
+                                       np.tril(bad.transpose(2, 0, 1), -1).transpose(2, 1, 0), Xt, Psi, priors=pri)
+    assert np.array_equal(nu_bad, nu_ok)                     # the upper triangle is never read
+    assert rel(nu_bad, nu) <= 64 * np.linalg.cond(r.iSigma_w[:, :, 0]) * np.finfo(float).eps, rel(nu_bad, nu)
+
+
 def test_cov_mode_with_missing_inputs_and_psi_ignores_psi_of_missing_dims():
     """Only Psi(o,o) enters (getPHI.m:84): garbage in the rows / columns of the missing dims must not matter."""
     model, theta, X, Y, Psi, omega, tr, va = problem("VC", True, True, True, n=400, d=3, m=12, seed=4)
