@@ -181,6 +181,7 @@ potf2_trti_kernel(const double* __restrict__ S, double* __restrict__ Lout, int64
                     a[q] = fma(-l, bq, a[q]);
                 }
             }
+            __syncwarp();                          // lanes 16..31 read the rows that lanes 0..15 now overwrite
             if (lane < SB) {
 #pragma unroll
                 for (int q = 0; q < SB; ++q)
