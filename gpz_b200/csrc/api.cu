@@ -2463,8 +2463,8 @@ int gpz_set_option(gpz_ctx* c, const char* name, double value) {
         g_solve_lookahead = value != 0.0;
         return GPZ_OK;
     }
-    if (strcmp(name, "phi_persist") == 0) {         // process-wide: persistent column-stationary PHI kernel (gemm.cu), 1 = default
-        g_phi_persist = value != 0.0;
+    if (strcmp(name, "phi_persist") == 0) {         // process-wide: persistent column-stationary PHI kernel (gemm.cu): 1 = default, 2 = staggered variant, 0 = off
+        g_phi_persist = value >= 2.0 ? 2 : (value != 0.0 ? 1 : 0);
         return GPZ_OK;
     }
     if (strcmp(name, "ozaki_int_fold") == 0) {      // process-wide: integer folding of the lowest digit levels (ozmma.cu), 1 = default

@@ -112,6 +112,50 @@ __device__ __forceinline__ double exp_tab(double x, const double* __restrict__ t
     return __hiloint2double(__double2hiint(v) + ((n >> 5) << 20), __double2loint(v));
 }
 
+static __device__ __noinline__ double exp_tab_cold(double x, const double* tab_sm) { return exp_tab(x, tab_sm); }
+
+// x[q] <- exp(x[q]) for N values at once, bit-identical to exp_tab per element.  exp_tab's range check is a branch per element, so
+// inside an unrolled epilogue every element's ~12-deep fp64 chain became its own basic block and ran serially (profiles/r02z_aux.md:
+// "wait" and math-pipe stalls, 6 cycles per instruction).  Here the check is one predicate for the whole group; the N chains are
+// straight-line code that the scheduler interleaves, and the per-element path only runs when some |x| > 708.
+template <int N>
+__device__ __forceinline__ void exp_tab_vec(double (&x)[N], const double* __restrict__ tab_sm) {
+    bool slow = false;
+#pragma unroll
+    for (int q = 0; q < N; ++q) slow |= !(fabs(x[q]) <= 708.0);
+    if (slow) {                                           // cold: one out-of-line copy instead of N inlined libm bodies per call site
+#pragma unroll
+        for (int q = 0; q < N; ++q) x[q] = exp_tab_cold(x[q], tab_sm);
+        return;
+    }
+    const double MAGIC = 6755399441055744.0;
+    int n[N];
+    double r[N], p[N];
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+        const double t = fma(x[q], 46.16624130844683, MAGIC);
+        n[q] = __double2loint(t);
+        const double nd = t - MAGIC;
+        r[q] = fma(nd, -0x1.cf79abc9e3b3ap-45, fma(nd, -0x1.62e42fefa0000p-6, x[q]));
+    }
+#pragma unroll
+    for (int q = 0; q < N; ++q) p[q] = fma(r[q], 1.0 / 720.0, 1.0 / 120.0);
+#pragma unroll
+    for (int q = 0; q < N; ++q) p[q] = fma(p[q], r[q], 1.0 / 24.0);
+#pragma unroll
+    for (int q = 0; q < N; ++q) p[q] = fma(p[q], r[q], 1.0 / 6.0);
+#pragma unroll
+    for (int q = 0; q < N; ++q) p[q] = fma(p[q], r[q], 0.5);
+#pragma unroll
+    for (int q = 0; q < N; ++q) p[q] = fma(p[q], r[q], 1.0);
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+        const double T = tab_sm[n[q] & 31];
+        const double v = fma(T, p[q] * r[q], T);
+        x[q] = __hiloint2double(__double2hiint(v) + ((n[q] >> 5) << 20), __double2loint(v));
+    }
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

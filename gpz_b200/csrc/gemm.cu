@@ -17,7 +17,7 @@
 namespace gpz {
 
 constexpr int STAGES = 4;
-int g_phi_persist = 1;     // PHI = exp(F W) through the persistent column-stationary kernel where it applies ("phi_persist" option)
+int g_phi_persist = 2;     // PHI = exp(F W) through the persistent column-stationary kernel where it applies ("phi_persist" option): 2 staggered M-groups (default), 1 CTA-synchronous, 0 off
 int g_gemm_warps = 0;       // 0 = defaults (Gram / T-GEMM 8 warps, PHI build 16 warps: its exp epilogue likes more warps);
                             // 8 / 16 force all three (gpz_set_option "gemm_warps").  8 vs 16 differ by <4 % either way across boxes.
 
@@ -426,11 +426,18 @@ tgemm_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict
             const int64_t gi = i0 + wm0 + i * 8 + g;
             const bool ok = gi < n;
             double s0 = 0.0, s1 = 0.0;
+            double ex[2 * NT];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                ex[2 * j] = acc[i][j][0];
+                ex[2 * j + 1] = acc[i][j][1];
+            }
+            if (!pe.plain) exp_tab_vec(ex, exp_sm);
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
                 const int64_t gj = j0 + wn0 + j * 8 + 2 * t;
-                double p0 = (gj < pe.m) ? (pe.plain ? acc[i][j][0] : exp_tab(acc[i][j][0], exp_sm)) : 0.0;
-                double p1 = (gj + 1 < pe.m) ? (pe.plain ? acc[i][j][1] : exp_tab(acc[i][j][1], exp_sm)) : 0.0;
+                double p0 = (gj < pe.m) ? ex[2 * j] : 0.0;
+                double p1 = (gj + 1 < pe.m) ? ex[2 * j + 1] : 0.0;
                 if (pe.ycol != nullptr && ok) {
                     if (gj == pe.m) p0 = pe.ycol[gi];
                     if (gj + 1 == pe.m) p1 = pe.ycol[gi];
@@ -501,6 +508,55 @@ __device__ __forceinline__ void pp_tma_2d(const CUtensorMap* map, uint32_t dst, 
                  : "memory");
 }
 
+// exp + store + row-dot partials of one warp's 32 x 32 accumulator block (both persistent kernels).  NDOT row dots are compiled in
+// (the training sweep needs one, PHI v; validation / predict two), and EDGE = false is the interior tile: no row / column masks, no
+// y column.  One exp_tab_vec call per 8 accumulators keeps their fp64 chains interleaved.
+template <int NDOT, bool EDGE, int MT, int NT>
+__device__ __forceinline__ void phi_epilogue(const double (&acc)[MT][NT][2], const PEpi& pe, int MP, int64_t n, int64_t i0, int64_t j0,
+                                             int wm0, int wn0, int g, int t, const double2 (&v0)[NT], const double2 (&v1)[NT],
+                                             const double* __restrict__ exp_sm, double (&rs0)[MT], double (&rs1)[MT]) {
+    double* prow = pe.Phi != nullptr ? pe.Phi + (i0 + wm0 + g) * MP + j0 + wn0 + 2 * t : nullptr;
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+        const int64_t gi = i0 + wm0 + i * 8 + g;
+        const bool ok = !EDGE || gi < n;
+        double ex[2 * NT];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            ex[2 * j] = acc[i][j][0];
+            ex[2 * j + 1] = acc[i][j][1];
+        }
+        exp_tab_vec(ex, exp_sm);
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            double p0 = ex[2 * j], p1 = ex[2 * j + 1];
+            if (EDGE) {
+                const int64_t gj = j0 + wn0 + j * 8 + 2 * t;
+                if (gj >= pe.m) p0 = 0.0;
+                if (gj + 1 >= pe.m) p1 = 0.0;
+                if (pe.ycol != nullptr && ok) {
+                    if (gj == pe.m) p0 = pe.ycol[gi];
+                    if (gj + 1 == pe.m) p1 = pe.ycol[gi];
+                }
+            }
+            if (ok && prow != nullptr) *reinterpret_cast<double2*>(prow + static_cast<int64_t>(i) * 8 * MP + j * 8) = make_double2(p0, p1);
+            if (NDOT > 0) s0 = fma(p0, v0[j].x, fma(p1, v0[j].y, s0));
+            if (NDOT > 1) s1 = fma(p0, v1[j].x, fma(p1, v1[j].y, s1));
+        }
+        if (NDOT > 0) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+        }
+        if (NDOT > 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        }
+        rs0[i] = s0;
+        rs1[i] = s1;
+    }
+}
+
 struct PhiPersist {
     const double* W;        // [K][MP]
     int MP, K4, LDK, ntn;
@@ -508,6 +564,7 @@ struct PhiPersist {
     PEpi pe;
 };
 
+template <int NDOT>
 __global__ void __launch_bounds__(512, 1)
 phi_persist_kernel(const __grid_constant__ CUtensorMap mapF, const PhiPersist a) {
     constexpr int WARPS_M = 4, WM = TILE / WARPS_M, MT = WM / 8, NT = 4;
@@ -542,8 +599,8 @@ phi_persist_kernel(const __grid_constant__ CUtensorMap mapF, const PhiPersist a)
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
         const int64_t gj = j0 + wn0 + j * 8 + 2 * t;
-        v0[j] = pe.ndot > 0 ? *reinterpret_cast<const double2*>(pe.vec[0] + gj) : make_double2(0.0, 0.0);
-        v1[j] = pe.ndot > 1 ? *reinterpret_cast<const double2*>(pe.vec[1] + gj) : make_double2(0.0, 0.0);
+        v0[j] = NDOT > 0 ? *reinterpret_cast<const double2*>(pe.vec[0] + gj) : make_double2(0.0, 0.0);
+        v1[j] = NDOT > 1 ? *reinterpret_cast<const double2*>(pe.vec[1] + gj) : make_double2(0.0, 0.0);
     }
     cp_async_wait<0>();
     __syncthreads();
@@ -579,37 +636,16 @@ phi_persist_kernel(const __grid_constant__ CUtensorMap mapF, const PhiPersist a)
         }
         const int64_t i0 = rt * TILE;
         double rs0[MT], rs1[MT];
-#pragma unroll
-        for (int i = 0; i < MT; ++i) {
-            const int64_t gi = i0 + wm0 + i * 8 + g;
-            const bool ok = gi < a.n;
-            double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-            for (int j = 0; j < NT; ++j) {
-                const int64_t gj = j0 + wn0 + j * 8 + 2 * t;
-                double p0 = (gj < pe.m) ? exp_tab(acc[i][j][0], exp_sm) : 0.0;
-                double p1 = (gj + 1 < pe.m) ? exp_tab(acc[i][j][1], exp_sm) : 0.0;
-                if (pe.ycol != nullptr && ok) {
-                    if (gj == pe.m) p0 = pe.ycol[gi];
-                    if (gj + 1 == pe.m) p1 = pe.ycol[gi];
-                }
-                if (ok && pe.Phi != nullptr) *reinterpret_cast<double2*>(pe.Phi + gi * a.MP + gj) = make_double2(p0, p1);
-                s0 = fma(p0, v0[j].x, fma(p1, v0[j].y, s0));
-                s1 = fma(p0, v1[j].x, fma(p1, v1[j].y, s1));
-            }
-            s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
-            s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-            rs0[i] = s0;
-            rs1[i] = s1;
-        }
-        if (pe.ndot > 0) {
+        if (j0 + TILE <= pe.m && i0 + TILE <= a.n)
+            phi_epilogue<NDOT, false>(acc, pe, a.MP, a.n, i0, j0, wm0, wn0, g, t, v0, v1, exp_sm, rs0, rs1);
+        else
+            phi_epilogue<NDOT, true>(acc, pe, a.MP, a.n, i0, j0, wm0, wn0, g, t, v0, v1, exp_sm, rs0, rs1);
+        if (NDOT > 0) {
             if (t == 0) {
 #pragma unroll
                 for (int i = 0; i < MT; ++i) {
                     red[0][warp & 3][wm0 + i * 8 + g] = rs0[i];
-                    red[1][warp & 3][wm0 + i * 8 + g] = rs1[i];
+                    if (NDOT > 1) red[1][warp & 3][wm0 + i * 8 + g] = rs1[i];
                 }
             }
             __syncthreads();
@@ -617,12 +653,142 @@ phi_persist_kernel(const __grid_constant__ CUtensorMap mapF, const PhiPersist a)
                 const int64_t gi = i0 + tid;
                 if (gi < a.n) {
                     pe.part[0][static_cast<int64_t>(ct) * pe.part_ld + gi] = red[0][0][tid] + red[0][1][tid] + red[0][2][tid] + red[0][3][tid];
-                    if (pe.ndot > 1)
+                    if (NDOT > 1)
                         pe.part[1][static_cast<int64_t>(ct) * pe.part_ld + gi] = red[1][0][tid] + red[1][1][tid] + red[1][2][tid] + red[1][3][tid];
                 }
             }
         }
         __syncthreads();                                                     // everyone is done with As[buf] and red
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Staggered form of the kernel above (g_phi_persist == 2; NOT the default: measured 7 % slower, see the end of this comment).  ncu on phi_persist_kernel (profiles/r02z_aux.md): DMMA
+// pipe 58 % active, FP64 pipe 12 %, top stall math-pipe throttle -- the CTA-wide barrier at the end of every row tile keeps
+// all 16 warps in phase, so the DMMA pipe is saturated during the K loops and idle during the exp/store epilogues.  Here no
+// barrier spans the CTA inside the tile loop:
+//   * the four M-groups (4 warps each, one per SM sub-partition) start one K-loop apart (a chain of named barriers in the
+//     first iteration) and stay that way: while one group multiplies, the other three exponentiate and store;
+//   * shared-memory row-feature buffers are released per warp (mbarrier empty[b], 16 arrivals) and refilled by TMA from
+//     thread 0 after ITS K loop, one tile ahead;
+//   * the row-dot partials of the 4 N-warps of an M-group are combined behind a 128-thread named barrier, double-buffered.
+// Same arithmetic in the same order: bit-identical to phi_persist_kernel and tgemm_kernel<1>.
+// Measured (profiles/r02z_stagger_ab2.log, interleaved A/B on one box): 8.42 ms against 7.85 ms for the CTA-synchronous kernel at
+// the headline shape, 2.10 against 2.08 ms at config 3.  The exp/store warps do not fill the DMMA pipe's idle time: while other
+// warps of the sub-partition stream DMMAs, DFMA issue starves (the same behaviour the tcgen05 kernel shows), so the
+// phases serialise either way and the extra barriers only cost.  Kept as an option for that record.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pp_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void pp_named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void pp_named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+template <int NDOT>
+__global__ void __launch_bounds__(512, 1)
+phi_stagger_kernel(const __grid_constant__ CUtensorMap mapF, const PhiPersist a) {
+    constexpr int WARPS_M = 4, WM = TILE / WARPS_M, MT = WM / 8, NT = 4;
+    extern __shared__ __align__(128) unsigned char pp_smem[];
+    double* Ws = reinterpret_cast<double*>(pp_smem);                       // [K4][LDT]
+    double* As = Ws + a.K4 * LDT;                                           // [2][TILE][LDK]
+    __shared__ double red[2][2][4][TILE];                                   // [tile parity][dot][N-warp][row]
+    __shared__ double exp_sm[32];
+    __shared__ __align__(8) unsigned long long bars[4];                     // full[2] (TMA landed), empty[2] (16 warps done reading)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int mg = warp >> 2, nw = warp & 3;
+    const int wm0 = mg * WM, wn0 = nw * 32;
+    const int ct = blockIdx.x % a.ntn;
+    const int64_t step = gridDim.x / a.ntn;
+    const int64_t j0 = static_cast<int64_t>(ct) * TILE;
+    const int LDK = a.LDK;
+    const uint32_t tile_bytes = static_cast<uint32_t>(TILE * LDK * sizeof(double));
+    const PEpi& pe = a.pe;
+    const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2]);
+
+    for (int c = tid; c < a.K4 * (TILE / 2); c += 512) {                    // this CTA's column tile of W, once
+        const int r = c >> 6, cc = c & 63;
+        cp_async16(Ws + r * LDT + cc * 2, a.W + static_cast<int64_t>(r) * a.MP + j0 + cc * 2, 16);
+    }
+    cp_async_commit();
+    exp_tab_stage(exp_sm);
+    if (tid == 0) {
+        pp_mbar_init(full0, 1);
+        pp_mbar_init(full0 + 8, 1);
+        pp_mbar_init(empty0, 16);
+        pp_mbar_init(empty0 + 8, 16);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    double2 v0[NT], v1[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        const int64_t gj = j0 + wn0 + j * 8 + 2 * t;
+        v0[j] = NDOT > 0 ? *reinterpret_cast<const double2*>(pe.vec[0] + gj) : make_double2(0.0, 0.0);
+        v1[j] = NDOT > 1 ? *reinterpret_cast<const double2*>(pe.vec[1] + gj) : make_double2(0.0, 0.0);
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    int64_t rt = blockIdx.x / a.ntn;
+    if (tid == 0 && rt < a.tiles_m) {
+        pp_mbar_expect(full0, tile_bytes);
+        pp_tma_2d(&mapF, smem_u32(As), full0, 0, static_cast<int>(rt * TILE));
+    }
+    for (uint32_t it = 0; rt < a.tiles_m; rt += step, ++it) {
+        const uint32_t buf = it & 1u;
+        if (it == 0 && mg > 0) pp_named_sync(4 + mg, 256);                   // start one K loop after the M-group before
+        pp_mbar_wait(full0 + 8 * buf, (it >> 1) & 1u);
+        const double* as = As + buf * TILE * LDK;
+        double acc[MT][NT][2];
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int kk = 0; kk < a.K4 / 4; ++kk) {
+            const int kc = kk * 4 + t;
+            double bf[NT];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) bf[j] = Ws[kc * LDT + wn0 + j * 8 + g];
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
+                const double af = as[(wm0 + i * 8 + g) * LDK + kc];
+#pragma unroll
+                for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], af, bf[j]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) pp_mbar_arrive(empty0 + 8 * buf);                     // this warp no longer reads As[buf]
+        if (it == 0 && mg < WARPS_M - 1) pp_named_arrive(4 + mg + 1, 256);
+        if (tid == 0 && rt + step < a.tiles_m) {                             // next row tile into the other buffer: every warp has
+            if (it >= 1) pp_mbar_wait(empty0 + 8 * (buf ^ 1u), ((it - 1) >> 1) & 1u);   // left the K loop of the tile before this one
+            pp_mbar_expect(full0 + 8 * (buf ^ 1u), tile_bytes);
+            pp_tma_2d(&mapF, smem_u32(As + (buf ^ 1u) * TILE * LDK), full0 + 8 * (buf ^ 1u), 0, static_cast<int>((rt + step) * TILE));
+        }
+        const int64_t i0 = rt * TILE;
+        double rs0[MT], rs1[MT];
+        if (j0 + TILE <= pe.m && i0 + TILE <= a.n)
+            phi_epilogue<NDOT, false>(acc, pe, a.MP, a.n, i0, j0, wm0, wn0, g, t, v0, v1, exp_sm, rs0, rs1);
+        else
+            phi_epilogue<NDOT, true>(acc, pe, a.MP, a.n, i0, j0, wm0, wn0, g, t, v0, v1, exp_sm, rs0, rs1);
+        if (NDOT > 0) {
+            double (*rd)[4][TILE] = red[buf];
+            if (t == 0) {
+#pragma unroll
+                for (int i = 0; i < MT; ++i) {
+                    rd[0][nw][wm0 + i * 8 + g] = rs0[i];
+                    if (NDOT > 1) rd[1][nw][wm0 + i * 8 + g] = rs1[i];
+                }
+            }
+            pp_named_sync(1 + mg, 128);                                      // the 4 N-warps of this M-group; red[buf] is written
+            if (nw == 0) {                                                   // again two tiles on, behind the next such barrier
+                const int row = wm0 + lane;
+                const int64_t gi = i0 + row;
+                if (gi < a.n) {
+                    pe.part[0][static_cast<int64_t>(ct) * pe.part_ld + gi] = rd[0][0][row] + rd[0][1][row] + rd[0][2][row] + rd[0][3][row];
+                    if (NDOT > 1)
+                        pe.part[1][static_cast<int64_t>(ct) * pe.part_ld + gi] = rd[1][0][row] + rd[1][1][row] + rd[1][2][row] + rd[1][3][row];
+                }
+            }
+        }
     }
 }
 
@@ -632,14 +798,22 @@ static int launch_phi_persist(const double* F, int64_t ldf, int kvalid, const do
     const int K4 = static_cast<int>(round_up(kvalid, 4));
     const int LDK = (K4 % 8 == 4) ? K4 : K4 + 4;
     const size_t smem = sizeof(double) * (static_cast<size_t>(K4) * LDT + 2 * static_cast<size_t>(TILE) * LDK);
-    if (!ozmma_available() || LDK > ldf || smem > 218 * 1024 || n >= (1LL << 31) - TILE || (reinterpret_cast<uintptr_t>(F) & 15) != 0)
+    const bool stagger = g_phi_persist >= 2;                                 // 8 KB more static shared memory (double-buffered partials)
+    if (!ozmma_available() || LDK > ldf || smem > (stagger ? 210 : 218) * 1024 || n >= (1LL << 31) - TILE ||
+        (reinterpret_cast<uintptr_t>(F) & 15) != 0)
         return GPZ_OK;                                                       // the tile-per-CTA kernel takes it
     static PerDeviceOnce once;
     static int sms_dev[128];
     int dev = 0;
     cudaGetDevice(&dev);
     if (once.need()) {
-        GPZ_CUDA(cudaFuncSetAttribute(phi_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024));   // + 8.4 KB static = the 227 KB a CTA may use
+        // dynamic + 8.4 KB (16.7 KB staggered) static = the 227 KB a CTA may use
+        GPZ_CUDA(cudaFuncSetAttribute(phi_persist_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024));
+        GPZ_CUDA(cudaFuncSetAttribute(phi_persist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024));
+        GPZ_CUDA(cudaFuncSetAttribute(phi_persist_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024));
+        GPZ_CUDA(cudaFuncSetAttribute(phi_stagger_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        GPZ_CUDA(cudaFuncSetAttribute(phi_stagger_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        GPZ_CUDA(cudaFuncSetAttribute(phi_stagger_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         sms_dev[dev & 127] = sms;
@@ -659,7 +833,17 @@ static int launch_phi_persist(const double* F, int64_t ldf, int kvalid, const do
     int64_t per = sms_dev[dev & 127] / a.ntn;
     if (per < 1) per = 1;
     if (per > a.tiles_m) per = a.tiles_m;
-    phi_persist_kernel<<<static_cast<unsigned>(per * a.ntn), 512, smem, st>>>(map, a);
+    const unsigned grid = static_cast<unsigned>(per * a.ntn);
+    const int nd = pe.ndot < 0 ? 0 : (pe.ndot > 2 ? 2 : pe.ndot);
+    if (stagger) {
+        if (nd == 0) phi_stagger_kernel<0><<<grid, 512, smem, st>>>(map, a);
+        else if (nd == 1) phi_stagger_kernel<1><<<grid, 512, smem, st>>>(map, a);
+        else phi_stagger_kernel<2><<<grid, 512, smem, st>>>(map, a);
+    } else {
+        if (nd == 0) phi_persist_kernel<0><<<grid, 512, smem, st>>>(map, a);
+        else if (nd == 1) phi_persist_kernel<1><<<grid, 512, smem, st>>>(map, a);
+        else phi_persist_kernel<2><<<grid, 512, smem, st>>>(map, a);
+    }
     GPZ_KERNEL_CHECK();
     *done = true;
     return GPZ_OK;

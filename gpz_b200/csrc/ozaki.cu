@@ -71,11 +71,33 @@ __device__ __forceinline__ void oz_store_digits4(const unsigned long long (&K)[4
 //       sum_i F_ij D_il = 2^-Ef sum_i w_i PHI_ij PHI_il, the row scale cancels inside the product.  Column m (aug) carries
 //       w_i 2^E_i y_i / (2^Ef cy), cy = 2^ceil(log2 max|y|), so that row m of the Gram is PHI'(w y)  (GPz/GPz.m:70).
 //   Rows in [n, n_pad) are zero-filled (the Gram contracts over whole 1024-row chunks).
+// S > 0: the digit count is a compile-time constant (the store loops and the bias fold); S == 0 reads it from `s`.
+// KEEP: rows of <= 1024 columns stay in registers between the two passes (row maximum, then digits); the second pass used to
+// re-read the row, and 56 % of that came from HBM again (profiles/r01h: 12.9 GB read for an 8.2 GB input).
+// A double4 that lies wholly inside [0, m) takes the mask-free path; the column tail and the y column take the general one.
+// ncu before this form (profiles/r02z_aux.md): 94 instructions per element, ALU pipe 60 % / issue 58 % active against DRAM at 60 %.
+template <int S>
+__device__ __forceinline__ void oz_store_digits4s(const unsigned long long (&K)[4], int s, int8_t* out, int64_t digit_stride) {
+    unsigned lo[4], hi[4];
+    oz_transpose4(static_cast<unsigned>(K[0]), static_cast<unsigned>(K[1]), static_cast<unsigned>(K[2]), static_cast<unsigned>(K[3]), lo);
+    if (S == 0 || S > 4)
+        oz_transpose4(static_cast<unsigned>(K[0] >> 32), static_cast<unsigned>(K[1] >> 32), static_cast<unsigned>(K[2] >> 32),
+                      static_cast<unsigned>(K[3] >> 32), hi);
+    const int ns = S > 0 ? S : s;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (S > 0 ? k >= S : k >= s) break;
+        *reinterpret_cast<unsigned*>(out + static_cast<int64_t>(ns - 1 - k) * digit_stride) = k < 4 ? lo[k] : hi[k - 4];
+    }
+}
+
+template <int S, bool KEEP>
 __global__ void __launch_bounds__(256)
-oz_digits_kernel(const double* __restrict__ Phi, int64_t ld, int src_cols, int m, int MP, int64_t n, int64_t n_pad, int s,
+oz_digits_kernel(const double* __restrict__ Phi, int64_t ld, int src_cols, int m, int MP, int64_t n, int64_t n_pad, int s_rt,
                  const double* __restrict__ wgt,
                  const double* __restrict__ scal, int aug, int8_t* __restrict__ D8, int8_t* __restrict__ F8, double* __restrict__ ea,
                  int* __restrict__ flag) {
+    const int s = S > 0 ? S : s_rt;
     const int lane = threadIdx.x & 31;
     const int64_t i = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
     if (i >= n_pad) return;
@@ -93,18 +115,25 @@ oz_digits_kernel(const double* __restrict__ Phi, int64_t ld, int src_cols, int m
     double mx = 0.0;
     bool bad = false;                                   // NaN / Inf cannot be expressed in digits: raise the failure flag instead
     const double4 zero4 = make_double4(0.0, 0.0, 0.0, 0.0);
-    // rows of up to 1024 columns stay in registers between the two passes (row maximum, then digits): the second pass used to
-    // re-read the row, and 56 % of that came from HBM again (profiles/r01h: 12.9 GB read for an 8.2 GB input)
-    constexpr int KEEP = 8;
-    const bool keep = MP <= KEEP * 128;
-    double4 vb[KEEP];
+    constexpr int NK = KEEP ? 8 : 1;
+    double4 vb[NK];
+    if (KEEP) {
 #pragma unroll
-    for (int it = 0; it < KEEP; ++it) {
-        const int j = lane * 4 + it * 128;
-        vb[it] = (keep && j < MP && j < src_cols) ? *reinterpret_cast<const double4*>(row + j) : zero4;
+        for (int it = 0; it < NK; ++it) {
+            const int j = lane * 4 + it * 128;
+            vb[it] = (j < MP && j < src_cols) ? *reinterpret_cast<const double4*>(row + j) : zero4;
+        }
     }
     const int lim = (aug && fout != nullptr) ? m + 1 : m;
     auto scan = [&](const double4& v, int j) {
+        if (j + 4 <= m) {                               // interior: one finite test on the sum of magnitudes, no masks
+            const double a0 = fabs(v.x), a1 = fabs(v.y), a2 = fabs(v.z), a3 = fabs(v.w);
+            const double m01 = fmax(a0, a1), m23 = fmax(a2, a3);
+            const double sum = (a0 + a1) + (a2 + a3), mq = fmax(m01, m23);
+            bad |= (sum != sum) || !(mq <= 1.7e308);           // a NaN survives the sum (fmax drops it), an Inf the maximum
+            mx = fmax(mx, mq);
+            return;
+        }
         if (j < lim) bad |= !(fabs(v.x) <= 1.7e308);
         if (j + 1 < lim) bad |= !(fabs(v.y) <= 1.7e308);
         if (j + 2 < lim) bad |= !(fabs(v.z) <= 1.7e308);
@@ -114,9 +143,9 @@ oz_digits_kernel(const double* __restrict__ Phi, int64_t ld, int src_cols, int m
         if (j + 2 < m) mx = fmax(mx, fabs(v.z));
         if (j + 3 < m) mx = fmax(mx, fabs(v.w));
     };
-    if (keep) {
+    if (KEEP) {
 #pragma unroll
-        for (int it = 0; it < KEEP; ++it)
+        for (int it = 0; it < NK; ++it)
             if (lane * 4 + it * 128 < MP) scan(vb[it], lane * 4 + it * 128);
     } else {
         for (int j = lane * 4; j < MP; j += 128) scan(j < src_cols ? *reinterpret_cast<const double4*>(row + j) : zero4, j);
@@ -137,18 +166,29 @@ oz_digits_kernel(const double* __restrict__ Phi, int64_t ld, int src_cols, int m
     auto emit = [&](const double4& v, int j) {
         const double x[4] = {v.x, v.y, v.z, v.w};
         unsigned long long I[4], J[4];
+        if (j + 4 <= m) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) I[q] = oz_digit_bytes(__double2ll_rn(x[q] * sc), bias);
+            oz_store_digits4s<S>(I, s, dout + j, MP);
+            if (fout != nullptr) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) J[q] = oz_digit_bytes(__double2ll_rn(x[q] * fs), bias);
+                oz_store_digits4s<S>(J, s, fout + j, MP);
+            }
+            return;
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const bool in = j + q < m;
             I[q] = oz_digit_bytes(in ? __double2ll_rn(x[q] * sc) : 0, bias);
             J[q] = oz_digit_bytes(in ? __double2ll_rn(x[q] * fs) : ((aug && j + q == m) ? __double2ll_rn(x[q] * fy) : 0), bias);
         }
-        oz_store_digits4(I, s, dout + j, MP);
-        if (fout != nullptr) oz_store_digits4(J, s, fout + j, MP);
+        oz_store_digits4s<S>(I, s, dout + j, MP);
+        if (fout != nullptr) oz_store_digits4s<S>(J, s, fout + j, MP);
     };
-    if (keep) {
+    if (KEEP) {
 #pragma unroll
-        for (int it = 0; it < KEEP; ++it)
+        for (int it = 0; it < NK; ++it)
             if (lane * 4 + it * 128 < MP) emit(vb[it], lane * 4 + it * 128);
     } else {
         for (int j = lane * 4; j < MP; j += 128) emit(j < src_cols ? *reinterpret_cast<const double4*>(row + j) : zero4, j);
@@ -195,6 +235,16 @@ int64_t oz_padded_rows(int64_t rows) { return round_up(rows > 0 ? rows : 1, OZG_
 // bytes of ONE digit set for `rows` rows (D8 or F8)
 int64_t oz_digit_bytes(int MP, int s, int64_t rows) { return al256(oz_padded_rows(rows) * static_cast<int64_t>(s) * MP); }
 
+static void launch_oz_digits(const double* A, int64_t ld, int src_cols, int m, int MP, int64_t rows, int64_t np, int s, const double* wgt,
+                             const double* d_scal, int aug, int8_t* D8, int8_t* F8, double* ea, int* flag, cudaStream_t st) {
+    const unsigned grid = static_cast<unsigned>(ceil_div(np, 8));
+    const bool keep = MP <= 1024;
+    if (s == 7 && keep) oz_digits_kernel<7, true><<<grid, 256, 0, st>>>(A, ld, src_cols, m, MP, rows, np, s, wgt, d_scal, aug, D8, F8, ea, flag);
+    else if (s == 7) oz_digits_kernel<7, false><<<grid, 256, 0, st>>>(A, ld, src_cols, m, MP, rows, np, s, wgt, d_scal, aug, D8, F8, ea, flag);
+    else if (keep) oz_digits_kernel<0, true><<<grid, 256, 0, st>>>(A, ld, src_cols, m, MP, rows, np, s, wgt, d_scal, aug, D8, F8, ea, flag);
+    else oz_digits_kernel<0, false><<<grid, 256, 0, st>>>(A, ld, src_cols, m, MP, rows, np, s, wgt, d_scal, aug, D8, F8, ea, flag);
+}
+
 // PHI rows -> D8 (and F8 when wgt != nullptr) + ea.  d_scal: [0] >= max w, [1] >= max |y| (device).
 int ozaki_digits(const double* Phi, int64_t ld, int MP, int m, int64_t rows, int s, const double* wgt, const double* d_scal, int aug,
                  int8_t* D8, int8_t* F8, double* ea, int* flag, cudaStream_t st, int64_t* launches) {
@@ -203,8 +253,7 @@ int ozaki_digits(const double* Phi, int64_t ld, int MP, int m, int64_t rows, int
         return GPZ_ERR_USAGE;
     }
     const int64_t np = oz_padded_rows(rows);
-    oz_digits_kernel<<<static_cast<unsigned>(ceil_div(np, 8)), 256, 0, st>>>(Phi, ld, MP, m, MP, rows, np, s, wgt, d_scal, aug, D8,
-                                                                             wgt != nullptr ? F8 : nullptr, ea, flag);
+    launch_oz_digits(Phi, ld, MP, m, MP, rows, np, s, wgt, d_scal, aug, D8, wgt != nullptr ? F8 : nullptr, ea, flag, st);
     GPZ_KERNEL_CHECK();
     ++*launches;
     return GPZ_OK;
@@ -295,8 +344,7 @@ int ozaki_row_digits(const double* A, int64_t lda, int cols, int K128, int64_t r
     }
     const int64_t np = oz_padded_rows(rows);
     const int src_cols = static_cast<int>(lda < K128 ? lda : K128);
-    oz_digits_kernel<<<static_cast<unsigned>(ceil_div(np, 8)), 256, 0, st>>>(A, lda, src_cols, cols, K128, rows, np, s, nullptr, nullptr, 0, A8,
-                                                                             nullptr, ea, flag);
+    launch_oz_digits(A, lda, src_cols, cols, K128, rows, np, s, nullptr, nullptr, 0, A8, nullptr, ea, flag, st);
     GPZ_KERNEL_CHECK();
     ++*launches;
     return GPZ_OK;
@@ -477,8 +525,7 @@ int ozaki_feature_digits(const double* F, int64_t ldf, int q, int64_t rows, int 
         return GPZ_ERR_USAGE;
     }
     const int64_t np = oz_padded_rows(rows);
-    oz_digits_kernel<<<static_cast<unsigned>(ceil_div(np, 8)), 256, 0, st>>>(F, ldf, static_cast<int>(ldf < 128 ? ldf : 128), q, 128, rows, np, s,
-                                                                             nullptr, nullptr, 0, FD8, nullptr, eaF, flag);
+    launch_oz_digits(F, ldf, static_cast<int>(ldf < 128 ? ldf : 128), q, 128, rows, np, s, nullptr, nullptr, 0, FD8, nullptr, eaF, flag, st);
     GPZ_KERNEL_CHECK();
     ++*launches;
     return GPZ_OK;

@@ -19,12 +19,15 @@ ths = bench.thetas_for(theta0, 2 * reps + 2)
 ctx.eval(ths[0])
 ctx.eval(ths[1])
 acc = {va: [], vb: []}
+res = {}
 for r in range(reps):
     for v in (va, vb):
         ctx.set_option(opt, v)
-        ctx.eval(ths[2 + r])
-        acc[v].append(ctx.last_timing())
+        f, g, _ = ctx.eval(ths[2 + r])
+        acc[v].append(dict(ctx.last_timing(), **{"k_" + k: x for k, x in ctx.kernel_timing().items()}))
+        res.setdefault(r, []).append((f, g))
 for v in (va, vb):
     keys = [k for k in acc[v][0] if k not in ("i8_gemms_ops", "int8_slices", "int8_gram")]
     print(opt, v, {k: round(float(np.mean([t[k] for t in acc[v]])), 3) for k in keys})
+print("bit-identical f and gradient between the two settings:", all(a[0] == b[0] and np.array_equal(a[1], b[1]) for a, b in res.values()))
 ctx.close()
