@@ -486,18 +486,32 @@ exp_rows_inplace_kernel(double* __restrict__ Phi, int64_t ld, int m, int MP, int
     if (i >= rows) return;
     double* row = Phi + i * ld;
     double s0 = 0.0, s1 = 0.0;
-    for (int j = 2 * lane; j < MP; j += 64) {
-        double2 v = *reinterpret_cast<const double2*>(row + j);
-        v.x = (j < m) ? exp_tab(v.x, exp_sm) : 0.0;
-        v.y = (j + 1 < m) ? exp_tab(v.y, exp_sm) : 0.0;
-        *reinterpret_cast<double2*>(row + j) = v;
-        if (dots.n > 0) {
-            const double2 a = __ldg(reinterpret_cast<const double2*>(dots.vec[0] + j));
-            s0 = fma(v.x, a.x, fma(v.y, a.y, s0));
+    for (int jb = 2 * lane; jb < MP; jb += 256) {                 // 4 double2 per lane and step: one grouped exp (exp_tab_vec)
+        double ex[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = jb + 64 * q;
+            const double2 v = j < MP ? *reinterpret_cast<const double2*>(row + j) : make_double2(0.0, 0.0);
+            ex[2 * q] = v.x;
+            ex[2 * q + 1] = v.y;
         }
-        if (dots.n > 1) {
-            const double2 b = __ldg(reinterpret_cast<const double2*>(dots.vec[1] + j));
-            s1 = fma(v.x, b.x, fma(v.y, b.y, s1));
+        exp_tab_vec(ex, exp_sm);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = jb + 64 * q;
+            if (j >= MP) continue;
+            double2 v;
+            v.x = (j < m) ? ex[2 * q] : 0.0;
+            v.y = (j + 1 < m) ? ex[2 * q + 1] : 0.0;
+            *reinterpret_cast<double2*>(row + j) = v;
+            if (dots.n > 0) {
+                const double2 a = __ldg(reinterpret_cast<const double2*>(dots.vec[0] + j));
+                s0 = fma(v.x, a.x, fma(v.y, a.y, s0));
+            }
+            if (dots.n > 1) {
+                const double2 b = __ldg(reinterpret_cast<const double2*>(dots.vec[1] + j));
+                s1 = fma(v.x, b.x, fma(v.y, b.y, s1));
+            }
         }
     }
     s0 = warp_sum(s0);
