@@ -2463,6 +2463,14 @@ int gpz_set_option(gpz_ctx* c, const char* name, double value) {
         g_solve_lookahead = value != 0.0;
         return GPZ_OK;
     }
+    if (strcmp(name, "prep_block") == 0) {          // process-wide: CTA size of the per-basis parameter kernels (phi.cu), 32 = default
+        if (value != 32.0 && value != 64.0 && value != 128.0) {
+            set_error("prep_block must be 32, 64 or 128");
+            return GPZ_ERR_USAGE;
+        }
+        g_prep_block = static_cast<int>(value);
+        return GPZ_OK;
+    }
     if (strcmp(name, "phi_persist") == 0) {         // process-wide: persistent column-stationary PHI kernel (gemm.cu): 1 = default, 2 = staggered variant, 0 = off
         g_phi_persist = value >= 2.0 ? 2 : (value != 0.0 ? 1 : 0);
         return GPZ_OK;

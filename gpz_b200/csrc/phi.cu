@@ -12,6 +12,7 @@
 namespace gpz {
 
 constexpr double kLn2 = 0.69314718055994530942;
+int g_prep_block = 32;          // threads per CTA of the per-basis theta -> parameter kernels ("prep_block" option: 32, 64 or 128)
 
 // ------------------------------------------------------------------------------------------------
 // theta -> per-basis arrays
@@ -177,14 +178,17 @@ prep_patterns_kernel(Params P) {
 }
 
 int prep_params(const double* d_theta, const Params& P, int need_sigma, cudaStream_t st, int64_t* launches) {
-    prep_kernel<<<static_cast<unsigned>(ceil_div(P.MP, 128)), 128, 0, st>>>(d_theta, P, need_sigma);
+    // one thread per basis with O(d^3) serial work each: latency-bound, so one warp per CTA spreads the m threads over 4x as many SMs
+    // (ncu launch list at m = 1000, d = 10: 128-thread CTAs 80 / 90 us per launch, the n-independent part of the 8-GPU step)
+    const int bt = g_prep_block;
+    prep_kernel<<<static_cast<unsigned>(ceil_div(P.MP, bt)), bt, 0, st>>>(d_theta, P, need_sigma);
     GPZ_KERNEL_CHECK();
     ++*launches;
     if (mode_is_cov(P.mode) && P.Mg != nullptr) {
-        dim3 grid(static_cast<unsigned>(ceil_div(P.MP, 128)), static_cast<unsigned>(P.npat));
-        if (P.d <= 8) prep_patterns_kernel<8><<<grid, 128, 0, st>>>(P);
-        else if (P.d <= 16) prep_patterns_kernel<16><<<grid, 128, 0, st>>>(P);
-        else prep_patterns_kernel<32><<<grid, 128, 0, st>>>(P);
+        dim3 grid(static_cast<unsigned>(ceil_div(P.MP, bt)), static_cast<unsigned>(P.npat));
+        if (P.d <= 8) prep_patterns_kernel<8><<<grid, bt, 0, st>>>(P);
+        else if (P.d <= 16) prep_patterns_kernel<16><<<grid, bt, 0, st>>>(P);
+        else prep_patterns_kernel<32><<<grid, bt, 0, st>>>(P);
         GPZ_KERNEL_CHECK();
         ++*launches;
     }
