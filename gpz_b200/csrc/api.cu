@@ -2459,8 +2459,8 @@ int gpz_set_option(gpz_ctx* c, const char* name, double value) {
         g_gemm_warps = static_cast<int>(value);
         return GPZ_OK;
     }
-    if (strcmp(name, "solve_lookahead") == 0) {     // process-wide: look-ahead blocked Cholesky (solve.cu), 1 = default
-        g_solve_lookahead = value != 0.0;
+    if (strcmp(name, "solve_lookahead") == 0) {     // process-wide: blocked Cholesky (solve.cu): 2 = look-ahead + incremental inverse (default), 1 = look-ahead, 0 = in-stream
+        g_solve_lookahead = value >= 2.0 ? 2 : (value != 0.0 ? 1 : 0);
         return GPZ_OK;
     }
     if (strcmp(name, "prep_block") == 0) {          // process-wide: CTA size of the per-basis parameter kernels (phi.cu), 32 = default

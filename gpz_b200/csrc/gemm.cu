@@ -1150,13 +1150,20 @@ struct SgemmBatch {
     int mlim, mstep, k_follows_m;
 };
 
+// TS = 64: 64 x 64 tile per CTA (4 warps x 32 x 32); TS = 32: 32 x 32 tile (4 warps x 16 x 16) for skinny products whose 64-tiles
+// would leave most SMs idle (a CTA is DMMA-bound at TS*TS*16 MACs per K step whatever else happens).
+// KS = K elements per step.  The operands go global -> registers -> shared one step ahead, so every step exposes whatever of the
+// global-load latency its own DMMAs do not cover; with 16 the ncu launch list (profiles/r02z_solve_launches.csv) showed 0.8 us per
+// step for the 32-tile and 2 us per step for K = 64 products -- latency, not arithmetic.  KS = 32 (64-tile) / 64 (32-tile) moves
+// 2-4x the bytes per latency.
+template <int TS, int KS>
 __global__ void __launch_bounds__(128)
 sgemm_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, int64_t sAi, int64_t sAk,
              const double* __restrict__ B, int64_t sBk, int64_t sBj, double beta, double* __restrict__ C, int64_t ldc,
              int lower_only, SgemmBatch bt) {
-    constexpr int TS = 64, LA = KSTEP + 4, LB = TS + 4;
+    constexpr int LA = KS + 4, LB = TS + 4, WT = TS / 2, MI = WT / 8, NQ = TS * KS / 128;
     __shared__ double As[TS][LA];
-    __shared__ double Bs[KSTEP][LB];
+    __shared__ double Bs[KS][LB];
     const int ti = blockIdx.y, tj = blockIdx.x;
     if (lower_only && tj > ti) return;
     if (lower_only == 2 && ti == 0 && tj == 0) return;      // look-ahead Cholesky: the next diagonal block is updated by its own kernel
@@ -1171,69 +1178,69 @@ sgemm_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, in
     C += blockIdx.z * bt.bsC;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int wm0 = (warp >> 1) * 32, wn0 = (warp & 1) * 32;
+    const int wm0 = (warp >> 1) * WT, wn0 = (warp & 1) * WT;
     const int i0 = ti * TS, j0 = tj * TS;
 
-    double acc[4][4][2];
+    double acc[MI][MI][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < MI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     // software pipeline: the next K tile is fetched into registers while the current one is multiplied
     const bool a_kfast = (sAk == 1), b_jfast = (sBj == 1);
-    double ra[8], rb[8];
+    double ra[NQ], rb[NQ];
     auto fetch = [&](int k0) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < NQ; ++q) {
             const int e = tid + q * 128;
             int r, c;
-            if (a_kfast) { r = e / KSTEP; c = e % KSTEP; } else { c = e / TS; r = e % TS; }
+            if (a_kfast) { r = e / KS; c = e % KS; } else { c = e / TS; r = e % TS; }
             const int gi = i0 + r, gk = k0 + c;
             ra[q] = (gi < M && gk < K) ? A[gi * sAi + gk * sAk] : 0.0;
             int rr, cc;
-            if (b_jfast) { rr = e / TS; cc = e % TS; } else { cc = e / KSTEP; rr = e % KSTEP; }
+            if (b_jfast) { rr = e / TS; cc = e % TS; } else { cc = e / KS; rr = e % KS; }
             const int gk2 = k0 + rr, gj = j0 + cc;
             rb[q] = (gk2 < K && gj < N) ? B[gk2 * sBk + gj * sBj] : 0.0;
         }
     };
     auto stash = [&]() {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < NQ; ++q) {
             const int e = tid + q * 128;
             int r, c;
-            if (a_kfast) { r = e / KSTEP; c = e % KSTEP; } else { c = e / TS; r = e % TS; }
+            if (a_kfast) { r = e / KS; c = e % KS; } else { c = e / TS; r = e % TS; }
             As[r][c] = ra[q];
             int rr, cc;
-            if (b_jfast) { rr = e / TS; cc = e % TS; } else { cc = e / KSTEP; rr = e % KSTEP; }
+            if (b_jfast) { rr = e / TS; cc = e % TS; } else { cc = e / KS; rr = e % KS; }
             Bs[rr][cc] = rb[q];
         }
     };
     if (K > 0) fetch(0);
-    for (int k0 = 0; k0 < K; k0 += KSTEP) {
+    for (int k0 = 0; k0 < K; k0 += KS) {
         stash();
         __syncthreads();
-        if (k0 + KSTEP < K) fetch(k0 + KSTEP);
+        if (k0 + KS < K) fetch(k0 + KS);
 #pragma unroll
-        for (int kk = 0; kk < KSTEP / 4; ++kk) {
+        for (int kk = 0; kk < KS / 4; ++kk) {
             const int kc = kk * 4 + t;
-            double bf[4];
+            double bf[MI];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bf[j] = Bs[kc][wn0 + j * 8 + g];
+            for (int j = 0; j < MI; ++j) bf[j] = Bs[kc][wn0 + j * 8 + g];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < MI; ++i) {
                 const double af = As[wm0 + i * 8 + g][kc];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af, bf[j]);
+                for (int j = 0; j < MI; ++j) dmma884(acc[i][j][0], acc[i][j][1], af, bf[j]);
             }
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < MI; ++i) {
         const int gi = i0 + wm0 + i * 8 + g;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < MI; ++j) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int gj = j0 + wn0 + j * 8 + 2 * t + e;
@@ -1250,8 +1257,16 @@ sgemm_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, in
 int sgemm(int M, int N, int K, double alpha, const double* A, int64_t sAi, int64_t sAk, const double* B, int64_t sBk,
           int64_t sBj, double beta, double* C, int64_t ldc, int lower_only, cudaStream_t st, int64_t* launches) {
     if (M <= 0 || N <= 0) return GPZ_OK;
+    // few 64-tiles and a long K: 32-tiles give 4x the CTAs (only without the tile-skipping options, whose tile index means 64)
+    if (!lower_only && K >= 256 && ceil_div(N, 64) * ceil_div(M, 64) <= 64) {
+        dim3 grid32(static_cast<unsigned>(ceil_div(N, 32)), static_cast<unsigned>(ceil_div(M, 32)));
+        sgemm_kernel<32, 64><<<grid32, 128, 0, st>>>(M, N, K, alpha, A, sAi, sAk, B, sBk, sBj, beta, C, ldc, 0, SgemmBatch{0, 0, 0, 0, 0, 0});
+        GPZ_KERNEL_CHECK();
+        ++*launches;
+        return GPZ_OK;
+    }
     dim3 grid(static_cast<unsigned>(ceil_div(N, 64)), static_cast<unsigned>(ceil_div(M, 64)));
-    sgemm_kernel<<<grid, 128, 0, st>>>(M, N, K, alpha, A, sAi, sAk, B, sBk, sBj, beta, C, ldc, lower_only, SgemmBatch{0, 0, 0, 0, 0, 0});
+    sgemm_kernel<64, 32><<<grid, 128, 0, st>>>(M, N, K, alpha, A, sAi, sAk, B, sBk, sBj, beta, C, ldc, lower_only, SgemmBatch{0, 0, 0, 0, 0, 0});
     GPZ_KERNEL_CHECK();
     ++*launches;
     return GPZ_OK;
@@ -1263,8 +1278,8 @@ int sgemm_batched(int M, int N, int K, double alpha, const double* A, int64_t sA
                   int mstep, int k_follows_m, cudaStream_t st, int64_t* launches) {
     if (M <= 0 || N <= 0 || batches <= 0) return GPZ_OK;
     dim3 grid(static_cast<unsigned>(ceil_div(N, 64)), static_cast<unsigned>(ceil_div(M, 64)), static_cast<unsigned>(batches));
-    sgemm_kernel<<<grid, 128, 0, st>>>(M, N, K, alpha, A, sAi, sAk, B, sBk, sBj, beta, C, ldc, 0,
-                                       SgemmBatch{bsA, bsB, bsC, mlim, mstep, k_follows_m});
+    sgemm_kernel<64, 32><<<grid, 128, 0, st>>>(M, N, K, alpha, A, sAi, sAk, B, sBk, sBj, beta, C, ldc, 0,
+                                           SgemmBatch{bsA, bsB, bsC, mlim, mstep, k_follows_m});
     GPZ_KERNEL_CHECK();
     ++*launches;
     return GPZ_OK;

@@ -139,6 +139,11 @@ struct SolveWs {
     cudaStream_t side = nullptr;
     cudaEvent_t evP[MAXBLK] = {};
     cudaEvent_t evT[MAXBLK] = {};
+    // incremental inverse (solve_lookahead = 2): a third chain builds L^-1 and Sinv = W'W block row by block row behind the factorisation
+    cudaStream_t inv = nullptr, acc = nullptr;   // block rows of W; their rank-64 updates of Sinv
+    cudaEvent_t evL[MAXBLK] = {};   // panel solve k done: column panel k of L is complete
+    cudaEvent_t evW[MAXBLK] = {};   // block row k of W done
+    cudaEvent_t evF = nullptr, evI = nullptr;   // fork / join of the third chain
 };
 extern int g_solve_lookahead;
 int solve_ws_alloc(SolveWs& ws, int MP);

@@ -12,7 +12,7 @@
 namespace gpz {
 
 constexpr int NB = 64;
-int g_solve_lookahead = 1;      // "solve_lookahead" option (process-wide)
+int g_solve_lookahead = 2;      // "solve_lookahead" option (process-wide): 0 in-stream, 1 look-ahead factorisation, 2 + incremental inverse (default)
 
 // W(o..o+32, o..o+32) = inverse of the lower-triangular 32 x 32 block of A at (o,o); lane = column (forward substitution
 // by rows, no cross-lane traffic: L[r][q] is a broadcast read)
@@ -116,7 +116,8 @@ __device__ __forceinline__ void mm16(double (*Cm)[NB + 1], int ro, int co, doubl
 // update of panel k-2.  L goes to Lout (== S in the in-place form).
 __global__ void __launch_bounds__(256)
 potf2_trti_kernel(const double* __restrict__ S, double* __restrict__ Lout, int64_t ld, int k0, int nb, double* __restrict__ Linv,
-                  const double* __restrict__ LinvPrev, double* __restrict__ logdet, int* __restrict__ flag, int first) {
+                  const double* __restrict__ LinvPrev, double* __restrict__ logdet, int* __restrict__ flag, int first,
+                  double* __restrict__ Wfull) {
     extern __shared__ double sm_potf[];
     double (*A)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm_potf);
     double (*W)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(sm_potf + NB * (NB + 1));
@@ -124,38 +125,66 @@ potf2_trti_kernel(const double* __restrict__ S, double* __restrict__ Lout, int64
     __shared__ int ok_sm;
     __shared__ double ldsh[2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // the three 64 x 64 blocks arrive by cp.async (all 48 copies of a thread in flight at once): as a load -> store loop the
+    // prologue paid one L2 round trip per 256 elements, ~10 us of the kernel (profiles/r02z_solve_launches.csv)
     for (int e = tid; e < NB * NB; e += 256) {
         const int r = e / NB, c = e % NB;
-        A[r][c] = (r < nb && c < nb && c <= r) ? S[static_cast<int64_t>(k0 + r) * ld + k0 + c] : (r == c ? 1.0 : 0.0);
-        W[r][c] = (LinvPrev != nullptr) ? LinvPrev[e] : 0.0;
-        if (LinvPrev != nullptr) T[r][c] = (r < nb) ? S[static_cast<int64_t>(k0 + r) * ld + (k0 - NB) + c] : 0.0;
+        if (r < nb && c < nb && c <= r) cp_async8(&A[r][c], S + static_cast<int64_t>(k0 + r) * ld + k0 + c);
+        else A[r][c] = (r == c) ? 1.0 : 0.0;
+        if (LinvPrev != nullptr) {
+            cp_async8(&W[r][c], LinvPrev + e);
+            if (r < nb) cp_async8(&T[r][c], S + static_cast<int64_t>(k0 + r) * ld + (k0 - NB) + c);
+            else T[r][c] = 0.0;
+        } else {
+            W[r][c] = 0.0;
+        }
     }
+    cp_async_commit();
     if (tid == 0) ok_sm = 1;
+    cp_async_wait<0>();
     __syncthreads();
     if (LinvPrev != nullptr) {
-        // L_{k,k-1}[r][c] = sum_{q<=c} A_{k,k-1}[r][q] Linv_{k-1}[c][q]; thread: row r = tid / 4, columns c = tid % 4 + 4 j
-        double lrow[NB / 4];
-        const int r = tid >> 2;
+        // Both 64 x 64 x 64 products on the DMMA pipe (8 warps x 8 rows x 64 columns each): as scalar FMA loops on 256 threads
+        // they cost ~18 us of the kernel's ~50, as much as the look-ahead saves by not waiting for the panel update.
+        const int g = lane >> 2, t = lane & 3, r0w = warp * 8;
+        {   // L_{k,k-1} = A_{k,k-1} Linv_{k-1}'  (Linv is stored with zeros above its diagonal): rows r0w.. of T, in place
+            double acc[8][2];
 #pragma unroll
-        for (int j = 0; j < NB / 4; ++j) {
-            const int c = (tid & 3) + 4 * j;
-            double s0 = 0.0;
-            for (int q = 0; q <= c; ++q) s0 = fma(T[r][q], W[c][q], s0);
-            lrow[j] = s0;
+            for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0.0;
+#pragma unroll 4
+            for (int kk = 0; kk < NB / 4; ++kk) {
+                const double af = T[r0w + g][4 * kk + t];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dmma884(acc[j][0], acc[j][1], af, W[8 * j + g][4 * kk + t]);
+            }
+            __syncwarp();                      // a warp reads only its own rows of T
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                T[r0w + g][8 * j + 2 * t] = acc[j][0];
+                T[r0w + g][8 * j + 2 * t + 1] = acc[j][1];
+            }
         }
         __syncthreads();
+        {   // A_kk -= L_{k,k-1} L_{k,k-1}'  (lower triangle)
+            double acc[8][2];
 #pragma unroll
-        for (int j = 0; j < NB / 4; ++j) T[r][(tid & 3) + 4 * j] = lrow[j];
-        __syncthreads();
-        for (int e = tid; e < NB * NB; e += 256) {
-            const int i = e / NB, j = e % NB;
-            W[i][j] = 0.0;
-            if (j > i || i >= nb) continue;
-            double s0 = 0.0;
-#pragma unroll 8
-            for (int c = 0; c < NB; ++c) s0 = fma(T[i][c], T[j][c], s0);
-            A[i][j] -= s0;
+            for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0.0;
+#pragma unroll 4
+            for (int kk = 0; kk < NB / 4; ++kk) {
+                const double af = T[r0w + g][4 * kk + t];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dmma884(acc[j][0], acc[j][1], af, T[8 * j + g][4 * kk + t]);
+            }
+            const int row = r0w + g;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int col = 8 * j + 2 * t + e;
+                    if (col <= row && row < nb) A[row][col] -= acc[j][e];
+                }
         }
+        for (int e = tid; e < NB * NB; e += 256) W[e / NB][e % NB] = 0.0;
         __syncthreads();
     }
     for (int jb = 0; jb < NB / SB; ++jb) {
@@ -252,7 +281,9 @@ potf2_trti_kernel(const double* __restrict__ S, double* __restrict__ Lout, int64
     }
     for (int e = tid; e < NB * NB; e += 256) {
         const int r = e / NB, c = e % NB;
-        Linv[e] = (r < nb && c < nb && c <= r) ? W[r][c] : 0.0;
+        const double wv = (r < nb && c < nb && c <= r) ? W[r][c] : 0.0;
+        Linv[e] = wv;
+        if (Wfull != nullptr && r < nb && c < nb) Wfull[static_cast<int64_t>(k0 + r) * ld + k0 + c] = wv;   // diagonal block of L^-1 in place
         if (r < nb && c < nb && c <= r) Lout[static_cast<int64_t>(k0 + r) * ld + k0 + c] = A[r][c];
     }
     if (tid == 0) *logdet = (first ? 0.0 : *logdet) + (ldsh[0] + ldsh[1]);
@@ -264,8 +295,8 @@ __global__ void zero_kernel(double* p, int64_t n) {
 }
 
 // copy the 64x64 inverse diagonal blocks into W
-__global__ void place_diag_kernel(const double* __restrict__ Linv, double* __restrict__ W, int64_t ld, int m) {
-    const int b = blockIdx.x;
+__global__ void place_diag_kernel(const double* __restrict__ Linv, double* __restrict__ W, int64_t ld, int m, int b0) {
+    const int b = b0 + blockIdx.x;
     for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
         const int r = e / NB, c = e % NB;
         const int gr = b * NB + r, gc = b * NB + c;
@@ -282,10 +313,16 @@ int solve_ws_alloc(SolveWs& ws, int MP) {
     // look-ahead factorisation: L is written to its own matrix, the panel GEMMs run on a side stream
     GPZ_CUDA(cudaMalloc(&ws.Lbuf, sizeof(double) * MP * MP));
     GPZ_CUDA(cudaStreamCreateWithFlags(&ws.side, cudaStreamNonBlocking));
+    GPZ_CUDA(cudaStreamCreateWithFlags(&ws.inv, cudaStreamNonBlocking));
+    GPZ_CUDA(cudaStreamCreateWithFlags(&ws.acc, cudaStreamNonBlocking));
     for (int i = 0; i < SolveWs::MAXBLK; ++i) {
         GPZ_CUDA(cudaEventCreateWithFlags(&ws.evP[i], cudaEventDisableTiming));
         GPZ_CUDA(cudaEventCreateWithFlags(&ws.evT[i], cudaEventDisableTiming));
+        GPZ_CUDA(cudaEventCreateWithFlags(&ws.evL[i], cudaEventDisableTiming));
+        GPZ_CUDA(cudaEventCreateWithFlags(&ws.evW[i], cudaEventDisableTiming));
     }
+    GPZ_CUDA(cudaEventCreateWithFlags(&ws.evF, cudaEventDisableTiming));
+    GPZ_CUDA(cudaEventCreateWithFlags(&ws.evI, cudaEventDisableTiming));
     return GPZ_OK;
 }
 
@@ -296,10 +333,16 @@ void solve_ws_free(SolveWs& ws) {
     cudaFree(ws.flag);
     cudaFree(ws.Lbuf);
     if (ws.side) cudaStreamDestroy(ws.side);
+    if (ws.inv) cudaStreamDestroy(ws.inv);
+    if (ws.acc) cudaStreamDestroy(ws.acc);
     for (int i = 0; i < SolveWs::MAXBLK; ++i) {
         if (ws.evP[i]) cudaEventDestroy(ws.evP[i]);
         if (ws.evT[i]) cudaEventDestroy(ws.evT[i]);
+        if (ws.evL[i]) cudaEventDestroy(ws.evL[i]);
+        if (ws.evW[i]) cudaEventDestroy(ws.evW[i]);
     }
+    if (ws.evF) cudaEventDestroy(ws.evF);
+    if (ws.evI) cudaEventDestroy(ws.evI);
     ws = SolveWs();
 }
 
@@ -319,14 +362,27 @@ int spd_inverse(double* S, int m, int MP, double* Sinv, double* d_logdet, SolveW
     //      panel solve k needs diagonal block k.  L is written to ws.Lbuf (the panel solve is out of place so that the next
     //      diagonal kernel can still read A_{k+1,k}), S keeps being updated as the trailing matrix.
     const bool la = g_solve_lookahead && ws.side != nullptr && nblk >= 3 && nblk <= SolveWs::MAXBLK;
+    // Incremental inverse (solve_lookahead = 2): W = L^-1 and Sinv = W'W do not have to wait for the whole factor.  Block row k of W
+    // needs only block row k of L (complete after panel solve k-1), the inverted diagonal block k and the rows of W above it:
+    //     W_k,0:k = -Linv_kk (L_k,0:k W_0:k,0:k),   W_kk = Linv_kk,   Sinv(0:k+1, 0:k+1) += W_k' W_k
+    // so a third chain on ws.inv follows the diagonal chain one step behind, and what is left after the last diagonal block is one
+    // block row (~50 us) instead of the 4-level recursive-doubling inverse plus an m^3 product (~0.3 ms at m = 1000).
+    const bool inc = la && g_solve_lookahead >= 2 && ws.inv != nullptr;
     double* Lm = la ? ws.Lbuf : S;
+    if (inc) {
+        GPZ_CUDA(cudaMemsetAsync(ws.W, 0, sizeof(double) * static_cast<size_t>(MP) * MP, st));   // the diagonal kernels write into it
+        GPZ_CUDA(cudaEventRecord(ws.evF, st));
+        GPZ_CUDA(cudaStreamWaitEvent(ws.inv, ws.evF, 0));
+        GPZ_CUDA(cudaStreamWaitEvent(ws.acc, ws.evF, 0));
+        GPZ_CUDA(cudaMemsetAsync(Sinv, 0, sizeof(double) * static_cast<size_t>(MP) * MP, ws.acc));
+    }
     for (int kb = 0; kb < nblk; ++kb) {
         const int k0 = kb * NB;
         const int nb = (m - k0 < NB) ? (m - k0) : NB;
         double* Lk = ws.Linv + static_cast<int64_t>(kb) * NB * NB;
         if (la && kb >= 2) GPZ_CUDA(cudaStreamWaitEvent(st, ws.evT[kb - 2], 0));
         potf2_trti_kernel<<<1, 256, kPotfSmem, st>>>(S, Lm, ld, k0, nb, Lk, (la && kb > 0) ? Lk - NB * NB : nullptr, d_logdet, ws.flag,
-                                                     kb == 0);
+                                                     kb == 0, inc ? ws.W : nullptr);
         GPZ_KERNEL_CHECK();
         ++*launches;
         const int rem = m - k0 - nb;
@@ -343,11 +399,39 @@ int spd_inverse(double* S, int m, int MP, double* Sinv, double* d_logdet, SolveW
             // L_ik = A_ik * Linv_kk'   (B(k,j) = Linv[j][k])
             rc = sgemm(rem, nb, nb, 1.0, panelA, ld, 1, Lk, 1, NB, 0.0, panelL, ld, 0, sg, launches);
             if (rc) return rc;
+            if (inc) GPZ_CUDA(cudaEventRecord(ws.evL[kb], ws.side));
             // trailing: A_ij -= L_ik L_jk'  (lower tiles only; look-ahead: not the next diagonal block, its kernel does that)
             rc = sgemm(rem, rem, nb, -1.0, panelL, ld, 1, panelL, 1, ld, 1.0, trail, ld, la ? 2 : 1, sg, launches);
             if (rc) return rc;
             if (la) GPZ_CUDA(cudaEventRecord(ws.evT[kb], ws.side));
         }
+        if (inc) {
+            // block row kb of W and its rank-nb contribution to Sinv, on the third chain
+            if (rem <= 0) GPZ_CUDA(cudaEventRecord(ws.evP[kb], st));           // (recorded above when there is a panel below)
+            GPZ_CUDA(cudaStreamWaitEvent(ws.inv, ws.evP[kb], 0));                // Linv_kk
+            if (kb > 0) GPZ_CUDA(cudaStreamWaitEvent(ws.inv, ws.evL[kb - 1], 0));   // L_kb,0:kb
+            double* Wk = ws.W + static_cast<int64_t>(k0) * ld;
+            if (kb > 0) {
+                // T = L_k,0:k0 * W_0:k0,0:k0   (nb x k0)
+                rc = sgemm(nb, k0, k0, 1.0, Lm + static_cast<int64_t>(k0) * ld, ld, 1, ws.W, ld, 1, 0.0, ws.tmp, ld, 0, ws.inv, launches);
+                if (rc) return rc;
+                // W_k,0:k0 = -Linv_kk * T
+                rc = sgemm(nb, k0, nb, -1.0, Lk, NB, 1, ws.tmp, ld, 1, 0.0, Wk, ld, 0, ws.inv, launches);
+                if (rc) return rc;
+            }
+            // Sinv(0:k0+nb, 0:k0+nb) += W_k' W_k :  A(i,q) = W[k0+q][i], B(q,j) = W[k0+q][j]; on its own chain (ws.acc) so that the
+            // next block row of W does not wait for it
+            GPZ_CUDA(cudaEventRecord(ws.evW[kb], ws.inv));
+            GPZ_CUDA(cudaStreamWaitEvent(ws.acc, ws.evW[kb], 0));
+            rc = sgemm(k0 + nb, k0 + nb, nb, 1.0, Wk, 1, ld, Wk, ld, 1, 1.0, Sinv, ld, 0, ws.acc, launches);
+            if (rc) return rc;
+        }
+    }
+    if (inc) {                                       // join the side chains (ws.acc is behind ws.inv by construction); Sinv is complete
+        GPZ_CUDA(cudaStreamWaitEvent(st, ws.evT[nblk - 2], 0));
+        GPZ_CUDA(cudaEventRecord(ws.evI, ws.acc));
+        GPZ_CUDA(cudaStreamWaitEvent(st, ws.evI, 0));
+        return GPZ_OK;
     }
     if (la) {                                        // join: everything the side stream did precedes the inverse below
         const int last = nblk - 2;                   // the last panel with rows below it
@@ -360,7 +444,7 @@ int spd_inverse(double* S, int m, int MP, double* Sinv, double* d_logdet, SolveW
         ws.W, static_cast<int64_t>(MP) * MP);
     GPZ_KERNEL_CHECK();
     ++*launches;
-    place_diag_kernel<<<nblk, 256, 0, st>>>(ws.Linv, ws.W, ld, m);
+    place_diag_kernel<<<nblk, 256, 0, st>>>(ws.Linv, ws.W, ld, m, 0);
     GPZ_KERNEL_CHECK();
     ++*launches;
     for (int b = NB; b < m; b *= 2) {

@@ -208,6 +208,36 @@ def test_predict_matches_oracle(method, psi):
     assert rel(PHI2, PHI) <= 1e-12
 
 
+@pytest.mark.parametrize("m", [200, 300, 470])
+def test_solve_schedules_agree_with_the_oracle(m):
+    """csrc/solve.cu has three schedules of the same blocked Cholesky + inverse (`solve_lookahead` 0: in-stream, 1: look-ahead
+    factorisation on two streams, 2: + W = L^-1 and Sinv = W'W built block row by block row on two more streams).  The fit exit
+    (GPz.m:84-87: w, iSigma_w from inv_logdet.m) must match the oracle under each, at block counts 4, 5 and 8 with a ragged
+    last block, and the process-wide option is restored."""
+    n, d = 4000, 3
+    model, theta, X, Y, _, omega, tr, _ = problem("VD", True, False, False, n=n, d=d, m=m, seed=31)
+    ref = O.GPz(theta, model, X, Y, None, omega, tr, None, fit_only=True)
+    cond = np.linalg.cond(ref.iSigma_w[:, :, 0])
+    bound = min(1e-5, 64 * cond * np.finfo(float).eps)
+    gm = L.make_model(d, 1, m, "VD", True)
+    ctx = L.Context(gm, X, Y, None, omega, tr, None)
+    try:
+        out = {}
+        for mode in (0, 1, 2):
+            ctx.set_option("solve_lookahead", mode)
+            nl, w, iS = ctx.fit(theta)
+            nl2, w2, iS2 = ctx.fit(theta)
+            assert np.array_equal(iS, iS2) and np.array_equal(w, w2)            # each schedule is deterministic
+            assert rel(iS, ref.iSigma_w) <= bound and rel(w, ref.w) <= bound and rel(nl, ref.nlogML) <= bound, \
+                (mode, rel(iS, ref.iSigma_w), rel(w, ref.w), bound)
+            assert rel(iS, iS.transpose(1, 0, 2)) <= bound
+            out[mode] = iS
+        assert rel(out[2], out[0]) <= bound and rel(out[1], out[0]) <= bound
+    finally:
+        ctx.set_option("solve_lookahead", 2)
+        ctx.close()
+
+
 @pytest.mark.parametrize("method", ["VD", "VC"])
 def test_pairwise_predict_reads_the_lower_triangle_of_iSigma_w(method):
     """predictDiag.m:113 / :193 / :279 and predictCov.m:119 / :209 / :313 read iSigma_w(i,j,:) with j <= i only.  The stored
