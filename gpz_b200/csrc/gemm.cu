@@ -663,7 +663,7 @@ phi_persist_kernel(const __grid_constant__ CUtensorMap mapF, const PhiPersist a)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Staggered form of the kernel above (g_phi_persist == 2; NOT the default: measured 7 % slower, see the end of this comment).  ncu on phi_persist_kernel (profiles/r02z_aux.md): DMMA
+// Staggered form of the kernel above (g_phi_persist == 2, the default).  ncu on phi_persist_kernel (profiles/r02z_aux.md): DMMA
 // pipe 58 % active, FP64 pipe 12 %, top stall math-pipe throttle -- the CTA-wide barrier at the end of every row tile keeps
 // all 16 warps in phase, so the DMMA pipe is saturated during the K loops and idle during the exp/store epilogues.  Here no
 // barrier spans the CTA inside the tile loop:
@@ -673,10 +673,12 @@ phi_persist_kernel(const __grid_constant__ CUtensorMap mapF, const PhiPersist a)
 //     thread 0 after ITS K loop, one tile ahead;
 //   * the row-dot partials of the 4 N-warps of an M-group are combined behind a 128-thread named barrier, double-buffered.
 // Same arithmetic in the same order: bit-identical to phi_persist_kernel and tgemm_kernel<1>.
-// Measured (profiles/r02z_stagger_ab2.log, interleaved A/B on one box): 8.42 ms against 7.85 ms for the CTA-synchronous kernel at
-// the headline shape, 2.10 against 2.08 ms at config 3.  The exp/store warps do not fill the DMMA pipe's idle time: while other
-// warps of the sub-partition stream DMMAs, DFMA issue starves (the same behaviour the tcgen05 kernel shows), so the
-// phases serialise either way and the extra barriers only cost.  Kept as an option for that record.
+// Measured, interleaved A/B on one box each (profiles/r02z_stagger_ab*.log, r02z_digits.log).  With the per-element exp epilogue
+// this variant was SLOWER (8.42 vs 7.85 ms at the headline shape): the exp/store warps do not fill the DMMA pipe's idle time,
+// because DFMA issue starves while other warps of the sub-partition stream DMMAs (the tcgen05 kernel shows the same),
+// so the phases serialise whatever the warp schedule and the extra barriers only cost.  With the grouped epilogue (phi_epilogue)
+// the two are level at the headline shape (7.55 vs 7.72, 7.53 vs 7.37 ms on two boxes) and this one is ~5 % ahead at config 3
+// (1.94 vs 2.04 ms), where the epilogue is the larger share -- hence the default.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pp_mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
