@@ -22,111 +22,113 @@ constexpr int GC_BP_WARPS = 12;      // warps per SM of gc_rows_backproj_kernel 
 int gc_feature_width(int d) { return static_cast<int>(round_up(1 + d + d * (d + 1) / 2, 32)); }
 static int gc_gwidth(int d) { return static_cast<int>(round_up(gc_feature_width(d), TILE)); }      // N of the row-tile GEMM dPHI G
 
-// warp per row: S = Psi_i + Sigma is factored in shared memory (lane = matrix row), L is inverted in place (lane = column),
-// M = L^-T L^-1 is formed column by column in registers, then the features are written.  One d x d array per warp.
+// warp per row, everything in registers: lane r holds row r of S = Psi_i + Sigma (lower triangle), the Cholesky factor is formed
+// right-looking with the pivot and the column moving by shuffles (no division: the pivot's reciprocal square root also scales
+// the inverse), then lane b builds column b of W = L^-1 by forward substitution (L_rq broadcast from lane r), column b of
+// M = W'W, z_b = (M x)_b, and the features are written.  The first form of this kernel kept S in shared memory with three warp
+// barriers per column and a division, a square root and a log per pivot: ~10 ms for 250 000 rows at d = 32
+// (profiles/r02u_cfg5_launches_partial.md).  ln|S| comes from the running product of the pivots (mantissa and exponent kept
+// apart, one log per row).  Dims >= d are padded with the identity.
 template <int DMAX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 gc_features_kernel(Params P, const double* __restrict__ X, const double* __restrict__ Psi, int64_t n, int64_t r0, int64_t r1, int KQ,
                    double* __restrict__ F) {
-    extern __shared__ double gcf_sm[];
+    extern __shared__ double gcf_sm[];                     // Sigma of basis 0 (GC shares it): [DMAX][DMAX + 1]
     constexpr int LD = DMAX + 1;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int d = P.d, MP = P.MP;
-    double* S = gcf_sm + static_cast<int64_t>(warp) * (DMAX * LD + 2 * DMAX);
-    double* xs = S + DMAX * LD;
-    double* zs = xs + DMAX;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int d = P.d, MP = P.MP, r = lane;
+    for (int e = threadIdx.x; e < DMAX * DMAX; e += blockDim.x) {
+        const int a = e / DMAX, b = e - a * DMAX;
+        gcf_sm[a * LD + b] = (a < d && b < d) ? P.Sj[(static_cast<int64_t>(a) * d + b) * MP] : 0.0;
+    }
+    __syncthreads();
     const int nv = d * (d + 1) / 2;
-    for (int64_t i = r0 + static_cast<int64_t>(blockIdx.x) * 8 + warp; i < r1; i += static_cast<int64_t>(gridDim.x) * 8) {
+    const double half_lndS = 0.5 * P.lndS[0];
+    for (int64_t i = r0 + static_cast<int64_t>(blockIdx.x) * wpb + warp; i < r1; i += static_cast<int64_t>(gridDim.x) * wpb) {
         const double* psi = Psi + i * d * d;
-        __syncwarp();
-        for (int e = lane; e < d * d; e += 32) {
-            const int a = e / d, b = e - a * d;
-            S[a * LD + b] = psi[a + b * d] + P.Sj[(static_cast<int64_t>(a) * d + b) * MP];      // basis 0: GC shares Sigma
-        }
-        if (lane < d) xs[lane] = X[lane * n + i];
-        __syncwarp();
-        // Cholesky, lower, in place: lane = row
-        double hl = 0.0;
-        bool ok = true;
-        for (int c = 0; c < d; ++c) {
-            const double piv = S[c * LD + c];
-            if (!(piv > 0.0)) {
-                ok = false;
-                break;
-            }
-            const double l = sqrt(piv), il = 1.0 / l;
-            hl += log(l);
-            __syncwarp();
-            if (lane == c) S[c * LD + c] = l;
-            else if (lane > c && lane < d) S[lane * LD + c] *= il;
-            __syncwarp();
-            if (lane > c && lane < d) {
-                const double arc = S[lane * LD + c];
-                for (int q = c + 1; q <= lane; ++q) S[lane * LD + q] -= arc * S[q * LD + c];
-            }
-            __syncwarp();
-        }
         double* f = F + (i - r0) * KQ;
-        if (!ok) {
+        double a[DMAX];
+#pragma unroll
+        for (int q = 0; q < DMAX; ++q)
+            a[q] = (r < d && q <= r) ? psi[r + q * d] + gcf_sm[r * LD + q] : ((q == r) ? 1.0 : 0.0);
+        const double xv = (r < d) ? X[r * n + i] : 0.0;
+        // ---- Cholesky (lower), lane = row
+        double pm = 1.0, ilself = 0.0;
+        int pe = 0;
+        bool ok = true;
+#pragma unroll
+        for (int c = 0; c < DMAX; ++c) {
+            const double piv = __shfl_sync(FULL, a[c], c);
+            if (c < d) {
+                if (!(piv >= 2.2250738585072014e-308) || !(piv < 1.7e308)) ok = false;
+                const int ph = __double2hiint(piv);                                   // piv = mant * 2^ex, mant in [1, 2)
+                pe += ((ph >> 20) & 0x7ff) - 1023;
+                pm *= __hiloint2double((ph & 0x800fffff) | 0x3ff00000, __double2loint(piv));
+                const int mh = __double2hiint(pm);                                    // pm back into [1, 2)
+                pe += ((mh >> 20) & 0x7ff) - 1023;
+                pm = __hiloint2double((mh & 0x800fffff) | 0x3ff00000, __double2loint(pm));
+            }
+            const double rs = rsqrt(piv);
+            const double mine = (r == c) ? piv * rs : a[c] * rs;                      // L[r][c]
+            a[c] = mine;
+            if (r == c) ilself = rs;                                                  // 1 / L[r][r]
+#pragma unroll
+            for (int q = c + 1; q < DMAX; ++q) {
+                const double bq = __shfl_sync(FULL, mine, q);                         // L[q][c]
+                a[q] = fma(-mine, bq, a[q]);
+            }
+        }
+        if (!ok) {                                                                    // uniform: every lane saw the same pivots
             for (int c = lane; c < KQ; c += 32) f[c] = nan("");
             continue;
         }
-        // W = L^-1 in place (lower): lane = column c, forward substitution down the rows; the column is kept in registers until
-        // every lane has finished reading L
-        double col[DMAX];
+        // ---- W = L^-1, lane = column b: x[rr] = W[rr][b]
+        double x[DMAX];
 #pragma unroll
-        for (int r = 0; r < DMAX; ++r) {
-            double sacc = (r == lane) ? 1.0 : 0.0;
-            if (r < d && lane < d && r >= lane) {
+        for (int rr = 0; rr < DMAX; ++rr) {
+            double sacc = (rr == r) ? 1.0 : 0.0;
 #pragma unroll
-                for (int q = 0; q < DMAX; ++q)
-                    if (q < r && q >= lane) sacc -= S[r * LD + q] * col[q];
-                col[r] = sacc / S[r * LD + r];
-            } else {
-                col[r] = 0.0;
+            for (int q = 0; q < rr; ++q) {
+                const double lrq = __shfl_sync(FULL, a[q], rr);                       // L[rr][q]
+                sacc = fma(-lrq, x[q], sacc);
             }
+            const double ilr = __shfl_sync(FULL, ilself, rr);
+            x[rr] = (rr >= r) ? sacc * ilr : 0.0;
         }
-        __syncwarp();
-        if (lane < d) {
+        // ---- M = W'W, lane = column b: mcol[aa] = M[aa][b] = sum_{c >= aa} W[c][aa] W[c][b]
+        double mcol[DMAX];
 #pragma unroll
-            for (int r = 0; r < DMAX; ++r)
-                if (r < d && r >= lane) S[r * LD + lane] = col[r];
-        }
-        __syncwarp();
-        // M[a][b] = sum_{c >= max(a,b)} W[c][a] W[c][b]: lane = b, all a <= b in registers, then stored in the upper triangle
-#pragma unroll
-        for (int a = 0; a < DMAX; ++a) {
+        for (int aa = 0; aa < DMAX; ++aa) {
             double sacc = 0.0;
-            if (a < d && lane < d && a <= lane)
-                for (int c = lane; c < d; ++c) sacc += S[c * LD + a] * S[c * LD + lane];
-            col[a] = sacc;
-        }
-        __syncwarp();
-        if (lane < d) {
 #pragma unroll
-            for (int a = 0; a < DMAX; ++a)
-                if (a <= lane && a < d) S[a * LD + lane] = col[a];               // upper triangle incl. diagonal now holds M
-        }
-        __syncwarp();
-        // z = M x (lane = a), q = x' z
-        double z = 0.0;
-        if (lane < d)
-            for (int b = 0; b < d; ++b) z += (b >= lane ? S[lane * LD + b] : S[b * LD + lane]) * xs[b];
-        double q = (lane < d) ? z * xs[lane] : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-        if (lane < d) f[1 + lane] = z;
-        if (lane == 0) f[0] = -0.5 * q + 0.5 * P.lndS[0] - hl;
-        for (int e = lane; e < KQ - 1 - d; e += 32) {
-            double v = 0.0;
-            if (e < nv) {
-                int a = 0, rem = e;
-                while (rem >= d - a) { rem -= d - a; ++a; }
-                v = S[a * LD + a + rem];
+            for (int c = aa; c < DMAX; ++c) {
+                const double wca = __shfl_sync(FULL, x[c], aa);
+                sacc = fma(wca, x[c], sacc);
             }
-            f[1 + d + e] = v;
+            mcol[aa] = sacc;
         }
-        (void)zs;
+        // ---- z = M x (M symmetric: z_b = sum_a M[a][b] x_a), q = x'z
+        double z = 0.0;
+#pragma unroll
+        for (int aa = 0; aa < DMAX; ++aa) {
+            const double xa = __shfl_sync(FULL, xv, aa);
+            z = fma(mcol[aa], xa, z);
+        }
+        double qv = (r < d) ? z * xv : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) qv += __shfl_xor_sync(FULL, qv, o);
+        if (r < d) f[1 + r] = z;
+        if (lane == 0) f[0] = -0.5 * qv + half_lndS - 0.5 * (log(pm) + pe * 0.69314718055994530942);
+        int off = 0;                                       // packed upper triangle: row aa, columns aa .. d-1
+#pragma unroll
+        for (int aa = 0; aa < DMAX; ++aa) {
+            if (aa < d) {
+                if (r >= aa && r < d) f[1 + d + off + r - aa] = mcol[aa];
+                off += d - aa;
+            }
+        }
+        for (int e = nv + lane; e < KQ - 1 - d; e += 32) f[1 + d + e] = 0.0;
     }
 }
 
@@ -168,20 +170,12 @@ int gc_features(const Params& P, const RowData& R, int64_t r0, int64_t r1, cudaS
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    const int64_t want = ceil_div(rows, 8);
-    const unsigned nb = static_cast<unsigned>(want < 3LL * sms ? want : 3LL * sms);
-    if (P.d <= 8) {
-        gc_features_kernel<8><<<nb, 256, sizeof(double) * 8 * (8 * 9 + 16), st>>>(P, R.X, R.Psi, R.n, r0, r1, KQ, R.gcF);
-    } else if (P.d <= 16) {
-        gc_features_kernel<16><<<nb, 256, sizeof(double) * 8 * (16 * 17 + 32), st>>>(P, R.X, R.Psi, R.n, r0, r1, KQ, R.gcF);
-    } else {
-        const size_t smem = sizeof(double) * 8 * (32 * 33 + 64);
-        static PerDeviceOnce once;
-        if (once.need()) {
-            GPZ_CUDA(cudaFuncSetAttribute(gc_features_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        }
-        gc_features_kernel<32><<<nb, 256, smem, st>>>(P, R.X, R.Psi, R.n, r0, r1, KQ, R.gcF);
-    }
+    const int64_t want = ceil_div(rows, 4);
+    const unsigned nb = static_cast<unsigned>(want < 4LL * sms ? want : 4LL * sms);
+    if (P.d <= 8) gc_features_kernel<8><<<nb, 128, sizeof(double) * 8 * 9, st>>>(P, R.X, R.Psi, R.n, r0, r1, KQ, R.gcF);
+    else if (P.d <= 16) gc_features_kernel<16><<<nb, 128, sizeof(double) * 16 * 17, st>>>(P, R.X, R.Psi, R.n, r0, r1, KQ, R.gcF);
+    else gc_features_kernel<32><<<nb, 128, sizeof(double) * 32 * 33, st>>>(P, R.X, R.Psi, R.n, r0, r1, KQ, R.gcF);
+    GPZ_KERNEL_CHECK();
     gc_basis_kernel<<<static_cast<unsigned>(ceil_div(P.MP, 128)), 128, 0, st>>>(P, KQ, gc_gwidth(P.d), R.gcW, R.gcG);
     GPZ_KERNEL_CHECK();
     *launches += 2;
@@ -208,6 +202,7 @@ gc_rows_backproj_kernel(int d, int KQ, int KN, int64_t rows, const double* __res
     for (int a = 0; a < DMAX; ++a) acc[a] = 0.0;
     double ssum = 0.0;
     const int nv = d * (d + 1) / 2;
+    for (int e = lane; e < 2 * DMAX * DMAX; e += 32) Ms[e] = 0.0;      // M and V: rows / columns >= d stay zero (the products run to DMAX)
     for (int64_t i = gw; i < rows; i += nw) {
         const double* f = F + i * KQ;
         const double* g = G1 + i * KN;
@@ -226,13 +221,29 @@ gc_rows_backproj_kernel(int d, int KQ, int KN, int64_t rows, const double* __res
         }
         const double ai = g[0];
         __syncwarp();
+        // Both d x d x d products keep the lane's operand COLUMN in registers and read the other operand as warp-wide broadcasts
+        // (two values per 16-byte load): one shared-memory instruction per two FMAs.  The first form read both operands from
+        // shared memory for every FMA -- 4 096 LDS.64 per row, i.e. 1 MB of shared-memory traffic per row, which is what bounded
+        // the kernel (10.9 ms for 250 000 rows at d = 32, profiles/r02u_cfg5_launches_partial.md).
         double tcol[DMAX];
         double yb = 0.0;
         if (lane < d) {
+            double vcol[DMAX];
+#pragma unroll
+            for (int c = 0; c < DMAX; ++c) vcol[c] = (c < d) ? Vs[c * DMAX + lane] : 0.0;
             for (int c = 0; c < d; ++c) yb += Ms[lane * DMAX + c] * us[c];          // y_b, b = lane
-            for (int a = 0; a < d; ++a) {                                            // T[a][b] = sum_c M[a][c] V[c][b]
+#pragma unroll 2
+            for (int a = 0; a < DMAX; ++a) {                                         // T[a][b] = sum_c M[a][c] V[c][b]
                 double s = 0.0;
-                for (int c = 0; c < d; ++c) s += Ms[a * DMAX + c] * Vs[c * DMAX + lane];
+                if (a < d) {
+                    const double2* mrow = reinterpret_cast<const double2*>(Ms + a * DMAX);
+#pragma unroll
+                    for (int c2 = 0; c2 < DMAX / 2; ++c2) {
+                        const double2 mv = mrow[c2];                                 // broadcast; columns >= d of M are 0
+                        s = fma(mv.x, vcol[2 * c2], s);
+                        s = fma(mv.y, vcol[2 * c2 + 1], s);
+                    }
+                }
                 tcol[a] = s;
             }
         }
@@ -245,10 +256,22 @@ gc_rows_backproj_kernel(int d, int KQ, int KN, int64_t rows, const double* __res
         __syncwarp();
         if (lane < d) {
             const double zb = zs[lane];
-            for (int a = 0; a < d; ++a) {
-                double r = 0.0;
-                for (int c = 0; c < d; ++c) r += Vs[a * DMAX + c] * Ms[c * DMAX + lane];     // (T M)[a][b]
-                acc[a] += ai * zs[a] * zb - zs[a] * yb - us[a] * zb + r - ai * Ms[a * DMAX + lane];
+            double mcol[DMAX];
+#pragma unroll
+            for (int c = 0; c < DMAX; ++c) mcol[c] = (c < d) ? Ms[c * DMAX + lane] : 0.0;
+#pragma unroll 2
+            for (int a = 0; a < DMAX; ++a) {
+                if (a < d) {
+                    double r = 0.0;
+                    const double2* trow = reinterpret_cast<const double2*>(Vs + a * DMAX);
+#pragma unroll
+                    for (int c2 = 0; c2 < DMAX / 2; ++c2) {
+                        const double2 tv = trow[c2];                                 // (T M)[a][b]; columns >= d of T are 0
+                        r = fma(tv.x, mcol[2 * c2], r);
+                        r = fma(tv.y, mcol[2 * c2 + 1], r);
+                    }
+                    acc[a] += ai * zs[a] * zb - zs[a] * yb - us[a] * zb + r - ai * mcol[a];
+                }
             }
         }
         ssum += ai;
