@@ -24,7 +24,13 @@ __global__ void prep_kernel(const double* __restrict__ th, Params P, int need_si
     const bool live = j < m;
     const double* thG = th + P.oG;
     // centres are stored relative to the dataset shift (X was shifted by the same constant at upload)
-    for (int a = 0; a < d; ++a) P.Pt[a * MP + j] = live ? th[a * m + j] - P.xshift[a] : 0.0;
+    // the centre is also kept locally (covariance modes: d <= 32) or recomputed (diagonal modes: any d) instead of read back
+    double pl[32];
+    for (int a = 0; a < d; ++a) {
+        const double pa = live ? th[a * m + j] - P.xshift[a] : 0.0;
+        if (a < 32) pl[a] = pa;
+        P.Pt[a * MP + j] = pa;
+    }
     if (!mode_is_cov(P.mode)) {
         for (int a = 0; a < d; ++a) {
             double gv = 0.0;
@@ -37,7 +43,7 @@ __global__ void prep_kernel(const double* __restrict__ th, Params P, int need_si
                 }
             }
             P.Gt[a * MP + j] = gv;
-            const double pa = P.Pt[a * MP + j];
+            const double pa = live ? th[a * m + j] - P.xshift[a] : 0.0;
             P.Ct[a * MP + j] = live ? gv * pa : 0.0;
             if (P.Wc != nullptr) {          // lnPHI = sum_a [ -1/2 g^2 x^2 + g^2 p x - 1/2 g^2 p^2 ]
                 P.Wc[static_cast<int64_t>(1 + a) * MP + j] = live ? gv * gv * pa : 0.0;
@@ -47,7 +53,16 @@ __global__ void prep_kernel(const double* __restrict__ th, Params P, int need_si
         if (P.Wc != nullptr) {
             double c0 = 0.0;
             for (int a = 0; a < d; ++a) {
-                const double gp = P.Ct[a * MP + j];
+                double gv = 0.0;
+                if (live) {
+                    switch (P.mode) {
+                        case GL: gv = thG[0]; break;
+                        case VL: gv = thG[j]; break;
+                        case GD: gv = thG[a]; break;
+                        default: gv = thG[a * m + j]; break;
+                    }
+                }
+                const double gp = live ? gv * (th[a * m + j] - P.xshift[a]) : 0.0;      // = P.Ct[a * MP + j], recomputed instead of read back
                 c0 = fma(gp, gp, c0);
             }
             P.Wc[j] = live ? -0.5 * c0 : 0.0;
@@ -60,7 +75,7 @@ __global__ void prep_kernel(const double* __restrict__ th, Params P, int need_si
             for (int a = 0; a < dp; ++a) {
                 const double gv = (live && a < d) ? G[b + a * d] : 0.0;
                 P.Gam[(static_cast<int64_t>(b) * dp + a) * MP + j] = gv;
-                if (live && a < d) c += gv * P.Pt[a * MP + j];
+                if (live && a < d) c += gv * pl[a];
             }
             P.Ct[b * MP + j] = c;
         }
@@ -137,7 +152,11 @@ prep_patterns_kernel(Params P) {
             for (int c = 0; c < nu; ++c) s += Um(r, c) * P.Aj[(static_cast<int64_t>(ui[c]) * d + b) * MP + j];
             Gg[(static_cast<int64_t>(ui[r]) * d + b) * MP + j] = ok ? s : nan("");
         }
-    // M(a,b) = A(a,b) - sum_{e in u} A(a,e) G(e,b)   for a,b in o
+    // M(a,b) = A(a,b) - sum_{e in u} A(a,e) G(e,b)   for a,b in o.  A copy stays in thread-local memory for the two uses below
+    // instead of being read back from global memory.  (The kernel is one thread per basis with O(d^3) dependent work, i.e.
+    // latency-bound at ~85 us for m = 1000, d = 10 whatever the memory path: profiles/r02z_prep.csv, r02z7_prep.csv.  Only the
+    // 8-GPU step notices it; a warp per basis is the next step there.)
+    double Ml[DMAX * DMAX];
     for (int a = 0; a < d; ++a)
         for (int b = 0; b < d; ++b) {
             double v = 0.0;
@@ -146,6 +165,7 @@ prep_patterns_kernel(Params P) {
                 for (int r = 0; r < nu; ++r)
                     v -= P.Aj[(static_cast<int64_t>(a) * d + ui[r]) * MP + j] * Gg[(static_cast<int64_t>(ui[r]) * d + b) * MP + j];
             }
+            Ml[a * d + b] = v;
             Mg[(static_cast<int64_t>(a) * d + b) * MP + j] = v;
         }
     {   // ln det M over the observed block (for the normalised densities N)
@@ -155,7 +175,7 @@ prep_patterns_kernel(Params P) {
             if (ob[a]) oi[no++] = a;
         LocalMat Om{U, no};
         for (int r = 0; r < no; ++r)
-            for (int c = 0; c <= r; ++c) Om(r, c) = Mg[(static_cast<int64_t>(oi[r]) * d + oi[c]) * MP + j];
+            for (int c = 0; c <= r; ++c) Om(r, c) = Ml[oi[r] * d + oi[c]];
         double hm = 0.0;
         const bool okm = no == 0 || chol_lower(Om, no, &hm);
         P.lndM[static_cast<int64_t>(g) * MP + j] = okm ? 2.0 * hm : nan("");
@@ -163,13 +183,15 @@ prep_patterns_kernel(Params P) {
     if (Wg == nullptr) return;
     double c0 = 0.0;
     int idx = 1 + d;
+    double pl[DMAX];
+    for (int a = 0; a < d; ++a) pl[a] = P.Pt[a * MP + j];
     for (int a = 0; a < d; ++a) {
         double bv = 0.0;
-        for (int b = 0; b < d; ++b) bv += Mg[(static_cast<int64_t>(a) * d + b) * MP + j] * P.Pt[b * MP + j];
-        c0 += bv * P.Pt[a * MP + j];
+        for (int b = 0; b < d; ++b) bv += Ml[a * d + b] * pl[b];
+        c0 += bv * pl[a];
         Wg[static_cast<int64_t>(1 + a) * MP + j] = bv;
         for (int b = a; b < d; ++b, ++idx) {
-            const double av = Mg[(static_cast<int64_t>(a) * d + b) * MP + j];
+            const double av = Ml[a * d + b];
             Wg[static_cast<int64_t>(idx) * MP + j] = (a == b) ? -0.5 * av : -av;
         }
     }
