@@ -72,3 +72,118 @@ def test_predict_noisy_cov_against_40_digit_arithmetic():
     assert rel(mu[0, 0], mu_x) <= 1e-12
     assert rel(nu[0, 0], nu_x) <= 1e-10, (float(nu_x), nu[0, 0], amp)
     assert abs(float(mp.mpf(float(ga[0, 0])) - ga_x)) <= 1e-12 * max(1.0, float(mu_x) ** 2)
+
+
+def _mp_nlogml(theta, meth, X, Y, omega, m, d, Psi=None):
+    """GPz.m:20-110,233 restated in 40-digit arithmetic for k = 1, heteroscedastic, no Psi, no NaN; theta holds mp numbers.
+    Only the OBJECTIVE: the gradient below comes from differencing it, which makes the check independent of the oracle's
+    (and the CUDA path's) hand-derived gradient code."""
+    n = X.shape[0]
+    md = m * d
+    P = [[theta[a * m + j] for a in range(d)] for j in range(m)]                       # P = reshape(theta(1:m*d), m, d)
+    if meth == "VC":
+        g_dim = d * d * m
+        Gam = [[[theta[md + b + a * d + j * d * d] for a in range(d)] for b in range(d)] for j in range(m)]   # Gamma(b, a, j)
+    else:                                                                              # VD: Gamma = reshape(., m, d)
+        g_dim = md
+        Gam = [[theta[md + j + a * m] for a in range(d)] for j in range(m)]
+    o = md + g_dim
+    lnA = theta[o:o + m]
+    b = theta[o + m]
+    v = theta[o + m + 1:o + m + 1 + m]
+    lnT = theta[o + m + 1 + m:o + m + 1 + 2 * m]
+    PHI = [[None] * m for _ in range(n)]
+    Sig = None
+    if Psi is not None and meth == "VC":                                               # Sigma_j = (Gamma_j' Gamma_j)^-1, getPHI.m:73
+        Sig = []
+        for j in range(m):
+            G = mp.matrix(Gam[j])
+            Sig.append(mp.inverse(G.T * G))
+    for i in range(n):
+        for j in range(m):
+            obs = [a for a in range(d) if not np.isnan(X[i, a])]
+            if len(obs) < d:                                                           # missing inputs (no Psi): getPHI.m:76 / :96
+                nmiss = d - len(obs)
+                if meth == "VC":
+                    if Sig is None:
+                        Sig = [None] * m
+                    if Sig[j] is None:
+                        G = mp.matrix(Gam[j])
+                        Sig[j] = mp.inverse(G.T * G)
+                    Soo = mp.matrix([[Sig[j][a, c] for c in obs] for a in obs])
+                    dv = mp.matrix([[mp.mpf(float(X[i, a])) - P[j][a] for a in obs]])
+                    e = -(dv * mp.inverse(Soo) * dv.T)[0] / 2
+                else:
+                    e = -sum(((mp.mpf(float(X[i, a])) - P[j][a]) * Gam[j][a]) ** 2 for a in obs) / 2
+                PHI[i][j] = mp.exp(e - mp.mpf(nmiss) * mp.log(2) / 2)
+                continue
+            dl = [mp.mpf(float(X[i, a])) - P[j][a] for a in range(d)]
+            if Psi is None:
+                if meth == "VC":                                                       # getPHI.m:73-77 without NaN: -1/2 |Gamma_j dl|^2
+                    q = sum(sum(Gam[j][bb][a] * dl[a] for a in range(d)) ** 2 for bb in range(d))
+                else:                                                                  # getPHI.m:93-98
+                    q = sum((dl[a] * Gam[j][a]) ** 2 for a in range(d))
+                PHI[i][j] = mp.exp(-q / 2)
+            elif meth == "VC":                                                         # getPHI.m:80-88: S = Psi_i + Sigma_j
+                Sm = Sig[j] + mp.matrix(np.asarray(Psi[:, :, i], dtype=np.float64).tolist())
+                dv = mp.matrix([dl])
+                PHI[i][j] = mp.exp(-(dv * mp.inverse(Sm) * dv.T)[0] / 2 + mp.log(mp.det(Sig[j])) / 2 - mp.log(mp.det(Sm)) / 2)
+            else:                                                                      # getPHI.m:102-105: Sigma_ja = Gamma_ja^-2
+                e = mp.mpf(0)
+                for a in range(d):
+                    sg = 1 / Gam[j][a] ** 2
+                    ps = mp.mpf(float(Psi[i, a]))
+                    e += -dl[a] ** 2 / (ps + sg) / 2 - mp.log(1 + ps / sg) / 2
+                PHI[i][j] = mp.exp(e)
+    lnBi = [b + sum(PHI[i][j] * v[j] for j in range(m)) for i in range(n)]             # getPHI.m:116-125
+    beta = [mp.exp(-t) for t in lnBi]
+    wb = [beta[i] * mp.mpf(float(omega[i])) for i in range(n)]
+    alpha = [mp.exp(t) for t in lnA]
+    S = mp.matrix(m, m)
+    r = mp.matrix(m, 1)
+    for a in range(m):
+        for c in range(m):
+            S[a, c] = sum(wb[i] * PHI[i][a] * PHI[i][c] for i in range(n)) + (alpha[a] if a == c else 0)   # GPz.m:65
+        r[a] = sum(wb[i] * PHI[i][a] * mp.mpf(float(Y[i])) for i in range(n))
+    w = mp.lu_solve(S, r)                                                              # :70
+    logdet = mp.log(mp.det(S))
+    delta = [sum(PHI[i][j] * w[j] for j in range(m)) - mp.mpf(float(Y[i])) for i in range(n)]
+    tau = [mp.exp(t) for t in lnT]
+    nl = -sum(wb[i] * delta[i] ** 2 for i in range(n)) / 2 - sum(alpha[j] * w[j] ** 2 for j in range(m)) / 2 \
+        + sum(lnA) / 2 - logdet / 2 - sum(lnBi[i] * mp.mpf(float(omega[i])) for i in range(n)) / 2            # :80-82
+    nl += -sum(v[j] ** 2 * tau[j] for j in range(m)) / 2 + sum(lnT) / 2 - mp.mpf(m) * mp.log(2 * mp.pi) / 2   # :103
+    nl -= mp.log(2 * mp.pi) * sum(mp.mpf(float(t)) for t in omega) / 2                                        # :110
+    return -nl / n                                                                                            # :233
+
+
+@pytest.mark.parametrize("meth,psi,nan", [("VC", False, False), ("VD", False, False), ("VC", True, False), ("VD", True, False),
+                                          ("VC", False, True), ("VD", False, True)])
+def test_oracle_objective_and_gradient_against_40_digit_differences(meth, psi, nan):
+    """The oracle's nlogML and its analytic gradient (GPz.m:113-234 restated) against the 40-digit objective and its central
+    differences (h = 1e-15: truncation 1e-30).  fp64 finite differences (the T1 identity tests) cannot see below ~1e-6."""
+    from gpz_b200 import synth
+    n, d, m = 36, 2, 5
+    X, Y = synth.make_data(n, d, seed=11)
+    X, Y = np.array(X), np.asarray(Y)
+    theta = synth.perturb_theta(synth.make_theta0(X, Y, meth, m, het=True, seed=12), 0.2, 13)
+    omega = 0.5 + np.random.default_rng(14).random((n, 1))
+    model = O.Model(d=d, k=1, m=m, method=meth, heteroscedastic=True)
+    tr = np.ones(n, dtype=bool)
+    if nan:                                                                            # two missing-input patterns + complete rows
+        X[3:12, 0] = np.nan
+        X[20:27, 1] = np.nan
+    Psi = synth.make_psi(n, d, meth, seed=15) if psi else None       # VD: n x d variances; VC: d x d x n covariances (fixPsi.m form)
+    ref = O.GPz(theta, model, X, Y, Psi, omega, tr, None)
+    mp.mp.dps = 40
+    th = [mp.mpf(float(t)) for t in theta]
+    f0 = _mp_nlogml(th, meth, X, Y[:, 0], omega[:, 0], m, d, Psi)
+    assert abs(float((mp.mpf(float(ref.nlogML)) - f0) / f0)) <= 1e-13
+    h = mp.mpf(10) ** -15
+    g = np.zeros(len(theta))
+    for q in range(len(theta)):
+        tp, tm = list(th), list(th)
+        tp[q] += h
+        tm[q] -= h
+        g[q] = float((_mp_nlogml(tp, meth, X, Y[:, 0], omega[:, 0], m, d, Psi) - _mp_nlogml(tm, meth, X, Y[:, 0], omega[:, 0], m, d, Psi)) / (2 * h))
+    err = np.max(np.abs(ref.grad - g)) / np.max(np.abs(g))
+    assert err <= 1e-11, err
