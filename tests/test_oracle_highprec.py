@@ -81,12 +81,25 @@ def _mp_nlogml(theta, meth, X, Y, omega, m, d, Psi=None):
     n = X.shape[0]
     md = m * d
     P = [[theta[a * m + j] for a in range(d)] for j in range(m)]                       # P = reshape(theta(1:m*d), m, d)
-    if meth == "VC":
+    cov = meth[1] == "C"
+    if meth == "VC":                                                                   # getPHI.m:26-40 / init.m:65-86
         g_dim = d * d * m
         Gam = [[[theta[md + b + a * d + j * d * d] for a in range(d)] for b in range(d)] for j in range(m)]   # Gamma(b, a, j)
-    else:                                                                              # VD: Gamma = reshape(., m, d)
+    elif meth == "GC":
+        g_dim = d * d
+        Gam = [[[theta[md + b + a * d] for a in range(d)] for b in range(d)] for j in range(m)]
+    elif meth == "VD":                                                                 # Gamma = reshape(., m, d)
         g_dim = md
         Gam = [[theta[md + j + a * m] for a in range(d)] for j in range(m)]
+    elif meth == "GD":
+        g_dim = d
+        Gam = [[theta[md + a] for a in range(d)] for j in range(m)]
+    elif meth == "VL":
+        g_dim = m
+        Gam = [[theta[md + j] for a in range(d)] for j in range(m)]
+    else:                                                                              # GL
+        g_dim = 1
+        Gam = [[theta[md] for a in range(d)] for j in range(m)]
     o = md + g_dim
     lnA = theta[o:o + m]
     b = theta[o + m]
@@ -94,47 +107,34 @@ def _mp_nlogml(theta, meth, X, Y, omega, m, d, Psi=None):
     lnT = theta[o + m + 1 + m:o + m + 1 + 2 * m]
     PHI = [[None] * m for _ in range(n)]
     Sig = None
-    if Psi is not None and meth == "VC":                                               # Sigma_j = (Gamma_j' Gamma_j)^-1, getPHI.m:73
+    if cov:                                                                            # Sigma_j = (Gamma_j' Gamma_j)^-1, getPHI.m:73
         Sig = []
         for j in range(m):
             G = mp.matrix(Gam[j])
             Sig.append(mp.inverse(G.T * G))
     for i in range(n):
+        obs = [a for a in range(d) if not np.isnan(X[i, a])]                           # getPHI.m:43-54: rows grouped by NaN pattern
+        nmiss = d - len(obs)
         for j in range(m):
-            obs = [a for a in range(d) if not np.isnan(X[i, a])]
-            if len(obs) < d:                                                           # missing inputs (no Psi): getPHI.m:76 / :96
-                nmiss = d - len(obs)
-                if meth == "VC":
-                    if Sig is None:
-                        Sig = [None] * m
-                    if Sig[j] is None:
-                        G = mp.matrix(Gam[j])
-                        Sig[j] = mp.inverse(G.T * G)
-                    Soo = mp.matrix([[Sig[j][a, c] for c in obs] for a in obs])
-                    dv = mp.matrix([[mp.mpf(float(X[i, a])) - P[j][a] for a in obs]])
+            dl = [mp.mpf(float(X[i, a])) - P[j][a] for a in obs]
+            if cov:                                                                    # getPHI.m:73-88 on the observed block
+                Soo = mp.matrix([[Sig[j][a, c] for c in obs] for a in obs])
+                dv = mp.matrix([dl])
+                if Psi is None:
                     e = -(dv * mp.inverse(Soo) * dv.T)[0] / 2
                 else:
-                    e = -sum(((mp.mpf(float(X[i, a])) - P[j][a]) * Gam[j][a]) ** 2 for a in obs) / 2
-                PHI[i][j] = mp.exp(e - mp.mpf(nmiss) * mp.log(2) / 2)
-                continue
-            dl = [mp.mpf(float(X[i, a])) - P[j][a] for a in range(d)]
-            if Psi is None:
-                if meth == "VC":                                                       # getPHI.m:73-77 without NaN: -1/2 |Gamma_j dl|^2
-                    q = sum(sum(Gam[j][bb][a] * dl[a] for a in range(d)) ** 2 for bb in range(d))
-                else:                                                                  # getPHI.m:93-98
-                    q = sum((dl[a] * Gam[j][a]) ** 2 for a in range(d))
-                PHI[i][j] = mp.exp(-q / 2)
-            elif meth == "VC":                                                         # getPHI.m:80-88: S = Psi_i + Sigma_j
-                Sm = Sig[j] + mp.matrix(np.asarray(Psi[:, :, i], dtype=np.float64).tolist())
-                dv = mp.matrix([dl])
-                PHI[i][j] = mp.exp(-(dv * mp.inverse(Sm) * dv.T)[0] / 2 + mp.log(mp.det(Sig[j])) / 2 - mp.log(mp.det(Sm)) / 2)
-            else:                                                                      # getPHI.m:102-105: Sigma_ja = Gamma_ja^-2
+                    Sm = Soo + mp.matrix([[mp.mpf(float(Psi[a, c, i])) for c in obs] for a in obs])
+                    e = -(dv * mp.inverse(Sm) * dv.T)[0] / 2 + mp.log(mp.det(Soo)) / 2 - mp.log(mp.det(Sm)) / 2
+            else:                                                                      # getPHI.m:93-105, Sigma_ja = Gamma_ja^-2
                 e = mp.mpf(0)
-                for a in range(d):
-                    sg = 1 / Gam[j][a] ** 2
-                    ps = mp.mpf(float(Psi[i, a]))
-                    e += -dl[a] ** 2 / (ps + sg) / 2 - mp.log(1 + ps / sg) / 2
-                PHI[i][j] = mp.exp(e)
+                for q, a in enumerate(obs):
+                    if Psi is None:
+                        e -= (dl[q] * Gam[j][a]) ** 2 / 2
+                    else:
+                        sg = 1 / Gam[j][a] ** 2
+                        ps = mp.mpf(float(Psi[i, a]))
+                        e += -dl[q] ** 2 / (ps + sg) / 2 - mp.log(1 + ps / sg) / 2
+            PHI[i][j] = mp.exp(e - mp.mpf(nmiss) * mp.log(2) / 2)
     lnBi = [b + sum(PHI[i][j] * v[j] for j in range(m)) for i in range(n)]             # getPHI.m:116-125
     beta = [mp.exp(-t) for t in lnBi]
     wb = [beta[i] * mp.mpf(float(omega[i])) for i in range(n)]
@@ -157,7 +157,9 @@ def _mp_nlogml(theta, meth, X, Y, omega, m, d, Psi=None):
 
 
 @pytest.mark.parametrize("meth,psi,nan", [("VC", False, False), ("VD", False, False), ("VC", True, False), ("VD", True, False),
-                                          ("VC", False, True), ("VD", False, True)])
+                                          ("VC", False, True), ("VD", False, True), ("GC", True, False), ("GC", False, True),
+                                          ("GL", True, False), ("VL", False, True), ("GD", True, False), ("VC", True, True), ("VD", True, True),
+                                          ("GC", True, True)])
 def test_oracle_objective_and_gradient_against_40_digit_differences(meth, psi, nan):
     """The oracle's nlogML and its analytic gradient (GPz.m:113-234 restated) against the 40-digit objective and its central
     differences (h = 1e-15: truncation 1e-30).  fp64 finite differences (the T1 identity tests) cannot see below ~1e-6."""
