@@ -189,3 +189,75 @@ def test_oracle_objective_and_gradient_against_40_digit_differences(meth, psi, n
         g[q] = float((_mp_nlogml(tp, meth, X, Y[:, 0], omega[:, 0], m, d, Psi) - _mp_nlogml(tm, meth, X, Y[:, 0], omega[:, 0], m, d, Psi)) / (2 * h))
     err = np.max(np.abs(ref.grad - g)) / np.max(np.abs(g))
     assert err <= 1e-11, err
+
+
+def test_predict_full_and_noisy_diag_against_40_digit_arithmetic():
+    """predictFull (predictDiag.m:58-74) and predictNoisy for the diagonal modes (predictDiag.m:75-125) of the oracle against
+    40-digit evaluations of the same expressions: VD, m = 8, d = 3, 4 rows, w / iSigma_w from the oracle's fit."""
+    from gpz_b200 import synth
+    n, d, m = 60, 3, 8
+    X, Y = synth.make_data(n, d, seed=21)
+    X, Y = np.asarray(X), np.asarray(Y)
+    theta = synth.perturb_theta(synth.make_theta0(X, Y, "VD", m, het=True, seed=22), 0.2, 23)
+    model = O.Model(d=d, k=1, m=m, method="VD", heteroscedastic=True)
+    tr = np.ones(n, dtype=bool)
+    fit = O.GPz(theta, model, X, Y, None, None, tr, None, fit_only=True)
+    model.muX, model.sdX, model.muY = np.zeros(d), np.ones(d), np.zeros(1)
+    md = m * d
+    o = md + model.g_dim
+    P = theta[:md].reshape((m, d), order="F")
+    vv = theta[o + m + 1:o + 2 * m + 1]
+    bb = theta[o + m]
+    model.best = dict(theta=theta, w=fit.w, iSigma_w=fit.iSigma_w, P=P, v=vv.reshape(m, 1))
+    Xt = X[:4]
+    Psi = synth.make_psi(4, d, "VD", seed=24)
+    mp.mp.dps = 40
+    f = lambda t: mp.mpf(float(t))                                                    # noqa: E731
+    G = [[f(theta[md + j + a * m]) for a in range(d)] for j in range(m)]
+    Pm = [[f(P[j, a]) for a in range(d)] for j in range(m)]
+    w = [f(t) for t in fit.w[:, 0]]
+    v = [f(t) for t in vv]
+    iSw = fit.iSigma_w[:, :, 0]
+    rel = lambda a, b: abs(float((f(a) - b) / b))                                     # noqa: E731
+
+    # ---- predictFull: mu = PHI w, nu = phi' iSigma_w phi, beta_i = exp(b + PHI v)
+    mu, sigma, nu, be, ga, PHI = O.predict(Xt, model)
+    for t in range(4):
+        phi = [mp.exp(-sum(((f(Xt[t, a]) - Pm[j][a]) * G[j][a]) ** 2 for a in range(d)) / 2) for j in range(m)]
+        mu_x = sum(phi[j] * w[j] for j in range(m))
+        nu_x = sum(phi[i] * f(iSw[i, j]) * phi[j] for i in range(m) for j in range(m))
+        be_x = mp.exp(f(bb) + sum(phi[j] * v[j] for j in range(m)))
+        assert rel(mu[t, 0], mu_x) <= 1e-12 and rel(be[t, 0], be_x) <= 1e-12 and rel(nu[t, 0], nu_x) <= 1e-9
+        assert ga[t, 0] == 0.0 and rel(sigma[t, 0], nu_x + be_x) <= 1e-11
+
+    # ---- predictNoisy (diag)
+    mu, sigma, nu, be, ga, PHI = O.predict(Xt, model, Psi=Psi)
+    iS = [[G[j][a] ** 2 for a in range(d)] for j in range(m)]
+    S = [[1 / iS[j][a] for a in range(d)] for j in range(m)]
+    lnz = [-sum(mp.log(iS[j][a]) for a in range(d)) / 2 for j in range(m)]
+    for t in range(4):
+        x = [f(Xt[t, a]) for a in range(d)]
+        ps = [f(Psi[t, a]) for a in range(d)]
+        phi = [mp.exp(sum(-(x[a] - Pm[j][a]) ** 2 / (ps[a] + S[j][a]) / 2 - mp.log(1 + ps[a] / S[j][a]) / 2 for a in range(d)))
+               for j in range(m)]                                                     # getPHI.m:102-105
+        mu_x = sum(phi[j] * w[j] for j in range(m))
+        ElnS = f(bb) + sum(phi[j] * v[j] for j in range(m))
+        ga_x = nu_x = V_x = mp.mpf(0)
+        for i in range(m):
+            for j in range(i + 1):
+                iC = [iS[i][a] + iS[j][a] for a in range(d)]
+                C = [1 / c for c in iC]
+                cc = [(Pm[i][a] * iS[i][a] + Pm[j][a] * iS[j][a]) / iC[a] for a in range(d)]
+                lnZ = lnz[i] + lnz[j] - sum((Pm[i][a] - Pm[j][a]) ** 2 / (S[i][a] + S[j][a]) for a in range(d)) / 2 \
+                    - sum(mp.log(S[i][a] + S[j][a]) for a in range(d)) / 2
+                lnN = -sum((x[a] - cc[a]) ** 2 / (ps[a] + C[a]) for a in range(d)) / 2 - sum(mp.log(ps[a] + C[a]) for a in range(d)) / 2
+                Z = mp.exp(lnZ + lnN)
+                fac = 2 if j < i else 1
+                ga_x += fac * Z * w[i] * w[j]
+                V_x += fac * Z * v[i] * v[j]
+                nu_x += fac * Z * f(iSw[i, j])
+        V_x -= (ElnS - f(bb)) ** 2
+        ga_x -= mu_x ** 2
+        be_x = mp.exp(ElnS) * (1 + V_x / 2)
+        assert rel(mu[t, 0], mu_x) <= 1e-12 and rel(be[t, 0], be_x) <= 1e-11
+        assert rel(nu[t, 0], nu_x) <= 1e-9 and abs(float(f(ga[t, 0]) - ga_x)) <= 1e-12 * max(1.0, float(mu_x) ** 2)
