@@ -261,3 +261,116 @@ def test_predict_full_and_noisy_diag_against_40_digit_arithmetic():
         be_x = mp.exp(ElnS) * (1 + V_x / 2)
         assert rel(mu[t, 0], mu_x) <= 1e-12 and rel(be[t, 0], be_x) <= 1e-11
         assert rel(nu[t, 0], nu_x) <= 1e-9 and abs(float(f(ga[t, 0]) - ga_x)) <= 1e-12 * max(1.0, float(mu_x) ** 2)
+
+
+def test_predict_missing_diag_against_40_digit_arithmetic():
+    """predictMissing for the diagonal modes (predictDiag.m:127-212) of the oracle against a 40-digit restatement: VD, m = 6,
+    d = 3, three rows sharing one missing dimension, priors from the oracle's getPrior (getPrior.m:7-20)."""
+    from gpz_b200 import synth
+    n, d, m = 50, 3, 6
+    X, Y = synth.make_data(n, d, seed=31)
+    X, Y = np.array(X), np.asarray(Y)
+    theta = synth.perturb_theta(synth.make_theta0(X, Y, "VD", m, het=True, seed=32), 0.2, 33)
+    model = O.Model(d=d, k=1, m=m, method="VD", heteroscedastic=True)
+    tr = np.ones(n, dtype=bool)
+    fit = O.GPz(theta, model, X, Y, None, None, tr, None, fit_only=True)
+    pri = O.getPrior(X, None, theta, model, tr)
+    model.muX, model.sdX, model.muY = np.zeros(d), np.ones(d), np.zeros(1)
+    md = m * d
+    o_ = md + model.g_dim
+    P = theta[:md].reshape((m, d), order="F")
+    vv = theta[o_ + m + 1:o_ + 2 * m + 1]
+    bb = theta[o_ + m]
+    model.best = dict(theta=theta, w=fit.w, iSigma_w=fit.iSigma_w, P=P, v=vv.reshape(m, 1), priors=pri)
+    Xt = X[:3].copy()
+    Xt[:, 1] = np.nan
+    mu, sigma, nu, be, ga, PHI = O.predict(Xt, model)
+
+    mp.mp.dps = 40
+    f = lambda t: mp.mpf(float(t))                                                    # noqa: E731
+    ob, un = [0, 2], [1]
+    G = [[f(theta[md + j + a * m]) for a in range(d)] for j in range(m)]
+    Pm = [[f(P[j, a]) for a in range(d)] for j in range(m)]
+    w = [f(t) for t in fit.w[:, 0]]
+    v = [f(t) for t in vv]
+    pr = [f(t) for t in np.asarray(pri).reshape(-1)]
+    iSw = fit.iSigma_w[:, :, 0]
+    iS = [[G[j][a] ** 2 for a in range(d)] for j in range(m)]
+    S = [[1 / iS[j][a] for a in range(d)] for j in range(m)]
+    lnz = [-sum(mp.log(iS[j][a]) for a in range(d)) / 2 for j in range(m)]
+    Nij = [[mp.exp(-sum((Pm[i][a] - Pm[j][a]) ** 2 / (S[i][a] + S[j][a]) for a in un) / 2
+                   - sum(mp.log(S[i][a] + S[j][a]) for a in un) / 2) for j in range(m)] for i in range(m)]     # :161
+    rel = lambda a, b: abs(float((f(a) - b) / b))                                     # noqa: E731
+    for t in range(3):
+        x = {a: f(Xt[t, a]) for a in ob}
+        No = [mp.exp(-sum((x[a] - Pm[i][a]) ** 2 / S[i][a] for a in ob) / 2 - sum(mp.log(S[i][a]) for a in ob) / 2) for i in range(m)]
+        Ex = [No[i] * pr[i] for i in range(m)]                                        # :145-151
+        Pio = [e / sum(Ex) for e in Ex]                                               # :153-155
+        phi = [mp.exp(lnz[i]) * No[i] * sum(Pio[j] * Nij[i][j] for j in range(m)) for i in range(m)]          # :163-164
+        mu_x = sum(phi[i] * w[i] for i in range(m))
+        ElnS = sum(phi[i] * v[i] for i in range(m))
+        ga_x = nu_x = V_x = mp.mpf(0)
+        for i in range(m):
+            for j in range(i + 1):
+                C = [1 / (iS[i][a] + iS[j][a]) for a in range(d)]
+                cc = [(Pm[i][a] * iS[i][a] + Pm[j][a] * iS[j][a]) * C[a] for a in range(d)]
+                No_p = mp.exp(-sum((x[a] - cc[a]) ** 2 / C[a] for a in ob) / 2 - sum(mp.log(C[a]) for a in ob) / 2)     # :180
+                Nu = [mp.exp(-sum((Pm[l][a] - cc[a]) ** 2 / (S[l][a] + C[a]) for a in un) / 2
+                             - sum(mp.log(S[l][a] + C[a]) for a in un) / 2) for l in range(m)]                          # :184
+                Ec = sum(No_p * Nu[l] * Pio[l] for l in range(m))                                                        # :186-187
+                Z = mp.exp(lnz[i] + lnz[j] - sum((Pm[i][a] - Pm[j][a]) ** 2 / (S[i][a] + S[j][a]) for a in range(d)) / 2
+                           - sum(mp.log(S[i][a] + S[j][a]) for a in range(d)) / 2) * Ec                                  # :190
+                fac = 2 if j < i else 1
+                ga_x += fac * Z * w[i] * w[j]
+                V_x += fac * Z * v[i] * v[j]
+                nu_x += fac * Z * f(iSw[i, j])
+        V_x -= ElnS ** 2                                                              # :204
+        be_x = mp.exp(ElnS + f(bb)) * (1 + V_x / 2)                                   # :206-208
+        ga_x -= mu_x ** 2
+        for i in range(m):
+            assert rel(PHI[t, i], phi[i]) <= 1e-12
+        assert rel(mu[t, 0], mu_x) <= 1e-12 and rel(be[t, 0], be_x) <= 1e-11
+        assert rel(nu[t, 0], nu_x) <= 1e-9 and abs(float(f(ga[t, 0]) - ga_x)) <= 1e-12 * max(1.0, float(mu_x) ** 2)
+
+
+def test_get_prior_against_40_digit_arithmetic():
+    """getPrior.m:7-20 (EM over the mixture weights of the normalised basis densities N of getPHI.m:98,114) in 40-digit
+    arithmetic against the oracle: VD, no Psi, one missing-input pattern among the rows."""
+    from gpz_b200 import synth
+    n, d, m = 40, 2, 5
+    X, Y = synth.make_data(n, d, seed=41)
+    X, Y = np.array(X), np.asarray(Y)
+    theta = synth.perturb_theta(synth.make_theta0(X, Y, "VD", m, het=True, seed=42), 0.2, 43)
+    X[5:11, 1] = np.nan
+    model = O.Model(d=d, k=1, m=m, method="VD", heteroscedastic=True)
+    tr = np.ones(n, dtype=bool)
+    pri = np.asarray(O.getPrior(X, None, theta, model, tr)).reshape(-1)
+    mp.mp.dps = 40
+    f = lambda t: mp.mpf(float(t))                                                    # noqa: E731
+    md = m * d
+    G = [[f(theta[md + j + a * m]) for a in range(d)] for j in range(m)]
+    Pm = [[f(theta[a * m + j]) for a in range(d)] for j in range(m)]
+    N = []
+    for i in range(n):
+        ob = [a for a in range(d) if not np.isnan(X[i, a])]
+        row = []
+        for j in range(m):
+            sg = {a: 1 / G[j][a] ** 2 for a in ob}
+            lnphi = -sum((f(X[i, a]) - Pm[j][a]) ** 2 / sg[a] for a in ob) / 2 - mp.mpf(d - len(ob)) * mp.log(2) / 2
+            lnN = lnphi - sum(mp.log(sg[a]) for a in ob) / 2 - mp.mpf(len(ob)) * mp.log(2 * mp.pi) / 2 \
+                + mp.mpf(d - len(ob)) * mp.log(2) / 2                                 # getPHI.m:98
+            row.append(mp.exp(lnN))
+        N.append(row)
+    prior = [mp.mpf(1) / m] * m
+    for _ in range(100):
+        old = list(prior)
+        W = [[N[i][j] * prior[j] for j in range(m)] for i in range(n)]
+        W = [[t / sum(r) for t in r] for r in W]
+        prior = [sum(W[i][j] for i in range(n)) / n for j in range(m)]
+        num = mp.sqrt(sum((a - b) ** 2 for a, b in zip(old, prior)))
+        den = mp.sqrt(sum((a + b) ** 2 for a, b in zip(old, prior)))
+        if num / den < mp.mpf(10) ** -10:
+            break
+    err = max(abs(float(f(pri[j]) - prior[j])) for j in range(m))
+    assert err <= 1e-9, err
+    assert abs(float(sum(prior)) - 1.0) <= 1e-30 and abs(pri.sum() - 1.0) <= 1e-12
