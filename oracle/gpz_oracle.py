@@ -11,7 +11,11 @@ MATLAB/Octave here) ships no tests, no golden vectors and no recorded outputs fo
 inv, mrdivide, exp; version unpinned, not under /root/reference).  What pins this restatement
 instead are the mathematical identities in tests/test_oracle_pins.py (finite-difference exact
 gradient, independent dense-GP evidence, six-mode equivalence, Psi=0 identity, predictNoisy ->
-predictFull limit, fit-path definitions) and self-derived golden vectors in tests/golden/.
+predictFull limit, fit-path definitions), self-derived golden vectors in tests/golden/, and
+tests/test_oracle_highprec.py: the objective of GPz.m restated on its own in 40-digit arithmetic
+(all six modes, with Psi and with missing inputs) against this file's nlogML (1e-13) and, by
+central differences of that objective, against its analytic gradient (1e-11); the predict
+branches (Full, Noisy diag / cov, Missing diag) and getPrior against 40-digit restatements.
 
 Every function cites the reference file:line it follows (paths under /root/reference/GPz).
 MATLAB semantics kept: column-major reshapes (order='F'), 1-based slices translated to
