@@ -17,22 +17,32 @@ int g_prep_block = 32;          // threads per CTA of the per-basis theta -> par
 // ------------------------------------------------------------------------------------------------
 // theta -> per-basis arrays
 // ------------------------------------------------------------------------------------------------
+// Both kernels below: blockDim = (bases, PREP_TY).  threadIdx.x walks the bases (all arrays are [..][MP], so accesses stay coalesced),
+// threadIdx.y splits the ROWS of the per-basis d x d work; what needs a whole matrix (Cholesky, the constant term) is done by the
+// y = 0 thread after a block barrier.  One thread per basis did O(d^3) dependent work: 55 + 85 us at m = 1000, d = 10
+// (profiles/r02z_small_launches.csv), the largest n-independent part of the 8-GPU step.  Every output element is still produced by
+// the same expression in the same order.
+constexpr int PREP_TY = 8;
+
 __global__ void prep_kernel(const double* __restrict__ th, Params P, int need_sigma) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= P.MP) return;
+    const int ty = threadIdx.y, TY = blockDim.y;
     const int d = P.d, m = P.m, MP = P.MP, k = P.k, dp = P.dp;
+    const bool valid = j < MP;
     const bool live = j < m;
     const double* thG = th + P.oG;
     // centres are stored relative to the dataset shift (X was shifted by the same constant at upload)
     // the centre is also kept locally (covariance modes: d <= 32) or recomputed (diagonal modes: any d) instead of read back
     double pl[32];
-    for (int a = 0; a < d; ++a) {
-        const double pa = live ? th[a * m + j] - P.xshift[a] : 0.0;
-        if (a < 32) pl[a] = pa;
-        P.Pt[a * MP + j] = pa;
-    }
-    if (!mode_is_cov(P.mode)) {
+    if (valid) {
         for (int a = 0; a < d; ++a) {
+            const double pa = live ? th[a * m + j] - P.xshift[a] : 0.0;
+            if (a < 32) pl[a] = pa;
+            if (ty == 0) P.Pt[a * MP + j] = pa;
+        }
+    }
+    if (valid && !mode_is_cov(P.mode)) {
+        for (int a = ty; a < d; a += TY) {
             double gv = 0.0;
             if (live) {
                 switch (P.mode) {
@@ -51,26 +61,28 @@ __global__ void prep_kernel(const double* __restrict__ th, Params P, int need_si
             }
         }
         if (P.Wc != nullptr) {
-            double c0 = 0.0;
-            for (int a = 0; a < d; ++a) {
-                double gv = 0.0;
-                if (live) {
-                    switch (P.mode) {
-                        case GL: gv = thG[0]; break;
-                        case VL: gv = thG[j]; break;
-                        case GD: gv = thG[a]; break;
-                        default: gv = thG[a * m + j]; break;
+            if (ty == 0) {
+                double c0 = 0.0;
+                for (int a = 0; a < d; ++a) {
+                    double gv = 0.0;
+                    if (live) {
+                        switch (P.mode) {
+                            case GL: gv = thG[0]; break;
+                            case VL: gv = thG[j]; break;
+                            case GD: gv = thG[a]; break;
+                            default: gv = thG[a * m + j]; break;
+                        }
                     }
+                    const double gp = live ? gv * (th[a * m + j] - P.xshift[a]) : 0.0;      // = P.Ct[a * MP + j], recomputed instead of read back
+                    c0 = fma(gp, gp, c0);
                 }
-                const double gp = live ? gv * (th[a * m + j] - P.xshift[a]) : 0.0;      // = P.Ct[a * MP + j], recomputed instead of read back
-                c0 = fma(gp, gp, c0);
+                P.Wc[j] = live ? -0.5 * c0 : 0.0;
             }
-            P.Wc[j] = live ? -0.5 * c0 : 0.0;
-            for (int r = 1 + 2 * d; r < P.KQ; ++r) P.Wc[static_cast<int64_t>(r) * MP + j] = 0.0;
+            for (int r = 1 + 2 * d + ty; r < P.KQ; r += TY) P.Wc[static_cast<int64_t>(r) * MP + j] = 0.0;
         }
-    } else {
+    } else if (valid) {
         const double* G = (P.mode == GC) ? thG : thG + static_cast<int64_t>(d) * d * j;   // Gamma_j(b,a) = G[b + a*d]
-        for (int b = 0; b < d; ++b) {
+        for (int b = ty; b < d; b += TY) {
             double c = 0.0;
             for (int a = 0; a < dp; ++a) {
                 const double gv = (live && a < d) ? G[b + a * d] : 0.0;
@@ -79,14 +91,17 @@ __global__ void prep_kernel(const double* __restrict__ th, Params P, int need_si
             }
             P.Ct[b * MP + j] = c;
         }
-        for (int a = 0; a < d; ++a)
+        for (int a = ty; a < d; a += TY)
             for (int b = 0; b < d; ++b) {
                 double s = 0.0;
                 if (live)
                     for (int c = 0; c < d; ++c) s += G[c + a * d] * G[c + b * d];
                 P.Aj[(static_cast<int64_t>(a) * d + b) * MP + j] = live ? s : (a == b ? 1.0 : 0.0);
             }
-        if (need_sigma) {
+    }
+    if (mode_is_cov(P.mode) && need_sigma) {
+        __syncthreads();                                  // the rows of Aj written by the other y threads of this block
+        if (valid && ty == 0) {
             StridedMat S{P.Sj + j, MP, d};
             StridedMat A{P.Aj + j, MP, d};
             for (int a = 0; a < d; ++a)
@@ -96,6 +111,7 @@ __global__ void prep_kernel(const double* __restrict__ th, Params P, int need_si
             P.lndS[j] = ok ? -2.0 * hl : nan("");
         }
     }
+    if (!valid || ty != 0) return;
     for (int o = 0; o < k; ++o) {
         P.alpha[o * MP + j] = live ? exp(th[P.oA + static_cast<int64_t>(o) * m + j]) : 1.0;
         if (P.het) {
@@ -114,103 +130,116 @@ __global__ void prep_kernel(const double* __restrict__ th, Params P, int need_si
 //   G  = A_uu^-1 A_uo                                       (GPz.m:156)
 //   W  = coefficients of  -1/2 (x-p)_o' M (x-p)_o - 1/2 |u| ln 2  in the monomials [1, x_a, x_a x_b (a<=b)]
 template <int DMAX>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(1024)
 prep_patterns_kernel(Params P) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ty = threadIdx.y, TY = blockDim.y;
     const int g = blockIdx.y;
     const int d = P.d, m = P.m, MP = P.MP;
-    if (j >= MP) return;
+    const bool valid = j < MP, live = j < m;
     const unsigned char* ob = P.obs + g * d;
     double* Mg = P.Mg + static_cast<int64_t>(g) * d * d * MP;
     double* Gg = P.Gg + static_cast<int64_t>(g) * d * d * MP;
     double* Wg = P.Wc != nullptr ? P.Wc + static_cast<int64_t>(g) * P.KQ * MP : nullptr;
-    if (j >= m) {
-        P.lndM[static_cast<int64_t>(g) * MP + j] = 0.0;
-        for (int e = 0; e < d * d; ++e) Mg[static_cast<int64_t>(e) * MP + j] = Gg[static_cast<int64_t>(e) * MP + j] = 0.0;
+    if (valid && !live) {
+        if (ty == 0) P.lndM[static_cast<int64_t>(g) * MP + j] = 0.0;
+        for (int e = ty; e < d * d; e += TY) Mg[static_cast<int64_t>(e) * MP + j] = Gg[static_cast<int64_t>(e) * MP + j] = 0.0;
         if (Wg != nullptr)
-            for (int r = 0; r < P.KQ; ++r) Wg[static_cast<int64_t>(r) * MP + j] = 0.0;
-        return;
+            for (int r = ty; r < P.KQ; r += TY) Wg[static_cast<int64_t>(r) * MP + j] = 0.0;
     }
     int ui[DMAX];
     int nu = 0;
     for (int a = 0; a < d; ++a)
         if (!ob[a]) ui[nu++] = a;
-    double U[DMAX * DMAX];            // A_uu, then its inverse (nu x nu)
+    double U[DMAX * DMAX];            // A_uu, then its inverse (nu x nu); every y thread forms its own copy (nu is small)
     LocalMat Um{U, nu};
-    for (int r = 0; r < nu; ++r)
-        for (int c = 0; c < nu; ++c) Um(r, c) = P.Aj[(static_cast<int64_t>(ui[r]) * d + ui[c]) * MP + j];
-    double hl = 0.0;
     bool ok = true;
-    if (nu > 0) ok = spd_inv(Um, nu, &hl);
-    // G(e,b) for e in u, b in o; zero elsewhere
-    for (int a = 0; a < d; ++a)
-        for (int b = 0; b < d; ++b) Gg[(static_cast<int64_t>(a) * d + b) * MP + j] = 0.0;
-    for (int r = 0; r < nu; ++r)
-        for (int b = 0; b < d; ++b) {
-            if (!ob[b]) continue;
-            double s = 0.0;
-            for (int c = 0; c < nu; ++c) s += Um(r, c) * P.Aj[(static_cast<int64_t>(ui[c]) * d + b) * MP + j];
-            Gg[(static_cast<int64_t>(ui[r]) * d + b) * MP + j] = ok ? s : nan("");
-        }
-    // M(a,b) = A(a,b) - sum_{e in u} A(a,e) G(e,b)   for a,b in o.  A copy stays in thread-local memory for the two uses below
-    // instead of being read back from global memory.  (The kernel is one thread per basis with O(d^3) dependent work, i.e.
-    // latency-bound at ~85 us for m = 1000, d = 10 whatever the memory path: profiles/r02z_prep.csv, r02z7_prep.csv.  Only the
-    // 8-GPU step notices it; a warp per basis is the next step there.)
-    double Ml[DMAX * DMAX];
-    for (int a = 0; a < d; ++a)
-        for (int b = 0; b < d; ++b) {
-            double v = 0.0;
-            if (ob[a] && ob[b]) {
-                v = P.Aj[(static_cast<int64_t>(a) * d + b) * MP + j];
-                for (int r = 0; r < nu; ++r)
-                    v -= P.Aj[(static_cast<int64_t>(a) * d + ui[r]) * MP + j] * Gg[(static_cast<int64_t>(ui[r]) * d + b) * MP + j];
+    if (live) {
+        for (int r = 0; r < nu; ++r)
+            for (int c = 0; c < nu; ++c) Um(r, c) = P.Aj[(static_cast<int64_t>(ui[r]) * d + ui[c]) * MP + j];
+        double hl = 0.0;
+        if (nu > 0) ok = spd_inv(Um, nu, &hl);
+        // G(e,b) for e in u, b in o; zero elsewhere: rows a of G split over y
+        for (int a = ty; a < d; a += TY)
+            for (int b = 0; b < d; ++b) Gg[(static_cast<int64_t>(a) * d + b) * MP + j] = 0.0;
+    }
+    __syncthreads();                                       // (zero fill before the rows that other y threads overwrite)
+    if (live) {
+        for (int r = ty; r < nu; r += TY)
+            for (int b = 0; b < d; ++b) {
+                if (!ob[b]) continue;
+                double s = 0.0;
+                for (int c = 0; c < nu; ++c) s += Um(r, c) * P.Aj[(static_cast<int64_t>(ui[c]) * d + b) * MP + j];
+                Gg[(static_cast<int64_t>(ui[r]) * d + b) * MP + j] = ok ? s : nan("");
             }
-            Ml[a * d + b] = v;
-            Mg[(static_cast<int64_t>(a) * d + b) * MP + j] = v;
-        }
-    {   // ln det M over the observed block (for the normalised densities N)
+    }
+    __syncthreads();                                       // G complete
+    // M(a,b) = A(a,b) - sum_{e in u} A(a,e) G(e,b)   for a,b in o: rows a split over y
+    if (live) {
+        for (int a = ty; a < d; a += TY)
+            for (int b = 0; b < d; ++b) {
+                double v = 0.0;
+                if (ob[a] && ob[b]) {
+                    v = P.Aj[(static_cast<int64_t>(a) * d + b) * MP + j];
+                    for (int r = 0; r < nu; ++r)
+                        v -= P.Aj[(static_cast<int64_t>(a) * d + ui[r]) * MP + j] * Gg[(static_cast<int64_t>(ui[r]) * d + b) * MP + j];
+                }
+                Mg[(static_cast<int64_t>(a) * d + b) * MP + j] = v;
+            }
+    }
+    __syncthreads();                                       // M complete
+    if (!live) return;
+    if (ty == 0) {   // ln det M over the observed block (for the normalised densities N)
         int oi[DMAX];
         int no = 0;
         for (int a = 0; a < d; ++a)
             if (ob[a]) oi[no++] = a;
         LocalMat Om{U, no};
         for (int r = 0; r < no; ++r)
-            for (int c = 0; c <= r; ++c) Om(r, c) = Ml[oi[r] * d + oi[c]];
+            for (int c = 0; c <= r; ++c) Om(r, c) = Mg[(static_cast<int64_t>(oi[r]) * d + oi[c]) * MP + j];
         double hm = 0.0;
         const bool okm = no == 0 || chol_lower(Om, no, &hm);
         P.lndM[static_cast<int64_t>(g) * MP + j] = okm ? 2.0 * hm : nan("");
     }
     if (Wg == nullptr) return;
-    double c0 = 0.0;
-    int idx = 1 + d;
     double pl[DMAX];
     for (int a = 0; a < d; ++a) pl[a] = P.Pt[a * MP + j];
-    for (int a = 0; a < d; ++a) {
+    // rows a of the coefficient table split over y; the y = 1 thread (y = 0 is busy with the Cholesky) also forms the constant
+    for (int a = ty; a < d; a += TY) {
         double bv = 0.0;
-        for (int b = 0; b < d; ++b) bv += Ml[a * d + b] * pl[b];
-        c0 += bv * pl[a];
+        for (int b = 0; b < d; ++b) bv += Mg[(static_cast<int64_t>(a) * d + b) * MP + j] * pl[b];
         Wg[static_cast<int64_t>(1 + a) * MP + j] = bv;
+        int idx = 1 + d + a * d - a * (a - 1) / 2;                                   // first entry of row a in the packed a <= b list
         for (int b = a; b < d; ++b, ++idx) {
-            const double av = Ml[a * d + b];
+            const double av = Mg[(static_cast<int64_t>(a) * d + b) * MP + j];
             Wg[static_cast<int64_t>(idx) * MP + j] = (a == b) ? -0.5 * av : -av;
         }
     }
-    Wg[j] = -0.5 * c0 - 0.5 * nu * kLn2;
-    for (int r = idx; r < P.KQ; ++r) Wg[static_cast<int64_t>(r) * MP + j] = 0.0;
+    const int tc = TY > 1 ? 1 : 0;
+    if (ty == tc) {
+        double c0 = 0.0;
+        for (int a = 0; a < d; ++a) {
+            double bv = 0.0;
+            for (int b = 0; b < d; ++b) bv += Mg[(static_cast<int64_t>(a) * d + b) * MP + j] * pl[b];
+            c0 += bv * pl[a];
+        }
+        Wg[j] = -0.5 * c0 - 0.5 * nu * kLn2;
+    }
+    for (int r = 1 + d + d * (d + 1) / 2 + ty; r < P.KQ; r += TY) Wg[static_cast<int64_t>(r) * MP + j] = 0.0;
 }
 
 int prep_params(const double* d_theta, const Params& P, int need_sigma, cudaStream_t st, int64_t* launches) {
-    // one thread per basis with O(d^3) serial work each: latency-bound, so one warp per CTA spreads the m threads over 4x as many SMs
-    // (ncu launch list at m = 1000, d = 10: 128-thread CTAs 80 / 90 us per launch, the n-independent part of the 8-GPU step)
+    // 32 bases x PREP_TY row threads per CTA: the per-basis work is latency-bound, so few bases per CTA spread it over many SMs
     const int bt = g_prep_block;
-    prep_kernel<<<static_cast<unsigned>(ceil_div(P.MP, bt)), bt, 0, st>>>(d_theta, P, need_sigma);
+    const dim3 blk(static_cast<unsigned>(bt), PREP_TY);
+    prep_kernel<<<static_cast<unsigned>(ceil_div(P.MP, bt)), blk, 0, st>>>(d_theta, P, need_sigma);
     GPZ_KERNEL_CHECK();
     ++*launches;
     if (mode_is_cov(P.mode) && P.Mg != nullptr) {
         dim3 grid(static_cast<unsigned>(ceil_div(P.MP, bt)), static_cast<unsigned>(P.npat));
-        if (P.d <= 8) prep_patterns_kernel<8><<<grid, bt, 0, st>>>(P);
-        else if (P.d <= 16) prep_patterns_kernel<16><<<grid, bt, 0, st>>>(P);
-        else prep_patterns_kernel<32><<<grid, bt, 0, st>>>(P);
+        if (P.d <= 8) prep_patterns_kernel<8><<<grid, blk, 0, st>>>(P);
+        else if (P.d <= 16) prep_patterns_kernel<16><<<grid, blk, 0, st>>>(P);
+        else prep_patterns_kernel<32><<<grid, blk, 0, st>>>(P);
         GPZ_KERNEL_CHECK();
         ++*launches;
     }
