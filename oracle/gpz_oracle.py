@@ -15,7 +15,8 @@ predictFull limit, fit-path definitions), self-derived golden vectors in tests/g
 tests/test_oracle_highprec.py: the objective of GPz.m restated on its own in 40-digit arithmetic
 (all six modes, with Psi and with missing inputs) against this file's nlogML (1e-13) and, by
 central differences of that objective, against its analytic gradient (1e-11); the predict
-branches (Full, Noisy diag / cov, Missing diag) and getPrior against 40-digit restatements.
+branches (Full, Noisy, Missing, NoisyMissing; diagonal and covariance modes) and getPrior against
+40-digit restatements.
 
 Every function cites the reference file:line it follows (paths under /root/reference/GPz).
 MATLAB semantics kept: column-major reshapes (order='F'), 1-based slices translated to

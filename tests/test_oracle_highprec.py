@@ -263,9 +263,11 @@ def test_predict_full_and_noisy_diag_against_40_digit_arithmetic():
         assert rel(nu[t, 0], nu_x) <= 1e-9 and abs(float(f(ga[t, 0]) - ga_x)) <= 1e-12 * max(1.0, float(mu_x) ** 2)
 
 
-def test_predict_missing_diag_against_40_digit_arithmetic():
-    """predictMissing for the diagonal modes (predictDiag.m:127-212) of the oracle against a 40-digit restatement: VD, m = 6,
-    d = 3, three rows sharing one missing dimension, priors from the oracle's getPrior (getPrior.m:7-20)."""
+@pytest.mark.parametrize("psi", [False, True])
+def test_predict_missing_diag_against_40_digit_arithmetic(psi):
+    """predictMissing (predictDiag.m:127-212) and predictNoisyMissing (predictDiag.m:213-295: the input-noise variances are
+    added to the variances of the OBSERVED dims, :230-232 and :262-264) for the diagonal modes of the oracle against a 40-digit
+    restatement: VD, m = 6, d = 3, three rows sharing one missing dimension, priors from the oracle's getPrior."""
     from gpz_b200 import synth
     n, d, m = 50, 3, 6
     X, Y = synth.make_data(n, d, seed=31)
@@ -284,7 +286,8 @@ def test_predict_missing_diag_against_40_digit_arithmetic():
     model.best = dict(theta=theta, w=fit.w, iSigma_w=fit.iSigma_w, P=P, v=vv.reshape(m, 1), priors=pri)
     Xt = X[:3].copy()
     Xt[:, 1] = np.nan
-    mu, sigma, nu, be, ga, PHI = O.predict(Xt, model)
+    Psi = synth.make_psi(3, d, "VD", seed=34) if psi else None
+    mu, sigma, nu, be, ga, PHI = O.predict(Xt, model, Psi=Psi)
 
     mp.mp.dps = 40
     f = lambda t: mp.mpf(float(t))                                                    # noqa: E731
@@ -303,7 +306,9 @@ def test_predict_missing_diag_against_40_digit_arithmetic():
     rel = lambda a, b: abs(float((f(a) - b) / b))                                     # noqa: E731
     for t in range(3):
         x = {a: f(Xt[t, a]) for a in ob}
-        No = [mp.exp(-sum((x[a] - Pm[i][a]) ** 2 / S[i][a] for a in ob) / 2 - sum(mp.log(S[i][a]) for a in ob) / 2) for i in range(m)]
+        ps = {a: (f(Psi[t, a]) if psi else mp.mpf(0)) for a in ob}
+        No = [mp.exp(-sum((x[a] - Pm[i][a]) ** 2 / (S[i][a] + ps[a]) for a in ob) / 2
+                     - sum(mp.log(S[i][a] + ps[a]) for a in ob) / 2) for i in range(m)]
         Ex = [No[i] * pr[i] for i in range(m)]                                        # :145-151
         Pio = [e / sum(Ex) for e in Ex]                                               # :153-155
         phi = [mp.exp(lnz[i]) * No[i] * sum(Pio[j] * Nij[i][j] for j in range(m)) for i in range(m)]          # :163-164
@@ -314,7 +319,8 @@ def test_predict_missing_diag_against_40_digit_arithmetic():
             for j in range(i + 1):
                 C = [1 / (iS[i][a] + iS[j][a]) for a in range(d)]
                 cc = [(Pm[i][a] * iS[i][a] + Pm[j][a] * iS[j][a]) * C[a] for a in range(d)]
-                No_p = mp.exp(-sum((x[a] - cc[a]) ** 2 / C[a] for a in ob) / 2 - sum(mp.log(C[a]) for a in ob) / 2)     # :180
+                No_p = mp.exp(-sum((x[a] - cc[a]) ** 2 / (C[a] + ps[a]) for a in ob) / 2
+                              - sum(mp.log(C[a] + ps[a]) for a in ob) / 2)                                               # :180 / :263
                 Nu = [mp.exp(-sum((Pm[l][a] - cc[a]) ** 2 / (S[l][a] + C[a]) for a in un) / 2
                              - sum(mp.log(S[l][a] + C[a]) for a in un) / 2) for l in range(m)]                          # :184
                 Ec = sum(No_p * Nu[l] * Pio[l] for l in range(m))                                                        # :186-187
@@ -374,3 +380,110 @@ def test_get_prior_against_40_digit_arithmetic():
     err = max(abs(float(f(pri[j]) - prior[j])) for j in range(m))
     assert err <= 1e-9, err
     assert abs(float(sum(prior)) - 1.0) <= 1e-30 and abs(pri.sum() - 1.0) <= 1e-12
+
+
+@pytest.mark.parametrize("psi", [False, True])
+def test_predict_missing_cov_against_40_digit_arithmetic(psi):
+    """predictMissing (predictCov.m:134-232) and predictNoisyMissing (predictCov.m:233-336: Psi(o,o) joins the observed block,
+    Psi_hat = T Psi_oo T' + Schur with T = [I; R'], :262-270) for the covariance modes of the oracle against a 40-digit restatement: VC, m = 4,
+    d = 3, two rows with the middle dimension missing.  Per basis l the missing block is completed by regression on the
+    observed one (R_l, X_hat_l, Psi_hat_l, :165-172); PHI_ti = e^{lnz_i} sum_j N(X_hat_tj; p_i, Sigma_i + Psi_hat_j) Pio_tj and the
+    pair sums use N(X_hat_tl; c_ij, C_ij + Psi_hat_l) (:186-206)."""
+    from gpz_b200 import synth
+    n, d, m = 50, 3, 4
+    X, Y = synth.make_data(n, d, seed=51)
+    X, Y = np.array(X), np.asarray(Y)
+    theta = synth.perturb_theta(synth.make_theta0(X, Y, "VC", m, het=True, seed=52), 0.2, 53)
+    model = O.Model(d=d, k=1, m=m, method="VC", heteroscedastic=True)
+    tr = np.ones(n, dtype=bool)
+    fit = O.GPz(theta, model, X, Y, None, None, tr, None, fit_only=True)
+    pri = O.getPrior(X, None, theta, model, tr)
+    model.muX, model.sdX, model.muY = np.zeros(d), np.ones(d), np.zeros(1)
+    md = m * d
+    o_ = md + model.g_dim
+    P = theta[:md].reshape((m, d), order="F")
+    vv = theta[o_ + m + 1:o_ + 2 * m + 1]
+    bb = theta[o_ + m]
+    model.best = dict(theta=theta, w=fit.w, iSigma_w=fit.iSigma_w, P=P, v=vv.reshape(m, 1), priors=pri)
+    Xt = X[:2].copy()
+    Xt[:, 1] = np.nan
+    Psi = synth.make_psi(2, d, "VC", seed=54) if psi else None
+    mu, sigma, nu, be, ga, PHI = O.predict(Xt, model, Psi=Psi)
+
+    mp.mp.dps = 40
+    f = lambda t: mp.mpf(float(t))                                                    # noqa: E731
+    M = lambda a: mp.matrix(np.asarray(a, dtype=np.float64).tolist())                 # noqa: E731
+    ob, un = [0, 2], [1]
+    sub = lambda A, r, c: mp.matrix([[A[i, j] for j in c] for i in r])               # noqa: E731
+    Gam = O.unpack_gamma(theta, model)
+    iS = [M(Gam[:, :, i]).T * M(Gam[:, :, i]) for i in range(m)]
+    S = [mp.inverse(a) for a in iS]
+    lnz = [-mp.log(mp.det(a)) / 2 for a in iS]
+    Pm = [M(P[i:i + 1, :]) for i in range(m)]
+    w = [f(t) for t in fit.w[:, 0]]
+    v = [f(t) for t in vv]
+    pr = [f(t) for t in np.asarray(pri).reshape(-1)]
+    iSw = fit.iSigma_w[:, :, 0]
+
+    def lnN(delta, C):
+        return -(delta * mp.inverse(C) * delta.T)[0] / 2 - mp.log(mp.det(C)) / 2
+
+    rel = lambda a, b: abs(float((f(a) - b) / b))                                     # noqa: E731
+    for t in range(2):
+        xo = mp.matrix([[f(Xt[t, a]) for a in ob]])
+        Ex, Xh, Ph = [], [], []
+        for i in range(m):
+            Soo = sub(S[i], ob, ob)
+            dl = xo - sub(Pm[i], [0], ob)
+            Poo = sub(M(Psi[:, :, t]), ob, ob) if psi else mp.zeros(len(ob), len(ob))
+            Ex.append(mp.exp(lnN(dl, Soo + Poo)) * pr[i])                             # :163-164 / :260
+            R = mp.inverse(Soo) * sub(S[i], ob, un)                                   # :166
+            ph = mp.zeros(d, d)
+            blk = sub(S[i], un, un) - sub(S[i], un, ob) * R                           # :168
+            if psi:                                                                   # T Psi_oo T', T = [I; R']  (:264-268)
+                order = ob + un
+                Tm = mp.zeros(d, len(ob))
+                for a_ in range(len(ob)):
+                    Tm[a_, a_] = 1
+                Rt = R.T
+                for a_ in range(len(un)):
+                    for b_ in range(len(ob)):
+                        Tm[len(ob) + a_, b_] = Rt[a_, b_]
+                TP = Tm * Poo * Tm.T
+                for a_, ia in enumerate(order):
+                    for b_, ib in enumerate(order):
+                        ph[ia, ib] = TP[a_, b_]
+            for a_, ia in enumerate(un):
+                for b_, ib in enumerate(un):
+                    ph[ia, ib] += blk[a_, b_]
+            xh = mp.zeros(1, d)
+            xu = dl * R + sub(Pm[i], [0], un)                                         # :170
+            for a_, ia in enumerate(un):
+                xh[0, ia] = xu[0, a_]
+            for a_, ia in enumerate(ob):
+                xh[0, ia] = xo[0, a_]
+            Ph.append(ph)
+            Xh.append(xh)
+        Pio = [e / sum(Ex) for e in Ex]
+        phi = [mp.exp(lnz[i]) * sum(mp.exp(lnN(Xh[j] - Pm[i], S[i] + Ph[j])) * Pio[j] for j in range(m)) for i in range(m)]
+        mu_x = sum(phi[i] * w[i] for i in range(m))
+        ElnS = sum(phi[i] * v[i] for i in range(m))
+        ga_x = nu_x = V_x = mp.mpf(0)
+        for i in range(m):
+            for j in range(i + 1):
+                iC = iS[i] + iS[j]
+                C = mp.inverse(iC)
+                c = (Pm[i] * iS[i] + Pm[j] * iS[j]) * C                               # :180-182
+                Ec = sum(mp.exp(lnN(Xh[l] - c, C + Ph[l])) * Pio[l] for l in range(m))                       # :196-201
+                Z = mp.exp(lnz[i] + lnz[j] + lnN(Pm[i] - Pm[j], S[i] + S[j])) * Ec                           # :203-204
+                fac = 2 if j < i else 1
+                ga_x += fac * Z * w[i] * w[j]
+                V_x += fac * Z * v[i] * v[j]
+                nu_x += fac * Z * f(iSw[i, j])
+        V_x -= ElnS ** 2
+        be_x = mp.exp(ElnS + f(bb)) * (1 + V_x / 2)
+        ga_x -= mu_x ** 2
+        for i in range(m):
+            assert rel(PHI[t, i], phi[i]) <= 1e-11
+        assert rel(mu[t, 0], mu_x) <= 1e-11 and rel(be[t, 0], be_x) <= 1e-10
+        assert rel(nu[t, 0], nu_x) <= 1e-8 and abs(float(f(ga[t, 0]) - ga_x)) <= 1e-11 * max(1.0, float(mu_x) ** 2)
