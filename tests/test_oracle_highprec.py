@@ -191,6 +191,57 @@ def test_oracle_objective_and_gradient_against_40_digit_differences(meth, psi, n
     assert err <= 1e-11, err
 
 
+def test_train_and_validation_statistics_against_40_digit_arithmetic():
+    """GPz.m:236-259: trainRMSE / trainLL on the training rows and validRMSE / validLL from a second getPHI on the validation
+    rows (weights omega, heteroscedastic beta), the four numbers callBack.m reads -- oracle against 40 digits (VD, no Psi)."""
+    from gpz_b200 import synth
+    n, d, m = 48, 2, 5
+    X, Y = synth.make_data(n, d, seed=61)
+    X, Y = np.asarray(X), np.asarray(Y)
+    theta = synth.perturb_theta(synth.make_theta0(X, Y, "VD", m, het=True, seed=62), 0.2, 63)
+    omega = 0.5 + np.random.default_rng(64).random((n, 1))
+    tr = np.arange(n) % 3 != 0
+    va = ~tr
+    model = O.Model(d=d, k=1, m=m, method="VD", heteroscedastic=True)
+    ref = O.GPz(theta, model, X, Y, None, omega, tr, va)
+    mp.mp.dps = 40
+    f = lambda t: mp.mpf(float(t))                                                    # noqa: E731
+    md = m * d
+    o_ = md + md
+    G = [[f(theta[md + j + a * m]) for a in range(d)] for j in range(m)]
+    Pm = [[f(theta[a * m + j]) for a in range(d)] for j in range(m)]
+    lnA = [f(t) for t in theta[o_:o_ + m]]
+    b = f(theta[o_ + m])
+    v = [f(t) for t in theta[o_ + m + 1:o_ + 2 * m + 1]]
+
+    def phi_row(i):
+        return [mp.exp(-sum(((f(X[i, a]) - Pm[j][a]) * G[j][a]) ** 2 for a in range(d)) / 2) for j in range(m)]
+
+    rows_t = [i for i in range(n) if tr[i]]
+    PHI = {i: phi_row(i) for i in range(n)}
+    beta = {i: mp.exp(-(b + sum(PHI[i][j] * v[j] for j in range(m)))) for i in range(n)}
+    S = mp.matrix(m, m)
+    r = mp.matrix(m, 1)
+    for a in range(m):
+        for c in range(m):
+            S[a, c] = sum(beta[i] * f(omega[i, 0]) * PHI[i][a] * PHI[i][c] for i in rows_t) + (mp.exp(lnA[a]) if a == c else 0)
+        r[a] = sum(beta[i] * f(omega[i, 0]) * PHI[i][a] * f(Y[i, 0]) for i in rows_t)
+    w = mp.lu_solve(S, r)
+
+    def stats(rows):
+        nr = len(rows)
+        delta = {i: sum(PHI[i][j] * w[j] for j in range(m)) - f(Y[i, 0]) for i in rows}
+        rmse = mp.sqrt(sum(f(omega[i, 0]) * delta[i] ** 2 for i in rows) / nr)
+        ll = sum(f(omega[i, 0]) * (-beta[i] * delta[i] ** 2 / 2 + mp.log(beta[i]) / 2) for i in rows) / nr - mp.log(2 * mp.pi) / 2
+        return rmse, ll
+
+    tr_rmse, tr_ll = stats(rows_t)
+    va_rmse, va_ll = stats([i for i in range(n) if va[i]])
+    rel = lambda a, x: abs(float((f(a) - x) / x))                                     # noqa: E731
+    assert rel(ref.stats["trainRMSE"], tr_rmse) <= 1e-12 and rel(ref.stats["trainLL"], tr_ll) <= 1e-12
+    assert rel(ref.stats["validRMSE"], va_rmse) <= 1e-12 and rel(ref.stats["validLL"], va_ll) <= 1e-12
+
+
 def test_predict_full_and_noisy_diag_against_40_digit_arithmetic():
     """predictFull (predictDiag.m:58-74) and predictNoisy for the diagonal modes (predictDiag.m:75-125) of the oracle against
     40-digit evaluations of the same expressions: VD, m = 8, d = 3, 4 rows, w / iSigma_w from the oracle's fit."""
