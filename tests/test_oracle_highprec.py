@@ -538,3 +538,64 @@ def test_predict_missing_cov_against_40_digit_arithmetic(psi):
             assert rel(PHI[t, i], phi[i]) <= 1e-11
         assert rel(mu[t, 0], mu_x) <= 1e-11 and rel(be[t, 0], be_x) <= 1e-10
         assert rel(nu[t, 0], nu_x) <= 1e-8 and abs(float(f(ga[t, 0]) - ga_x)) <= 1e-11 * max(1.0, float(mu_x) ** 2)
+
+
+def _mp_nlogml_multi(theta, X, Y, omega, m, d, k):
+    """GPz.m:20-110,233 for k outputs, VD, heteroscedastic, no Psi / NaN, in 40-digit arithmetic.  Keeps the reference's treatment of
+    the constant: -1/2 m k ln(2 pi) is added to EACH of the k per-output terms (GPz.m:103) before they are summed (:110)."""
+    n = X.shape[0]
+    md = m * d
+    P = [[theta[a * m + j] for a in range(d)] for j in range(m)]
+    Gam = [[theta[md + j + a * m] for a in range(d)] for j in range(m)]
+    o = 2 * md
+    lnA = [[theta[o + j + c * m] for j in range(m)] for c in range(k)]
+    b = [theta[o + m * k + c] for c in range(k)]
+    v = [[theta[o + m * k + k + j + c * m] for j in range(m)] for c in range(k)]
+    lnT = [[theta[o + m * k + k + m * k + j + c * m] for j in range(m)] for c in range(k)]
+    PHI = [[mp.exp(-sum(((mp.mpf(float(X[i, a])) - P[j][a]) * Gam[j][a]) ** 2 for a in range(d)) / 2) for j in range(m)] for i in range(n)]
+    total = mp.mpf(0)
+    for c in range(k):
+        lnBi = [b[c] + sum(PHI[i][j] * v[c][j] for j in range(m)) for i in range(n)]
+        wb = [mp.exp(-lnBi[i]) * mp.mpf(float(omega[i])) for i in range(n)]
+        alpha = [mp.exp(t) for t in lnA[c]]
+        S = mp.matrix(m, m)
+        r = mp.matrix(m, 1)
+        for a in range(m):
+            for e in range(m):
+                S[a, e] = sum(wb[i] * PHI[i][a] * PHI[i][e] for i in range(n)) + (alpha[a] if a == e else 0)
+            r[a] = sum(wb[i] * PHI[i][a] * mp.mpf(float(Y[i, c])) for i in range(n))
+        w = mp.lu_solve(S, r)
+        delta = [sum(PHI[i][j] * w[j] for j in range(m)) - mp.mpf(float(Y[i, c])) for i in range(n)]
+        nl = -sum(wb[i] * delta[i] ** 2 for i in range(n)) / 2 - sum(alpha[j] * w[j] ** 2 for j in range(m)) / 2 \
+            + sum(lnA[c]) / 2 - mp.log(mp.det(S)) / 2 - sum(lnBi[i] * mp.mpf(float(omega[i])) for i in range(n)) / 2
+        nl += -sum(v[c][j] ** 2 * mp.exp(lnT[c][j]) for j in range(m)) / 2 + sum(lnT[c]) / 2 - mp.mpf(m * k) * mp.log(2 * mp.pi) / 2
+        total += nl
+    total -= mp.log(2 * mp.pi) * sum(mp.mpf(float(t)) for t in omega) / 2
+    return -total / (n * k)
+
+
+def test_two_outputs_objective_and_gradient_against_40_digit_differences():
+    """k = 2: per-output Gram / solve / noise head, shared PHI and basis parameters, and the reference's constant
+    (GPz.m:103: counted k times) -- the oracle's nlogML and gradient against the 40-digit objective and its differences."""
+    from gpz_b200 import synth
+    n, d, m, k = 30, 2, 4, 2
+    X, Y = synth.make_data(n, d, seed=71, k=k)
+    X, Y = np.asarray(X), np.asarray(Y)
+    theta = synth.perturb_theta(synth.make_theta0(X, Y, "VD", m, het=True, seed=72), 0.2, 73)
+    omega = 0.5 + np.random.default_rng(74).random((n, 1))
+    model = O.Model(d=d, k=k, m=m, method="VD", heteroscedastic=True)
+    tr = np.ones(n, dtype=bool)
+    ref = O.GPz(theta, model, X, Y, None, omega, tr, None)
+    mp.mp.dps = 40
+    th = [mp.mpf(float(t)) for t in theta]
+    f0 = _mp_nlogml_multi(th, X, Y, omega[:, 0], m, d, k)
+    assert abs(float((mp.mpf(float(ref.nlogML)) - f0) / f0)) <= 1e-13
+    h = mp.mpf(10) ** -15
+    g = np.zeros(len(theta))
+    for q in range(len(theta)):
+        tp, tm = list(th), list(th)
+        tp[q] += h
+        tm[q] -= h
+        g[q] = float((_mp_nlogml_multi(tp, X, Y, omega[:, 0], m, d, k) - _mp_nlogml_multi(tm, X, Y, omega[:, 0], m, d, k)) / (2 * h))
+    err = np.max(np.abs(ref.grad - g)) / np.max(np.abs(g))
+    assert err <= 1e-11, err
