@@ -228,7 +228,10 @@ oz_slice_cols_kernel(const double* __restrict__ Sinv, int MP, int m, const doubl
 
 static int64_t al256(int64_t b) { return (b + 255) / 256 * 256; }
 
-constexpr int OZG_CH = 1024;      // rows per K chunk of the Gram: the digits of the ~4 chunks in flight (x all tiles) stay in L2
+#ifndef GPZ_OZG_CH
+#define GPZ_OZG_CH 1024
+#endif
+constexpr int OZG_CH = GPZ_OZG_CH;      // rows per K chunk of the Gram: the digits of the ~4 chunks in flight (x all tiles) stay in L2
 
 int64_t oz_padded_rows(int64_t rows) { return round_up(rows > 0 ? rows : 1, OZG_CH); }
 
