@@ -599,3 +599,27 @@ def test_two_outputs_objective_and_gradient_against_40_digit_differences():
         g[q] = float((_mp_nlogml_multi(tp, X, Y, omega[:, 0], m, d, k) - _mp_nlogml_multi(tm, X, Y, omega[:, 0], m, d, k)) / (2 * h))
     err = np.max(np.abs(ref.grad - g)) / np.max(np.abs(g))
     assert err <= 1e-11, err
+
+
+def test_inv_logdet_against_40_digit_svd():
+    """inv_logdet.m:3-15: SVD pseudo-inverse with tol = max(size) * eps(largest singular value) and log det over the retained
+    singular values -- the oracle against a 40-digit SVD, for a well-conditioned SPD matrix and a rank-3 one of size 6."""
+    rng = np.random.default_rng(81)
+    mp.mp.dps = 40
+    for rank in (6, 3):
+        B = rng.standard_normal((6, rank))
+        A = B @ B.T + (np.eye(6) if rank == 6 else 0.0)
+        Xi, ld = O.inv_logdet(A)
+        U, s, V = mp.svd_r(mp.matrix(A.tolist()))
+        smax = max(s[i] for i in range(6))
+        tol = 6 * float(np.spacing(float(smax)))
+        keep = [i for i in range(6) if s[i] > tol]
+        assert len(keep) == rank
+        Xi_x = mp.zeros(6, 6)
+        for i in keep:
+            Xi_x += (V[i, :].T * U[:, i].T) / s[i]                                    # V(:,i) U(:,i)' / s_i
+        ld_x = sum(mp.log(s[i]) for i in keep)
+        err = max(abs(float(mp.mpf(float(Xi[a, b])) - Xi_x[a, b])) for a in range(6) for b in range(6))
+        scale = max(abs(float(Xi_x[a, b])) for a in range(6) for b in range(6))
+        assert err <= 1e-12 * scale * (1 if rank == 6 else float(smax / min(s[i] for i in keep)))
+        assert abs(ld - float(ld_x)) <= 1e-12 * max(1.0, abs(float(ld_x)))
