@@ -2463,6 +2463,14 @@ int gpz_set_option(gpz_ctx* c, const char* name, double value) {
         g_solve_lookahead = value >= 2.0 ? 2 : (value != 0.0 ? 1 : 0);
         return GPZ_OK;
     }
+    if (strcmp(name, "moment_warps") == 0) {        // process-wide: warps per CTA of the moment GEMM dPHI'F (gemm.cu): 0 = by shape (default), 8 or 16
+        if (value != 0.0 && value != 8.0 && value != 16.0) {
+            set_error("moment_warps must be 0 (by shape), 8 or 16");
+            return GPZ_ERR_USAGE;
+        }
+        g_moment_warps = static_cast<int>(value);
+        return GPZ_OK;
+    }
     if (strcmp(name, "prep_block") == 0) {          // process-wide: CTA size of the per-basis parameter kernels (phi.cu), 32 = default
         if (value != 32.0 && value != 64.0 && value != 128.0) {
             set_error("prep_block must be 32, 64 or 128");

@@ -18,6 +18,7 @@ namespace gpz {
 
 constexpr int STAGES = 4;
 int g_phi_persist = 2;     // PHI = exp(F W) through the persistent column-stationary kernel where it applies ("phi_persist" option): 2 staggered M-groups (default), 1 CTA-synchronous, 0 off
+int g_moment_warps = 0;     // warps per CTA of the back-projection moment GEMM ("moment_warps" option: 0 = by shape, 8 or 16)
 int g_gemm_warps = 0;       // 0 = defaults (Gram / T-GEMM 8 warps, PHI build 16 warps: its exp epilogue likes more warps);
                             // 8 / 16 force all three (gpz_set_option "gemm_warps").  8 vs 16 differ by <4 % either way across boxes.
 
@@ -929,8 +930,10 @@ int gemm_rows(const double* A, int64_t lda, int K, const double* B, int N, int64
 // ------------------------------------------------------------------------------------------------
 constexpr int DSTAGES = 3;
 
-template <int NT>
-__global__ void __launch_bounds__(256, 1)
+// WARPS = 8: 16 rows per stage, each warp 16 bases x TN; WARPS = 16: 32 rows per stage, each warp 8 bases x TN -- half as many CTA
+// barriers per row and four warps per sub-partition instead of two ("moment_warps" option).
+template <int NT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
 atb_dphi_kernel(const double* __restrict__ Phi, const double* __restrict__ H, int64_t ld, const double* __restrict__ F,
                 int64_t ldf, const double* __restrict__ cw, const double* __restrict__ dbeta,
                 const double* __restrict__ w, const double* __restrict__ v, int64_t row0, int64_t row1,
@@ -938,23 +941,23 @@ atb_dphi_kernel(const double* __restrict__ Phi, const double* __restrict__ H, in
                 int col_accumulate) {
     constexpr int TN = 8 * NT;
     constexpr int LDB = TN + 4;
-    constexpr int MT = 2;                    // 8 warps x 16 bases
+    constexpr int THREADS = WARPS * 32, KS = (THREADS / 64) * 4, MT = 16 / WARPS;      // rows per stage; 8-base blocks per warp
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* As = reinterpret_cast<double*>(smem_raw);           // [DSTAGES][KSTEP][LDT]
-    double* Bs = As + DSTAGES * KSTEP * LDT;                    // [DSTAGES][KSTEP][LDB]
-    __shared__ double csum[4][4][64];                           // [row group][q0,q1,v0,v1][column pair]
+    double* As = reinterpret_cast<double*>(smem_raw);           // [DSTAGES][KS][LDT]
+    double* Bs = As + DSTAGES * KS * LDT;                       // [DSTAGES][KS][LDB]
+    __shared__ double csum[THREADS / 64][4][64];                // [row group][q0,q1,v0,v1][column pair]
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int wm0 = warp * 16;
+    const int wm0 = warp * (8 * MT);
     const int jt = blockIdx.x;
     const int64_t a_col0 = static_cast<int64_t>(jt) * TILE;
     const int64_t rbeg = row0 + static_cast<int64_t>(blockIdx.y) * rows_per_split;
     int64_t rend = rbeg + rows_per_split;
     if (rend > row1) rend = row1;
     const int64_t nrows = rend > rbeg ? rend - rbeg : 0;
-    const int nk = static_cast<int>((nrows + KSTEP - 1) / KSTEP);
+    const int nk = static_cast<int>((nrows + KS - 1) / KS);
 
     // this thread's fixed column pair and row group in the A tile
     const int cc = tid & 63, rg = tid >> 6;
@@ -965,10 +968,10 @@ atb_dphi_kernel(const double* __restrict__ Phi, const double* __restrict__ H, in
     double2 rp[4], rh[4];
     double rc_[4], rd_[4];
     auto load_a_regs = [&](int kt) {
-        const int64_t rb = rbeg + static_cast<int64_t>(kt) * KSTEP;
+        const int64_t rb = rbeg + static_cast<int64_t>(kt) * KS;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int64_t gr = rb + rg + 4 * q;
+            const int64_t gr = rb + rg + (THREADS / 64) * q;
             if (gr < rend) {
                 rp[q] = *reinterpret_cast<const double2*>(Phi + gr * ld + a_col0 + cc * 2);
                 rh[q] = *reinterpret_cast<const double2*>(H + gr * ld + a_col0 + cc * 2);
@@ -981,12 +984,12 @@ atb_dphi_kernel(const double* __restrict__ Phi, const double* __restrict__ H, in
         }
     };
     auto store_a_smem = [&](int stage) {
-        double* as = As + stage * KSTEP * LDT;
+        double* as = As + stage * KS * LDT;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const double c0 = fma(rc_[q], wj.x, rd_[q] * vj.x), c1 = fma(rc_[q], wj.y, rd_[q] * vj.y);
             const double2 dphi = make_double2(fma(rp[q].x, c0, -rh[q].x), fma(rp[q].y, c1, -rh[q].y));
-            *reinterpret_cast<double2*>(as + (rg + 4 * q) * LDT + cc * 2) = dphi;
+            *reinterpret_cast<double2*>(as + (rg + (THREADS / 64) * q) * LDT + cc * 2) = dphi;
             sq0 = fma(rp[q].x, -rc_[q], sq0);
             sq1 = fma(rp[q].y, -rc_[q], sq1);
             sv0 = fma(rp[q].x, rd_[q], sv0);
@@ -994,12 +997,12 @@ atb_dphi_kernel(const double* __restrict__ Phi, const double* __restrict__ H, in
         }
     };
     auto load_b = [&](int kt, int stage) {
-        const int64_t rb = rbeg + static_cast<int64_t>(kt) * KSTEP;
-        double* bs = Bs + stage * KSTEP * LDB;
-        constexpr int BCH = KSTEP * TN / 2;
+        const int64_t rb = rbeg + static_cast<int64_t>(kt) * KS;
+        double* bs = Bs + stage * KS * LDB;
+        constexpr int BCH = KS * TN / 2;
 #pragma unroll
-        for (int q = 0; q < (BCH + 255) / 256; ++q) {
-            const int c = tid + q * 256;
+        for (int q = 0; q < (BCH + THREADS - 1) / THREADS; ++q) {
+            const int c = tid + q * THREADS;
             if (c < BCH) {
                 const int r = c / (TN / 2), c2 = c % (TN / 2);
                 const int64_t gr = rb + r;
@@ -1035,10 +1038,10 @@ atb_dphi_kernel(const double* __restrict__ Phi, const double* __restrict__ H, in
         }
         cp_async_commit();
         const int stage = kt % DSTAGES;
-        const double* as = As + stage * KSTEP * LDT;
-        const double* bs = Bs + stage * KSTEP * LDB;
+        const double* as = As + stage * KS * LDT;
+        const double* bs = Bs + stage * KS * LDB;
 #pragma unroll
-        for (int kk = 0; kk < KSTEP / 4; ++kk) {
+        for (int kk = 0; kk < KS / 4; ++kk) {
             const int kr = kk * 4 + t;
             double bf[NT];
 #pragma unroll
@@ -1079,31 +1082,47 @@ atb_dphi_kernel(const double* __restrict__ Phi, const double* __restrict__ H, in
     __syncthreads();
     if (tid < 128) {
         const int c2 = tid >> 1, e = tid & 1;
-        const double q = csum[0][e][c2] + csum[1][e][c2] + csum[2][e][c2] + csum[3][e][c2];
-        const double dv = csum[0][2 + e][c2] + csum[1][2 + e][c2] + csum[2][2 + e][c2] + csum[3][2 + e][c2];
+        double q = csum[0][e][c2] + csum[1][e][c2] + csum[2][e][c2] + csum[3][e][c2];
+        double dv = csum[0][2 + e][c2] + csum[1][2 + e][c2] + csum[2][2 + e][c2] + csum[3][2 + e][c2];
+        if (THREADS / 64 == 8) {
+            q += csum[4][e][c2] + csum[5][e][c2] + csum[6][e][c2] + csum[7][e][c2];
+            dv += csum[4][2 + e][c2] + csum[5][2 + e][c2] + csum[6][2 + e][c2] + csum[7][2 + e][c2];
+        }
         double* cp = colp + static_cast<int64_t>(blockIdx.y) * 2 * MP + a_col0 + tid;
         cp[0] = (col_accumulate ? cp[0] : 0.0) + q;
         cp[MP] = (col_accumulate ? cp[MP] : 0.0) + dv;
     }
 }
 
+template <int NT, int WARPS>
+static int launch_atb_dphi_w(const double* Phi, const double* H, int64_t ld, const double* F, int64_t ldf, const double* cw,
+                           const double* dbeta, const double* w, const double* v, int64_t row0, int64_t row1, int nsplit,
+                           double* partial, double* colp, int MP, int accumulate, int col_accumulate, cudaStream_t st) {
+    constexpr int TN = 8 * NT, KS = (WARPS / 2) * 4;
+    const size_t smem = sizeof(double) * (DSTAGES * KS * LDT + DSTAGES * KS * (TN + 4));
+    static PerDeviceOnce once;
+    if (once.need()) {
+        GPZ_CUDA(cudaFuncSetAttribute(atb_dphi_kernel<NT, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    }
+    int64_t rps = ceil_div(row1 - row0, nsplit);
+    rps = round_up(rps > 0 ? rps : 1, KS);
+    dim3 grid(MP / TILE, nsplit);
+    atb_dphi_kernel<NT, WARPS><<<grid, WARPS * 32, smem, st>>>(Phi, H, ld, F, ldf, cw, dbeta, w, v, row0, row1, rps, partial, colp, MP,
+                                                             accumulate, col_accumulate);
+    GPZ_KERNEL_CHECK();
+    return GPZ_OK;
+}
+
 template <int NT>
 static int launch_atb_dphi(const double* Phi, const double* H, int64_t ld, const double* F, int64_t ldf, const double* cw,
                            const double* dbeta, const double* w, const double* v, int64_t row0, int64_t row1, int nsplit,
                            double* partial, double* colp, int MP, int accumulate, int col_accumulate, cudaStream_t st) {
-    constexpr int TN = 8 * NT;
-    const size_t smem = sizeof(double) * (DSTAGES * KSTEP * LDT + DSTAGES * KSTEP * (TN + 4));
-    static PerDeviceOnce once;
-    if (once.need()) {
-        GPZ_CUDA(cudaFuncSetAttribute(atb_dphi_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    }
-    int64_t rps = ceil_div(row1 - row0, nsplit);
-    rps = round_up(rps > 0 ? rps : 1, KSTEP);
-    dim3 grid(MP / TILE, nsplit);
-    atb_dphi_kernel<NT><<<grid, 256, smem, st>>>(Phi, H, ld, F, ldf, cw, dbeta, w, v, row0, row1, rps, partial, colp, MP, accumulate,
-                                                 col_accumulate);
-    GPZ_KERNEL_CHECK();
-    return GPZ_OK;
+    // 16 warps pay for narrow feature tiles on many rows (config 3, VD: NT = 3, 1.87 -> 1.54 ms) and cost 35 % at NT = 9, where each
+    // warp's B fragment loads are no longer shared by two row blocks (profiles/r02zf_moment_warps.log)
+    const bool wide = g_moment_warps == 16 || (g_moment_warps == 0 && NT <= 4 && row1 - row0 >= 200000);
+    if (wide)
+        return launch_atb_dphi_w<NT, 16>(Phi, H, ld, F, ldf, cw, dbeta, w, v, row0, row1, nsplit, partial, colp, MP, accumulate, col_accumulate, st);
+    return launch_atb_dphi_w<NT, 8>(Phi, H, ld, F, ldf, cw, dbeta, w, v, row0, row1, nsplit, partial, colp, MP, accumulate, col_accumulate, st);
 }
 
 // F rows have stride QP (multiple of 32, <= 128); only the first q feature columns are multiplied, rounded up to the

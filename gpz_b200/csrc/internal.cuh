@@ -104,6 +104,7 @@ int transpose_out(const double* src_rowmajor, int64_t ld, int64_t n, int m, doub
 extern int g_gemm_warps;
 extern int g_phi_persist;
 extern int g_prep_block;
+extern int g_moment_warps;
 int gram_nsplit(int MP, int sm_count);
 int gram_syrk_main(const double* Phi, int64_t ld, int MP, const double* wgt, int64_t row0, int64_t row1, int nsplit,
                    double* partial, int accumulate, cudaStream_t st, int64_t* launches);

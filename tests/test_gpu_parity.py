@@ -208,6 +208,27 @@ def test_predict_matches_oracle(method, psi):
     assert rel(PHI2, PHI) <= 1e-12
 
 
+@pytest.mark.parametrize("method", ["VD", "VC", "GL"])
+def test_moment_gemm_warp_variants_match_the_oracle(method):
+    """The back-projection moment GEMM dPHI'F (gemm.cu: atb_dphi_kernel) has an 8-warp / 16-row-stage and a 16-warp / 32-row-stage
+    form, chosen by shape; both are forced here (`moment_warps`) on a problem with a ragged last stage and compared with the oracle."""
+    n, d, m = 3001, 3, 150
+    model, theta, X, Y, _, omega, tr, va = problem(method, True, False, False, n=n, d=d, m=m, seed=41)
+    ref = O.GPz(theta, model, X, Y, None, omega, tr, va)
+    gm = L.make_model(d, 1, m, method, True)
+    ctx = L.Context(gm, X, Y, None, omega, tr, va)
+    try:
+        for warps in (8, 16):
+            ctx.set_option("moment_warps", warps)
+            f, g, st = ctx.eval(theta)
+            f2, g2, _ = ctx.eval(theta)
+            assert f == f2 and np.array_equal(g, g2)
+            assert rel(f, ref.nlogML) <= 1e-10 and rel(g, ref.grad) <= 2e-9, (warps, rel(f, ref.nlogML), rel(g, ref.grad))
+    finally:
+        ctx.set_option("moment_warps", 0)
+        ctx.close()
+
+
 @pytest.mark.parametrize("m", [200, 300, 470])
 def test_solve_schedules_agree_with_the_oracle(m):
     """csrc/solve.cu has three schedules of the same blocked Cholesky + inverse (`solve_lookahead` 0: in-stream, 1: look-ahead
