@@ -477,7 +477,7 @@ tgemm_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
-// PHI = exp(F W), persistent form for short K (the monomial features of d <= 10: K <= 72).
+// PHI = exp(F W), persistent form for short K (the monomial features of d <= 10: K <= 68 after rounding to the DMMA k step).
 // The kernel above gives every 128 x 128 tile its own CTA: operand loads start cold for each tile and its exp/store epilogue
 // overlaps nothing (one CTA per SM), so the fp64 pipe idles 35-40 % of the time (profiles/r01h, r02e: DMMA 52-57 % + FP64
 // 11-12 % active).  Here a CTA keeps ONE column tile of W in shared memory for its whole life and walks down the row tiles
